@@ -1,0 +1,137 @@
+// Shared declarations for libbsnative (sm_100a).  Internal header, not part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace bs {
+
+// ---- error plumbing (thread-local message, C ABI returns negative codes) ----
+void set_error(const std::string &msg);
+#define BS_OK 0
+#define BS_ERR_CUDA (-1)
+#define BS_ERR_ARG (-2)
+#define BS_ERR_OVERFLOW (-3)
+#define BS_ERR_STATE (-4)
+
+#define BS_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            char _b[512];                                                                     \
+            snprintf(_b, sizeof(_b), "%s:%d: %s -> %s", __FILE__, __LINE__, #call,            \
+                     cudaGetErrorString(_e));                                                 \
+            bs::set_error(_b);                                                                \
+            return BS_ERR_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+#define BS_TRY(call)                 \
+    do {                             \
+        int _r = (call);             \
+        if (_r != BS_OK) return _r;  \
+    } while (0)
+
+#define BS_ARG(cond, msg)            \
+    do {                             \
+        if (!(cond)) {               \
+            bs::set_error(msg);      \
+            return BS_ERR_ARG;       \
+        }                            \
+    } while (0)
+
+// launch counter (bench.py reports gpu_launches from it)
+extern unsigned long long g_launches;
+#define BS_LAUNCH(kernel, grid, block, smem, stream, ...)          \
+    do {                                                           \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); \
+        bs::g_launches++;                                          \
+    } while (0)
+
+// ---- stream-ordered scratch buffer ----
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaStream_t s = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    int alloc(size_t n, cudaStream_t stream) {
+        release();
+        s = stream;
+        bytes = n;
+        if (n == 0) n = 16;
+        BS_CUDA(cudaMallocAsync(&p, n, stream));
+        return BS_OK;
+    }
+    int alloc_zero(size_t n, cudaStream_t stream) {
+        BS_TRY(alloc(n, stream));
+        BS_CUDA(cudaMemsetAsync(p, 0, n ? n : 16, stream));
+        return BS_OK;
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T>
+    T *as() const {
+        return (T *)p;
+    }
+};
+
+static inline unsigned int cdiv(size_t a, size_t b) { return (unsigned int)((a + b - 1) / b); }
+
+// ---- primitives (prims.cu) ----
+// out[i] = sum_{j<i} in[j]; total (device pointer, may be null) = sum of all.  in/out may alias.
+int scan_exclusive_u32(const uint32_t *in, uint32_t *out, size_t n, uint32_t *total_dev, cudaStream_t s);
+int scan_exclusive_u8(const uint8_t *in, uint32_t *out, size_t n, uint32_t *total_dev, cudaStream_t s);
+// stable LSD radix sort of (key u64, value u32) pairs on bits [bit_lo, bit_hi); result ends in keys/vals
+// (tmp buffers of the same size are used for ping-pong).
+int radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, size_t n,
+                     int bit_lo, int bit_hi, cudaStream_t s);
+
+// ---- device helpers ----
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// lock-free union-find on int parents; the root of a set is its minimum index
+__device__ __forceinline__ int uf_find(const int *parent, int x) {
+    int p = parent[x];
+    while (p != x) {
+        x = p;
+        p = parent[x];
+    }
+    return x;
+}
+__device__ __forceinline__ int uf_find_v(volatile int *parent, int x) {
+    int p = parent[x];
+    while (p != x) {
+        x = p;
+        p = parent[x];
+    }
+    return x;
+}
+__device__ __forceinline__ void uf_union(int *parent, int a, int b) {
+    for (;;) {
+        a = uf_find_v(parent, a);
+        b = uf_find_v(parent, b);
+        if (a == b) return;
+        if (a < b) {
+            int t = a;
+            a = b;
+            b = t;
+        }
+        // a > b: hang a under b if a is still a root
+        int old = atomicMin(&parent[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+}  // namespace bs
