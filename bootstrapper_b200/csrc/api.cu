@@ -1,0 +1,251 @@
+// extern "C" surface of libbsnative (include/bsnative.h).  No torch types, no CPU fallback.
+#include <string.h>
+
+#include <algorithm>
+
+#include "geom.h"
+
+namespace bs {
+int g_debug = 0;
+int stage1_run(Plan &P, const void *affs, const uint8_t *mask, uint64_t *frags_out, cudaStream_t s);
+int stage2_run(Plan &P, const void *affs, const uint64_t *frags, cudaStream_t s);
+int connected_components(const uint64_t *nodes, int64_t n, const uint64_t *eu, const uint64_t *ev, const float *scores,
+                         int64_t m, float thr, uint64_t *comp, cudaStream_t s);
+int relabel(const uint64_t *frags, int64_t n, const uint64_t *keys, const uint64_t *vals, int64_t k, uint64_t *seg,
+            cudaStream_t s);
+int synth_affs(void *out, int dtype, const int32_t *shape, const int32_t *offset, uint64_t seed, cudaStream_t s);
+}  // namespace bs
+
+using namespace bs;
+
+struct bs_plan {
+    Plan *p;
+};
+
+static int copy_out(void *dst, const void *src, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return BS_OK;
+    BS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
+    BS_CUDA(cudaStreamSynchronize(s));
+    return BS_OK;
+}
+
+extern "C" {
+
+const char *bs_last_error(void) { return get_error(); }
+unsigned long long bs_launch_count(void) { return g_launches; }
+int bs_version(void) { return 100; }
+int bs_set_debug(int on) {
+    g_debug = on;
+    return BS_OK;
+}
+
+int bs_plan_create(const bs_ws_config *cfg, bs_plan **out) {
+    BS_ARG(cfg && out, "bs_plan_create: null argument");
+    for (int d = 0; d < 3; d++)
+        BS_ARG(cfg->context[d] <= cfg->block_size[d], "bs_plan_create: context larger than the block is not supported");
+    Plan *p = nullptr;
+    BS_TRY(plan_build(*cfg, &p));
+    bs_plan *h = new bs_plan();
+    h->p = p;
+    *out = h;
+    return BS_OK;
+}
+
+void bs_plan_destroy(bs_plan *p) {
+    if (!p) return;
+    delete p->p;
+    delete p;
+}
+
+int bs_plan_num_blocks(const bs_plan *p, int64_t *n_total, int64_t *n_owned) {
+    BS_ARG(p, "null plan");
+    if (n_total) *n_total = (int64_t)p->p->blocks.size();
+    if (n_owned) *n_owned = (int64_t)p->p->owned.size();
+    return BS_OK;
+}
+
+int bs_plan_block_info(const bs_plan *p, int64_t *block_id, int32_t *write_offset, int32_t *write_shape) {
+    BS_ARG(p, "null plan");
+    const auto &bl = p->p->blocks;
+    for (size_t i = 0; i < bl.size(); i++) {
+        if (block_id) block_id[i] = bl[i].block_id;
+        for (int d = 0; d < 3; d++) {
+            if (write_offset) write_offset[3 * i + d] = bl[i].wo[d];
+            if (write_shape) write_shape[3 * i + d] = bl[i].ws[d];
+        }
+    }
+    return BS_OK;
+}
+
+int bs_stage1_fragments(bs_plan *p, const void *affs, const uint8_t *mask, uint64_t *frags_out, void *stream) {
+    BS_ARG(p && affs && frags_out, "bs_stage1_fragments: null argument");
+    return stage1_run(*p->p, affs, mask, frags_out, (cudaStream_t)stream);
+}
+
+int bs_stage1_num_nodes(const bs_plan *p, int64_t *n) {
+    BS_ARG(p && n, "null argument");
+    *n = p->p->n_nodes;
+    return BS_OK;
+}
+
+int bs_stage1_get_nodes(const bs_plan *p, uint64_t *ids, int32_t *pos_zyx, uint32_t *sizes, void *stream) {
+    BS_ARG(p, "null plan");
+    cudaStream_t s = (cudaStream_t)stream;
+    size_t n = (size_t)p->p->n_nodes;
+    if (ids) BS_TRY(copy_out(ids, p->p->node_id.p, 8 * n, s));
+    if (pos_zyx) BS_TRY(copy_out(pos_zyx, p->p->node_pos.p, 12 * n, s));
+    if (sizes) BS_TRY(copy_out(sizes, p->p->node_size.p, 4 * n, s));
+    return BS_OK;
+}
+
+int bs_stage1_block_counts(const bs_plan *p, int64_t *counts) {
+    BS_ARG(p && counts, "null argument");
+    for (size_t i = 0; i < p->p->blocks.size(); i++) counts[i] = p->p->blocks[i].owned ? p->p->block_count[i] : 0;
+    return BS_OK;
+}
+
+int bs_stage1_set_block_counts(bs_plan *p, const int64_t *counts) {
+    BS_ARG(p && counts, "null argument");
+    Plan &P = *p->p;
+    for (size_t i = 0; i < P.blocks.size(); i++) {
+        if (P.blocks[i].owned && P.block_count[i] != counts[i]) {
+            set_error("bs_stage1_set_block_counts: counts of owned blocks differ from this rank's stage-1 result");
+            return BS_ERR_STATE;
+        }
+        P.block_count[i] = counts[i];
+    }
+    P.block_nbase[0] = 0;
+    for (size_t b = 0; b < P.blocks.size(); b++) P.block_nbase[b + 1] = P.block_nbase[b] + P.block_count[b];
+    P.node_first = P.owned.empty() ? 0 : P.block_nbase[P.owned[0]];
+    P.counts_global = true;
+    return BS_OK;
+}
+
+int bs_stage2_agglomerate(bs_plan *p, const void *affs, const uint64_t *frags, void *stream) {
+    BS_ARG(p && affs && frags, "bs_stage2_agglomerate: null argument");
+    Plan &P = *p->p;
+    if (P.owned.size() != P.blocks.size() && !P.counts_global) {
+        set_error("bs_stage2_agglomerate: multi-rank plan needs bs_stage1_set_block_counts first");
+        return BS_ERR_STATE;
+    }
+    return stage2_run(P, affs, frags, (cudaStream_t)stream);
+}
+
+int bs_stage2_num_edges(const bs_plan *p, int64_t *n) {
+    BS_ARG(p && n, "null argument");
+    *n = p->p->n_edges;
+    return BS_OK;
+}
+
+int bs_stage2_get_edges(const bs_plan *p, uint64_t *u, uint64_t *v, float *score, void *stream) {
+    BS_ARG(p, "null plan");
+    cudaStream_t s = (cudaStream_t)stream;
+    size_t n = (size_t)p->p->n_edges;
+    if (u) BS_TRY(copy_out(u, p->p->edge_u.p, 8 * n, s));
+    if (v) BS_TRY(copy_out(v, p->p->edge_v.p, 8 * n, s));
+    if (score) BS_TRY(copy_out(score, p->p->edge_score.p, 4 * n, s));
+    return BS_OK;
+}
+
+int bs_connected_components(const uint64_t *nodes, int64_t n, const uint64_t *edges_u, const uint64_t *edges_v,
+                            const float *scores, int64_t m, float threshold, uint64_t *components_out, void *stream) {
+    BS_ARG(n == 0 || (nodes && components_out), "bs_connected_components: null argument");
+    BS_ARG(m == 0 || (edges_u && edges_v), "bs_connected_components: null edges");
+    return connected_components(nodes, n, edges_u, edges_v, scores, m, threshold, components_out, (cudaStream_t)stream);
+}
+
+int bs_relabel(const uint64_t *frags, int64_t n_vox, const uint64_t *lut_keys, const uint64_t *lut_vals, int64_t n_lut,
+               uint64_t *seg_out, void *stream) {
+    BS_ARG(n_vox == 0 || (frags && seg_out), "bs_relabel: null argument");
+    BS_ARG(n_lut == 0 || (lut_keys && lut_vals), "bs_relabel: null lut");
+    return relabel(frags, n_vox, lut_keys, lut_vals, n_lut, seg_out, (cudaStream_t)stream);
+}
+
+int bs_watershed_from_affinities(const void *affs, int aff_dtype, int Z, int Y, int X, int fragments_in_xy,
+                                 int min_seed_distance, uint64_t *frags_out, uint64_t *seeds_out, int64_t *n_out,
+                                 void *stream) {
+    BS_ARG(affs && frags_out, "bs_watershed_from_affinities: null argument");
+    BS_ARG(seeds_out == nullptr, "bs_watershed_from_affinities: return_seeds is not implemented");
+    bs_ws_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.vol_shape[0] = cfg.roi_shape[0] = cfg.block_size[0] = Z;
+    cfg.vol_shape[1] = cfg.roi_shape[1] = cfg.block_size[1] = Y;
+    cfg.vol_shape[2] = cfg.roi_shape[2] = cfg.block_size[2] = X;
+    cfg.aff_dtype = aff_dtype;
+    cfg.n_channels = 3;
+    cfg.fragments_in_xy = fragments_in_xy;
+    cfg.min_seed_distance = min_seed_distance;
+    cfg.remove_debris = 0;
+    cfg.filter_fragments = 0.0;
+    cfg.queue_bins = 256;
+    cfg.keep_cheaper = 1;
+    cfg.crop_relabel = 1;
+    cfg.block_begin = cfg.block_end = -1;
+    Plan *p = nullptr;
+    BS_TRY(plan_build(cfg, &p));
+    int rc = stage1_run(*p, affs, nullptr, frags_out, (cudaStream_t)stream);
+    if (rc == BS_OK && n_out) *n_out = p->n_nodes;
+    cudaStreamSynchronize((cudaStream_t)stream);
+    delete p;
+    return rc;
+}
+
+int bs_synth_affs(void *out, int aff_dtype, const int32_t *shape, const int32_t *offset, const int32_t *vol_shape,
+                  uint64_t seed, void *stream) {
+    BS_ARG(out && shape && offset, "bs_synth_affs: null argument");
+    (void)vol_shape;
+    return synth_affs(out, aff_dtype, shape, offset, seed, (cudaStream_t)stream);
+}
+
+int bs_debug_fetch(const bs_plan *p, const char *name, void *dst_host, int64_t *n_out) {
+    BS_ARG(p && name, "null argument");
+    auto it = p->p->dbg.find(name);
+    if (it == p->p->dbg.end()) {
+        set_error(std::string("bs_debug_fetch: no such array: ") + name);
+        return BS_ERR_STATE;
+    }
+    auto meta = p->p->dbg_meta[name];
+    if (n_out) *n_out = meta.second;
+    if (dst_host) {
+        BS_CUDA(cudaDeviceSynchronize());
+        BS_CUDA(cudaMemcpy(dst_host, it->second->p, (size_t)meta.first * meta.second, cudaMemcpyDeviceToHost));
+    }
+    return BS_OK;
+}
+
+/* test hooks for the device primitives (prims.cu) */
+int bs_dbg_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *total_dev, void *stream) {
+    return scan_exclusive_u32(in, out, (size_t)n, total_dev, (cudaStream_t)stream);
+}
+int bs_dbg_scan_u8(const uint8_t *in, uint32_t *out, int64_t n, uint32_t *total_dev, void *stream) {
+    return scan_exclusive_u8(in, out, (size_t)n, total_dev, (cudaStream_t)stream);
+}
+int bs_dbg_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, int64_t n, int bit_lo,
+                      int bit_hi, void *stream) {
+    return radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, (size_t)n, bit_lo, bit_hi, (cudaStream_t)stream);
+}
+
+int bs_set_profiling(int on) {
+    g_prof.on = on != 0;
+    return BS_OK;
+}
+
+int bs_get_profile(char *names_out, int names_cap, float *ms_out, int cap, int *n_out) {
+    int n = 0;
+    std::string names;
+    for (auto &r : g_prof.result) {
+        if (n >= cap) break;
+        if (ms_out) ms_out[n] = r.second;
+        names += r.first;
+        names += ";";
+        n++;
+    }
+    if (names_out && names_cap > 0) {
+        strncpy(names_out, names.c_str(), names_cap - 1);
+        names_out[names_cap - 1] = 0;
+    }
+    if (n_out) *n_out = n;
+    return BS_OK;
+}
+
+}  // extern "C"

@@ -3,17 +3,23 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+
 #include <string>
+#include <utility>
+#include <vector>
 
 namespace bs {
 
 // ---- error plumbing (thread-local message, C ABI returns negative codes) ----
 void set_error(const std::string &msg);
+const char *get_error();
+#ifndef BS_OK
 #define BS_OK 0
 #define BS_ERR_CUDA (-1)
 #define BS_ERR_ARG (-2)
 #define BS_ERR_OVERFLOW (-3)
 #define BS_ERR_STATE (-4)
+#endif
 
 #define BS_CUDA(call)                                                                         \
     do {                                                                                      \
@@ -71,10 +77,20 @@ struct DevBuf {
         BS_CUDA(cudaMemsetAsync(p, 0, n ? n : 16, stream));
         return BS_OK;
     }
+    int alloc_fill(size_t n, int byte, cudaStream_t stream) {
+        BS_TRY(alloc(n, stream));
+        BS_CUDA(cudaMemsetAsync(p, byte, n ? n : 16, stream));
+        return BS_OK;
+    }
     void release() {
         if (p) cudaFreeAsync(p, s);
         p = nullptr;
         bytes = 0;
+    }
+    void swap(DevBuf &o) {
+        std::swap(p, o.p);
+        std::swap(bytes, o.bytes);
+        std::swap(s, o.s);
     }
     template <typename T>
     T *as() const {
@@ -83,6 +99,21 @@ struct DevBuf {
 };
 
 static inline unsigned int cdiv(size_t a, size_t b) { return (unsigned int)((a + b - 1) / b); }
+
+// ---- per-phase device timing (CUDA events on the caller's stream), off by default ----
+struct Profiler {
+    bool on = false;
+    struct Ev {
+        std::string name;
+        cudaEvent_t ev;
+    };
+    std::vector<Ev> evs;
+    std::vector<std::pair<std::string, float>> result;
+    void mark(const char *name, cudaStream_t s);   // marks the START of phase `name`
+    void finish(cudaStream_t s);                   // closes the last phase, synchronises, accumulates
+    void reset();
+};
+extern Profiler g_prof;
 
 // ---- primitives (prims.cu) ----
 // out[i] = sum_{j<i} in[j]; total (device pointer, may be null) = sum of all.  in/out may alias.
@@ -99,36 +130,33 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
 }
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
-// lock-free union-find on int parents; the root of a set is its minimum index
-__device__ __forceinline__ int uf_find(const int *parent, int x) {
-    int p = parent[x];
+// L2-coherent accesses for data exchanged between lanes / CTAs inside one kernel
+__device__ __forceinline__ uint32_t ld_cg(const uint32_t *p) { return __ldcg(p); }
+__device__ __forceinline__ void st_cg(uint32_t *p, uint32_t v) { __stcg(p, v); }
+
+// lock-free union-find on u32 parents; the root of a set is its minimum index
+__device__ __forceinline__ uint32_t uf_find(const uint32_t *parent, uint32_t x) {
+    uint32_t p = __ldcg(&parent[x]);
     while (p != x) {
         x = p;
-        p = parent[x];
+        p = __ldcg(&parent[x]);
     }
     return x;
 }
-__device__ __forceinline__ int uf_find_v(volatile int *parent, int x) {
-    int p = parent[x];
-    while (p != x) {
-        x = p;
-        p = parent[x];
-    }
-    return x;
-}
-__device__ __forceinline__ void uf_union(int *parent, int a, int b) {
+__device__ __forceinline__ void uf_union(uint32_t *parent, uint32_t a, uint32_t b) {
     for (;;) {
-        a = uf_find_v(parent, a);
-        b = uf_find_v(parent, b);
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
         if (a == b) return;
         if (a < b) {
-            int t = a;
+            uint32_t t = a;
             a = b;
             b = t;
         }
         // a > b: hang a under b if a is still a root
-        int old = atomicMin(&parent[a], b);
+        uint32_t old = atomicMin(&parent[a], b);
         if (old == a) return;
         a = old;
     }

@@ -1,37 +1,62 @@
-// Block / tile geometry shared by the stage kernels (host + device PODs).
+// Block / tile geometry of one blockwise `bs segment --ws` run (host + device PODs) and the
+// plan object behind the C ABI.  Internal header.
 #pragma once
 #include <stdint.h>
 
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/bsnative.h"
+#include "common.cuh"
+
 namespace bs {
 
-// One watershed problem: a 2-D slice (xy mode, D = 1) or a 3-D block (D > 1) of a
-// daisy block's read ROI.  Per-pixel scratch arrays are indexed base + (z*H + y)*W + x.
+// One watershed problem: a 2-D slice (xy mode, D = 1, ndim = 2) or a whole 3-D read ROI
+// (ndim = 3) of a daisy block.  Per-pixel scratch arrays are indexed base + (z*H + y)*W + x.
 struct Tile {
-    int gz, gy, gx;      // dataset coordinates of tile voxel (0,0,0) (may be negative / beyond: zero fill)
+    int gz, gy, gx;      // dataset coordinates of tile voxel (0,0,0); may lie outside the volume (zero fill)
     int D, H, W;         // tile extent
     int wz, wy, wx;      // write region offset inside the tile
     int wD, wH, wW;      // write region extent
-    int block;           // linear block index
-    int pad_;
-    long long base;      // offset of this tile in the per-pixel scratch arrays
-    long long wbase;     // offset of this tile's write region in block-raster write order
+    int block;           // index into the plan's block table
+    int ndim;            // 2 or 3 (array rank the reference hands to scipy / skimage)
+    long long base;      // offset of this tile in the per-pixel scratch arrays (batch local)
+    long long wbase;     // offset of this tile's write region in batch write order
 };
 
 struct Blk {
-    long long block_id;      // daisy block id (cantor number)
-    int wo[3], ws[3];        // write ROI (dataset voxel coords), shape
-    int ro[3], rs[3];        // read ROI
-    int nb[27];              // linear index of the 27 neighbouring blocks (incl. self at 13), -1 if none
-    int tile_first, tile_count;
-    long long wbase;         // first write-order index of the block
+    long long block_id;      // daisy block id (cantor number of the block index)
+    int idx[3];              // block grid index
+    int wo[3], ws[3];        // write ROI offset (dataset voxel coords) and shape
+    int ro[3], rs[3];        // read ROI offset and shape (write grown by context; not clipped)
+    int nb[27];              // plan block indices of the 3x3x3 neighbourhood (self at 13), -1 if none
+    int owned;               // 1 if this rank processes the block
+    int pad_;
 };
 
-struct VolGeom {
-    int Z, Y, X;             // dataset (affinity array) spatial shape
-    int ro[3], rs[3];        // task ROI offset / shape inside the dataset (fragments array has shape rs)
-    int bs[3];               // block size
-    int ctx[3];              // context
-    int nb[3];               // blocks per axis
+struct Plan {
+    bs_ws_config cfg;
+    std::vector<Blk> blocks;             // ALL blocks of the task, ascending block_id
+    std::vector<int> owned;              // indices of owned blocks (ascending)
+    long long nvox_block;                // prod(block_size)
+    // ---- stage 1 results
+    std::vector<long long> block_count;  // fragments per block (all blocks once counts are known)
+    std::vector<long long> block_nbase;  // exclusive prefix of block_count (dense node numbering)
+    bool counts_global = false;
+    DevBuf fidx;                         // u32 roi_shape: dense node index + 1 (0 = background) -- owned blocks only
+    DevBuf node_id, node_pos, node_size; // owned nodes, ascending id
+    long long n_nodes = 0;
+    long long node_first = 0;            // dense index of the first owned node
+    // ---- stage 2 results
+    DevBuf edge_u, edge_v, edge_score;   // owned edges
+    long long n_edges = 0;
+    // ---- debug scratch kept from the last run (name -> buffer)
+    std::map<std::string, DevBuf *> dbg;
+    std::map<std::string, std::pair<int, long long>> dbg_meta;  // name -> (element bytes, count)
+    ~Plan();
 };
+
+int plan_build(const bs_ws_config &cfg, Plan **out);
 
 }  // namespace bs

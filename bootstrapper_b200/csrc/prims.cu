@@ -7,6 +7,39 @@ static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
 const char *get_error() { return g_err.c_str(); }
 unsigned long long g_launches = 0;
+Profiler g_prof;
+
+void Profiler::mark(const char *name, cudaStream_t s) {
+    if (!on) return;
+    Ev e;
+    e.name = name;
+    cudaEventCreate(&e.ev);
+    cudaEventRecord(e.ev, s);
+    evs.push_back(e);
+}
+void Profiler::finish(cudaStream_t s) {
+    if (!on || evs.empty()) return;
+    mark("", s);
+    cudaEventSynchronize(evs.back().ev);
+    for (size_t i = 0; i + 1 < evs.size(); i++) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, evs[i].ev, evs[i + 1].ev);
+        bool found = false;
+        for (auto &r : result)
+            if (r.first == evs[i].name) {
+                r.second += ms;
+                found = true;
+            }
+        if (!found) result.push_back(std::make_pair(evs[i].name, ms));
+    }
+    for (auto &e : evs) cudaEventDestroy(e.ev);
+    evs.clear();
+}
+void Profiler::reset() {
+    for (auto &e : evs) cudaEventDestroy(e.ev);
+    evs.clear();
+    result.clear();
+}
 
 // ------------------------------------------------------------------ scan
 // 3-phase reduce-then-scan: tile = 256 threads x 16 items.

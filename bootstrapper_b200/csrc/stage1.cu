@@ -1,0 +1,1106 @@
+// Stage 1: affinities -> supervoxel fragments for every owned block (sm_100a).
+//
+// Replaces WatershedFrags.process_block (post/blockwise/watershed_frags.py:196-246) and what it
+// calls: watershed_from_affinities / watershed_from_boundary_distance (post/ws.py:8-112),
+// filter_avg_fragments (watershed_frags.py:148-156), remove_small_objects (:188-192), crop +
+// skimage.measure.label + global ids (:216-224), node statistics (:230-246).
+//
+// Kernel chain per batch of tiles (a tile = one z-slice of a block's read ROI in xy mode, or the
+// whole read ROI in 3-D mode); every array is tile-concatenated, tile-local indices are u32:
+//   k_mask_rowdist   boundary mask (integer test for u8, replayed f32 ops for f32) + distance to the
+//                    nearest background pixel along x (warp per row, ballot bit rows in smem)
+//   k_coldist/zdist  exact squared EDT by pruned lower-envelope search along y (and z)
+//   k_maxfilt        separable maximum filter, size = min_seed_distance, scipy 'reflect' borders
+//   k_seed_*         seeds = (maxfilter == d2) & mask, 4/6-connected components by lock-free
+//                    min-root union-find
+//   k_hist/k_levels  per-tile histogram of d2 -> dense priority levels + FIFO segment per level
+//   k_flood          exact emulation of skimage's (value, age) priority flood: one warp per tile,
+//                    32 queue items per step, neighbours claimed with atomicMin(rank*8+slot),
+//                    step truncated at the first item that pushes a higher-priority pixel,
+//                    order-preserving multi-level append
+//   k_fragstats      per-fragment affinity sum + voxel count (warp-aggregated atomics)
+//   k_crop_*         keep/drop decision, 8/26-connected relabel of the cropped write ROI
+//   k_finalize       raster-order ids (+ block_id * prod(block_size)), uint64 output, node statistics
+#include <algorithm>
+
+#include "geom.h"
+
+namespace bs {
+
+static constexpr uint32_t UNLAB = 0xFFFFFFFFu;   // in mask, not labelled yet
+static constexpr uint32_t CLAIM = 0x80000000u;   // claim keys live in [CLAIM, UNLAB)
+static constexpr uint32_t NONE32 = 0xFFFFFFFFu;
+static constexpr uint16_t GINF = 0xFFFF;
+static constexpr uint32_t DBIG = 0x3FFFFFFFu;
+static constexpr int MAXW = 4096;
+static constexpr unsigned FULL = 0xFFFFFFFFu;
+
+struct AffView {
+    const void *p;
+    const uint8_t *mask;
+    int C, Z, Y, X;
+};
+
+// ------------------------------------------------------------------ affinity access
+template <typename T>
+struct AffOps;
+template <>
+struct AffOps<uint8_t> {
+    // post/ws.py:64,77 on uint8/255 in float64 reduces exactly to a_y + a_x > 255 (2-D) and
+    // post/ws.py:100 to a_z + a_y + a_x > 382 (3-D)  (exhaustively probed)
+    static __device__ __forceinline__ bool boundary(const uint8_t *a, size_t n, size_t i, int ndim) {
+        int ay = a[n + i], ax = a[2 * n + i];
+        if (ndim == 2) return ay + ax > 255;
+        return (int)a[i] + ay + ax > 382;
+    }
+    typedef unsigned long long acc_t;
+    static __device__ __forceinline__ acc_t value(const uint8_t *a, size_t n, size_t i) {
+        return (acc_t)a[i] + a[n + i] + a[2 * n + i];
+    }
+};
+template <>
+struct AffOps<float> {
+    static __device__ __forceinline__ bool boundary(const float *a, size_t n, size_t i, int ndim) {
+        float ay = a[n + i], ax = a[2 * n + i];
+        if (ndim == 2) return __fmul_rn(0.5f, __fadd_rn(ax, ay)) > 0.5f;
+        return __fdiv_rn(__fadd_rn(__fadd_rn(a[i], ay), ax), 3.0f) > 0.5f;
+    }
+    typedef double acc_t;
+    static __device__ __forceinline__ acc_t value(const float *a, size_t n, size_t i) {
+        return (double)__fdiv_rn(__fadd_rn(__fadd_rn(a[i], a[n + i]), a[2 * n + i]), 3.0f);
+    }
+};
+
+// ------------------------------------------------------------------ mask + row distance
+template <typename T>
+__global__ void __launch_bounds__(256) k_mask_rowdist(const Tile *__restrict__ tiles, AffView A, uint8_t *__restrict__ msk,
+                                                      uint16_t *__restrict__ g, uint32_t *__restrict__ tileflags) {
+    __shared__ uint32_t bits[8][MAXW / 32];
+    const Tile t = tiles[blockIdx.y];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rows = t.D * t.H, W = t.W, nw = (W + 31) >> 5;
+    const size_t nvol = (size_t)A.Z * A.Y * A.X;
+    const T *a = (const T *)A.p;
+    bool anybg = false;
+    for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
+        int z = r / t.H, y = r - z * t.H;
+        int gz = t.gz + z, gy = t.gy + y;
+        bool rowin = gz >= 0 && gz < A.Z && gy >= 0 && gy < A.Y;
+        size_t rowoff = rowin ? ((size_t)gz * A.Y + gy) * A.X : 0;
+        long long pbase = t.base + (long long)r * W;
+        for (int c = 0; c < nw; c++) {
+            int x = c * 32 + lane;
+            bool m = false;
+            if (x < W && rowin) {
+                int gx = t.gx + x;
+                if (gx >= 0 && gx < A.X) {
+                    size_t i = rowoff + gx;
+                    if (!A.mask || A.mask[i] > 0) m = AffOps<T>::boundary(a, nvol, i, t.ndim);
+                }
+            }
+            unsigned b = __ballot_sync(FULL, m);
+            int rem = W - c * 32;
+            unsigned valid = rem >= 32 ? FULL : ((1u << rem) - 1u);
+            unsigned bg = ~b & valid;
+            if (lane == 0) bits[warp][c] = bg;
+            anybg |= (bg != 0);
+            if (x < W) msk[pbase + x] = m ? 1 : 0;
+        }
+        __syncwarp();
+        for (int c = 0; c < nw; c++) {
+            int x = c * 32 + lane;
+            if (x < W) {
+                int w = x >> 5, bpos = x & 31;
+                uint32_t word = bits[warp][w];
+                uint32_t dist;
+                if ((word >> bpos) & 1u) {
+                    dist = 0;
+                } else {
+                    uint32_t dl = GINF, dr = GINF;
+                    uint32_t wl = word & ((1u << bpos) - 1u);
+                    for (int ww = w;;) {
+                        if (wl) {
+                            dl = x - (ww * 32 + 31 - __clz(wl));
+                            break;
+                        }
+                        if (--ww < 0) break;
+                        wl = bits[warp][ww];
+                    }
+                    uint32_t wr = word & ~((2u << bpos) - 1u);
+                    for (int ww = w;;) {
+                        if (wr) {
+                            dr = (ww * 32 + __ffs(wr) - 1) - x;
+                            break;
+                        }
+                        if (++ww >= nw) break;
+                        wr = bits[warp][ww];
+                    }
+                    dist = min(dl, dr);
+                }
+                g[pbase + x] = (uint16_t)dist;
+            }
+        }
+        __syncwarp();
+    }
+    if (anybg && lane == 0) atomicOr(&tileflags[blockIdx.y], 1u);
+}
+
+// ------------------------------------------------------------------ exact squared EDT, y and z passes
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) { return __reduce_max_sync(FULL, v); }
+
+// in-plane pass: out = min_y' g(y',x)^2 + (y-y')^2 ; DBIG if the slice has no background.
+// final2d: the tile is a 2-D array -> apply scipy's all-foreground rule and record the tile maximum.
+__global__ void __launch_bounds__(256) k_coldist(const Tile *__restrict__ tiles, const uint16_t *__restrict__ g,
+                                                 uint32_t *__restrict__ out, uint32_t *__restrict__ tilemax) {
+    const Tile t = tiles[blockIdx.y];
+    const int W = t.W, H = t.H;
+    const long long npix = (long long)t.D * H * W;
+    const bool final2d = (t.ndim == 2);
+    uint32_t mymax = 0;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < npix; i0 += (long long)gridDim.x * blockDim.x) {
+        long long i = i0 + threadIdx.x;
+        uint32_t best = 0;
+        if (i < npix) {
+            int x = (int)(i % W);
+            int y = (int)((i / W) % H);
+            const uint16_t *gp = g + t.base + i;
+            uint32_t g0 = gp[0];
+            best = g0 == GINF ? DBIG : g0 * g0;
+            for (int dy = 1;; dy++) {
+                uint32_t dd = (uint32_t)dy * dy;
+                if (dd >= best) break;
+                bool any = false;
+                if (y - dy >= 0) {
+                    any = true;
+                    uint32_t v = gp[-(long long)dy * W];
+                    if (v != GINF) best = min(best, v * v + dd);
+                }
+                if (y + dy < H) {
+                    any = true;
+                    uint32_t v = gp[(long long)dy * W];
+                    if (v != GINF) best = min(best, v * v + dd);
+                }
+                if (!any) break;
+            }
+            if (final2d && best == DBIG) best = (uint32_t)(y + 1) * (y + 1) + (uint32_t)x * x;
+            out[t.base + i] = best;
+            if (final2d) mymax = max(mymax, best);
+        }
+    }
+    if (final2d) {
+        mymax = warp_max_u32(mymax);
+        if ((threadIdx.x & 31) == 0 && mymax) atomicMax(&tilemax[blockIdx.y], mymax);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_zdist(const Tile *__restrict__ tiles, const uint32_t *__restrict__ in,
+                                               uint32_t *__restrict__ out, uint32_t *__restrict__ tilemax) {
+    const Tile t = tiles[blockIdx.y];
+    const int W = t.W, H = t.H, D = t.D;
+    const long long HW = (long long)H * W, npix = (long long)D * HW;
+    uint32_t mymax = 0;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < npix; i0 += (long long)gridDim.x * blockDim.x) {
+        long long i = i0 + threadIdx.x;
+        if (i < npix) {
+            int x = (int)(i % W);
+            int y = (int)((i / W) % H);
+            int z = (int)(i / HW);
+            const uint32_t *ip = in + t.base + i;
+            uint32_t best = ip[0];
+            for (int dz = 1;; dz++) {
+                uint32_t dd = (uint32_t)dz * dz;
+                if (dd >= best) break;
+                bool any = false;
+                if (z - dz >= 0) {
+                    any = true;
+                    best = min(best, ip[-(long long)dz * HW] + dd);
+                }
+                if (z + dz < D) {
+                    any = true;
+                    best = min(best, ip[(long long)dz * HW] + dd);
+                }
+                if (!any) break;
+            }
+            if (best >= DBIG) best = (uint32_t)(z + 1) * (z + 1) + (uint32_t)y * y + (uint32_t)x * x;
+            out[t.base + i] = best;
+            mymax = max(mymax, best);
+        }
+    }
+    mymax = warp_max_u32(mymax);
+    if ((threadIdx.x & 31) == 0 && mymax) atomicMax(&tilemax[blockIdx.y], mymax);
+}
+
+// ------------------------------------------------------------------ maximum filter (scipy, mode='reflect')
+// 1-D pass along `axis` (0 = z, 1 = y, 2 = x): window [c - size/2, c - size/2 + size - 1].
+// last = 1: compare with d2 and emit the seed parent array instead of the filtered value.
+__global__ void __launch_bounds__(256) k_maxfilt(const Tile *__restrict__ tiles, const uint32_t *__restrict__ in,
+                                                 uint32_t *__restrict__ out, int axis, int size, int last,
+                                                 const uint32_t *__restrict__ d2, const uint8_t *__restrict__ msk,
+                                                 uint32_t *__restrict__ par, uint8_t *__restrict__ seedflag) {
+    const Tile t = tiles[blockIdx.y];
+    const int W = t.W, H = t.H, D = t.D;
+    const long long HW = (long long)H * W, npix = (long long)D * HW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+        int x = (int)(i % W);
+        int y = (int)((i / W) % H);
+        int z = (int)(i / HW);
+        int c, L;
+        long long st;
+        if (axis == 2) {
+            c = x, L = W, st = 1;
+        } else if (axis == 1) {
+            c = y, L = H, st = W;
+        } else {
+            c = z, L = D, st = HW;
+        }
+        const uint32_t *ip = in + t.base + i;
+        int lo = c - size / 2;
+        uint32_t m = 0;
+        for (int k = 0; k < size; k++) {
+            int j = lo + k;
+            while (j < 0 || j >= L) {
+                if (j < 0) j = -j - 1;
+                if (j >= L) j = 2 * L - j - 1;
+            }
+            m = max(m, ip[(long long)(j - c) * st]);
+        }
+        if (!last) {
+            out[t.base + i] = m;
+        } else {
+            bool seed = (m == d2[t.base + i]) && msk[t.base + i];
+            par[t.base + i] = seed ? (uint32_t)i : NONE32;
+            seedflag[t.base + i] = seed ? 1 : 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ seed connected components (conn-1)
+__global__ void __launch_bounds__(256) k_seed_union(const Tile *__restrict__ tiles, uint32_t *__restrict__ par) {
+    const Tile t = tiles[blockIdx.y];
+    const int W = t.W, H = t.H, D = t.D;
+    const long long HW = (long long)H * W, npix = (long long)D * HW;
+    uint32_t *pp = par + t.base;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+        if (__ldcg(&pp[i]) == NONE32) continue;
+        int x = (int)(i % W);
+        int y = (int)((i / W) % H);
+        int z = (int)(i / HW);
+        if (x > 0 && __ldcg(&pp[i - 1]) != NONE32) uf_union(pp, (uint32_t)i, (uint32_t)(i - 1));
+        if (y > 0 && __ldcg(&pp[i - W]) != NONE32) uf_union(pp, (uint32_t)i, (uint32_t)(i - W));
+        if (z > 0 && __ldcg(&pp[i - HW]) != NONE32) uf_union(pp, (uint32_t)i, (uint32_t)(i - HW));
+    }
+}
+
+// lab = root+1 for seeds, UNLAB in mask, 0 outside; histogram of d2 over the mask
+__global__ void __launch_bounds__(256) k_seed_label_hist(const Tile *__restrict__ tiles, const uint32_t *__restrict__ par,
+                                                         const uint8_t *__restrict__ msk, const uint32_t *__restrict__ d2,
+                                                         uint32_t *__restrict__ lab, const uint32_t *__restrict__ hbase,
+                                                         uint32_t *__restrict__ hist) {
+    const Tile t = tiles[blockIdx.y];
+    const long long npix = (long long)t.D * t.H * t.W;
+    const uint32_t *pp = par + t.base;
+    const uint32_t hb = hbase[blockIdx.y];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+        uint32_t l = 0;
+        if (msk[t.base + i]) {
+            l = UNLAB;
+            if (pp[i] != NONE32) l = uf_find(pp, (uint32_t)i) + 1;
+            atomicAdd(&hist[hb + d2[t.base + i]], 1u);
+        }
+        lab[t.base + i] = l;
+    }
+}
+
+__global__ void k_tile_hsize(const uint32_t *__restrict__ tilemax, uint32_t *__restrict__ hsize, int ntiles) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ntiles) hsize[i] = tilemax[i] + 1;
+}
+
+__global__ void k_nzflag(const uint32_t *__restrict__ hist, uint8_t *__restrict__ nz, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) nz[i] = hist[i] ? 1 : 0;
+}
+
+// level tables: for every non-empty histogram entry, its dense rank gets the FIFO segment start
+__global__ void k_levels(const uint32_t *__restrict__ hist, const uint32_t *__restrict__ lrank,
+                         const uint32_t *__restrict__ qoff, uint32_t *__restrict__ lvl_qstart, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && hist[i]) lvl_qstart[lrank[i]] = qoff[i];
+}
+
+__global__ void k_tile_ranges(const Tile *__restrict__ tiles, int ntiles, const uint32_t *__restrict__ hbase,
+                              const uint32_t *__restrict__ lrank, const uint32_t *__restrict__ nlevels,
+                              const uint32_t *__restrict__ sscan, const uint32_t *__restrict__ nseeds,
+                              uint32_t *__restrict__ tile_lvl, uint32_t *__restrict__ tile_seed) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ntiles) {
+        tile_lvl[i] = lrank[hbase[i]];
+        tile_seed[i] = sscan[tiles[i].base];
+    } else if (i == ntiles) {
+        tile_lvl[i] = *nlevels;
+        tile_seed[i] = *nseeds;
+    }
+}
+
+// lv = dense level rank of every mask pixel; seed list compaction (tile-local pixel indices)
+__global__ void __launch_bounds__(256) k_pixel_levels(const Tile *__restrict__ tiles, const uint8_t *__restrict__ msk,
+                                                      const uint32_t *__restrict__ d2, const uint32_t *__restrict__ hbase,
+                                                      const uint32_t *__restrict__ lrank, uint32_t *__restrict__ lv,
+                                                      const uint8_t *__restrict__ seedflag, const uint32_t *__restrict__ sscan,
+                                                      uint32_t *__restrict__ seedlist) {
+    const Tile t = tiles[blockIdx.y];
+    const long long npix = (long long)t.D * t.H * t.W;
+    const uint32_t hb = hbase[blockIdx.y];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+        long long p = t.base + i;
+        if (msk[p]) lv[p] = lrank[hb + d2[p]];
+        if (seedflag[p]) seedlist[sscan[p]] = (uint32_t)i;
+    }
+}
+
+// ------------------------------------------------------------------ the flood
+// Order-preserving append of up to NS candidates per lane (order: lane-major, slot-minor) to the
+// FIFO of their level.  `cur`/`tailc`: the current level's tail lives in a register.
+template <int NS>
+__device__ __forceinline__ void warp_append(const bool (&valid_in)[NS], const uint32_t (&lvl)[NS], const uint32_t (&pix)[NS],
+                                            uint32_t *__restrict__ queue, const uint32_t *__restrict__ lvl_qstart,
+                                            uint32_t *__restrict__ lvl_tail, uint32_t cur, uint32_t &tailc, int lane) {
+    bool valid[NS];
+    uint32_t tl[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        valid[s] = valid_in[s];
+        tl[s] = 0;
+        if (valid[s] && lvl[s] != cur) tl[s] = __ldcg(&lvl_tail[lvl[s]]);
+    }
+    for (;;) {
+        uint32_t mylo = NONE32;
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+            if (valid[s]) mylo = min(mylo, lvl[s]);
+        uint32_t L = __reduce_min_sync(FULL, mylo);
+        if (L == NONE32) break;
+        int c = 0;
+        uint32_t mytail = 0;
+#pragma unroll
+        for (int s = NS - 1; s >= 0; s--)
+            if (valid[s] && lvl[s] == L) {
+                c++;
+                mytail = tl[s];
+            }
+        unsigned has = __ballot_sync(FULL, c > 0);
+        int src = __ffs(has) - 1;
+        uint32_t base = __shfl_sync(FULL, mytail, src);
+        if (L == cur) base = tailc;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int total = __shfl_sync(FULL, incl, 31);
+        uint32_t pos = lvl_qstart[L] + base + (uint32_t)(incl - c);
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+            if (valid[s] && lvl[s] == L) {
+                __stcg(&queue[pos++], pix[s]);
+                valid[s] = false;
+            }
+        if (L == cur)
+            tailc = base + total;
+        else if (lane == 0)
+            __stcg(&lvl_tail[L], base + (uint32_t)total);
+    }
+}
+
+// One warp per tile.  Level ranks: higher rank = larger d2 = smaller skimage value = pops first.
+__global__ void __launch_bounds__(64) k_flood(const Tile *__restrict__ tiles, int ntiles, uint32_t *__restrict__ lab_all,
+                                              const uint32_t *__restrict__ lv_all, uint32_t *__restrict__ queue,
+                                              const uint32_t *__restrict__ lvl_qstart, uint32_t *__restrict__ lvl_head,
+                                              uint32_t *__restrict__ lvl_tail, const uint32_t *__restrict__ tile_lvl,
+                                              const uint32_t *__restrict__ seedlist, const uint32_t *__restrict__ tile_seed,
+                                              uint32_t *__restrict__ stats) {
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= ntiles) return;
+    const Tile t = tiles[wid];
+    uint32_t *lab = lab_all + t.base;
+    const uint32_t *lv = lv_all + t.base;
+    const int W = t.W, H = t.H, D = t.D;
+    const int HW = H * W;
+    const uint32_t lo = tile_lvl[wid], hi = tile_lvl[wid + 1];
+    if (lo == hi) return;
+    uint32_t steps = 0, intr = 0;
+
+    // ---- seeds, ascending raveled index (oracle seed_tie = "index")
+    uint32_t cur = lo, tailc = 0, headc = 0;
+    {
+        const uint32_t sb = tile_seed[wid], se = tile_seed[wid + 1];
+        if (sb == se) return;
+        uint32_t maxr = lo;
+        uint32_t dummy_tail = 0;
+        for (uint32_t s0 = sb; s0 < se; s0 += 32) {
+            bool v[1];
+            uint32_t l[1], px[1];
+            v[0] = s0 + lane < se;
+            px[0] = v[0] ? seedlist[s0 + lane] : 0;
+            l[0] = v[0] ? lv[px[0]] : 0;
+            if (v[0]) maxr = max(maxr, l[0]);
+            warp_append<1>(v, l, px, queue, lvl_qstart, lvl_tail, NONE32, dummy_tail, lane);
+            __syncwarp();
+        }
+        cur = __reduce_max_sync(FULL, maxr);
+        headc = 0;
+        tailc = __ldcg(&lvl_tail[cur]);
+    }
+    uint32_t qs = lvl_qstart[cur];
+
+    for (;;) {
+        if (headc == tailc) {
+            // level exhausted: write back and descend to the next non-empty level
+            if (lane == 0) {
+                __stcg(&lvl_head[cur], headc);
+                __stcg(&lvl_tail[cur], tailc);
+            }
+            __syncwarp();
+            bool found = false;
+            long long r0 = (long long)cur - 1;
+            while (r0 >= (long long)lo) {
+                long long r = r0 - lane;
+                bool ne = false;
+                if (r >= (long long)lo) ne = __ldcg(&lvl_tail[r]) != __ldcg(&lvl_head[r]);
+                unsigned b = __ballot_sync(FULL, ne);
+                if (b) {
+                    cur = (uint32_t)(r0 - (__ffs(b) - 1));
+                    found = true;
+                    break;
+                }
+                r0 -= 32;
+            }
+            if (!found) break;
+            headc = __ldcg(&lvl_head[cur]);
+            tailc = __ldcg(&lvl_tail[cur]);
+            qs = lvl_qstart[cur];
+            continue;
+        }
+        steps++;
+        const uint32_t k = min(32u, tailc - headc);
+        const bool act = (uint32_t)lane < k;
+        uint32_t p = 0, mylab = 0;
+        if (act) {
+            p = __ldcg(&queue[qs + headc + lane]);
+            mylab = __ldcg(&lab[p]);
+        }
+        int z = p / HW;
+        int rem = p - z * HW;
+        int y = rem / W;
+        int x = rem - y * W;
+        // neighbour order of skimage (connectivity 1): -z, -y, -x, +x, +y, +z
+        uint32_t nb[6];
+        bool cand[6];
+        nb[0] = (act && z > 0) ? p - HW : NONE32;
+        nb[1] = (act && y > 0) ? p - W : NONE32;
+        nb[2] = (act && x > 0) ? p - 1 : NONE32;
+        nb[3] = (act && x + 1 < W) ? p + 1 : NONE32;
+        nb[4] = (act && y + 1 < H) ? p + W : NONE32;
+        nb[5] = (act && z + 1 < D) ? p + HW : NONE32;
+        const uint32_t keybase = CLAIM | ((uint32_t)lane << 3);
+#pragma unroll
+        for (int s = 0; s < 6; s++) {
+            cand[s] = false;
+            if (nb[s] != NONE32) {
+                uint32_t old = atomicMin(&lab[nb[s]], keybase | s);
+                cand[s] = old >= CLAIM;
+            }
+        }
+        __syncwarp();
+        uint32_t l[6];
+        bool up = false;
+#pragma unroll
+        for (int s = 0; s < 6; s++) {
+            l[s] = 0;
+            if (cand[s]) {
+                cand[s] = __ldcg(&lab[nb[s]]) == (keybase | s);
+                if (cand[s]) {
+                    l[s] = lv[nb[s]];
+                    up |= l[s] > cur;
+                }
+            }
+        }
+        const unsigned ball = __ballot_sync(FULL, up);
+        const int rstar = ball ? __ffs(ball) - 1 : 31;
+        if (lane > rstar) {
+#pragma unroll
+            for (int s = 0; s < 6; s++)
+                if (cand[s]) {
+                    __stcg(&lab[nb[s]], UNLAB);
+                    cand[s] = false;
+                }
+        } else {
+#pragma unroll
+            for (int s = 0; s < 6; s++)
+                if (cand[s]) __stcg(&lab[nb[s]], mylab);
+        }
+        headc += min(k, (uint32_t)rstar + 1u);
+        warp_append<6>(cand, l, nb, queue, lvl_qstart, lvl_tail, cur, tailc, lane);
+        __syncwarp();
+        if (ball) {
+            intr++;
+            uint32_t mx = 0;
+#pragma unroll
+            for (int s = 0; s < 6; s++)
+                if (cand[s]) mx = max(mx, l[s]);
+            mx = __reduce_max_sync(FULL, mx);
+            if (lane == 0) {
+                __stcg(&lvl_head[cur], headc);
+                __stcg(&lvl_tail[cur], tailc);
+            }
+            __syncwarp();
+            cur = mx;
+            headc = __ldcg(&lvl_head[cur]);
+            tailc = __ldcg(&lvl_tail[cur]);
+            qs = lvl_qstart[cur];
+        }
+    }
+    if (lane == 0 && stats) {
+        atomicAdd(&stats[0], steps);
+        atomicAdd(&stats[1], intr);
+        atomicMax(&stats[2], steps);
+    }
+}
+
+// ------------------------------------------------------------------ fragment statistics
+template <typename T>
+__global__ void __launch_bounds__(256) k_fragstats(const Tile *__restrict__ tiles, AffView A, const uint32_t *__restrict__ lab,
+                                                   typename AffOps<T>::acc_t *__restrict__ fsum, uint32_t *__restrict__ fcnt) {
+    const Tile t = tiles[blockIdx.y];
+    const int W = t.W, H = t.H;
+    const long long HW = (long long)H * W, npix = (long long)t.D * HW;
+    const size_t nvol = (size_t)A.Z * A.Y * A.X;
+    const T *a = (const T *)A.p;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < npix; i0 += (long long)gridDim.x * blockDim.x) {
+        long long i = i0 + threadIdx.x;
+        uint32_t l = 0;
+        typename AffOps<T>::acc_t val = 0;
+        if (i < npix) {
+            l = lab[t.base + i];
+            if (l >= CLAIM) l = 0;
+            if (l) {
+                // a labelled pixel is inside the mask, hence inside the volume and not masked out
+                int x = (int)(i % W);
+                int y = (int)((i / W) % H);
+                int z = (int)(i / HW);
+                size_t gi = ((size_t)(t.gz + z) * A.Y + (t.gy + y)) * A.X + (t.gx + x);
+                val = AffOps<T>::value(a, nvol, gi);
+            }
+        }
+        unsigned act = __ballot_sync(FULL, l != 0);
+        if (l) {
+            unsigned peers = __match_any_sync(act, l);
+            int leader = __ffs(peers) - 1;
+            int cnt = __popc(peers);
+            if constexpr (sizeof(T) == 1) {
+                unsigned s = __reduce_add_sync(peers, (unsigned)val);
+                if ((threadIdx.x & 31) == leader) {
+                    atomicAdd(&fsum[t.base + l - 1], (unsigned long long)s);
+                    atomicAdd(&fcnt[t.base + l - 1], (uint32_t)cnt);
+                }
+            } else {
+                atomicAdd(&fsum[t.base + l - 1], val);
+                if ((threadIdx.x & 31) == leader) atomicAdd(&fcnt[t.base + l - 1], (uint32_t)cnt);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ crop + full-connectivity relabel
+template <typename ACC>
+__device__ __forceinline__ bool frag_keep(ACC sum, uint32_t cnt, double ff, int rd, bool is_u8) {
+    if (ff > 0.0) {
+        double mean = is_u8 ? ((double)sum / 765.0) / (double)cnt : (double)sum / (double)cnt;
+        if (mean < ff) return false;            // watershed_frags.py:153
+    }
+    if (rd > 0 && cnt < (uint32_t)rd) return false;  // remove_small_objects(min_size=rd)
+    return true;
+}
+
+// cpar (tile-local parent, only write-region pixels participate): own index if kept else NONE32
+template <typename ACC>
+__global__ void __launch_bounds__(256) k_crop_init(const Tile *__restrict__ tiles, const uint32_t *__restrict__ lab,
+                                                   const ACC *__restrict__ fsum, const uint32_t *__restrict__ fcnt,
+                                                   double ff, int rd, int is_u8, uint32_t *__restrict__ cpar) {
+    const Tile t = tiles[blockIdx.y];
+    const int W = t.W, H = t.H;
+    const long long HW = (long long)H * W, npix = (long long)t.D * HW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+        int x = (int)(i % W);
+        int y = (int)((i / W) % H);
+        int z = (int)(i / HW);
+        uint32_t v = NONE32;
+        if (z >= t.wz && z < t.wz + t.wD && y >= t.wy && y < t.wy + t.wH && x >= t.wx && x < t.wx + t.wW) {
+            uint32_t l = lab[t.base + i];
+            if (l && l < CLAIM) {
+                bool keep = true;
+                if (ff > 0.0 || rd > 0) keep = frag_keep<ACC>(fsum[t.base + l - 1], fcnt[t.base + l - 1], ff, rd, is_u8 != 0);
+                if (keep) v = (uint32_t)i;
+            }
+        }
+        cpar[t.base + i] = v;
+    }
+}
+
+// union with the raster-preceding neighbours of the full (8 / 26) neighbourhood carrying the same label
+__global__ void __launch_bounds__(256) k_crop_union(const Tile *__restrict__ tiles, const uint32_t *__restrict__ lab,
+                                                    uint32_t *__restrict__ cpar) {
+    const Tile t = tiles[blockIdx.y];
+    const int W = t.W, H = t.H, D = t.D;
+    const long long HW = (long long)H * W, npix = (long long)D * HW;
+    uint32_t *pp = cpar + t.base;
+    const uint32_t *ll = lab + t.base;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+        if (__ldcg(&pp[i]) == NONE32) continue;
+        int x = (int)(i % W);
+        int y = (int)((i / W) % H);
+        int z = (int)(i / HW);
+        uint32_t l = ll[i];
+        for (int dz = -1; dz <= 0; dz++)
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    if (dz == 0 && (dy > 0 || (dy == 0 && dx >= 0))) continue;
+                    int zz = z + dz, yy = y + dy, xx = x + dx;
+                    if (zz < 0 || yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                    long long j = (long long)zz * HW + (long long)yy * W + xx;
+                    if (ll[j] != l || __ldcg(&pp[j]) == NONE32) continue;
+                    uf_union(pp, (uint32_t)i, (uint32_t)j);
+                }
+    }
+}
+
+__device__ __forceinline__ long long tile_widx(const Tile &t, int z, int y, int x) {
+    return t.wbase + ((long long)(z - t.wz) * t.wH + (y - t.wy)) * t.wW + (x - t.wx);
+}
+
+// croot[write index] = write index of the component root (NONE32 for background); isroot flags
+__global__ void __launch_bounds__(256) k_crop_flatten(const Tile *__restrict__ tiles, const uint32_t *__restrict__ cpar,
+                                                      uint32_t *__restrict__ croot, uint8_t *__restrict__ isroot) {
+    const Tile t = tiles[blockIdx.y];
+    const int W = t.W, H = t.H;
+    const long long HW = (long long)H * W;
+    const long long nw = (long long)t.wD * t.wH * t.wW;
+    const uint32_t *pp = cpar + t.base;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nw; k += (long long)gridDim.x * blockDim.x) {
+        int x = (int)(k % t.wW) + t.wx;
+        int y = (int)((k / t.wW) % t.wH) + t.wy;
+        int z = (int)(k / ((long long)t.wW * t.wH)) + t.wz;
+        long long i = (long long)z * HW + (long long)y * W + x;
+        uint32_t r = NONE32;
+        uint8_t ir = 0;
+        if (pp[i] != NONE32) {
+            uint32_t root = uf_find(pp, (uint32_t)i);
+            int rz = root / HW;
+            int rr = root - rz * HW;
+            int ry = rr / W, rx = rr - ry * W;
+            r = (uint32_t)tile_widx(t, rz, ry, rx);
+            ir = root == (uint32_t)i;
+        }
+        croot[t.wbase + k] = r;
+        isroot[t.wbase + k] = ir;
+    }
+}
+
+struct BlkDev {
+    long long block_id;
+    long long wbase;       // batch write-order base of the block
+    int wo[3], ws[3];
+    int plan_index;
+    int pad_;
+};
+
+// ids, uint64 output, node statistics.  One CTA column per block (blockIdx.y).
+__global__ void __launch_bounds__(256) k_finalize(const BlkDev *__restrict__ blks, const uint32_t *__restrict__ croot,
+                                                  const uint32_t *__restrict__ rank, long long nvox_block,
+                                                  int roi_oz, int roi_oy, int roi_ox, int roi_Y, int roi_X,
+                                                  uint64_t *__restrict__ frags, uint32_t *__restrict__ ncnt,
+                                                  unsigned long long *__restrict__ nsum, uint32_t *__restrict__ blk_first) {
+    const BlkDev b = blks[blockIdx.y];
+    const long long nw = (long long)b.ws[0] * b.ws[1] * b.ws[2];
+    const uint32_t first = rank[b.wbase];
+    if (blockIdx.x == 0 && threadIdx.x == 0) blk_first[blockIdx.y] = first;
+    for (long long k0 = (long long)blockIdx.x * blockDim.x; k0 < nw; k0 += (long long)gridDim.x * blockDim.x) {
+        long long k = k0 + threadIdx.x;
+        uint32_t node = NONE32;
+        int x = 0, y = 0, z = 0;
+        if (k < nw) {
+            x = (int)(k % b.ws[2]);
+            y = (int)((k / b.ws[2]) % b.ws[1]);
+            z = (int)(k / ((long long)b.ws[2] * b.ws[1]));
+            uint32_t r = croot[b.wbase + k];
+            uint64_t id = 0;
+            if (r != NONE32) {
+                node = rank[r];
+                id = (uint64_t)(node - first + 1) + (uint64_t)b.block_id * (uint64_t)nvox_block;
+            }
+            size_t o = ((size_t)(b.wo[0] + z - roi_oz) * roi_Y + (b.wo[1] + y - roi_oy)) * roi_X + (b.wo[2] + x - roi_ox);
+            frags[o] = id;
+        }
+        unsigned act = __ballot_sync(FULL, node != NONE32);
+        if (node != NONE32) {
+            unsigned peers = __match_any_sync(act, node);
+            int leader = __ffs(peers) - 1;
+            unsigned sz = __reduce_add_sync(peers, (unsigned)z);
+            unsigned sy = __reduce_add_sync(peers, (unsigned)y);
+            unsigned sx = __reduce_add_sync(peers, (unsigned)x);
+            if ((threadIdx.x & 31) == leader) {
+                atomicAdd(&ncnt[node], (uint32_t)__popc(peers));
+                atomicAdd(&nsum[3 * (size_t)node + 0], (unsigned long long)sz);
+                atomicAdd(&nsum[3 * (size_t)node + 1], (unsigned long long)sy);
+                atomicAdd(&nsum[3 * (size_t)node + 2], (unsigned long long)sx);
+            }
+        }
+    }
+}
+
+// node table: id, position = write offset + trunc(centre of mass), size   (watershed_frags.py:230-246)
+__global__ void k_nodes(const BlkDev *__restrict__ blks, int nblk, const uint32_t *__restrict__ blk_first, uint32_t n_nodes,
+                        const uint32_t *__restrict__ ncnt, const unsigned long long *__restrict__ nsum, long long nvox_block,
+                        uint64_t *__restrict__ ids, int32_t *__restrict__ pos, uint32_t *__restrict__ sizes) {
+    uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_nodes) return;
+    // block of node n: last block with blk_first <= n (blocks are in ascending order)
+    int lo = 0, hi = nblk - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (blk_first[mid] <= n)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const BlkDev b = blks[lo];
+    uint32_t c = ncnt[n];
+    ids[n] = (uint64_t)(n - blk_first[lo] + 1) + (uint64_t)b.block_id * (uint64_t)nvox_block;
+    sizes[n] = c;
+    for (int d = 0; d < 3; d++) pos[3 * (size_t)n + d] = b.wo[d] + (int32_t)(nsum[3 * (size_t)n + d] / c);
+}
+
+// ------------------------------------------------------------------ host driver
+static int keep_debug(Plan &P, const char *name, DevBuf &buf, int elem, long long count) {
+    auto it = P.dbg.find(name);
+    if (it != P.dbg.end()) {
+        delete it->second;
+        P.dbg.erase(it);
+    }
+    DevBuf *b = new DevBuf();
+    b->swap(buf);
+    P.dbg[name] = b;
+    P.dbg_meta[name] = std::make_pair(elem, count);
+    return BS_OK;
+}
+
+extern int g_debug;
+
+template <typename T>
+static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64_t *frags_out, long long node_base,
+                        long long *n_new_nodes, cudaStream_t s) {
+    typedef typename AffOps<T>::acc_t acc_t;
+    const bs_ws_config &cfg = P.cfg;
+    const bool xy = cfg.fragments_in_xy != 0;
+    // ---- tiles
+    std::vector<Tile> tiles;
+    std::vector<BlkDev> blks;
+    long long P_pix = 0, V_w = 0, maxpix = 0, maxw = 0;
+    for (size_t bi = 0; bi < bidx.size(); bi++) {
+        const Blk &b = P.blocks[bidx[bi]];
+        BlkDev bd;
+        bd.block_id = b.block_id;
+        bd.wbase = V_w;
+        for (int d = 0; d < 3; d++) bd.wo[d] = b.wo[d], bd.ws[d] = b.ws[d];
+        bd.plan_index = bidx[bi];
+        bd.pad_ = 0;
+        blks.push_back(bd);
+        long long wv = (long long)b.ws[0] * b.ws[1] * b.ws[2];
+        maxw = std::max(maxw, wv);
+        if (xy) {
+            for (int z = 0; z < b.ws[0]; z++) {
+                Tile t;
+                t.gz = b.wo[0] + z, t.gy = b.ro[1], t.gx = b.ro[2];
+                t.D = 1, t.H = b.rs[1], t.W = b.rs[2];
+                t.wz = 0, t.wy = cfg.context[1], t.wx = cfg.context[2];
+                t.wD = 1, t.wH = b.ws[1], t.wW = b.ws[2];
+                t.block = (int)bi;
+                t.ndim = 2;
+                t.base = P_pix;
+                t.wbase = V_w + (long long)z * b.ws[1] * b.ws[2];
+                long long np = (long long)t.H * t.W;
+                P_pix += np;
+                maxpix = std::max(maxpix, np);
+                tiles.push_back(t);
+            }
+        } else {
+            Tile t;
+            t.gz = b.ro[0], t.gy = b.ro[1], t.gx = b.ro[2];
+            t.D = b.rs[0], t.H = b.rs[1], t.W = b.rs[2];
+            t.wz = cfg.context[0], t.wy = cfg.context[1], t.wx = cfg.context[2];
+            t.wD = b.ws[0], t.wH = b.ws[1], t.wW = b.ws[2];
+            t.block = (int)bi;
+            t.ndim = 3;
+            t.base = P_pix;
+            t.wbase = V_w;
+            long long np = (long long)t.D * t.H * t.W;
+            P_pix += np;
+            maxpix = std::max(maxpix, np);
+            tiles.push_back(t);
+        }
+        V_w += wv;
+    }
+    const int ntiles = (int)tiles.size();
+    BS_ARG(ntiles > 0 && ntiles <= 65535, "stage1: batch has too many tiles (lower max_batch_voxels)");
+    BS_ARG(P_pix < (1LL << 31) && maxpix < (1LL << 31), "stage1: batch too large for 32-bit tile indices");
+    for (auto &t : tiles) BS_ARG(t.W <= MAXW && t.W < 65535, "stage1: tile wider than 4096 voxels is not supported");
+
+    DevBuf d_tiles, d_blks;
+    BS_TRY(d_tiles.alloc(sizeof(Tile) * ntiles, s));
+    BS_TRY(d_blks.alloc(sizeof(BlkDev) * blks.size(), s));
+    BS_CUDA(cudaMemcpyAsync(d_tiles.p, tiles.data(), sizeof(Tile) * ntiles, cudaMemcpyHostToDevice, s));
+    BS_CUDA(cudaMemcpyAsync(d_blks.p, blks.data(), sizeof(BlkDev) * blks.size(), cudaMemcpyHostToDevice, s));
+    const Tile *dt = d_tiles.as<Tile>();
+
+    const unsigned gx = (unsigned)std::min<long long>(std::max<long long>((maxpix + 1023) / 1024, 1), 2048);
+    const dim3 grid(gx, ntiles);
+
+    DevBuf msk, g, d2, tmpA, tmpB, lab, lv, seedflag, tileflags, tilemax;
+    BS_TRY(msk.alloc(P_pix, s));
+    BS_TRY(g.alloc(P_pix * 2, s));
+    BS_TRY(d2.alloc(P_pix * 4, s));
+    BS_TRY(tmpA.alloc(P_pix * 4, s));
+    BS_TRY(lab.alloc(P_pix * 4, s));
+    BS_TRY(lv.alloc(P_pix * 4, s));
+    BS_TRY(seedflag.alloc(P_pix, s));
+    BS_TRY(tileflags.alloc_zero(4 * ntiles, s));
+    BS_TRY(tilemax.alloc_zero(4 * (ntiles + 1), s));
+
+    // ---- mask, exact squared EDT
+    g_prof.mark("s1.mask_rowdist", s);
+    {
+        int rows = 0;
+        for (auto &t : tiles) rows = std::max(rows, t.D * t.H);
+        dim3 gr((unsigned)std::min(std::max((rows + 7) / 8, 1), 4096), ntiles);
+        BS_LAUNCH((k_mask_rowdist<T>), gr, 256, 0, s, dt, A, msk.as<uint8_t>(), g.as<uint16_t>(), tileflags.as<uint32_t>());
+    }
+    g_prof.mark("s1.edt", s);
+    if (xy) {
+        BS_LAUNCH(k_coldist, grid, 256, 0, s, dt, g.as<uint16_t>(), d2.as<uint32_t>(), tilemax.as<uint32_t>());
+    } else {
+        BS_LAUNCH(k_coldist, grid, 256, 0, s, dt, g.as<uint16_t>(), tmpA.as<uint32_t>(), tilemax.as<uint32_t>());
+        BS_LAUNCH(k_zdist, grid, 256, 0, s, dt, tmpA.as<uint32_t>(), d2.as<uint32_t>(), tilemax.as<uint32_t>());
+    }
+    // ---- maximum filter -> seeds (parent array in lv, flags in seedflag)
+    g_prof.mark("s1.maxfilt", s);
+    const int msd = cfg.min_seed_distance;
+    if (xy) {
+        BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, d2.as<uint32_t>(), tmpA.as<uint32_t>(), 2, msd, 0, nullptr, nullptr, nullptr,
+                  nullptr);
+        BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, tmpA.as<uint32_t>(), nullptr, 1, msd, 1, d2.as<uint32_t>(),
+                  msk.as<uint8_t>(), lv.as<uint32_t>(), seedflag.as<uint8_t>());
+    } else {
+        BS_TRY(tmpB.alloc(P_pix * 4, s));
+        BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, d2.as<uint32_t>(), tmpA.as<uint32_t>(), 2, msd, 0, nullptr, nullptr, nullptr,
+                  nullptr);
+        BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, tmpA.as<uint32_t>(), tmpB.as<uint32_t>(), 1, msd, 0, nullptr, nullptr, nullptr,
+                  nullptr);
+        BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, tmpB.as<uint32_t>(), nullptr, 0, msd, 1, d2.as<uint32_t>(),
+                  msk.as<uint8_t>(), lv.as<uint32_t>(), seedflag.as<uint8_t>());
+        tmpB.release();
+    }
+    g_prof.mark("s1.seed_cc", s);
+    BS_LAUNCH(k_seed_union, grid, 256, 0, s, dt, lv.as<uint32_t>());
+
+    // ---- histogram sizes (host sync #1: total histogram entries, number of seed pixels)
+    DevBuf hsize, hbase, totals, sscan;
+    BS_TRY(hsize.alloc(4 * (ntiles + 1), s));
+    BS_TRY(hbase.alloc(4 * (ntiles + 1), s));
+    BS_TRY(totals.alloc_zero(4 * 8, s));
+    BS_TRY(sscan.alloc(P_pix * 4, s));
+    uint32_t *d_tot = totals.as<uint32_t>();  // [0]=hist entries [1]=seed pixels [2]=levels [3]=mask pixels [4]=roots
+    BS_LAUNCH(k_tile_hsize, cdiv(ntiles, 256), 256, 0, s, tilemax.as<uint32_t>(), hsize.as<uint32_t>(), ntiles);
+    BS_TRY(scan_exclusive_u32(hsize.as<uint32_t>(), hbase.as<uint32_t>(), ntiles, d_tot + 0, s));
+    BS_TRY(scan_exclusive_u8(seedflag.as<uint8_t>(), sscan.as<uint32_t>(), P_pix, d_tot + 1, s));
+    uint32_t h_tot[8];
+    BS_CUDA(cudaMemcpyAsync(h_tot, d_tot, 32, cudaMemcpyDeviceToHost, s));
+    BS_CUDA(cudaStreamSynchronize(s));
+    const size_t Htot = h_tot[0], nseeds = h_tot[1];
+
+    g_prof.mark("s1.levels", s);
+    DevBuf hist, nz, lrank, qoff, lvl_qstart, lvl_head, lvl_tail, tile_lvl, tile_seed, seedlist, queue, fstats;
+    BS_TRY(hist.alloc_zero(4 * (Htot + 1), s));
+    BS_TRY(nz.alloc(Htot + 1, s));
+    BS_TRY(lrank.alloc(4 * (Htot + 1), s));
+    BS_TRY(qoff.alloc(4 * (Htot + 1), s));
+    BS_TRY(lvl_qstart.alloc(4 * (Htot + 1), s));
+    BS_TRY(lvl_head.alloc_zero(4 * (Htot + 1), s));
+    BS_TRY(lvl_tail.alloc_zero(4 * (Htot + 1), s));
+    BS_TRY(tile_lvl.alloc(4 * (ntiles + 1), s));
+    BS_TRY(tile_seed.alloc(4 * (ntiles + 1), s));
+    BS_TRY(seedlist.alloc(4 * (nseeds + 1), s));
+    BS_TRY(queue.alloc(4 * (size_t)P_pix, s));
+    BS_TRY(fstats.alloc_zero(16, s));
+    BS_LAUNCH(k_seed_label_hist, grid, 256, 0, s, dt, lv.as<uint32_t>(), msk.as<uint8_t>(), d2.as<uint32_t>(),
+              lab.as<uint32_t>(), hbase.as<uint32_t>(), hist.as<uint32_t>());
+    if (Htot) {
+        BS_LAUNCH(k_nzflag, cdiv(Htot, 256), 256, 0, s, hist.as<uint32_t>(), nz.as<uint8_t>(), Htot);
+        BS_TRY(scan_exclusive_u8(nz.as<uint8_t>(), lrank.as<uint32_t>(), Htot, d_tot + 2, s));
+        BS_TRY(scan_exclusive_u32(hist.as<uint32_t>(), qoff.as<uint32_t>(), Htot, d_tot + 3, s));
+        BS_LAUNCH(k_levels, cdiv(Htot, 256), 256, 0, s, hist.as<uint32_t>(), lrank.as<uint32_t>(), qoff.as<uint32_t>(),
+                  lvl_qstart.as<uint32_t>(), Htot);
+    }
+    // lrank needs a valid entry at hbase[t] for every tile: hbase[t] < Htot always (hsize >= 1)
+    BS_LAUNCH(k_tile_ranges, cdiv(ntiles + 1, 256), 256, 0, s, dt, ntiles, hbase.as<uint32_t>(), lrank.as<uint32_t>(),
+              d_tot + 2, sscan.as<uint32_t>(), d_tot + 1, tile_lvl.as<uint32_t>(), tile_seed.as<uint32_t>());
+    // the seed parent array lives in lv and is consumed by k_seed_label_hist above; now lv becomes the level
+    BS_LAUNCH(k_pixel_levels, grid, 256, 0, s, dt, msk.as<uint8_t>(), d2.as<uint32_t>(), hbase.as<uint32_t>(),
+              lrank.as<uint32_t>(), lv.as<uint32_t>(), seedflag.as<uint8_t>(), sscan.as<uint32_t>(), seedlist.as<uint32_t>());
+    if (g_debug) {
+        DevBuf c1, c2;
+        BS_TRY(c1.alloc(P_pix * 4, s));
+        BS_CUDA(cudaMemcpyAsync(c1.p, d2.p, P_pix * 4, cudaMemcpyDeviceToDevice, s));
+        keep_debug(P, "d2", c1, 4, P_pix);
+        BS_TRY(c2.alloc(P_pix * 4, s));
+        BS_CUDA(cudaMemcpyAsync(c2.p, lab.p, P_pix * 4, cudaMemcpyDeviceToDevice, s));
+        keep_debug(P, "seeds", c2, 4, P_pix);
+    }
+    // ---- flood
+    g_prof.mark("s1.flood", s);
+    BS_LAUNCH(k_flood, cdiv((size_t)ntiles * 32, 64), 64, 0, s, dt, ntiles, lab.as<uint32_t>(), lv.as<uint32_t>(),
+              queue.as<uint32_t>(), lvl_qstart.as<uint32_t>(), lvl_head.as<uint32_t>(), lvl_tail.as<uint32_t>(),
+              tile_lvl.as<uint32_t>(), seedlist.as<uint32_t>(), tile_seed.as<uint32_t>(), fstats.as<uint32_t>());
+    // release what the flood no longer needs
+    queue.release();
+    sscan.release();
+    hist.release();
+    nz.release();
+    lrank.release();
+    qoff.release();
+    g.release();
+    tmpA.release();
+    if (g_debug) {
+        DevBuf c1;
+        BS_TRY(c1.alloc(P_pix * 4, s));
+        BS_CUDA(cudaMemcpyAsync(c1.p, lab.p, P_pix * 4, cudaMemcpyDeviceToDevice, s));
+        keep_debug(P, "flood", c1, 4, P_pix);
+        keep_debug(P, "flood_stats", fstats, 4, 4);
+    }
+
+    // ---- fragment statistics, keep/drop, crop relabel
+    g_prof.mark("s1.fragstats", s);
+    DevBuf fsum, fcnt, croot, isroot, rank;
+    const bool need_stats = cfg.filter_fragments > 0.0 || cfg.remove_debris > 0;
+    BS_TRY(fsum.alloc_zero(need_stats ? (size_t)P_pix * 8 : 16, s));
+    BS_TRY(fcnt.alloc_zero(need_stats ? (size_t)P_pix * 4 : 16, s));
+    if (need_stats)
+        BS_LAUNCH((k_fragstats<T>), grid, 256, 0, s, dt, A, lab.as<uint32_t>(), fsum.as<acc_t>(), fcnt.as<uint32_t>());
+    g_prof.mark("s1.crop_cc", s);
+    // cpar reuses lv
+    BS_LAUNCH((k_crop_init<acc_t>), grid, 256, 0, s, dt, lab.as<uint32_t>(), fsum.as<acc_t>(), fcnt.as<uint32_t>(),
+              need_stats ? cfg.filter_fragments : 0.0, need_stats ? cfg.remove_debris : 0, sizeof(T) == 1 ? 1 : 0,
+              lv.as<uint32_t>());
+    BS_LAUNCH(k_crop_union, grid, 256, 0, s, dt, lab.as<uint32_t>(), lv.as<uint32_t>());
+    BS_TRY(croot.alloc((size_t)V_w * 4, s));
+    BS_TRY(isroot.alloc((size_t)V_w, s));
+    BS_TRY(rank.alloc((size_t)V_w * 4 + 4, s));
+    BS_LAUNCH(k_crop_flatten, grid, 256, 0, s, dt, lv.as<uint32_t>(), croot.as<uint32_t>(), isroot.as<uint8_t>());
+    BS_TRY(scan_exclusive_u8(isroot.as<uint8_t>(), rank.as<uint32_t>(), V_w, d_tot + 4, s));
+    // host sync #2: number of fragments in this batch
+    BS_CUDA(cudaMemcpyAsync(h_tot, d_tot, 32, cudaMemcpyDeviceToHost, s));
+    BS_CUDA(cudaStreamSynchronize(s));
+    const uint32_t nn = h_tot[4];
+    *n_new_nodes = nn;
+
+    g_prof.mark("s1.finalize", s);
+    DevBuf ncnt, nsum, blk_first;
+    BS_TRY(ncnt.alloc_zero(4 * ((size_t)nn + 1), s));
+    BS_TRY(nsum.alloc_zero(24 * ((size_t)nn + 1), s));
+    BS_TRY(blk_first.alloc(4 * blks.size(), s));
+    {
+        const unsigned gxw = (unsigned)std::min<long long>(std::max<long long>((maxw + 1023) / 1024, 1), 2048);
+        dim3 gr(gxw, (unsigned)blks.size());
+        BS_LAUNCH(k_finalize, gr, 256, 0, s, d_blks.as<BlkDev>(), croot.as<uint32_t>(), rank.as<uint32_t>(), P.nvox_block,
+                  cfg.roi_offset[0], cfg.roi_offset[1], cfg.roi_offset[2], cfg.roi_shape[1], cfg.roi_shape[2], frags_out,
+                  ncnt.as<uint32_t>(), nsum.as<unsigned long long>(), blk_first.as<uint32_t>());
+    }
+    // ---- grow the plan's node table
+    {
+        DevBuf nid, npos, nsz;
+        size_t tot = (size_t)(node_base + nn);
+        BS_TRY(nid.alloc(8 * (tot + 1), s));
+        BS_TRY(npos.alloc(12 * (tot + 1), s));
+        BS_TRY(nsz.alloc(4 * (tot + 1), s));
+        if (node_base) {
+            BS_CUDA(cudaMemcpyAsync(nid.p, P.node_id.p, 8 * node_base, cudaMemcpyDeviceToDevice, s));
+            BS_CUDA(cudaMemcpyAsync(npos.p, P.node_pos.p, 12 * node_base, cudaMemcpyDeviceToDevice, s));
+            BS_CUDA(cudaMemcpyAsync(nsz.p, P.node_size.p, 4 * node_base, cudaMemcpyDeviceToDevice, s));
+        }
+        if (nn)
+            BS_LAUNCH(k_nodes, cdiv(nn, 256), 256, 0, s, d_blks.as<BlkDev>(), (int)blks.size(), blk_first.as<uint32_t>(), nn,
+                      ncnt.as<uint32_t>(), nsum.as<unsigned long long>(), P.nvox_block, nid.as<uint64_t>() + node_base,
+                      npos.as<int32_t>() + 3 * node_base, nsz.as<uint32_t>() + node_base);
+        P.node_id.swap(nid);
+        P.node_pos.swap(npos);
+        P.node_size.swap(nsz);
+    }
+    // per-block counts
+    std::vector<uint32_t> h_first(blks.size());
+    BS_CUDA(cudaMemcpyAsync(h_first.data(), blk_first.p, 4 * blks.size(), cudaMemcpyDeviceToHost, s));
+    BS_CUDA(cudaStreamSynchronize(s));
+    for (size_t i = 0; i < blks.size(); i++) {
+        uint32_t nxt = i + 1 < blks.size() ? h_first[i + 1] : nn;
+        P.block_count[blks[i].plan_index] = (long long)nxt - h_first[i];
+    }
+    BS_CUDA(cudaGetLastError());
+    return BS_OK;
+}
+
+int stage1_run(Plan &P, const void *affs, const uint8_t *mask, uint64_t *frags_out, cudaStream_t s) {
+    const bs_ws_config &cfg = P.cfg;
+    AffView A;
+    A.p = affs;
+    A.mask = mask;
+    A.C = cfg.n_channels;
+    A.Z = cfg.vol_shape[0], A.Y = cfg.vol_shape[1], A.X = cfg.vol_shape[2];
+    long long cap = cfg.max_batch_voxels > 0 ? cfg.max_batch_voxels : (1LL << 30);
+    cap = std::min(cap, (1LL << 31) - 1);
+    std::fill(P.block_count.begin(), P.block_count.end(), 0);
+    P.counts_global = false;
+    P.n_nodes = 0;
+    g_prof.reset();
+    // batches of owned blocks (ascending block id)
+    size_t i = 0;
+    long long node_base = 0;
+    while (i < P.owned.size()) {
+        std::vector<int> batch;
+        long long pix = 0;
+        int tiles = 0;
+        while (i < P.owned.size()) {
+            const Blk &b = P.blocks[P.owned[i]];
+            long long bp = cfg.fragments_in_xy ? (long long)b.ws[0] * b.rs[1] * b.rs[2] : (long long)b.rs[0] * b.rs[1] * b.rs[2];
+            int bt = cfg.fragments_in_xy ? b.ws[0] : 1;
+            if (!batch.empty() && (pix + bp > cap || tiles + bt > 65535)) break;
+            batch.push_back(P.owned[i]);
+            pix += bp;
+            tiles += bt;
+            i++;
+        }
+        long long nn = 0;
+        int rc = cfg.aff_dtype == BS_DTYPE_U8 ? stage1_batch<uint8_t>(P, batch, A, frags_out, node_base, &nn, s)
+                                               : stage1_batch<float>(P, batch, A, frags_out, node_base, &nn, s);
+        if (rc != BS_OK) return rc;
+        node_base += nn;
+    }
+    P.n_nodes = node_base;
+    g_prof.finish(s);
+    // dense numbering over the blocks known so far (single rank: complete)
+    P.block_nbase[0] = 0;
+    for (size_t b = 0; b < P.blocks.size(); b++) P.block_nbase[b + 1] = P.block_nbase[b] + P.block_count[b];
+    P.node_first = P.owned.empty() ? 0 : P.block_nbase[P.owned[0]];
+    return BS_OK;
+}
+
+}  // namespace bs

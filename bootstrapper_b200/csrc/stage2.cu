@@ -1,0 +1,1033 @@
+// Stage 2: region adjacency graph + waterz agglomeration + merge-tree edge scores per owned block.
+//
+// Replaces WaterzAgglom.process_block (post/blockwise/waterz_agglom.py:106-170):
+//   funlib.segment relabel (:116)             -> dense node numbers are a monotone map of the ids
+//   waterz get_region_graph + MeanAffinity     -> k_rag_accumulate (hash table of (u,v) with exact
+//                                                 integer affinity sums, counts and first-sight key)
+//   waterz mergeUntil with BinQueue<256>       -> k_agglomerate (one warp per block, exact emulation of
+//     (:131-139, thresholds [0, 1.0])             the FIFO bin queue incl. lazy stale re-scoring)
+//   MergeTree replay + find_merges (:153-168)  -> merge tree built in k_agglomerate, k_lca per edge
+//   write_graph ownership (:170)               -> edge kept by the block that owns node min(u, v)
+#include <algorithm>
+
+#include "geom.h"
+
+namespace bs {
+
+static constexpr uint32_t NONE32 = 0xFFFFFFFFu;
+static constexpr uint64_t EMPTY64 = 0xFFFFFFFFFFFFFFFFull;
+static constexpr uint64_t TOMB64 = 0xFFFFFFFFFFFFFFFEull;
+static constexpr unsigned FULL = 0xFFFFFFFFu;
+extern int g_debug;
+
+struct S2Blk {
+    long long block_id;
+    int ro[3], rs[3];          // read ROI
+    uint32_t own_first, own_count;   // dense node range of the block's own fragments
+    uint32_t tbase, tcap;      // RAG hash table range (tcap power of two)
+    uint32_t vbase, nv;        // view-local node range
+    uint32_t nview;            // number of view ranges
+    uint32_t view_first[27], view_count[27], view_prefix[27];   // ascending dense ranges of the 3x3x3 blocks
+    long long view_block_id[27];
+};
+
+struct IdMap {
+    const uint32_t *cantor2dense;   // block_id -> dense base of that block (NONE32 if unknown)
+    long long max_block_id;
+    long long nvox_block;
+};
+
+__device__ __forceinline__ uint32_t id_to_dense(const IdMap &m, uint64_t id) {
+    if (id == 0) return NONE32;
+    uint64_t bid = id / (uint64_t)m.nvox_block;
+    if ((long long)bid > m.max_block_id) return NONE32;
+    uint32_t base = m.cantor2dense[bid];
+    if (base == NONE32) return NONE32;
+    return base + (uint32_t)(id - bid * (uint64_t)m.nvox_block) - 1u;
+}
+
+__device__ __forceinline__ uint64_t hash64(uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return k;
+}
+
+// ------------------------------------------------------------------ RAG accumulation
+// waterz get_region_graph: raster loop over the read ROI; for d in (z, y, x) pair p with
+// p - e_d using affs[d][p]; ids 0 skipped.  Sums are exact integers (u8: raw bytes; f32: rint(a * 2^38)),
+// DESIGN.md D2.  first = min over contributions of (raveled read-ROI index * 3 + d) = creation order.
+template <typename T>
+__device__ __forceinline__ unsigned long long aff_fixed(T v);
+template <>
+__device__ __forceinline__ unsigned long long aff_fixed<uint8_t>(uint8_t v) {
+    return v;
+}
+template <>
+__device__ __forceinline__ unsigned long long aff_fixed<float>(float v) {
+    return (unsigned long long)__double2ll_rn(ldexp((double)v, 38));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_rag_accumulate(const S2Blk *__restrict__ blks, const T *__restrict__ affs,
+                                                        const uint64_t *__restrict__ frags, IdMap idm, int volZ, int volY,
+                                                        int volX, int roz, int roy, int rox, int rsz, int rsy, int rsx,
+                                                        unsigned long long *hkeys, unsigned long long *hsum, uint32_t *hcnt,
+                                                        uint32_t *hfirst, uint32_t *overflow) {
+    const S2Blk &b = blks[blockIdx.y];
+    const int RZ = b.rs[0], RY = b.rs[1], RX = b.rs[2];
+    const long long nvox = (long long)RZ * RY * RX;
+    const size_t nvol = (size_t)volZ * volY * volX;
+    const uint32_t tmask = b.tcap - 1;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < nvox; i0 += (long long)gridDim.x * blockDim.x) {
+        long long i = i0 + threadIdx.x;
+        uint32_t id1 = NONE32;
+        int x = 0, y = 0, z = 0, gx = 0, gy = 0, gz = 0;
+        if (i < nvox) {
+            x = (int)(i % RX);
+            y = (int)((i / RX) % RY);
+            z = (int)(i / ((long long)RX * RY));
+            gz = b.ro[0] + z, gy = b.ro[1] + y, gx = b.ro[2] + x;
+            // fragments array covers the task ROI; outside: zero fill
+            int fz = gz - roz, fy = gy - roy, fx = gx - rox;
+            if (fz >= 0 && fz < rsz && fy >= 0 && fy < rsy && fx >= 0 && fx < rsx)
+                id1 = id_to_dense(idm, frags[((size_t)fz * rsy + fy) * rsx + fx]);
+        }
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            uint32_t id2 = NONE32;
+            if (id1 != NONE32) {
+                int lc = d == 0 ? z : (d == 1 ? y : x);
+                if (lc > 0) {
+                    int fz = gz - roz - (d == 0), fy = gy - roy - (d == 1), fx = gx - rox - (d == 2);
+                    if (fz >= 0 && fy >= 0 && fx >= 0) id2 = id_to_dense(idm, frags[((size_t)fz * rsy + fy) * rsx + fx]);
+                }
+            }
+            bool has = id1 != NONE32 && id2 != NONE32 && id2 != id1;
+            unsigned act = __ballot_sync(FULL, has);
+            if (has) {
+                uint32_t lo = min(id1, id2), hi = max(id1, id2);
+                unsigned long long key = ((unsigned long long)lo << 32) | hi;
+                unsigned long long a = aff_fixed<T>(affs[(size_t)d * nvol + ((size_t)gz * volY + gy) * volX + gx]);
+                uint32_t fk = (uint32_t)(i * 3 + d);
+                unsigned peers = __match_any_sync(act, key);
+                int leader = __ffs(peers) - 1;
+                uint32_t fmin = __reduce_min_sync(peers, fk);
+                unsigned long long asum;
+                if constexpr (sizeof(T) == 1) {
+                    asum = __reduce_add_sync(peers, (unsigned)a);
+                } else {
+                    // 64-bit segmented sum over the peer group
+                    asum = 0;
+                    unsigned rem = peers;
+                    while (rem) {
+                        int src = __ffs(rem) - 1;
+                        rem &= rem - 1;
+                        asum += __shfl_sync(peers, a, src);
+                    }
+                }
+                if ((threadIdx.x & 31) == leader) {
+                    uint32_t slot = (uint32_t)hash64(key) & tmask;
+                    uint32_t probes = 0;
+                    for (;;) {
+                        unsigned long long *kp = &hkeys[(size_t)b.tbase + slot];
+                        unsigned long long k = *((volatile unsigned long long *)kp);
+                        if (k == EMPTY64) k = atomicCAS(kp, EMPTY64, key);
+                        if (k == EMPTY64 || k == key) break;
+                        slot = (slot + 1) & tmask;
+                        if (++probes > tmask) {
+                            atomicExch(overflow, 1u);
+                            slot = NONE32;
+                            break;
+                        }
+                    }
+                    if (slot != NONE32) {
+                        size_t s = (size_t)b.tbase + slot;
+                        atomicAdd(&hsum[s], asum);
+                        atomicAdd(&hcnt[s], (uint32_t)__popc(peers));
+                        atomicMin(&hfirst[s], fmin);
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void k_flag_keys(const unsigned long long *__restrict__ hkeys, uint8_t *__restrict__ flag, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = hkeys[i] != EMPTY64 ? 1 : 0;
+}
+
+__global__ void k_block_ebase(const S2Blk *__restrict__ blks, int nblk, const uint32_t *__restrict__ escan,
+                              const uint32_t *__restrict__ etotal, uint32_t *__restrict__ ebase) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nblk) ebase[i] = escan[blks[i].tbase];
+    if (i == nblk) ebase[i] = *etotal;
+}
+
+// sort keys: (block << 32 | first-sight key); value = table slot
+__global__ void k_edge_sortkeys(const S2Blk *__restrict__ blks, const unsigned long long *__restrict__ hkeys,
+                                const uint32_t *__restrict__ hfirst, const uint32_t *__restrict__ escan,
+                                uint64_t *__restrict__ skeys, uint32_t *__restrict__ svals) {
+    const S2Blk &b = blks[blockIdx.y];
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < b.tcap; s += gridDim.x * blockDim.x) {
+        size_t g = (size_t)b.tbase + s;
+        if (hkeys[g] != EMPTY64) {
+            uint32_t o = escan[g];
+            skeys[o] = ((uint64_t)blockIdx.y << 32) | hfirst[g];
+            svals[o] = (uint32_t)g;
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t dense_to_local(const S2Blk &b, uint32_t dense) {
+    for (uint32_t k = 0; k < b.nview; k++)
+        if (dense >= b.view_first[k] && dense - b.view_first[k] < b.view_count[k])
+            return b.view_prefix[k] + (dense - b.view_first[k]);
+    return NONE32;
+}
+
+__device__ __forceinline__ uint64_t local_to_id(const S2Blk &b, uint32_t local, long long nvox_block) {
+    for (uint32_t k = 0; k < b.nview; k++)
+        if (local >= b.view_prefix[k] && local - b.view_prefix[k] < b.view_count[k])
+            return (uint64_t)(local - b.view_prefix[k] + 1) + (uint64_t)b.view_block_id[k] * (uint64_t)nvox_block;
+    return 0;
+}
+
+// gather sorted edges; endpoints become view-local node numbers; node degrees
+__global__ void k_edge_gather(const S2Blk *__restrict__ blks, const uint32_t *__restrict__ ebase, int nblk,
+                              const uint32_t *__restrict__ svals, const unsigned long long *__restrict__ hkeys,
+                              const unsigned long long *__restrict__ hsum, const uint32_t *__restrict__ hcnt, uint32_t E,
+                              uint32_t *__restrict__ eu, uint32_t *__restrict__ ev, unsigned long long *__restrict__ esum,
+                              uint32_t *__restrict__ ecnt, uint32_t *__restrict__ eblk, uint32_t *__restrict__ deg) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    int lo = 0, hi = nblk - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (ebase[mid] <= e)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const S2Blk &b = blks[lo];
+    size_t g = svals[e];
+    unsigned long long key = hkeys[g];
+    uint32_t u = dense_to_local(b, (uint32_t)(key >> 32)), v = dense_to_local(b, (uint32_t)key);
+    eu[e] = u;
+    ev[e] = v;
+    esum[e] = hsum[g];
+    ecnt[e] = hcnt[g];
+    eblk[e] = lo;
+    atomicAdd(&deg[b.vbase + u], 1u);
+    atomicAdd(&deg[b.vbase + v], 1u);
+}
+
+__global__ void k_nchunks(const uint32_t *__restrict__ deg, uint32_t *__restrict__ nch, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) nch[i] = (deg[i] + 31) >> 5;
+}
+
+// adjacency chunk chains: node i owns chunks [cstart[i], cstart[i] + nch[i])
+__global__ void k_adj_nodes(const uint32_t *__restrict__ deg, const uint32_t *__restrict__ cstart,
+                            uint32_t *__restrict__ ahead, uint32_t *__restrict__ atail, uint32_t *__restrict__ cnext, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t nc = (deg[i] + 31) >> 5;
+    if (nc == 0) {
+        ahead[i] = NONE32;
+        atail[i] = NONE32;
+        return;
+    }
+    uint32_t c0 = cstart[i];
+    ahead[i] = c0;
+    atail[i] = c0 + nc - 1;
+    for (uint32_t c = 0; c < nc; c++) cnext[c0 + c] = c + 1 < nc ? c0 + c + 1 : NONE32;
+}
+
+__global__ void k_adj_fill(const S2Blk *__restrict__ blks, const uint32_t *__restrict__ ebase, const uint32_t *__restrict__ eblk,
+                           const uint32_t *__restrict__ eu, const uint32_t *__restrict__ ev, uint32_t E,
+                           const uint32_t *__restrict__ cstart, uint32_t *__restrict__ cursor, uint32_t *__restrict__ centries) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const S2Blk &b = blks[eblk[e]];
+    uint32_t el = e - ebase[eblk[e]];
+    uint32_t nu = b.vbase + eu[e], nv = b.vbase + ev[e];
+    uint32_t pu = atomicAdd(&cursor[nu], 1u);
+    centries[(size_t)cstart[nu] * 32 + pu] = el;
+    uint32_t pv = atomicAdd(&cursor[nv], 1u);
+    centries[(size_t)cstart[nv] * 32 + pv] = el;
+}
+
+// ------------------------------------------------------------------ agglomeration
+struct AggArrays {
+    // edges (global index = ebase[b] + local)
+    uint32_t *eu, *ev, *ecnt, *etime;
+    unsigned long long *esum;
+    float *escore;
+    uint8_t *edead;
+    // nodes (global index = vbase + local)
+    uint32_t *ufp, *stamp, *ahead, *atail, *tnode;
+    // adjacency chunks
+    uint32_t *centries, *cnext;
+    // pair hash (per block range hbase/hcap)
+    unsigned long long *pkeys;
+    uint32_t *pvals;
+    // queue chunk pool
+    uint32_t *qentries, *qnext;
+    // merge tree (per block base 2*vbase) and history (base vbase)
+    uint32_t *tparent, *tlevel;
+    float *tscore;
+    uint32_t *ha, *hb;
+    float *hs;
+    uint32_t *nmerges;
+    uint32_t *counters;   // per block: pops, stale, dead
+    uint32_t *error;
+};
+
+struct AggBlk {
+    uint32_t ebase, E, vbase, nv, hbase, hcap, qbase, qcap;
+};
+
+template <bool U8>
+__device__ __forceinline__ float edge_score(unsigned long long isum, uint32_t cnt) {
+    // OneMinus<MeanAffinity>: (float)(1.0 - mean), mean = float(sum) / float(count)   (oracle edge_score)
+    float sum;
+    if (U8)
+        sum = __double2float_rn(__ddiv_rn((double)isum, 255.0));
+    else
+        sum = __double2float_rn(ldexp((double)(long long)isum, -38));
+    float mean = __fdiv_rn(sum, __uint2float_rn(cnt));
+    return __double2float_rn(__dsub_rn(1.0, (double)mean));
+}
+
+__device__ __forceinline__ int score_bin(float score, int nbins) {
+    int i = (int)__fmul_rn(score, (float)nbins);
+    return min(max(0, i), nbins - 1);
+}
+
+__device__ __forceinline__ uint32_t agg_find(uint32_t *ufp, uint32_t x) {
+    // path halving; concurrent lanes only ever write ancestors
+    for (;;) {
+        uint32_t p = ufp[x];
+        if (p == x) return x;
+        uint32_t gp = ufp[p];
+        if (gp == p) return p;
+        ufp[x] = gp;
+        x = gp;
+    }
+}
+
+__device__ __forceinline__ unsigned long long pair_key(uint32_t a, uint32_t b) {
+    return a < b ? (((unsigned long long)a << 32) | b) : (((unsigned long long)b << 32) | a);
+}
+
+// lookup: returns slot of key or NONE32
+__device__ __forceinline__ uint32_t pair_lookup(const unsigned long long *pkeys, uint32_t hmask, unsigned long long key) {
+    uint32_t slot = (uint32_t)hash64(key) & hmask;
+    for (uint32_t probes = 0; probes <= hmask; probes++) {
+        unsigned long long k = __ldcg(&pkeys[slot]);
+        if (k == key) return slot;
+        if (k == EMPTY64) return NONE32;
+        slot = (slot + 1) & hmask;
+    }
+    return NONE32;
+}
+
+// insert a key known to be absent; reuses tombstones; returns slot or NONE32 on overflow
+__device__ __forceinline__ uint32_t pair_insert(unsigned long long *pkeys, uint32_t hmask, unsigned long long key) {
+    uint32_t slot = (uint32_t)hash64(key) & hmask;
+    for (uint32_t probes = 0; probes <= hmask; probes++) {
+        unsigned long long k = __ldcg(&pkeys[slot]);
+        if (k == EMPTY64 || k == TOMB64) {
+            unsigned long long old = atomicCAS(&pkeys[slot], k, key);
+            if (old == k) return slot;
+            continue;   // somebody else took it: re-examine the same slot
+        }
+        slot = (slot + 1) & hmask;
+    }
+    return NONE32;
+}
+
+struct BinQ {
+    uint32_t hc[256], ho[256], tc[256], tf[256];
+};
+
+template <bool U8>
+__global__ void __launch_bounds__(32) k_agglomerate(const AggBlk *__restrict__ blks, AggArrays A, float threshold, int nbins,
+                                                    int keep_cheaper) {
+    __shared__ BinQ Q;
+    const AggBlk B = blks[blockIdx.x];
+    const int lane = threadIdx.x;
+    uint32_t *eu = A.eu + B.ebase, *ev = A.ev + B.ebase, *ecnt = A.ecnt + B.ebase, *etime = A.etime + B.ebase;
+    unsigned long long *esum = A.esum + B.ebase;
+    float *escore = A.escore + B.ebase;
+    uint8_t *edead = A.edead + B.ebase;
+    uint32_t *ufp = A.ufp + B.vbase, *stamp = A.stamp + B.vbase, *ahead = A.ahead + B.vbase, *atail = A.atail + B.vbase,
+             *tnode = A.tnode + B.vbase;
+    unsigned long long *pkeys = A.pkeys + B.hbase;
+    uint32_t *pvals = A.pvals + B.hbase;
+    const uint32_t hmask = B.hcap - 1;
+    uint32_t *qentries = A.qentries + (size_t)B.qbase * 32, *qnext = A.qnext + B.qbase;
+    uint32_t *tparent = A.tparent + 2 * (size_t)B.vbase, *tlevel = A.tlevel + 2 * (size_t)B.vbase;
+    float *tscore = A.tscore + 2 * (size_t)B.vbase;
+    uint32_t *ha = A.ha + B.vbase, *hb = A.hb + B.vbase;
+    float *hs = A.hs + B.vbase;
+
+    for (int i = lane; i < 256; i += 32) {
+        Q.hc[i] = NONE32;
+        Q.ho[i] = 0;
+        Q.tc[i] = NONE32;
+        Q.tf[i] = 0;
+    }
+    __syncwarp();
+    // uniform (replicated) allocator state
+    uint32_t q_bump = 0, q_free = NONE32;
+    bool fail = false;
+    uint32_t n_pops = 0, n_stale = 0, n_dead = 0;
+
+    auto alloc_chunk = [&]() -> uint32_t {
+        uint32_t c;
+        if (q_free != NONE32) {
+            c = q_free;
+            q_free = qnext[c];
+        } else {
+            c = q_bump++;
+            if (c >= B.qcap) {
+                fail = true;
+                c = 0;
+            }
+        }
+        return c;
+    };
+    // order-preserving (lane order) append of edge `e` to bin `bin` for lanes with `valid`
+    auto bin_append = [&](bool valid, int bin, uint32_t e) {
+        for (;;) {
+            int mine = valid ? bin : 0x7fffffff;
+            int Bn = __reduce_min_sync(FULL, mine);
+            if (Bn == 0x7fffffff) break;
+            bool c = valid && bin == Bn;
+            unsigned m = __ballot_sync(FULL, c);
+            uint32_t total = __popc(m), off = __popc(m & lanemask_lt());
+            uint32_t tc = Q.tc[Bn], tf = Q.tf[Bn];
+            uint32_t tfe = tc == NONE32 ? 32u : tf;
+            bool need_new = tfe + total > 32u;
+            uint32_t newc = NONE32;
+            if (need_new) {
+                newc = alloc_chunk();
+                if (lane == 0) qnext[newc] = NONE32;
+            }
+            if (c) {
+                uint32_t pos = tfe + off;
+                if (pos < 32u)
+                    qentries[(size_t)tc * 32 + pos] = e;
+                else
+                    qentries[(size_t)newc * 32 + (pos - 32u)] = e;
+                valid = false;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (need_new) {
+                    if (tc != NONE32)
+                        qnext[tc] = newc;
+                    else {
+                        Q.hc[Bn] = newc;
+                        Q.ho[Bn] = 0;
+                    }
+                    Q.tc[Bn] = newc;
+                    Q.tf[Bn] = tfe + total - 32u;
+                } else {
+                    Q.tf[Bn] = tf + total;
+                }
+            }
+            __syncwarp();
+        }
+    };
+
+    // ---- node + tree init, pair hash of the initial edges
+    for (uint32_t i = lane; i < B.nv; i += 32) {
+        ufp[i] = i;
+        stamp[i] = 0;
+        tnode[i] = i;
+        tparent[i] = NONE32;
+        tlevel[i] = 0;
+        tscore[i] = 0.f;
+    }
+    for (uint32_t e = lane; e < B.E; e += 32) {
+        uint32_t s = pair_insert(pkeys, hmask, pair_key(eu[e], ev[e]));
+        if (s == NONE32)
+            fail = true;
+        else
+            pvals[s] = e;
+    }
+    __syncwarp();
+    // ---- initial scoring, edges pushed in creation order (waterz mergeUntil first call)
+    for (uint32_t e0 = 0; e0 < B.E; e0 += 32) {
+        uint32_t e = e0 + lane;
+        bool v = e < B.E;
+        int bin = 0;
+        if (v) {
+            float sc = edge_score<U8>(esum[e], ecnt[e]);
+            escore[e] = sc;
+            etime[e] = 0;
+            edead[e] = 0;
+            bin = score_bin(sc, nbins);
+        }
+        bin_append(v, bin, e);
+    }
+    fail = __any_sync(FULL, fail);
+
+    uint32_t clock = 0, nmerge = 0;
+    int minbin = 0;
+    while (!fail) {
+        // lowest non-empty bin
+        int cb = minbin;
+        uint32_t hc = NONE32, ho = 0, tc = NONE32, tf = 0;
+        for (; cb < nbins; cb++) {
+            hc = Q.hc[cb], ho = Q.ho[cb], tc = Q.tc[cb], tf = Q.tf[cb];
+            if (hc != NONE32 && !(hc == tc && ho == tf)) break;
+        }
+        if (cb >= nbins) break;
+        minbin = cb;
+        const uint32_t k = (hc == tc ? tf : 32u) - ho;
+        const bool act = (uint32_t)lane < k;
+        uint32_t e = 0, ru = 0, rv = 0;
+        int cls = 1;   // 0 stop, 1 dead/inactive, 2 stale, 3 merge
+        float newsc = 0.f;
+        int nbin = 0;
+        if (act) {
+            e = qentries[(size_t)hc * 32 + ho + lane];
+            float sc = escore[e];
+            if (sc >= threshold)
+                cls = 0;
+            else if (edead[e])
+                cls = 1;
+            else {
+                ru = agg_find(ufp, eu[e]);
+                rv = agg_find(ufp, ev[e]);
+                uint32_t te = etime[e];
+                if (stamp[ru] > te || stamp[rv] > te) {
+                    cls = 2;
+                    newsc = edge_score<U8>(esum[e], ecnt[e]);
+                    nbin = score_bin(newsc, nbins);
+                } else
+                    cls = 3;
+            }
+        }
+        bool trig = act && (cls == 0 || cls == 3 || (cls == 2 && nbin < cb));
+        unsigned tb = __ballot_sync(FULL, trig);
+        int rstar = tb ? __ffs(tb) - 1 : (int)k;
+        int tcls = __shfl_sync(FULL, cls, rstar & 31);
+        if (!tb) tcls = -1;
+        // stale entries before the trigger (and a stale trigger itself) are re-scored and re-queued
+        bool redo = act && cls == 2 && (lane < rstar || (lane == rstar && tcls == 2));
+        if (redo) {
+            escore[e] = newsc;
+            etime[e] = clock;
+        }
+        uint32_t consumed = (uint32_t)rstar + ((tcls == 3 || tcls == 2) ? 1u : 0u);
+        n_pops += consumed;
+        n_stale += __popc(__ballot_sync(FULL, redo));
+        n_dead += __popc(__ballot_sync(FULL, act && cls == 1 && lane < rstar));
+        bin_append(redo, nbin, e);
+        // advance the head of bin cb (re-read: the append may have touched the tail)
+        if (lane == 0) {
+            uint32_t ho2 = ho + consumed;
+            uint32_t tc2 = Q.tc[cb], tf2 = Q.tf[cb];
+            if (hc == tc2) {
+                if (ho2 == tf2) {
+                    ho2 = 0;
+                    Q.tf[cb] = 0;
+                }
+                Q.ho[cb] = ho2;
+            } else if (ho2 == 32u) {
+                Q.hc[cb] = qnext[hc];
+                Q.ho[cb] = 0;
+            } else {
+                Q.ho[cb] = ho2;
+            }
+        }
+        bool freed = (hc != Q.tc[cb]) && (ho + consumed == 32u);
+        __syncwarp();
+        if (freed) {
+            // chunk hc fully consumed and not the tail: recycle (all lanes keep the replicated free list)
+            if (lane == 0) qnext[hc] = q_free;
+            q_free = hc;
+            __syncwarp();
+        }
+        if (tcls == 0) break;
+        if (tcls == 2) {
+            minbin = __shfl_sync(FULL, nbin, rstar);
+            continue;
+        }
+        if (tcls != 3) continue;
+
+        // ---- merge: edge me joins clusters a < b, a survives (waterz mergeRegions)
+        const uint32_t me = __shfl_sync(FULL, e, rstar);
+        const uint32_t r1 = __shfl_sync(FULL, ru, rstar), r2 = __shfl_sync(FULL, rv, rstar);
+        const uint32_t a = min(r1, r2), b = max(r1, r2);
+        clock++;
+        if (lane == 0) {
+            float sc = escore[me];
+            ha[nmerge] = a;
+            hb[nmerge] = b;
+            hs[nmerge] = sc;
+            uint32_t t = B.nv + nmerge, ta = tnode[a], tbn = tnode[b];
+            tparent[ta] = t;
+            tparent[tbn] = t;
+            tparent[t] = NONE32;
+            tlevel[t] = max(tlevel[ta], tlevel[tbn]) + 1;
+            tscore[t] = sc;
+            tnode[a] = t;
+            ufp[b] = a;
+            stamp[a] = clock;
+            edead[me] = 1;
+            uint32_t s = pair_lookup(pkeys, hmask, pair_key(a, b));
+            if (s != NONE32) __stcg(&pkeys[s], TOMB64);
+        }
+        nmerge++;
+        __syncwarp();
+        uint32_t c = ahead[b];
+        while (c != NONE32) {
+            uint32_t ne = A.centries[(size_t)c * 32 + lane];
+            bool valid = ne != NONE32 && !edead[ne];
+            if (valid) {
+                uint32_t x1 = agg_find(ufp, eu[ne]), x2 = agg_find(ufp, ev[ne]);
+                uint32_t x = x1 == a ? x2 : x1;
+                if (x == a) {
+                    edead[ne] = 1;   // cannot happen for a consistent graph; keep the state sane
+                } else {
+                    // the stale key (b, x) is retired, the edge now lives under (a, x)
+                    uint32_t so = pair_lookup(pkeys, hmask, pair_key(b, x));
+                    if (so != NONE32) __stcg(&pkeys[so], TOMB64);
+                    uint32_t sa = pair_lookup(pkeys, hmask, pair_key(a, x));
+                    if (sa == NONE32) {
+                        uint32_t sn = pair_insert(pkeys, hmask, pair_key(a, x));
+                        if (sn == NONE32)
+                            fail = true;
+                        else
+                            pvals[sn] = ne;
+                    } else {
+                        uint32_t ae = pvals[sa];
+                        if (!keep_cheaper || escore[ne] > escore[ae]) {
+                            esum[ae] += esum[ne];
+                            ecnt[ae] += ecnt[ne];
+                            edead[ne] = 1;
+                        } else {
+                            esum[ne] += esum[ae];
+                            ecnt[ne] += ecnt[ae];
+                            edead[ae] = 1;
+                            pvals[sa] = ne;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            c = A.cnext[c];
+        }
+        if (lane == 0) {
+            uint32_t hbh = ahead[b];
+            if (hbh != NONE32) {
+                if (ahead[a] == NONE32)
+                    ahead[a] = hbh;
+                else
+                    A.cnext[atail[a]] = hbh;
+                atail[a] = atail[b];
+            }
+        }
+        fail = __any_sync(FULL, fail);
+        __syncwarp();
+    }
+    if (lane == 0) {
+        A.nmerges[blockIdx.x] = nmerge;
+        A.counters[3 * blockIdx.x + 0] = n_pops;
+        A.counters[3 * blockIdx.x + 1] = n_stale;
+        A.counters[3 * blockIdx.x + 2] = n_dead;
+        if (fail) atomicExch(A.error, 1u);
+    }
+}
+
+// ------------------------------------------------------------------ merge-tree score of every initial edge
+// post/merge_tree.py:5-27: climb from the lower-level side until both sides meet; NaN if they never do.
+__global__ void k_lca(const S2Blk *__restrict__ blks, const uint32_t *__restrict__ ebase, const uint32_t *__restrict__ eblk,
+                      const uint32_t *__restrict__ eu, const uint32_t *__restrict__ ev, uint32_t E,
+                      const uint32_t *__restrict__ tparent, const uint32_t *__restrict__ tlevel, const float *__restrict__ tscore,
+                      long long nvox_block, uint64_t *__restrict__ out_u, uint64_t *__restrict__ out_v, float *__restrict__ out_s,
+                      uint8_t *__restrict__ owned) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const S2Blk &b = blks[eblk[e]];
+    const uint32_t *tp = tparent + 2 * (size_t)b.vbase, *tl = tlevel + 2 * (size_t)b.vbase;
+    const float *ts = tscore + 2 * (size_t)b.vbase;
+    uint32_t u = eu[e], v = ev[e];
+    float score;
+    for (;;) {
+        if (u == v) {
+            score = ts[u];
+            break;
+        }
+        if (tl[u] > tl[v]) {
+            uint32_t t = u;
+            u = v;
+            v = t;
+        }
+        uint32_t p = tp[u];
+        if (p == NONE32) {
+            score = __int_as_float(0x7fc00000);
+            break;
+        }
+        u = p;
+    }
+    uint32_t lu = eu[e], lv = ev[e];
+    out_u[e] = local_to_id(b, lu, nvox_block);
+    out_v[e] = local_to_id(b, lv, nvox_block);
+    out_s[e] = score;
+    // write_graph(rag, block.write_roi): the edge is persisted by the block holding node min(u, v)
+    // (its stored position, a centre of mass, always lies inside its own block's write ROI)
+    uint32_t own_prefix = NONE32;
+    for (uint32_t k = 0; k < b.nview; k++)
+        if (b.view_first[k] == b.own_first && b.view_count[k] == b.own_count) own_prefix = b.view_prefix[k];
+    uint32_t lo = min(lu, lv);
+    owned[e] = (own_prefix != NONE32 && lo >= own_prefix && lo - own_prefix < b.own_count) ? 1 : 0;
+}
+
+__global__ void k_compact_edges(const uint8_t *__restrict__ owned, const uint32_t *__restrict__ oscan, uint32_t E,
+                                const uint64_t *__restrict__ in_u, const uint64_t *__restrict__ in_v,
+                                const float *__restrict__ in_s, uint64_t *__restrict__ out_u, uint64_t *__restrict__ out_v,
+                                float *__restrict__ out_s) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E || !owned[e]) return;
+    uint32_t o = oscan[e];
+    out_u[o] = in_u[e];
+    out_v[o] = in_v[e];
+    out_s[o] = in_s[e];
+}
+
+// ------------------------------------------------------------------ host driver
+static uint32_t next_pow2(uint64_t v) {
+    uint64_t p = 1;
+    while (p < v) p <<= 1;
+    return (uint32_t)std::min<uint64_t>(p, 1ull << 31);
+}
+
+static int keep_debug2(Plan &P, const char *name, DevBuf &buf, int elem, long long count) {
+    auto it = P.dbg.find(name);
+    if (it != P.dbg.end()) {
+        delete it->second;
+        P.dbg.erase(it);
+    }
+    DevBuf *b = new DevBuf();
+    b->swap(buf);
+    P.dbg[name] = b;
+    P.dbg_meta[name] = std::make_pair(elem, count);
+    return BS_OK;
+}
+
+template <typename T>
+static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int table_mult, cudaStream_t s, bool *overflowed) {
+    const bs_ws_config &cfg = P.cfg;
+    const int nown = (int)P.owned.size();
+    *overflowed = false;
+    P.n_edges = 0;
+    if (nown == 0) return BS_OK;
+    BS_ARG(nown <= 65535, "stage2: too many owned blocks for one launch");
+    // dense numbering of all blocks
+    const size_t nblocks = P.blocks.size();
+    long long max_bid = 0;
+    for (auto &b : P.blocks) max_bid = std::max(max_bid, b.block_id);
+    std::vector<uint32_t> c2d((size_t)max_bid + 1, NONE32);
+    for (size_t i = 0; i < nblocks; i++) c2d[P.blocks[i].block_id] = (uint32_t)P.block_nbase[i];
+    BS_ARG(P.block_nbase[nblocks] < (1LL << 32) - 2, "stage2: more than 2^32 fragments");
+
+    std::vector<S2Blk> hb(nown);
+    uint64_t tcur = 0, vcur = 0;
+    for (int i = 0; i < nown; i++) {
+        const Blk &b = P.blocks[P.owned[i]];
+        S2Blk &d = hb[i];
+        d.block_id = b.block_id;
+        for (int k = 0; k < 3; k++) d.ro[k] = b.ro[k], d.rs[k] = b.rs[k];
+        d.own_first = (uint32_t)P.block_nbase[P.owned[i]];
+        d.own_count = (uint32_t)P.block_count[P.owned[i]];
+        // view ranges in ascending dense order (= ascending block id = ascending plan index)
+        std::vector<int> nbs;
+        for (int k = 0; k < 27; k++)
+            if (b.nb[k] >= 0) nbs.push_back(b.nb[k]);
+        std::sort(nbs.begin(), nbs.end());
+        d.nview = 0;
+        uint32_t pre = 0;
+        double est = 0;
+        for (int nbi : nbs) {
+            uint32_t k = d.nview++;
+            d.view_first[k] = (uint32_t)P.block_nbase[nbi];
+            d.view_count[k] = (uint32_t)P.block_count[nbi];
+            d.view_prefix[k] = pre;
+            d.view_block_id[k] = P.blocks[nbi].block_id;
+            pre += d.view_count[k];
+            est += nbi == P.owned[i] ? (double)d.view_count[k] : 0.5 * d.view_count[k];
+        }
+        d.nv = pre;
+        d.vbase = (uint32_t)vcur;
+        vcur += pre;
+        d.tcap = next_pow2((uint64_t)std::max(4096.0, 16.0 * est * table_mult));
+        d.tbase = (uint32_t)tcur;
+        tcur += d.tcap;
+        BS_ARG(tcur < (1ull << 32) && vcur < (1ull << 31), "stage2: RAG tables exceed 32-bit indexing");
+    }
+    const size_t Ttot = tcur, Vtot = vcur;
+
+    DevBuf d_blks, d_c2d, hkeys, hsum, hcnt, hfirst, ovf;
+    BS_TRY(d_blks.alloc(sizeof(S2Blk) * nown, s));
+    BS_CUDA(cudaMemcpyAsync(d_blks.p, hb.data(), sizeof(S2Blk) * nown, cudaMemcpyHostToDevice, s));
+    BS_TRY(d_c2d.alloc(4 * c2d.size(), s));
+    BS_CUDA(cudaMemcpyAsync(d_c2d.p, c2d.data(), 4 * c2d.size(), cudaMemcpyHostToDevice, s));
+    BS_TRY(hkeys.alloc_fill(8 * Ttot, 0xFF, s));
+    BS_TRY(hsum.alloc_zero(8 * Ttot, s));
+    BS_TRY(hcnt.alloc_zero(4 * Ttot, s));
+    BS_TRY(hfirst.alloc_fill(4 * Ttot, 0xFF, s));
+    BS_TRY(ovf.alloc_zero(16, s));
+    IdMap idm;
+    idm.cantor2dense = d_c2d.as<uint32_t>();
+    idm.max_block_id = max_bid;
+    idm.nvox_block = P.nvox_block;
+    const S2Blk *db = d_blks.as<S2Blk>();
+
+    g_prof.mark("s2.rag", s);
+    long long maxread = 0;
+    for (auto &d : hb) {
+        long long rv = (long long)d.rs[0] * d.rs[1] * d.rs[2];
+        BS_ARG(rv * 3 < (1LL << 32), "stage2: block read ROI too large for 32-bit first-sight keys");
+        maxread = std::max(maxread, rv);
+    }
+    {
+        dim3 gr((unsigned)std::min<long long>(std::max<long long>((maxread + 1023) / 1024, 1), 4096), nown);
+        BS_LAUNCH((k_rag_accumulate<T>), gr, 256, 0, s, db, (const T *)affs, frags, idm, cfg.vol_shape[0], cfg.vol_shape[1],
+                  cfg.vol_shape[2], cfg.roi_offset[0], cfg.roi_offset[1], cfg.roi_offset[2], cfg.roi_shape[0],
+                  cfg.roi_shape[1], cfg.roi_shape[2], hkeys.as<unsigned long long>(), hsum.as<unsigned long long>(),
+                  hcnt.as<uint32_t>(), hfirst.as<uint32_t>(), ovf.as<uint32_t>());
+    }
+    // ---- compaction + creation-order sort (host sync: number of edges)
+    g_prof.mark("s2.edges", s);
+    DevBuf flag, escan, tot, ebase;
+    BS_TRY(flag.alloc(Ttot, s));
+    BS_TRY(escan.alloc(4 * Ttot, s));
+    BS_TRY(tot.alloc_zero(32, s));
+    BS_TRY(ebase.alloc(4 * (nown + 1), s));
+    BS_LAUNCH(k_flag_keys, cdiv(Ttot, 256), 256, 0, s, hkeys.as<unsigned long long>(), flag.as<uint8_t>(), Ttot);
+    BS_TRY(scan_exclusive_u8(flag.as<uint8_t>(), escan.as<uint32_t>(), Ttot, tot.as<uint32_t>(), s));
+    BS_LAUNCH(k_block_ebase, cdiv(nown + 1, 256), 256, 0, s, db, nown, escan.as<uint32_t>(), tot.as<uint32_t>(),
+              ebase.as<uint32_t>());
+    uint32_t h_tot[2] = {0, 0};
+    BS_CUDA(cudaMemcpyAsync(&h_tot[0], tot.p, 4, cudaMemcpyDeviceToHost, s));
+    BS_CUDA(cudaMemcpyAsync(&h_tot[1], ovf.p, 4, cudaMemcpyDeviceToHost, s));
+    BS_CUDA(cudaStreamSynchronize(s));
+    if (h_tot[1]) {
+        *overflowed = true;
+        return BS_OK;
+    }
+    const uint32_t E = h_tot[0];
+    std::vector<uint32_t> h_ebase(nown + 1);
+    BS_CUDA(cudaMemcpyAsync(h_ebase.data(), ebase.p, 4 * (nown + 1), cudaMemcpyDeviceToHost, s));
+    BS_CUDA(cudaStreamSynchronize(s));
+
+    DevBuf skeys, svals, skeys2, svals2;
+    BS_TRY(skeys.alloc(8 * ((size_t)E + 1), s));
+    BS_TRY(svals.alloc(4 * ((size_t)E + 1), s));
+    BS_TRY(skeys2.alloc(8 * ((size_t)E + 1), s));
+    BS_TRY(svals2.alloc(4 * ((size_t)E + 1), s));
+    {
+        uint32_t maxcap = 0;
+        for (auto &d : hb) maxcap = std::max(maxcap, d.tcap);
+        dim3 gr(std::min<unsigned>(cdiv(maxcap, 256), 1024), nown);
+        BS_LAUNCH(k_edge_sortkeys, gr, 256, 0, s, db, hkeys.as<unsigned long long>(), hfirst.as<uint32_t>(),
+                  escan.as<uint32_t>(), skeys.as<uint64_t>(), svals.as<uint32_t>());
+    }
+    int bbits = 0;
+    while ((1 << bbits) < nown) bbits++;
+    BS_TRY(radix_sort_pairs(skeys.as<uint64_t>(), svals.as<uint32_t>(), skeys2.as<uint64_t>(), svals2.as<uint32_t>(), E, 0,
+                            32 + ((bbits + 7) / 8) * 8, s));
+    skeys2.release();
+    svals2.release();
+    flag.release();
+    escan.release();
+
+    DevBuf eu, ev, esum, ecnt, eblk, deg;
+    BS_TRY(eu.alloc(4 * ((size_t)E + 1), s));
+    BS_TRY(ev.alloc(4 * ((size_t)E + 1), s));
+    BS_TRY(esum.alloc(8 * ((size_t)E + 1), s));
+    BS_TRY(ecnt.alloc(4 * ((size_t)E + 1), s));
+    BS_TRY(eblk.alloc(4 * ((size_t)E + 1), s));
+    BS_TRY(deg.alloc_zero(4 * (Vtot + 1), s));
+    if (E)
+        BS_LAUNCH(k_edge_gather, cdiv(E, 256), 256, 0, s, db, ebase.as<uint32_t>(), nown, svals.as<uint32_t>(),
+                  hkeys.as<unsigned long long>(), hsum.as<unsigned long long>(), hcnt.as<uint32_t>(), E, eu.as<uint32_t>(),
+                  ev.as<uint32_t>(), esum.as<unsigned long long>(), ecnt.as<uint32_t>(), eblk.as<uint32_t>(),
+                  deg.as<uint32_t>());
+    hkeys.release();
+    hsum.release();
+    hcnt.release();
+    hfirst.release();
+    skeys.release();
+    svals.release();
+
+    // ---- adjacency chunk chains
+    g_prof.mark("s2.adjacency", s);
+    const size_t NCmax = Vtot + (size_t)E / 16 + 2;
+    DevBuf nch, cstart, ahead, atail, cnext, centries, cursor;
+    BS_TRY(nch.alloc(4 * (Vtot + 1), s));
+    BS_TRY(cstart.alloc(4 * (Vtot + 1), s));
+    BS_TRY(ahead.alloc(4 * (Vtot + 1), s));
+    BS_TRY(atail.alloc(4 * (Vtot + 1), s));
+    BS_TRY(cnext.alloc(4 * NCmax, s));
+    BS_TRY(centries.alloc_fill(4 * NCmax * 32, 0xFF, s));
+    BS_TRY(cursor.alloc_zero(4 * (Vtot + 1), s));
+    if (Vtot) {
+        BS_LAUNCH(k_nchunks, cdiv(Vtot, 256), 256, 0, s, deg.as<uint32_t>(), nch.as<uint32_t>(), Vtot);
+        BS_TRY(scan_exclusive_u32(nch.as<uint32_t>(), cstart.as<uint32_t>(), Vtot, nullptr, s));
+        BS_LAUNCH(k_adj_nodes, cdiv(Vtot, 256), 256, 0, s, deg.as<uint32_t>(), cstart.as<uint32_t>(), ahead.as<uint32_t>(),
+                  atail.as<uint32_t>(), cnext.as<uint32_t>(), Vtot);
+    }
+    if (E)
+        BS_LAUNCH(k_adj_fill, cdiv(E, 256), 256, 0, s, db, ebase.as<uint32_t>(), eblk.as<uint32_t>(), eu.as<uint32_t>(),
+                  ev.as<uint32_t>(), E, cstart.as<uint32_t>(), cursor.as<uint32_t>(), centries.as<uint32_t>());
+
+    // ---- agglomeration
+    g_prof.mark("s2.agglomerate", s);
+    std::vector<AggBlk> ab(nown);
+    uint64_t hcur = 0, qcur = 0;
+    for (int i = 0; i < nown; i++) {
+        AggBlk &a = ab[i];
+        a.ebase = h_ebase[i];
+        a.E = h_ebase[i + 1] - h_ebase[i];
+        a.vbase = hb[i].vbase;
+        a.nv = hb[i].nv;
+        a.hcap = next_pow2((uint64_t)std::max<uint32_t>(64, 4 * a.E));
+        a.hbase = (uint32_t)hcur;
+        hcur += a.hcap;
+        a.qcap = a.E / 16 + 2 * 256 + 64;
+        a.qbase = (uint32_t)qcur;
+        qcur += a.qcap;
+        BS_ARG(hcur < (1ull << 32), "stage2: pair hash exceeds 32-bit indexing");
+    }
+    DevBuf d_ab, etime, escore, edead, ufp, stamp, tnode, pkeys, pvals, qentries, qnext, tparent, tlevel, tscore, ha, hbb, hs,
+        nmerges, counters, err;
+    BS_TRY(d_ab.alloc(sizeof(AggBlk) * nown, s));
+    BS_CUDA(cudaMemcpyAsync(d_ab.p, ab.data(), sizeof(AggBlk) * nown, cudaMemcpyHostToDevice, s));
+    BS_TRY(etime.alloc(4 * ((size_t)E + 1), s));
+    BS_TRY(escore.alloc(4 * ((size_t)E + 1), s));
+    BS_TRY(edead.alloc(((size_t)E + 1), s));
+    BS_TRY(ufp.alloc(4 * (Vtot + 1), s));
+    BS_TRY(stamp.alloc(4 * (Vtot + 1), s));
+    BS_TRY(tnode.alloc(4 * (Vtot + 1), s));
+    BS_TRY(pkeys.alloc_fill(8 * (size_t)hcur, 0xFF, s));
+    BS_TRY(pvals.alloc(4 * (size_t)hcur, s));
+    BS_TRY(qentries.alloc(4 * (size_t)qcur * 32, s));
+    BS_TRY(qnext.alloc(4 * (size_t)qcur, s));
+    BS_TRY(tparent.alloc(4 * (2 * Vtot + 2), s));
+    BS_TRY(tlevel.alloc(4 * (2 * Vtot + 2), s));
+    BS_TRY(tscore.alloc(4 * (2 * Vtot + 2), s));
+    BS_TRY(ha.alloc(4 * (Vtot + 1), s));
+    BS_TRY(hbb.alloc(4 * (Vtot + 1), s));
+    BS_TRY(hs.alloc(4 * (Vtot + 1), s));
+    BS_TRY(nmerges.alloc_zero(4 * nown, s));
+    BS_TRY(counters.alloc_zero(12 * nown, s));
+    BS_TRY(err.alloc_zero(16, s));
+    AggArrays A;
+    A.eu = eu.as<uint32_t>(), A.ev = ev.as<uint32_t>(), A.ecnt = ecnt.as<uint32_t>(), A.etime = etime.as<uint32_t>();
+    A.esum = esum.as<unsigned long long>();
+    A.escore = escore.as<float>();
+    A.edead = edead.as<uint8_t>();
+    A.ufp = ufp.as<uint32_t>(), A.stamp = stamp.as<uint32_t>(), A.ahead = ahead.as<uint32_t>(), A.atail = atail.as<uint32_t>(),
+    A.tnode = tnode.as<uint32_t>();
+    A.centries = centries.as<uint32_t>(), A.cnext = cnext.as<uint32_t>();
+    A.pkeys = pkeys.as<unsigned long long>(), A.pvals = pvals.as<uint32_t>();
+    A.qentries = qentries.as<uint32_t>(), A.qnext = qnext.as<uint32_t>();
+    A.tparent = tparent.as<uint32_t>(), A.tlevel = tlevel.as<uint32_t>(), A.tscore = tscore.as<float>();
+    A.ha = ha.as<uint32_t>(), A.hb = hbb.as<uint32_t>(), A.hs = hs.as<float>();
+    A.nmerges = nmerges.as<uint32_t>();
+    A.counters = counters.as<uint32_t>();
+    A.error = err.as<uint32_t>();
+    const int nbins = cfg.queue_bins;
+    BS_ARG(nbins == 256, "stage2: only the BinQueue<256> agglomeration of the blockwise path is implemented");
+    if (sizeof(T) == 1)
+        BS_LAUNCH((k_agglomerate<true>), nown, 32, 0, s, d_ab.as<AggBlk>(), A, 1.0f, nbins, cfg.keep_cheaper);
+    else
+        BS_LAUNCH((k_agglomerate<false>), nown, 32, 0, s, d_ab.as<AggBlk>(), A, 1.0f, nbins, cfg.keep_cheaper);
+
+    // ---- merge-tree scores, ownership, output (host sync: number of owned edges)
+    g_prof.mark("s2.lca", s);
+    DevBuf ou, ov, os, owned, oscan;
+    BS_TRY(ou.alloc(8 * ((size_t)E + 1), s));
+    BS_TRY(ov.alloc(8 * ((size_t)E + 1), s));
+    BS_TRY(os.alloc(4 * ((size_t)E + 1), s));
+    BS_TRY(owned.alloc(((size_t)E + 1), s));
+    BS_TRY(oscan.alloc(4 * ((size_t)E + 1), s));
+    if (E) {
+        BS_LAUNCH(k_lca, cdiv(E, 256), 256, 0, s, db, ebase.as<uint32_t>(), eblk.as<uint32_t>(), eu.as<uint32_t>(),
+                  ev.as<uint32_t>(), E, tparent.as<uint32_t>(), tlevel.as<uint32_t>(), tscore.as<float>(), P.nvox_block,
+                  ou.as<uint64_t>(), ov.as<uint64_t>(), os.as<float>(), owned.as<uint8_t>());
+        BS_TRY(scan_exclusive_u8(owned.as<uint8_t>(), oscan.as<uint32_t>(), E, tot.as<uint32_t>() + 1, s));
+    }
+    uint32_t h2[2] = {0, 0};
+    BS_CUDA(cudaMemcpyAsync(&h2[0], tot.as<uint32_t>() + 1, 4, cudaMemcpyDeviceToHost, s));
+    BS_CUDA(cudaMemcpyAsync(&h2[1], err.p, 4, cudaMemcpyDeviceToHost, s));
+    BS_CUDA(cudaStreamSynchronize(s));
+    if (h2[1]) {
+        set_error("stage2: agglomeration workspace overflow (pair hash or queue pool)");
+        return BS_ERR_OVERFLOW;
+    }
+    const uint32_t EO = E ? h2[0] : 0;
+    BS_TRY(P.edge_u.alloc(8 * ((size_t)EO + 1), s));
+    BS_TRY(P.edge_v.alloc(8 * ((size_t)EO + 1), s));
+    BS_TRY(P.edge_score.alloc(4 * ((size_t)EO + 1), s));
+    if (E)
+        BS_LAUNCH(k_compact_edges, cdiv(E, 256), 256, 0, s, owned.as<uint8_t>(), oscan.as<uint32_t>(), E, ou.as<uint64_t>(),
+                  ov.as<uint64_t>(), os.as<float>(), P.edge_u.as<uint64_t>(), P.edge_v.as<uint64_t>(), P.edge_score.as<float>());
+    P.n_edges = EO;
+    if (g_debug) {
+        // everything the parity tests inspect: all per-block edges (creation order) with statistics and
+        // scores, and the merge histories
+        keep_debug2(P, "s2_ebase", ebase, 4, nown + 1);
+        keep_debug2(P, "s2_eu", ou, 8, E);
+        keep_debug2(P, "s2_ev", ov, 8, E);
+        keep_debug2(P, "s2_escore", os, 4, E);
+        keep_debug2(P, "s2_esum", esum, 8, E);
+        keep_debug2(P, "s2_ecnt", ecnt, 4, E);
+        keep_debug2(P, "s2_owned", owned, 1, E);
+        keep_debug2(P, "s2_ha", ha, 4, Vtot);
+        keep_debug2(P, "s2_hb", hbb, 4, Vtot);
+        keep_debug2(P, "s2_hs", hs, 4, Vtot);
+        keep_debug2(P, "s2_nmerges", nmerges, 4, nown);
+        keep_debug2(P, "s2_counters", counters, 4, 3 * nown);
+        std::vector<uint32_t> vb(nown);
+        for (int i = 0; i < nown; i++) vb[i] = hb[i].vbase;
+        DevBuf dvb;
+        BS_TRY(dvb.alloc(4 * nown, s));
+        BS_CUDA(cudaMemcpyAsync(dvb.p, vb.data(), 4 * nown, cudaMemcpyHostToDevice, s));
+        BS_CUDA(cudaStreamSynchronize(s));
+        keep_debug2(P, "s2_vbase", dvb, 4, nown);
+    }
+    BS_CUDA(cudaGetLastError());
+    return BS_OK;
+}
+
+int stage2_run(Plan &P, const void *affs, const uint64_t *frags, cudaStream_t s) {
+    g_prof.reset();
+    int mult = 1;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        bool ovf = false;
+        int rc = P.cfg.aff_dtype == BS_DTYPE_U8 ? stage2_impl<uint8_t>(P, affs, frags, mult, s, &ovf)
+                                                : stage2_impl<float>(P, affs, frags, mult, s, &ovf);
+        if (rc != BS_OK) return rc;
+        if (!ovf) {
+            g_prof.finish(s);
+            return BS_OK;
+        }
+        mult *= 4;
+    }
+    set_error("stage2: RAG hash table overflow after 4 attempts");
+    return BS_ERR_OVERFLOW;
+}
+
+}  // namespace bs

@@ -1,0 +1,89 @@
+// Stage 3: global thresholded connected components over the fragment graph, LUT, relabel.
+//
+// Replaces funlib.segment.graphs.impl.connected_components (post/watershed.py:177-182, U7: edges
+// with score <= threshold, float32 compare), volara LUT + Relabel (post/watershed.py:187-202).
+#include "geom.h"
+
+namespace bs {
+
+static constexpr uint32_t NONE32 = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t find_sorted(const uint64_t *__restrict__ keys, uint32_t n, uint64_t id) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (keys[mid] < id)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return (lo < n && keys[lo] == id) ? lo : NONE32;
+}
+
+__global__ void k_iota(uint32_t *p, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+__global__ void k_cc_union(const uint64_t *__restrict__ nodes, uint32_t n, const uint64_t *__restrict__ eu,
+                           const uint64_t *__restrict__ ev, const float *__restrict__ scores, size_t m, float thr,
+                           uint32_t *parent) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    if (scores && !(scores[e] <= thr)) return;   // NaN (merge_score NULL) never passes
+    uint32_t a = find_sorted(nodes, n, eu[e]), b = find_sorted(nodes, n, ev[e]);
+    if (a == NONE32 || b == NONE32 || a == b) return;
+    uf_union(parent, a, b);
+}
+
+__global__ void k_cc_flatten(const uint64_t *__restrict__ nodes, uint32_t n, const uint32_t *parent, uint64_t *__restrict__ comp) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) comp[i] = nodes[uf_find(parent, i)];
+}
+
+int connected_components(const uint64_t *nodes, int64_t n, const uint64_t *eu, const uint64_t *ev, const float *scores,
+                         int64_t m, float thr, uint64_t *comp, cudaStream_t s) {
+    BS_ARG(n >= 0 && n < (1LL << 32) - 1 && m >= 0, "bs_connected_components: bad sizes");
+    if (n == 0) return BS_OK;
+    DevBuf parent;
+    BS_TRY(parent.alloc(4 * (size_t)n, s));
+    BS_LAUNCH(k_iota, cdiv(n, 256), 256, 0, s, parent.as<uint32_t>(), (uint32_t)n);
+    if (m) BS_LAUNCH(k_cc_union, cdiv(m, 256), 256, 0, s, nodes, (uint32_t)n, eu, ev, scores, (size_t)m, thr, parent.as<uint32_t>());
+    BS_LAUNCH(k_cc_flatten, cdiv(n, 256), 256, 0, s, nodes, (uint32_t)n, parent.as<uint32_t>(), comp);
+    BS_CUDA(cudaGetLastError());
+    return BS_OK;
+}
+
+// generic LUT relabel (volara Relabel / funlib replace_values): ids absent from the LUT are unchanged.
+// Neighbouring voxels mostly carry the same id: the previous hit is reused before searching.
+__global__ void __launch_bounds__(256) k_relabel(const uint64_t *__restrict__ frags, size_t n, const uint64_t *__restrict__ keys,
+                                                 const uint64_t *__restrict__ vals, uint32_t k, uint64_t *__restrict__ seg) {
+    uint64_t last_id = 0, last_val = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t id = frags[i];
+        uint64_t out = id;
+        if (id != 0) {
+            if (id == last_id)
+                out = last_val;
+            else {
+                uint32_t j = find_sorted(keys, k, id);
+                if (j != NONE32) out = vals[j];
+                last_id = id;
+                last_val = out;
+            }
+        }
+        seg[i] = out;
+    }
+}
+
+int relabel(const uint64_t *frags, int64_t n, const uint64_t *keys, const uint64_t *vals, int64_t k, uint64_t *seg,
+            cudaStream_t s) {
+    BS_ARG(n >= 0 && k >= 0 && k < (1LL << 32) - 1, "bs_relabel: bad sizes");
+    if (n == 0) return BS_OK;
+    unsigned grid = (unsigned)std::min<size_t>(cdiv(n, 256), 148 * 16 * 8);
+    BS_LAUNCH(k_relabel, grid, 256, 0, s, frags, (size_t)n, keys, vals, (uint32_t)k, seg);
+    BS_CUDA(cudaGetLastError());
+    return BS_OK;
+}
+
+}  // namespace bs

@@ -1,0 +1,260 @@
+"""ctypes binding of libbsnative.so (the C ABI declared in include/bsnative.h).
+
+The library is built in-tree by ``bootstrapper_b200/csrc/build.py`` (``__graft_entry__.build()``).
+There is no CPU fallback: if the shared library is missing, or a call is made without a CUDA
+device, this module raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbsnative.so")
+
+BS_DTYPE_U8, BS_DTYPE_F32 = 0, 1
+
+
+class BsError(RuntimeError):
+    pass
+
+
+class WsConfig(C.Structure):
+    """bs_ws_config (include/bsnative.h)."""
+    _fields_ = [
+        ("vol_shape", C.c_int32 * 3), ("roi_offset", C.c_int32 * 3), ("roi_shape", C.c_int32 * 3),
+        ("block_size", C.c_int32 * 3), ("context", C.c_int32 * 3),
+        ("aff_dtype", C.c_int32), ("n_channels", C.c_int32), ("fragments_in_xy", C.c_int32),
+        ("min_seed_distance", C.c_int32), ("remove_debris", C.c_int32), ("queue_bins", C.c_int32),
+        ("keep_cheaper", C.c_int32), ("crop_relabel", C.c_int32), ("block_begin", C.c_int32),
+        ("block_end", C.c_int32), ("filter_fragments", C.c_double), ("max_batch_voxels", C.c_int64),
+    ]
+
+
+EXPORTS = [
+    "bs_last_error", "bs_launch_count", "bs_version", "bs_plan_create", "bs_plan_destroy", "bs_plan_num_blocks",
+    "bs_plan_block_info", "bs_stage1_fragments", "bs_stage1_num_nodes", "bs_stage1_get_nodes",
+    "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_stage2_agglomerate", "bs_stage2_num_edges",
+    "bs_stage2_get_edges", "bs_connected_components", "bs_relabel", "bs_watershed_from_affinities",
+    "bs_synth_affs", "bs_debug_fetch", "bs_set_debug", "bs_set_profiling", "bs_get_profile",
+    "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libbsnative.so; fail loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BsError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback for the bs segment hot path)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.bs_last_error.restype = C.c_char_p
+        _lib.bs_launch_count.restype = C.c_ulonglong
+        for name in EXPORTS:
+            getattr(_lib, name)
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise BsError(f"libbsnative error {rc}: {lib().bs_last_error().decode()}")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(t, dtype=None):
+    if not t.is_cuda:
+        raise BsError("libbsnative needs CUDA tensors (no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise BsError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise BsError("tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def _aff_dtype(t):
+    if t.dtype == torch.uint8:
+        return BS_DTYPE_U8
+    if t.dtype == torch.float32:
+        return BS_DTYPE_F32
+    raise BsError(f"affinities must be uint8 or float32, got {t.dtype}")
+
+
+def launch_count():
+    return int(lib().bs_launch_count())
+
+
+def set_debug(on):
+    _check(lib().bs_set_debug(C.c_int(1 if on else 0)))
+
+
+def set_profiling(on):
+    _check(lib().bs_set_profiling(C.c_int(1 if on else 0)))
+
+
+def get_profile():
+    names = C.create_string_buffer(4096)
+    ms = (C.c_float * 64)()
+    n = C.c_int(0)
+    _check(lib().bs_get_profile(names, 4096, ms, 64, C.byref(n)))
+    keys = names.value.decode().split(";")[: n.value]
+    return {k: float(ms[i]) for i, k in enumerate(keys)}
+
+
+class Plan:
+    """Geometry + results of one blockwise `bs segment --ws` run on this rank (bs_plan)."""
+
+    def __init__(self, vol_shape, block_size, context, aff_dtype, roi_offset=None, roi_shape=None, n_channels=3,
+                 fragments_in_xy=True, min_seed_distance=10, filter_fragments=0.1, remove_debris=64,
+                 queue_bins=256, keep_cheaper=True, block_begin=-1, block_end=-1, max_batch_voxels=0):
+        cfg = WsConfig()
+        roi_offset = roi_offset if roi_offset is not None else (0, 0, 0)
+        roi_shape = roi_shape if roi_shape is not None else vol_shape
+        for d in range(3):
+            cfg.vol_shape[d] = int(vol_shape[d])
+            cfg.roi_offset[d] = int(roi_offset[d])
+            cfg.roi_shape[d] = int(roi_shape[d])
+            cfg.block_size[d] = int(block_size[d])
+            cfg.context[d] = int(context[d])
+        cfg.aff_dtype = aff_dtype
+        cfg.n_channels = n_channels
+        cfg.fragments_in_xy = 1 if fragments_in_xy else 0
+        cfg.min_seed_distance = int(min_seed_distance)
+        cfg.remove_debris = int(remove_debris or 0)
+        cfg.queue_bins = int(queue_bins)
+        cfg.keep_cheaper = 1 if keep_cheaper else 0
+        cfg.crop_relabel = 1
+        cfg.block_begin = int(block_begin)
+        cfg.block_end = int(block_end)
+        cfg.filter_fragments = float(filter_fragments or 0.0)
+        cfg.max_batch_voxels = int(max_batch_voxels)
+        self.cfg = cfg
+        self.roi_shape = tuple(int(v) for v in roi_shape)
+        self._h = C.c_void_p()
+        _check(lib().bs_plan_create(C.byref(cfg), C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().bs_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    # ---- geometry
+    def num_blocks(self):
+        a, b = C.c_int64(), C.c_int64()
+        _check(lib().bs_plan_num_blocks(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def block_info(self):
+        n, _ = self.num_blocks()
+        ids = np.zeros(n, np.int64)
+        wo = np.zeros((n, 3), np.int32)
+        ws = np.zeros((n, 3), np.int32)
+        _check(lib().bs_plan_block_info(self._h, ids.ctypes.data_as(C.c_void_p), wo.ctypes.data_as(C.c_void_p),
+                                        ws.ctypes.data_as(C.c_void_p)))
+        return ids, wo, ws
+
+    # ---- stage 1
+    def fragments(self, affs, frags_out=None, mask=None):
+        """WatershedFrags over all owned blocks.  Returns the uint64 fragments tensor (roi_shape),
+        stored as torch.int64 bit patterns."""
+        if frags_out is None:
+            frags_out = torch.zeros(self.roi_shape, dtype=torch.int64, device=affs.device)
+        _check(lib().bs_stage1_fragments(self._h, _dev(affs), _dev(mask, torch.uint8) if mask is not None else None,
+                                         _dev(frags_out, torch.int64), _stream()))
+        return frags_out
+
+    def num_nodes(self):
+        n = C.c_int64()
+        _check(lib().bs_stage1_num_nodes(self._h, C.byref(n)))
+        return n.value
+
+    def nodes(self, device):
+        n = self.num_nodes()
+        ids = torch.empty(n, dtype=torch.int64, device=device)
+        pos = torch.empty((n, 3), dtype=torch.int32, device=device)
+        sizes = torch.empty(n, dtype=torch.int32, device=device)
+        _check(lib().bs_stage1_get_nodes(self._h, _dev(ids), _dev(pos), _dev(sizes), _stream()))
+        return ids, pos, sizes
+
+    def block_counts(self):
+        n, _ = self.num_blocks()
+        c = np.zeros(n, np.int64)
+        _check(lib().bs_stage1_block_counts(self._h, c.ctypes.data_as(C.c_void_p)))
+        return c
+
+    def set_block_counts(self, counts):
+        c = np.ascontiguousarray(counts, dtype=np.int64)
+        _check(lib().bs_stage1_set_block_counts(self._h, c.ctypes.data_as(C.c_void_p)))
+
+    # ---- stage 2
+    def agglomerate(self, affs, frags):
+        _check(lib().bs_stage2_agglomerate(self._h, _dev(affs), _dev(frags, torch.int64), _stream()))
+
+    def num_edges(self):
+        n = C.c_int64()
+        _check(lib().bs_stage2_num_edges(self._h, C.byref(n)))
+        return n.value
+
+    def edges(self, device):
+        n = self.num_edges()
+        u = torch.empty(n, dtype=torch.int64, device=device)
+        v = torch.empty(n, dtype=torch.int64, device=device)
+        s = torch.empty(n, dtype=torch.float32, device=device)
+        _check(lib().bs_stage2_get_edges(self._h, _dev(u), _dev(v), _dev(s), _stream()))
+        return u, v, s
+
+    # ---- debug
+    def debug_fetch(self, name, dtype):
+        n = C.c_int64()
+        _check(lib().bs_debug_fetch(self._h, name.encode(), None, C.byref(n)))
+        out = np.empty(n.value, dtype=dtype)
+        _check(lib().bs_debug_fetch(self._h, name.encode(), out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return out
+
+
+def connected_components(nodes, edges_u, edges_v, scores, threshold):
+    """funlib.segment.graphs.impl.connected_components on the device (post/watershed.py:182)."""
+    comp = torch.empty_like(nodes)
+    _check(lib().bs_connected_components(_dev(nodes, torch.int64), C.c_int64(nodes.numel()),
+                                         _dev(edges_u, torch.int64) if edges_u.numel() else None,
+                                         _dev(edges_v, torch.int64) if edges_v.numel() else None,
+                                         _dev(scores, torch.float32) if scores.numel() else None,
+                                         C.c_int64(edges_u.numel()), C.c_float(threshold), _dev(comp), _stream()))
+    return comp
+
+
+def relabel(frags, lut_keys, lut_vals, out=None):
+    """volara Relabel / replace_values on the device (post/watershed.py:192-202)."""
+    if out is None:
+        out = torch.empty_like(frags)
+    _check(lib().bs_relabel(_dev(frags, torch.int64), C.c_int64(frags.numel()),
+                            _dev(lut_keys, torch.int64) if lut_keys.numel() else None,
+                            _dev(lut_vals, torch.int64) if lut_vals.numel() else None,
+                            C.c_int64(lut_keys.numel()), _dev(out, torch.int64), _stream()))
+    return out
+
+
+def watershed_from_affinities(affs, fragments_in_xy, min_seed_distance):
+    """post/ws.py:38 on one device array.  Returns (fragments int64 tensor, n)."""
+    _, Z, Y, X = affs.shape
+    out = torch.zeros((Z, Y, X), dtype=torch.int64, device=affs.device)
+    n = C.c_int64()
+    _check(lib().bs_watershed_from_affinities(_dev(affs), C.c_int(_aff_dtype(affs)), Z, Y, X,
+                                              C.c_int(1 if fragments_in_xy else 0), C.c_int(int(min_seed_distance)),
+                                              _dev(out), None, C.byref(n), _stream()))
+    return out, n.value
+
+
+def synth_affs(shape, seed=0, dtype=torch.uint8, offset=(0, 0, 0), device="cuda"):
+    """Device generator, bit-identical to bootstrapper_b200.synth.synth_affs."""
+    out = torch.empty((3,) + tuple(shape), dtype=dtype, device=device)
+    sh = (C.c_int32 * 3)(*[int(v) for v in shape])
+    of = (C.c_int32 * 3)(*[int(v) for v in offset])
+    _check(lib().bs_synth_affs(_dev(out), C.c_int(_aff_dtype(out)), sh, of, None, C.c_uint64(seed), _stream()))
+    return out

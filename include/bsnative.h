@@ -1,0 +1,150 @@
+/*
+ * libbsnative — C ABI of the B200-native `bs segment --ws` hot path.
+ *
+ * This is the drop-in boundary: plain C types, device pointers owned by the caller
+ * (torch tensors on the Python side), a cudaStream_t passed as void*.  Every entry
+ * point returns 0 on success or a negative BS_ERR_* code; bs_last_error() gives the
+ * thread-local message.  There is NO CPU fallback anywhere behind this ABI.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to
+ * /root/reference/bootstrapper, upstream ucsdmanorlab/bootstrapper v0.3.2).
+ */
+#ifndef BSNATIVE_H
+#define BSNATIVE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BS_OK 0
+#define BS_ERR_CUDA (-1)
+#define BS_ERR_ARG (-2)
+#define BS_ERR_OVERFLOW (-3)
+#define BS_ERR_STATE (-4)
+
+#define BS_DTYPE_U8 0
+#define BS_DTYPE_F32 1
+
+/* Resolved `ws_params` + blockwise geometry (segment.py:11-23 DEFAULTS["ws"],
+ * post/watershed.py:28-98).  All coordinates are voxels, (z, y, x). */
+typedef struct bs_ws_config {
+    int32_t vol_shape[3];      /* spatial shape of the affinity array (C, Z, Y, X)          */
+    int32_t roi_offset[3];     /* task ROI inside the array (post/watershed.py:69-73)       */
+    int32_t roi_shape[3];
+    int32_t block_size[3];     /* block_shape (post/watershed.py:75-78)                      */
+    int32_t context[3];        /* context     (post/watershed.py:79-83)                      */
+    int32_t aff_dtype;         /* BS_DTYPE_U8 (normalised /255) or BS_DTYPE_F32              */
+    int32_t n_channels;        /* C >= 3; only [:3] is read (watershed_frags.py:117)         */
+    int32_t fragments_in_xy;   /* ws_params.fragments_in_xy                                  */
+    int32_t min_seed_distance; /* ws_params.min_seed_distance                                */
+    int32_t remove_debris;     /* ws_params.remove_debris (0 = off)                          */
+    int32_t queue_bins;        /* waterz discretize_queue: 256 blockwise (waterz_agglom.py:136) */
+    int32_t keep_cheaper;      /* oracle switch U6c (1 = default)                            */
+    int32_t crop_relabel;      /* 1 = blockwise path: crop + skimage.measure.label + global ids
+                                  (watershed_frags.py:216-224); 0 = raw watershed ids           */
+    int32_t block_begin;       /* this rank owns blocks [block_begin, block_end) of the      */
+    int32_t block_end;         /*   z-major block grid, in units of z-layers of blocks; -1/-1 = all */
+    double filter_fragments;   /* ws_params.filter_fragments (0 = off)                       */
+    int64_t max_batch_voxels;  /* scratch bound for stage 1 (0 = default)                    */
+} bs_ws_config;
+
+typedef struct bs_plan bs_plan;
+
+const char *bs_last_error(void);
+/* number of kernels launched by this library in this process (bench.py gpu_launches) */
+unsigned long long bs_launch_count(void);
+int bs_version(void);
+
+/* ---- plan: geometry of one `bs segment --ws -b` run ------------------------------- */
+/* replaces: volara BlockwiseTask geometry as used by WatershedFrags / WaterzAgglom
+ * (post/blockwise/watershed_frags.py:75-96, waterz_agglom.py:77-96) + daisy block
+ * enumeration (blockwise.py:31-62). */
+int bs_plan_create(const bs_ws_config *cfg, bs_plan **out);
+void bs_plan_destroy(bs_plan *p);
+int bs_plan_num_blocks(const bs_plan *p, int64_t *n_total, int64_t *n_owned);
+/* per block (all blocks of the task, ascending daisy block id): block_id (cantor number),
+ * write offset[3], write shape[3]; arrays of n_total entries (host pointers). */
+int bs_plan_block_info(const bs_plan *p, int64_t *block_id, int32_t *write_offset, int32_t *write_shape);
+
+/* ---- stage 1: fragments ------------------------------------------------------------
+ * replaces: WatershedFrags.process_block for every owned block
+ * (post/blockwise/watershed_frags.py:196-246), which itself calls
+ * watershed_from_affinities (post/ws.py:38-112), filter_avg_fragments (:148-156),
+ * skimage remove_small_objects (:188-192), skimage.measure.label (:222).
+ *   affs      device, (C, Z, Y, X) of cfg.aff_dtype, C-contiguous
+ *   mask      device, (Z, Y, X) uint8 or NULL (mask_dataset, watershed_frags.py:207-213)
+ *   frags_out device, roi_shape uint64; owned blocks' write ROIs are written, the rest untouched
+ */
+int bs_stage1_fragments(bs_plan *p, const void *affs, const uint8_t *mask, uint64_t *frags_out, void *stream);
+/* RAG nodes written by stage 1 (watershed_frags.py:230-246): id, position (voxels, write
+ * offset + truncated centre of mass), size.  Host or device destination pointers. */
+int bs_stage1_num_nodes(const bs_plan *p, int64_t *n);
+int bs_stage1_get_nodes(const bs_plan *p, uint64_t *ids, int32_t *pos_zyx, uint32_t *sizes, void *stream);
+/* per-block fragment counts of the owned blocks (n_total entries, 0 for blocks not owned) */
+int bs_stage1_block_counts(const bs_plan *p, int64_t *counts);
+/* multi-GPU: install the fragment counts of ALL blocks (after an all-gather) so that
+ * stage 2 can number halo fragments of neighbouring ranks. */
+int bs_stage1_set_block_counts(bs_plan *p, const int64_t *counts);
+
+/* ---- stage 2: RAG extraction + waterz agglomeration + merge-tree scores ------------
+ * replaces: WaterzAgglom.process_block for every owned block
+ * (post/blockwise/waterz_agglom.py:106-170): funlib.segment relabel (:116),
+ * waterz.agglomerate(thresholds=[0,1], discretize_queue=256, merge history + region
+ * graph) (:131-151), MergeTree replay + LCA query (:153-168, post/merge_tree.py),
+ * write_graph ownership (:170).
+ *   frags     device, roi_shape uint64 (the stage-1 output incl. neighbour ranks' halo)
+ */
+int bs_stage2_agglomerate(bs_plan *p, const void *affs, const uint64_t *frags, void *stream);
+int bs_stage2_num_edges(const bs_plan *p, int64_t *n);
+/* edges persisted by the owned blocks: u < v (fragment ids), merge_score (NaN = NULL) */
+int bs_stage2_get_edges(const bs_plan *p, uint64_t *u, uint64_t *v, float *score, void *stream);
+
+/* ---- stage 3: global thresholded connected components + relabel --------------------
+ * replaces: funlib.segment.graphs.impl.connected_components (post/watershed.py:182),
+ * volara LUT (post/watershed.py:187-188) and volara Relabel (post/watershed.py:192-202).
+ *   nodes (n) uint64 ascending, edges_u/v (m), scores (m, NaN skipped), all device
+ *   components_out (n) uint64 device: component id = smallest node id of the component
+ */
+int bs_connected_components(const uint64_t *nodes, int64_t n, const uint64_t *edges_u, const uint64_t *edges_v,
+                            const float *scores, int64_t m, float threshold, uint64_t *components_out,
+                            void *stream);
+/* seg[i] = lut_vals[k] if frags[i] == lut_keys[k] else frags[i]; lut_keys ascending */
+int bs_relabel(const uint64_t *frags, int64_t n_vox, const uint64_t *lut_keys, const uint64_t *lut_vals,
+               int64_t n_lut, uint64_t *seg_out, void *stream);
+
+/* ---- post/ws.py plug point ----------------------------------------------------------
+ * replaces: watershed_from_affinities(affs, max_affinity_value, fragments_in_xy,
+ * return_seeds, min_seed_distance) (post/ws.py:38-112) on one in-memory array.
+ *   affs (3, Z, Y, X) u8 (max_affinity_value 255) or f32 (1.0); frags_out (Z,Y,X) uint64;
+ *   seeds_out optional (NULL).  n_out (host) = number of fragment ids used (max id).
+ */
+int bs_watershed_from_affinities(const void *affs, int aff_dtype, int Z, int Y, int X, int fragments_in_xy,
+                                 int min_seed_distance, uint64_t *frags_out, uint64_t *seeds_out,
+                                 int64_t *n_out, void *stream);
+
+/* ---- test / bench harness (not part of the reference's path) -------------------------
+ * seeded block-addressable synthetic affinities (same arithmetic as
+ * bootstrapper_b200/synth.py), written for region [offset, offset+shape) of a volume. */
+int bs_synth_affs(void *out, int aff_dtype, const int32_t *shape, const int32_t *offset, const int32_t *vol_shape,
+                  uint64_t seed, void *stream);
+/* debug: copy a named scratch array of the last stage-1 batch / stage-2 run to the host
+ * (returns element count via n_out if dst is NULL). */
+int bs_debug_fetch(const bs_plan *p, const char *name, void *dst_host, int64_t *n_out);
+/* per-stage device times (ms) of the last run, measured with CUDA events on the caller's
+ * stream when enabled via bs_set_profiling(1). names/values up to cap entries. */
+int bs_set_debug(int on);
+/* test hooks for the device primitives (exclusive scan, stable LSD radix sort) */
+int bs_dbg_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *total_dev, void *stream);
+int bs_dbg_scan_u8(const uint8_t *in, uint32_t *out, int64_t n, uint32_t *total_dev, void *stream);
+int bs_dbg_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, int64_t n, int bit_lo,
+                      int bit_hi, void *stream);
+int bs_set_profiling(int on);
+int bs_get_profile(char *names_out, int names_cap, float *ms_out, int cap, int *n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSNATIVE_H */
