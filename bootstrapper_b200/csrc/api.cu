@@ -39,8 +39,23 @@ int bs_set_debug(int on) {
     return BS_OK;
 }
 
+// keep freed scratch in the stream-ordered pool instead of returning it to the driver at every sync
+static void init_mempool() {
+    static bool done = false;
+    if (done) return;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done = true;
+}
+
 int bs_plan_create(const bs_ws_config *cfg, bs_plan **out) {
     BS_ARG(cfg && out, "bs_plan_create: null argument");
+    init_mempool();
     for (int d = 0; d < 3; d++)
         BS_ARG(cfg->context[d] <= cfg->block_size[d], "bs_plan_create: context larger than the block is not supported");
     Plan *p = nullptr;
@@ -74,6 +89,21 @@ int bs_plan_block_info(const bs_plan *p, int64_t *block_id, int32_t *write_offse
             if (write_shape) write_shape[3 * i + d] = bl[i].ws[d];
         }
     }
+    return BS_OK;
+}
+
+int bs_plan_set_owned(bs_plan *p, const int32_t *indices, int64_t n) {
+    BS_ARG(p && (n == 0 || indices), "bs_plan_set_owned: null argument");
+    Plan &P = *p->p;
+    std::vector<int> own;
+    for (auto &b : P.blocks) b.owned = 0;
+    for (int64_t i = 0; i < n; i++) {
+        BS_ARG(indices[i] >= 0 && (size_t)indices[i] < P.blocks.size(), "bs_plan_set_owned: block index out of range");
+        P.blocks[indices[i]].owned = 1;
+    }
+    for (size_t i = 0; i < P.blocks.size(); i++)
+        if (P.blocks[i].owned) own.push_back((int)i);
+    P.owned = own;
     return BS_OK;
 }
 
@@ -223,6 +253,16 @@ int bs_dbg_scan_u8(const uint8_t *in, uint32_t *out, int64_t n, uint32_t *total_
 int bs_dbg_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, int64_t n, int bit_lo,
                       int bit_hi, void *stream) {
     return radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, (size_t)n, bit_lo, bit_hi, (cudaStream_t)stream);
+}
+
+int bs_release_scratch(void) {
+    int dev = 0;
+    BS_CUDA(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    BS_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    BS_CUDA(cudaDeviceSynchronize());
+    BS_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return BS_OK;
 }
 
 int bs_set_profiling(int on) {

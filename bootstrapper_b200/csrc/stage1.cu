@@ -624,7 +624,8 @@ __device__ __forceinline__ bool frag_keep(ACC sum, uint32_t cnt, double ff, int 
     return true;
 }
 
-// cpar (tile-local parent, only write-region pixels participate): own index if kept else NONE32
+// cpar (tile-local parent, only write-region pixels participate): NONE32 if dropped, else the start of
+// the pixel's row run of equal labels inside its warp chunk (pre-linked rows keep union-find chains short)
 template <typename ACC>
 __global__ void __launch_bounds__(256) k_crop_init(const Tile *__restrict__ tiles, const uint32_t *__restrict__ lab,
                                                    const ACC *__restrict__ fsum, const uint32_t *__restrict__ fcnt,
@@ -632,24 +633,41 @@ __global__ void __launch_bounds__(256) k_crop_init(const Tile *__restrict__ tile
     const Tile t = tiles[blockIdx.y];
     const int W = t.W, H = t.H;
     const long long HW = (long long)H * W, npix = (long long)t.D * HW;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    auto kept_label = [&](long long i) -> uint32_t {
         int x = (int)(i % W);
         int y = (int)((i / W) % H);
         int z = (int)(i / HW);
-        uint32_t v = NONE32;
         if (z >= t.wz && z < t.wz + t.wD && y >= t.wy && y < t.wy + t.wH && x >= t.wx && x < t.wx + t.wW) {
             uint32_t l = lab[t.base + i];
             if (l && l < CLAIM) {
                 bool keep = true;
                 if (ff > 0.0 || rd > 0) keep = frag_keep<ACC>(fsum[t.base + l - 1], fcnt[t.base + l - 1], ff, rd, is_u8 != 0);
-                if (keep) v = (uint32_t)i;
+                if (keep) return l;
             }
         }
-        cpar[t.base + i] = v;
+        return 0;
+    };
+    for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < npix; i0 += (long long)gridDim.x * blockDim.x) {
+        long long i = i0 + threadIdx.x;
+        uint32_t l = i < npix ? kept_label(i) : 0;
+        uint32_t ll = __shfl_up_sync(FULL, l, 1);
+        if (lane == 0) ll = (l && i > 0) ? kept_label(i - 1) : 0;
+        bool sl = l && (i % W) != 0 && ll == l;
+        unsigned startbits = __ballot_sync(FULL, l && !sl);
+        if (i < npix) {
+            uint32_t v = NONE32;
+            if (l) {
+                unsigned m = startbits & (FULL >> (31 - lane));
+                v = m ? (uint32_t)(i - (lane - (31 - __clz(m)))) : (uint32_t)(i - lane);
+            }
+            cpar[t.base + i] = v;
+        }
     }
 }
 
-// union with the raster-preceding neighbours of the full (8 / 26) neighbourhood carrying the same label
+// union with the raster-preceding neighbours of the full (8 / 26) neighbourhood carrying the same label;
+// links implied by row adjacency of equal labels are skipped
 __global__ void __launch_bounds__(256) k_crop_union(const Tile *__restrict__ tiles, const uint32_t *__restrict__ lab,
                                                     uint32_t *__restrict__ cpar) {
     const Tile t = tiles[blockIdx.y];
@@ -662,17 +680,35 @@ __global__ void __launch_bounds__(256) k_crop_union(const Tile *__restrict__ til
         int x = (int)(i % W);
         int y = (int)((i / W) % H);
         int z = (int)(i / HW);
-        uint32_t l = ll[i];
-        for (int dz = -1; dz <= 0; dz++)
-            for (int dy = -1; dy <= 1; dy++)
-                for (int dx = -1; dx <= 1; dx++) {
-                    if (dz == 0 && (dy > 0 || (dy == 0 && dx >= 0))) continue;
-                    int zz = z + dz, yy = y + dy, xx = x + dx;
-                    if (zz < 0 || yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-                    long long j = (long long)zz * HW + (long long)yy * W + xx;
-                    if (ll[j] != l || __ldcg(&pp[j]) == NONE32) continue;
-                    uf_union(pp, (uint32_t)i, (uint32_t)j);
-                }
+        const uint32_t l = ll[i];
+        auto same = [&](long long j) -> bool { return ll[j] == l && __ldcg(&pp[j]) != NONE32; };
+        const bool left = x > 0 && same(i - 1);
+        // row link across a warp-chunk boundary (inside a chunk k_crop_init linked the run already)
+        if (left && (i & 31) == 0) uf_union(pp, (uint32_t)i, (uint32_t)(i - 1));
+        if (y > 0) {
+            const bool up = same(i - W);
+            if (up) {
+                if (!(left && same(i - W - 1))) uf_union(pp, (uint32_t)i, (uint32_t)(i - W));
+            } else {
+                if (x > 0 && !left && same(i - W - 1)) uf_union(pp, (uint32_t)i, (uint32_t)(i - W - 1));
+                if (x + 1 < W && same(i - W + 1) && !same(i + 1)) uf_union(pp, (uint32_t)i, (uint32_t)(i - W + 1));
+            }
+        }
+        if (z > 0) {
+            const long long b = i - HW;
+            if (same(b)) {
+                if (!(left && same(b - 1))) uf_union(pp, (uint32_t)i, (uint32_t)b);
+            } else {
+                for (int dy = -1; dy <= 1; dy++)
+                    for (int dx = -1; dx <= 1; dx++) {
+                        if (dy == 0 && dx == 0) continue;
+                        int yy = y + dy, xx = x + dx;
+                        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                        long long j = b + (long long)dy * W + dx;
+                        if (same(j)) uf_union(pp, (uint32_t)i, (uint32_t)j);
+                    }
+            }
+        }
     }
 }
 
@@ -1067,7 +1103,7 @@ int stage1_run(Plan &P, const void *affs, const uint8_t *mask, uint64_t *frags_o
     A.Z = cfg.vol_shape[0], A.Y = cfg.vol_shape[1], A.X = cfg.vol_shape[2];
     long long cap = cfg.max_batch_voxels > 0 ? cfg.max_batch_voxels : (1LL << 30);
     cap = std::min(cap, (1LL << 31) - 1);
-    std::fill(P.block_count.begin(), P.block_count.end(), 0);
+    for (int bi : P.owned) P.block_count[bi] = 0;
     P.counts_global = false;
     P.n_nodes = 0;
     g_prof.reset();

@@ -34,11 +34,11 @@ class WsConfig(C.Structure):
 
 EXPORTS = [
     "bs_last_error", "bs_launch_count", "bs_version", "bs_plan_create", "bs_plan_destroy", "bs_plan_num_blocks",
-    "bs_plan_block_info", "bs_stage1_fragments", "bs_stage1_num_nodes", "bs_stage1_get_nodes",
+    "bs_plan_block_info", "bs_plan_set_owned", "bs_stage1_fragments", "bs_stage1_num_nodes", "bs_stage1_get_nodes",
     "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_stage2_agglomerate", "bs_stage2_num_edges",
     "bs_stage2_get_edges", "bs_connected_components", "bs_relabel", "bs_watershed_from_affinities",
     "bs_synth_affs", "bs_debug_fetch", "bs_set_debug", "bs_set_profiling", "bs_get_profile",
-    "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
+    "bs_release_scratch", "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
 ]
 
 _lib = None
@@ -92,6 +92,10 @@ def launch_count():
 
 def set_debug(on):
     _check(lib().bs_set_debug(C.c_int(1 if on else 0)))
+
+
+def release_scratch():
+    _check(lib().bs_release_scratch())
 
 
 def set_profiling(on):
@@ -158,6 +162,10 @@ class Plan:
         _check(lib().bs_plan_block_info(self._h, ids.ctypes.data_as(C.c_void_p), wo.ctypes.data_as(C.c_void_p),
                                         ws.ctypes.data_as(C.c_void_p)))
         return ids, wo, ws
+
+    def set_owned(self, indices):
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        _check(lib().bs_plan_set_owned(self._h, idx.ctypes.data_as(C.c_void_p), C.c_int64(idx.size)))
 
     # ---- stage 1
     def fragments(self, affs, frags_out=None, mask=None):

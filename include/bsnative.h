@@ -69,6 +69,11 @@ int bs_plan_num_blocks(const bs_plan *p, int64_t *n_total, int64_t *n_owned);
  * write offset[3], write shape[3]; arrays of n_total entries (host pointers). */
 int bs_plan_block_info(const bs_plan *p, int64_t *block_id, int32_t *write_offset, int32_t *write_shape);
 
+/* restrict the blocks this plan processes to the given plan indices (ascending block-id order, as
+ * returned by bs_plan_block_info): one daisy block = one process_block(block) call
+ * (watershed_frags.py:248-258), or one rank's slab. */
+int bs_plan_set_owned(bs_plan *p, const int32_t *indices, int64_t n);
+
 /* ---- stage 1: fragments ------------------------------------------------------------
  * replaces: WatershedFrags.process_block for every owned block
  * (post/blockwise/watershed_frags.py:196-246), which itself calls
@@ -136,6 +141,8 @@ int bs_debug_fetch(const bs_plan *p, const char *name, void *dst_host, int64_t *
 /* per-stage device times (ms) of the last run, measured with CUDA events on the caller's
  * stream when enabled via bs_set_profiling(1). names/values up to cap entries. */
 int bs_set_debug(int on);
+/* return the library's cached scratch memory (stream-ordered pool) to the driver */
+int bs_release_scratch(void);
 /* test hooks for the device primitives (exclusive scan, stable LSD radix sort) */
 int bs_dbg_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *total_dev, void *stream);
 int bs_dbg_scan_u8(const uint8_t *in, uint32_t *out, int64_t n, uint32_t *total_dev, void *stream);
