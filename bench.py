@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""Headline benchmark: voxels/s, affinities -> segmentation (BASELINE.json metric), blockwise ws path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): synthetic CREMI-sized uint8 affinities 3x(125,1250,1250) per GPU,
+block_shape (25,250,250), context (3,31,31) (the reference's //8 rule), ws defaults, 3 thresholds.
+N > 1: weak scaling — the volume is N slabs of 125 planes stacked in z, one slab per rank (one process per
+GPU); ranks exchange fragment halos and RAG edges (bootstrapper_b200/sharded.py).
+A step = one pass of the whole path over one volume: stage 1 fragments, stage 2 RAG + agglomeration scores,
+stage 3 thresholded CC + relabel for every threshold.
+
+`value`   device-timed (CUDA events, max over ranks), affinities already resident in HBM.
+`e2e`     the same through the public API with HOST buffers: pinned host affinities -> device, the path,
+          fragments + all segmentations -> pinned host memory, copies inside the timed region.
+`--impl reference` times the CPU oracle (a port of the reference path; the reference itself cannot be
+          installed here) with one process per block on all host cores, on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHAPE = (125, 1250, 1250)
+BLOCK = (25, 250, 250)
+CONTEXT = (3, 31, 31)
+THRESHOLDS = [0.2, 0.35, 0.5]
+BYTES_PER_VOXEL = 3 * 1 + 8 + 8 * len(THRESHOLDS)      # u8 affs in, u64 fragments + T u64 segmentations out
+CPU_SAMPLE = (75, 750, 750)                            # 27 blocks of the same geometry
+METRIC = "voxels/sec affs->segmentation (blockwise ws, fragments + RAG + agglomeration at 3 thresholds)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_oracle_rate(sample_shape, workers=None, seed=0):
+    """voxels/s of the CPU oracle (one process per block) on a bounded sample of the workload"""
+    from bootstrapper_b200.synth import synth_affs
+    from oracle.parallel import waterz_pipeline_parallel
+    affs = synth_affs(sample_shape, seed=seed)
+    tm = {}
+    waterz_pipeline_parallel(affs, {"thresholds": THRESHOLDS}, block_size=BLOCK, context=CONTEXT, timings=tm, workers=workers)
+    return float(np.prod(sample_shape)) / tm["total"], tm
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (kind 'port')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    sample = (50, 500, 500) if args.quick else CPU_SAMPLE
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_oracle_rate((25, 250, 250), cores)
+    rates, ms = [], []
+    for _ in range(max(1, args.steps)):
+        r, tm = cpu_oracle_rate(sample, cores)
+        rates.append(r)
+        ms.append(tm["total"] * 1e3)
+    v = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "CREMI-sized synthetic uint8 affinities 3x(125,1250,1250), block (25,250,250), context (3,31,31), "
+                               "ws defaults, thresholds [0.2,0.35,0.5]", "l2": "inputs larger than L2"},
+        "cpu_baseline": {"value": v, "unit": "voxels/s", "cores": cores, "kind": "port",
+                         "sample": f"sub-volume {sample} of the workload ({int(np.prod(sample) / np.prod(BLOCK))} blocks, same "
+                                   "block geometry), one process per block"},
+        "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from bootstrapper_b200 import native
+    from bootstrapper_b200.sharded import ShardedSegmenter
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    shape = (SHAPE[0] * world, SHAPE[1], SHAPE[2]) if not args.quick else (50 * world, 500, 500)
+    params = {"thresholds": THRESHOLDS}
+    seg = ShardedSegmenter(shape, BLOCK, CONTEXT, params, rank=rank, world=world, device=dev)
+    affs = seg.synth_local_affs(seed=0)                    # this rank's slab + z halo, generated on the device
+    torch.cuda.synchronize()
+    V_total = float(np.prod(shape))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    native.set_profiling(True)
+    for _ in range(args.warmup):
+        seg.run(affs)
+    barrier()
+    l0 = native.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof_acc = {}
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        seg.run(affs)
+        for k, v in seg.last_profile.items():
+            prof_acc[k] = prof_acc.get(k, 0.0) + v
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = native.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = V_total / (ms_step * 1e-3)
+
+    # ---- end to end through the public API with host buffers (pinned), copies inside the timed region
+    host_affs = torch.empty(affs.shape, dtype=affs.dtype, pin_memory=True)
+    host_affs.copy_(affs)
+    own_shape = seg.own_shape
+    host_out = [torch.empty(own_shape, dtype=torch.int64, pin_memory=True) for _ in range(1 + len(THRESHOLDS))]
+    e2e_steps = max(1, min(args.steps, 3))
+    seg.run_host(host_affs, host_out)                      # warm-up
+    barrier()
+    ev0.record()
+    for _ in range(e2e_steps):
+        seg.run_host(host_affs, host_out)
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / e2e_steps
+    h2d = host_affs.numel() * host_affs.element_size()
+    d2h = sum(o.numel() * 8 for o in host_out)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        steps = args.steps
+        prof = {k: v / steps for k, v in prof_acc.items()}
+        dom = max(prof, key=prof.get)
+        # algorithmic bytes of one launch of the dominant kernel = 35 B/voxel x the voxels this rank's launch covers
+        alg_bytes = BYTES_PER_VOXEL * float(np.prod(seg.own_shape))
+        achieved = alg_bytes / (prof[dom] * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(dom)
+        cpu = None
+        if not args.no_cpu:
+            sample = (50, 500, 500) if args.quick else CPU_SAMPLE
+            r, tm = cpu_oracle_rate(sample)
+            cpu = {"value": r, "unit": "voxels/s", "cores": tm["workers"], "kind": "port",
+                   "sample": f"sub-volume {sample} of the workload ({tm['blocks']} blocks, same block geometry), "
+                             f"one process per block, {tm['total']:.1f} s"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": f"CREMI-sized synthetic uint8 affinities 3x{shape} ({world} z-slab(s) of {SHAPE}), "
+                                   "block (25,250,250), context (3,31,31), ws defaults, thresholds [0.2,0.35,0.5]",
+                       "l2": "inputs larger than L2 (586 MB affinities, 6.2 GB outputs per step per GPU)",
+                       "parity": "bit-exact vs oracle (seed_tie=index, stats_mode=canonical), tests/test_gpu_parity.py"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": prof[dom],
+                         "whole_path_frac": (BYTES_PER_VOXEL * V_total / world / (ms_step * 1e-3) / 1e9) / peak},
+            "stage_ms": {k: round(v, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])},
+            "cpu_baseline": cpu,
+            "e2e": {"value": V_total / (e2e_ms * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--quick", action="store_true", help="small volume (smoke / CI), not a valid bench number")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -138,7 +138,7 @@ int bs_stage1_set_block_counts(bs_plan *p, const int64_t *counts) {
     BS_ARG(p && counts, "null argument");
     Plan &P = *p->p;
     for (size_t i = 0; i < P.blocks.size(); i++) {
-        if (P.blocks[i].owned && P.block_count[i] != counts[i]) {
+        if (P.blocks[i].owned && P.block_count[i] != 0 && P.block_count[i] != counts[i]) {
             set_error("bs_stage1_set_block_counts: counts of owned blocks differ from this rank's stage-1 result");
             return BS_ERR_STATE;
         }

@@ -41,6 +41,10 @@ int plan_build(const bs_ws_config &cfg, Plan **out) {
     BS_ARG(cfg.n_channels >= 3, "bs_plan_create: need at least 3 affinity channels");
     BS_ARG(cfg.min_seed_distance >= 1, "bs_plan_create: min_seed_distance must be >= 1");
     BS_ARG(cfg.queue_bins == 256 || cfg.queue_bins == 0, "bs_plan_create: queue_bins must be 0 or 256");
+    if (cfg.win_z > 0)
+        BS_ARG(cfg.roi_offset[0] == 0 && cfg.roi_shape[0] == cfg.vol_shape[0] && cfg.win_z0 >= 0 &&
+                   cfg.win_z0 + cfg.win_z <= cfg.vol_shape[0],
+               "bs_plan_create: a slab window needs roi to span all of z and the window inside the volume");
     Plan *p = new Plan();
     p->cfg = cfg;
     int nb[3];

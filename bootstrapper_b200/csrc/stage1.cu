@@ -38,7 +38,8 @@ static constexpr unsigned FULL = 0xFFFFFFFFu;
 struct AffView {
     const void *p;
     const uint8_t *mask;
-    int C, Z, Y, X;
+    int C, Z, Y, X;   // global volume shape (zero fill outside)
+    int z0, Zw;       // the array holds the global planes [z0, z0 + Zw) (multi-GPU slab window; else 0, Z)
 };
 
 // ------------------------------------------------------------------ affinity access
@@ -79,14 +80,14 @@ __global__ void __launch_bounds__(256) k_mask_rowdist(const Tile *__restrict__ t
     const Tile t = tiles[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rows = t.D * t.H, W = t.W, nw = (W + 31) >> 5;
-    const size_t nvol = (size_t)A.Z * A.Y * A.X;
+    const size_t nvol = (size_t)A.Zw * A.Y * A.X;
     const T *a = (const T *)A.p;
     bool anybg = false;
     for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
         int z = r / t.H, y = r - z * t.H;
         int gz = t.gz + z, gy = t.gy + y;
-        bool rowin = gz >= 0 && gz < A.Z && gy >= 0 && gy < A.Y;
-        size_t rowoff = rowin ? ((size_t)gz * A.Y + gy) * A.X : 0;
+        bool rowin = gz >= 0 && gz < A.Z && gy >= 0 && gy < A.Y && gz >= A.z0 && gz < A.z0 + A.Zw;
+        size_t rowoff = rowin ? ((size_t)(gz - A.z0) * A.Y + gy) * A.X : 0;
         long long pbase = t.base + (long long)r * W;
         for (int c = 0; c < nw; c++) {
             int x = c * 32 + lane;
@@ -576,7 +577,7 @@ __global__ void __launch_bounds__(256) k_fragstats(const Tile *__restrict__ tile
     const Tile t = tiles[blockIdx.y];
     const int W = t.W, H = t.H;
     const long long HW = (long long)H * W, npix = (long long)t.D * HW;
-    const size_t nvol = (size_t)A.Z * A.Y * A.X;
+    const size_t nvol = (size_t)A.Zw * A.Y * A.X;
     const T *a = (const T *)A.p;
     for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < npix; i0 += (long long)gridDim.x * blockDim.x) {
         long long i = i0 + threadIdx.x;
@@ -590,7 +591,7 @@ __global__ void __launch_bounds__(256) k_fragstats(const Tile *__restrict__ tile
                 int x = (int)(i % W);
                 int y = (int)((i / W) % H);
                 int z = (int)(i / HW);
-                size_t gi = ((size_t)(t.gz + z) * A.Y + (t.gy + y)) * A.X + (t.gx + x);
+                size_t gi = ((size_t)(t.gz + z - A.z0) * A.Y + (t.gy + y)) * A.X + (t.gx + x);
                 val = AffOps<T>::value(a, nvol, gi);
             }
         }
@@ -1059,7 +1060,7 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
         const unsigned gxw = (unsigned)std::min<long long>(std::max<long long>((maxw + 1023) / 1024, 1), 2048);
         dim3 gr(gxw, (unsigned)blks.size());
         BS_LAUNCH(k_finalize, gr, 256, 0, s, d_blks.as<BlkDev>(), croot.as<uint32_t>(), rank.as<uint32_t>(), P.nvox_block,
-                  cfg.roi_offset[0], cfg.roi_offset[1], cfg.roi_offset[2], cfg.roi_shape[1], cfg.roi_shape[2], frags_out,
+                  cfg.roi_offset[0] + (cfg.win_z > 0 ? cfg.win_z0 : 0), cfg.roi_offset[1], cfg.roi_offset[2], cfg.roi_shape[1], cfg.roi_shape[2], frags_out,
                   ncnt.as<uint32_t>(), nsum.as<unsigned long long>(), blk_first.as<uint32_t>());
     }
     // ---- grow the plan's node table
@@ -1101,6 +1102,8 @@ int stage1_run(Plan &P, const void *affs, const uint8_t *mask, uint64_t *frags_o
     A.mask = mask;
     A.C = cfg.n_channels;
     A.Z = cfg.vol_shape[0], A.Y = cfg.vol_shape[1], A.X = cfg.vol_shape[2];
+    A.z0 = cfg.win_z > 0 ? cfg.win_z0 : 0;
+    A.Zw = cfg.win_z > 0 ? cfg.win_z : cfg.vol_shape[0];
     long long cap = cfg.max_batch_voxels > 0 ? cfg.max_batch_voxels : (1LL << 30);
     cap = std::min(cap, (1LL << 31) - 1);
     for (int bi : P.owned) P.block_count[bi] = 0;

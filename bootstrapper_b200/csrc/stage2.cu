@@ -73,7 +73,7 @@ __device__ __forceinline__ unsigned long long aff_fixed<float>(float v) {
 template <typename T>
 __global__ void __launch_bounds__(256) k_rag_accumulate(const S2Blk *__restrict__ blks, const T *__restrict__ affs,
                                                         const uint64_t *__restrict__ frags, IdMap idm, int volZ, int volY,
-                                                        int volX, int roz, int roy, int rox, int rsz, int rsy, int rsx,
+                                                        int volX, int wz0, int roz, int roy, int rox, int rsz, int rsy, int rsx,
                                                         unsigned long long *hkeys, unsigned long long *hsum, uint32_t *hcnt,
                                                         uint32_t *hfirst, uint32_t *overflow) {
     const S2Blk &b = blks[blockIdx.y];
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) k_rag_accumulate(const S2Blk *__restrict_
             if (has) {
                 uint32_t lo = min(id1, id2), hi = max(id1, id2);
                 unsigned long long key = ((unsigned long long)lo << 32) | hi;
-                unsigned long long a = aff_fixed<T>(affs[(size_t)d * nvol + ((size_t)gz * volY + gy) * volX + gx]);
+                unsigned long long a = aff_fixed<T>(affs[(size_t)d * nvol + ((size_t)(gz - wz0) * volY + gy) * volX + gx]);
                 uint32_t fk = (uint32_t)(i * 3 + d);
                 unsigned peers = __match_any_sync(act, key);
                 int leader = __ffs(peers) - 1;
@@ -802,9 +802,10 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
     }
     {
         dim3 gr((unsigned)std::min<long long>(std::max<long long>((maxread + 1023) / 1024, 1), 4096), nown);
-        BS_LAUNCH((k_rag_accumulate<T>), gr, 256, 0, s, db, (const T *)affs, frags, idm, cfg.vol_shape[0], cfg.vol_shape[1],
-                  cfg.vol_shape[2], cfg.roi_offset[0], cfg.roi_offset[1], cfg.roi_offset[2], cfg.roi_shape[0],
-                  cfg.roi_shape[1], cfg.roi_shape[2], hkeys.as<unsigned long long>(), hsum.as<unsigned long long>(),
+        BS_LAUNCH((k_rag_accumulate<T>), gr, 256, 0, s, db, (const T *)affs, frags, idm, cfg.win_z > 0 ? cfg.win_z : cfg.vol_shape[0],
+                  cfg.vol_shape[1], cfg.vol_shape[2], cfg.win_z > 0 ? cfg.win_z0 : 0,
+                  cfg.roi_offset[0] + (cfg.win_z > 0 ? cfg.win_z0 : 0), cfg.roi_offset[1], cfg.roi_offset[2],
+                  cfg.win_z > 0 ? cfg.win_z : cfg.roi_shape[0], cfg.roi_shape[1], cfg.roi_shape[2], hkeys.as<unsigned long long>(), hsum.as<unsigned long long>(),
                   hcnt.as<uint32_t>(), hfirst.as<uint32_t>(), ovf.as<uint32_t>());
     }
     // ---- compaction + creation-order sort (host sync: number of edges)

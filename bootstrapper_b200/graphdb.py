@@ -1,0 +1,83 @@
+"""Fragment RAG store: SQLite file with the node / edge attributes the reference writes through
+volara's SQLite wrapper (post/watershed.py:104-113: edge_attrs={"merge_score": "float"}; nodes carry
+position and size, post/blockwise/watershed_frags.py:238-246).  Table layout follows
+funlib.persistence's SQLite graph provider as far as it can be recalled without its source
+(nodes: id, position_0..2, size; edges: u, v, merge_score) — SURVEY N1, unverified.
+PostgreSQL configs are rejected (no server / driver in this image).
+"""
+import os
+import sqlite3
+
+import numpy as np
+
+
+class SQLiteRag:
+    db_type = "sqlite"
+
+    def __init__(self, path, edge_attrs=None):
+        self.path = path
+        self.edge_attrs = edge_attrs or {"merge_score": "float"}
+
+    @property
+    def id(self):
+        return os.path.splitext(os.path.basename(self.path))[0]
+
+    def _con(self):
+        os.makedirs(os.path.dirname(os.path.abspath(self.path)), exist_ok=True)
+        return sqlite3.connect(self.path)
+
+    def init(self):
+        with self._con() as con:
+            con.execute("CREATE TABLE IF NOT EXISTS nodes (id INTEGER PRIMARY KEY, position_0 INTEGER, "
+                        "position_1 INTEGER, position_2 INTEGER, size INTEGER)")
+            con.execute("CREATE TABLE IF NOT EXISTS edges (u INTEGER, v INTEGER, merge_score REAL, PRIMARY KEY (u, v))")
+
+    def drop(self):
+        if os.path.exists(self.path):
+            os.remove(self.path)
+
+    def drop_edges(self):
+        if os.path.exists(self.path):
+            with self._con() as con:
+                con.execute("DROP TABLE IF EXISTS edges")
+
+    def write_nodes(self, ids, positions, sizes):
+        rows = zip(ids.astype(np.int64).tolist(), *[positions[:, d].tolist() for d in range(3)], sizes.tolist())
+        with self._con() as con:
+            con.executemany("INSERT OR REPLACE INTO nodes VALUES (?, ?, ?, ?, ?)", rows)
+
+    def write_edges(self, u, v, scores):
+        sc = [None if np.isnan(s) else float(s) for s in scores]
+        with self._con() as con:
+            con.executemany("INSERT OR REPLACE INTO edges VALUES (?, ?, ?)",
+                            zip(u.astype(np.int64).tolist(), v.astype(np.int64).tolist(), sc))
+
+    def read_graph(self):
+        """-> nodes (N,) uint64 ascending, edges (E,2) uint64, scores (E,) float32 (NaN = NULL)"""
+        with self._con() as con:
+            nodes = np.array([r[0] for r in con.execute("SELECT id FROM nodes ORDER BY id")], dtype=np.int64)
+            rows = list(con.execute("SELECT u, v, merge_score FROM edges"))
+        edges = np.array([(r[0], r[1]) for r in rows], dtype=np.int64).reshape(-1, 2)
+        scores = np.array([np.nan if r[2] is None else r[2] for r in rows], dtype=np.float32)
+        return nodes.view(np.uint64), edges.view(np.uint64), scores
+
+
+def open_db(db_config):
+    """post/watershed.py:104-113"""
+    if "db_file" in db_config:
+        return SQLiteRag(db_config["db_file"], edge_attrs={"merge_score": "float"})
+    raise NotImplementedError("PostgreSQL RAG stores are not available in this environment; use db_file (SQLite)")
+
+
+class LUT:
+    """volara.lut.LUT: `<path>.npz` with `fragment_segment_lut` = (2, N) uint64."""
+
+    def __init__(self, path):
+        self.path = path
+
+    def save(self, lut):
+        os.makedirs(os.path.dirname(os.path.abspath(self.path)), exist_ok=True)
+        np.savez_compressed(self.path + ".npz", fragment_segment_lut=np.asarray(lut, dtype=np.uint64))
+
+    def load(self):
+        return np.load(self.path + ".npz")["fragment_segment_lut"]

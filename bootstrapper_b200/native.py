@@ -28,7 +28,7 @@ class WsConfig(C.Structure):
         ("aff_dtype", C.c_int32), ("n_channels", C.c_int32), ("fragments_in_xy", C.c_int32),
         ("min_seed_distance", C.c_int32), ("remove_debris", C.c_int32), ("queue_bins", C.c_int32),
         ("keep_cheaper", C.c_int32), ("crop_relabel", C.c_int32), ("block_begin", C.c_int32),
-        ("block_end", C.c_int32), ("filter_fragments", C.c_double), ("max_batch_voxels", C.c_int64),
+        ("block_end", C.c_int32), ("win_z0", C.c_int32), ("win_z", C.c_int32), ("filter_fragments", C.c_double), ("max_batch_voxels", C.c_int64),
     ]
 
 
@@ -116,7 +116,7 @@ class Plan:
 
     def __init__(self, vol_shape, block_size, context, aff_dtype, roi_offset=None, roi_shape=None, n_channels=3,
                  fragments_in_xy=True, min_seed_distance=10, filter_fragments=0.1, remove_debris=64,
-                 queue_bins=256, keep_cheaper=True, block_begin=-1, block_end=-1, max_batch_voxels=0):
+                 queue_bins=256, keep_cheaper=True, block_begin=-1, block_end=-1, max_batch_voxels=0, win_z0=0, win_z=0):
         cfg = WsConfig()
         roi_offset = roi_offset if roi_offset is not None else (0, 0, 0)
         roi_shape = roi_shape if roi_shape is not None else vol_shape
@@ -136,10 +136,14 @@ class Plan:
         cfg.crop_relabel = 1
         cfg.block_begin = int(block_begin)
         cfg.block_end = int(block_end)
+        cfg.win_z0 = int(win_z0)
+        cfg.win_z = int(win_z)
         cfg.filter_fragments = float(filter_fragments or 0.0)
         cfg.max_batch_voxels = int(max_batch_voxels)
         self.cfg = cfg
         self.roi_shape = tuple(int(v) for v in roi_shape)
+        if win_z > 0:
+            self.roi_shape = (int(win_z),) + self.roi_shape[1:]
         self._h = C.c_void_p()
         _check(lib().bs_plan_create(C.byref(cfg), C.byref(self._h)))
 

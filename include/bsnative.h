@@ -47,6 +47,9 @@ typedef struct bs_ws_config {
                                   (watershed_frags.py:216-224); 0 = raw watershed ids           */
     int32_t block_begin;       /* this rank owns blocks [block_begin, block_end) of the      */
     int32_t block_end;         /*   z-major block grid, in units of z-layers of blocks; -1/-1 = all */
+    int32_t win_z0;            /* multi-GPU slab window: when win_z > 0 the affinity array is  */
+    int32_t win_z;             /*   (C, win_z, Y, X) and the fragment array (win_z, Y, X), both holding
+                                    the global planes [win_z0, win_z0 + win_z); roi must span all of z */
     double filter_fragments;   /* ws_params.filter_fragments (0 = off)                       */
     int64_t max_batch_voxels;  /* scratch bound for stage 1 (0 = default)                    */
 } bs_ws_config;

@@ -1,0 +1,53 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/bsnative.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "bsnative.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/bsnative.h but not exported"
+
+
+def test_python_binding_lists_the_same_symbols(built_lib):
+    from bootstrapper_b200 import native
+    assert sorted(native.EXPORTS) == declared_symbols()
+    native.lib()
+    assert native.lib().bs_version() >= 100
+
+
+def test_error_reporting_without_compute(built_lib):
+    from bootstrapper_b200 import native
+    with pytest.raises(native.BsError) as e:
+        native.Plan((10, 10, 10), (0, 5, 5), (0, 1, 1), native.BS_DTYPE_U8)
+    assert "positive" in str(e.value)
+    with pytest.raises(native.BsError):
+        native.Plan((10, 10, 10), (5, 5, 5), (6, 1, 1), native.BS_DTYPE_U8)     # context > block
+
+
+def test_no_cpu_fallback(built_lib):
+    """CPU tensors are refused, the product never routes through the oracle."""
+    import torch
+    from bootstrapper_b200 import native
+    from bootstrapper_b200.post.pipeline import segment_blockwise
+    with pytest.raises(native.BsError):
+        segment_blockwise(torch.zeros((3, 4, 8, 8), dtype=torch.uint8))
+    pkg = os.path.join(ROOT, "bootstrapper_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"

@@ -1,0 +1,204 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Bit-exact bar for everything integer (fragments incl. ids, nodes, RAG edge sets, LUTs, segmentations);
+edge scores: identical float32 (tolerance 1e-6 relative per BASELINE.json north_star, asserted below).
+Oracle switches: seed_tie="index" (DESIGN.md D1), stats_mode="canonical" (D2).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SCORE_RTOL = 1e-6
+
+
+def _run_gpu(affs_np, params, block, ctx, roi=None, mask_np=None):
+    from bootstrapper_b200.post.pipeline import segment_blockwise
+    dev = torch.device("cuda:0")
+    affs = torch.from_numpy(affs_np).to(dev)
+    mask = torch.from_numpy(mask_np).to(dev) if mask_np is not None else None
+    r = segment_blockwise(affs, params, block, ctx, roi=roi, mask=mask)
+    torch.cuda.synchronize()
+    return r
+
+
+def _check(r, ref):
+    f = r["fragments"].cpu().numpy().view(np.uint64)
+    assert np.array_equal(f, ref["fragments"]), "fragment ids differ"
+    nid, npos, nsz = [t.cpu().numpy() for t in r["nodes"]]
+    rn = np.array(sorted(ref["rag"].node_pos), dtype=np.uint64)
+    assert np.array_equal(nid.view(np.uint64), rn)
+    if len(rn):
+        assert np.array_equal(npos, np.array([ref["rag"].node_pos[int(i)] for i in rn]))
+        assert np.array_equal(nsz, np.array([ref["rag"].node_size[int(i)] for i in rn]))
+    eu, ev, es = [t.cpu().numpy() for t in r["edges"]]
+    got = dict(zip(zip(eu.view(np.uint64).tolist(), ev.view(np.uint64).tolist()), es.tolist()))
+    want = ref["rag"].edges
+    assert set(got) == set(want), "RAG edge sets differ"
+    for k, s in want.items():
+        if s is None:
+            assert np.isnan(got[k])
+        else:
+            assert abs(got[k] - s) <= SCORE_RTOL * abs(s), (k, got[k], s)
+    for thr, seg in r["segs"].items():
+        assert np.array_equal(seg.cpu().numpy().view(np.uint64), ref["segs"][thr]["seg"]), f"segmentation {thr}"
+        assert np.array_equal(r["luts"][thr].cpu().numpy().view(np.uint64), ref["segs"][thr]["lut"][1])
+
+
+def _oracle(affs, params, block, ctx, roi=None, mask=None):
+    from oracle.blockwise import waterz_pipeline
+    return waterz_pipeline(affs, params, block_size=block, context=ctx, roi=roi, mask=mask, seed_tie="index",
+                           stats_mode="canonical")
+
+
+CASES = [
+    # shape, block, context, params, dtype
+    ((20, 160, 160), (10, 80, 80), (2, 10, 10), {}, np.uint8),
+    ((24, 130, 170), (10, 64, 64), (1, 8, 8), {}, np.uint8),                                  # ragged: trailing blocks shrink
+    ((16, 96, 96), (8, 48, 48), (1, 6, 6), {"fragments_in_xy": False}, np.uint8),             # 3-D seeded mode
+    ((12, 120, 120), (6, 60, 60), (1, 8, 8), {"filter_fragments": 0.0, "remove_debris": 0}, np.uint8),
+    ((12, 120, 120), (6, 60, 60), (1, 8, 8), {"min_seed_distance": 5, "thresholds": [0.1, 0.9]}, np.uint8),
+    ((12, 120, 120), (6, 60, 60), (1, 8, 8), {}, np.float32),
+    ((12, 100, 100), (6, 50, 50), (1, 6, 6), {"fragments_in_xy": False}, np.float32),
+]
+
+
+@pytest.mark.parametrize("shape,block,ctx,params,dtype", CASES)
+def test_pipeline_matches_oracle(shape, block, ctx, params, dtype):
+    from bootstrapper_b200.synth import synth_affs
+    affs = synth_affs(shape, seed=1, dtype=dtype)
+    _check(_run_gpu(affs, params, block, ctx), _oracle(affs, params, block, ctx))
+
+
+def test_single_block_roi_mode():
+    """block_shape == "roi": one block, no context (post/watershed.py:84-86, :361-364)"""
+    from bootstrapper_b200.synth import synth_affs
+    affs = synth_affs((8, 150, 150), seed=3)
+    _check(_run_gpu(affs, {}, None, None), _oracle(affs, {}, None, None))
+
+
+def test_roi_inside_volume():
+    from bootstrapper_b200.synth import synth_affs
+    affs = synth_affs((20, 140, 150), seed=4)
+    roi = ((4, 20, 30), (12, 100, 100))
+    _check(_run_gpu(affs, {}, (6, 50, 50), (1, 6, 6), roi=roi), _oracle(affs, {}, (6, 50, 50), (1, 6, 6), roi=roi))
+
+
+def test_mask():
+    from bootstrapper_b200.synth import synth_affs
+    affs = synth_affs((10, 120, 120), seed=5)
+    mask = np.ones((10, 120, 120), np.uint8)
+    mask[:, 40:70, 30:90] = 0
+    mask[3:5] = 0
+    _check(_run_gpu(affs, {}, (5, 60, 60), (1, 8, 8), mask_np=mask), _oracle(affs, {}, (5, 60, 60), (1, 8, 8), mask=mask))
+
+
+def test_empty_and_saturated_inputs():
+    zeros = np.zeros((3, 8, 64, 64), np.uint8)
+    r = _run_gpu(zeros, {}, (4, 32, 32), (1, 4, 4))
+    assert int(r["fragments"].abs().sum()) == 0 and r["nodes"][0].numel() == 0 and r["edges"][0].numel() == 0
+    # all-foreground slices exercise scipy's "background at (-1, 0)" rule for the EDT
+    ones = np.full((3, 6, 48, 48), 255, np.uint8)
+    ones[:, :, 0, :] = 0          # only the first row of every slice is background in the volume
+    p = {"filter_fragments": 0.0, "remove_debris": 0}
+    _check(_run_gpu(ones, p, (3, 24, 24), (1, 4, 4)), _oracle(ones, p, (3, 24, 24), (1, 4, 4)))
+    full = np.full((3, 4, 40, 40), 255, np.uint8)
+    _check(_run_gpu(full, p, None, None), _oracle(full, p, None, None))
+
+
+def test_edt_and_flood_intermediates():
+    """stage-1 intermediates straight from the device scratch: exact squared EDT vs scipy, flood vs the
+    restated skimage priority flood (index rule) per tile."""
+    from scipy.ndimage import distance_transform_edt
+    from bootstrapper_b200 import native
+    from bootstrapper_b200.synth import synth_affs
+    from oracle.ws import watershed_from_boundary_distance
+    affs = synth_affs((6, 150, 130), seed=7)
+    native.set_debug(True)
+    try:
+        plan = native.Plan(affs.shape[1:], affs.shape[1:], (0, 0, 0), native.BS_DTYPE_U8, filter_fragments=0, remove_debris=0)
+        plan.fragments(torch.from_numpy(affs).cuda())
+        d2 = plan.debug_fetch("d2", np.uint32).reshape(affs.shape[1:])
+        flood = plan.debug_fetch("flood", np.uint32).reshape(affs.shape[1:])
+    finally:
+        native.set_debug(False)
+    a = affs.astype(np.float64) / 255
+    for z in range(affs.shape[1]):
+        mask = 0.5 * (a[2, z] + a[1, z]) > 0.5
+        dist = distance_transform_edt(mask)
+        assert np.array_equal(d2[z], np.rint(dist * dist).astype(np.uint32))
+        ref, _ = watershed_from_boundary_distance(dist, mask, seed_tie="index")
+        got = np.where(flood[z] >= 0x80000000, 0, flood[z]).astype(np.int64)
+        pairs = np.unique(np.stack([got.ravel(), ref.ravel().astype(np.int64)], 1), axis=0)
+        assert len(np.unique(pairs[:, 0])) == len(pairs) == len(np.unique(pairs[:, 1]))
+
+
+def test_watershed_from_affinities_plug():
+    """post/ws.py:38 signature; partition equality (ids are a relabelling, see the module docstring)"""
+    from bootstrapper_b200.post.ws import watershed_from_affinities
+    from bootstrapper_b200.synth import synth_affs
+    from oracle.ws import watershed_from_affinities as ref_ws
+    affs = synth_affs((5, 140, 140), seed=8)
+    for xy in (True, False):
+        got, n = watershed_from_affinities(affs, max_affinity_value=255, fragments_in_xy=xy, min_seed_distance=10)
+        ref, _ = ref_ws(affs.astype(np.float64) / 255, fragments_in_xy=xy, min_seed_distance=10, seed_tie="index")
+        assert got.dtype == np.uint64 and n == len(np.unique(got)) - 1
+        pairs = np.unique(np.stack([got.ravel().astype(np.int64), ref.ravel().astype(np.int64)], 1), axis=0)
+        assert len(np.unique(pairs[:, 0])) == len(pairs) == len(np.unique(pairs[:, 1]))
+
+
+def test_connected_components_and_relabel_kernels():
+    from bootstrapper_b200 import native
+    from oracle.native import connected_components as ref_cc
+    rng = np.random.default_rng(0)
+    nodes = np.sort(rng.choice(np.arange(1, 10 ** 6), 5000, replace=False)).astype(np.uint64)
+    e = rng.choice(nodes, (12000, 2))
+    scores = rng.random(12000).astype(np.float32)
+    scores[::7] = np.nan
+    dev = "cuda"
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x).view(np.int64) if x.dtype == np.uint64 else x).to(dev)  # noqa: E731
+    for thr in (0.0, 0.3, 0.3000001, 1.0):
+        comp = native.connected_components(t(nodes), t(e[:, 0].copy()), t(e[:, 1].copy()), t(scores), thr)
+        keep = ~np.isnan(scores)
+        ref = ref_cc(nodes, e[keep], scores[keep], thr)
+        assert np.array_equal(comp.cpu().numpy().view(np.uint64), ref)
+    frags = rng.choice(np.concatenate([[0, 999999999], nodes]), (40, 50, 60)).astype(np.uint64)
+    seg = native.relabel(t(frags), t(nodes), comp).cpu().numpy().view(np.uint64)
+    lut = dict(zip(nodes.tolist(), comp.cpu().numpy().view(np.uint64).tolist()))
+    ref = np.vectorize(lambda v: lut.get(v, v), otypes=[np.uint64])(frags)
+    assert np.array_equal(seg, ref)
+    # idempotence: component ids are fixed points of the LUT
+    assert np.array_equal(native.relabel(t(seg), t(nodes), comp).cpu().numpy().view(np.uint64), seg)
+
+
+def test_full_size_properties():
+    """CREMI-sized slab (BASELINE config 2 geometry, reduced z) through size-independent properties."""
+    from bootstrapper_b200 import native
+    from bootstrapper_b200.post.pipeline import segment_blockwise
+    affs = native.synth_affs((50, 1250, 1250), seed=0)
+    r = segment_blockwise(affs, {}, (25, 250, 250), (3, 31, 31))
+    torch.cuda.synchronize()
+    frags = r["fragments"]
+    ids, pos, sizes = r["nodes"]
+    assert bool((ids[1:] > ids[:-1]).all())                                        # ascending unique ids
+    assert int(sizes.sum()) == int((frags != 0).sum())                              # node sizes partition the foreground
+    uniq = torch.unique(frags)
+    assert torch.equal(uniq[uniq != 0], ids)
+    nvox = 25 * 250 * 250
+    bid = torch.div(ids, nvox, rounding_mode="floor")
+    plan_ids, wo, ws = r["plan"].block_info()
+    assert set(bid.unique().tolist()) <= set(plan_ids.tolist())
+    eu, ev, es = r["edges"]
+    assert bool((eu < ev).all()) and torch.unique(torch.stack([eu, ev]), dim=1).shape[1] == eu.numel()
+    ok = ~torch.isnan(es)
+    assert bool(((es[ok] >= 0) & (es[ok] < 1)).all())
+    prev = None
+    for thr in sorted(r["segs"]):
+        seg = r["segs"][thr]
+        assert torch.equal(seg == 0, frags == 0)
+        n = torch.unique(seg).numel()
+        assert prev is None or n <= prev                                            # coarser with the threshold
+        prev = n
+        # every segment id is the smallest fragment id it contains
+        assert bool((seg <= frags).all())

@@ -1,0 +1,177 @@
+"""The oracle itself: pinned pieces against fixtures generated from the reference's own files, and
+hand-checkable micro cases for the restated third-party routines (parity unpinned, SURVEY U-list)."""
+import heapq
+import os
+
+import numpy as np
+import pytest
+
+from oracle import blockwise as ob
+from oracle.merge_tree import MergeTree
+from oracle.native import Waterz, connected_components, sk_label, sk_watershed
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_merge_tree_pinned_against_reference():
+    d = np.load(os.path.join(GOLD, "merge_tree.npz"))
+    n_cases = len([k for k in d.files if k.endswith("_leaves")])
+    assert n_cases >= 4
+    for ci in range(n_cases):
+        mt = MergeTree(d[f"c{ci}_leaves"])
+        for a, b, c, s in d[f"c{ci}_hist"]:
+            mt.merge(int(a), int(b), int(c), s)
+        out = mt.find_merges(d[f"c{ci}_us"], d[f"c{ci}_vs"])
+        ref = d[f"c{ci}_out"]
+        assert np.array_equal(np.isnan(out), np.isnan(ref))
+        assert np.array_equal(out[~np.isnan(out)], ref[~np.isnan(ref)])
+
+
+def test_cantor_numbers():
+    # funlib.math.cantor_number: 1-D identity, 2-D Cantor pairing, 3-D simplex pairing
+    assert [ob.cantor_number((i,)) for i in range(4)] == [0, 1, 2, 3]
+    assert [ob.cantor_number(c) for c in [(0, 0), (1, 0), (0, 1), (2, 0), (1, 1), (0, 2)]] == [0, 2, 1, 5, 4, 3]
+    ids = {ob.cantor_number((i, j, k)) for i in range(6) for j in range(6) for k in range(6)}
+    assert len(ids) == 216 and ob.cantor_number((0, 0, 0)) == 0
+
+
+# ---- skimage.segmentation.watershed restated
+def _ws1d(image, markers, mask=None, tie="heap"):
+    image = np.asarray(image, np.float64)[None]
+    markers = np.asarray(markers, np.int64)[None]
+    mask = np.ones_like(markers, np.uint8) if mask is None else np.asarray(mask, np.uint8)[None]
+    return sk_watershed(image, markers, mask, seed_tie=tie)[0].tolist()
+
+
+@pytest.mark.parametrize("tie", ["heap", "index"])
+def test_watershed_micro_cases(tie):
+    assert _ws1d([0, 1, 2, 1, 0], [1, 0, 0, 0, 2], tie=tie) == [1, 1, 1, 2, 2]          # FIFO: lower age claims the ridge
+    assert _ws1d([0, 0, 0, 0], [1, 0, 0, 2], tie=tie) == [1, 1, 2, 2]                    # plateau split by age
+    assert _ws1d([0, 5, 1, 5, 0], [1, 0, 0, 0, 2], tie=tie) == [1, 1, 1, 2, 2]           # un-seeded pit, value not clamped
+    assert _ws1d([0, 0, 0, 0, 0], [1, 0, 0, 0, 0], mask=[1, 1, 0, 1, 1], tie=tie) == [1, 1, 0, 0, 0]   # mask blocks
+    assert _ws1d([0, 0, 0], [7, 0, 0], mask=[0, 1, 1], tie=tie) == [0, 0, 0]             # markers * mask
+    out = sk_watershed(np.zeros((3, 3)), np.array([[0, 1, 0], [2, 0, 0], [0, 0, 0]]), np.ones((3, 3), np.uint8), seed_tie=tie)
+    # neighbour order (-row, -col, +col, +row): seed 1 pops first and takes the centre
+    assert out.tolist() == [[1, 1, 1], [2, 1, 1], [2, 1, 1]]
+
+
+def _flood_python(image, markers, mask):
+    """independent restatement with heapq; valid for the 'index' rule where (value, age) is a strict order"""
+    shape = image.shape
+    out = (markers * mask).astype(np.int64)
+    seeds = np.flatnonzero(out.ravel())
+    heap = [(image.ravel()[i], k - len(seeds), int(i)) for k, i in enumerate(seeds)]
+    heapq.heapify(heap)
+    age = 1
+    nd = image.ndim
+    strides = [int(np.prod(shape[d + 1:])) for d in range(nd)]
+    offs = [(-1, d) for d in range(nd)] + [(1, d) for d in reversed(range(nd))]
+    flat, m, im = out.ravel(), mask.ravel(), image.ravel()
+    while heap:
+        _, _, i = heapq.heappop(heap)
+        c = np.unravel_index(i, shape)
+        for sgn, d in offs:
+            if not 0 <= c[d] + sgn < shape[d]:
+                continue
+            j = i + sgn * strides[d]
+            if not m[j] or flat[j]:
+                continue
+            age += 1
+            flat[j] = flat[i]
+            heapq.heappush(heap, (im[j], age, j))
+    return out
+
+
+@pytest.mark.parametrize("shape", [(17, 23), (5, 9, 11)])
+def test_watershed_index_rule_matches_independent_restatement(shape):
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        image = rng.integers(0, 4, shape).astype(np.float64)       # few levels -> ties everywhere
+        markers = (rng.random(shape) < 0.03) * rng.integers(1, 50, shape)
+        mask = (rng.random(shape) < 0.9).astype(np.uint8)
+        assert np.array_equal(sk_watershed(image, markers, mask, seed_tie="index"), _flood_python(image, markers, mask))
+
+
+def test_watershed_heap_vs_index_census():
+    """D1: the two seed tie rules differ only on contested voxels between equal-valued seeds."""
+    from bootstrapper_b200.synth import synth_affs
+    from oracle.ws import watershed_from_affinities
+    affs = synth_affs((4, 160, 160), seed=5).astype(np.float64) / 255.0
+    a, _ = watershed_from_affinities(affs, fragments_in_xy=True, seed_tie="heap")
+    b, _ = watershed_from_affinities(affs, fragments_in_xy=True, seed_tie="index")
+    assert np.array_equal(a == 0, b == 0)
+    frac = float((a != b).mean())
+    assert frac < 0.02, frac
+
+
+def test_label_full_connectivity_raster_ids():
+    x = np.array([[5, 0, 5], [0, 5, 0], [7, 0, 0], [0, 0, 5]])
+    out, n = sk_label(x)
+    assert n == 3 and out.tolist() == [[1, 0, 1], [0, 1, 0], [2, 0, 0], [0, 0, 3]]
+    x3 = np.zeros((2, 2, 2), np.int64)
+    x3[0, 0, 0] = x3[1, 1, 1] = 4                                   # 26-connectivity joins the corner pair
+    assert sk_label(x3)[1] == 1
+
+
+# ---- waterz restated
+def _vol(frags, ax=None, ay=None, az=None):
+    frags = np.asarray(frags, np.uint64)
+    affs = np.zeros((3,) + frags.shape, np.uint8)
+    for c, a in enumerate((az, ay, ax)):
+        if a is not None:
+            affs[c] = np.asarray(a, np.uint8)
+    return affs, frags
+
+
+def test_waterz_chain_and_thresholds():
+    affs, frags = _vol([[[1, 2, 3, 3]]], ax=[[[0, 200, 100, 255]]])
+    wz = Waterz(affs, frags, 256, "canonical")
+    a, b, c, s = wz.merge_until(0.5)
+    assert (a.tolist(), b.tolist(), c.tolist()) == ([1], [2], [1]) and s[0] == np.float32(1 - np.float32(200 / 255))
+    assert wz.segmentation().ravel().tolist() == [1, 1, 3, 3]
+    a, b, c, s = wz.merge_until(1.0)
+    assert (a.tolist(), b.tolist()) == ([1], [3]) and abs(s[0] - (1 - 100 / 255)) < 1e-6
+    assert wz.counters()["stale"] == 1                                 # (2,3) was re-scored once after the first merge
+
+
+def test_waterz_shared_neighbour_keeps_cheaper_edge_and_rescoring():
+    affs, frags = _vol([[[1, 2], [3, 3]]], ax=[[[0, 250], [0, 0]]], ay=[[[0, 0], [100, 200]]])
+    wz = Waterz(affs, frags, 256, "canonical")
+    wz.merge_until(0.0)
+    u, v, s, _, cnt = wz.region_graph()
+    assert sorted(zip(u.tolist(), v.tolist())) == [(1, 2), (1, 3), (2, 3)]
+    assert [(int(a), int(b)) for a, b in zip(u, v)] == [(1, 2), (1, 3), (2, 3)]     # creation order: raster, then z,y,x
+    a, b, c, s = wz.merge_until(1.0)
+    assert list(zip(a.tolist(), b.tolist())) == [(1, 2), (1, 3)]
+    assert abs(s[1] - (1 - 150 / 255)) < 1e-6                           # merged edge: mean of both contacts
+    mt = MergeTree(np.array([0, 1, 2, 3], np.uint64))
+    for ai, bi, ci, si in zip(a, b, c, s):
+        mt.merge(ai, bi, ci, si)
+    out = mt.find_merges([1, 1, 2], [2, 3, 3])
+    assert out[0] == s[0] and out[1] == s[1] and out[2] == s[1]
+
+
+def test_waterz_zero_affinity_edges_never_merge():
+    affs, frags = _vol([[[1, 2, 3]]], ax=[[[0, 0, 255]]])
+    wz = Waterz(affs, frags, 256, "canonical")
+    a, b, _, s = wz.merge_until(1.0)
+    assert list(zip(a.tolist(), b.tolist())) == [(2, 3)]               # score(1,2) == 1.0 is not < 1.0
+
+
+def test_connected_components_threshold_is_inclusive():
+    nodes = np.array([3, 5, 9, 11], np.uint64)
+    edges = np.array([[3, 5], [5, 9], [9, 11]], np.uint64)
+    scores = np.array([0.2, 0.35, 0.5], np.float32)
+    assert connected_components(nodes, edges, scores, 0.35).tolist() == [3, 3, 3, 11]
+    assert connected_components(nodes, edges, scores, 0.34999).tolist() == [3, 3, 9, 11]
+
+
+def test_blockwise_oracle_is_block_order_independent():
+    from bootstrapper_b200.synth import synth_affs
+    from oracle.parallel import waterz_pipeline_parallel
+    affs = synth_affs((12, 100, 100), seed=2)
+    kw = dict(block_size=(6, 50, 50), context=(1, 6, 6), seed_tie="index", stats_mode="canonical")
+    a = ob.waterz_pipeline(affs, **kw)
+    b = waterz_pipeline_parallel(affs, workers=2, **kw)
+    assert np.array_equal(a["fragments"], b["fragments"]) and a["rag"].edges == b["rag"].edges
+    assert len(a["rag"].node_pos) > 20 and len(a["rag"].edges) > 20
