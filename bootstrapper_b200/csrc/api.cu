@@ -7,6 +7,7 @@
 
 namespace bs {
 int g_debug = 0;
+int g_flood_version = 0;   // 0 = auto (v2 when eligible), 1 = force the global-memory flood
 int stage1_run(Plan &P, const void *affs, const uint8_t *mask, uint64_t *frags_out, cudaStream_t s);
 int stage2_run(Plan &P, const void *affs, const uint64_t *frags, cudaStream_t s);
 int connected_components(const uint64_t *nodes, int64_t n, const uint64_t *eu, const uint64_t *ev, const float *scores,
@@ -51,6 +52,11 @@ static void init_mempool() {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     done = true;
+}
+
+int bs_set_flood_version(int v) {
+    g_flood_version = v;
+    return BS_OK;
 }
 
 int bs_plan_create(const bs_ws_config *cfg, bs_plan **out) {

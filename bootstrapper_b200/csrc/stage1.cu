@@ -296,16 +296,22 @@ __global__ void __launch_bounds__(256) k_seed_union(const Tile *__restrict__ til
 __global__ void __launch_bounds__(256) k_seed_label_hist(const Tile *__restrict__ tiles, const uint32_t *__restrict__ par,
                                                          const uint8_t *__restrict__ msk, const uint32_t *__restrict__ d2,
                                                          uint32_t *__restrict__ lab, const uint32_t *__restrict__ hbase,
-                                                         uint32_t *__restrict__ hist) {
+                                                         uint32_t *__restrict__ hist, const uint32_t *__restrict__ sscan,
+                                                         int compact_labels) {
     const Tile t = tiles[blockIdx.y];
     const long long npix = (long long)t.D * t.H * t.W;
     const uint32_t *pp = par + t.base;
     const uint32_t hb = hbase[blockIdx.y];
+    const uint32_t s0 = compact_labels ? sscan[t.base] : 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
         uint32_t l = 0;
         if (msk[t.base + i]) {
             l = UNLAB;
-            if (pp[i] != NONE32) l = uf_find(pp, (uint32_t)i) + 1;
+            if (pp[i] != NONE32) {
+                uint32_t root = uf_find(pp, (uint32_t)i);
+                // label = root pixel + 1, or (flood v2) the root's rank among the tile's seed pixels + 1
+                l = compact_labels ? sscan[t.base + root] - s0 + 1 : root + 1;
+            }
             atomicAdd(&hist[hb + d2[t.base + i]], 1u);
         }
         lab[t.base + i] = l;
@@ -332,15 +338,31 @@ __global__ void k_levels(const uint32_t *__restrict__ hist, const uint32_t *__re
 __global__ void k_tile_ranges(const Tile *__restrict__ tiles, int ntiles, const uint32_t *__restrict__ hbase,
                               const uint32_t *__restrict__ lrank, const uint32_t *__restrict__ nlevels,
                               const uint32_t *__restrict__ sscan, const uint32_t *__restrict__ nseeds,
-                              uint32_t *__restrict__ tile_lvl, uint32_t *__restrict__ tile_seed) {
+                              uint32_t *__restrict__ tile_lvl, uint32_t *__restrict__ tile_seed,
+                              const uint32_t *__restrict__ qoff, const uint32_t *__restrict__ nmask,
+                              uint32_t *__restrict__ tile_q) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < ntiles) {
         tile_lvl[i] = lrank[hbase[i]];
         tile_seed[i] = sscan[tiles[i].base];
+        tile_q[i] = qoff[hbase[i]];
     } else if (i == ntiles) {
         tile_lvl[i] = *nlevels;
         tile_seed[i] = *nseeds;
+        tile_q[i] = *nmask;
     }
+}
+
+// largest number of seed pixels in one tile (decides whether 15-bit labels suffice for flood v2)
+__global__ void k_tile_seed_max(const Tile *__restrict__ tiles, int ntiles, const uint32_t *__restrict__ sscan,
+                                const uint32_t *__restrict__ nseeds, const uint32_t *__restrict__ tilemax,
+                                uint32_t *__restrict__ out_seedmax, uint32_t *__restrict__ out_d2max) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntiles) return;
+    uint32_t b = sscan[tiles[i].base];
+    uint32_t e = i + 1 < ntiles ? sscan[tiles[i + 1].base] : *nseeds;
+    atomicMax(out_seedmax, e - b);
+    atomicMax(out_d2max, tilemax[i]);
 }
 
 // lv = dense level rank of every mask pixel; seed list compaction (tile-local pixel indices)
@@ -348,14 +370,33 @@ __global__ void __launch_bounds__(256) k_pixel_levels(const Tile *__restrict__ t
                                                       const uint32_t *__restrict__ d2, const uint32_t *__restrict__ hbase,
                                                       const uint32_t *__restrict__ lrank, uint32_t *__restrict__ lv,
                                                       const uint8_t *__restrict__ seedflag, const uint32_t *__restrict__ sscan,
-                                                      uint32_t *__restrict__ seedlist) {
+                                                      uint32_t *__restrict__ seedlist, uint16_t *__restrict__ lv16,
+                                                      uint32_t *__restrict__ availw) {
     const Tile t = tiles[blockIdx.y];
     const long long npix = (long long)t.D * t.H * t.W;
     const uint32_t hb = hbase[blockIdx.y];
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t l0 = lrank[hb];
+    for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < npix; i0 += (long long)gridDim.x * blockDim.x) {
+        long long i = i0 + threadIdx.x;
         long long p = t.base + i;
-        if (msk[p]) lv[p] = lrank[hb + d2[p]];
-        if (seedflag[p]) seedlist[sscan[p]] = (uint32_t)i;
+        bool av = false;
+        if (i < npix) {
+            bool m = msk[p] != 0, sd = seedflag[p] != 0;
+            if (m) {
+                uint32_t r = lrank[hb + d2[p]];
+                if (lv16)
+                    lv16[p] = (uint16_t)(r - l0);   // tile-relative level (flood v2)
+                else
+                    lv[p] = r;
+            }
+            if (sd) seedlist[sscan[p]] = (uint32_t)i;
+            av = m && !sd;
+        }
+        if (availw) {
+            // tile bases are 32-aligned: one ballot = one word of the tile's "in mask, not labelled" bitmap
+            unsigned w = __ballot_sync(FULL, av);
+            if ((threadIdx.x & 31) == 0 && i < npix) availw[p >> 5] = w;
+        }
     }
 }
 
@@ -567,6 +608,188 @@ __global__ void __launch_bounds__(64) k_flood(const Tile *__restrict__ tiles, in
         atomicAdd(&stats[0], steps);
         atomicAdd(&stats[1], intr);
         atomicMax(&stats[2], steps);
+    }
+}
+
+// ------------------------------------------------------------------ flood v2 (2-D tiles up to 2^17 pixels)
+// Same step semantics as k_flood, but the per-pixel state the hot loop touches lives on chip: the
+// "in mask, not labelled yet" bitmap of the tile and a small claim table sit in shared memory (no global
+// atomics, nothing to undo when a step is truncated), queue entries carry (label << 17 | pixel), levels
+// are u16.  Global traffic per flooded pixel: one queue entry written + read, one u16 level read.
+static constexpr int F2_WARPS = 4;
+static constexpr int F2_HASH = 256;
+static constexpr uint32_t F2_PIXMASK = 0x1FFFFu;
+static constexpr int F2_MAXPIX = 1 << 17;
+
+__global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict__ tiles, int ntiles,
+                                                          const uint32_t *__restrict__ lab_all, const uint16_t *__restrict__ lv16_all,
+                                                          const uint32_t *__restrict__ availw_all, uint32_t *__restrict__ queue,
+                                                          const uint32_t *__restrict__ lvl_qstart, uint32_t *__restrict__ lvl_head,
+                                                          uint32_t *__restrict__ lvl_tail, const uint32_t *__restrict__ tile_lvl,
+                                                          const uint32_t *__restrict__ seedlist, const uint32_t *__restrict__ tile_seed,
+                                                          int nwords_max, uint32_t *__restrict__ stats) {
+    extern __shared__ uint32_t f2_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * F2_WARPS + warp;
+    if (wid >= ntiles) return;
+    uint32_t *avail = f2_smem + (size_t)warp * (nwords_max + F2_HASH);
+    uint32_t *claim = avail + nwords_max;
+    const Tile t = tiles[wid];
+    const uint16_t *lv16 = lv16_all + t.base;
+    const int W = t.W, H = t.H;
+    const int npix = H * W, nwords = (npix + 31) >> 5;
+    const uint32_t lo = tile_lvl[wid], hi = tile_lvl[wid + 1];
+    if (lo == hi) return;
+    const uint32_t sb = tile_seed[wid], se = tile_seed[wid + 1];
+    if (sb == se) return;
+    for (int w = lane; w < nwords; w += 32) avail[w] = availw_all[(t.base >> 5) + w];
+    __syncwarp();
+    uint32_t steps = 0, intr = 0;
+    uint32_t cur = lo, tailc = 0, headc = 0;
+    {
+        uint32_t maxr = lo, dummy_tail = 0;
+        for (uint32_t s0 = sb; s0 < se; s0 += 32) {
+            bool v[1];
+            uint32_t l[1], ent[1];
+            v[0] = s0 + lane < se;
+            uint32_t px = v[0] ? seedlist[s0 + lane] : 0;
+            l[0] = v[0] ? lo + lv16[px] : 0;
+            ent[0] = v[0] ? ((lab_all[t.base + px] << 17) | px) : 0;
+            if (v[0]) maxr = max(maxr, l[0]);
+            warp_append<1>(v, l, ent, queue, lvl_qstart, lvl_tail, NONE32, dummy_tail, lane);
+            __syncwarp();
+        }
+        cur = __reduce_max_sync(FULL, maxr);
+        headc = 0;
+        tailc = __ldcg(&lvl_tail[cur]);
+    }
+    uint32_t qs = lvl_qstart[cur];
+    for (;;) {
+        if (headc == tailc) {
+            if (lane == 0) {
+                __stcg(&lvl_head[cur], headc);
+                __stcg(&lvl_tail[cur], tailc);
+            }
+            __syncwarp();
+            bool found = false;
+            long long r0 = (long long)cur - 1;
+            while (r0 >= (long long)lo) {
+                long long r = r0 - lane;
+                bool ne = false;
+                if (r >= (long long)lo) ne = __ldcg(&lvl_tail[r]) != __ldcg(&lvl_head[r]);
+                unsigned b = __ballot_sync(FULL, ne);
+                if (b) {
+                    cur = (uint32_t)(r0 - (__ffs(b) - 1));
+                    found = true;
+                    break;
+                }
+                r0 -= 32;
+            }
+            if (!found) break;
+            headc = __ldcg(&lvl_head[cur]);
+            tailc = __ldcg(&lvl_tail[cur]);
+            qs = lvl_qstart[cur];
+            continue;
+        }
+        steps++;
+        const uint32_t k = min(32u, tailc - headc);
+        const bool act = (uint32_t)lane < k;
+        uint32_t entry = act ? __ldcg(&queue[qs + headc + lane]) : 0;
+        const uint32_t p = entry & F2_PIXMASK, mylab = entry >> 17;
+        const int y = p / W, x = p - y * W;
+        // neighbour order of skimage (connectivity 1, 2-D): -y, -x, +x, +y
+        uint32_t nb[4];
+        bool cand[4], pend[4];
+        uint32_t hs[4];
+        nb[0] = (act && y > 0) ? p - W : NONE32;
+        nb[1] = (act && x > 0) ? p - 1 : NONE32;
+        nb[2] = (act && x + 1 < W) ? p + 1 : NONE32;
+        nb[3] = (act && y + 1 < H) ? p + W : NONE32;
+#pragma unroll
+        for (int j = 0; j < F2_HASH / 32; j++) claim[lane + 32 * j] = NONE32;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            cand[s] = nb[s] != NONE32 && ((avail[nb[s] >> 5] >> (nb[s] & 31)) & 1u);
+            pend[s] = cand[s];
+            hs[s] = (nb[s] * 2654435761u) >> 24;
+        }
+        __syncwarp();
+        // the lowest (lane, slot) key wins every contested pixel
+        for (;;) {
+#pragma unroll
+            for (int s = 0; s < 4; s++)
+                if (pend[s]) atomicMin(&claim[hs[s]], ((uint32_t)(lane * 4 + s) << 17) | nb[s]);
+            __syncwarp();
+            bool again = false;
+#pragma unroll
+            for (int s = 0; s < 4; s++)
+                if (pend[s]) {
+                    uint32_t v = claim[hs[s]];
+                    if ((v & F2_PIXMASK) == nb[s]) {
+                        cand[s] = (v >> 17) == (uint32_t)(lane * 4 + s);
+                        pend[s] = false;
+                    } else {
+                        hs[s] = (hs[s] + 1) & (F2_HASH - 1);
+                        again = true;
+                    }
+                }
+            if (!__any_sync(FULL, again)) break;
+        }
+        uint32_t l[4], ent[4];
+        bool up = false;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            l[s] = 0;
+            ent[s] = 0;
+            if (cand[s]) {
+                l[s] = lo + lv16[nb[s]];
+                ent[s] = (mylab << 17) | nb[s];
+                up |= l[s] > cur;
+            }
+        }
+        const unsigned ball = __ballot_sync(FULL, up);
+        const int rstar = ball ? __ffs(ball) - 1 : 31;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            if (lane > rstar) cand[s] = false;
+            if (cand[s]) atomicAnd(&avail[nb[s] >> 5], ~(1u << (nb[s] & 31)));
+        }
+        headc += min(k, (uint32_t)rstar + 1u);
+        warp_append<4>(cand, l, ent, queue, lvl_qstart, lvl_tail, cur, tailc, lane);
+        __syncwarp();
+        if (ball) {
+            intr++;
+            uint32_t mx = 0;
+#pragma unroll
+            for (int s = 0; s < 4; s++)
+                if (cand[s]) mx = max(mx, l[s]);
+            mx = __reduce_max_sync(FULL, mx);
+            if (lane == 0) {
+                __stcg(&lvl_head[cur], headc);
+                __stcg(&lvl_tail[cur], tailc);
+            }
+            __syncwarp();
+            cur = mx;
+            headc = __ldcg(&lvl_head[cur]);
+            tailc = __ldcg(&lvl_tail[cur]);
+            qs = lvl_qstart[cur];
+        }
+    }
+    if (lane == 0 && stats) {
+        atomicAdd(&stats[0], steps);
+        atomicAdd(&stats[1], intr);
+        atomicMax(&stats[2], steps);
+    }
+}
+
+// labels of flood v2: every queue entry (seed or flooded pixel) carries its label
+__global__ void __launch_bounds__(256) k_scatter_labels(const Tile *__restrict__ tiles, const uint32_t *__restrict__ tile_q,
+                                                        const uint32_t *__restrict__ queue, uint32_t *__restrict__ lab) {
+    const Tile t = tiles[blockIdx.y];
+    const uint32_t qb = tile_q[blockIdx.y], qe = tile_q[blockIdx.y + 1];
+    for (uint32_t q = qb + blockIdx.x * blockDim.x + threadIdx.x; q < qe; q += gridDim.x * blockDim.x) {
+        uint32_t e = queue[q];
+        if (e != NONE32) lab[t.base + (e & F2_PIXMASK)] = e >> 17;
     }
 }
 
@@ -834,6 +1057,7 @@ static int keep_debug(Plan &P, const char *name, DevBuf &buf, int elem, long lon
 }
 
 extern int g_debug;
+extern int g_flood_version;
 
 template <typename T>
 static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64_t *frags_out, long long node_base,
@@ -868,7 +1092,7 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
                 t.base = P_pix;
                 t.wbase = V_w + (long long)z * b.ws[1] * b.ws[2];
                 long long np = (long long)t.H * t.W;
-                P_pix += np;
+                P_pix += (np + 31) & ~31LL;   // 32-aligned tile bases (bitmap words of flood v2)
                 maxpix = std::max(maxpix, np);
                 tiles.push_back(t);
             }
@@ -911,7 +1135,7 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     BS_TRY(tmpA.alloc(P_pix * 4, s));
     BS_TRY(lab.alloc(P_pix * 4, s));
     BS_TRY(lv.alloc(P_pix * 4, s));
-    BS_TRY(seedflag.alloc(P_pix, s));
+    BS_TRY(seedflag.alloc_zero(P_pix, s));
     BS_TRY(tileflags.alloc_zero(4 * ntiles, s));
     BS_TRY(tilemax.alloc_zero(4 * (ntiles + 1), s));
 
@@ -961,13 +1185,23 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     BS_LAUNCH(k_tile_hsize, cdiv(ntiles, 256), 256, 0, s, tilemax.as<uint32_t>(), hsize.as<uint32_t>(), ntiles);
     BS_TRY(scan_exclusive_u32(hsize.as<uint32_t>(), hbase.as<uint32_t>(), ntiles, d_tot + 0, s));
     BS_TRY(scan_exclusive_u8(seedflag.as<uint8_t>(), sscan.as<uint32_t>(), P_pix, d_tot + 1, s));
+    BS_LAUNCH(k_tile_seed_max, cdiv(ntiles, 256), 256, 0, s, dt, ntiles, sscan.as<uint32_t>(), d_tot + 1,
+              tilemax.as<uint32_t>(), d_tot + 5, d_tot + 6);
     uint32_t h_tot[8];
     BS_CUDA(cudaMemcpyAsync(h_tot, d_tot, 32, cudaMemcpyDeviceToHost, s));
     BS_CUDA(cudaStreamSynchronize(s));
     const size_t Htot = h_tot[0], nseeds = h_tot[1];
+    // flood v2 (on-chip state) needs 2-D tiles of <= 2^17 pixels, 15-bit labels and 16-bit levels
+    const bool v2 = xy && g_flood_version != 1 && maxpix <= F2_MAXPIX && h_tot[5] < 32767 && h_tot[6] < 65535;
 
     g_prof.mark("s1.levels", s);
-    DevBuf hist, nz, lrank, qoff, lvl_qstart, lvl_head, lvl_tail, tile_lvl, tile_seed, seedlist, queue, fstats;
+    DevBuf hist, nz, lrank, qoff, lvl_qstart, lvl_head, lvl_tail, tile_lvl, tile_seed, seedlist, queue, fstats, tile_q, lv16,
+        availw;
+    BS_TRY(tile_q.alloc(4 * (ntiles + 1), s));
+    if (v2) {
+        BS_TRY(lv16.alloc(2 * (size_t)P_pix, s));
+        BS_TRY(availw.alloc_zero(4 * ((size_t)P_pix / 32 + 1), s));
+    }
     BS_TRY(hist.alloc_zero(4 * (Htot + 1), s));
     BS_TRY(nz.alloc(Htot + 1, s));
     BS_TRY(lrank.alloc(4 * (Htot + 1), s));
@@ -978,10 +1212,13 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     BS_TRY(tile_lvl.alloc(4 * (ntiles + 1), s));
     BS_TRY(tile_seed.alloc(4 * (ntiles + 1), s));
     BS_TRY(seedlist.alloc(4 * (nseeds + 1), s));
-    BS_TRY(queue.alloc(4 * (size_t)P_pix, s));
+    if (v2)
+        BS_TRY(queue.alloc_fill(4 * (size_t)P_pix, 0xFF, s));
+    else
+        BS_TRY(queue.alloc(4 * (size_t)P_pix, s));
     BS_TRY(fstats.alloc_zero(16, s));
     BS_LAUNCH(k_seed_label_hist, grid, 256, 0, s, dt, lv.as<uint32_t>(), msk.as<uint8_t>(), d2.as<uint32_t>(),
-              lab.as<uint32_t>(), hbase.as<uint32_t>(), hist.as<uint32_t>());
+              lab.as<uint32_t>(), hbase.as<uint32_t>(), hist.as<uint32_t>(), sscan.as<uint32_t>(), v2 ? 1 : 0);
     if (Htot) {
         BS_LAUNCH(k_nzflag, cdiv(Htot, 256), 256, 0, s, hist.as<uint32_t>(), nz.as<uint8_t>(), Htot);
         BS_TRY(scan_exclusive_u8(nz.as<uint8_t>(), lrank.as<uint32_t>(), Htot, d_tot + 2, s));
@@ -991,10 +1228,12 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     }
     // lrank needs a valid entry at hbase[t] for every tile: hbase[t] < Htot always (hsize >= 1)
     BS_LAUNCH(k_tile_ranges, cdiv(ntiles + 1, 256), 256, 0, s, dt, ntiles, hbase.as<uint32_t>(), lrank.as<uint32_t>(),
-              d_tot + 2, sscan.as<uint32_t>(), d_tot + 1, tile_lvl.as<uint32_t>(), tile_seed.as<uint32_t>());
+              d_tot + 2, sscan.as<uint32_t>(), d_tot + 1, tile_lvl.as<uint32_t>(), tile_seed.as<uint32_t>(),
+              qoff.as<uint32_t>(), d_tot + 3, tile_q.as<uint32_t>());
     // the seed parent array lives in lv and is consumed by k_seed_label_hist above; now lv becomes the level
     BS_LAUNCH(k_pixel_levels, grid, 256, 0, s, dt, msk.as<uint8_t>(), d2.as<uint32_t>(), hbase.as<uint32_t>(),
-              lrank.as<uint32_t>(), lv.as<uint32_t>(), seedflag.as<uint8_t>(), sscan.as<uint32_t>(), seedlist.as<uint32_t>());
+              lrank.as<uint32_t>(), lv.as<uint32_t>(), seedflag.as<uint8_t>(), sscan.as<uint32_t>(), seedlist.as<uint32_t>(),
+              v2 ? lv16.as<uint16_t>() : nullptr, v2 ? availw.as<uint32_t>() : nullptr);
     if (g_debug) {
         DevBuf c1, c2;
         BS_TRY(c1.alloc(P_pix * 4, s));
@@ -1006,9 +1245,25 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     }
     // ---- flood
     g_prof.mark("s1.flood", s);
-    BS_LAUNCH(k_flood, cdiv((size_t)ntiles * 32, 64), 64, 0, s, dt, ntiles, lab.as<uint32_t>(), lv.as<uint32_t>(),
-              queue.as<uint32_t>(), lvl_qstart.as<uint32_t>(), lvl_head.as<uint32_t>(), lvl_tail.as<uint32_t>(),
-              tile_lvl.as<uint32_t>(), seedlist.as<uint32_t>(), tile_seed.as<uint32_t>(), fstats.as<uint32_t>());
+    if (v2) {
+        const int nwords_max = (int)((maxpix + 31) / 32);
+        const size_t smem = (size_t)F2_WARPS * (nwords_max + F2_HASH) * 4;
+        static bool attr_set = false;
+        if (!attr_set) {
+            BS_CUDA(cudaFuncSetAttribute(k_flood2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        BS_LAUNCH(k_flood2, cdiv(ntiles, F2_WARPS), 32 * F2_WARPS, smem, s, dt, ntiles, lab.as<uint32_t>(), lv16.as<uint16_t>(),
+                  availw.as<uint32_t>(), queue.as<uint32_t>(), lvl_qstart.as<uint32_t>(), lvl_head.as<uint32_t>(),
+                  lvl_tail.as<uint32_t>(), tile_lvl.as<uint32_t>(), seedlist.as<uint32_t>(), tile_seed.as<uint32_t>(),
+                  nwords_max, fstats.as<uint32_t>());
+        g_prof.mark("s1.flood_scatter", s);
+        BS_LAUNCH(k_scatter_labels, grid, 256, 0, s, dt, tile_q.as<uint32_t>(), queue.as<uint32_t>(), lab.as<uint32_t>());
+    } else {
+        BS_LAUNCH(k_flood, cdiv((size_t)ntiles * 32, 64), 64, 0, s, dt, ntiles, lab.as<uint32_t>(), lv.as<uint32_t>(),
+                  queue.as<uint32_t>(), lvl_qstart.as<uint32_t>(), lvl_head.as<uint32_t>(), lvl_tail.as<uint32_t>(),
+                  tile_lvl.as<uint32_t>(), seedlist.as<uint32_t>(), tile_seed.as<uint32_t>(), fstats.as<uint32_t>());
+    }
     // release what the flood no longer needs
     queue.release();
     sscan.release();

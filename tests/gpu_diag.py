@@ -139,7 +139,7 @@ def main():
                 t_d2 = d2[base:base + n].reshape(H, W)
                 t_seed = seeds[base:base + n].reshape(H, W)
                 t_flood = flood[base:base + n].reshape(H, W)
-                base += n
+                base += (n + 31) & ~31          # tile bases are 32-aligned in xy mode
                 bad["tiles"] += 1
                 bad["d2"] += int((t_d2 != r_d2).sum())
                 fr, _, sd = watershed_from_boundary_distance(dist, mask, return_seeds=True, seed_tie="index")

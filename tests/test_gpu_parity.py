@@ -119,8 +119,10 @@ def test_edt_and_flood_intermediates():
     try:
         plan = native.Plan(affs.shape[1:], affs.shape[1:], (0, 0, 0), native.BS_DTYPE_U8, filter_fragments=0, remove_debris=0)
         plan.fragments(torch.from_numpy(affs).cuda())
-        d2 = plan.debug_fetch("d2", np.uint32).reshape(affs.shape[1:])
-        flood = plan.debug_fetch("flood", np.uint32).reshape(affs.shape[1:])
+        Z, Y, X = affs.shape[1:]
+        stride = (Y * X + 31) & ~31                               # tile bases are 32-aligned
+        d2 = plan.debug_fetch("d2", np.uint32).reshape(Z, stride)[:, :Y * X].reshape(Z, Y, X)
+        flood = plan.debug_fetch("flood", np.uint32).reshape(Z, stride)[:, :Y * X].reshape(Z, Y, X)
     finally:
         native.set_debug(False)
     a = affs.astype(np.float64) / 255
@@ -132,6 +134,22 @@ def test_edt_and_flood_intermediates():
         got = np.where(flood[z] >= 0x80000000, 0, flood[z]).astype(np.int64)
         pairs = np.unique(np.stack([got.ravel(), ref.ravel().astype(np.int64)], 1), axis=0)
         assert len(np.unique(pairs[:, 0])) == len(pairs) == len(np.unique(pairs[:, 1]))
+
+
+def test_flood_versions_agree():
+    """the shared-memory flood (v2) and the global-memory flood (v1) are the same function"""
+    from bootstrapper_b200 import native
+    from bootstrapper_b200.post.pipeline import segment_blockwise
+    from bootstrapper_b200.synth import synth_affs
+    affs = torch.from_numpy(synth_affs((6, 200, 200), seed=11)).cuda()
+    out = []
+    for v in (1, 0):
+        native.set_flood_version(v)
+        try:
+            out.append(segment_blockwise(affs, {}, (3, 100, 100), (1, 12, 12))["fragments"].clone())
+        finally:
+            native.set_flood_version(0)
+    assert torch.equal(out[0], out[1]) and int((out[0] != 0).sum()) > 0
 
 
 def test_watershed_from_affinities_plug():
