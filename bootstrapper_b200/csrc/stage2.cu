@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(32) k_agglomerate(const AggBlk *__restrict__ b
     // uniform (replicated) allocator state
     uint32_t q_bump = 0, q_free = NONE32;
     bool fail = false;
-    uint32_t n_pops = 0, n_stale = 0, n_dead = 0;
+    uint32_t n_pops = 0, n_stale = 0, n_dead = 0, n_iter = 0, n_chunk = 0, n_append = 0;
 
     auto alloc_chunk = [&]() -> uint32_t {
         uint32_t c;
@@ -408,6 +408,7 @@ __global__ void __launch_bounds__(32) k_agglomerate(const AggBlk *__restrict__ b
             int mine = valid ? bin : 0x7fffffff;
             int Bn = __reduce_min_sync(FULL, mine);
             if (Bn == 0x7fffffff) break;
+            n_append++;
             bool c = valid && bin == Bn;
             unsigned m = __ballot_sync(FULL, c);
             uint32_t total = __popc(m), off = __popc(m & lanemask_lt());
@@ -491,6 +492,7 @@ __global__ void __launch_bounds__(32) k_agglomerate(const AggBlk *__restrict__ b
         }
         if (cb >= nbins) break;
         minbin = cb;
+        n_iter++;
         const uint32_t k = (hc == tc ? tf : 32u) - ho;
         const bool act = (uint32_t)lane < k;
         uint32_t e = 0, ru = 0, rv = 0;
@@ -589,10 +591,16 @@ __global__ void __launch_bounds__(32) k_agglomerate(const AggBlk *__restrict__ b
         }
         nmerge++;
         __syncwarp();
+        // walk b's incident-edge chain; surviving entries are re-packed in place (write cursor never passes
+        // the read cursor), so a cluster's chain stays proportional to its live degree
         uint32_t c = ahead[b];
+        uint32_t wc = c, wo = 0, wlast = NONE32;   // write chunk, fill, last chunk that holds a kept entry
         while (c != NONE32) {
+            n_chunk++;
+            const uint32_t cn = A.cnext[c];
             uint32_t ne = A.centries[(size_t)c * 32 + lane];
             bool valid = ne != NONE32 && !edead[ne];
+            bool keep = false;
             if (valid) {
                 uint32_t x1 = agg_find(ufp, eu[ne]), x2 = agg_find(ufp, ev[ne]);
                 uint32_t x = x1 == a ? x2 : x1;
@@ -609,6 +617,7 @@ __global__ void __launch_bounds__(32) k_agglomerate(const AggBlk *__restrict__ b
                             fail = true;
                         else
                             pvals[sn] = ne;
+                        keep = true;
                     } else {
                         uint32_t ae = pvals[sa];
                         if (!keep_cheaper || escore[ne] > escore[ae]) {
@@ -620,21 +629,52 @@ __global__ void __launch_bounds__(32) k_agglomerate(const AggBlk *__restrict__ b
                             ecnt[ne] += ecnt[ae];
                             edead[ae] = 1;
                             pvals[sa] = ne;
+                            keep = true;
                         }
                     }
                 }
             }
             __syncwarp();
-            c = A.cnext[c];
+            const unsigned km = __ballot_sync(FULL, keep);
+            if (km) {
+                const uint32_t pos = wo + __popc(km & lanemask_lt());
+                const uint32_t wnext = A.cnext[wc];
+                if (keep) {
+                    if (pos < 32u)
+                        A.centries[(size_t)wc * 32 + pos] = ne;
+                    else
+                        A.centries[(size_t)wnext * 32 + (pos - 32u)] = ne;
+                }
+                const uint32_t tot = wo + __popc(km);
+                if (tot > 32u) {
+                    wc = wnext;
+                    wo = tot - 32u;
+                    wlast = wc;
+                } else {
+                    wo = tot;
+                    wlast = wc;
+                    if (tot == 32u && cn != NONE32) {
+                        // next kept entry starts a fresh chunk; stay put if the chain ends here
+                        wc = wnext;
+                        wo = 0;
+                    }
+                }
+            }
+            __syncwarp();
+            c = cn;
         }
-        if (lane == 0) {
-            uint32_t hbh = ahead[b];
-            if (hbh != NONE32) {
+        // terminate the re-packed chain and append it to a's
+        const uint32_t bhead = ahead[b];
+        if (wlast != NONE32) {
+            // slots behind the write cursor in the last chunk are cleared; wo == 0 with wc != wlast means full
+            if (wc == wlast && (uint32_t)lane >= wo && wo < 32u) A.centries[(size_t)wlast * 32 + lane] = NONE32;
+            if (lane == 0) {
+                A.cnext[wlast] = NONE32;
                 if (ahead[a] == NONE32)
-                    ahead[a] = hbh;
+                    ahead[a] = bhead;
                 else
-                    A.cnext[atail[a]] = hbh;
-                atail[a] = atail[b];
+                    A.cnext[atail[a]] = bhead;
+                atail[a] = wlast;
             }
         }
         fail = __any_sync(FULL, fail);
@@ -642,9 +682,12 @@ __global__ void __launch_bounds__(32) k_agglomerate(const AggBlk *__restrict__ b
     }
     if (lane == 0) {
         A.nmerges[blockIdx.x] = nmerge;
-        A.counters[3 * blockIdx.x + 0] = n_pops;
-        A.counters[3 * blockIdx.x + 1] = n_stale;
-        A.counters[3 * blockIdx.x + 2] = n_dead;
+        A.counters[6 * blockIdx.x + 0] = n_pops;
+        A.counters[6 * blockIdx.x + 1] = n_stale;
+        A.counters[6 * blockIdx.x + 2] = n_dead;
+        A.counters[6 * blockIdx.x + 3] = n_iter;
+        A.counters[6 * blockIdx.x + 4] = n_chunk;
+        A.counters[6 * blockIdx.x + 5] = n_append;
         if (fail) atomicExch(A.error, 1u);
     }
 }
@@ -932,7 +975,7 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
     BS_TRY(hbb.alloc(4 * (Vtot + 1), s));
     BS_TRY(hs.alloc(4 * (Vtot + 1), s));
     BS_TRY(nmerges.alloc_zero(4 * nown, s));
-    BS_TRY(counters.alloc_zero(12 * nown, s));
+    BS_TRY(counters.alloc_zero(24 * nown, s));
     BS_TRY(err.alloc_zero(16, s));
     AggArrays A;
     A.eu = eu.as<uint32_t>(), A.ev = ev.as<uint32_t>(), A.ecnt = ecnt.as<uint32_t>(), A.etime = etime.as<uint32_t>();
@@ -1000,7 +1043,7 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
         keep_debug2(P, "s2_hb", hbb, 4, Vtot);
         keep_debug2(P, "s2_hs", hs, 4, Vtot);
         keep_debug2(P, "s2_nmerges", nmerges, 4, nown);
-        keep_debug2(P, "s2_counters", counters, 4, 3 * nown);
+        keep_debug2(P, "s2_counters", counters, 4, 6 * nown);
         std::vector<uint32_t> vb(nown);
         for (int i = 0; i < nown; i++) vb[i] = hb[i].vbase;
         DevBuf dvb;

@@ -214,7 +214,7 @@ def main():
             worst = max(worst, rel)
             nbad += rel > 1e-6
     print("edge scores: mismatches(>1e-6 rel) %d, worst rel err %.3g" % (nbad, worst))
-    cnt = plan.debug_fetch("s2_counters", np.uint32).reshape(-1, 3)
+    cnt = plan.debug_fetch("s2_counters", np.uint32).reshape(-1, 6)[:, :3]
     print("agglomeration counters (pops, stale, dead) summed:", cnt.sum(0), "merges:", plan.debug_fetch("s2_nmerges", np.uint32).sum())
 
     # per-block deep check of block 0: initial edge statistics + history
