@@ -14,6 +14,8 @@ int connected_components(const uint64_t *nodes, int64_t n, const uint64_t *eu, c
                          int64_t m, float thr, uint64_t *comp, cudaStream_t s);
 int relabel(const uint64_t *frags, int64_t n, const uint64_t *keys, const uint64_t *vals, int64_t k, uint64_t *seg,
             cudaStream_t s);
+int relabel_dense(Plan &P, const uint64_t *frags, int64_t n, const uint64_t *const *comps, int T, uint64_t *const *segs,
+                  cudaStream_t s);
 int synth_affs(void *out, int dtype, const int32_t *shape, const int32_t *offset, uint64_t seed, cudaStream_t s);
 }  // namespace bs
 
@@ -195,6 +197,12 @@ int bs_relabel(const uint64_t *frags, int64_t n_vox, const uint64_t *lut_keys, c
     BS_ARG(n_vox == 0 || (frags && seg_out), "bs_relabel: null argument");
     BS_ARG(n_lut == 0 || (lut_keys && lut_vals), "bs_relabel: null lut");
     return relabel(frags, n_vox, lut_keys, lut_vals, n_lut, seg_out, (cudaStream_t)stream);
+}
+
+int bs_stage3_relabel(bs_plan *p, const uint64_t *frags, int64_t n_vox, const uint64_t *const *components, int n_thresholds,
+                      uint64_t *const *segs_out, void *stream) {
+    BS_ARG(p && (n_vox == 0 || (frags && components && segs_out)), "bs_stage3_relabel: null argument");
+    return relabel_dense(*p->p, frags, n_vox, components, n_thresholds, segs_out, (cudaStream_t)stream);
 }
 
 int bs_watershed_from_affinities(const void *affs, int aff_dtype, int Z, int Y, int X, int fragments_in_xy,

@@ -132,6 +132,32 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// (x, y, z) of a raveled index inside a tile / block (all such indices are < 2^31): 32-bit divisions only
+__device__ __forceinline__ void unravel3(long long i, int W, int H, int &x, int &y, int &z) {
+    uint32_t u = (uint32_t)i;
+    uint32_t row = u / (uint32_t)W;
+    x = (int)(u - row * (uint32_t)W);
+    uint32_t zz = row / (uint32_t)H;
+    y = (int)(row - zz * (uint32_t)H);
+    z = (int)zz;
+}
+
+// fragment id -> dense node index (blocks ascending by id, ids 1..n per block + block_id * prod(block_size))
+struct IdMap {
+    const uint32_t *cantor2dense;   // block_id -> dense base of that block (0xFFFFFFFF if unknown)
+    long long max_block_id;
+    long long nvox_block;
+};
+__device__ __forceinline__ uint32_t id_to_dense(const IdMap &m, uint64_t id) {
+    if (id == 0) return 0xFFFFFFFFu;
+    // floor(id / nvox) through a round-towards-zero double division: exact for id < 2^53
+    uint64_t bid = (uint64_t)__double2ull_rz(__ddiv_rz((double)id, (double)m.nvox_block));
+    if ((long long)bid > m.max_block_id) return 0xFFFFFFFFu;
+    uint32_t base = m.cantor2dense[bid];
+    if (base == 0xFFFFFFFFu) return 0xFFFFFFFFu;
+    return base + (uint32_t)(id - bid * (uint64_t)m.nvox_block) - 1u;
+}
+
 // L2-coherent accesses for data exchanged between lanes / CTAs inside one kernel
 __device__ __forceinline__ uint32_t ld_cg(const uint32_t *p) { return __ldcg(p); }
 __device__ __forceinline__ void st_cg(uint32_t *p, uint32_t v) { __stcg(p, v); }

@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(256) k_coldist(const Tile *__restrict__ tiles,
         long long i = i0 + threadIdx.x;
         uint32_t best = 0;
         if (i < npix) {
-            int x = (int)(i % W);
-            int y = (int)((i / W) % H);
+            int x, y, zq;
+            unravel3(i, W, H, x, y, zq);
             const uint16_t *gp = g + t.base + i;
             uint32_t g0 = gp[0];
             best = g0 == GINF ? DBIG : g0 * g0;
@@ -203,9 +203,8 @@ __global__ void __launch_bounds__(256) k_zdist(const Tile *__restrict__ tiles, c
     for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < npix; i0 += (long long)gridDim.x * blockDim.x) {
         long long i = i0 + threadIdx.x;
         if (i < npix) {
-            int x = (int)(i % W);
-            int y = (int)((i / W) % H);
-            int z = (int)(i / HW);
+            int x, y, z;
+            unravel3(i, W, H, x, y, z);
             const uint32_t *ip = in + t.base + i;
             uint32_t best = ip[0];
             for (int dz = 1;; dz++) {
@@ -242,9 +241,8 @@ __global__ void __launch_bounds__(256) k_maxfilt(const Tile *__restrict__ tiles,
     const int W = t.W, H = t.H, D = t.D;
     const long long HW = (long long)H * W, npix = (long long)D * HW;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
-        int x = (int)(i % W);
-        int y = (int)((i / W) % H);
-        int z = (int)(i / HW);
+        int x, y, z;
+        unravel3(i, W, H, x, y, z);
         int c, L;
         long long st;
         if (axis == 2) {
@@ -283,9 +281,8 @@ __global__ void __launch_bounds__(256) k_seed_union(const Tile *__restrict__ til
     uint32_t *pp = par + t.base;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
         if (__ldcg(&pp[i]) == NONE32) continue;
-        int x = (int)(i % W);
-        int y = (int)((i / W) % H);
-        int z = (int)(i / HW);
+        int x, y, z;
+        unravel3(i, W, H, x, y, z);
         if (x > 0 && __ldcg(&pp[i - 1]) != NONE32) uf_union(pp, (uint32_t)i, (uint32_t)(i - 1));
         if (y > 0 && __ldcg(&pp[i - W]) != NONE32) uf_union(pp, (uint32_t)i, (uint32_t)(i - W));
         if (z > 0 && __ldcg(&pp[i - HW]) != NONE32) uf_union(pp, (uint32_t)i, (uint32_t)(i - HW));
@@ -303,6 +300,11 @@ __global__ void __launch_bounds__(256) k_seed_label_hist(const Tile *__restrict_
     const uint32_t *pp = par + t.base;
     const uint32_t hb = hbase[blockIdx.y];
     const uint32_t s0 = compact_labels ? sscan[t.base] : 0;
+    // most mask pixels carry a small d2: privatise the low part of the histogram per CTA
+    constexpr int SH = 2048;
+    __shared__ uint32_t sh[SH];
+    for (int j = threadIdx.x; j < SH; j += blockDim.x) sh[j] = 0;
+    __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
         uint32_t l = 0;
         if (msk[t.base + i]) {
@@ -312,10 +314,17 @@ __global__ void __launch_bounds__(256) k_seed_label_hist(const Tile *__restrict_
                 // label = root pixel + 1, or (flood v2) the root's rank among the tile's seed pixels + 1
                 l = compact_labels ? sscan[t.base + root] - s0 + 1 : root + 1;
             }
-            atomicAdd(&hist[hb + d2[t.base + i]], 1u);
+            uint32_t d = d2[t.base + i];
+            if (d < SH)
+                atomicAdd(&sh[d], 1u);
+            else
+                atomicAdd(&hist[hb + d], 1u);
         }
         lab[t.base + i] = l;
     }
+    __syncthreads();
+    for (int j = threadIdx.x; j < SH; j += blockDim.x)
+        if (sh[j]) atomicAdd(&hist[hb + j], sh[j]);
 }
 
 __global__ void k_tile_hsize(const uint32_t *__restrict__ tilemax, uint32_t *__restrict__ hsize, int ntiles) {
@@ -811,9 +820,8 @@ __global__ void __launch_bounds__(256) k_fragstats(const Tile *__restrict__ tile
             if (l >= CLAIM) l = 0;
             if (l) {
                 // a labelled pixel is inside the mask, hence inside the volume and not masked out
-                int x = (int)(i % W);
-                int y = (int)((i / W) % H);
-                int z = (int)(i / HW);
+                int x, y, z;
+                unravel3(i, W, H, x, y, z);
                 size_t gi = ((size_t)(t.gz + z - A.z0) * A.Y + (t.gy + y)) * A.X + (t.gx + x);
                 val = AffOps<T>::value(a, nvol, gi);
             }
@@ -848,6 +856,16 @@ __device__ __forceinline__ bool frag_keep(ACC sum, uint32_t cnt, double ff, int 
     return true;
 }
 
+// one decision per fragment (entries with a non-zero count are fragment roots): fcnt becomes keep ? 1 : 0
+template <typename ACC>
+__global__ void __launch_bounds__(256) k_frag_decide(const ACC *__restrict__ fsum, uint32_t *__restrict__ fcnt, size_t n,
+                                                     double ff, int rd, int is_u8) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c = fcnt[i];
+    if (c) fcnt[i] = frag_keep<ACC>(fsum[i], c, ff, rd, is_u8 != 0) ? 1u : 0u;
+}
+
 // cpar (tile-local parent, only write-region pixels participate): NONE32 if dropped, else the start of
 // the pixel's row run of equal labels inside its warp chunk (pre-linked rows keep union-find chains short)
 template <typename ACC>
@@ -859,15 +877,12 @@ __global__ void __launch_bounds__(256) k_crop_init(const Tile *__restrict__ tile
     const long long HW = (long long)H * W, npix = (long long)t.D * HW;
     const int lane = threadIdx.x & 31;
     auto kept_label = [&](long long i) -> uint32_t {
-        int x = (int)(i % W);
-        int y = (int)((i / W) % H);
-        int z = (int)(i / HW);
+        int x, y, z;
+        unravel3(i, W, H, x, y, z);
         if (z >= t.wz && z < t.wz + t.wD && y >= t.wy && y < t.wy + t.wH && x >= t.wx && x < t.wx + t.wW) {
             uint32_t l = lab[t.base + i];
             if (l && l < CLAIM) {
-                bool keep = true;
-                if (ff > 0.0 || rd > 0) keep = frag_keep<ACC>(fsum[t.base + l - 1], fcnt[t.base + l - 1], ff, rd, is_u8 != 0);
-                if (keep) return l;
+                if (!(ff > 0.0 || rd > 0) || fcnt[t.base + l - 1]) return l;
             }
         }
         return 0;
@@ -877,7 +892,7 @@ __global__ void __launch_bounds__(256) k_crop_init(const Tile *__restrict__ tile
         uint32_t l = i < npix ? kept_label(i) : 0;
         uint32_t ll = __shfl_up_sync(FULL, l, 1);
         if (lane == 0) ll = (l && i > 0) ? kept_label(i - 1) : 0;
-        bool sl = l && (i % W) != 0 && ll == l;
+        bool sl = l && ((uint32_t)i % (uint32_t)W) != 0 && ll == l;
         unsigned startbits = __ballot_sync(FULL, l && !sl);
         if (i < npix) {
             uint32_t v = NONE32;
@@ -901,9 +916,8 @@ __global__ void __launch_bounds__(256) k_crop_union(const Tile *__restrict__ til
     const uint32_t *ll = lab + t.base;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
         if (__ldcg(&pp[i]) == NONE32) continue;
-        int x = (int)(i % W);
-        int y = (int)((i / W) % H);
-        int z = (int)(i / HW);
+        int x, y, z;
+        unravel3(i, W, H, x, y, z);
         const uint32_t l = ll[i];
         auto same = [&](long long j) -> bool { return ll[j] == l && __ldcg(&pp[j]) != NONE32; };
         const bool left = x > 0 && same(i - 1);
@@ -949,17 +963,16 @@ __global__ void __launch_bounds__(256) k_crop_flatten(const Tile *__restrict__ t
     const long long nw = (long long)t.wD * t.wH * t.wW;
     const uint32_t *pp = cpar + t.base;
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nw; k += (long long)gridDim.x * blockDim.x) {
-        int x = (int)(k % t.wW) + t.wx;
-        int y = (int)((k / t.wW) % t.wH) + t.wy;
-        int z = (int)(k / ((long long)t.wW * t.wH)) + t.wz;
+        int x, y, z;
+        unravel3(k, t.wW, t.wH, x, y, z);
+        x += t.wx, y += t.wy, z += t.wz;
         long long i = (long long)z * HW + (long long)y * W + x;
         uint32_t r = NONE32;
         uint8_t ir = 0;
         if (pp[i] != NONE32) {
             uint32_t root = uf_find(pp, (uint32_t)i);
-            int rz = root / HW;
-            int rr = root - rz * HW;
-            int ry = rr / W, rx = rr - ry * W;
+            int rx, ry, rz;
+            unravel3(root, W, H, rx, ry, rz);
             r = (uint32_t)tile_widx(t, rz, ry, rx);
             ir = root == (uint32_t)i;
         }
@@ -991,9 +1004,7 @@ __global__ void __launch_bounds__(256) k_finalize(const BlkDev *__restrict__ blk
         uint32_t node = NONE32;
         int x = 0, y = 0, z = 0;
         if (k < nw) {
-            x = (int)(k % b.ws[2]);
-            y = (int)((k / b.ws[2]) % b.ws[1]);
-            z = (int)(k / ((long long)b.ws[2] * b.ws[1]));
+            unravel3(k, b.ws[2], b.ws[1], x, y, z);
             uint32_t r = croot[b.wbase + k];
             uint64_t id = 0;
             if (r != NONE32) {
@@ -1289,6 +1300,9 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     BS_TRY(fcnt.alloc_zero(need_stats ? (size_t)P_pix * 4 : 16, s));
     if (need_stats)
         BS_LAUNCH((k_fragstats<T>), grid, 256, 0, s, dt, A, lab.as<uint32_t>(), fsum.as<acc_t>(), fcnt.as<uint32_t>());
+    if (need_stats)
+        BS_LAUNCH((k_frag_decide<acc_t>), cdiv((size_t)P_pix, 256), 256, 0, s, fsum.as<acc_t>(), fcnt.as<uint32_t>(), (size_t)P_pix,
+                  cfg.filter_fragments, cfg.remove_debris, sizeof(T) == 1 ? 1 : 0);
     g_prof.mark("s1.crop_cc", s);
     // cpar reuses lv
     BS_LAUNCH((k_crop_init<acc_t>), grid, 256, 0, s, dt, lab.as<uint32_t>(), fsum.as<acc_t>(), fcnt.as<uint32_t>(),

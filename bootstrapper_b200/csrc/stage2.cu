@@ -31,21 +31,6 @@ struct S2Blk {
     long long view_block_id[27];
 };
 
-struct IdMap {
-    const uint32_t *cantor2dense;   // block_id -> dense base of that block (NONE32 if unknown)
-    long long max_block_id;
-    long long nvox_block;
-};
-
-__device__ __forceinline__ uint32_t id_to_dense(const IdMap &m, uint64_t id) {
-    if (id == 0) return NONE32;
-    uint64_t bid = id / (uint64_t)m.nvox_block;
-    if ((long long)bid > m.max_block_id) return NONE32;
-    uint32_t base = m.cantor2dense[bid];
-    if (base == NONE32) return NONE32;
-    return base + (uint32_t)(id - bid * (uint64_t)m.nvox_block) - 1u;
-}
-
 __device__ __forceinline__ uint64_t hash64(uint64_t k) {
     k ^= k >> 33;
     k *= 0xff51afd7ed558ccdull;
@@ -86,9 +71,7 @@ __global__ void __launch_bounds__(256) k_rag_accumulate(const S2Blk *__restrict_
         uint32_t id1 = NONE32;
         int x = 0, y = 0, z = 0, gx = 0, gy = 0, gz = 0;
         if (i < nvox) {
-            x = (int)(i % RX);
-            y = (int)((i / RX) % RY);
-            z = (int)(i / ((long long)RX * RY));
+            unravel3(i, RX, RY, x, y, z);
             gz = b.ro[0] + z, gy = b.ro[1] + y, gx = b.ro[2] + x;
             // fragments array covers the task ROI; outside: zero fill
             int fz = gz - roz, fy = gy - roy, fx = gx - rox;

@@ -2,6 +2,8 @@
 //
 // Replaces funlib.segment.graphs.impl.connected_components (post/watershed.py:177-182, U7: edges
 // with score <= threshold, float32 compare), volara LUT + Relabel (post/watershed.py:187-202).
+#include <algorithm>
+
 #include "geom.h"
 
 namespace bs {
@@ -82,6 +84,54 @@ int relabel(const uint64_t *frags, int64_t n, const uint64_t *keys, const uint64
     if (n == 0) return BS_OK;
     unsigned grid = (unsigned)std::min<size_t>(cdiv(n, 256), 148 * 16 * 8);
     BS_LAUNCH(k_relabel, grid, 256, 0, s, frags, (size_t)n, keys, vals, (uint32_t)k, seg);
+    BS_CUDA(cudaGetLastError());
+    return BS_OK;
+}
+
+// ---- Relabel of all thresholds in one pass: the LUT is indexed by the dense node number derived from the id
+struct RelabelSet {
+    const uint64_t *comp[8];
+    uint64_t *seg[8];
+    int T;
+};
+
+__global__ void __launch_bounds__(256) k_relabel_dense(const uint64_t *__restrict__ frags, size_t n, IdMap idm, uint32_t n_nodes,
+                                                       RelabelSet rs) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t id = frags[i];
+        uint32_t d = id_to_dense(idm, id);
+        bool hit = d != NONE32 && d < n_nodes;
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+            if (t < rs.T) rs.seg[t][i] = hit ? rs.comp[t][d] : id;
+    }
+}
+
+int relabel_dense(Plan &P, const uint64_t *frags, int64_t n, const uint64_t *const *comps, int T, uint64_t *const *segs,
+                  cudaStream_t s) {
+    BS_ARG(T >= 1 && T <= 8, "bs_stage3_relabel: 1..8 thresholds per call");
+    if (n == 0) return BS_OK;
+    const size_t nblocks = P.blocks.size();
+    long long max_bid = 0;
+    for (auto &b : P.blocks) max_bid = std::max(max_bid, b.block_id);
+    std::vector<uint32_t> c2d((size_t)max_bid + 1, NONE32);
+    for (size_t i = 0; i < nblocks; i++) c2d[P.blocks[i].block_id] = (uint32_t)P.block_nbase[i];
+    DevBuf d_c2d;
+    BS_TRY(d_c2d.alloc(4 * c2d.size(), s));
+    BS_CUDA(cudaMemcpyAsync(d_c2d.p, c2d.data(), 4 * c2d.size(), cudaMemcpyHostToDevice, s));
+    IdMap idm;
+    idm.cantor2dense = d_c2d.as<uint32_t>();
+    idm.max_block_id = max_bid;
+    idm.nvox_block = P.nvox_block;
+    RelabelSet rs;
+    rs.T = T;
+    for (int t = 0; t < 8; t++) {
+        rs.comp[t] = t < T ? comps[t] : nullptr;
+        rs.seg[t] = t < T ? segs[t] : nullptr;
+    }
+    unsigned grid = (unsigned)std::min<size_t>(cdiv(n, 256), 148 * 16 * 8);
+    BS_LAUNCH(k_relabel_dense, grid, 256, 0, s, frags, (size_t)n, idm, (uint32_t)P.block_nbase[nblocks], rs);
+    BS_CUDA(cudaStreamSynchronize(s));   // c2d is a host-staged copy
     BS_CUDA(cudaGetLastError());
     return BS_OK;
 }

@@ -36,7 +36,7 @@ EXPORTS = [
     "bs_last_error", "bs_launch_count", "bs_version", "bs_plan_create", "bs_plan_destroy", "bs_plan_num_blocks",
     "bs_plan_block_info", "bs_plan_set_owned", "bs_stage1_fragments", "bs_stage1_num_nodes", "bs_stage1_get_nodes",
     "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_stage2_agglomerate", "bs_stage2_num_edges",
-    "bs_stage2_get_edges", "bs_connected_components", "bs_relabel", "bs_watershed_from_affinities",
+    "bs_stage2_get_edges", "bs_connected_components", "bs_relabel", "bs_stage3_relabel", "bs_watershed_from_affinities",
     "bs_synth_affs", "bs_debug_fetch", "bs_set_debug", "bs_set_profiling", "bs_get_profile",
     "bs_release_scratch", "bs_set_flood_version", "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
 ]
@@ -224,6 +224,19 @@ class Plan:
         s = torch.empty(n, dtype=torch.float32, device=device)
         _check(lib().bs_stage2_get_edges(self._h, _dev(u), _dev(v), _dev(s), _stream()))
         return u, v, s
+
+    # ---- stage 3
+    def relabel(self, frags, comps, outs=None):
+        """all thresholds in one pass; comps: list of (N,) LUT value tensors in ascending node-id order"""
+        T = len(comps)
+        if outs is None:
+            outs = [torch.empty_like(frags) for _ in range(T)]
+        cp = (C.c_void_p * T)(*[c.data_ptr() for c in comps])
+        sp = (C.c_void_p * T)(*[o.data_ptr() for o in outs])
+        for t in list(comps) + list(outs):
+            _dev(t, torch.int64)
+        _check(lib().bs_stage3_relabel(self._h, _dev(frags, torch.int64), C.c_int64(frags.numel()), cp, C.c_int(T), sp, _stream()))
+        return outs
 
     # ---- debug
     def debug_fetch(self, name, dtype):

@@ -66,11 +66,13 @@ def segment_blockwise(affs, params=None, block_size=None, context=None, roi=None
     node_ids, node_pos, node_size = plan.nodes(dev)
     plan.agglomerate(affs, frags)
     eu, ev, es = plan.edges(dev)
-    luts, segs = {}, {}
-    for i, thr in enumerate(p["thresholds"]):
-        comp = native.connected_components(node_ids, eu, ev, es, float(thr))
-        luts[thr] = comp
-        seg_out = None if out is None else out["segs"][i]
-        segs[thr] = native.relabel(frags, node_ids, comp, out=seg_out)
+    thrs = list(p["thresholds"])
+    comps = [native.connected_components(node_ids, eu, ev, es, float(thr)) for thr in thrs]
+    luts = dict(zip(thrs, comps))
+    segs = {}
+    for i in range(0, len(thrs), 8):           # Relabel: up to 8 thresholds per pass over the fragments
+        outs = None if out is None else out["segs"][i:i + 8]
+        for thr, sg in zip(thrs[i:i + 8], plan.relabel(frags, comps[i:i + 8], outs)):
+            segs[thr] = sg
     return dict(fragments=frags, nodes=(node_ids, node_pos, node_size), edges=(eu, ev, es), luts=luts, segs=segs,
                 plan=plan, params=p)

@@ -166,11 +166,14 @@ class ShardedSegmenter:
         eu, ev, es = allgather_edges(eu, ev, es, self.world, self.group)
         nodes = global_node_ids(self.block_ids, counts, self.nvox_block, affs_win.device)
         own = frags[g["z0"] - g["w0"]:g["z1"] - g["w0"]]
-        segs, luts = {}, {}
-        for i, thr in enumerate(self.p["thresholds"]):
-            comp = native.connected_components(nodes, eu, ev, es, float(thr))
-            luts[thr] = comp
-            segs[thr] = native.relabel(own, nodes, comp, out=None if out is None else out[i])
+        thrs = list(self.p["thresholds"])
+        comps = [native.connected_components(nodes, eu, ev, es, float(thr)) for thr in thrs]
+        luts = dict(zip(thrs, comps))
+        segs = {}
+        own = own.contiguous()
+        for i in range(0, len(thrs), 8):
+            for thr, sg in zip(thrs[i:i + 8], plan.relabel(own, comps[i:i + 8], None if out is None else out[i:i + 8])):
+                segs[thr] = sg
         ev1.record()
         ev1.synchronize()
         prof["s3.cc_relabel"] = ev0.elapsed_time(ev1)

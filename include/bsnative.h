@@ -123,6 +123,13 @@ int bs_connected_components(const uint64_t *nodes, int64_t n, const uint64_t *ed
 int bs_relabel(const uint64_t *frags, int64_t n_vox, const uint64_t *lut_keys, const uint64_t *lut_vals,
                int64_t n_lut, uint64_t *seg_out, void *stream);
 
+/* Relabel for up to 8 thresholds in one pass over the fragments (volara Relabel, post/watershed.py:192-202):
+ * components[t] is the LUT value row for threshold t, indexed by node in ascending-id order (all nodes of the
+ * task, i.e. the plan must know every block's fragment count); ids unknown to the plan are copied through.
+ * `components` / `segs_out` are HOST arrays of device pointers. */
+int bs_stage3_relabel(bs_plan *p, const uint64_t *frags, int64_t n_vox, const uint64_t *const *components, int n_thresholds,
+                      uint64_t *const *segs_out, void *stream);
+
 /* ---- post/ws.py plug point ----------------------------------------------------------
  * replaces: watershed_from_affinities(affs, max_affinity_value, fragments_in_xy,
  * return_seeds, min_seed_distance) (post/ws.py:38-112) on one in-memory array.
