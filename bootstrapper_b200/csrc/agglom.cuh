@@ -1,0 +1,60 @@
+// Shared declarations of the waterz agglomeration kernels (stage2.cu, agglom_smem.cu, agglom_pq.cu).
+// Internal header.
+#pragma once
+#include "geom.h"
+
+namespace bs {
+
+struct AggArrays {
+    // edges (global index = ebase[b] + local); eu / ev are block-compact node numbers
+    uint32_t *eu, *ev, *ecnt, *etime;
+    unsigned long long *esum;
+    float *escore;
+    uint8_t *edead;
+    // nodes (global index = vbase + compact number)
+    uint32_t *ufp, *stamp, *ahead, *atail, *tnode;
+    // adjacency chunks
+    uint32_t *centries, *cnext;
+    // pair hash (per block range hbase/hcap)
+    unsigned long long *pkeys;
+    uint32_t *pvals;
+    // queue chunk pool
+    uint32_t *qentries, *qnext;
+    // merge tree (per block base 2*vbase) and history (base vbase)
+    uint32_t *tparent, *tlevel;
+    float *tscore;
+    uint32_t *ha, *hb;
+    float *hs;
+    uint32_t *nmerges;
+    uint32_t *counters;   // per block: pops, stale, dead, iterations, chunk steps, append rounds
+    uint32_t *error;
+};
+
+struct AggBlk {
+    uint32_t ebase, E, vbase, nv, hbase, hcap, qbase, qcap;
+};
+
+template <bool U8>
+__device__ __forceinline__ float edge_score(unsigned long long isum, uint32_t cnt) {
+    // OneMinus<MeanAffinity>: (float)(1.0 - mean), mean = float(sum) / float(count)   (oracle edge_score)
+    float sum;
+    if (U8)
+        sum = __double2float_rn(__ddiv_rn((double)isum, 255.0));
+    else
+        sum = __double2float_rn(ldexp((double)(long long)isum, -38));
+    float mean = __fdiv_rn(sum, __uint2float_rn(cnt));
+    return __double2float_rn(__dsub_rn(1.0, (double)mean));
+}
+
+__device__ __forceinline__ int score_bin(float score, int nbins) {
+    int i = (int)__fmul_rn(score, (float)nbins);
+    return min(max(0, i), nbins - 1);
+}
+
+// agglom_smem.cu: BinQueue<256> agglomeration with the whole block state in shared memory.
+// `list` (device) = indices into blks of the blocks to process; u8 selects the affinity sum scaling.
+size_t agglom_smem_bytes(uint32_t Ecap, uint32_t Ncap, bool sum64);
+int agglom_smem_launch(const AggBlk *blks, const int *list, int nlist, const AggArrays &A, float threshold, int keep_cheaper,
+                       bool u8, bool sum64, uint32_t Ecap, uint32_t Ncap, cudaStream_t s);
+
+}  // namespace bs

@@ -7,6 +7,7 @@
 
 namespace bs {
 int g_debug = 0;
+int g_agglom_version = 0;  // 0 = auto (shared-memory kernel when the block fits), 1 = force the global-memory kernel
 int g_flood_version = 0;   // 0 = auto (v2 when eligible), 1 = force the global-memory flood
 int stage1_run(Plan &P, const void *affs, const uint8_t *mask, uint64_t *frags_out, cudaStream_t s);
 int stage2_run(Plan &P, const void *affs, const uint64_t *frags, cudaStream_t s);
@@ -58,6 +59,11 @@ static void init_mempool() {
 
 int bs_set_flood_version(int v) {
     g_flood_version = v;
+    return BS_OK;
+}
+
+int bs_set_agglom_version(int v) {
+    g_agglom_version = v;
     return BS_OK;
 }
 

@@ -6,11 +6,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libbsnative.so")
-SOURCES = ["prims.cu", "plan.cu", "stage1.cu", "stage2.cu", "stage3.cu", "synth.cu", "api.cu"]
-HEADERS = ["common.cuh", "geom.h", os.path.join("..", "..", "include", "bsnative.h")]
+SOURCES = ["prims.cu", "plan.cu", "stage1.cu", "stage2.cu", "agglom_smem.cu", "stage3.cu", "synth.cu", "api.cu"]
+HEADERS = ["common.cuh", "geom.h", "agglom.cuh", os.path.join("..", "..", "include", "bsnative.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-         "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + (["-DBS_TRACE"] if os.environ.get("BS_TRACE") else [])
 
 
 def needs_build():

@@ -10,7 +10,7 @@
 //   write_graph ownership (:170)               -> edge kept by the block that owns node min(u, v)
 #include <algorithm>
 
-#include "geom.h"
+#include "agglom.cuh"
 
 namespace bs {
 
@@ -19,6 +19,7 @@ static constexpr uint64_t EMPTY64 = 0xFFFFFFFFFFFFFFFFull;
 static constexpr uint64_t TOMB64 = 0xFFFFFFFFFFFFFFFEull;
 static constexpr unsigned FULL = 0xFFFFFFFFu;
 extern int g_debug;
+extern int g_agglom_version;   // 0 = shared-memory kernel when the block fits, 1 = force the global-memory kernel
 
 struct S2Blk {
     long long block_id;
@@ -208,6 +209,37 @@ __global__ void k_edge_gather(const S2Blk *__restrict__ blks, const uint32_t *__
     atomicAdd(&deg[b.vbase + v], 1u);
 }
 
+// ---- block-compact node numbering: only fragments that carry at least one edge of the block take part in
+// the agglomeration (the view of a block spans the fragments of all 27 neighbouring blocks)
+__global__ void k_used_flag(const uint32_t *__restrict__ deg, uint8_t *__restrict__ used, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) used[i] = deg[i] ? 1 : 0;
+}
+
+__global__ void k_block_cbase(const S2Blk *__restrict__ blks, int nblk, const uint32_t *__restrict__ cscan, uint32_t nview,
+                              const uint32_t *__restrict__ ctotal, uint32_t *__restrict__ cbase) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nblk) cbase[i] = blks[i].vbase < nview ? cscan[blks[i].vbase] : *ctotal;
+    if (i == nblk) cbase[i] = *ctotal;
+}
+
+__global__ void k_compact_endpoints(const S2Blk *__restrict__ blks, const uint32_t *__restrict__ eblk,
+                                    const uint32_t *__restrict__ eu, const uint32_t *__restrict__ ev, uint32_t E,
+                                    const uint32_t *__restrict__ cscan, uint32_t *__restrict__ ceu, uint32_t *__restrict__ cev) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const uint32_t vb = blks[eblk[e]].vbase;
+    const uint32_t c0 = cscan[vb];
+    ceu[e] = cscan[vb + eu[e]] - c0;
+    cev[e] = cscan[vb + ev[e]] - c0;
+}
+
+__global__ void k_compact_deg(const uint32_t *__restrict__ deg, const uint32_t *__restrict__ cscan, size_t n,
+                              uint32_t *__restrict__ cdeg) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && deg[i]) cdeg[cscan[i]] = deg[i];
+}
+
 __global__ void k_nchunks(const uint32_t *__restrict__ deg, uint32_t *__restrict__ nch, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) nch[i] = (deg[i] + 31) >> 5;
@@ -230,14 +262,14 @@ __global__ void k_adj_nodes(const uint32_t *__restrict__ deg, const uint32_t *__
     for (uint32_t c = 0; c < nc; c++) cnext[c0 + c] = c + 1 < nc ? c0 + c + 1 : NONE32;
 }
 
-__global__ void k_adj_fill(const S2Blk *__restrict__ blks, const uint32_t *__restrict__ ebase, const uint32_t *__restrict__ eblk,
-                           const uint32_t *__restrict__ eu, const uint32_t *__restrict__ ev, uint32_t E,
+__global__ void k_adj_fill(const uint32_t *__restrict__ cbase, const uint32_t *__restrict__ ebase, const uint32_t *__restrict__ eblk,
+                           const uint32_t *__restrict__ ceu, const uint32_t *__restrict__ cev, uint32_t E,
                            const uint32_t *__restrict__ cstart, uint32_t *__restrict__ cursor, uint32_t *__restrict__ centries) {
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
-    const S2Blk &b = blks[eblk[e]];
+    const uint32_t cb = cbase[eblk[e]];
     uint32_t el = e - ebase[eblk[e]];
-    uint32_t nu = b.vbase + eu[e], nv = b.vbase + ev[e];
+    uint32_t nu = cb + ceu[e], nv = cb + cev[e];
     uint32_t pu = atomicAdd(&cursor[nu], 1u);
     centries[(size_t)cstart[nu] * 32 + pu] = el;
     uint32_t pv = atomicAdd(&cursor[nv], 1u);
@@ -245,52 +277,6 @@ __global__ void k_adj_fill(const S2Blk *__restrict__ blks, const uint32_t *__res
 }
 
 // ------------------------------------------------------------------ agglomeration
-struct AggArrays {
-    // edges (global index = ebase[b] + local)
-    uint32_t *eu, *ev, *ecnt, *etime;
-    unsigned long long *esum;
-    float *escore;
-    uint8_t *edead;
-    // nodes (global index = vbase + local)
-    uint32_t *ufp, *stamp, *ahead, *atail, *tnode;
-    // adjacency chunks
-    uint32_t *centries, *cnext;
-    // pair hash (per block range hbase/hcap)
-    unsigned long long *pkeys;
-    uint32_t *pvals;
-    // queue chunk pool
-    uint32_t *qentries, *qnext;
-    // merge tree (per block base 2*vbase) and history (base vbase)
-    uint32_t *tparent, *tlevel;
-    float *tscore;
-    uint32_t *ha, *hb;
-    float *hs;
-    uint32_t *nmerges;
-    uint32_t *counters;   // per block: pops, stale, dead
-    uint32_t *error;
-};
-
-struct AggBlk {
-    uint32_t ebase, E, vbase, nv, hbase, hcap, qbase, qcap;
-};
-
-template <bool U8>
-__device__ __forceinline__ float edge_score(unsigned long long isum, uint32_t cnt) {
-    // OneMinus<MeanAffinity>: (float)(1.0 - mean), mean = float(sum) / float(count)   (oracle edge_score)
-    float sum;
-    if (U8)
-        sum = __double2float_rn(__ddiv_rn((double)isum, 255.0));
-    else
-        sum = __double2float_rn(ldexp((double)(long long)isum, -38));
-    float mean = __fdiv_rn(sum, __uint2float_rn(cnt));
-    return __double2float_rn(__dsub_rn(1.0, (double)mean));
-}
-
-__device__ __forceinline__ int score_bin(float score, int nbins) {
-    int i = (int)__fmul_rn(score, (float)nbins);
-    return min(max(0, i), nbins - 1);
-}
-
 __device__ __forceinline__ uint32_t agg_find(uint32_t *ufp, uint32_t x) {
     // path halving; concurrent lanes only ever write ancestors
     for (;;) {
@@ -339,10 +325,11 @@ struct BinQ {
 };
 
 template <bool U8>
-__global__ void __launch_bounds__(32) k_agglomerate(const AggBlk *__restrict__ blks, AggArrays A, float threshold, int nbins,
-                                                    int keep_cheaper) {
+__global__ void __launch_bounds__(32) k_agglomerate(const AggBlk *__restrict__ blks, const int *__restrict__ list, AggArrays A,
+                                                    float threshold, int nbins, int keep_cheaper) {
     __shared__ BinQ Q;
-    const AggBlk B = blks[blockIdx.x];
+    const int bi = list[blockIdx.x];
+    const AggBlk B = blks[bi];
     const int lane = threadIdx.x;
     uint32_t *eu = A.eu + B.ebase, *ev = A.ev + B.ebase, *ecnt = A.ecnt + B.ebase, *etime = A.etime + B.ebase;
     unsigned long long *esum = A.esum + B.ebase;
@@ -664,30 +651,32 @@ __global__ void __launch_bounds__(32) k_agglomerate(const AggBlk *__restrict__ b
         __syncwarp();
     }
     if (lane == 0) {
-        A.nmerges[blockIdx.x] = nmerge;
-        A.counters[6 * blockIdx.x + 0] = n_pops;
-        A.counters[6 * blockIdx.x + 1] = n_stale;
-        A.counters[6 * blockIdx.x + 2] = n_dead;
-        A.counters[6 * blockIdx.x + 3] = n_iter;
-        A.counters[6 * blockIdx.x + 4] = n_chunk;
-        A.counters[6 * blockIdx.x + 5] = n_append;
+        A.nmerges[bi] = nmerge;
+        A.counters[6 * bi + 0] = n_pops;
+        A.counters[6 * bi + 1] = n_stale;
+        A.counters[6 * bi + 2] = n_dead;
+        A.counters[6 * bi + 3] = n_iter;
+        A.counters[6 * bi + 4] = n_chunk;
+        A.counters[6 * bi + 5] = n_append;
         if (fail) atomicExch(A.error, 1u);
     }
 }
 
 // ------------------------------------------------------------------ merge-tree score of every initial edge
 // post/merge_tree.py:5-27: climb from the lower-level side until both sides meet; NaN if they never do.
-__global__ void k_lca(const S2Blk *__restrict__ blks, const uint32_t *__restrict__ ebase, const uint32_t *__restrict__ eblk,
-                      const uint32_t *__restrict__ eu, const uint32_t *__restrict__ ev, uint32_t E,
-                      const uint32_t *__restrict__ tparent, const uint32_t *__restrict__ tlevel, const float *__restrict__ tscore,
-                      long long nvox_block, uint64_t *__restrict__ out_u, uint64_t *__restrict__ out_v, float *__restrict__ out_s,
+__global__ void k_lca(const S2Blk *__restrict__ blks, const uint32_t *__restrict__ cbase, const uint32_t *__restrict__ eblk,
+                      const uint32_t *__restrict__ eu, const uint32_t *__restrict__ ev, const uint32_t *__restrict__ ceu,
+                      const uint32_t *__restrict__ cev, uint32_t E, const uint32_t *__restrict__ tparent,
+                      const uint32_t *__restrict__ tlevel, const float *__restrict__ tscore, long long nvox_block,
+                      uint64_t *__restrict__ out_u, uint64_t *__restrict__ out_v, float *__restrict__ out_s,
                       uint8_t *__restrict__ owned) {
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
     const S2Blk &b = blks[eblk[e]];
-    const uint32_t *tp = tparent + 2 * (size_t)b.vbase, *tl = tlevel + 2 * (size_t)b.vbase;
-    const float *ts = tscore + 2 * (size_t)b.vbase;
-    uint32_t u = eu[e], v = ev[e];
+    const size_t tb = 2 * (size_t)cbase[eblk[e]];
+    const uint32_t *tp = tparent + tb, *tl = tlevel + tb;
+    const float *ts = tscore + tb;
+    uint32_t u = ceu[e], v = cev[e];
     float score;
     for (;;) {
         if (u == v) {
@@ -898,37 +887,61 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
     skeys.release();
     svals.release();
 
-    // ---- adjacency chunk chains
+    // ---- block-compact node numbers (host sync: compact node count per block)
     g_prof.mark("s2.adjacency", s);
-    const size_t NCmax = Vtot + (size_t)E / 16 + 2;
-    DevBuf nch, cstart, ahead, atail, cnext, centries, cursor;
-    BS_TRY(nch.alloc(4 * (Vtot + 1), s));
-    BS_TRY(cstart.alloc(4 * (Vtot + 1), s));
-    BS_TRY(ahead.alloc(4 * (Vtot + 1), s));
-    BS_TRY(atail.alloc(4 * (Vtot + 1), s));
-    BS_TRY(cnext.alloc(4 * NCmax, s));
-    BS_TRY(centries.alloc_fill(4 * NCmax * 32, 0xFF, s));
-    BS_TRY(cursor.alloc_zero(4 * (Vtot + 1), s));
+    DevBuf used, cscan, cbase, ceu, cev;
+    BS_TRY(used.alloc(Vtot + 1, s));
+    BS_TRY(cscan.alloc(4 * (Vtot + 2), s));
+    BS_TRY(cbase.alloc(4 * (nown + 1), s));
+    BS_TRY(ceu.alloc(4 * ((size_t)E + 1), s));
+    BS_TRY(cev.alloc(4 * ((size_t)E + 1), s));
+    std::vector<uint32_t> h_cbase(nown + 1, 0);
     if (Vtot) {
-        BS_LAUNCH(k_nchunks, cdiv(Vtot, 256), 256, 0, s, deg.as<uint32_t>(), nch.as<uint32_t>(), Vtot);
-        BS_TRY(scan_exclusive_u32(nch.as<uint32_t>(), cstart.as<uint32_t>(), Vtot, nullptr, s));
-        BS_LAUNCH(k_adj_nodes, cdiv(Vtot, 256), 256, 0, s, deg.as<uint32_t>(), cstart.as<uint32_t>(), ahead.as<uint32_t>(),
-                  atail.as<uint32_t>(), cnext.as<uint32_t>(), Vtot);
+        BS_LAUNCH(k_used_flag, cdiv(Vtot, 256), 256, 0, s, deg.as<uint32_t>(), used.as<uint8_t>(), Vtot);
+        BS_TRY(scan_exclusive_u8(used.as<uint8_t>(), cscan.as<uint32_t>(), Vtot, tot.as<uint32_t>() + 2, s));
+        BS_LAUNCH(k_block_cbase, cdiv(nown + 1, 256), 256, 0, s, db, nown, cscan.as<uint32_t>(), (uint32_t)Vtot,
+                  tot.as<uint32_t>() + 2, cbase.as<uint32_t>());
+        if (E)
+            BS_LAUNCH(k_compact_endpoints, cdiv(E, 256), 256, 0, s, db, eblk.as<uint32_t>(), eu.as<uint32_t>(),
+                      ev.as<uint32_t>(), E, cscan.as<uint32_t>(), ceu.as<uint32_t>(), cev.as<uint32_t>());
+        BS_CUDA(cudaMemcpyAsync(h_cbase.data(), cbase.p, 4 * (nown + 1), cudaMemcpyDeviceToHost, s));
+        BS_CUDA(cudaStreamSynchronize(s));
     }
-    if (E)
-        BS_LAUNCH(k_adj_fill, cdiv(E, 256), 256, 0, s, db, ebase.as<uint32_t>(), eblk.as<uint32_t>(), eu.as<uint32_t>(),
-                  ev.as<uint32_t>(), E, cstart.as<uint32_t>(), cursor.as<uint32_t>(), centries.as<uint32_t>());
+    const size_t Ctot = h_cbase[nown];
 
-    // ---- agglomeration
-    g_prof.mark("s2.agglomerate", s);
+    // ---- which blocks fit the shared-memory kernel (agglom_smem.cu)
     std::vector<AggBlk> ab(nown);
-    uint64_t hcur = 0, qcur = 0;
+    std::vector<int> l_smem, l_glob;
+    uint32_t Emax = 8, Nmax = 8;
+    const bool u8 = sizeof(T) == 1;
+    bool sum64 = !u8;
     for (int i = 0; i < nown; i++) {
         AggBlk &a = ab[i];
         a.ebase = h_ebase[i];
         a.E = h_ebase[i + 1] - h_ebase[i];
-        a.vbase = hb[i].vbase;
-        a.nv = hb[i].nv;
+        a.vbase = h_cbase[i];
+        a.nv = h_cbase[i + 1] - h_cbase[i];
+        a.hbase = a.hcap = a.qbase = a.qcap = 0;
+        // u8 affinity sums of a whole block fit 32 bits when 3 * 255 * read voxels < 2^32
+        if (u8 && 765.0 * hb[i].rs[0] * hb[i].rs[1] * hb[i].rs[2] >= 4294967295.0) sum64 = true;
+    }
+    {
+        const size_t limit = 227 * 1024;
+        for (int i = 0; i < nown; i++) {
+            uint32_t Ec = (std::max<uint32_t>(ab[i].E, 8) + 7) & ~7u, Nc = (std::max<uint32_t>(ab[i].nv, 8) + 7) & ~7u;
+            bool fits = g_agglom_version != 1 && Ec <= 32760 && Nc <= 32760 && agglom_smem_bytes(Ec, Nc, sum64) <= limit;
+            if (fits && agglom_smem_bytes(std::max(Emax, Ec), std::max(Nmax, Nc), sum64) <= limit) {
+                Emax = std::max(Emax, Ec);
+                Nmax = std::max(Nmax, Nc);
+                l_smem.push_back(i);
+            } else {
+                l_glob.push_back(i);
+            }
+        }
+    }
+    uint64_t hcur = 0, qcur = 0;
+    for (int i : l_glob) {
+        AggBlk &a = ab[i];
         a.hcap = next_pow2((uint64_t)std::max<uint32_t>(64, 4 * a.E));
         a.hbase = (uint32_t)hcur;
         hcur += a.hcap;
@@ -937,31 +950,67 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
         qcur += a.qcap;
         BS_ARG(hcur < (1ull << 32), "stage2: pair hash exceeds 32-bit indexing");
     }
-    DevBuf d_ab, etime, escore, edead, ufp, stamp, tnode, pkeys, pvals, qentries, qnext, tparent, tlevel, tscore, ha, hbb, hs,
-        nmerges, counters, err;
+    const bool any_glob = !l_glob.empty();
+
+    // ---- adjacency chunk chains (global-memory kernel only)
+    const size_t NCmax = any_glob ? Ctot + (size_t)E / 16 + 2 : 1;
+    DevBuf cdeg, nch, cstart, ahead, atail, cnext, centries, cursor;
+    if (any_glob) {
+        BS_TRY(cdeg.alloc_zero(4 * (Ctot + 1), s));
+        BS_TRY(nch.alloc(4 * (Ctot + 1), s));
+        BS_TRY(cstart.alloc(4 * (Ctot + 1), s));
+        BS_TRY(ahead.alloc(4 * (Ctot + 1), s));
+        BS_TRY(atail.alloc(4 * (Ctot + 1), s));
+        BS_TRY(cnext.alloc(4 * NCmax, s));
+        BS_TRY(centries.alloc_fill(4 * NCmax * 32, 0xFF, s));
+        BS_TRY(cursor.alloc_zero(4 * (Ctot + 1), s));
+        if (Ctot) {
+            BS_LAUNCH(k_compact_deg, cdiv(Vtot, 256), 256, 0, s, deg.as<uint32_t>(), cscan.as<uint32_t>(), Vtot,
+                      cdeg.as<uint32_t>());
+            BS_LAUNCH(k_nchunks, cdiv(Ctot, 256), 256, 0, s, cdeg.as<uint32_t>(), nch.as<uint32_t>(), Ctot);
+            BS_TRY(scan_exclusive_u32(nch.as<uint32_t>(), cstart.as<uint32_t>(), Ctot, nullptr, s));
+            BS_LAUNCH(k_adj_nodes, cdiv(Ctot, 256), 256, 0, s, cdeg.as<uint32_t>(), cstart.as<uint32_t>(), ahead.as<uint32_t>(),
+                      atail.as<uint32_t>(), cnext.as<uint32_t>(), Ctot);
+        }
+        if (E)
+            BS_LAUNCH(k_adj_fill, cdiv(E, 256), 256, 0, s, cbase.as<uint32_t>(), ebase.as<uint32_t>(), eblk.as<uint32_t>(),
+                      ceu.as<uint32_t>(), cev.as<uint32_t>(), E, cstart.as<uint32_t>(), cursor.as<uint32_t>(),
+                      centries.as<uint32_t>());
+    }
+
+    // ---- agglomeration
+    g_prof.mark("s2.agglomerate", s);
+    DevBuf d_ab, d_list, etime, escore, edead, ufp, stamp, tnode, pkeys, pvals, qentries, qnext, tparent, tlevel, tscore, ha, hbb,
+        hs, nmerges, counters, err;
     BS_TRY(d_ab.alloc(sizeof(AggBlk) * nown, s));
     BS_CUDA(cudaMemcpyAsync(d_ab.p, ab.data(), sizeof(AggBlk) * nown, cudaMemcpyHostToDevice, s));
-    BS_TRY(etime.alloc(4 * ((size_t)E + 1), s));
-    BS_TRY(escore.alloc(4 * ((size_t)E + 1), s));
-    BS_TRY(edead.alloc(((size_t)E + 1), s));
-    BS_TRY(ufp.alloc(4 * (Vtot + 1), s));
-    BS_TRY(stamp.alloc(4 * (Vtot + 1), s));
-    BS_TRY(tnode.alloc(4 * (Vtot + 1), s));
-    BS_TRY(pkeys.alloc_fill(8 * (size_t)hcur, 0xFF, s));
-    BS_TRY(pvals.alloc(4 * (size_t)hcur, s));
-    BS_TRY(qentries.alloc(4 * (size_t)qcur * 32, s));
-    BS_TRY(qnext.alloc(4 * (size_t)qcur, s));
-    BS_TRY(tparent.alloc(4 * (2 * Vtot + 2), s));
-    BS_TRY(tlevel.alloc(4 * (2 * Vtot + 2), s));
-    BS_TRY(tscore.alloc(4 * (2 * Vtot + 2), s));
-    BS_TRY(ha.alloc(4 * (Vtot + 1), s));
-    BS_TRY(hbb.alloc(4 * (Vtot + 1), s));
-    BS_TRY(hs.alloc(4 * (Vtot + 1), s));
+    std::vector<int> h_list(l_smem);
+    h_list.insert(h_list.end(), l_glob.begin(), l_glob.end());
+    BS_TRY(d_list.alloc(sizeof(int) * (nown + 1), s));
+    BS_CUDA(cudaMemcpyAsync(d_list.p, h_list.data(), sizeof(int) * nown, cudaMemcpyHostToDevice, s));
+    if (any_glob) {
+        BS_TRY(etime.alloc(4 * ((size_t)E + 1), s));
+        BS_TRY(escore.alloc(4 * ((size_t)E + 1), s));
+        BS_TRY(edead.alloc(((size_t)E + 1), s));
+        BS_TRY(ufp.alloc(4 * (Ctot + 1), s));
+        BS_TRY(stamp.alloc(4 * (Ctot + 1), s));
+        BS_TRY(tnode.alloc(4 * (Ctot + 1), s));
+        BS_TRY(pkeys.alloc_fill(8 * (size_t)hcur, 0xFF, s));
+        BS_TRY(pvals.alloc(4 * (size_t)hcur, s));
+        BS_TRY(qentries.alloc(4 * (size_t)qcur * 32, s));
+        BS_TRY(qnext.alloc(4 * (size_t)qcur, s));
+    }
+    BS_TRY(tparent.alloc(4 * (2 * Ctot + 2), s));
+    BS_TRY(tlevel.alloc(4 * (2 * Ctot + 2), s));
+    BS_TRY(tscore.alloc(4 * (2 * Ctot + 2), s));
+    BS_TRY(ha.alloc(4 * (Ctot + 1), s));
+    BS_TRY(hbb.alloc(4 * (Ctot + 1), s));
+    BS_TRY(hs.alloc(4 * (Ctot + 1), s));
     BS_TRY(nmerges.alloc_zero(4 * nown, s));
     BS_TRY(counters.alloc_zero(24 * nown, s));
     BS_TRY(err.alloc_zero(16, s));
     AggArrays A;
-    A.eu = eu.as<uint32_t>(), A.ev = ev.as<uint32_t>(), A.ecnt = ecnt.as<uint32_t>(), A.etime = etime.as<uint32_t>();
+    A.eu = ceu.as<uint32_t>(), A.ev = cev.as<uint32_t>(), A.ecnt = ecnt.as<uint32_t>(), A.etime = etime.as<uint32_t>();
     A.esum = esum.as<unsigned long long>();
     A.escore = escore.as<float>();
     A.edead = edead.as<uint8_t>();
@@ -977,10 +1026,17 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
     A.error = err.as<uint32_t>();
     const int nbins = cfg.queue_bins;
     BS_ARG(nbins == 256, "stage2: only the BinQueue<256> agglomeration of the blockwise path is implemented");
-    if (sizeof(T) == 1)
-        BS_LAUNCH((k_agglomerate<true>), nown, 32, 0, s, d_ab.as<AggBlk>(), A, 1.0f, nbins, cfg.keep_cheaper);
-    else
-        BS_LAUNCH((k_agglomerate<false>), nown, 32, 0, s, d_ab.as<AggBlk>(), A, 1.0f, nbins, cfg.keep_cheaper);
+    BS_TRY(agglom_smem_launch(d_ab.as<AggBlk>(), d_list.as<int>(), (int)l_smem.size(), A, 1.0f, cfg.keep_cheaper, u8, sum64,
+                              Emax, Nmax, s));
+    if (any_glob) {
+        const int *gl = d_list.as<int>() + l_smem.size();
+        if (u8)
+            BS_LAUNCH((k_agglomerate<true>), (unsigned)l_glob.size(), 32, 0, s, d_ab.as<AggBlk>(), gl, A, 1.0f, nbins,
+                      cfg.keep_cheaper);
+        else
+            BS_LAUNCH((k_agglomerate<false>), (unsigned)l_glob.size(), 32, 0, s, d_ab.as<AggBlk>(), gl, A, 1.0f, nbins,
+                      cfg.keep_cheaper);
+    }
 
     // ---- merge-tree scores, ownership, output (host sync: number of owned edges)
     g_prof.mark("s2.lca", s);
@@ -991,8 +1047,8 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
     BS_TRY(owned.alloc(((size_t)E + 1), s));
     BS_TRY(oscan.alloc(4 * ((size_t)E + 1), s));
     if (E) {
-        BS_LAUNCH(k_lca, cdiv(E, 256), 256, 0, s, db, ebase.as<uint32_t>(), eblk.as<uint32_t>(), eu.as<uint32_t>(),
-                  ev.as<uint32_t>(), E, tparent.as<uint32_t>(), tlevel.as<uint32_t>(), tscore.as<float>(), P.nvox_block,
+        BS_LAUNCH(k_lca, cdiv(E, 256), 256, 0, s, db, cbase.as<uint32_t>(), eblk.as<uint32_t>(), eu.as<uint32_t>(),
+                  ev.as<uint32_t>(), ceu.as<uint32_t>(), cev.as<uint32_t>(), E, tparent.as<uint32_t>(), tlevel.as<uint32_t>(), tscore.as<float>(), P.nvox_block,
                   ou.as<uint64_t>(), ov.as<uint64_t>(), os.as<float>(), owned.as<uint8_t>());
         BS_TRY(scan_exclusive_u8(owned.as<uint8_t>(), oscan.as<uint32_t>(), E, tot.as<uint32_t>() + 1, s));
     }
@@ -1022,9 +1078,9 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
         keep_debug2(P, "s2_esum", esum, 8, E);
         keep_debug2(P, "s2_ecnt", ecnt, 4, E);
         keep_debug2(P, "s2_owned", owned, 1, E);
-        keep_debug2(P, "s2_ha", ha, 4, Vtot);
-        keep_debug2(P, "s2_hb", hbb, 4, Vtot);
-        keep_debug2(P, "s2_hs", hs, 4, Vtot);
+        keep_debug2(P, "s2_ha", ha, 4, Ctot);
+        keep_debug2(P, "s2_hb", hbb, 4, Ctot);
+        keep_debug2(P, "s2_hs", hs, 4, Ctot);
         keep_debug2(P, "s2_nmerges", nmerges, 4, nown);
         keep_debug2(P, "s2_counters", counters, 4, 6 * nown);
         std::vector<uint32_t> vb(nown);

@@ -38,7 +38,7 @@ EXPORTS = [
     "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_stage2_agglomerate", "bs_stage2_num_edges",
     "bs_stage2_get_edges", "bs_connected_components", "bs_relabel", "bs_stage3_relabel", "bs_watershed_from_affinities",
     "bs_synth_affs", "bs_debug_fetch", "bs_set_debug", "bs_set_profiling", "bs_get_profile",
-    "bs_release_scratch", "bs_set_flood_version", "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
+    "bs_release_scratch", "bs_set_flood_version", "bs_set_agglom_version", "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
 ]
 
 _lib = None
@@ -96,6 +96,10 @@ def set_debug(on):
 
 def set_flood_version(v):
     _check(lib().bs_set_flood_version(C.c_int(int(v))))
+
+
+def set_agglom_version(v):
+    _check(lib().bs_set_agglom_version(C.c_int(int(v))))
 
 
 def release_scratch():
