@@ -273,6 +273,122 @@ __global__ void __launch_bounds__(256) k_maxfilt(const Tile *__restrict__ tiles,
     }
 }
 
+// ---- shared-memory variants for 2-D slices (the default fragments_in_xy mode) ------------------------------
+// Column pass over a strip of CS_W columns: the strip's row distances sit in shared memory, so the pruned
+// search costs shared-memory reads instead of L1/L2 round trips.  Same arithmetic as k_coldist.
+static constexpr int CS_W = 32;
+__global__ void __launch_bounds__(256) k_coldist_strip(const Tile *__restrict__ tiles, const uint16_t *__restrict__ g,
+                                                       uint32_t *__restrict__ out, uint32_t *__restrict__ tilemax) {
+    extern __shared__ uint16_t cs_g[];   // [H][CS_W]
+    const Tile t = tiles[blockIdx.y];
+    const int W = t.W, H = t.H;
+    const int nstrips = (W + CS_W - 1) / CS_W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool final2d = (t.ndim == 2);
+    uint32_t mymax = 0;
+    // blockIdx.x enumerates (slice z, strip)
+    for (int job = blockIdx.x; job < t.D * nstrips; job += gridDim.x) {
+        const int z = job / nstrips, x0 = (job - z * nstrips) * CS_W;
+        const int x = x0 + lane;
+        const long long sbase = t.base + (long long)z * H * W;
+        __syncthreads();
+        for (int y = warp; y < H; y += 8) cs_g[y * CS_W + lane] = x < W ? g[sbase + (long long)y * W + x] : GINF;
+        __syncthreads();
+        if (x < W)
+            for (int y = warp; y < H; y += 8) {
+                const uint16_t *gp = cs_g + y * CS_W + lane;
+                uint32_t g0 = gp[0];
+                uint32_t best = g0 == GINF ? DBIG : g0 * g0;
+                for (int dy = 1;; dy++) {
+                    uint32_t dd = (uint32_t)dy * dy;
+                    if (dd >= best) break;
+                    bool any = false;
+                    if (y - dy >= 0) {
+                        any = true;
+                        uint32_t v = gp[-dy * CS_W];
+                        if (v != GINF) best = min(best, v * v + dd);
+                    }
+                    if (y + dy < H) {
+                        any = true;
+                        uint32_t v = gp[dy * CS_W];
+                        if (v != GINF) best = min(best, v * v + dd);
+                    }
+                    if (!any) break;
+                }
+                if (final2d && best == DBIG) best = (uint32_t)(y + 1) * (y + 1) + (uint32_t)x * x;
+                out[sbase + (long long)y * W + x] = best;
+                if (final2d) mymax = max(mymax, best);
+            }
+    }
+    if (final2d) {
+        mymax = warp_max_u32(mymax);
+        if (lane == 0 && mymax) atomicMax(&tilemax[blockIdx.y], mymax);
+    }
+}
+
+// x and y passes of the maximum filter fused through a shared-memory patch with reflected halo.
+// final2d = 1: emit the seed parent array / flags (2-D tiles); 0: write the xy-filtered value (3-D tiles,
+// the z pass follows with k_maxfilt).
+static constexpr int MF_TW = 64, MF_TH = 32;
+__device__ __forceinline__ int reflect_idx(int j, int L) {
+    while (j < 0 || j >= L) {
+        if (j < 0) j = -j - 1;
+        if (j >= L) j = 2 * L - j - 1;
+    }
+    return j;
+}
+__global__ void __launch_bounds__(256) k_maxfilt_xy(const Tile *__restrict__ tiles, const uint32_t *__restrict__ d2, int size,
+                                                    int final2d, const uint8_t *__restrict__ msk, uint32_t *__restrict__ out,
+                                                    uint8_t *__restrict__ seedflag) {
+    extern __shared__ uint32_t mf_s[];
+    const Tile t = tiles[blockIdx.y];
+    const int W = t.W, H = t.H;
+    const int lo = size / 2;
+    const int PW = MF_TW + size - 1, PH = MF_TH + size - 1;
+    uint32_t *A = mf_s;              // [PH][PW] input patch
+    uint32_t *B = mf_s + PH * PW;    // [PH][MF_TW] row maxima
+    const int ntx = (W + MF_TW - 1) / MF_TW, nty = (H + MF_TH - 1) / MF_TH;
+    const int njobs = t.D * ntx * nty;
+    for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+        const int z = job / (ntx * nty), r = job - z * ntx * nty;
+        const int ty = r / ntx, tx = r - ty * ntx;
+        const int x0 = tx * MF_TW, y0 = ty * MF_TH;
+        const long long sbase = t.base + (long long)z * H * W;
+        __syncthreads();
+        for (int i = threadIdx.x; i < PH * PW; i += 256) {
+            int py = i / PW, px = i - py * PW;
+            int yy = reflect_idx(y0 - lo + py, H), xx = reflect_idx(x0 - lo + px, W);
+            A[i] = d2[sbase + (long long)yy * W + xx];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < PH * MF_TW; i += 256) {
+            int py = i / MF_TW, px = i - py * MF_TW;
+            const uint32_t *a = A + py * PW + px;
+            uint32_t m = 0;
+            for (int k = 0; k < size; k++) m = max(m, a[k]);
+            B[i] = m;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < MF_TH * MF_TW; i += 256) {
+            int py = i / MF_TW, px = i - py * MF_TW;
+            int y = y0 + py, x = x0 + px;
+            if (y < H && x < W) {
+                const uint32_t *b = B + py * MF_TW + px;
+                uint32_t m = 0;
+                for (int k = 0; k < size; k++) m = max(m, b[k * MF_TW]);
+                const long long p = sbase + (long long)y * W + x;
+                if (!final2d) {
+                    out[p] = m;
+                } else {
+                    bool seed = (m == A[(py + lo) * PW + px + lo]) && msk[p];
+                    out[p] = seed ? (uint32_t)((long long)z * H * W + (long long)y * W + x) : NONE32;
+                    seedflag[p] = seed ? 1 : 0;
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ seed connected components (conn-1)
 __global__ void __launch_bounds__(256) k_seed_union(const Tile *__restrict__ tiles, uint32_t *__restrict__ par) {
     const Tile t = tiles[blockIdx.y];
@@ -1159,26 +1275,64 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
         BS_LAUNCH((k_mask_rowdist<T>), gr, 256, 0, s, dt, A, msk.as<uint8_t>(), g.as<uint16_t>(), tileflags.as<uint32_t>());
     }
     g_prof.mark("s1.edt", s);
+    int maxH = 0, maxW = 0, maxD = 0;
+    for (auto &t : tiles) maxH = std::max(maxH, t.H), maxW = std::max(maxW, t.W), maxD = std::max(maxD, t.D);
+    const size_t strip_smem = (size_t)maxH * CS_W * 2;
+    const bool use_strip = strip_smem <= 96 * 1024;
+    const dim3 grid_strip((unsigned)std::min<long long>((long long)maxD * ((maxW + CS_W - 1) / CS_W), 8192), ntiles);
+    if (use_strip) {
+        static bool attr_strip = false;
+        if (!attr_strip) {
+            BS_CUDA(cudaFuncSetAttribute(k_coldist_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_strip = true;
+        }
+    }
     if (xy) {
-        BS_LAUNCH(k_coldist, grid, 256, 0, s, dt, g.as<uint16_t>(), d2.as<uint32_t>(), tilemax.as<uint32_t>());
+        if (use_strip)
+            BS_LAUNCH(k_coldist_strip, grid_strip, 256, strip_smem, s, dt, g.as<uint16_t>(), d2.as<uint32_t>(), tilemax.as<uint32_t>());
+        else
+            BS_LAUNCH(k_coldist, grid, 256, 0, s, dt, g.as<uint16_t>(), d2.as<uint32_t>(), tilemax.as<uint32_t>());
     } else {
-        BS_LAUNCH(k_coldist, grid, 256, 0, s, dt, g.as<uint16_t>(), tmpA.as<uint32_t>(), tilemax.as<uint32_t>());
+        if (use_strip)
+            BS_LAUNCH(k_coldist_strip, grid_strip, 256, strip_smem, s, dt, g.as<uint16_t>(), tmpA.as<uint32_t>(), tilemax.as<uint32_t>());
+        else
+            BS_LAUNCH(k_coldist, grid, 256, 0, s, dt, g.as<uint16_t>(), tmpA.as<uint32_t>(), tilemax.as<uint32_t>());
         BS_LAUNCH(k_zdist, grid, 256, 0, s, dt, tmpA.as<uint32_t>(), d2.as<uint32_t>(), tilemax.as<uint32_t>());
     }
     // ---- maximum filter -> seeds (parent array in lv, flags in seedflag)
     g_prof.mark("s1.maxfilt", s);
     const int msd = cfg.min_seed_distance;
+    const size_t mf_smem = ((size_t)(MF_TH + msd - 1) * (MF_TW + msd - 1) + (size_t)(MF_TH + msd - 1) * MF_TW) * 4;
+    const bool use_mf = mf_smem <= 96 * 1024;
+    const dim3 grid_mf((unsigned)std::min<long long>((long long)maxD * ((maxW + MF_TW - 1) / MF_TW) * ((maxH + MF_TH - 1) / MF_TH), 8192),
+                       ntiles);
+    if (use_mf) {
+        static bool attr_mf = false;
+        if (!attr_mf) {
+            BS_CUDA(cudaFuncSetAttribute(k_maxfilt_xy, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_mf = true;
+        }
+    }
     if (xy) {
-        BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, d2.as<uint32_t>(), tmpA.as<uint32_t>(), 2, msd, 0, nullptr, nullptr, nullptr,
-                  nullptr);
-        BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, tmpA.as<uint32_t>(), nullptr, 1, msd, 1, d2.as<uint32_t>(),
-                  msk.as<uint8_t>(), lv.as<uint32_t>(), seedflag.as<uint8_t>());
+        if (use_mf) {
+            BS_LAUNCH(k_maxfilt_xy, grid_mf, 256, mf_smem, s, dt, d2.as<uint32_t>(), msd, 1, msk.as<uint8_t>(), lv.as<uint32_t>(),
+                      seedflag.as<uint8_t>());
+        } else {
+            BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, d2.as<uint32_t>(), tmpA.as<uint32_t>(), 2, msd, 0, nullptr, nullptr, nullptr,
+                      nullptr);
+            BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, tmpA.as<uint32_t>(), nullptr, 1, msd, 1, d2.as<uint32_t>(),
+                      msk.as<uint8_t>(), lv.as<uint32_t>(), seedflag.as<uint8_t>());
+        }
     } else {
         BS_TRY(tmpB.alloc(P_pix * 4, s));
-        BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, d2.as<uint32_t>(), tmpA.as<uint32_t>(), 2, msd, 0, nullptr, nullptr, nullptr,
-                  nullptr);
-        BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, tmpA.as<uint32_t>(), tmpB.as<uint32_t>(), 1, msd, 0, nullptr, nullptr, nullptr,
-                  nullptr);
+        if (use_mf) {
+            BS_LAUNCH(k_maxfilt_xy, grid_mf, 256, mf_smem, s, dt, d2.as<uint32_t>(), msd, 0, nullptr, tmpB.as<uint32_t>(), nullptr);
+        } else {
+            BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, d2.as<uint32_t>(), tmpA.as<uint32_t>(), 2, msd, 0, nullptr, nullptr, nullptr,
+                      nullptr);
+            BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, tmpA.as<uint32_t>(), tmpB.as<uint32_t>(), 1, msd, 0, nullptr, nullptr, nullptr,
+                      nullptr);
+        }
         BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, tmpB.as<uint32_t>(), nullptr, 0, msd, 1, d2.as<uint32_t>(),
                   msk.as<uint8_t>(), lv.as<uint32_t>(), seedflag.as<uint8_t>());
         tmpB.release();
