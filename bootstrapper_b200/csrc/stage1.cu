@@ -919,17 +919,31 @@ __global__ void __launch_bounds__(256) k_scatter_labels(const Tile *__restrict__
 }
 
 // ------------------------------------------------------------------ fragment statistics
+// One table entry per watershed fragment (index = fbase[tile] + label - 1): affinity sum + voxel count over the
+// whole read-ROI tile (filter_avg_fragments / remove_small_objects see the uncropped array,
+// watershed_frags.py:148-156,188-192), the smallest write-order index of its voxels inside the write ROI, and
+// whether it also has voxels outside the write ROI ("crossing": only such a fragment can fall apart when cropped).
+static constexpr uint8_t FF_CROSS = 1, FF_KEEP = 2;
+
+__device__ __forceinline__ long long tile_widx(const Tile &t, int z, int y, int x) {
+    return t.wbase + ((long long)(z - t.wz) * t.wH + (y - t.wy)) * t.wW + (x - t.wx);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_fragstats(const Tile *__restrict__ tiles, AffView A, const uint32_t *__restrict__ lab,
-                                                   typename AffOps<T>::acc_t *__restrict__ fsum, uint32_t *__restrict__ fcnt) {
+                                                   const uint32_t *__restrict__ fbase, int need_stats,
+                                                   typename AffOps<T>::acc_t *__restrict__ fsum, uint32_t *__restrict__ fcnt,
+                                                   uint32_t *__restrict__ fmin, uint8_t *__restrict__ fflag) {
     const Tile t = tiles[blockIdx.y];
     const int W = t.W, H = t.H;
     const long long HW = (long long)H * W, npix = (long long)t.D * HW;
     const size_t nvol = (size_t)A.Zw * A.Y * A.X;
     const T *a = (const T *)A.p;
+    const uint32_t fb = fbase[blockIdx.y];
     for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < npix; i0 += (long long)gridDim.x * blockDim.x) {
         long long i = i0 + threadIdx.x;
-        uint32_t l = 0;
+        uint32_t l = 0, w = NONE32;
+        unsigned outside = 0;
         typename AffOps<T>::acc_t val = 0;
         if (i < npix) {
             l = lab[t.base + i];
@@ -938,24 +952,33 @@ __global__ void __launch_bounds__(256) k_fragstats(const Tile *__restrict__ tile
                 // a labelled pixel is inside the mask, hence inside the volume and not masked out
                 int x, y, z;
                 unravel3(i, W, H, x, y, z);
-                size_t gi = ((size_t)(t.gz + z - A.z0) * A.Y + (t.gy + y)) * A.X + (t.gx + x);
-                val = AffOps<T>::value(a, nvol, gi);
+                if (z >= t.wz && z < t.wz + t.wD && y >= t.wy && y < t.wy + t.wH && x >= t.wx && x < t.wx + t.wW)
+                    w = (uint32_t)tile_widx(t, z, y, x);
+                else
+                    outside = 1;
+                if (need_stats) {
+                    size_t gi = ((size_t)(t.gz + z - A.z0) * A.Y + (t.gy + y)) * A.X + (t.gx + x);
+                    val = AffOps<T>::value(a, nvol, gi);
+                }
             }
         }
         unsigned act = __ballot_sync(FULL, l != 0);
         if (l) {
             unsigned peers = __match_any_sync(act, l);
-            int leader = __ffs(peers) - 1;
-            int cnt = __popc(peers);
+            const bool leader = (int)(threadIdx.x & 31) == __ffs(peers) - 1;
+            const size_t fi = (size_t)fb + l - 1;
+            uint32_t wmin = __reduce_min_sync(peers, w);
+            unsigned anyout = __reduce_or_sync(peers, outside);
             if constexpr (sizeof(T) == 1) {
-                unsigned s = __reduce_add_sync(peers, (unsigned)val);
-                if ((threadIdx.x & 31) == leader) {
-                    atomicAdd(&fsum[t.base + l - 1], (unsigned long long)s);
-                    atomicAdd(&fcnt[t.base + l - 1], (uint32_t)cnt);
-                }
+                unsigned sm = __reduce_add_sync(peers, (unsigned)val);
+                if (leader && need_stats) atomicAdd(&fsum[fi], (unsigned long long)sm);
             } else {
-                atomicAdd(&fsum[t.base + l - 1], val);
-                if ((threadIdx.x & 31) == leader) atomicAdd(&fcnt[t.base + l - 1], (uint32_t)cnt);
+                if (need_stats) atomicAdd(&fsum[fi], val);
+            }
+            if (leader) {
+                atomicAdd(&fcnt[fi], (uint32_t)__popc(peers));
+                if (wmin != NONE32) atomicMin(&fmin[fi], wmin);
+                if (anyout) fflag[fi] = FF_CROSS;   // every writer stores the same value
             }
         }
     }
@@ -972,45 +995,47 @@ __device__ __forceinline__ bool frag_keep(ACC sum, uint32_t cnt, double ff, int 
     return true;
 }
 
-// one decision per fragment (entries with a non-zero count are fragment roots): fcnt becomes keep ? 1 : 0
+// one decision per fragment
 template <typename ACC>
-__global__ void __launch_bounds__(256) k_frag_decide(const ACC *__restrict__ fsum, uint32_t *__restrict__ fcnt, size_t n,
-                                                     double ff, int rd, int is_u8) {
+__global__ void __launch_bounds__(256) k_frag_decide(const ACC *__restrict__ fsum, const uint32_t *__restrict__ fcnt,
+                                                     uint8_t *__restrict__ fflag, size_t n, double ff, int rd, int is_u8) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t c = fcnt[i];
-    if (c) fcnt[i] = frag_keep<ACC>(fsum[i], c, ff, rd, is_u8 != 0) ? 1u : 0u;
+    if (c && frag_keep<ACC>(fsum[i], c, ff, rd, is_u8 != 0)) fflag[i] |= FF_KEEP;
 }
 
-// cpar (tile-local parent, only write-region pixels participate): NONE32 if dropped, else the start of
-// the pixel's row run of equal labels inside its warp chunk (pre-linked rows keep union-find chains short)
-template <typename ACC>
+// Write-ROI voxels of kept crossing fragments take part in a pixel-level union-find (cpar, tile-local indices):
+// parent = start of the voxel's row run of equal labels inside its warp chunk (pre-linked runs keep chains
+// short), NONE32 for every other write-ROI voxel.  Fragments entirely inside the write ROI stay connected.
 __global__ void __launch_bounds__(256) k_crop_init(const Tile *__restrict__ tiles, const uint32_t *__restrict__ lab,
-                                                   const ACC *__restrict__ fsum, const uint32_t *__restrict__ fcnt,
-                                                   double ff, int rd, int is_u8, uint32_t *__restrict__ cpar) {
+                                                   const uint32_t *__restrict__ fbase, const uint8_t *__restrict__ fflag,
+                                                   uint32_t *__restrict__ cpar) {
     const Tile t = tiles[blockIdx.y];
     const int W = t.W, H = t.H;
-    const long long HW = (long long)H * W, npix = (long long)t.D * HW;
+    const long long nw = (long long)t.wD * t.wH * t.wW;
     const int lane = threadIdx.x & 31;
-    auto kept_label = [&](long long i) -> uint32_t {
-        int x, y, z;
-        unravel3(i, W, H, x, y, z);
-        if (z >= t.wz && z < t.wz + t.wD && y >= t.wy && y < t.wy + t.wH && x >= t.wx && x < t.wx + t.wW) {
-            uint32_t l = lab[t.base + i];
-            if (l && l < CLAIM) {
-                if (!(ff > 0.0 || rd > 0) || fcnt[t.base + l - 1]) return l;
-            }
-        }
+    const uint32_t fb = fbase[blockIdx.y];
+    auto part_label = [&](long long i) -> uint32_t {
+        uint32_t l = lab[t.base + i];
+        if (l && l < CLAIM && (fflag[(size_t)fb + l - 1] & (FF_CROSS | FF_KEEP)) == (FF_CROSS | FF_KEEP)) return l;
         return 0;
     };
-    for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < npix; i0 += (long long)gridDim.x * blockDim.x) {
-        long long i = i0 + threadIdx.x;
-        uint32_t l = i < npix ? kept_label(i) : 0;
+    for (long long k0 = (long long)blockIdx.x * blockDim.x; k0 < nw; k0 += (long long)gridDim.x * blockDim.x) {
+        long long kk = k0 + threadIdx.x;
+        uint32_t l = 0;
+        long long i = 0;
+        int x = 0, y = 0, z = 0;
+        if (kk < nw) {
+            unravel3(kk, t.wW, t.wH, x, y, z);
+            i = ((long long)(z + t.wz) * H + (y + t.wy)) * W + (x + t.wx);
+            l = part_label(i);
+        }
         uint32_t ll = __shfl_up_sync(FULL, l, 1);
-        if (lane == 0) ll = (l && i > 0) ? kept_label(i - 1) : 0;
-        bool sl = l && ((uint32_t)i % (uint32_t)W) != 0 && ll == l;
+        if (lane == 0) ll = (l && x > 0) ? part_label(i - 1) : 0;
+        bool sl = l && x > 0 && ll == l;
         unsigned startbits = __ballot_sync(FULL, l && !sl);
-        if (i < npix) {
+        if (kk < nw) {
             uint32_t v = NONE32;
             if (l) {
                 unsigned m = startbits & (FULL >> (31 - lane));
@@ -1021,31 +1046,33 @@ __global__ void __launch_bounds__(256) k_crop_init(const Tile *__restrict__ tile
     }
 }
 
-// union with the raster-preceding neighbours of the full (8 / 26) neighbourhood carrying the same label;
-// links implied by row adjacency of equal labels are skipped
+// union with the raster-preceding neighbours of the full (8 / 26) neighbourhood inside the write ROI that
+// carry the same label; links implied by row adjacency of equal labels are skipped
 __global__ void __launch_bounds__(256) k_crop_union(const Tile *__restrict__ tiles, const uint32_t *__restrict__ lab,
                                                     uint32_t *__restrict__ cpar) {
     const Tile t = tiles[blockIdx.y];
-    const int W = t.W, H = t.H, D = t.D;
-    const long long HW = (long long)H * W, npix = (long long)D * HW;
+    const int W = t.W, H = t.H;
+    const long long HW = (long long)H * W;
+    const long long nw = (long long)t.wD * t.wH * t.wW;
     uint32_t *pp = cpar + t.base;
     const uint32_t *ll = lab + t.base;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
-        if (__ldcg(&pp[i]) == NONE32) continue;
+    for (long long kk = (long long)blockIdx.x * blockDim.x + threadIdx.x; kk < nw; kk += (long long)gridDim.x * blockDim.x) {
         int x, y, z;
-        unravel3(i, W, H, x, y, z);
+        unravel3(kk, t.wW, t.wH, x, y, z);
+        const long long i = ((long long)(z + t.wz) * H + (y + t.wy)) * W + (x + t.wx);
+        if (__ldcg(&pp[i]) == NONE32) continue;
         const uint32_t l = ll[i];
         auto same = [&](long long j) -> bool { return ll[j] == l && __ldcg(&pp[j]) != NONE32; };
         const bool left = x > 0 && same(i - 1);
         // row link across a warp-chunk boundary (inside a chunk k_crop_init linked the run already)
-        if (left && (i & 31) == 0) uf_union(pp, (uint32_t)i, (uint32_t)(i - 1));
+        if (left && (kk & 31) == 0) uf_union(pp, (uint32_t)i, (uint32_t)(i - 1));
         if (y > 0) {
             const bool up = same(i - W);
             if (up) {
                 if (!(left && same(i - W - 1))) uf_union(pp, (uint32_t)i, (uint32_t)(i - W));
             } else {
                 if (x > 0 && !left && same(i - W - 1)) uf_union(pp, (uint32_t)i, (uint32_t)(i - W - 1));
-                if (x + 1 < W && same(i - W + 1) && !same(i + 1)) uf_union(pp, (uint32_t)i, (uint32_t)(i - W + 1));
+                if (x + 1 < t.wW && same(i - W + 1) && !same(i + 1)) uf_union(pp, (uint32_t)i, (uint32_t)(i - W + 1));
             }
         }
         if (z > 0) {
@@ -1057,7 +1084,7 @@ __global__ void __launch_bounds__(256) k_crop_union(const Tile *__restrict__ til
                     for (int dx = -1; dx <= 1; dx++) {
                         if (dy == 0 && dx == 0) continue;
                         int yy = y + dy, xx = x + dx;
-                        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                        if (yy < 0 || yy >= t.wH || xx < 0 || xx >= t.wW) continue;
                         long long j = b + (long long)dy * W + dx;
                         if (same(j)) uf_union(pp, (uint32_t)i, (uint32_t)j);
                     }
@@ -1066,35 +1093,40 @@ __global__ void __launch_bounds__(256) k_crop_union(const Tile *__restrict__ til
     }
 }
 
-__device__ __forceinline__ long long tile_widx(const Tile &t, int z, int y, int x) {
-    return t.wbase + ((long long)(z - t.wz) * t.wH + (y - t.wy)) * t.wW + (x - t.wx);
-}
-
-// croot[write index] = write index of the component root (NONE32 for background); isroot flags
-__global__ void __launch_bounds__(256) k_crop_flatten(const Tile *__restrict__ tiles, const uint32_t *__restrict__ cpar,
-                                                      uint32_t *__restrict__ croot, uint8_t *__restrict__ isroot) {
+// one bit per write-ROI voxel (batch write order): set for the first voxel of every output fragment
+__global__ void __launch_bounds__(256) k_root_bits_pix(const Tile *__restrict__ tiles, const uint32_t *__restrict__ cpar,
+                                                       uint32_t *__restrict__ bits) {
     const Tile t = tiles[blockIdx.y];
     const int W = t.W, H = t.H;
-    const long long HW = (long long)H * W;
     const long long nw = (long long)t.wD * t.wH * t.wW;
-    const uint32_t *pp = cpar + t.base;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nw; k += (long long)gridDim.x * blockDim.x) {
+    for (long long kk = (long long)blockIdx.x * blockDim.x + threadIdx.x; kk < nw; kk += (long long)gridDim.x * blockDim.x) {
         int x, y, z;
-        unravel3(k, t.wW, t.wH, x, y, z);
-        x += t.wx, y += t.wy, z += t.wz;
-        long long i = (long long)z * HW + (long long)y * W + x;
-        uint32_t r = NONE32;
-        uint8_t ir = 0;
-        if (pp[i] != NONE32) {
-            uint32_t root = uf_find(pp, (uint32_t)i);
-            int rx, ry, rz;
-            unravel3(root, W, H, rx, ry, rz);
-            r = (uint32_t)tile_widx(t, rz, ry, rx);
-            ir = root == (uint32_t)i;
+        unravel3(kk, t.wW, t.wH, x, y, z);
+        const long long i = ((long long)(z + t.wz) * H + (y + t.wy)) * W + (x + t.wx);
+        if (cpar[t.base + i] == (uint32_t)i) {
+            const uint32_t w = (uint32_t)(t.wbase + kk);
+            atomicOr(&bits[w >> 5], 1u << (w & 31));
         }
-        croot[t.wbase + k] = r;
-        isroot[t.wbase + k] = ir;
     }
+}
+
+__global__ void __launch_bounds__(256) k_root_bits_frag(const uint32_t *__restrict__ fcnt, const uint8_t *__restrict__ fflag,
+                                                        const uint32_t *__restrict__ fmin, size_t n, uint32_t *__restrict__ bits) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (fcnt[i] && (fflag[i] & (FF_CROSS | FF_KEEP)) == FF_KEEP) {
+        const uint32_t w = fmin[i];
+        atomicOr(&bits[w >> 5], 1u << (w & 31));
+    }
+}
+
+__global__ void k_popc_words(const uint32_t *__restrict__ bits, uint32_t *__restrict__ cnt, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cnt[i] = __popc(bits[i]);
+}
+
+__device__ __forceinline__ uint32_t bit_rank(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ wscan, uint32_t w) {
+    return wscan[w >> 5] + __popc(bits[w >> 5] & ((1u << (w & 31)) - 1u));
 }
 
 struct BlkDev {
@@ -1105,27 +1137,57 @@ struct BlkDev {
     int pad_;
 };
 
-// ids, uint64 output, node statistics.  One CTA column per block (blockIdx.y).
-__global__ void __launch_bounds__(256) k_finalize(const BlkDev *__restrict__ blks, const uint32_t *__restrict__ croot,
-                                                  const uint32_t *__restrict__ rank, long long nvox_block,
-                                                  int roi_oz, int roi_oy, int roi_ox, int roi_Y, int roi_X,
+__global__ void k_blk_first(const BlkDev *__restrict__ blks, int nblk, const uint32_t *__restrict__ bits,
+                            const uint32_t *__restrict__ wscan, uint32_t *__restrict__ blk_first) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nblk) blk_first[i] = bit_rank(bits, wscan, (uint32_t)blks[i].wbase);
+}
+
+// ids (raster order of each fragment's first voxel, + block_id * prod(block_size)), uint64 output, node
+// statistics.  One CTA column per tile (blockIdx.y).
+__global__ void __launch_bounds__(256) k_finalize(const Tile *__restrict__ tiles, const BlkDev *__restrict__ blks,
+                                                  const uint32_t *__restrict__ lab, const uint32_t *__restrict__ cpar,
+                                                  const uint32_t *__restrict__ fbase, const uint8_t *__restrict__ fflag,
+                                                  const uint32_t *__restrict__ fmin, const uint32_t *__restrict__ bits,
+                                                  const uint32_t *__restrict__ wscan, const uint32_t *__restrict__ blk_first,
+                                                  long long nvox_block, int roi_oz, int roi_oy, int roi_ox, int roi_Y, int roi_X,
                                                   uint64_t *__restrict__ frags, uint32_t *__restrict__ ncnt,
-                                                  unsigned long long *__restrict__ nsum, uint32_t *__restrict__ blk_first) {
-    const BlkDev b = blks[blockIdx.y];
-    const long long nw = (long long)b.ws[0] * b.ws[1] * b.ws[2];
-    const uint32_t first = rank[b.wbase];
-    if (blockIdx.x == 0 && threadIdx.x == 0) blk_first[blockIdx.y] = first;
+                                                  unsigned long long *__restrict__ nsum) {
+    const Tile t = tiles[blockIdx.y];
+    const BlkDev b = blks[t.block];
+    const int W = t.W, H = t.H;
+    const long long nw = (long long)t.wD * t.wH * t.wW;
+    const long long koff = t.wbase - b.wbase;
+    const uint32_t first = blk_first[t.block];
+    const uint32_t fb = fbase[blockIdx.y];
+    const uint32_t *pp = cpar + t.base;
     for (long long k0 = (long long)blockIdx.x * blockDim.x; k0 < nw; k0 += (long long)gridDim.x * blockDim.x) {
-        long long k = k0 + threadIdx.x;
+        long long kk = k0 + threadIdx.x;
         uint32_t node = NONE32;
         int x = 0, y = 0, z = 0;
-        if (k < nw) {
-            unravel3(k, b.ws[2], b.ws[1], x, y, z);
-            uint32_t r = croot[b.wbase + k];
+        if (kk < nw) {
+            int tx, ty, tz;
+            unravel3(kk, t.wW, t.wH, tx, ty, tz);
+            const long long i = ((long long)(tz + t.wz) * H + (ty + t.wy)) * W + (tx + t.wx);
+            unravel3(koff + kk, b.ws[2], b.ws[1], x, y, z);
+            uint32_t l = lab[t.base + i];
             uint64_t id = 0;
-            if (r != NONE32) {
-                node = rank[r];
-                id = (uint64_t)(node - first + 1) + (uint64_t)b.block_id * (uint64_t)nvox_block;
+            if (l && l < CLAIM) {
+                const size_t fi = (size_t)fb + l - 1;
+                const uint8_t fl = fflag[fi];
+                if (fl & FF_KEEP) {
+                    uint32_t rw;
+                    if (fl & FF_CROSS) {
+                        uint32_t root = uf_find(pp, (uint32_t)i);
+                        int rx, ry, rz;
+                        unravel3(root, W, H, rx, ry, rz);
+                        rw = (uint32_t)tile_widx(t, rz, ry, rx);
+                    } else {
+                        rw = fmin[fi];
+                    }
+                    node = bit_rank(bits, wscan, rw);
+                    id = (uint64_t)(node - first + 1) + (uint64_t)b.block_id * (uint64_t)nvox_block;
+                }
             }
             size_t o = ((size_t)(b.wo[0] + z - roi_oz) * roi_Y + (b.wo[1] + y - roi_oy)) * roi_X + (b.wo[2] + x - roi_ox);
             frags[o] = id;
@@ -1448,26 +1510,43 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
 
     // ---- fragment statistics, keep/drop, crop relabel
     g_prof.mark("s1.fragstats", s);
-    DevBuf fsum, fcnt, croot, isroot, rank;
+    DevBuf fsum, fcnt, fmin, fflag, fbase_v1, bits, wcnt, wscan;
     const bool need_stats = cfg.filter_fragments > 0.0 || cfg.remove_debris > 0;
-    BS_TRY(fsum.alloc_zero(need_stats ? (size_t)P_pix * 8 : 16, s));
-    BS_TRY(fcnt.alloc_zero(need_stats ? (size_t)P_pix * 4 : 16, s));
-    if (need_stats)
-        BS_LAUNCH((k_fragstats<T>), grid, 256, 0, s, dt, A, lab.as<uint32_t>(), fsum.as<acc_t>(), fcnt.as<uint32_t>());
-    if (need_stats)
-        BS_LAUNCH((k_frag_decide<acc_t>), cdiv((size_t)P_pix, 256), 256, 0, s, fsum.as<acc_t>(), fcnt.as<uint32_t>(), (size_t)P_pix,
-                  cfg.filter_fragments, cfg.remove_debris, sizeof(T) == 1 ? 1 : 0);
+    // fragment table: flood v2 labels are ranks among the tile's seed pixels, v1 labels are root pixel + 1
+    const size_t nF = (v2 ? nseeds : (size_t)P_pix) + 1;
+    const uint32_t *d_fbase = tile_seed.as<uint32_t>();
+    if (!v2) {
+        std::vector<uint32_t> hb(ntiles);
+        for (int i = 0; i < ntiles; i++) hb[i] = (uint32_t)tiles[i].base;
+        BS_TRY(fbase_v1.alloc(4 * (size_t)ntiles, s));
+        BS_CUDA(cudaMemcpyAsync(fbase_v1.p, hb.data(), 4 * (size_t)ntiles, cudaMemcpyHostToDevice, s));
+        BS_CUDA(cudaStreamSynchronize(s));
+        d_fbase = fbase_v1.as<uint32_t>();
+    }
+    BS_TRY(fsum.alloc_zero(nF * 8, s));
+    BS_TRY(fcnt.alloc_zero(nF * 4, s));
+    BS_TRY(fmin.alloc_fill(nF * 4, 0xFF, s));
+    BS_TRY(fflag.alloc_zero(nF, s));
+    BS_LAUNCH((k_fragstats<T>), grid, 256, 0, s, dt, A, lab.as<uint32_t>(), d_fbase, need_stats ? 1 : 0, fsum.as<acc_t>(),
+              fcnt.as<uint32_t>(), fmin.as<uint32_t>(), fflag.as<uint8_t>());
+    BS_LAUNCH((k_frag_decide<acc_t>), cdiv(nF, 256), 256, 0, s, fsum.as<acc_t>(), fcnt.as<uint32_t>(), fflag.as<uint8_t>(), nF,
+              need_stats ? cfg.filter_fragments : 0.0, need_stats ? cfg.remove_debris : 0, sizeof(T) == 1 ? 1 : 0);
     g_prof.mark("s1.crop_cc", s);
+    long long maxwt = 1;
+    for (auto &t : tiles) maxwt = std::max(maxwt, (long long)t.wD * t.wH * t.wW);
+    const dim3 gridw((unsigned)std::min<long long>(std::max<long long>((maxwt + 1023) / 1024, 1), 2048), ntiles);
     // cpar reuses lv
-    BS_LAUNCH((k_crop_init<acc_t>), grid, 256, 0, s, dt, lab.as<uint32_t>(), fsum.as<acc_t>(), fcnt.as<uint32_t>(),
-              need_stats ? cfg.filter_fragments : 0.0, need_stats ? cfg.remove_debris : 0, sizeof(T) == 1 ? 1 : 0,
-              lv.as<uint32_t>());
-    BS_LAUNCH(k_crop_union, grid, 256, 0, s, dt, lab.as<uint32_t>(), lv.as<uint32_t>());
-    BS_TRY(croot.alloc((size_t)V_w * 4, s));
-    BS_TRY(isroot.alloc((size_t)V_w, s));
-    BS_TRY(rank.alloc((size_t)V_w * 4 + 4, s));
-    BS_LAUNCH(k_crop_flatten, grid, 256, 0, s, dt, lv.as<uint32_t>(), croot.as<uint32_t>(), isroot.as<uint8_t>());
-    BS_TRY(scan_exclusive_u8(isroot.as<uint8_t>(), rank.as<uint32_t>(), V_w, d_tot + 4, s));
+    BS_LAUNCH(k_crop_init, gridw, 256, 0, s, dt, lab.as<uint32_t>(), d_fbase, fflag.as<uint8_t>(), lv.as<uint32_t>());
+    BS_LAUNCH(k_crop_union, gridw, 256, 0, s, dt, lab.as<uint32_t>(), lv.as<uint32_t>());
+    const size_t nwords = ((size_t)V_w + 31) / 32 + 1;
+    BS_TRY(bits.alloc_zero(4 * nwords, s));
+    BS_TRY(wcnt.alloc(4 * nwords, s));
+    BS_TRY(wscan.alloc(4 * nwords, s));
+    BS_LAUNCH(k_root_bits_pix, gridw, 256, 0, s, dt, lv.as<uint32_t>(), bits.as<uint32_t>());
+    BS_LAUNCH(k_root_bits_frag, cdiv(nF, 256), 256, 0, s, fcnt.as<uint32_t>(), fflag.as<uint8_t>(), fmin.as<uint32_t>(), nF,
+              bits.as<uint32_t>());
+    BS_LAUNCH(k_popc_words, cdiv(nwords, 256), 256, 0, s, bits.as<uint32_t>(), wcnt.as<uint32_t>(), nwords);
+    BS_TRY(scan_exclusive_u32(wcnt.as<uint32_t>(), wscan.as<uint32_t>(), nwords, d_tot + 4, s));
     // host sync #2: number of fragments in this batch
     BS_CUDA(cudaMemcpyAsync(h_tot, d_tot, 32, cudaMemcpyDeviceToHost, s));
     BS_CUDA(cudaStreamSynchronize(s));
@@ -1479,13 +1558,12 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     BS_TRY(ncnt.alloc_zero(4 * ((size_t)nn + 1), s));
     BS_TRY(nsum.alloc_zero(24 * ((size_t)nn + 1), s));
     BS_TRY(blk_first.alloc(4 * blks.size(), s));
-    {
-        const unsigned gxw = (unsigned)std::min<long long>(std::max<long long>((maxw + 1023) / 1024, 1), 2048);
-        dim3 gr(gxw, (unsigned)blks.size());
-        BS_LAUNCH(k_finalize, gr, 256, 0, s, d_blks.as<BlkDev>(), croot.as<uint32_t>(), rank.as<uint32_t>(), P.nvox_block,
-                  cfg.roi_offset[0] + (cfg.win_z > 0 ? cfg.win_z0 : 0), cfg.roi_offset[1], cfg.roi_offset[2], cfg.roi_shape[1], cfg.roi_shape[2], frags_out,
-                  ncnt.as<uint32_t>(), nsum.as<unsigned long long>(), blk_first.as<uint32_t>());
-    }
+    BS_LAUNCH(k_blk_first, cdiv(blks.size(), 256), 256, 0, s, d_blks.as<BlkDev>(), (int)blks.size(), bits.as<uint32_t>(),
+              wscan.as<uint32_t>(), blk_first.as<uint32_t>());
+    BS_LAUNCH(k_finalize, gridw, 256, 0, s, dt, d_blks.as<BlkDev>(), lab.as<uint32_t>(), lv.as<uint32_t>(), d_fbase,
+              fflag.as<uint8_t>(), fmin.as<uint32_t>(), bits.as<uint32_t>(), wscan.as<uint32_t>(), blk_first.as<uint32_t>(),
+              P.nvox_block, cfg.roi_offset[0] + (cfg.win_z > 0 ? cfg.win_z0 : 0), cfg.roi_offset[1], cfg.roi_offset[2],
+              cfg.roi_shape[1], cfg.roi_shape[2], frags_out, ncnt.as<uint32_t>(), nsum.as<unsigned long long>());
     // ---- grow the plan's node table
     {
         DevBuf nid, npos, nsz;
