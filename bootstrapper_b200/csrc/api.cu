@@ -17,6 +17,7 @@ int relabel(const uint64_t *frags, int64_t n, const uint64_t *keys, const uint64
             cudaStream_t s);
 int relabel_dense(Plan &P, const uint64_t *frags, int64_t n, const uint64_t *const *comps, int T, uint64_t *const *segs,
                   cudaStream_t s);
+int plan_node_ids(Plan &P, uint64_t *out, long long *n_out, cudaStream_t s);
 int synth_affs(void *out, int dtype, const int32_t *shape, const int32_t *offset, uint64_t seed, cudaStream_t s);
 }  // namespace bs
 
@@ -162,6 +163,19 @@ int bs_stage1_set_block_counts(bs_plan *p, const int64_t *counts) {
     for (size_t b = 0; b < P.blocks.size(); b++) P.block_nbase[b + 1] = P.block_nbase[b] + P.block_count[b];
     P.node_first = P.owned.empty() ? 0 : P.block_nbase[P.owned[0]];
     P.counts_global = true;
+    return BS_OK;
+}
+
+int bs_plan_node_ids(bs_plan *p, uint64_t *ids_out, int64_t *n_out, void *stream) {
+    BS_ARG(p, "null plan");
+    Plan &P = *p->p;
+    if (P.owned.size() != P.blocks.size() && !P.counts_global) {
+        set_error("bs_plan_node_ids: multi-rank plan needs bs_stage1_set_block_counts first");
+        return BS_ERR_STATE;
+    }
+    long long n = 0;
+    BS_TRY(plan_node_ids(P, ids_out, &n, (cudaStream_t)stream));
+    if (n_out) *n_out = n;
     return BS_OK;
 }
 

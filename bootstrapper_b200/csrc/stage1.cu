@@ -35,6 +35,12 @@ static constexpr uint32_t DBIG = 0x3FFFFFFFu;
 static constexpr int MAXW = 4096;
 static constexpr unsigned FULL = 0xFFFFFFFFu;
 
+// rank of position w in a bitmap whose per-word popcounts were scanned into wscan (exclusive)
+__device__ __forceinline__ uint32_t bit_rank(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ wscan, uint32_t w) {
+    return wscan[w >> 5] + __popc(bits[w >> 5] & ((1u << (w & 31)) - 1u));
+}
+__device__ __forceinline__ bool bit_test(const uint32_t *__restrict__ bits, uint32_t w) { return (bits[w >> 5] >> (w & 31)) & 1u; }
+
 struct AffView {
     const void *p;
     const uint8_t *mask;
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(256) k_zdist(const Tile *__restrict__ tiles, c
 __global__ void __launch_bounds__(256) k_maxfilt(const Tile *__restrict__ tiles, const uint32_t *__restrict__ in,
                                                  uint32_t *__restrict__ out, int axis, int size, int last,
                                                  const uint32_t *__restrict__ d2, const uint8_t *__restrict__ msk,
-                                                 uint32_t *__restrict__ par, uint8_t *__restrict__ seedflag) {
+                                                 uint32_t *__restrict__ par, uint32_t *__restrict__ sbits) {
     const Tile t = tiles[blockIdx.y];
     const int W = t.W, H = t.H, D = t.D;
     const long long HW = (long long)H * W, npix = (long long)D * HW;
@@ -268,7 +274,7 @@ __global__ void __launch_bounds__(256) k_maxfilt(const Tile *__restrict__ tiles,
         } else {
             bool seed = (m == d2[t.base + i]) && msk[t.base + i];
             par[t.base + i] = seed ? (uint32_t)i : NONE32;
-            seedflag[t.base + i] = seed ? 1 : 0;
+            if (seed) atomicOr(&sbits[(t.base + i) >> 5], 1u << ((t.base + i) & 31));
         }
     }
 }
@@ -339,7 +345,7 @@ __device__ __forceinline__ int reflect_idx(int j, int L) {
 }
 __global__ void __launch_bounds__(256) k_maxfilt_xy(const Tile *__restrict__ tiles, const uint32_t *__restrict__ d2, int size,
                                                     int final2d, const uint8_t *__restrict__ msk, uint32_t *__restrict__ out,
-                                                    uint8_t *__restrict__ seedflag) {
+                                                    uint32_t *__restrict__ sbits) {
     extern __shared__ uint32_t mf_s[];
     const Tile t = tiles[blockIdx.y];
     const int W = t.W, H = t.H;
@@ -382,7 +388,7 @@ __global__ void __launch_bounds__(256) k_maxfilt_xy(const Tile *__restrict__ til
                 } else {
                     bool seed = (m == A[(py + lo) * PW + px + lo]) && msk[p];
                     out[p] = seed ? (uint32_t)((long long)z * H * W + (long long)y * W + x) : NONE32;
-                    seedflag[p] = seed ? 1 : 0;
+                    if (seed) atomicOr(&sbits[p >> 5], 1u << (p & 31));
                 }
             }
         }
@@ -409,13 +415,13 @@ __global__ void __launch_bounds__(256) k_seed_union(const Tile *__restrict__ til
 __global__ void __launch_bounds__(256) k_seed_label_hist(const Tile *__restrict__ tiles, const uint32_t *__restrict__ par,
                                                          const uint8_t *__restrict__ msk, const uint32_t *__restrict__ d2,
                                                          uint32_t *__restrict__ lab, const uint32_t *__restrict__ hbase,
-                                                         uint32_t *__restrict__ hist, const uint32_t *__restrict__ sscan,
-                                                         int compact_labels) {
+                                                         uint32_t *__restrict__ hist, const uint32_t *__restrict__ sbits,
+                                                         const uint32_t *__restrict__ swscan, int compact_labels) {
     const Tile t = tiles[blockIdx.y];
     const long long npix = (long long)t.D * t.H * t.W;
     const uint32_t *pp = par + t.base;
     const uint32_t hb = hbase[blockIdx.y];
-    const uint32_t s0 = compact_labels ? sscan[t.base] : 0;
+    const uint32_t s0 = compact_labels ? bit_rank(sbits, swscan, (uint32_t)t.base) : 0;
     // most mask pixels carry a small d2: privatise the low part of the histogram per CTA
     constexpr int SH = 2048;
     __shared__ uint32_t sh[SH];
@@ -428,7 +434,7 @@ __global__ void __launch_bounds__(256) k_seed_label_hist(const Tile *__restrict_
             if (pp[i] != NONE32) {
                 uint32_t root = uf_find(pp, (uint32_t)i);
                 // label = root pixel + 1, or (flood v2) the root's rank among the tile's seed pixels + 1
-                l = compact_labels ? sscan[t.base + root] - s0 + 1 : root + 1;
+                l = compact_labels ? bit_rank(sbits, swscan, (uint32_t)(t.base + root)) - s0 + 1 : root + 1;
             }
             uint32_t d = d2[t.base + i];
             if (d < SH)
@@ -462,14 +468,14 @@ __global__ void k_levels(const uint32_t *__restrict__ hist, const uint32_t *__re
 
 __global__ void k_tile_ranges(const Tile *__restrict__ tiles, int ntiles, const uint32_t *__restrict__ hbase,
                               const uint32_t *__restrict__ lrank, const uint32_t *__restrict__ nlevels,
-                              const uint32_t *__restrict__ sscan, const uint32_t *__restrict__ nseeds,
-                              uint32_t *__restrict__ tile_lvl, uint32_t *__restrict__ tile_seed,
+                              const uint32_t *__restrict__ sbits, const uint32_t *__restrict__ swscan,
+                              const uint32_t *__restrict__ nseeds, uint32_t *__restrict__ tile_lvl, uint32_t *__restrict__ tile_seed,
                               const uint32_t *__restrict__ qoff, const uint32_t *__restrict__ nmask,
                               uint32_t *__restrict__ tile_q) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < ntiles) {
         tile_lvl[i] = lrank[hbase[i]];
-        tile_seed[i] = sscan[tiles[i].base];
+        tile_seed[i] = bit_rank(sbits, swscan, (uint32_t)tiles[i].base);
         tile_q[i] = qoff[hbase[i]];
     } else if (i == ntiles) {
         tile_lvl[i] = *nlevels;
@@ -479,13 +485,14 @@ __global__ void k_tile_ranges(const Tile *__restrict__ tiles, int ntiles, const 
 }
 
 // largest number of seed pixels in one tile (decides whether 15-bit labels suffice for flood v2)
-__global__ void k_tile_seed_max(const Tile *__restrict__ tiles, int ntiles, const uint32_t *__restrict__ sscan,
+__global__ void k_tile_seed_max(const Tile *__restrict__ tiles, int ntiles, const uint32_t *__restrict__ sbits,
+                                const uint32_t *__restrict__ swscan,
                                 const uint32_t *__restrict__ nseeds, const uint32_t *__restrict__ tilemax,
                                 uint32_t *__restrict__ out_seedmax, uint32_t *__restrict__ out_d2max) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ntiles) return;
-    uint32_t b = sscan[tiles[i].base];
-    uint32_t e = i + 1 < ntiles ? sscan[tiles[i + 1].base] : *nseeds;
+    uint32_t b = bit_rank(sbits, swscan, (uint32_t)tiles[i].base);
+    uint32_t e = i + 1 < ntiles ? bit_rank(sbits, swscan, (uint32_t)tiles[i + 1].base) : *nseeds;
     atomicMax(out_seedmax, e - b);
     atomicMax(out_d2max, tilemax[i]);
 }
@@ -494,7 +501,7 @@ __global__ void k_tile_seed_max(const Tile *__restrict__ tiles, int ntiles, cons
 __global__ void __launch_bounds__(256) k_pixel_levels(const Tile *__restrict__ tiles, const uint8_t *__restrict__ msk,
                                                       const uint32_t *__restrict__ d2, const uint32_t *__restrict__ hbase,
                                                       const uint32_t *__restrict__ lrank, uint32_t *__restrict__ lv,
-                                                      const uint8_t *__restrict__ seedflag, const uint32_t *__restrict__ sscan,
+                                                      const uint32_t *__restrict__ sbits, const uint32_t *__restrict__ swscan,
                                                       uint32_t *__restrict__ seedlist, uint16_t *__restrict__ lv16,
                                                       uint32_t *__restrict__ availw) {
     const Tile t = tiles[blockIdx.y];
@@ -506,7 +513,7 @@ __global__ void __launch_bounds__(256) k_pixel_levels(const Tile *__restrict__ t
         long long p = t.base + i;
         bool av = false;
         if (i < npix) {
-            bool m = msk[p] != 0, sd = seedflag[p] != 0;
+            bool m = msk[p] != 0, sd = bit_test(sbits, (uint32_t)p);
             if (m) {
                 uint32_t r = lrank[hb + d2[p]];
                 if (lv16)
@@ -514,7 +521,7 @@ __global__ void __launch_bounds__(256) k_pixel_levels(const Tile *__restrict__ t
                 else
                     lv[p] = r;
             }
-            if (sd) seedlist[sscan[p]] = (uint32_t)i;
+            if (sd) seedlist[bit_rank(sbits, swscan, (uint32_t)p)] = (uint32_t)i;
             av = m && !sd;
         }
         if (availw) {
@@ -1125,10 +1132,6 @@ __global__ void k_popc_words(const uint32_t *__restrict__ bits, uint32_t *__rest
     if (i < n) cnt[i] = __popc(bits[i]);
 }
 
-__device__ __forceinline__ uint32_t bit_rank(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ wscan, uint32_t w) {
-    return wscan[w >> 5] + __popc(bits[w >> 5] & ((1u << (w & 31)) - 1u));
-}
-
 struct BlkDev {
     long long block_id;
     long long wbase;       // batch write-order base of the block
@@ -1317,14 +1320,17 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     const unsigned gx = (unsigned)std::min<long long>(std::max<long long>((maxpix + 1023) / 1024, 1), 2048);
     const dim3 grid(gx, ntiles);
 
-    DevBuf msk, g, d2, tmpA, tmpB, lab, lv, seedflag, tileflags, tilemax;
+    DevBuf msk, g, d2, tmpA, tmpB, lab, lv, sbits, swcnt, swscan, tileflags, tilemax;
     BS_TRY(msk.alloc(P_pix, s));
     BS_TRY(g.alloc(P_pix * 2, s));
     BS_TRY(d2.alloc(P_pix * 4, s));
     BS_TRY(tmpA.alloc(P_pix * 4, s));
     BS_TRY(lab.alloc(P_pix * 4, s));
     BS_TRY(lv.alloc(P_pix * 4, s));
-    BS_TRY(seedflag.alloc_zero(P_pix, s));
+    const size_t nsw = ((size_t)P_pix + 31) / 32 + 1;   // seed bitmap (one bit per tile pixel)
+    BS_TRY(sbits.alloc_zero(4 * nsw, s));
+    BS_TRY(swcnt.alloc(4 * nsw, s));
+    BS_TRY(swscan.alloc(4 * nsw, s));
     BS_TRY(tileflags.alloc_zero(4 * ntiles, s));
     BS_TRY(tilemax.alloc_zero(4 * (ntiles + 1), s));
 
@@ -1378,12 +1384,12 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     if (xy) {
         if (use_mf) {
             BS_LAUNCH(k_maxfilt_xy, grid_mf, 256, mf_smem, s, dt, d2.as<uint32_t>(), msd, 1, msk.as<uint8_t>(), lv.as<uint32_t>(),
-                      seedflag.as<uint8_t>());
+                      sbits.as<uint32_t>());
         } else {
             BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, d2.as<uint32_t>(), tmpA.as<uint32_t>(), 2, msd, 0, nullptr, nullptr, nullptr,
                       nullptr);
             BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, tmpA.as<uint32_t>(), nullptr, 1, msd, 1, d2.as<uint32_t>(),
-                      msk.as<uint8_t>(), lv.as<uint32_t>(), seedflag.as<uint8_t>());
+                      msk.as<uint8_t>(), lv.as<uint32_t>(), sbits.as<uint32_t>());
         }
     } else {
         BS_TRY(tmpB.alloc(P_pix * 4, s));
@@ -1396,23 +1402,23 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
                       nullptr);
         }
         BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, tmpB.as<uint32_t>(), nullptr, 0, msd, 1, d2.as<uint32_t>(),
-                  msk.as<uint8_t>(), lv.as<uint32_t>(), seedflag.as<uint8_t>());
+                  msk.as<uint8_t>(), lv.as<uint32_t>(), sbits.as<uint32_t>());
         tmpB.release();
     }
     g_prof.mark("s1.seed_cc", s);
     BS_LAUNCH(k_seed_union, grid, 256, 0, s, dt, lv.as<uint32_t>());
 
     // ---- histogram sizes (host sync #1: total histogram entries, number of seed pixels)
-    DevBuf hsize, hbase, totals, sscan;
+    DevBuf hsize, hbase, totals;
     BS_TRY(hsize.alloc(4 * (ntiles + 1), s));
     BS_TRY(hbase.alloc(4 * (ntiles + 1), s));
     BS_TRY(totals.alloc_zero(4 * 8, s));
-    BS_TRY(sscan.alloc(P_pix * 4, s));
     uint32_t *d_tot = totals.as<uint32_t>();  // [0]=hist entries [1]=seed pixels [2]=levels [3]=mask pixels [4]=roots
     BS_LAUNCH(k_tile_hsize, cdiv(ntiles, 256), 256, 0, s, tilemax.as<uint32_t>(), hsize.as<uint32_t>(), ntiles);
     BS_TRY(scan_exclusive_u32(hsize.as<uint32_t>(), hbase.as<uint32_t>(), ntiles, d_tot + 0, s));
-    BS_TRY(scan_exclusive_u8(seedflag.as<uint8_t>(), sscan.as<uint32_t>(), P_pix, d_tot + 1, s));
-    BS_LAUNCH(k_tile_seed_max, cdiv(ntiles, 256), 256, 0, s, dt, ntiles, sscan.as<uint32_t>(), d_tot + 1,
+    BS_LAUNCH(k_popc_words, cdiv(nsw, 256), 256, 0, s, sbits.as<uint32_t>(), swcnt.as<uint32_t>(), nsw);
+    BS_TRY(scan_exclusive_u32(swcnt.as<uint32_t>(), swscan.as<uint32_t>(), nsw, d_tot + 1, s));
+    BS_LAUNCH(k_tile_seed_max, cdiv(ntiles, 256), 256, 0, s, dt, ntiles, sbits.as<uint32_t>(), swscan.as<uint32_t>(), d_tot + 1,
               tilemax.as<uint32_t>(), d_tot + 5, d_tot + 6);
     uint32_t h_tot[8];
     BS_CUDA(cudaMemcpyAsync(h_tot, d_tot, 32, cudaMemcpyDeviceToHost, s));
@@ -1445,7 +1451,7 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
         BS_TRY(queue.alloc(4 * (size_t)P_pix, s));
     BS_TRY(fstats.alloc_zero(16, s));
     BS_LAUNCH(k_seed_label_hist, grid, 256, 0, s, dt, lv.as<uint32_t>(), msk.as<uint8_t>(), d2.as<uint32_t>(),
-              lab.as<uint32_t>(), hbase.as<uint32_t>(), hist.as<uint32_t>(), sscan.as<uint32_t>(), v2 ? 1 : 0);
+              lab.as<uint32_t>(), hbase.as<uint32_t>(), hist.as<uint32_t>(), sbits.as<uint32_t>(), swscan.as<uint32_t>(), v2 ? 1 : 0);
     if (Htot) {
         BS_LAUNCH(k_nzflag, cdiv(Htot, 256), 256, 0, s, hist.as<uint32_t>(), nz.as<uint8_t>(), Htot);
         BS_TRY(scan_exclusive_u8(nz.as<uint8_t>(), lrank.as<uint32_t>(), Htot, d_tot + 2, s));
@@ -1455,11 +1461,11 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     }
     // lrank needs a valid entry at hbase[t] for every tile: hbase[t] < Htot always (hsize >= 1)
     BS_LAUNCH(k_tile_ranges, cdiv(ntiles + 1, 256), 256, 0, s, dt, ntiles, hbase.as<uint32_t>(), lrank.as<uint32_t>(),
-              d_tot + 2, sscan.as<uint32_t>(), d_tot + 1, tile_lvl.as<uint32_t>(), tile_seed.as<uint32_t>(),
+              d_tot + 2, sbits.as<uint32_t>(), swscan.as<uint32_t>(), d_tot + 1, tile_lvl.as<uint32_t>(), tile_seed.as<uint32_t>(),
               qoff.as<uint32_t>(), d_tot + 3, tile_q.as<uint32_t>());
     // the seed parent array lives in lv and is consumed by k_seed_label_hist above; now lv becomes the level
     BS_LAUNCH(k_pixel_levels, grid, 256, 0, s, dt, msk.as<uint8_t>(), d2.as<uint32_t>(), hbase.as<uint32_t>(),
-              lrank.as<uint32_t>(), lv.as<uint32_t>(), seedflag.as<uint8_t>(), sscan.as<uint32_t>(), seedlist.as<uint32_t>(),
+              lrank.as<uint32_t>(), lv.as<uint32_t>(), sbits.as<uint32_t>(), swscan.as<uint32_t>(), seedlist.as<uint32_t>(),
               v2 ? lv16.as<uint16_t>() : nullptr, v2 ? availw.as<uint32_t>() : nullptr);
     if (g_debug) {
         DevBuf c1, c2;
@@ -1493,7 +1499,6 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     }
     // release what the flood no longer needs
     queue.release();
-    sscan.release();
     hist.release();
     nz.release();
     lrank.release();

@@ -69,25 +69,35 @@ __global__ void __launch_bounds__(256) k_rag_accumulate(const S2Blk *__restrict_
     const uint32_t tmask = b.tcap - 1;
     for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < nvox; i0 += (long long)gridDim.x * blockDim.x) {
         long long i = i0 + threadIdx.x;
-        uint32_t id1 = NONE32;
+        uint64_t f1 = 0;
         int x = 0, y = 0, z = 0, gx = 0, gy = 0, gz = 0;
         if (i < nvox) {
             unravel3(i, RX, RY, x, y, z);
             gz = b.ro[0] + z, gy = b.ro[1] + y, gx = b.ro[2] + x;
             // fragments array covers the task ROI; outside: zero fill
             int fz = gz - roz, fy = gy - roy, fx = gx - rox;
-            if (fz >= 0 && fz < rsz && fy >= 0 && fy < rsy && fx >= 0 && fx < rsx)
-                id1 = id_to_dense(idm, frags[((size_t)fz * rsy + fy) * rsx + fx]);
+            if (fz >= 0 && fz < rsz && fy >= 0 && fy < rsy && fx >= 0 && fx < rsx) f1 = frags[((size_t)fz * rsy + fy) * rsx + fx];
         }
+        // raw ids are compared first: only voxels on a fragment boundary pay for the id -> node translation
+        uint32_t id1 = NONE32;
+        bool id1_done = false;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-            uint32_t id2 = NONE32;
-            if (id1 != NONE32) {
+            uint64_t f2 = 0;
+            if (f1 != 0) {
                 int lc = d == 0 ? z : (d == 1 ? y : x);
                 if (lc > 0) {
                     int fz = gz - roz - (d == 0), fy = gy - roy - (d == 1), fx = gx - rox - (d == 2);
-                    if (fz >= 0 && fy >= 0 && fx >= 0) id2 = id_to_dense(idm, frags[((size_t)fz * rsy + fy) * rsx + fx]);
+                    if (fz >= 0 && fy >= 0 && fx >= 0) f2 = frags[((size_t)fz * rsy + fy) * rsx + fx];
                 }
+            }
+            uint32_t id2 = NONE32;
+            if (f2 != 0 && f2 != f1) {
+                if (!id1_done) {
+                    id1 = id_to_dense(idm, f1);
+                    id1_done = true;
+                }
+                id2 = id_to_dense(idm, f2);
             }
             bool has = id1 != NONE32 && id2 != NONE32 && id2 != id1;
             unsigned act = __ballot_sync(FULL, has);

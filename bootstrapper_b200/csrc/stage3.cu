@@ -136,4 +136,40 @@ int relabel_dense(Plan &P, const uint64_t *frags, int64_t n, const uint64_t *con
     return BS_OK;
 }
 
+// ---- node ids of the whole task from the per-block fragment counts (ids are 1..n per block + block_id * prod(block_size),
+// watershed_frags.py:224; blocks ascending by id): the sorted key row of the fragment -> segment LUT
+__global__ void k_node_ids(const long long *__restrict__ nbase, const long long *__restrict__ bid, int nblocks,
+                           long long nvox_block, long long n, uint64_t *__restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo = 0, hi = nblocks - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (nbase[mid] <= i)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    out[i] = (uint64_t)(i - nbase[lo] + 1) + (uint64_t)bid[lo] * (uint64_t)nvox_block;
+}
+
+int plan_node_ids(Plan &P, uint64_t *out, long long *n_out, cudaStream_t s) {
+    const size_t nb = P.blocks.size();
+    const long long n = P.block_nbase[nb];
+    if (n_out) *n_out = n;
+    if (!out || n == 0) return BS_OK;
+    std::vector<long long> h(2 * nb);
+    for (size_t i = 0; i < nb; i++) {
+        h[i] = P.block_nbase[i];
+        h[nb + i] = P.blocks[i].block_id;
+    }
+    DevBuf d;
+    BS_TRY(d.alloc(16 * nb, s));
+    BS_CUDA(cudaMemcpyAsync(d.p, h.data(), 16 * nb, cudaMemcpyHostToDevice, s));
+    BS_LAUNCH(k_node_ids, cdiv((size_t)n, 256), 256, 0, s, d.as<long long>(), d.as<long long>() + nb, (int)nb, P.nvox_block, n, out);
+    BS_CUDA(cudaStreamSynchronize(s));   // h is a host-staged copy
+    BS_CUDA(cudaGetLastError());
+    return BS_OK;
+}
+
 }  // namespace bs

@@ -35,7 +35,7 @@ class WsConfig(C.Structure):
 EXPORTS = [
     "bs_last_error", "bs_launch_count", "bs_version", "bs_plan_create", "bs_plan_destroy", "bs_plan_num_blocks",
     "bs_plan_block_info", "bs_plan_set_owned", "bs_stage1_fragments", "bs_stage1_num_nodes", "bs_stage1_get_nodes",
-    "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_stage2_agglomerate", "bs_stage2_num_edges",
+    "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_plan_node_ids", "bs_stage2_agglomerate", "bs_stage2_num_edges",
     "bs_stage2_get_edges", "bs_connected_components", "bs_relabel", "bs_stage3_relabel", "bs_watershed_from_affinities",
     "bs_synth_affs", "bs_debug_fetch", "bs_set_debug", "bs_set_profiling", "bs_get_profile",
     "bs_release_scratch", "bs_set_flood_version", "bs_set_agglom_version", "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
@@ -211,6 +211,15 @@ class Plan:
     def set_block_counts(self, counts):
         c = np.ascontiguousarray(counts, dtype=np.int64)
         _check(lib().bs_stage1_set_block_counts(self._h, c.ctypes.data_as(C.c_void_p)))
+
+    def node_ids(self, device):
+        """ascending ids of all fragments of the task (needs every block's count: single rank, or after
+        set_block_counts)"""
+        n = C.c_int64()
+        _check(lib().bs_plan_node_ids(self._h, None, C.byref(n), _stream()))
+        ids = torch.empty(n.value, dtype=torch.int64, device=device)
+        _check(lib().bs_plan_node_ids(self._h, _dev(ids), C.byref(n), _stream()))
+        return ids
 
     # ---- stage 2
     def agglomerate(self, affs, frags):

@@ -151,7 +151,10 @@ class ShardedSegmenter:
         plan = self._plan(native._aff_dtype(affs_win))
         g = self.geo
         prof = {}
-        frags = torch.zeros(self.win_shape, dtype=torch.int64, device=affs_win.device)
+        # every voxel of the task ROI lies in some block's write ROI; halo planes of a slab window are filled by
+        # the neighbour exchange, so only multi-rank windows need the zero fill
+        alloc = torch.zeros if self.world > 1 else torch.empty
+        frags = alloc(self.win_shape, dtype=torch.int64, device=affs_win.device)
         plan.fragments(affs_win, frags_out=frags)
         prof.update(native.get_profile())
         counts = allgather_counts(plan.block_counts(), self.world, affs_win.device, self.group)
@@ -164,7 +167,7 @@ class ShardedSegmenter:
         ev0.record()
         eu, ev, es = plan.edges(affs_win.device)
         eu, ev, es = allgather_edges(eu, ev, es, self.world, self.group)
-        nodes = global_node_ids(self.block_ids, counts, self.nvox_block, affs_win.device)
+        nodes = plan.node_ids(affs_win.device)
         own = frags[g["z0"] - g["w0"]:g["z1"] - g["w0"]]
         thrs = list(self.p["thresholds"])
         comps = [native.connected_components(nodes, eu, ev, es, float(thr)) for thr in thrs]

@@ -97,6 +97,10 @@ int bs_stage1_block_counts(const bs_plan *p, int64_t *counts);
  * stage 2 can number halo fragments of neighbouring ranks. */
 int bs_stage1_set_block_counts(bs_plan *p, const int64_t *counts);
 
+/* ids of ALL fragments of the task in ascending order (the key row of the fragment->segment LUT,
+ * post/watershed.py:156-161,187) derived from the per-block counts; ids_out device (NULL: count only). */
+int bs_plan_node_ids(bs_plan *p, uint64_t *ids_out, int64_t *n_out, void *stream);
+
 /* ---- stage 2: RAG extraction + waterz agglomeration + merge-tree scores ------------
  * replaces: WaterzAgglom.process_block for every owned block
  * (post/blockwise/waterz_agglom.py:106-170): funlib.segment relabel (:116),
