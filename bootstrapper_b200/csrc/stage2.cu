@@ -64,33 +64,38 @@ __global__ void __launch_bounds__(256) k_rag_accumulate(const S2Blk *__restrict_
                                                         uint32_t *hfirst, uint32_t *overflow) {
     const S2Blk &b = blks[blockIdx.y];
     const int RZ = b.rs[0], RY = b.rs[1], RX = b.rs[2];
-    const long long nvox = (long long)RZ * RY * RX;
     const size_t nvol = (size_t)volZ * volY * volX;
     const uint32_t tmask = b.tcap - 1;
-    for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < nvox; i0 += (long long)gridDim.x * blockDim.x) {
-        long long i = i0 + threadIdx.x;
-        uint64_t f1 = 0;
-        int x = 0, y = 0, z = 0, gx = 0, gy = 0, gz = 0;
-        if (i < nvox) {
-            unravel3(i, RX, RY, x, y, z);
-            gz = b.ro[0] + z, gy = b.ro[1] + y, gx = b.ro[2] + x;
-            // fragments array covers the task ROI; outside: zero fill
-            int fz = gz - roz, fy = gy - roy, fx = gx - rox;
-            if (fz >= 0 && fz < rsz && fy >= 0 && fy < rsy && fx >= 0 && fx < rsx) f1 = frags[((size_t)fz * rsy + fy) * rsx + fx];
-        }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t plane = (size_t)rsy * rsx;
+    // one warp per row of the read ROI: the row / plane predecessors are loaded once per 32 voxels and the
+    // x predecessor comes from the neighbouring lane
+    for (int r = blockIdx.x * 8 + warp; r < RZ * RY; r += gridDim.x * 8) {
+        const int z = r / RY, y = r - z * RY;
+        const int gz = b.ro[0] + z, gy = b.ro[1] + y;
+        // fragments array covers the task ROI; outside: zero fill
+        const int fz = gz - roz, fy = gy - roy;
+        const bool row_in = fz >= 0 && fz < rsz && fy >= 0 && fy < rsy;
+        const uint64_t *rowp = frags + (row_in ? ((size_t)fz * rsy + fy) * rsx : 0);
+        const bool up_ok = row_in && y > 0 && fy > 0, zm_ok = row_in && z > 0 && fz > 0;
+        uint64_t carry = 0;
+      for (int x0 = 0; x0 < RX; x0 += 32) {
+        const int x = x0 + lane;
+        const int gx = b.ro[2] + x, fx = gx - rox;
+        const bool in = x < RX && row_in && fx >= 0 && fx < rsx;
+        const long long i = (long long)r * RX + x;
+        const uint64_t f1 = in ? rowp[fx] : 0;
+        uint64_t fxm = __shfl_up_sync(FULL, f1, 1);
+        if (lane == 0) fxm = carry;
+        carry = __shfl_sync(FULL, f1, 31);
+        const uint64_t fym = (in && up_ok && f1) ? rowp[(long long)fx - rsx] : 0;
+        const uint64_t fzm = (in && zm_ok && f1) ? rowp[(long long)fx - (long long)plane] : 0;
         // raw ids are compared first: only voxels on a fragment boundary pay for the id -> node translation
         uint32_t id1 = NONE32;
         bool id1_done = false;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-            uint64_t f2 = 0;
-            if (f1 != 0) {
-                int lc = d == 0 ? z : (d == 1 ? y : x);
-                if (lc > 0) {
-                    int fz = gz - roz - (d == 0), fy = gy - roy - (d == 1), fx = gx - rox - (d == 2);
-                    if (fz >= 0 && fy >= 0 && fx >= 0) f2 = frags[((size_t)fz * rsy + fy) * rsx + fx];
-                }
-            }
+            const uint64_t f2 = f1 == 0 ? 0 : (d == 0 ? fzm : (d == 1 ? fym : fxm));
             uint32_t id2 = NONE32;
             if (f2 != 0 && f2 != f1) {
                 if (!id1_done) {
@@ -146,6 +151,7 @@ __global__ void __launch_bounds__(256) k_rag_accumulate(const S2Blk *__restrict_
                 }
             }
         }
+      }
     }
 }
 
@@ -826,7 +832,9 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
         maxread = std::max(maxread, rv);
     }
     {
-        dim3 gr((unsigned)std::min<long long>(std::max<long long>((maxread + 1023) / 1024, 1), 4096), nown);
+        int maxrows = 1;
+        for (auto &d : hb) maxrows = std::max(maxrows, d.rs[0] * d.rs[1]);
+        dim3 gr((unsigned)std::min(std::max((maxrows + 15) / 16, 1), 4096), nown);
         BS_LAUNCH((k_rag_accumulate<T>), gr, 256, 0, s, db, (const T *)affs, frags, idm, cfg.win_z > 0 ? cfg.win_z : cfg.vol_shape[0],
                   cfg.vol_shape[1], cfg.vol_shape[2], cfg.win_z > 0 ? cfg.win_z0 : 0,
                   cfg.roi_offset[0] + (cfg.win_z > 0 ? cfg.win_z0 : 0), cfg.roi_offset[1], cfg.roi_offset[2],
