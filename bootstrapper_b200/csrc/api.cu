@@ -295,6 +295,7 @@ int bs_release_scratch(void) {
     cudaMemPool_t pool;
     BS_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
     BS_CUDA(cudaDeviceSynchronize());
+    g_arena.destroy();
     BS_CUDA(cudaMemPoolTrimTo(pool, 0));
     return BS_OK;
 }

@@ -55,16 +55,50 @@ extern unsigned long long g_launches;
         bs::g_launches++;                                          \
     } while (0)
 
-// ---- stream-ordered scratch buffer ----
+// ---- scratch memory ----
+// Stage scratch comes from one grow-only arena per process (bump allocation, reset at the start of every stage
+// batch): a stage issues ~50 allocations whose sizes depend on the data, and carving them from a cached slab keeps
+// cudaMallocAsync / cudaFreeAsync (and the pool's occasional re-mapping) out of the step.  The first run of a
+// given size finds no arena, allocates stream-ordered and records the bytes it needed; the next run gets the slab.
+struct Arena {
+    char *base = nullptr;
+    size_t cap = 0, off = 0, need = 0, need_last = 0;
+    bool active = false;
+    int begin(bool enable);   // (re)size from the recorded need, reset the bump pointer
+    void end();
+    void destroy();
+};
+extern Arena g_arena;
+
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
     cudaStream_t s = 0;
+    bool from_arena = false;
     DevBuf() {}
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     int alloc(size_t n, cudaStream_t stream) {
+        release();
+        s = stream;
+        bytes = n;
+        if (n == 0) n = 16;
+        if (g_arena.active) {
+            size_t a = (n + 255) & ~(size_t)255;
+            g_arena.need += a;
+            if (g_arena.off + a <= g_arena.cap) {
+                p = g_arena.base + g_arena.off;
+                g_arena.off += a;
+                from_arena = true;
+                return BS_OK;
+            }
+        }
+        BS_CUDA(cudaMallocAsync(&p, n, stream));
+        return BS_OK;
+    }
+    // results that outlive the stage call (plan-owned node / edge tables)
+    int alloc_persistent(size_t n, cudaStream_t stream) {
         release();
         s = stream;
         bytes = n;
@@ -83,14 +117,16 @@ struct DevBuf {
         return BS_OK;
     }
     void release() {
-        if (p) cudaFreeAsync(p, s);
+        if (p && !from_arena) cudaFreeAsync(p, s);
         p = nullptr;
         bytes = 0;
+        from_arena = false;
     }
     void swap(DevBuf &o) {
         std::swap(p, o.p);
         std::swap(bytes, o.bytes);
         std::swap(s, o.s);
+        std::swap(from_arena, o.from_arena);
     }
     template <typename T>
     T *as() const {

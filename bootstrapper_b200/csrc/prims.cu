@@ -8,6 +8,43 @@ void set_error(const std::string &msg) { g_err = msg; }
 const char *get_error() { return g_err.c_str(); }
 unsigned long long g_launches = 0;
 Profiler g_prof;
+Arena g_arena;
+
+int Arena::begin(bool enable) {
+    active = false;
+    off = 0;
+    need = 0;
+    if (!enable) return BS_OK;
+    if (need_last > cap) {
+        // nothing of the previous stage call is live any more: stage results are plan-owned (alloc_persistent)
+        BS_CUDA(cudaDeviceSynchronize());
+        if (base) BS_CUDA(cudaFree(base));
+        base = nullptr;
+        cap = 0;
+        size_t want = need_last + need_last / 8 + (64u << 20);
+        if (cudaMalloc((void **)&base, want) == cudaSuccess) {
+            cap = want;
+        } else {
+            cudaGetLastError();   // not enough memory for a slab: stay on the stream-ordered allocator
+            base = nullptr;
+            need_last = 0;
+        }
+    }
+    active = true;   // also without a slab: the bytes this run needs are recorded
+    return BS_OK;
+}
+
+void Arena::end() {
+    if (need > need_last) need_last = need;
+    active = false;
+}
+
+void Arena::destroy() {
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = off = need = need_last = 0;
+    active = false;
+}
 
 void Profiler::mark(const char *name, cudaStream_t s) {
     if (!on) return;

@@ -748,7 +748,7 @@ __global__ void __launch_bounds__(64) k_flood(const Tile *__restrict__ tiles, in
 // "in mask, not labelled yet" bitmap of the tile and a small claim table sit in shared memory (no global
 // atomics, nothing to undo when a step is truncated), queue entries carry (label << 17 | pixel), levels
 // are u16.  Global traffic per flooded pixel: one queue entry written + read, one u16 level read.
-static constexpr int F2_WARPS = 4;
+static constexpr int F2_WARPS = 1;
 static constexpr int F2_HASH = 256;
 static constexpr uint32_t F2_PIXMASK = 0x1FFFFu;
 static constexpr int F2_MAXPIX = 1 << 17;
@@ -1573,9 +1573,9 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     {
         DevBuf nid, npos, nsz;
         size_t tot = (size_t)(node_base + nn);
-        BS_TRY(nid.alloc(8 * (tot + 1), s));
-        BS_TRY(npos.alloc(12 * (tot + 1), s));
-        BS_TRY(nsz.alloc(4 * (tot + 1), s));
+        BS_TRY(nid.alloc_persistent(8 * (tot + 1), s));
+        BS_TRY(npos.alloc_persistent(12 * (tot + 1), s));
+        BS_TRY(nsz.alloc_persistent(4 * (tot + 1), s));
         if (node_base) {
             BS_CUDA(cudaMemcpyAsync(nid.p, P.node_id.p, 8 * node_base, cudaMemcpyDeviceToDevice, s));
             BS_CUDA(cudaMemcpyAsync(npos.p, P.node_pos.p, 12 * node_base, cudaMemcpyDeviceToDevice, s));
@@ -1634,8 +1634,10 @@ int stage1_run(Plan &P, const void *affs, const uint8_t *mask, uint64_t *frags_o
             i++;
         }
         long long nn = 0;
+        BS_TRY(g_arena.begin(!g_debug));
         int rc = cfg.aff_dtype == BS_DTYPE_U8 ? stage1_batch<uint8_t>(P, batch, A, frags_out, node_base, &nn, s)
                                                : stage1_batch<float>(P, batch, A, frags_out, node_base, &nn, s);
+        g_arena.end();
         if (rc != BS_OK) return rc;
         node_base += nn;
     }

@@ -1079,9 +1079,9 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
         return BS_ERR_OVERFLOW;
     }
     const uint32_t EO = E ? h2[0] : 0;
-    BS_TRY(P.edge_u.alloc(8 * ((size_t)EO + 1), s));
-    BS_TRY(P.edge_v.alloc(8 * ((size_t)EO + 1), s));
-    BS_TRY(P.edge_score.alloc(4 * ((size_t)EO + 1), s));
+    BS_TRY(P.edge_u.alloc_persistent(8 * ((size_t)EO + 1), s));
+    BS_TRY(P.edge_v.alloc_persistent(8 * ((size_t)EO + 1), s));
+    BS_TRY(P.edge_score.alloc_persistent(4 * ((size_t)EO + 1), s));
     if (E)
         BS_LAUNCH(k_compact_edges, cdiv(E, 256), 256, 0, s, owned.as<uint8_t>(), oscan.as<uint32_t>(), E, ou.as<uint64_t>(),
                   ov.as<uint64_t>(), os.as<float>(), P.edge_u.as<uint64_t>(), P.edge_v.as<uint64_t>(), P.edge_score.as<float>());
@@ -1118,8 +1118,10 @@ int stage2_run(Plan &P, const void *affs, const uint64_t *frags, cudaStream_t s)
     int mult = 1;
     for (int attempt = 0; attempt < 4; attempt++) {
         bool ovf = false;
+        BS_TRY(g_arena.begin(!g_debug));
         int rc = P.cfg.aff_dtype == BS_DTYPE_U8 ? stage2_impl<uint8_t>(P, affs, frags, mult, s, &ovf)
                                                 : stage2_impl<float>(P, affs, frags, mult, s, &ovf);
+        g_arena.end();
         if (rc != BS_OK) return rc;
         if (!ovf) {
             g_prof.finish(s);
