@@ -57,4 +57,18 @@ size_t agglom_smem_bytes(uint32_t Ecap, uint32_t Ncap, bool sum64);
 int agglom_smem_launch(const AggBlk *blks, const int *list, int nlist, const AggArrays &A, float threshold, int keep_cheaper,
                        bool u8, bool sum64, uint32_t Ecap, uint32_t Ncap, cudaStream_t s);
 
+// agglom_pq.cu: waterz with the non-discretised queue (single-shot ws path) on one region graph.
+struct PqRequest {
+    const float *thresholds;   // host, ascending
+    int T;
+    uint64_t *const *segs;     // host array of T device pointers (roi-shaped uint64)
+    uint32_t counters[4];      // out: pops, stale, deleted, merges
+};
+int agglom_pq_run(bool u8, uint32_t E, uint32_t Nc, const uint32_t *ceu, const uint32_t *cev, unsigned long long *esum,
+                  uint32_t *ecnt, const float *thresholds_host, int T, int keep_cheaper, uint32_t *roots_out,
+                  uint32_t *counters_host, cudaStream_t s);
+int agglom_pq_relabel(const uint64_t *frags, size_t n, IdMap idm, const uint32_t *roots, const uint32_t *cscan, const uint8_t *used,
+                      uint32_t Nc, uint32_t nview, uint32_t dense0, long long block_id, long long nvox_block, int T,
+                      uint64_t *const *segs, cudaStream_t s);
+
 }  // namespace bs

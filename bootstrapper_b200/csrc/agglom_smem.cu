@@ -137,14 +137,17 @@ __global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restric
         const unsigned act = __ballot_sync(FULL, v);
 #pragma unroll
         for (int side = 0; side < 2; side++) {
+            uint32_t node = 0;
+            unsigned peers = 0;
             if (v) {
-                const uint32_t node = side ? ev[e] : eu[e];
-                const unsigned peers = __match_any_sync(act, node);
+                node = side ? ev[e] : eu[e];
+                peers = __match_any_sync(act, node);
                 const unsigned higher = peers & ~((2u << lane) - 1u);
                 const uint32_t nxt = higher ? 2 * (e0 + (__ffs(higher) - 1)) + side : (uint32_t)ahead[node];
                 anext[2 * e + side] = (uint16_t)nxt;
-                if (lane == __ffs(peers) - 1) ahead[node] = (uint16_t)(2 * e + side);
             }
+            __syncwarp();   // the old heads are read before any leader replaces them
+            if (v && lane == __ffs(peers) - 1) ahead[node] = (uint16_t)(2 * e + side);
             __syncwarp();
         }
     }

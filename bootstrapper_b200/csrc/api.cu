@@ -3,14 +3,14 @@
 
 #include <algorithm>
 
-#include "geom.h"
+#include "agglom.cuh"
 
 namespace bs {
 int g_debug = 0;
 int g_agglom_version = 0;  // 0 = auto (shared-memory kernel when the block fits), 1 = force the global-memory kernel
 int g_flood_version = 0;   // 0 = auto (v2 when eligible), 1 = force the global-memory flood
 int stage1_run(Plan &P, const void *affs, const uint8_t *mask, uint64_t *frags_out, cudaStream_t s);
-int stage2_run(Plan &P, const void *affs, const uint64_t *frags, cudaStream_t s);
+int stage2_run(Plan &P, const void *affs, const uint64_t *frags, cudaStream_t s, PqRequest *pq);
 int connected_components(const uint64_t *nodes, int64_t n, const uint64_t *eu, const uint64_t *ev, const float *scores,
                          int64_t m, float thr, uint64_t *comp, cudaStream_t s);
 int relabel(const uint64_t *frags, int64_t n, const uint64_t *keys, const uint64_t *vals, int64_t k, uint64_t *seg,
@@ -186,7 +186,25 @@ int bs_stage2_agglomerate(bs_plan *p, const void *affs, const uint64_t *frags, v
         set_error("bs_stage2_agglomerate: multi-rank plan needs bs_stage1_set_block_counts first");
         return BS_ERR_STATE;
     }
-    return stage2_run(P, affs, frags, (cudaStream_t)stream);
+    return stage2_run(P, affs, frags, (cudaStream_t)stream, nullptr);
+}
+
+int bs_waterz_segment(bs_plan *p, const void *affs, const uint64_t *frags, const float *thresholds, int n_thresholds,
+                      uint64_t *const *segs_out, uint32_t *counters_out, void *stream) {
+    BS_ARG(p && affs && frags && thresholds && segs_out && n_thresholds >= 1, "bs_waterz_segment: null argument");
+    for (int t = 1; t < n_thresholds; t++)
+        BS_ARG(thresholds[t] >= thresholds[t - 1], "bs_waterz_segment: thresholds must be ascending (waterz sorts them)");
+    Plan &P = *p->p;
+    BS_ARG(P.blocks.size() == 1 && P.owned.size() == 1, "bs_waterz_segment: needs a single-block plan (block = roi, context 0)");
+    PqRequest rq;
+    rq.thresholds = thresholds;
+    rq.T = n_thresholds;
+    rq.segs = segs_out;
+    for (int i = 0; i < 4; i++) rq.counters[i] = 0;
+    int rc = stage2_run(P, affs, frags, (cudaStream_t)stream, &rq);
+    if (rc == BS_OK && counters_out)
+        for (int i = 0; i < 4; i++) counters_out[i] = rq.counters[i];
+    return rc;
 }
 
 int bs_stage2_num_edges(const bs_plan *p, int64_t *n) {

@@ -757,7 +757,8 @@ static int keep_debug2(Plan &P, const char *name, DevBuf &buf, int elem, long lo
 }
 
 template <typename T>
-static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int table_mult, cudaStream_t s, bool *overflowed) {
+static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int table_mult, cudaStream_t s, bool *overflowed,
+                       PqRequest *pq) {
     const bs_ws_config &cfg = P.cfg;
     const int nown = (int)P.owned.size();
     *overflowed = false;
@@ -926,6 +927,22 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
         BS_CUDA(cudaStreamSynchronize(s));
     }
     const size_t Ctot = h_cbase[nown];
+
+    if (pq) {
+        // ---- single-shot path: one region graph, non-discretised queue, a segmentation per threshold
+        BS_ARG(nown == 1 && P.blocks.size() == 1, "simple_watershed needs a single-block plan (block = roi, no context)");
+        BS_ARG(Ctot < (1ull << 31) && E < (1u << 31), "simple_watershed: region graph too large");
+        g_prof.mark("s2.agglomerate", s);
+        DevBuf roots;
+        BS_TRY(roots.alloc(4 * ((size_t)pq->T * (Ctot + 1)), s));
+        BS_TRY(agglom_pq_run(sizeof(T) == 1, E, (uint32_t)Ctot, ceu.as<uint32_t>(), cev.as<uint32_t>(), esum.as<unsigned long long>(),
+                             ecnt.as<uint32_t>(), pq->thresholds, pq->T, cfg.keep_cheaper, roots.as<uint32_t>(), pq->counters, s));
+        g_prof.mark("s2.relabel", s);
+        const size_t nvox = (size_t)(cfg.win_z > 0 ? cfg.win_z : cfg.roi_shape[0]) * cfg.roi_shape[1] * cfg.roi_shape[2];
+        BS_TRY(agglom_pq_relabel(frags, nvox, idm, roots.as<uint32_t>(), cscan.as<uint32_t>(), used.as<uint8_t>(), (uint32_t)Ctot,
+                                 (uint32_t)Vtot, hb[0].view_first[0], hb[0].block_id, P.nvox_block, pq->T, pq->segs, s));
+        return BS_OK;
+    }
 
     // ---- which blocks fit the shared-memory kernel (agglom_smem.cu)
     std::vector<AggBlk> ab(nown);
@@ -1113,14 +1130,14 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
     return BS_OK;
 }
 
-int stage2_run(Plan &P, const void *affs, const uint64_t *frags, cudaStream_t s) {
+int stage2_run(Plan &P, const void *affs, const uint64_t *frags, cudaStream_t s, PqRequest *pq) {
     g_prof.reset();
     int mult = 1;
     for (int attempt = 0; attempt < 4; attempt++) {
         bool ovf = false;
         BS_TRY(g_arena.begin(!g_debug));
-        int rc = P.cfg.aff_dtype == BS_DTYPE_U8 ? stage2_impl<uint8_t>(P, affs, frags, mult, s, &ovf)
-                                                : stage2_impl<float>(P, affs, frags, mult, s, &ovf);
+        int rc = P.cfg.aff_dtype == BS_DTYPE_U8 ? stage2_impl<uint8_t>(P, affs, frags, mult, s, &ovf, pq)
+                                                : stage2_impl<float>(P, affs, frags, mult, s, &ovf, pq);
         g_arena.end();
         if (rc != BS_OK) return rc;
         if (!ovf) {

@@ -5,6 +5,7 @@ Mirrors the three stages + barriers of the reference's waterz_pipeline (post/wat
 WatershedFrags -> WaterzAgglom -> thresholded connected components -> LUT -> Relabel.
 Everything numeric runs in libbsnative (CUDA, sm_100a); torch only owns the memory and the stream.
 """
+import numpy as np
 import torch
 
 from .. import native
@@ -29,6 +30,45 @@ def resolve_ws_params(params):
         raise NotImplementedError("blockwise agglomeration supports merge_function='mean' only "
                                   "(as the reference: post/blockwise/waterz_agglom.py:24-36)")
     return p
+
+
+SIMPLE_MERGE_FUNCTIONS = (  # post/watershed.py:232-244
+    "mean", "hist_quant_10", "hist_quant_10_initmax", "hist_quant_25", "hist_quant_25_initmax", "hist_quant_50",
+    "hist_quant_50_initmax", "hist_quant_75", "hist_quant_75_initmax", "hist_quant_90", "hist_quant_90_initmax")
+
+
+def segment_simple(affs, params=None, mask=None):
+    """In-memory core of `simple_watershed` (post/watershed.py:206-354): fragments of the whole ROI, then waterz
+    with the default (non-discretised) queue, one segmentation per threshold.  affs: CUDA tensor (C, Z, Y, X)
+    uint8 (normalised /255 as the reference does) or float32; only [:3] is read; a 2-channel input gets an empty
+    z channel.  Returns dict(fragments, n, segs {thr: tensor}, counters)."""
+    if not affs.is_cuda:
+        raise native.BsError("segment_simple needs the affinities on a CUDA device (no CPU fallback)")
+    p = dict(WS_DEFAULTS)
+    p.update(params or {})
+    for k in ("sigma", "noise_eps", "bias"):
+        if p.get(k) is not None:
+            raise NotImplementedError(f"ws parameter {k!r} is not implemented in the CUDA path yet")
+    if p["merge_function"] not in SIMPLE_MERGE_FUNCTIONS:
+        raise KeyError(p["merge_function"])
+    if p["merge_function"] != "mean":
+        raise NotImplementedError("only merge_function='mean' (OneMinus<MeanAffinity>) is implemented in the CUDA path")
+    affs = affs[:3]
+    if affs.shape[0] == 2:   # post/watershed.py:305-308
+        affs = torch.cat([torch.zeros_like(affs[:1]), affs], 0)
+    if mask is not None:     # affs_data *= (mask > 0)   (post/watershed.py:271-272)
+        affs = affs * (mask > 0).to(affs.dtype)
+    affs = affs.contiguous()
+    vol_shape = tuple(affs.shape[1:])
+    plan = native.Plan(vol_shape, vol_shape, (0, 0, 0), native._aff_dtype(affs), n_channels=3,
+                       fragments_in_xy=p["fragments_in_xy"], min_seed_distance=p["min_seed_distance"],
+                       filter_fragments=0.0, remove_debris=0)
+    frags = plan.fragments(affs)
+    outs, thr, counters = plan.waterz_segment(affs, frags, p["thresholds"])
+    segs = {}
+    for t in p["thresholds"]:
+        segs[t] = outs[thr.index(float(np.float32(t)))]
+    return dict(fragments=frags, n=plan.num_nodes(), segs=segs, counters=counters, params=p, plan=plan)
 
 
 def default_context(block_size):

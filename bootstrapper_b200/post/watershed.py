@@ -107,9 +107,50 @@ def waterz_pipeline(config):
 
 
 def simple_watershed(config):
-    raise NotImplementedError(
-        "the single-shot ws path (waterz with the non-discretised queue, post/watershed.py:206-354) is not built yet; "
-        "use blockwise=true (block_shape='roi' gives one block)")
+    """post/watershed.py:206-354: single-shot fragments + waterz over the sorted thresholds, no blocks, no DB."""
+    from .pipeline import segment_simple
+    affs_ds = config["affs_dataset"]
+    frags_ds_prefix = config["fragments_dataset"]
+    seg_ds_prefix = config["seg_dataset_prefix"]
+    mask_ds = config.get("mask_dataset")
+    roi_offset, roi_shape = config.get("roi_offset"), config.get("roi_shape")
+    thresholds = config.get("thresholds", [0.2, 0.35, 0.5])
+    merge_function = config.get("merge_function", "mean")
+    frag_params = dict(fragments_in_xy=config.get("fragments_in_xy", True),
+                       min_seed_distance=config.get("min_seed_distance", 10), sigma=config.get("sigma"),
+                       noise_eps=config.get("noise_eps"), bias=config.get("bias"))
+
+    affs = open_ds(affs_ds)
+    offset, shape = (tuple(roi_offset), tuple(roi_shape)) if roi_offset is not None else affs.roi
+    vs = affs.voxel_size
+    start = [int((o - ao) // v) for o, ao, v in zip(offset, affs.offset, vs)]
+    stop = [s0 + int(sh // v) for s0, sh, v in zip(start, shape, vs)]
+    affs_data = affs.read((0,) + tuple(start), (min(3, affs.shape[0]),) + tuple(stop))
+    dev = "cuda"
+    affs_t = torch.from_numpy(np.ascontiguousarray(affs_data)).to(dev)
+    if affs_t.dtype not in (torch.uint8, torch.float32):
+        affs_t = affs_t.to(torch.float32)
+    mask_t = None
+    if mask_ds is not None:
+        mask = open_ds(mask_ds)
+        mstart = [int((o - mo) // v) for o, mo, v in zip(offset, mask.offset, mask.voxel_size)]
+        mstop = [s0 + (b - a) for s0, a, b in zip(mstart, start, stop)]
+        mask_t = torch.from_numpy(np.ascontiguousarray(mask.read(tuple(mstart), tuple(mstop)))).to(dev)
+
+    r = segment_simple(affs_t, dict(thresholds=thresholds, merge_function=merge_function, **frag_params), mask=mask_t)
+
+    frags_ds_name = str(Path(frags_ds_prefix) / build_name(frag_params))
+    frags = prepare_ds(frags_ds_name, tuple(r["fragments"].shape), tuple(offset), vs, np.uint64,
+                       axis_names=affs.axis_names[1:] if affs.axis_names else None, units=affs.units)
+    frags.write(r["fragments"].cpu().numpy().view(np.uint64))
+    dump_params(frags_ds_name, {"method": "ws", "blockwise": False, **frag_params})
+    for threshold in thresholds:
+        params = {"merge_function": merge_function, "threshold": threshold, **frag_params}
+        seg_ds_name = str(Path(seg_ds_prefix) / build_name(params))
+        seg = prepare_ds(seg_ds_name, tuple(r["fragments"].shape), tuple(offset), vs, np.uint64,
+                         axis_names=affs.axis_names[1:] if affs.axis_names else None, units=affs.units)
+        seg.write(r["segs"][threshold].cpu().numpy().view(np.uint64))
+        dump_params(seg_ds_name, {"method": "ws", "blockwise": False, **params})
 
 
 def watershed_segmentation(config):

@@ -114,6 +114,17 @@ int bs_stage2_num_edges(const bs_plan *p, int64_t *n);
 /* edges persisted by the owned blocks: u < v (fragment ids), merge_score (NaN = NULL) */
 int bs_stage2_get_edges(const bs_plan *p, uint64_t *u, uint64_t *v, float *score, void *stream);
 
+/* ---- single-shot path: waterz with the default (non-discretised) queue ------------------
+ * replaces: waterz.agglomerate(affs, thresholds, fragments=..., scoring_function=OneMinus<MeanAffinity>)
+ * as simple_watershed drives it (post/watershed.py:333-340): region graph of the whole ROI, priority
+ * queue ordered by (score, edge id), one segmentation per (ascending) threshold.
+ *   plan       single block (block_size = roi_shape, context 0) whose stage 1 produced `frags`
+ *   thresholds host, ascending;  segs_out host array of n_thresholds device pointers (roi_shape uint64)
+ *   counters_out host[4] or NULL: pops, stale re-scores, deleted pops, merges
+ */
+int bs_waterz_segment(bs_plan *p, const void *affs, const uint64_t *frags, const float *thresholds, int n_thresholds,
+                      uint64_t *const *segs_out, uint32_t *counters_out, void *stream);
+
 /* ---- stage 3: global thresholded connected components + relabel --------------------
  * replaces: funlib.segment.graphs.impl.connected_components (post/watershed.py:182),
  * volara LUT (post/watershed.py:187-188) and volara Relabel (post/watershed.py:192-202).
