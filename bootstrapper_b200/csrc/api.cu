@@ -18,6 +18,8 @@ int relabel(const uint64_t *frags, int64_t n, const uint64_t *keys, const uint64
 int relabel_dense(Plan &P, const uint64_t *frags, int64_t n, const uint64_t *const *comps, int T, uint64_t *const *segs,
                   cudaStream_t s);
 int plan_node_ids(Plan &P, uint64_t *out, long long *n_out, cudaStream_t s);
+int cc_affs(const void *affs, int dtype, const uint8_t *mask, int Z, int Y, int X, float thr, int remove_debris, uint64_t *frags_out,
+            uint64_t *seg_out, int64_t *n_out, cudaStream_t s);
 int synth_affs(void *out, int dtype, const int32_t *shape, const int32_t *offset, uint64_t seed, cudaStream_t s);
 }  // namespace bs
 
@@ -270,6 +272,14 @@ int bs_watershed_from_affinities(const void *affs, int aff_dtype, int Z, int Y, 
     cudaStreamSynchronize((cudaStream_t)stream);
     delete p;
     return rc;
+}
+
+int bs_cc_affs(const void *affs, int aff_dtype, const uint8_t *mask, int Z, int Y, int X, float threshold, int remove_debris,
+               uint64_t *frags_out, uint64_t *seg_out, int64_t *n_out, void *stream) {
+    BS_ARG(affs && frags_out, "bs_cc_affs: null argument");
+    BS_ARG(aff_dtype == BS_DTYPE_U8 || aff_dtype == BS_DTYPE_F32, "bs_cc_affs: aff_dtype must be u8 or f32");
+    init_mempool();
+    return cc_affs(affs, aff_dtype, mask, Z, Y, X, threshold, remove_debris, frags_out, seg_out, n_out, (cudaStream_t)stream);
 }
 
 int bs_synth_affs(void *out, int aff_dtype, const int32_t *shape, const int32_t *offset, const int32_t *vol_shape,

@@ -36,7 +36,7 @@ EXPORTS = [
     "bs_last_error", "bs_launch_count", "bs_version", "bs_plan_create", "bs_plan_destroy", "bs_plan_num_blocks",
     "bs_plan_block_info", "bs_plan_set_owned", "bs_stage1_fragments", "bs_stage1_num_nodes", "bs_stage1_get_nodes",
     "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_plan_node_ids", "bs_stage2_agglomerate", "bs_stage2_num_edges",
-    "bs_stage2_get_edges", "bs_waterz_segment", "bs_connected_components", "bs_relabel", "bs_stage3_relabel", "bs_watershed_from_affinities",
+    "bs_stage2_get_edges", "bs_waterz_segment", "bs_cc_affs", "bs_connected_components", "bs_relabel", "bs_stage3_relabel", "bs_watershed_from_affinities",
     "bs_synth_affs", "bs_debug_fetch", "bs_set_debug", "bs_set_profiling", "bs_get_profile",
     "bs_release_scratch", "bs_set_flood_version", "bs_set_agglom_version", "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
 ]
@@ -296,6 +296,19 @@ def relabel(frags, lut_keys, lut_vals, out=None):
                             _dev(lut_vals, torch.int64) if lut_vals.numel() else None,
                             C.c_int64(lut_keys.numel()), _dev(out, torch.int64), _stream()))
     return out
+
+
+def cc_affs(affs, threshold, remove_debris=0, mask=None):
+    """post/connected_components.py cc_affs on one device array (C >= 3, Z, Y, X) uint8 / float32.
+    Returns (fragments, segmentation after remove_debris, number of components)."""
+    _, Z, Y, X = affs.shape
+    frags = torch.empty((Z, Y, X), dtype=torch.int64, device=affs.device)
+    seg = torch.empty_like(frags)
+    n = C.c_int64()
+    _check(lib().bs_cc_affs(_dev(affs), C.c_int(_aff_dtype(affs)), _dev(mask, torch.uint8) if mask is not None else None,
+                            Z, Y, X, C.c_float(float(threshold)), C.c_int(int(remove_debris or 0)), _dev(frags), _dev(seg),
+                            C.byref(n), _stream()))
+    return frags, seg, n.value
 
 
 def watershed_from_affinities(affs, fragments_in_xy, min_seed_distance):

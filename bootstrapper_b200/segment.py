@@ -3,7 +3,7 @@
 Same key set, defaults, override order and error behaviour as the reference's
 bootstrapper/segment.py (DEFAULTS :10-62, get_seg_config :95-135, run_segmentation :138-163);
 pinned by tests/golden/seg_config.json, which was produced by executing the reference file.
-Only the ws method runs on the CUDA path; mws / cc are outside SURVEY §8's built rows and raise.
+The ws and cc methods run on the CUDA path; mws is not built yet and raises.
 """
 import ast
 import copy
@@ -85,6 +85,9 @@ def run_segmentation(config_file, mode="ws", **kwargs):
     if mode == "ws":
         from .post.watershed import watershed_segmentation
         return watershed_segmentation(config)
-    if mode in ("mws", "cc"):
+    if mode == "cc":
+        from .post.connected_components import cc_segmentation
+        return cc_segmentation(config)
+    if mode in ("mws",):
         raise NotImplementedError(f"segmentation mode {mode!r} is not part of the CUDA hot path yet (SURVEY §8)")
     raise ValueError(f"Unknown segmentation mode: {mode}")

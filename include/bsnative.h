@@ -145,6 +145,16 @@ int bs_relabel(const uint64_t *frags, int64_t n_vox, const uint64_t *lut_keys, c
 int bs_stage3_relabel(bs_plan *p, const uint64_t *frags, int64_t n_vox, const uint64_t *const *components, int n_thresholds,
                       uint64_t *const *segs_out, void *stream);
 
+/* ---- `bs segment --cc` -----------------------------------------------------------------
+ * replaces: cc_affs + compute_connected_component_segmentation (post/connected_components.py:15-127,
+ * post/cc.py:7-74): hard = affs[:3] > threshold (float32 compare; uint8 input is /255 first), components of
+ * the "+e_d" affinity graph, ids in raster order of each component's first voxel; remove_debris > 0 additionally
+ * writes the remove_small_objects result to seg_out.
+ *   affs (>=3, Z, Y, X) u8 / f32 (channels 0..2 read); mask (Z,Y,X) u8 or NULL; frags_out, seg_out (Z,Y,X) uint64
+ *   (seg_out may be NULL); n_out (host) = number of components. */
+int bs_cc_affs(const void *affs, int aff_dtype, const uint8_t *mask, int Z, int Y, int X, float threshold, int remove_debris,
+               uint64_t *frags_out, uint64_t *seg_out, int64_t *n_out, void *stream);
+
 /* ---- post/ws.py plug point ----------------------------------------------------------
  * replaces: watershed_from_affinities(affs, max_affinity_value, fragments_in_xy,
  * return_seeds, min_seed_distance) (post/ws.py:38-112) on one in-memory array.

@@ -6,7 +6,7 @@ Writes tests/golden/*.npz / *.json.  Nothing at test time reads /root/reference.
 
 Sources executed (unmodified, loaded by path):
   bootstrapper/post/merge_tree.py   -> merge_tree.npz   (MergeTree.merge / find_merges)
-  bootstrapper/post/cc.py           -> cc_flood.npz     (compute_connected_component_segmentation)
+  bootstrapper/post/cc.py           -> cc_flood.npz, cc_affs.npz (compute_connected_component_segmentation)
   bootstrapper/post/naming.py       -> naming.json      (build_name; `import zarr` stubbed)
   bootstrapper/segment.py           -> seg_config.json  (DEFAULTS, get_seg_config)
 """
@@ -74,6 +74,34 @@ def golden_cc():
         cases[f"c{ci}_hard"] = hard
         cases[f"c{ci}_seg"] = seg
     np.savez_compressed(f"{OUT}/cc_flood.npz", **cases)
+
+
+def golden_cc_affs():
+    """cc_affs front end (post/connected_components.py:52-56,66,81) restated in numpy + the reference's cc.py."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from bootstrapper_b200.synth import synth_affs
+    cc_mod = load("ref_cc", f"{REF}/post/cc.py")
+    rng = np.random.default_rng(5)
+    cases = {}
+    specs = [("u8", (8, 48, 48), 0.5, False), ("u8", (6, 40, 56), 0.8, True), ("f32", (5, 32, 32), 0.3, True)]
+    for ci, (kind, shape, thr, with_mask) in enumerate(specs):
+        if kind == "u8":
+            affs = synth_affs(shape, seed=20 + ci, dtype=np.uint8)
+            data = affs.astype(np.float32) / 255.0
+        else:
+            affs = rng.random((3,) + shape).astype(np.float32)
+            data = affs.astype(np.float32)
+        mask = None
+        if with_mask:
+            mask = (rng.random(shape) < 0.9).astype(np.uint8)
+            data *= (mask > 0).astype(np.uint8)
+        hard = data > thr
+        seg = cc_mod.compute_connected_component_segmentation(hard)
+        cases[f"c{ci}_affs"] = affs
+        cases[f"c{ci}_thr"] = np.float64(thr)
+        cases[f"c{ci}_mask"] = mask if mask is not None else np.zeros(0, np.uint8)
+        cases[f"c{ci}_seg"] = seg
+    np.savez_compressed(f"{OUT}/cc_affs.npz", **cases)
 
 
 NAMING_CASES = [
@@ -169,6 +197,7 @@ def golden_config():
 if __name__ == "__main__":
     golden_merge_tree()
     golden_cc()
+    golden_cc_affs()
     golden_naming()
     golden_config()
     print("golden fixtures written to", OUT)

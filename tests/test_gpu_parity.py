@@ -276,3 +276,30 @@ def test_simple_watershed_cremi_crop():
     assert _same_partition(r["fragments"].cpu().numpy().view(np.uint64), ref["fragments"])
     for thr in ref["params"]["thresholds"]:
         assert _same_partition(r["segs"][thr].cpu().numpy().view(np.uint64), ref["segs"][thr]), thr
+
+
+# ---------------------------------------------------------------- cc method
+def test_cc_affs_golden_and_oracle():
+    """bs_cc_affs against outputs of the reference's own post/cc.py (golden) and, at a larger size, the oracle."""
+    import os
+    from bootstrapper_b200 import native
+    from bootstrapper_b200.synth import synth_affs
+    from oracle import cc as occ
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gdir, "cc_flood.npz"))
+    for ci in range(3):
+        affs = torch.from_numpy(g[f"c{ci}_hard"].astype(np.float32)).cuda()
+        frags, seg, n = native.cc_affs(affs, 0.5)
+        assert np.array_equal(frags.cpu().numpy(), g[f"c{ci}_seg"].astype(np.int64))
+        assert n == int(g[f"c{ci}_seg"].max())
+    g = np.load(os.path.join(gdir, "cc_affs.npz"))
+    for ci in range(3):
+        mask = torch.from_numpy(g[f"c{ci}_mask"]).cuda() if g[f"c{ci}_mask"].size else None
+        frags, seg, n = native.cc_affs(torch.from_numpy(g[f"c{ci}_affs"]).cuda(), float(g[f"c{ci}_thr"]), 0, mask)
+        assert np.array_equal(frags.cpu().numpy(), g[f"c{ci}_seg"].astype(np.int64))
+    for dtype, thr, rd in [(np.uint8, 0.5, 64), (np.float32, 0.9, 5), (np.uint8, 0.0, 0)]:
+        affs = synth_affs((12, 150, 170), seed=4, dtype=dtype)
+        rf, rs = occ.cc_affs(affs, thr, rd)
+        frags, seg, n = native.cc_affs(torch.from_numpy(affs).cuda(), thr, rd)
+        assert np.array_equal(frags.cpu().numpy(), rf.astype(np.int64))
+        assert np.array_equal(seg.cpu().numpy(), rs.astype(np.int64))

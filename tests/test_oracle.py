@@ -175,3 +175,16 @@ def test_blockwise_oracle_is_block_order_independent():
     b = waterz_pipeline_parallel(affs, workers=2, **kw)
     assert np.array_equal(a["fragments"], b["fragments"]) and a["rag"].edges == b["rag"].edges
     assert len(a["rag"].node_pos) > 20 and len(a["rag"].edges) > 20
+
+
+def test_cc_restatement_matches_reference_goldens():
+    """oracle/cc.py against outputs of the reference's own post/cc.py (tests/golden/make_golden.py)."""
+    from oracle import cc as occ
+    g = np.load(os.path.join(GOLD, "cc_flood.npz"))
+    for ci in range(3):
+        assert np.array_equal(occ.compute_connected_component_segmentation(g[f"c{ci}_hard"]), g[f"c{ci}_seg"])
+    g = np.load(os.path.join(GOLD, "cc_affs.npz"))
+    for ci in range(3):
+        mask = g[f"c{ci}_mask"] if g[f"c{ci}_mask"].size else None
+        frags, _ = occ.cc_affs(g[f"c{ci}_affs"], float(g[f"c{ci}_thr"]), 0, mask)
+        assert np.array_equal(frags, g[f"c{ci}_seg"])
