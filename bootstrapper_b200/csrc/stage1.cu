@@ -21,6 +21,8 @@
 //   k_fragstats      per-fragment affinity sum + voxel count (warp-aggregated atomics)
 //   k_crop_*         keep/drop decision, 8/26-connected relabel of the cropped write ROI
 //   k_finalize       raster-order ids (+ block_id * prod(block_size)), uint64 output, node statistics
+#include <string.h>
+
 #include <algorithm>
 
 #include "geom.h"
@@ -78,9 +80,63 @@ struct AffOps<float> {
     }
 };
 
-// ------------------------------------------------------------------ mask + row distance
+// ---- optional shifts (watershed_frags.py:118-146): the watershed sees affs_data + shift with
+//   shift = bias[c] - seed_eps * EDT(seeds == 0)      (noise_eps / sigma are not supported)
+// replayed in the dtype numpy uses: float64 for uint8 input (normalised /255 in float64, watershed_frags.py:198-200),
+// float32 for float32 input (the shift array is zeros_like(affs), in-place updates round to float32).
+struct PreRef {          // the seed_eps pre-pass tile (= read ROI of the block) a main tile looks its distances up in
+    long long base;
+    int oz, oy, ox, H, W, pad_;
+};
+struct ShiftView {
+    int has_bias, has_eps;
+    double bias[3];
+    double eps;
+    const uint32_t *D2;      // squared distance to the nearest seed, per pre-pass tile pixel
+    const PreRef *pre;       // per main tile
+};
+
+// inmask: voxel inside the volume and not masked out (else the normalised affinity is 0.0, to which the shift is added)
 template <typename T>
-__global__ void __launch_bounds__(256) k_mask_rowdist(const Tile *__restrict__ tiles, AffView A, uint8_t *__restrict__ msk,
+__device__ __forceinline__ bool boundary_shifted(const T *a, size_t n, size_t i, bool inmask, int ndim, const ShiftView &S,
+                                                 double dist);
+template <>
+__device__ __forceinline__ bool boundary_shifted<uint8_t>(const uint8_t *a, size_t n, size_t i, bool inmask, int ndim,
+                                                          const ShiftView &S, double dist) {
+    double v[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        if (c == 0 && ndim == 2) continue;
+        double x = inmask ? __ddiv_rn((double)a[(size_t)c * n + i], 255.0) : 0.0;
+        double sh = S.has_bias ? S.bias[c] : 0.0;                      // zeros += bias
+        if (S.has_eps) sh = __dsub_rn(sh, __dmul_rn(S.eps, dist));     // shift -= seed_eps * D
+        v[c] = __dadd_rn(x, sh);
+    }
+    if (ndim == 2) return __dmul_rn(0.5, __dadd_rn(v[2], v[1])) > 0.5;                // post/ws.py:64,77
+    return __ddiv_rn(__dadd_rn(__dadd_rn(v[0], v[1]), v[2]), 3.0) > 0.5;              // post/ws.py:100
+}
+template <>
+__device__ __forceinline__ bool boundary_shifted<float>(const float *a, size_t n, size_t i, bool inmask, int ndim,
+                                                        const ShiftView &S, double dist) {
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        if (c == 0 && ndim == 2) continue;
+        float x = inmask ? a[(size_t)c * n + i] : 0.0f;
+        float sh = S.has_bias ? __double2float_rn(S.bias[c]) : 0.0f;                                     // float32(0 + bias)
+        if (S.has_eps) sh = __double2float_rn(__dsub_rn((double)sh, __dmul_rn(S.eps, dist)));            // float32(shift - eps * D)
+        v[c] = __fadd_rn(x, sh);
+    }
+    if (ndim == 2) return __fmul_rn(0.5f, __fadd_rn(v[2], v[1])) > 0.5f;
+    return __fdiv_rn(__fadd_rn(__fadd_rn(v[0], v[1]), v[2]), 3.0f) > 0.5f;
+}
+
+// ------------------------------------------------------------------ mask + row distance
+// MODE 0: boundary mask from the affinities; 1: from the shifted affinities; 2: "not a seed" (pred[p] == NONE32),
+// the input of the seed-distance transform EDT(seeds == 0).
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) k_mask_rowdist(const Tile *__restrict__ tiles, AffView A, ShiftView S,
+                                                      const uint32_t *__restrict__ pred, uint8_t *__restrict__ msk,
                                                       uint16_t *__restrict__ g, uint32_t *__restrict__ tileflags) {
     __shared__ uint32_t bits[8][MAXW / 32];
     const Tile t = tiles[blockIdx.y];
@@ -98,12 +154,30 @@ __global__ void __launch_bounds__(256) k_mask_rowdist(const Tile *__restrict__ t
         for (int c = 0; c < nw; c++) {
             int x = c * 32 + lane;
             bool m = false;
-            if (x < W && rowin) {
-                int gx = t.gx + x;
-                if (gx >= 0 && gx < A.X) {
-                    size_t i = rowoff + gx;
-                    if (!A.mask || A.mask[i] > 0) m = AffOps<T>::boundary(a, nvol, i, t.ndim);
+            if (MODE == 0) {
+                if (x < W && rowin) {
+                    int gx = t.gx + x;
+                    if (gx >= 0 && gx < A.X) {
+                        size_t i = rowoff + gx;
+                        if (!A.mask || A.mask[i] > 0) m = AffOps<T>::boundary(a, nvol, i, t.ndim);
+                    }
                 }
+            } else if (MODE == 1) {
+                if (x < W) {
+                    int gx = t.gx + x;
+                    bool inside = rowin && gx >= 0 && gx < A.X;
+                    size_t i = inside ? rowoff + gx : 0;
+                    bool inmask = inside && (!A.mask || A.mask[i] > 0);
+                    double dist = 0.0;
+                    if (S.has_eps) {
+                        const PreRef pr = S.pre[blockIdx.y];
+                        long long q = pr.base + ((long long)(gz - pr.oz) * pr.H + (gy - pr.oy)) * pr.W + (gx - pr.ox);
+                        dist = __dsqrt_rn((double)S.D2[q]);
+                    }
+                    m = boundary_shifted<T>(a, nvol, i, inmask, t.ndim, S, dist);
+                }
+            } else {
+                if (x < W) m = pred[pbase + x] == NONE32;
             }
             unsigned b = __ballot_sync(FULL, m);
             int rem = W - c * 32;
@@ -111,7 +185,7 @@ __global__ void __launch_bounds__(256) k_mask_rowdist(const Tile *__restrict__ t
             unsigned bg = ~b & valid;
             if (lane == 0) bits[warp][c] = bg;
             anybg |= (bg != 0);
-            if (x < W) msk[pbase + x] = m ? 1 : 0;
+            if (MODE != 2 && x < W) msk[pbase + x] = m ? 1 : 0;
         }
         __syncwarp();
         for (int c = 0; c < nw; c++) {
@@ -149,7 +223,7 @@ __global__ void __launch_bounds__(256) k_mask_rowdist(const Tile *__restrict__ t
         }
         __syncwarp();
     }
-    if (anybg && lane == 0) atomicOr(&tileflags[blockIdx.y], 1u);
+    if (MODE != 2 && anybg && lane == 0) atomicOr(&tileflags[blockIdx.y], 1u);
 }
 
 // ------------------------------------------------------------------ exact squared EDT, y and z passes
@@ -1235,6 +1309,141 @@ __global__ void k_nodes(const BlkDev *__restrict__ blks, int nblk, const uint32_
 }
 
 // ------------------------------------------------------------------ host driver
+struct TileDims {
+    int ntiles, maxD, maxH, maxW;
+    long long maxpix;
+};
+
+static dim3 pixel_grid(const TileDims &td) {
+    return dim3((unsigned)std::min<long long>(std::max<long long>((td.maxpix + 1023) / 1024, 1), 2048), td.ntiles);
+}
+
+// exact squared EDT of the mask whose row distances are in g -> out (tmp: in-plane result of 3-D tiles)
+static int launch_edt(const Tile *dt, const TileDims &td, bool three_d, const uint16_t *g, uint32_t *tmp, uint32_t *out,
+                      uint32_t *tilemax, cudaStream_t s) {
+    const dim3 grid = pixel_grid(td);
+    const size_t strip_smem = (size_t)td.maxH * CS_W * 2;
+    const bool use_strip = strip_smem <= 96 * 1024;
+    const dim3 grid_strip((unsigned)std::min<long long>((long long)td.maxD * ((td.maxW + CS_W - 1) / CS_W), 8192), td.ntiles);
+    if (use_strip) {
+        static bool attr_strip = false;
+        if (!attr_strip) {
+            BS_CUDA(cudaFuncSetAttribute(k_coldist_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_strip = true;
+        }
+    }
+    uint32_t *plane_out = three_d ? tmp : out;
+    if (use_strip)
+        BS_LAUNCH(k_coldist_strip, grid_strip, 256, strip_smem, s, dt, g, plane_out, tilemax);
+    else
+        BS_LAUNCH(k_coldist, grid, 256, 0, s, dt, g, plane_out, tilemax);
+    if (three_d) BS_LAUNCH(k_zdist, grid, 256, 0, s, dt, tmp, out, tilemax);
+    return BS_OK;
+}
+
+// seeds = (maximum_filter(d2, msd) == d2) & msk: parent array (own index / NONE32) + seed bitmap
+static int launch_seeds(const Tile *dt, const TileDims &td, bool three_d, int msd, const uint32_t *d2, const uint8_t *msk,
+                        uint32_t *tmpA, uint32_t *tmpB, uint32_t *par, uint32_t *sbits, cudaStream_t s) {
+    const dim3 grid = pixel_grid(td);
+    const size_t mf_smem = ((size_t)(MF_TH + msd - 1) * (MF_TW + msd - 1) + (size_t)(MF_TH + msd - 1) * MF_TW) * 4;
+    const bool use_mf = mf_smem <= 96 * 1024;
+    const dim3 grid_mf((unsigned)std::min<long long>(
+                           (long long)td.maxD * ((td.maxW + MF_TW - 1) / MF_TW) * ((td.maxH + MF_TH - 1) / MF_TH), 8192),
+                       td.ntiles);
+    if (use_mf) {
+        static bool attr_mf = false;
+        if (!attr_mf) {
+            BS_CUDA(cudaFuncSetAttribute(k_maxfilt_xy, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_mf = true;
+        }
+    }
+    if (!three_d) {
+        if (use_mf) {
+            BS_LAUNCH(k_maxfilt_xy, grid_mf, 256, mf_smem, s, dt, d2, msd, 1, msk, par, sbits);
+        } else {
+            BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, d2, tmpA, 2, msd, 0, nullptr, nullptr, nullptr, nullptr);
+            BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, tmpA, nullptr, 1, msd, 1, d2, msk, par, sbits);
+        }
+    } else {
+        if (use_mf) {
+            BS_LAUNCH(k_maxfilt_xy, grid_mf, 256, mf_smem, s, dt, d2, msd, 0, nullptr, tmpB, nullptr);
+        } else {
+            BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, d2, tmpA, 2, msd, 0, nullptr, nullptr, nullptr, nullptr);
+            BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, tmpA, tmpB, 1, msd, 0, nullptr, nullptr, nullptr, nullptr);
+        }
+        BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, tmpB, nullptr, 0, msd, 1, d2, msk, par, sbits);
+    }
+    return BS_OK;
+}
+
+static int rowdist_grid_rows(const std::vector<Tile> &tiles) {
+    int rows = 0;
+    for (auto &t : tiles) rows = std::max(rows, t.D * t.H);
+    return std::min(std::max((rows + 7) / 8, 1), 4096);
+}
+
+// seed_eps pre-pass (watershed_frags.py:131-139) on the 3-D read ROI of every block of the batch:
+//   boundary_mask = mean(affs) > 0.5; seeds = (maximum_filter(EDT(mask), msd) == EDT(mask)) & mask;
+//   D = EDT(seeds == 0)            -> D2 (exact squared distances; the sqrt is taken where the shift is applied)
+template <typename T>
+static int seed_distance_prepass(Plan &P, const std::vector<int> &bidx, AffView A, DevBuf &D2, std::vector<PreRef> &refs,
+                                 cudaStream_t s) {
+    const bs_ws_config &cfg = P.cfg;
+    std::vector<Tile> pt;
+    long long Ppre = 0, maxpix = 0;
+    refs.clear();
+    for (size_t bi = 0; bi < bidx.size(); bi++) {
+        const Blk &b = P.blocks[bidx[bi]];
+        Tile t;
+        t.gz = b.ro[0], t.gy = b.ro[1], t.gx = b.ro[2];
+        t.D = b.rs[0], t.H = b.rs[1], t.W = b.rs[2];
+        t.wz = t.wy = t.wx = 0;
+        t.wD = t.D, t.wH = t.H, t.wW = t.W;
+        t.block = (int)bi;
+        t.ndim = 3;
+        t.base = Ppre;
+        t.wbase = 0;
+        PreRef r;
+        r.base = Ppre, r.oz = t.gz, r.oy = t.gy, r.ox = t.gx, r.H = t.H, r.W = t.W, r.pad_ = 0;
+        refs.push_back(r);
+        long long np = (long long)t.D * t.H * t.W;
+        Ppre += np;
+        maxpix = std::max(maxpix, np);
+        pt.push_back(t);
+    }
+    BS_ARG(Ppre < (1LL << 31), "stage1: seed_eps pre-pass too large for 32-bit tile indices (lower max_batch_voxels)");
+    for (auto &t : pt) BS_ARG(t.W <= MAXW, "stage1: tile wider than 4096 voxels is not supported");
+    const int np_tiles = (int)pt.size();
+    TileDims td;
+    td.ntiles = np_tiles, td.maxpix = maxpix, td.maxD = td.maxH = td.maxW = 0;
+    for (auto &t : pt) td.maxH = std::max(td.maxH, t.H), td.maxW = std::max(td.maxW, t.W), td.maxD = std::max(td.maxD, t.D);
+    DevBuf d_pt, msk, g, d2, tmpA, tmpB, par, sb, flags, tmax;
+    BS_TRY(d_pt.alloc(sizeof(Tile) * np_tiles, s));
+    BS_CUDA(cudaMemcpyAsync(d_pt.p, pt.data(), sizeof(Tile) * np_tiles, cudaMemcpyHostToDevice, s));
+    BS_CUDA(cudaStreamSynchronize(s));   // pt is a host-staged copy
+    const Tile *dt = d_pt.as<Tile>();
+    BS_TRY(msk.alloc(Ppre, s));
+    BS_TRY(g.alloc(Ppre * 2, s));
+    BS_TRY(d2.alloc(Ppre * 4, s));
+    BS_TRY(tmpA.alloc(Ppre * 4, s));
+    BS_TRY(tmpB.alloc(Ppre * 4, s));
+    BS_TRY(par.alloc(Ppre * 4, s));
+    BS_TRY(sb.alloc_zero(4 * ((size_t)Ppre / 32 + 2), s));
+    BS_TRY(flags.alloc_zero(4 * (np_tiles + 1), s));
+    BS_TRY(tmax.alloc_zero(4 * (np_tiles + 1), s));
+    BS_TRY(D2.alloc(Ppre * 4, s));
+    ShiftView none;
+    memset(&none, 0, sizeof(none));
+    const dim3 gr((unsigned)rowdist_grid_rows(pt), np_tiles);
+    BS_LAUNCH((k_mask_rowdist<T, 0>), gr, 256, 0, s, dt, A, none, nullptr, msk.as<uint8_t>(), g.as<uint16_t>(), flags.as<uint32_t>());
+    BS_TRY(launch_edt(dt, td, true, g.as<uint16_t>(), tmpA.as<uint32_t>(), d2.as<uint32_t>(), tmax.as<uint32_t>(), s));
+    BS_TRY(launch_seeds(dt, td, true, cfg.min_seed_distance, d2.as<uint32_t>(), msk.as<uint8_t>(), tmpA.as<uint32_t>(),
+                        tmpB.as<uint32_t>(), par.as<uint32_t>(), sb.as<uint32_t>(), s));
+    BS_LAUNCH((k_mask_rowdist<T, 2>), gr, 256, 0, s, dt, A, none, par.as<uint32_t>(), nullptr, g.as<uint16_t>(), nullptr);
+    BS_TRY(launch_edt(dt, td, true, g.as<uint16_t>(), tmpA.as<uint32_t>(), D2.as<uint32_t>(), tmax.as<uint32_t>(), s));
+    return BS_OK;
+}
+
 static int keep_debug(Plan &P, const char *name, DevBuf &buf, int elem, long long count) {
     auto it = P.dbg.find(name);
     if (it != P.dbg.end()) {
@@ -1337,74 +1546,43 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     // ---- mask, exact squared EDT
     g_prof.mark("s1.mask_rowdist", s);
     {
-        int rows = 0;
-        for (auto &t : tiles) rows = std::max(rows, t.D * t.H);
-        dim3 gr((unsigned)std::min(std::max((rows + 7) / 8, 1), 4096), ntiles);
-        BS_LAUNCH((k_mask_rowdist<T>), gr, 256, 0, s, dt, A, msk.as<uint8_t>(), g.as<uint16_t>(), tileflags.as<uint32_t>());
+        dim3 gr((unsigned)rowdist_grid_rows(tiles), ntiles);
+        ShiftView S;
+        memset(&S, 0, sizeof(S));
+        S.has_bias = cfg.has_bias, S.has_eps = cfg.has_seed_eps;
+        for (int d = 0; d < 3; d++) S.bias[d] = cfg.bias[d];
+        S.eps = cfg.seed_eps;
+        DevBuf D2, d_pre;
+        if (cfg.has_seed_eps) {
+            g_prof.mark("s1.seed_eps", s);
+            std::vector<PreRef> brefs, trefs(ntiles);
+            BS_TRY(seed_distance_prepass<T>(P, bidx, A, D2, brefs, s));
+            for (int i = 0; i < ntiles; i++) trefs[i] = brefs[tiles[i].block];
+            BS_TRY(d_pre.alloc(sizeof(PreRef) * ntiles, s));
+            BS_CUDA(cudaMemcpyAsync(d_pre.p, trefs.data(), sizeof(PreRef) * ntiles, cudaMemcpyHostToDevice, s));
+            BS_CUDA(cudaStreamSynchronize(s));   // trefs is a host-staged copy
+            S.D2 = D2.as<uint32_t>();
+            S.pre = d_pre.as<PreRef>();
+            g_prof.mark("s1.mask_rowdist", s);
+        }
+        if (cfg.has_bias || cfg.has_seed_eps)
+            BS_LAUNCH((k_mask_rowdist<T, 1>), gr, 256, 0, s, dt, A, S, nullptr, msk.as<uint8_t>(), g.as<uint16_t>(),
+                      tileflags.as<uint32_t>());
+        else
+            BS_LAUNCH((k_mask_rowdist<T, 0>), gr, 256, 0, s, dt, A, S, nullptr, msk.as<uint8_t>(), g.as<uint16_t>(),
+                      tileflags.as<uint32_t>());
     }
     g_prof.mark("s1.edt", s);
-    int maxH = 0, maxW = 0, maxD = 0;
-    for (auto &t : tiles) maxH = std::max(maxH, t.H), maxW = std::max(maxW, t.W), maxD = std::max(maxD, t.D);
-    const size_t strip_smem = (size_t)maxH * CS_W * 2;
-    const bool use_strip = strip_smem <= 96 * 1024;
-    const dim3 grid_strip((unsigned)std::min<long long>((long long)maxD * ((maxW + CS_W - 1) / CS_W), 8192), ntiles);
-    if (use_strip) {
-        static bool attr_strip = false;
-        if (!attr_strip) {
-            BS_CUDA(cudaFuncSetAttribute(k_coldist_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            attr_strip = true;
-        }
-    }
-    if (xy) {
-        if (use_strip)
-            BS_LAUNCH(k_coldist_strip, grid_strip, 256, strip_smem, s, dt, g.as<uint16_t>(), d2.as<uint32_t>(), tilemax.as<uint32_t>());
-        else
-            BS_LAUNCH(k_coldist, grid, 256, 0, s, dt, g.as<uint16_t>(), d2.as<uint32_t>(), tilemax.as<uint32_t>());
-    } else {
-        if (use_strip)
-            BS_LAUNCH(k_coldist_strip, grid_strip, 256, strip_smem, s, dt, g.as<uint16_t>(), tmpA.as<uint32_t>(), tilemax.as<uint32_t>());
-        else
-            BS_LAUNCH(k_coldist, grid, 256, 0, s, dt, g.as<uint16_t>(), tmpA.as<uint32_t>(), tilemax.as<uint32_t>());
-        BS_LAUNCH(k_zdist, grid, 256, 0, s, dt, tmpA.as<uint32_t>(), d2.as<uint32_t>(), tilemax.as<uint32_t>());
-    }
-    // ---- maximum filter -> seeds (parent array in lv, flags in seedflag)
+    TileDims td;
+    td.ntiles = ntiles, td.maxpix = maxpix, td.maxD = td.maxH = td.maxW = 0;
+    for (auto &t : tiles) td.maxH = std::max(td.maxH, t.H), td.maxW = std::max(td.maxW, t.W), td.maxD = std::max(td.maxD, t.D);
+    BS_TRY(launch_edt(dt, td, !xy, g.as<uint16_t>(), tmpA.as<uint32_t>(), d2.as<uint32_t>(), tilemax.as<uint32_t>(), s));
+    // ---- maximum filter -> seeds (parent array in lv, seed bitmap in sbits)
     g_prof.mark("s1.maxfilt", s);
-    const int msd = cfg.min_seed_distance;
-    const size_t mf_smem = ((size_t)(MF_TH + msd - 1) * (MF_TW + msd - 1) + (size_t)(MF_TH + msd - 1) * MF_TW) * 4;
-    const bool use_mf = mf_smem <= 96 * 1024;
-    const dim3 grid_mf((unsigned)std::min<long long>((long long)maxD * ((maxW + MF_TW - 1) / MF_TW) * ((maxH + MF_TH - 1) / MF_TH), 8192),
-                       ntiles);
-    if (use_mf) {
-        static bool attr_mf = false;
-        if (!attr_mf) {
-            BS_CUDA(cudaFuncSetAttribute(k_maxfilt_xy, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            attr_mf = true;
-        }
-    }
-    if (xy) {
-        if (use_mf) {
-            BS_LAUNCH(k_maxfilt_xy, grid_mf, 256, mf_smem, s, dt, d2.as<uint32_t>(), msd, 1, msk.as<uint8_t>(), lv.as<uint32_t>(),
-                      sbits.as<uint32_t>());
-        } else {
-            BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, d2.as<uint32_t>(), tmpA.as<uint32_t>(), 2, msd, 0, nullptr, nullptr, nullptr,
-                      nullptr);
-            BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, tmpA.as<uint32_t>(), nullptr, 1, msd, 1, d2.as<uint32_t>(),
-                      msk.as<uint8_t>(), lv.as<uint32_t>(), sbits.as<uint32_t>());
-        }
-    } else {
-        BS_TRY(tmpB.alloc(P_pix * 4, s));
-        if (use_mf) {
-            BS_LAUNCH(k_maxfilt_xy, grid_mf, 256, mf_smem, s, dt, d2.as<uint32_t>(), msd, 0, nullptr, tmpB.as<uint32_t>(), nullptr);
-        } else {
-            BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, d2.as<uint32_t>(), tmpA.as<uint32_t>(), 2, msd, 0, nullptr, nullptr, nullptr,
-                      nullptr);
-            BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, tmpA.as<uint32_t>(), tmpB.as<uint32_t>(), 1, msd, 0, nullptr, nullptr, nullptr,
-                      nullptr);
-        }
-        BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, tmpB.as<uint32_t>(), nullptr, 0, msd, 1, d2.as<uint32_t>(),
-                  msk.as<uint8_t>(), lv.as<uint32_t>(), sbits.as<uint32_t>());
-        tmpB.release();
-    }
+    if (!xy) BS_TRY(tmpB.alloc(P_pix * 4, s));
+    BS_TRY(launch_seeds(dt, td, !xy, cfg.min_seed_distance, d2.as<uint32_t>(), msk.as<uint8_t>(), tmpA.as<uint32_t>(),
+                        tmpB.as<uint32_t>(), lv.as<uint32_t>(), sbits.as<uint32_t>(), s));
+    tmpB.release();
     g_prof.mark("s1.seed_cc", s);
     BS_LAUNCH(k_seed_union, grid, 256, 0, s, dt, lv.as<uint32_t>());
 

@@ -29,6 +29,7 @@ class WsConfig(C.Structure):
         ("min_seed_distance", C.c_int32), ("remove_debris", C.c_int32), ("queue_bins", C.c_int32),
         ("keep_cheaper", C.c_int32), ("crop_relabel", C.c_int32), ("block_begin", C.c_int32),
         ("block_end", C.c_int32), ("win_z0", C.c_int32), ("win_z", C.c_int32), ("filter_fragments", C.c_double), ("max_batch_voxels", C.c_int64),
+        ("has_bias", C.c_int32), ("has_seed_eps", C.c_int32), ("bias", C.c_double * 3), ("seed_eps", C.c_double),
     ]
 
 
@@ -124,7 +125,8 @@ class Plan:
 
     def __init__(self, vol_shape, block_size, context, aff_dtype, roi_offset=None, roi_shape=None, n_channels=3,
                  fragments_in_xy=True, min_seed_distance=10, filter_fragments=0.1, remove_debris=64,
-                 queue_bins=256, keep_cheaper=True, block_begin=-1, block_end=-1, max_batch_voxels=0, win_z0=0, win_z=0):
+                 queue_bins=256, keep_cheaper=True, block_begin=-1, block_end=-1, max_batch_voxels=0, win_z0=0, win_z=0,
+                 bias=None, seed_eps=None):
         cfg = WsConfig()
         roi_offset = roi_offset if roi_offset is not None else (0, 0, 0)
         roi_shape = roi_shape if roi_shape is not None else vol_shape
@@ -148,6 +150,15 @@ class Plan:
         cfg.win_z = int(win_z)
         cfg.filter_fragments = float(filter_fragments or 0.0)
         cfg.max_batch_voxels = int(max_batch_voxels)
+        cfg.has_bias = 0 if bias is None else 1
+        if bias is not None:   # watershed_frags.py:123-129: a scalar bias applies to every channel
+            b = list(bias) if isinstance(bias, (list, tuple)) else [bias] * 3
+            if len(b) != 3:
+                raise BsError("bias must be a scalar or have one entry per affinity channel (3)")
+            for d in range(3):
+                cfg.bias[d] = float(b[d])
+        cfg.has_seed_eps = 0 if seed_eps is None else 1
+        cfg.seed_eps = float(seed_eps or 0.0)
         self.cfg = cfg
         self.roi_shape = tuple(int(v) for v in roi_shape)
         if win_z > 0:

@@ -15,7 +15,7 @@ WS_DEFAULTS = dict(  # reference segment.py:11-23
     filter_fragments=0.1, remove_debris=64, thresholds=[0.2, 0.35, 0.5], merge_function="mean",
     sigma=None, noise_eps=None, bias=None)
 
-UNSUPPORTED = ("seed_eps", "sigma", "noise_eps", "bias")
+UNSUPPORTED = ("sigma", "noise_eps")   # sigma: scipy gaussian_filter replay; noise_eps: unseeded RNG in the reference
 
 
 def resolve_ws_params(params):
@@ -87,7 +87,7 @@ def make_plan(affs, params, block_size, context=None, roi=None, **kw):
     return native.Plan(vol_shape, block_size, context, native._aff_dtype(affs), roi_offset=roi_offset,
                        roi_shape=roi_shape, n_channels=affs.shape[0], fragments_in_xy=p["fragments_in_xy"],
                        min_seed_distance=p["min_seed_distance"], filter_fragments=p["filter_fragments"],
-                       remove_debris=p["remove_debris"], **kw), p
+                       remove_debris=p["remove_debris"], bias=p["bias"], seed_eps=p["seed_eps"], **kw), p
 
 
 def segment_blockwise(affs, params=None, block_size=None, context=None, roi=None, mask=None, plan=None,

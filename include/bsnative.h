@@ -52,6 +52,11 @@ typedef struct bs_ws_config {
                                     the global planes [win_z0, win_z0 + win_z); roi must span all of z */
     double filter_fragments;   /* ws_params.filter_fragments (0 = off)                       */
     int64_t max_batch_voxels;  /* scratch bound for stage 1 (0 = default)                    */
+    /* optional shifts of the affinities the watershed sees (watershed_frags.py:118-139):       */
+    int32_t has_bias;          /* ws_params.bias given                                        */
+    int32_t has_seed_eps;      /* ws_params.seed_eps given                                    */
+    double bias[3];            /* per channel (a scalar bias is replicated by the caller)    */
+    double seed_eps;           /* shift -= seed_eps * EDT(seeds == 0)                        */
 } bs_ws_config;
 
 typedef struct bs_plan bs_plan;

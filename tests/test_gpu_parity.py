@@ -61,6 +61,12 @@ CASES = [
     ((12, 120, 120), (6, 60, 60), (1, 8, 8), {"min_seed_distance": 5, "thresholds": [0.1, 0.9]}, np.uint8),
     ((12, 120, 120), (6, 60, 60), (1, 8, 8), {}, np.float32),
     ((12, 100, 100), (6, 50, 50), (1, 6, 6), {"fragments_in_xy": False}, np.float32),
+    # optional shifts (watershed_frags.py:118-139): bias, seed_eps (BASELINE config 4 uses 3-D + seed_eps = 0.01)
+    ((12, 120, 120), (6, 60, 60), (1, 8, 8), {"bias": [-0.05, -0.1, -0.1]}, np.uint8),
+    ((12, 120, 120), (6, 60, 60), (1, 8, 8), {"bias": 0.08, "fragments_in_xy": False}, np.float32),
+    ((16, 96, 96), (8, 48, 48), (2, 6, 6), {"fragments_in_xy": False, "seed_eps": 0.01}, np.uint8),
+    ((12, 120, 120), (6, 60, 60), (1, 8, 8), {"seed_eps": 0.02}, np.uint8),
+    ((12, 100, 100), (6, 50, 50), (2, 6, 6), {"seed_eps": 0.01, "bias": [-0.02, -0.03, -0.03], "fragments_in_xy": False}, np.float32),
 ]
 
 
