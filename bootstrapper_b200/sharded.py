@@ -126,6 +126,7 @@ class ShardedSegmenter:
         self.own_shape = (g["z1"] - g["z0"],) + self.vol_shape[1:]
         self.nvox_block = int(np.prod(self.block_size))
         self.plan = None
+        self._copy_stream = None
         self.last_profile = {}
 
     def _plan(self, dtype_code):
@@ -146,7 +147,7 @@ class ShardedSegmenter:
         g = self.geo
         return native.synth_affs(self.win_shape, seed=seed, dtype=dtype, offset=(g["w0"], 0, 0), device=self.device)
 
-    def run(self, affs_win, out=None):
+    def run(self, affs_win, out=None, frag_sink=None):
         """affs_win: (C, w1-w0, Y, X) on this rank's device.  Returns dict with the fragment window, the
         segmentations of the own planes per threshold and the global graph."""
         plan = self._plan(native._aff_dtype(affs_win))
@@ -158,6 +159,15 @@ class ShardedSegmenter:
         frags = alloc(self.win_shape, dtype=torch.int64, device=affs_win.device)
         plan.fragments(affs_win, frags_out=frags)
         prof.update(native.get_profile())
+        if frag_sink is not None:
+            # the own planes are final after stage 1: their device->host copy overlaps stages 2 and 3
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=affs_win.device)
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(ev)
+                frag_sink.copy_(frags[g["z0"] - g["w0"]:g["z1"] - g["w0"]], non_blocking=True)
         counts = allgather_counts(plan.block_counts(), self.world, affs_win.device, self.group)
         if self.world > 1:
             plan.set_block_counts(counts)
@@ -187,9 +197,9 @@ class ShardedSegmenter:
     def run_host(self, host_affs, host_out):
         """end-to-end with HOST buffers: pinned affinities in, fragments + segmentations out (pinned)."""
         affs = host_affs.to(self.device, non_blocking=True)
-        r = self.run(affs)
-        host_out[0].copy_(r["own_fragments"], non_blocking=True)
+        r = self.run(affs, frag_sink=host_out[0])
         for i, thr in enumerate(self.p["thresholds"]):
             host_out[1 + i].copy_(r["segs"][thr], non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        self._copy_stream.synchronize()
         return r

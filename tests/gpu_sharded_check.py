@@ -22,7 +22,8 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     ok_all = True
     for shape, block, ctx, params in [((36, 120, 120), (6, 60, 60), (2, 8, 8), {}),
-                                      ((30, 100, 100), (8, 50, 50), (1, 6, 6), {"fragments_in_xy": False})]:
+                                      ((30, 100, 100), (8, 50, 50), (1, 6, 6), {"fragments_in_xy": False}),
+                                      ((32, 96, 96), (8, 48, 48), (2, 6, 6), {"fragments_in_xy": False, "seed_eps": 0.01})]:
         from oracle.blockwise import waterz_pipeline
         affs = synth_affs(shape, seed=2)
         ref = waterz_pipeline(affs, params, block_size=block, context=ctx, seed_tie="index", stats_mode="canonical")
