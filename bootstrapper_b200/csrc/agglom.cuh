@@ -7,31 +7,20 @@ namespace bs {
 
 struct AggArrays {
     // edges (global index = ebase[b] + local); eu / ev are block-compact node numbers
-    uint32_t *eu, *ev, *ecnt, *etime;
-    unsigned long long *esum;
-    float *escore;
-    uint8_t *edead;
-    // nodes (global index = vbase + compact number)
-    uint32_t *ufp, *stamp, *ahead, *atail, *tnode;
-    // adjacency chunks
-    uint32_t *centries, *cnext;
-    // pair hash (per block range hbase/hcap)
-    unsigned long long *pkeys;
-    uint32_t *pvals;
-    // queue chunk pool
-    uint32_t *qentries, *qnext;
-    // merge tree (per block base 2*vbase) and history (base vbase)
+    const uint32_t *eu, *ev, *ecnt;
+    const unsigned long long *esum;
+    // merge tree (per block base 2 * vbase) and merge history (base vbase), in block-compact numbering
     uint32_t *tparent, *tlevel;
     float *tscore;
     uint32_t *ha, *hb;
     float *hs;
     uint32_t *nmerges;
-    uint32_t *counters;   // per block: pops, stale, dead, iterations, chunk steps, append rounds
+    uint32_t *counters;   // per block: pops, stale, dead, iterations, list-walk batches, append rounds
     uint32_t *error;
 };
 
 struct AggBlk {
-    uint32_t ebase, E, vbase, nv, hbase, hcap, qbase, qcap;
+    uint32_t ebase, E, vbase, nv;   // edge range, compact node range
 };
 
 template <bool U8>
@@ -54,6 +43,9 @@ __device__ __forceinline__ int score_bin(float score, int nbins) {
 // agglom_smem.cu: BinQueue<256> agglomeration with the whole block state in shared memory.
 // `list` (device) = indices into blks of the blocks to process; u8 selects the affinity sum scaling.
 size_t agglom_smem_bytes(uint32_t Ecap, uint32_t Ncap, bool sum64);
+size_t agglom_work_bytes(uint32_t Ecap, uint32_t Ncap, bool sum64, int idx);
+int agglom_global_launch(const AggBlk *blks, const int *list, int nlist, const AggArrays &A, float threshold, int keep_cheaper,
+                         bool u8, unsigned char *work, const unsigned long long *woff, cudaStream_t s);
 int agglom_smem_launch(const AggBlk *blks, const int *list, int nlist, const AggArrays &A, float threshold, int keep_cheaper,
                        bool u8, bool sum64, uint32_t Ecap, uint32_t Ncap, cudaStream_t s);
 

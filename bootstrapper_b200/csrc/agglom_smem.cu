@@ -33,62 +33,70 @@ namespace bs {
     } while (0)
 #endif
 
-static constexpr uint32_t N16 = 0xFFFFu;
 static constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 static constexpr unsigned FULL = 0xFFFFFFFFu;
 static constexpr int QCH = 8;        // entries per queue chunk = largest batch of pops per step
 static constexpr int NBINS = 256;
-static constexpr uint32_t DEADBIT = 0x8000u;
 
 __host__ __device__ static inline uint32_t smem_qc(uint32_t Ecap) { return Ecap / QCH + 2 * NBINS + 32; }
 
-size_t agglom_smem_bytes(uint32_t Ecap, uint32_t Ncap, bool sum64) {
+// bytes of one block's working set; idx = bytes per node / edge index (2 in shared memory, 4 in global memory)
+size_t agglom_work_bytes(uint32_t Ecap, uint32_t Ncap, bool sum64, int idx) {
     size_t b = 0;
     b += (size_t)(sum64 ? 8 : 4) * Ecap;   // esum
     b += 4 * (size_t)Ecap * 2;             // escore, ecnt
     b += 32;                               // occupancy bitmap
-    b += 2 * (size_t)Ecap * 5;             // eu, ev, etd, anext[2E]
+    b += (size_t)idx * Ecap * 5;           // eu, ev, etd, anext[2E]
     const size_t QC = smem_qc(Ecap);
-    b += 2 * QC * QCH + 2 * QC;            // queue chunks + chunk links
-    b += 2 * (size_t)Ncap * 7;             // ufp, stamp, ahead, tnode, clevel, mark, markgen
-    b += 2 * (size_t)NBINS * 4;            // bin head chunk / tail chunk / head offset / tail fill
-    return (b + 15) & ~(size_t)15;
+    b += (size_t)idx * (QC * QCH + QC);    // queue chunks + chunk links
+    b += (size_t)idx * Ncap * 7;           // ufp, stamp, ahead, tnode, clevel, mark, markgen
+    b += (size_t)idx * NBINS * 4;          // bin head chunk / tail chunk / head offset / tail fill
+    return (b + 255) & ~(size_t)255;
 }
+size_t agglom_smem_bytes(uint32_t Ecap, uint32_t Ncap, bool sum64) { return agglom_work_bytes(Ecap, Ncap, sum64, 2); }
 
-__device__ __forceinline__ uint32_t find16(uint16_t *ufp, uint32_t x) {
+template <typename IdxT>
+__device__ __forceinline__ uint32_t find16(IdxT *ufp, uint32_t x) {
     // path halving; concurrent lanes only ever write ancestors
     for (;;) {
         uint32_t p = ufp[x];
         if (p == x) return x;
         uint32_t gp = ufp[p];
         if (gp == p) return p;
-        ufp[x] = (uint16_t)gp;
+        ufp[x] = (IdxT)gp;
         x = gp;
     }
 }
 
-template <bool U8, typename SumT>
-__global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restrict__ blks, const int *__restrict__ list,
-                                                         AggArrays A, float threshold, int keep_cheaper, uint32_t Ecap,
-                                                         uint32_t Ncap) {
+// IdxT = uint16_t with the working set in shared memory (SMEM), uint32_t with it in a global-memory slab
+// (blocks too large for shared memory; same algorithm, L1 / L2 latencies instead of shared-memory ones).
+template <bool U8, typename SumT, typename IdxT, bool SMEM>
+__global__ void __launch_bounds__(32) k_agglomerate_lists(const AggBlk *__restrict__ blks, const int *__restrict__ list,
+                                                          AggArrays A, float threshold, int keep_cheaper, uint32_t Ecap_,
+                                                          uint32_t Ncap_, unsigned char *__restrict__ gwork,
+                                                          const unsigned long long *__restrict__ gwoff) {
     extern __shared__ __align__(16) unsigned char smraw[];
+    constexpr uint32_t N16 = (uint32_t)(IdxT)~(IdxT)0;                 // "none" in the index type
+    constexpr uint32_t DEADBIT = 1u << (8 * sizeof(IdxT) - 1);        // etd = time | dead flag
     const int bi = list[blockIdx.x];
     const AggBlk B = blks[bi];
     const int lane = threadIdx.x;
-    const uint32_t QC = smem_qc(Ecap);
     const uint32_t E = B.E, nc = B.nv;
+    const uint32_t Ecap = SMEM ? Ecap_ : ((max(E, 8u) + 7u) & ~7u), Ncap = SMEM ? Ncap_ : ((max(nc, 8u) + 7u) & ~7u);
+    const uint32_t QC = smem_qc(Ecap);
+    unsigned char *work = SMEM ? smraw : gwork + gwoff[blockIdx.x];
 
-    SumT *esum = (SumT *)smraw;
+    SumT *esum = (SumT *)work;
     float *escore = (float *)(esum + Ecap);
     uint32_t *ecnt = (uint32_t *)(escore + Ecap);
     uint32_t *occ = ecnt + Ecap;
-    uint16_t *eu = (uint16_t *)(occ + 8);
-    uint16_t *ev = eu + Ecap, *etd = ev + Ecap, *anext = etd + Ecap;
-    uint16_t *qent = anext + 2 * Ecap;
-    uint16_t *qcnext = qent + QC * QCH;
-    uint16_t *ufp = qcnext + QC, *stamp = ufp + Ncap, *ahead = stamp + Ncap, *tnode = ahead + Ncap, *clevel = tnode + Ncap,
-             *mark = clevel + Ncap, *markgen = mark + Ncap;
-    uint16_t *bhc = markgen + Ncap, *btc = bhc + NBINS, *bho = btc + NBINS, *btf = bho + NBINS;
+    IdxT *eu = (IdxT *)(occ + 8);
+    IdxT *ev = eu + Ecap, *etd = ev + Ecap, *anext = etd + Ecap;
+    IdxT *qent = anext + 2 * Ecap;
+    IdxT *qcnext = qent + QC * QCH;
+    IdxT *ufp = qcnext + QC, *stamp = ufp + Ncap, *ahead = stamp + Ncap, *tnode = ahead + Ncap, *clevel = tnode + Ncap,
+         *mark = clevel + Ncap, *markgen = mark + Ncap;
+    IdxT *bhc = markgen + Ncap, *btc = bhc + NBINS, *bho = btc + NBINS, *btf = bho + NBINS;
 
     const uint32_t *geu = A.eu + B.ebase, *gev = A.ev + B.ebase, *gcnt = A.ecnt + B.ebase;
     const unsigned long long *gsum = A.esum + B.ebase;
@@ -99,10 +107,10 @@ __global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restric
 
     // ---- load the block's graph
     for (uint32_t i = lane; i < nc; i += 32) {
-        ufp[i] = (uint16_t)i;
+        ufp[i] = (IdxT)i;
         stamp[i] = 0;
         ahead[i] = N16;
-        tnode[i] = (uint16_t)i;
+        tnode[i] = (IdxT)i;
         clevel[i] = 0;
         markgen[i] = 0;
         tparent[i] = NONE32;
@@ -121,8 +129,8 @@ __global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restric
         uint32_t u = geu[e], v = gev[e];
         SumT s = (SumT)gsum[e];
         uint32_t c = gcnt[e];
-        eu[e] = (uint16_t)u;
-        ev[e] = (uint16_t)v;
+        eu[e] = (IdxT)u;
+        ev[e] = (IdxT)v;
         esum[e] = s;
         ecnt[e] = c;
         escore[e] = edge_score<U8>((unsigned long long)s, c);
@@ -144,10 +152,10 @@ __global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restric
                 peers = __match_any_sync(act, node);
                 const unsigned higher = peers & ~((2u << lane) - 1u);
                 const uint32_t nxt = higher ? 2 * (e0 + (__ffs(higher) - 1)) + side : (uint32_t)ahead[node];
-                anext[2 * e + side] = (uint16_t)nxt;
+                anext[2 * e + side] = (IdxT)nxt;
             }
             __syncwarp();   // the old heads are read before any leader replaces them
-            if (v && lane == __ffs(peers) - 1) ahead[node] = (uint16_t)(2 * e + side);
+            if (v && lane == __ffs(peers) - 1) ahead[node] = (IdxT)(2 * e + side);
             __syncwarp();
         }
     }
@@ -164,7 +172,7 @@ __global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restric
         unsigned act = __ballot_sync(FULL, v);
         if (v) {
             unsigned peers = __match_any_sync(act, bin);
-            if (lane == __ffs(peers) - 1) btf[bin] = (uint16_t)(btf[bin] + __popc(peers));
+            if (lane == __ffs(peers) - 1) btf[bin] = (IdxT)(btf[bin] + __popc(peers));
         }
         __syncwarp();
     }
@@ -191,10 +199,10 @@ __global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restric
         for (int j = 0; j < 8; j++) {
             int bin = lane * 8 + j;
             if (cnt[j]) {
-                bhc[bin] = (uint16_t)cs;
-                btc[bin] = (uint16_t)(cs + nch[j] - 1);
-                btf[bin] = (uint16_t)(cnt[j] - QCH * (nch[j] - 1));
-                for (uint32_t c = 0; c < nch[j]; c++) qcnext[cs + c] = (uint16_t)(c + 1 < nch[j] ? cs + c + 1 : N16);
+                bhc[bin] = (IdxT)cs;
+                btc[bin] = (IdxT)(cs + nch[j] - 1);
+                btf[bin] = (IdxT)(cnt[j] - QCH * (nch[j] - 1));
+                for (uint32_t c = 0; c < nch[j]; c++) qcnext[cs + c] = (IdxT)(c + 1 < nch[j] ? cs + c + 1 : N16);
                 bits |= 1u << j;
             }
             cs += nch[j];
@@ -222,8 +230,8 @@ __global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restric
             __syncwarp();
             if (v) {
                 uint32_t p = base + __popc(peers & lanemask_lt());
-                qent[((uint32_t)bhc[bin] + p / QCH) * QCH + (p % QCH)] = (uint16_t)e;
-                if (lane == __ffs(peers) - 1) bho[bin] = (uint16_t)(base + __popc(peers));
+                qent[((uint32_t)bhc[bin] + p / QCH) * QCH + (p % QCH)] = (IdxT)e;
+                if (lane == __ffs(peers) - 1) bho[bin] = (IdxT)(base + __popc(peers));
             }
             __syncwarp();
         }
@@ -270,25 +278,25 @@ __global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restric
             if (c) {
                 uint32_t pos = tf + off;
                 if (pos < (uint32_t)QCH)
-                    qent[tc * QCH + pos] = (uint16_t)e;
+                    qent[tc * QCH + pos] = (IdxT)e;
                 else
-                    qent[newc * QCH + (pos - QCH)] = (uint16_t)e;
+                    qent[newc * QCH + (pos - QCH)] = (IdxT)e;
                 valid = false;
             }
             if (lane == 0) {
                 if (need_new) {
                     qcnext[newc] = N16;
                     if (tc != N16)
-                        qcnext[tc] = (uint16_t)newc;
+                        qcnext[tc] = (IdxT)newc;
                     else {
-                        bhc[Bn] = (uint16_t)newc;
+                        bhc[Bn] = (IdxT)newc;
                         bho[Bn] = 0;
                         occ[Bn >> 5] |= 1u << (Bn & 31);
                     }
-                    btc[Bn] = (uint16_t)newc;
-                    btf[Bn] = (uint16_t)(tf + total - QCH);
+                    btc[Bn] = (IdxT)newc;
+                    btf[Bn] = (IdxT)(tf + total - QCH);
                 } else {
-                    btf[Bn] = (uint16_t)(tf + total);
+                    btf[Bn] = (IdxT)(tf + total);
                 }
             }
             __syncwarp();
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restric
                     if (prev == N16)
                         head = nx;
                     else if (lane == 0)
-                        anext[prev] = (uint16_t)nx;
+                        anext[prev] = (IdxT)nx;
                 } else {
                     if (lane == cnt) mineh = h;
                     cnt++;
@@ -374,8 +382,8 @@ __global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restric
             else if (td & DEADBIT)
                 cls = 1;
             else {
-                ru = find16(ufp, eu[e]);
-                rv = find16(ufp, ev[e]);
+                ru = find16<IdxT>(ufp, eu[e]);
+                rv = find16<IdxT>(ufp, ev[e]);
                 AGG_CHK(ru < nc && rv < nc && ru != rv, "roots");
                 if (stamp[ru] > td || stamp[rv] > td) {
                     cls = 2;
@@ -394,7 +402,7 @@ __global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restric
         const bool redo = act && cls == 2 && (lane < rstar || (lane == rstar && tcls == 2));
         if (redo) {
             escore[e] = newsc;
-            etd[e] = (uint16_t)clock;
+            etd[e] = (IdxT)clock;
         }
         const uint32_t consumed = (uint32_t)rstar + ((tcls == 3 || tcls == 2) ? 1u : 0u);
         n_pops += consumed;
@@ -418,7 +426,7 @@ __global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restric
                         occ[cb >> 5] &= ~(1u << (cb & 31));
                     }
                 } else if (lane == 0)
-                    bho[cb] = (uint16_t)ho2;
+                    bho[cb] = (IdxT)ho2;
             } else if (ho2 == (uint32_t)QCH) {
                 freed = true;
                 if (lane == 0) {
@@ -426,9 +434,9 @@ __global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restric
                     bho[cb] = 0;
                 }
             } else if (lane == 0)
-                bho[cb] = (uint16_t)ho2;
+                bho[cb] = (IdxT)ho2;
             if (freed) {
-                if (lane == 0) qcnext[hc] = (uint16_t)q_free;
+                if (lane == 0) qcnext[hc] = (IdxT)q_free;
                 q_free = hc;
             }
             __syncwarp();
@@ -447,18 +455,18 @@ __global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restric
         clock++;
         const uint32_t gen = clock;
         const float msc = escore[me];
-        if (lane == 0) etd[me] = (uint16_t)(etd[me] | DEADBIT);
+        if (lane == 0) etd[me] = (IdxT)(etd[me] | DEADBIT);
         __syncwarp();
         // pass 1: b's neighbours are marked with their edge
         uint32_t head_b = ahead[b], tail_b = N16;
         walk(head_b, tail_b, [&](uint32_t h) {
             if (h != N16) {
                 uint32_t ne = h >> 1;
-                uint32_t x1 = find16(ufp, eu[ne]), x2 = find16(ufp, ev[ne]);
+                uint32_t x1 = find16<IdxT>(ufp, eu[ne]), x2 = find16<IdxT>(ufp, ev[ne]);
                 uint32_t x = x1 == b ? x2 : x1;
                 AGG_CHK((x1 == b || x2 == b) && x < nc && x != b && x != a, "b neighbour");
-                mark[x] = (uint16_t)ne;
-                markgen[x] = (uint16_t)gen;
+                mark[x] = (IdxT)ne;
+                markgen[x] = (IdxT)gen;
             }
         });
         // pass 2: a's edges to a common neighbour absorb (or are absorbed by) b's edge
@@ -466,7 +474,7 @@ __global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restric
         walk(head_a, tail_a, [&](uint32_t h) {
             if (h != N16) {
                 uint32_t ae = h >> 1;
-                uint32_t x1 = find16(ufp, eu[ae]), x2 = find16(ufp, ev[ae]);
+                uint32_t x1 = find16<IdxT>(ufp, eu[ae]), x2 = find16<IdxT>(ufp, ev[ae]);
                 uint32_t x = x1 == a ? x2 : x1;
                 AGG_CHK((x1 == a || x2 == a) && x < nc && x != b && x != a, "a neighbour");
                 if (markgen[x] == gen) {
@@ -474,11 +482,11 @@ __global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restric
                     if (!keep_cheaper || escore[ne] > escore[ae]) {
                         esum[ae] += esum[ne];
                         ecnt[ae] += ecnt[ne];
-                        etd[ne] = (uint16_t)(etd[ne] | DEADBIT);
+                        etd[ne] = (IdxT)(etd[ne] | DEADBIT);
                     } else {
                         esum[ne] += esum[ae];
                         ecnt[ne] += ecnt[ae];
-                        etd[ae] = (uint16_t)(etd[ae] | DEADBIT);
+                        etd[ae] = (IdxT)(etd[ae] | DEADBIT);
                     }
                 }
             }
@@ -489,11 +497,11 @@ __global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restric
                 if (head_a == N16)
                     head_a = head_b;
                 else
-                    anext[tail_a] = (uint16_t)head_b;
+                    anext[tail_a] = (IdxT)head_b;
             }
-            ahead[a] = (uint16_t)head_a;
-            ufp[b] = (uint16_t)a;
-            stamp[a] = (uint16_t)clock;
+            ahead[a] = (IdxT)head_a;
+            ufp[b] = (IdxT)a;
+            stamp[a] = (IdxT)clock;
             const uint32_t t = nc + nmerge, ta = tnode[a], tbn = tnode[b];
             const uint32_t lvl = max((uint32_t)clevel[a], (uint32_t)clevel[b]) + 1;
             tparent[ta] = t;
@@ -501,8 +509,8 @@ __global__ void __launch_bounds__(32) k_agglomerate_smem(const AggBlk *__restric
             tparent[t] = NONE32;
             tlevel[t] = lvl;
             tscore[t] = msc;
-            tnode[a] = (uint16_t)t;
-            clevel[a] = (uint16_t)lvl;
+            tnode[a] = (IdxT)t;
+            clevel[a] = (IdxT)lvl;
             ha[nmerge] = a;
             hb[nmerge] = b;
             hs[nmerge] = msc;
@@ -532,12 +540,12 @@ int agglom_smem_launch(const AggBlk *blks, const int *list, int nlist, const Agg
     const size_t smem = agglom_smem_bytes(Ecap, Ncap, sum64);
     BS_ARG(smem <= 227 * 1024 && Ecap <= 32760 && Ncap <= 32760 && (Ecap % 8) == 0 && (Ncap % 8) == 0,
            "agglom_smem_launch: block graph does not fit in shared memory");
-#define BS_AGG_SMEM(U8_, SumT_)                                                                                     \
-    do {                                                                                                            \
-        BS_CUDA(cudaFuncSetAttribute(k_agglomerate_smem<U8_, SumT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                     227 * 1024));                                                                  \
-        BS_LAUNCH((k_agglomerate_smem<U8_, SumT_>), nlist, 32, smem, s, blks, list, A, threshold, keep_cheaper, Ecap, \
-                  Ncap);                                                                                            \
+#define BS_AGG_SMEM(U8_, SumT_)                                                                                              \
+    do {                                                                                                                     \
+        BS_CUDA(cudaFuncSetAttribute(k_agglomerate_lists<U8_, SumT_, uint16_t, true>,                                        \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));                              \
+        BS_LAUNCH((k_agglomerate_lists<U8_, SumT_, uint16_t, true>), nlist, 32, smem, s, blks, list, A, threshold,           \
+                  keep_cheaper, Ecap, Ncap, nullptr, nullptr);                                                               \
     } while (0)
     if (u8 && !sum64)
         BS_AGG_SMEM(true, uint32_t);
@@ -546,6 +554,19 @@ int agglom_smem_launch(const AggBlk *blks, const int *list, int nlist, const Agg
     else
         BS_AGG_SMEM(false, unsigned long long);
 #undef BS_AGG_SMEM
+    return BS_OK;
+}
+
+// blocks too large for shared memory: the same kernel on a global-memory slab per block (32-bit indices)
+int agglom_global_launch(const AggBlk *blks, const int *list, int nlist, const AggArrays &A, float threshold, int keep_cheaper,
+                         bool u8, unsigned char *work, const unsigned long long *woff, cudaStream_t s) {
+    if (nlist == 0) return BS_OK;
+    if (u8)
+        BS_LAUNCH((k_agglomerate_lists<true, unsigned long long, uint32_t, false>), nlist, 32, 0, s, blks, list, A, threshold,
+                  keep_cheaper, 0u, 0u, work, woff);
+    else
+        BS_LAUNCH((k_agglomerate_lists<false, unsigned long long, uint32_t, false>), nlist, 32, 0, s, blks, list, A, threshold,
+                  keep_cheaper, 0u, 0u, work, woff);
     return BS_OK;
 }
 

@@ -250,434 +250,6 @@ __global__ void k_compact_endpoints(const S2Blk *__restrict__ blks, const uint32
     cev[e] = cscan[vb + ev[e]] - c0;
 }
 
-__global__ void k_compact_deg(const uint32_t *__restrict__ deg, const uint32_t *__restrict__ cscan, size_t n,
-                              uint32_t *__restrict__ cdeg) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && deg[i]) cdeg[cscan[i]] = deg[i];
-}
-
-__global__ void k_nchunks(const uint32_t *__restrict__ deg, uint32_t *__restrict__ nch, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) nch[i] = (deg[i] + 31) >> 5;
-}
-
-// adjacency chunk chains: node i owns chunks [cstart[i], cstart[i] + nch[i])
-__global__ void k_adj_nodes(const uint32_t *__restrict__ deg, const uint32_t *__restrict__ cstart,
-                            uint32_t *__restrict__ ahead, uint32_t *__restrict__ atail, uint32_t *__restrict__ cnext, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t nc = (deg[i] + 31) >> 5;
-    if (nc == 0) {
-        ahead[i] = NONE32;
-        atail[i] = NONE32;
-        return;
-    }
-    uint32_t c0 = cstart[i];
-    ahead[i] = c0;
-    atail[i] = c0 + nc - 1;
-    for (uint32_t c = 0; c < nc; c++) cnext[c0 + c] = c + 1 < nc ? c0 + c + 1 : NONE32;
-}
-
-__global__ void k_adj_fill(const uint32_t *__restrict__ cbase, const uint32_t *__restrict__ ebase, const uint32_t *__restrict__ eblk,
-                           const uint32_t *__restrict__ ceu, const uint32_t *__restrict__ cev, uint32_t E,
-                           const uint32_t *__restrict__ cstart, uint32_t *__restrict__ cursor, uint32_t *__restrict__ centries) {
-    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= E) return;
-    const uint32_t cb = cbase[eblk[e]];
-    uint32_t el = e - ebase[eblk[e]];
-    uint32_t nu = cb + ceu[e], nv = cb + cev[e];
-    uint32_t pu = atomicAdd(&cursor[nu], 1u);
-    centries[(size_t)cstart[nu] * 32 + pu] = el;
-    uint32_t pv = atomicAdd(&cursor[nv], 1u);
-    centries[(size_t)cstart[nv] * 32 + pv] = el;
-}
-
-// ------------------------------------------------------------------ agglomeration
-__device__ __forceinline__ uint32_t agg_find(uint32_t *ufp, uint32_t x) {
-    // path halving; concurrent lanes only ever write ancestors
-    for (;;) {
-        uint32_t p = ufp[x];
-        if (p == x) return x;
-        uint32_t gp = ufp[p];
-        if (gp == p) return p;
-        ufp[x] = gp;
-        x = gp;
-    }
-}
-
-__device__ __forceinline__ unsigned long long pair_key(uint32_t a, uint32_t b) {
-    return a < b ? (((unsigned long long)a << 32) | b) : (((unsigned long long)b << 32) | a);
-}
-
-// lookup: returns slot of key or NONE32
-__device__ __forceinline__ uint32_t pair_lookup(const unsigned long long *pkeys, uint32_t hmask, unsigned long long key) {
-    uint32_t slot = (uint32_t)hash64(key) & hmask;
-    for (uint32_t probes = 0; probes <= hmask; probes++) {
-        unsigned long long k = __ldcg(&pkeys[slot]);
-        if (k == key) return slot;
-        if (k == EMPTY64) return NONE32;
-        slot = (slot + 1) & hmask;
-    }
-    return NONE32;
-}
-
-// insert a key known to be absent; reuses tombstones; returns slot or NONE32 on overflow
-__device__ __forceinline__ uint32_t pair_insert(unsigned long long *pkeys, uint32_t hmask, unsigned long long key) {
-    uint32_t slot = (uint32_t)hash64(key) & hmask;
-    for (uint32_t probes = 0; probes <= hmask; probes++) {
-        unsigned long long k = __ldcg(&pkeys[slot]);
-        if (k == EMPTY64 || k == TOMB64) {
-            unsigned long long old = atomicCAS(&pkeys[slot], k, key);
-            if (old == k) return slot;
-            continue;   // somebody else took it: re-examine the same slot
-        }
-        slot = (slot + 1) & hmask;
-    }
-    return NONE32;
-}
-
-struct BinQ {
-    uint32_t hc[256], ho[256], tc[256], tf[256];
-};
-
-template <bool U8>
-__global__ void __launch_bounds__(32) k_agglomerate(const AggBlk *__restrict__ blks, const int *__restrict__ list, AggArrays A,
-                                                    float threshold, int nbins, int keep_cheaper) {
-    __shared__ BinQ Q;
-    const int bi = list[blockIdx.x];
-    const AggBlk B = blks[bi];
-    const int lane = threadIdx.x;
-    uint32_t *eu = A.eu + B.ebase, *ev = A.ev + B.ebase, *ecnt = A.ecnt + B.ebase, *etime = A.etime + B.ebase;
-    unsigned long long *esum = A.esum + B.ebase;
-    float *escore = A.escore + B.ebase;
-    uint8_t *edead = A.edead + B.ebase;
-    uint32_t *ufp = A.ufp + B.vbase, *stamp = A.stamp + B.vbase, *ahead = A.ahead + B.vbase, *atail = A.atail + B.vbase,
-             *tnode = A.tnode + B.vbase;
-    unsigned long long *pkeys = A.pkeys + B.hbase;
-    uint32_t *pvals = A.pvals + B.hbase;
-    const uint32_t hmask = B.hcap - 1;
-    uint32_t *qentries = A.qentries + (size_t)B.qbase * 32, *qnext = A.qnext + B.qbase;
-    uint32_t *tparent = A.tparent + 2 * (size_t)B.vbase, *tlevel = A.tlevel + 2 * (size_t)B.vbase;
-    float *tscore = A.tscore + 2 * (size_t)B.vbase;
-    uint32_t *ha = A.ha + B.vbase, *hb = A.hb + B.vbase;
-    float *hs = A.hs + B.vbase;
-
-    for (int i = lane; i < 256; i += 32) {
-        Q.hc[i] = NONE32;
-        Q.ho[i] = 0;
-        Q.tc[i] = NONE32;
-        Q.tf[i] = 0;
-    }
-    __syncwarp();
-    // uniform (replicated) allocator state
-    uint32_t q_bump = 0, q_free = NONE32;
-    bool fail = false;
-    uint32_t n_pops = 0, n_stale = 0, n_dead = 0, n_iter = 0, n_chunk = 0, n_append = 0;
-
-    auto alloc_chunk = [&]() -> uint32_t {
-        uint32_t c;
-        if (q_free != NONE32) {
-            c = q_free;
-            q_free = qnext[c];
-        } else {
-            c = q_bump++;
-            if (c >= B.qcap) {
-                fail = true;
-                c = 0;
-            }
-        }
-        return c;
-    };
-    // order-preserving (lane order) append of edge `e` to bin `bin` for lanes with `valid`
-    auto bin_append = [&](bool valid, int bin, uint32_t e) {
-        for (;;) {
-            int mine = valid ? bin : 0x7fffffff;
-            int Bn = __reduce_min_sync(FULL, mine);
-            if (Bn == 0x7fffffff) break;
-            n_append++;
-            bool c = valid && bin == Bn;
-            unsigned m = __ballot_sync(FULL, c);
-            uint32_t total = __popc(m), off = __popc(m & lanemask_lt());
-            uint32_t tc = Q.tc[Bn], tf = Q.tf[Bn];
-            uint32_t tfe = tc == NONE32 ? 32u : tf;
-            bool need_new = tfe + total > 32u;
-            uint32_t newc = NONE32;
-            if (need_new) {
-                newc = alloc_chunk();
-                if (lane == 0) qnext[newc] = NONE32;
-            }
-            if (c) {
-                uint32_t pos = tfe + off;
-                if (pos < 32u)
-                    qentries[(size_t)tc * 32 + pos] = e;
-                else
-                    qentries[(size_t)newc * 32 + (pos - 32u)] = e;
-                valid = false;
-            }
-            __syncwarp();
-            if (lane == 0) {
-                if (need_new) {
-                    if (tc != NONE32)
-                        qnext[tc] = newc;
-                    else {
-                        Q.hc[Bn] = newc;
-                        Q.ho[Bn] = 0;
-                    }
-                    Q.tc[Bn] = newc;
-                    Q.tf[Bn] = tfe + total - 32u;
-                } else {
-                    Q.tf[Bn] = tf + total;
-                }
-            }
-            __syncwarp();
-        }
-    };
-
-    // ---- node + tree init, pair hash of the initial edges
-    for (uint32_t i = lane; i < B.nv; i += 32) {
-        ufp[i] = i;
-        stamp[i] = 0;
-        tnode[i] = i;
-        tparent[i] = NONE32;
-        tlevel[i] = 0;
-        tscore[i] = 0.f;
-    }
-    for (uint32_t e = lane; e < B.E; e += 32) {
-        uint32_t s = pair_insert(pkeys, hmask, pair_key(eu[e], ev[e]));
-        if (s == NONE32)
-            fail = true;
-        else
-            pvals[s] = e;
-    }
-    __syncwarp();
-    // ---- initial scoring, edges pushed in creation order (waterz mergeUntil first call)
-    for (uint32_t e0 = 0; e0 < B.E; e0 += 32) {
-        uint32_t e = e0 + lane;
-        bool v = e < B.E;
-        int bin = 0;
-        if (v) {
-            float sc = edge_score<U8>(esum[e], ecnt[e]);
-            escore[e] = sc;
-            etime[e] = 0;
-            edead[e] = 0;
-            bin = score_bin(sc, nbins);
-        }
-        bin_append(v, bin, e);
-    }
-    fail = __any_sync(FULL, fail);
-
-    uint32_t clock = 0, nmerge = 0;
-    int minbin = 0;
-    while (!fail) {
-        // lowest non-empty bin
-        int cb = minbin;
-        uint32_t hc = NONE32, ho = 0, tc = NONE32, tf = 0;
-        for (; cb < nbins; cb++) {
-            hc = Q.hc[cb], ho = Q.ho[cb], tc = Q.tc[cb], tf = Q.tf[cb];
-            if (hc != NONE32 && !(hc == tc && ho == tf)) break;
-        }
-        if (cb >= nbins) break;
-        minbin = cb;
-        n_iter++;
-        const uint32_t k = (hc == tc ? tf : 32u) - ho;
-        const bool act = (uint32_t)lane < k;
-        uint32_t e = 0, ru = 0, rv = 0;
-        int cls = 1;   // 0 stop, 1 dead/inactive, 2 stale, 3 merge
-        float newsc = 0.f;
-        int nbin = 0;
-        if (act) {
-            e = qentries[(size_t)hc * 32 + ho + lane];
-            float sc = escore[e];
-            if (sc >= threshold)
-                cls = 0;
-            else if (edead[e])
-                cls = 1;
-            else {
-                ru = agg_find(ufp, eu[e]);
-                rv = agg_find(ufp, ev[e]);
-                uint32_t te = etime[e];
-                if (stamp[ru] > te || stamp[rv] > te) {
-                    cls = 2;
-                    newsc = edge_score<U8>(esum[e], ecnt[e]);
-                    nbin = score_bin(newsc, nbins);
-                } else
-                    cls = 3;
-            }
-        }
-        bool trig = act && (cls == 0 || cls == 3 || (cls == 2 && nbin < cb));
-        unsigned tb = __ballot_sync(FULL, trig);
-        int rstar = tb ? __ffs(tb) - 1 : (int)k;
-        int tcls = __shfl_sync(FULL, cls, rstar & 31);
-        if (!tb) tcls = -1;
-        // stale entries before the trigger (and a stale trigger itself) are re-scored and re-queued
-        bool redo = act && cls == 2 && (lane < rstar || (lane == rstar && tcls == 2));
-        if (redo) {
-            escore[e] = newsc;
-            etime[e] = clock;
-        }
-        uint32_t consumed = (uint32_t)rstar + ((tcls == 3 || tcls == 2) ? 1u : 0u);
-        n_pops += consumed;
-        n_stale += __popc(__ballot_sync(FULL, redo));
-        n_dead += __popc(__ballot_sync(FULL, act && cls == 1 && lane < rstar));
-        bin_append(redo, nbin, e);
-        // advance the head of bin cb (re-read: the append may have touched the tail)
-        if (lane == 0) {
-            uint32_t ho2 = ho + consumed;
-            uint32_t tc2 = Q.tc[cb], tf2 = Q.tf[cb];
-            if (hc == tc2) {
-                if (ho2 == tf2) {
-                    ho2 = 0;
-                    Q.tf[cb] = 0;
-                }
-                Q.ho[cb] = ho2;
-            } else if (ho2 == 32u) {
-                Q.hc[cb] = qnext[hc];
-                Q.ho[cb] = 0;
-            } else {
-                Q.ho[cb] = ho2;
-            }
-        }
-        bool freed = (hc != Q.tc[cb]) && (ho + consumed == 32u);
-        __syncwarp();
-        if (freed) {
-            // chunk hc fully consumed and not the tail: recycle (all lanes keep the replicated free list)
-            if (lane == 0) qnext[hc] = q_free;
-            q_free = hc;
-            __syncwarp();
-        }
-        if (tcls == 0) break;
-        if (tcls == 2) {
-            minbin = __shfl_sync(FULL, nbin, rstar);
-            continue;
-        }
-        if (tcls != 3) continue;
-
-        // ---- merge: edge me joins clusters a < b, a survives (waterz mergeRegions)
-        const uint32_t me = __shfl_sync(FULL, e, rstar);
-        const uint32_t r1 = __shfl_sync(FULL, ru, rstar), r2 = __shfl_sync(FULL, rv, rstar);
-        const uint32_t a = min(r1, r2), b = max(r1, r2);
-        clock++;
-        if (lane == 0) {
-            float sc = escore[me];
-            ha[nmerge] = a;
-            hb[nmerge] = b;
-            hs[nmerge] = sc;
-            uint32_t t = B.nv + nmerge, ta = tnode[a], tbn = tnode[b];
-            tparent[ta] = t;
-            tparent[tbn] = t;
-            tparent[t] = NONE32;
-            tlevel[t] = max(tlevel[ta], tlevel[tbn]) + 1;
-            tscore[t] = sc;
-            tnode[a] = t;
-            ufp[b] = a;
-            stamp[a] = clock;
-            edead[me] = 1;
-            uint32_t s = pair_lookup(pkeys, hmask, pair_key(a, b));
-            if (s != NONE32) __stcg(&pkeys[s], TOMB64);
-        }
-        nmerge++;
-        __syncwarp();
-        // walk b's incident-edge chain; surviving entries are re-packed in place (write cursor never passes
-        // the read cursor), so a cluster's chain stays proportional to its live degree
-        uint32_t c = ahead[b];
-        uint32_t wc = c, wo = 0, wlast = NONE32;   // write chunk, fill, last chunk that holds a kept entry
-        while (c != NONE32) {
-            n_chunk++;
-            const uint32_t cn = A.cnext[c];
-            uint32_t ne = A.centries[(size_t)c * 32 + lane];
-            bool valid = ne != NONE32 && !edead[ne];
-            bool keep = false;
-            if (valid) {
-                uint32_t x1 = agg_find(ufp, eu[ne]), x2 = agg_find(ufp, ev[ne]);
-                uint32_t x = x1 == a ? x2 : x1;
-                if (x == a) {
-                    edead[ne] = 1;   // cannot happen for a consistent graph; keep the state sane
-                } else {
-                    // the stale key (b, x) is retired, the edge now lives under (a, x)
-                    uint32_t so = pair_lookup(pkeys, hmask, pair_key(b, x));
-                    if (so != NONE32) __stcg(&pkeys[so], TOMB64);
-                    uint32_t sa = pair_lookup(pkeys, hmask, pair_key(a, x));
-                    if (sa == NONE32) {
-                        uint32_t sn = pair_insert(pkeys, hmask, pair_key(a, x));
-                        if (sn == NONE32)
-                            fail = true;
-                        else
-                            pvals[sn] = ne;
-                        keep = true;
-                    } else {
-                        uint32_t ae = pvals[sa];
-                        if (!keep_cheaper || escore[ne] > escore[ae]) {
-                            esum[ae] += esum[ne];
-                            ecnt[ae] += ecnt[ne];
-                            edead[ne] = 1;
-                        } else {
-                            esum[ne] += esum[ae];
-                            ecnt[ne] += ecnt[ae];
-                            edead[ae] = 1;
-                            pvals[sa] = ne;
-                            keep = true;
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            const unsigned km = __ballot_sync(FULL, keep);
-            if (km) {
-                const uint32_t pos = wo + __popc(km & lanemask_lt());
-                const uint32_t wnext = A.cnext[wc];
-                if (keep) {
-                    if (pos < 32u)
-                        A.centries[(size_t)wc * 32 + pos] = ne;
-                    else
-                        A.centries[(size_t)wnext * 32 + (pos - 32u)] = ne;
-                }
-                const uint32_t tot = wo + __popc(km);
-                if (tot > 32u) {
-                    wc = wnext;
-                    wo = tot - 32u;
-                    wlast = wc;
-                } else {
-                    wo = tot;
-                    wlast = wc;
-                    if (tot == 32u && cn != NONE32) {
-                        // next kept entry starts a fresh chunk; stay put if the chain ends here
-                        wc = wnext;
-                        wo = 0;
-                    }
-                }
-            }
-            __syncwarp();
-            c = cn;
-        }
-        // terminate the re-packed chain and append it to a's
-        const uint32_t bhead = ahead[b];
-        if (wlast != NONE32) {
-            // slots behind the write cursor in the last chunk are cleared; wo == 0 with wc != wlast means full
-            if (wc == wlast && (uint32_t)lane >= wo && wo < 32u) A.centries[(size_t)wlast * 32 + lane] = NONE32;
-            if (lane == 0) {
-                A.cnext[wlast] = NONE32;
-                if (ahead[a] == NONE32)
-                    ahead[a] = bhead;
-                else
-                    A.cnext[atail[a]] = bhead;
-                atail[a] = wlast;
-            }
-        }
-        fail = __any_sync(FULL, fail);
-        __syncwarp();
-    }
-    if (lane == 0) {
-        A.nmerges[bi] = nmerge;
-        A.counters[6 * bi + 0] = n_pops;
-        A.counters[6 * bi + 1] = n_stale;
-        A.counters[6 * bi + 2] = n_dead;
-        A.counters[6 * bi + 3] = n_iter;
-        A.counters[6 * bi + 4] = n_chunk;
-        A.counters[6 * bi + 5] = n_append;
-        if (fail) atomicExch(A.error, 1u);
-    }
-}
-
 // ------------------------------------------------------------------ merge-tree score of every initial edge
 // post/merge_tree.py:5-27: climb from the lower-level side until both sides meet; NaN if they never do.
 __global__ void k_lca(const S2Blk *__restrict__ blks, const uint32_t *__restrict__ cbase, const uint32_t *__restrict__ eblk,
@@ -956,7 +528,6 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
         a.E = h_ebase[i + 1] - h_ebase[i];
         a.vbase = h_cbase[i];
         a.nv = h_cbase[i + 1] - h_cbase[i];
-        a.hbase = a.hcap = a.qbase = a.qcap = 0;
         // u8 affinity sums of a whole block fit 32 bits when 3 * 255 * read voxels < 2^32
         if (u8 && 765.0 * hb[i].rs[0] * hb[i].rs[1] * hb[i].rs[2] >= 4294967295.0) sum64 = true;
     }
@@ -974,49 +545,18 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
             }
         }
     }
-    uint64_t hcur = 0, qcur = 0;
-    for (int i : l_glob) {
-        AggBlk &a = ab[i];
-        a.hcap = next_pow2((uint64_t)std::max<uint32_t>(64, 4 * a.E));
-        a.hbase = (uint32_t)hcur;
-        hcur += a.hcap;
-        a.qcap = a.E / 16 + 2 * 256 + 64;
-        a.qbase = (uint32_t)qcur;
-        qcur += a.qcap;
-        BS_ARG(hcur < (1ull << 32), "stage2: pair hash exceeds 32-bit indexing");
+    // blocks too large for shared memory: a global-memory slab each (32-bit indices, 64-bit sums)
+    std::vector<unsigned long long> h_woff(l_glob.size() + 1, 0);
+    for (size_t k = 0; k < l_glob.size(); k++) {
+        const AggBlk &a = ab[l_glob[k]];
+        uint32_t Ec = (std::max<uint32_t>(a.E, 8) + 7) & ~7u, Nc = (std::max<uint32_t>(a.nv, 8) + 7) & ~7u;
+        h_woff[k + 1] = h_woff[k] + agglom_work_bytes(Ec, Nc, true, 4);
     }
     const bool any_glob = !l_glob.empty();
 
-    // ---- adjacency chunk chains (global-memory kernel only)
-    const size_t NCmax = any_glob ? Ctot + (size_t)E / 16 + 2 : 1;
-    DevBuf cdeg, nch, cstart, ahead, atail, cnext, centries, cursor;
-    if (any_glob) {
-        BS_TRY(cdeg.alloc_zero(4 * (Ctot + 1), s));
-        BS_TRY(nch.alloc(4 * (Ctot + 1), s));
-        BS_TRY(cstart.alloc(4 * (Ctot + 1), s));
-        BS_TRY(ahead.alloc(4 * (Ctot + 1), s));
-        BS_TRY(atail.alloc(4 * (Ctot + 1), s));
-        BS_TRY(cnext.alloc(4 * NCmax, s));
-        BS_TRY(centries.alloc_fill(4 * NCmax * 32, 0xFF, s));
-        BS_TRY(cursor.alloc_zero(4 * (Ctot + 1), s));
-        if (Ctot) {
-            BS_LAUNCH(k_compact_deg, cdiv(Vtot, 256), 256, 0, s, deg.as<uint32_t>(), cscan.as<uint32_t>(), Vtot,
-                      cdeg.as<uint32_t>());
-            BS_LAUNCH(k_nchunks, cdiv(Ctot, 256), 256, 0, s, cdeg.as<uint32_t>(), nch.as<uint32_t>(), Ctot);
-            BS_TRY(scan_exclusive_u32(nch.as<uint32_t>(), cstart.as<uint32_t>(), Ctot, nullptr, s));
-            BS_LAUNCH(k_adj_nodes, cdiv(Ctot, 256), 256, 0, s, cdeg.as<uint32_t>(), cstart.as<uint32_t>(), ahead.as<uint32_t>(),
-                      atail.as<uint32_t>(), cnext.as<uint32_t>(), Ctot);
-        }
-        if (E)
-            BS_LAUNCH(k_adj_fill, cdiv(E, 256), 256, 0, s, cbase.as<uint32_t>(), ebase.as<uint32_t>(), eblk.as<uint32_t>(),
-                      ceu.as<uint32_t>(), cev.as<uint32_t>(), E, cstart.as<uint32_t>(), cursor.as<uint32_t>(),
-                      centries.as<uint32_t>());
-    }
-
     // ---- agglomeration
     g_prof.mark("s2.agglomerate", s);
-    DevBuf d_ab, d_list, etime, escore, edead, ufp, stamp, tnode, pkeys, pvals, qentries, qnext, tparent, tlevel, tscore, ha, hbb,
-        hs, nmerges, counters, err;
+    DevBuf d_ab, d_list, gwork, d_woff, tparent, tlevel, tscore, ha, hbb, hs, nmerges, counters, err;
     BS_TRY(d_ab.alloc(sizeof(AggBlk) * nown, s));
     BS_CUDA(cudaMemcpyAsync(d_ab.p, ab.data(), sizeof(AggBlk) * nown, cudaMemcpyHostToDevice, s));
     std::vector<int> h_list(l_smem);
@@ -1024,16 +564,9 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
     BS_TRY(d_list.alloc(sizeof(int) * (nown + 1), s));
     BS_CUDA(cudaMemcpyAsync(d_list.p, h_list.data(), sizeof(int) * nown, cudaMemcpyHostToDevice, s));
     if (any_glob) {
-        BS_TRY(etime.alloc(4 * ((size_t)E + 1), s));
-        BS_TRY(escore.alloc(4 * ((size_t)E + 1), s));
-        BS_TRY(edead.alloc(((size_t)E + 1), s));
-        BS_TRY(ufp.alloc(4 * (Ctot + 1), s));
-        BS_TRY(stamp.alloc(4 * (Ctot + 1), s));
-        BS_TRY(tnode.alloc(4 * (Ctot + 1), s));
-        BS_TRY(pkeys.alloc_fill(8 * (size_t)hcur, 0xFF, s));
-        BS_TRY(pvals.alloc(4 * (size_t)hcur, s));
-        BS_TRY(qentries.alloc(4 * (size_t)qcur * 32, s));
-        BS_TRY(qnext.alloc(4 * (size_t)qcur, s));
+        BS_TRY(gwork.alloc((size_t)h_woff[l_glob.size()], s));
+        BS_TRY(d_woff.alloc(8 * h_woff.size(), s));
+        BS_CUDA(cudaMemcpyAsync(d_woff.p, h_woff.data(), 8 * h_woff.size(), cudaMemcpyHostToDevice, s));
     }
     BS_TRY(tparent.alloc(4 * (2 * Ctot + 2), s));
     BS_TRY(tlevel.alloc(4 * (2 * Ctot + 2), s));
@@ -1045,33 +578,19 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
     BS_TRY(counters.alloc_zero(24 * nown, s));
     BS_TRY(err.alloc_zero(16, s));
     AggArrays A;
-    A.eu = ceu.as<uint32_t>(), A.ev = cev.as<uint32_t>(), A.ecnt = ecnt.as<uint32_t>(), A.etime = etime.as<uint32_t>();
+    A.eu = ceu.as<uint32_t>(), A.ev = cev.as<uint32_t>(), A.ecnt = ecnt.as<uint32_t>();
     A.esum = esum.as<unsigned long long>();
-    A.escore = escore.as<float>();
-    A.edead = edead.as<uint8_t>();
-    A.ufp = ufp.as<uint32_t>(), A.stamp = stamp.as<uint32_t>(), A.ahead = ahead.as<uint32_t>(), A.atail = atail.as<uint32_t>(),
-    A.tnode = tnode.as<uint32_t>();
-    A.centries = centries.as<uint32_t>(), A.cnext = cnext.as<uint32_t>();
-    A.pkeys = pkeys.as<unsigned long long>(), A.pvals = pvals.as<uint32_t>();
-    A.qentries = qentries.as<uint32_t>(), A.qnext = qnext.as<uint32_t>();
     A.tparent = tparent.as<uint32_t>(), A.tlevel = tlevel.as<uint32_t>(), A.tscore = tscore.as<float>();
     A.ha = ha.as<uint32_t>(), A.hb = hbb.as<uint32_t>(), A.hs = hs.as<float>();
     A.nmerges = nmerges.as<uint32_t>();
     A.counters = counters.as<uint32_t>();
     A.error = err.as<uint32_t>();
-    const int nbins = cfg.queue_bins;
-    BS_ARG(nbins == 256, "stage2: only the BinQueue<256> agglomeration of the blockwise path is implemented");
+    BS_ARG(cfg.queue_bins == 256, "stage2: only the BinQueue<256> agglomeration of the blockwise path is implemented");
     BS_TRY(agglom_smem_launch(d_ab.as<AggBlk>(), d_list.as<int>(), (int)l_smem.size(), A, 1.0f, cfg.keep_cheaper, u8, sum64,
                               Emax, Nmax, s));
-    if (any_glob) {
-        const int *gl = d_list.as<int>() + l_smem.size();
-        if (u8)
-            BS_LAUNCH((k_agglomerate<true>), (unsigned)l_glob.size(), 32, 0, s, d_ab.as<AggBlk>(), gl, A, 1.0f, nbins,
-                      cfg.keep_cheaper);
-        else
-            BS_LAUNCH((k_agglomerate<false>), (unsigned)l_glob.size(), 32, 0, s, d_ab.as<AggBlk>(), gl, A, 1.0f, nbins,
-                      cfg.keep_cheaper);
-    }
+    if (any_glob)
+        BS_TRY(agglom_global_launch(d_ab.as<AggBlk>(), d_list.as<int>() + l_smem.size(), (int)l_glob.size(), A, 1.0f,
+                                    cfg.keep_cheaper, u8, gwork.as<unsigned char>(), d_woff.as<unsigned long long>(), s));
 
     // ---- merge-tree scores, ownership, output (host sync: number of owned edges)
     g_prof.mark("s2.lca", s);

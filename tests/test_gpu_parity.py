@@ -309,3 +309,18 @@ def test_cc_affs_golden_and_oracle():
         frags, seg, n = native.cc_affs(torch.from_numpy(affs).cuda(), thr, rd)
         assert np.array_equal(frags.cpu().numpy(), rf.astype(np.int64))
         assert np.array_equal(seg.cpu().numpy(), rs.astype(np.int64))
+
+
+def test_agglomeration_kernels_agree():
+    """the shared-memory agglomeration and its global-memory form (large blocks) give identical graphs"""
+    from bootstrapper_b200 import native
+    from bootstrapper_b200.synth import synth_affs
+    affs = synth_affs((20, 160, 160), seed=5)
+    block, ctx = (10, 80, 80), (2, 10, 10)
+    ref = _oracle(affs, {}, block, ctx)
+    try:
+        native.set_agglom_version(1)
+        r = _run_gpu(affs, {}, block, ctx)
+    finally:
+        native.set_agglom_version(0)
+    _check(r, ref)
