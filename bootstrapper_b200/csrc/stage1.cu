@@ -870,6 +870,7 @@ __global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict
         tailc = __ldcg(&lvl_tail[cur]);
     }
     uint32_t qs = lvl_qstart[cur];
+    uint32_t pre_level = NONE32, pre_head = 0, pre_tail = 0, pre_entry = 0;
     for (;;) {
         if (headc == tailc) {
             if (lane == 0) {
@@ -900,13 +901,16 @@ __global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict
         steps++;
         const uint32_t k = min(32u, tailc - headc);
         const bool act = (uint32_t)lane < k;
-        uint32_t entry = act ? __ldcg(&queue[qs + headc + lane]) : 0;
+        // entries that were already queued when the previous step ended were fetched during that step
+        uint32_t entry = 0;
+        if (act) entry = (pre_level == cur && pre_head == headc && headc + lane < pre_tail) ? pre_entry : __ldcg(&queue[qs + headc + lane]);
         const uint32_t p = entry & F2_PIXMASK, mylab = entry >> 17;
         const int y = p / W, x = p - y * W;
         // neighbour order of skimage (connectivity 1, 2-D): -y, -x, +x, +y
         uint32_t nb[4];
         bool cand[4], pend[4];
         uint32_t hs[4];
+        uint16_t lraw[4];
         nb[0] = (act && y > 0) ? p - W : NONE32;
         nb[1] = (act && x > 0) ? p - 1 : NONE32;
         nb[2] = (act && x + 1 < W) ? p + 1 : NONE32;
@@ -918,6 +922,7 @@ __global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict
             cand[s] = nb[s] != NONE32 && ((avail[nb[s] >> 5] >> (nb[s] & 31)) & 1u);
             pend[s] = cand[s];
             hs[s] = (nb[s] * 2654435761u) >> 24;
+            lraw[s] = cand[s] ? lv16[nb[s]] : (uint16_t)0;   // issued early: the claim resolution hides the latency
         }
         __syncwarp();
         // the lowest (lane, slot) key wins every contested pixel
@@ -948,7 +953,7 @@ __global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict
             l[s] = 0;
             ent[s] = 0;
             if (cand[s]) {
-                l[s] = lo + lv16[nb[s]];
+                l[s] = lo + lraw[s];
                 ent[s] = (mylab << 17) | nb[s];
                 up |= l[s] > cur;
             }
@@ -961,6 +966,9 @@ __global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict
             if (cand[s]) atomicAnd(&avail[nb[s] >> 5], ~(1u << (nb[s] & 31)));
         }
         headc += min(k, (uint32_t)rstar + 1u);
+        // prefetch the next batch of this level (what is queued so far) behind the append
+        pre_level = cur, pre_head = headc, pre_tail = tailc;
+        pre_entry = headc + lane < tailc ? __ldcg(&queue[qs + headc + lane]) : 0;
         warp_append<4>(cand, l, ent, queue, lvl_qstart, lvl_tail, cur, tailc, lane);
         __syncwarp();
         if (ball) {
