@@ -21,6 +21,7 @@
 //   k_fragstats      per-fragment affinity sum + voxel count (warp-aggregated atomics)
 //   k_crop_*         keep/drop decision, 8/26-connected relabel of the cropped write ROI
 //   k_finalize       raster-order ids (+ block_id * prod(block_size)), uint64 output, node statistics
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -35,6 +36,9 @@ static constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 static constexpr uint16_t GINF = 0xFFFF;
 static constexpr uint32_t DBIG = 0x3FFFFFFFu;
 static constexpr int MAXW = 4096;
+// pixels a 256-thread CTA of the per-pixel kernels walks through: enough work to amortise the tile set-up, enough CTAs
+// (tiles x pixels / PIX_PER_CTA) to fill 148 SMs on small batches
+static const long long PIX_PER_CTA = getenv("BS_PIX_PER_CTA") ? atoll(getenv("BS_PIX_PER_CTA")) : 4096;
 static constexpr unsigned FULL = 0xFFFFFFFFu;
 
 // rank of position w in a bitmap whose per-word popcounts were scanned into wscan (exclusive)
@@ -1323,7 +1327,7 @@ struct TileDims {
 };
 
 static dim3 pixel_grid(const TileDims &td) {
-    return dim3((unsigned)std::min<long long>(std::max<long long>((td.maxpix + 1023) / 1024, 1), 2048), td.ntiles);
+    return dim3((unsigned)std::min<long long>(std::max<long long>((td.maxpix + PIX_PER_CTA - 1) / PIX_PER_CTA, 1), 2048), td.ntiles);
 }
 
 // exact squared EDT of the mask whose row distances are in g -> out (tmp: in-plane result of 3-D tiles)
@@ -1534,7 +1538,7 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     BS_CUDA(cudaMemcpyAsync(d_blks.p, blks.data(), sizeof(BlkDev) * blks.size(), cudaMemcpyHostToDevice, s));
     const Tile *dt = d_tiles.as<Tile>();
 
-    const unsigned gx = (unsigned)std::min<long long>(std::max<long long>((maxpix + 1023) / 1024, 1), 2048);
+    const unsigned gx = (unsigned)std::min<long long>(std::max<long long>((maxpix + PIX_PER_CTA - 1) / PIX_PER_CTA, 1), 2048);
     const dim3 grid(gx, ntiles);
 
     DevBuf msk, g, d2, tmpA, tmpB, lab, lv, sbits, swcnt, swscan, tileflags, tilemax;
@@ -1677,7 +1681,7 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
                   lvl_tail.as<uint32_t>(), tile_lvl.as<uint32_t>(), seedlist.as<uint32_t>(), tile_seed.as<uint32_t>(),
                   nwords_max, fstats.as<uint32_t>());
         g_prof.mark("s1.flood_scatter", s);
-        BS_LAUNCH(k_scatter_labels, grid, 256, 0, s, dt, tile_q.as<uint32_t>(), queue.as<uint32_t>(), lab.as<uint32_t>());
+        BS_LAUNCH(k_scatter_labels, dim3((unsigned)std::min<long long>(std::max<long long>((maxpix + 1023) / 1024, 1), 2048), ntiles), 256, 0, s, dt, tile_q.as<uint32_t>(), queue.as<uint32_t>(), lab.as<uint32_t>());
     } else {
         BS_LAUNCH(k_flood, cdiv((size_t)ntiles * 32, 64), 64, 0, s, dt, ntiles, lab.as<uint32_t>(), lv.as<uint32_t>(),
                   queue.as<uint32_t>(), lvl_qstart.as<uint32_t>(), lvl_head.as<uint32_t>(), lvl_tail.as<uint32_t>(),
@@ -1725,7 +1729,9 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     g_prof.mark("s1.crop_cc", s);
     long long maxwt = 1;
     for (auto &t : tiles) maxwt = std::max(maxwt, (long long)t.wD * t.wH * t.wW);
+    // the union-find kernels run better with many small CTAs (their atomics stay spatially clustered)
     const dim3 gridw((unsigned)std::min<long long>(std::max<long long>((maxwt + 1023) / 1024, 1), 2048), ntiles);
+    const dim3 gridf((unsigned)std::min<long long>(std::max<long long>((maxwt + PIX_PER_CTA - 1) / PIX_PER_CTA, 1), 2048), ntiles);
     // cpar reuses lv
     BS_LAUNCH(k_crop_init, gridw, 256, 0, s, dt, lab.as<uint32_t>(), d_fbase, fflag.as<uint8_t>(), lv.as<uint32_t>());
     BS_LAUNCH(k_crop_union, gridw, 256, 0, s, dt, lab.as<uint32_t>(), lv.as<uint32_t>());
@@ -1751,7 +1757,7 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     BS_TRY(blk_first.alloc(4 * blks.size(), s));
     BS_LAUNCH(k_blk_first, cdiv(blks.size(), 256), 256, 0, s, d_blks.as<BlkDev>(), (int)blks.size(), bits.as<uint32_t>(),
               wscan.as<uint32_t>(), blk_first.as<uint32_t>());
-    BS_LAUNCH(k_finalize, gridw, 256, 0, s, dt, d_blks.as<BlkDev>(), lab.as<uint32_t>(), lv.as<uint32_t>(), d_fbase,
+    BS_LAUNCH(k_finalize, gridf, 256, 0, s, dt, d_blks.as<BlkDev>(), lab.as<uint32_t>(), lv.as<uint32_t>(), d_fbase,
               fflag.as<uint8_t>(), fmin.as<uint32_t>(), bits.as<uint32_t>(), wscan.as<uint32_t>(), blk_first.as<uint32_t>(),
               P.nvox_block, cfg.roi_offset[0] + (cfg.win_z > 0 ? cfg.win_z0 : 0), cfg.roi_offset[1], cfg.roi_offset[2],
               cfg.roi_shape[1], cfg.roi_shape[2], frags_out, ncnt.as<uint32_t>(), nsum.as<unsigned long long>());
