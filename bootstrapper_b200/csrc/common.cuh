@@ -178,16 +178,38 @@ __device__ __forceinline__ void unravel3(long long i, int W, int H, int &x, int 
     z = (int)zz;
 }
 
-// fragment id -> dense node index (blocks ascending by id, ids 1..n per block + block_id * prod(block_size))
+// fragment id -> dense node index (blocks ascending by id, ids 1..n per block + block_id * prod(block_size)).
+// The division by the run-constant prod(block_size) is a multiply-high with a precomputed magic number
+// (round-up method, exact for every 64-bit id): q = (((n - mulhi(m, n)) >> 1) + mulhi(m, n)) >> sh.
 struct IdMap {
     const uint32_t *cantor2dense;   // block_id -> dense base of that block (0xFFFFFFFF if unknown)
     long long max_block_id;
     long long nvox_block;
+    unsigned long long magic;       // 0: nvox_block is a power of two, divide by shifting `sh`
+    int sh;
+    void set_divisor(long long d) {
+        nvox_block = d;
+        unsigned long long ud = (unsigned long long)d;
+        int l = 0;
+        while ((1ull << l) < ud && l < 63) l++;
+        if ((1ull << l) == ud) {
+            magic = 0;
+            sh = l;
+        } else {
+            unsigned __int128 num = ((unsigned __int128)((1ull << l) - ud)) << 64;
+            magic = (unsigned long long)(num / ud) + 1;
+            sh = l - 1;
+        }
+    }
 };
+__device__ __forceinline__ uint64_t id_block(const IdMap &m, uint64_t id) {
+    if (m.magic == 0) return id >> m.sh;
+    uint64_t t = __umul64hi(m.magic, id);
+    return (((id - t) >> 1) + t) >> m.sh;
+}
 __device__ __forceinline__ uint32_t id_to_dense(const IdMap &m, uint64_t id) {
     if (id == 0) return 0xFFFFFFFFu;
-    // floor(id / nvox) through a round-towards-zero double division: exact for id < 2^53
-    uint64_t bid = (uint64_t)__double2ull_rz(__ddiv_rz((double)id, (double)m.nvox_block));
+    uint64_t bid = id_block(m, id);
     if ((long long)bid > m.max_block_id) return 0xFFFFFFFFu;
     uint32_t base = m.cantor2dense[bid];
     if (base == 0xFFFFFFFFu) return 0xFFFFFFFFu;

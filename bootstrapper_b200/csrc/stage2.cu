@@ -394,7 +394,7 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
     IdMap idm;
     idm.cantor2dense = d_c2d.as<uint32_t>();
     idm.max_block_id = max_bid;
-    idm.nvox_block = P.nvox_block;
+    idm.set_divisor(P.nvox_block);
     const S2Blk *db = d_blks.as<S2Blk>();
 
     g_prof.mark("s2.rag", s);

@@ -122,7 +122,7 @@ int relabel_dense(Plan &P, const uint64_t *frags, int64_t n, const uint64_t *con
     IdMap idm;
     idm.cantor2dense = d_c2d.as<uint32_t>();
     idm.max_block_id = max_bid;
-    idm.nvox_block = P.nvox_block;
+    idm.set_divisor(P.nvox_block);
     RelabelSet rs;
     rs.T = T;
     for (int t = 0; t < 8; t++) {
