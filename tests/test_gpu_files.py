@@ -62,3 +62,63 @@ def test_waterz_pipeline_files(tmp_path):
     assert np.array_equal(fr.read(), ref["fragments"])
     nodes, edges, scores = open_db(cfg["db"]).read_graph()
     assert {tuple(e) for e in edges.tolist()} == set(ref["rag"].edges)
+
+
+def _write_affs(tmp_path, affs, vs, off):
+    from bootstrapper_b200 import zarrio
+    store = str(tmp_path / "v.zarr")
+    a = zarrio.prepare_ds(os.path.join(store, "affs"), affs.shape, off, vs, affs.dtype, chunk_shape=(3, 6, 60, 60),
+                          axis_names=["c^", "z", "y", "x"], units=["nm"] * 3, compressor={"id": "zlib", "level": 1})
+    a.write(affs)
+    return store
+
+
+def test_simple_watershed_files(tmp_path):
+    """non-blockwise `bs segment --ws`: dataset names, attrs and contents of the single-shot path
+    (post/watershed.py:206-354; names per post/naming.py)."""
+    import toml
+    from bootstrapper_b200 import segment, zarrio
+    from bootstrapper_b200.synth import synth_affs
+    from oracle.blockwise import simple_watershed as ref_simple
+    from test_gpu_parity import _same_partition
+    affs = synth_affs((10, 120, 120), seed=12)
+    vs, off = (40, 4, 4), (0, 8, 8)
+    store = _write_affs(tmp_path, affs, vs, off)
+    cfg = dict(affs_dataset=os.path.join(store, "affs"), fragments_dataset=os.path.join(store, "post/fragments"),
+               seg_dataset_prefix=os.path.join(store, "post/segmentations"), ws_params=dict(thresholds=[0.3, 0.6]))
+    p = tmp_path / "seg.toml"
+    p.write_text(toml.dumps(cfg))
+    segment.run_segmentation(str(p), "ws")
+    ref = ref_simple(affs, dict(thresholds=[0.3, 0.6]), seed_tie="index", stats_mode="canonical")
+    fr = zarrio.open_ds(os.path.join(store, "post/fragments", "xy--msd10"))
+    assert fr.offset == off and fr.voxel_size == vs and fr.dtype == np.uint64
+    assert fr.attrs["bs_params"]["method"] == "ws" and fr.attrs["bs_params"]["blockwise"] is False
+    assert _same_partition(fr.read(), ref["fragments"])
+    for thr in (0.3, 0.6):
+        seg = zarrio.open_ds(os.path.join(store, "post/segmentations", f"mfmean--t{thr:g}--xy--msd10"))
+        assert _same_partition(seg.read(), ref["segs"][thr])
+        assert seg.attrs["bs_params"]["threshold"] == thr
+
+
+def test_cc_files(tmp_path):
+    """`bs segment --cc` (post/connected_components.py:15-127): fragments + debris-filtered segmentation datasets."""
+    import toml
+    from bootstrapper_b200 import segment, zarrio
+    from bootstrapper_b200.synth import synth_affs
+    from oracle import cc as occ
+    affs = synth_affs((10, 120, 120), seed=13)
+    vs, off = (40, 4, 4), (40, 0, 4)
+    store = _write_affs(tmp_path, affs, vs, off)
+    cfg = dict(affs_dataset=os.path.join(store, "affs"), fragments_dataset=os.path.join(store, "post/fragments"),
+               seg_dataset_prefix=os.path.join(store, "post/segmentations"), cc_params=dict(threshold=0.6, remove_debris=30))
+    p = tmp_path / "seg.toml"
+    p.write_text(toml.dumps(cfg))
+    segment.run_segmentation(str(p), "cc")
+    rf, rs = occ.cc_affs(affs, 0.6, 30)
+    fr = zarrio.open_ds(os.path.join(store, "post/fragments", "t0.6"))
+    assert fr.offset == off and fr.attrs["bs_params"]["method"] == "cc"
+    assert np.array_equal(fr.read(), rf.astype(np.uint64))
+    seg = zarrio.open_ds(os.path.join(store, "post/segmentations", "t0.6--rd30"))
+    assert np.array_equal(seg.read(), rs.astype(np.uint64))
+    with pytest.raises(ValueError):      # segment.py:115-116: "Blockwise connected components is not supported!"
+        segment.run_segmentation(str(p), "cc", blockwise=True)
