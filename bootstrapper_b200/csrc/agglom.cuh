@@ -49,6 +49,14 @@ int agglom_global_launch(const AggBlk *blks, const int *list, int nlist, const A
 int agglom_smem_launch(const AggBlk *blks, const int *list, int nlist, const AggArrays &A, float threshold, int keep_cheaper,
                        bool u8, bool sum64, uint32_t Ecap, uint32_t Ncap, cudaStream_t s);
 
+// agglom_par.cu: the same agglomeration by a CTA of several warps that commits independent merges of a batch together
+size_t agglom_par_bytes(uint32_t Ecap, uint32_t Ncap, bool sum64, int idx);
+size_t agglom_par_static_smem();
+int agglom_par_launch(const AggBlk *blks, const int *list, int nlist, const AggArrays &A, float threshold, int keep_cheaper,
+                      bool u8, bool sum64, uint32_t Ecap, uint32_t Ncap, cudaStream_t s);
+int agglom_par_global_launch(const AggBlk *blks, const int *list, int nlist, const AggArrays &A, float threshold, int keep_cheaper,
+                             bool u8, unsigned char *work, const unsigned long long *woff, cudaStream_t s);
+
 // agglom_pq.cu: waterz with the non-discretised queue (single-shot ws path) on one region graph.
 struct PqRequest {
     const float *thresholds;   // host, ascending

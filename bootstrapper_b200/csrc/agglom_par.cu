@@ -1,0 +1,679 @@
+// waterz BinQueue<256> agglomeration of one daisy block by a CTA of PNW warps that commits several merges per round.
+//
+// Same result as the single-warp kernel (agglom_smem.cu), to the bit: the pop order of the FIFO bin queue is
+// emulated exactly, but a whole batch of queue entries is resolved per round and the merges found in it run
+// concurrently, one warp each.  A prefix of the batch may commit together when processing it entry by entry would
+// give the same state:
+//   * an entry (stale or merge) that shares a cluster with an earlier merge of the batch would see a changed edge
+//     (re-keyed, re-scored or deleted)                                          -> the batch is cut before it;
+//   * two merges whose clusters are joined by an edge would both rewrite that edge -> the later one waits;
+//   * everything else commutes: merges touch only edges incident to their own two clusters, stale entries only
+//     their own edge, and clocks / merge numbers are assigned in queue order.
+// Round = A (warp 0: pick the lowest bin, classify up to PQCH entries, cut at the first stop / re-queue into a lower
+// bin / cluster conflict)  ->  B (one warp per candidate merge: read-only walk of both incidence lists, neighbours of
+// the absorbed cluster into a warp-private hash, adjacency conflicts with the other candidates)  ->  C (warp 0:
+// commit the stale / dead entries of the final prefix, advance the queue)  ||  D (candidate warps: resolve common
+// neighbours against the private hash, splice lists, union, merge-tree node).
+// A merge whose absorbed cluster has more than PBIG neighbours runs alone on the node-mark arrays.
+#include <type_traits>
+
+#include "agglom.cuh"
+
+namespace bs {
+
+static constexpr uint32_t NONE32 = 0xFFFFFFFFu;
+static constexpr unsigned FULL = 0xFFFFFFFFu;
+static constexpr int PQCH = 16;      // entries per queue chunk = batch size of a round
+static constexpr int PNW = 4;        // warps per CTA = merges per round
+static constexpr int PHASH = 128;    // slots of a warp's private neighbour hash
+static constexpr int PBIG = 80;      // neighbours of the absorbed cluster the private hash takes
+static constexpr int NBINS = 256;
+
+__host__ __device__ static inline uint32_t par_qc(uint32_t Ecap) { return Ecap / PQCH + 2 * NBINS + 32; }
+
+struct ParCtl {
+    uint32_t ncand, cut1, cut2, clock0, nmerge0;
+    int exit_, fail;
+    uint32_t ce[PNW], ca[PNW], cb[PNW], clane[PNW];
+    uint32_t hkey[PNW][PHASH], hval[PNW][PHASH];
+};
+
+size_t agglom_par_bytes(uint32_t Ecap, uint32_t Ncap, bool sum64, int idx) {
+    size_t b = 0;
+    b += (size_t)(sum64 ? 8 : 4) * Ecap;   // esum
+    b += 4 * (size_t)Ecap * 2;             // escore, ecnt
+    b += 32;                               // occupancy bitmap
+    b += (size_t)idx * Ecap * 5;           // eu, ev, etd, anext[2E]
+    const size_t QC = par_qc(Ecap);
+    b += (size_t)idx * (QC * PQCH + QC);   // queue chunks + chunk links
+    b += (size_t)idx * Ncap * 7;           // ufp, stamp, ahead, tnode, clevel, mark, markgen
+    b += (size_t)idx * NBINS * 4;          // bin head chunk / tail chunk / head offset / tail fill
+    return (b + 255) & ~(size_t)255;
+}
+size_t agglom_par_static_smem() { return sizeof(ParCtl) + 64; }
+
+template <typename IdxT>
+__device__ __forceinline__ uint32_t pfind(IdxT *ufp, uint32_t x) {
+    // path halving; concurrent lanes / warps only ever write ancestors
+    for (;;) {
+        uint32_t p = ufp[x];
+        if (p == x) return x;
+        uint32_t gp = ufp[p];
+        if (gp == p) return p;
+        ufp[x] = (IdxT)gp;
+        x = gp;
+    }
+}
+
+template <bool U8, typename SumT, typename IdxT, bool SMEM>
+__global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__restrict__ blks, const int *__restrict__ list,
+                                                              AggArrays A, float threshold, int keep_cheaper, uint32_t Ecap_,
+                                                              uint32_t Ncap_, unsigned char *__restrict__ gwork,
+                                                              const unsigned long long *__restrict__ gwoff) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ ParCtl C;
+    constexpr uint32_t N16 = (uint32_t)(IdxT)~(IdxT)0;                 // "none" in the index type
+    constexpr uint32_t DEADBIT = 1u << (8 * sizeof(IdxT) - 1);        // etd = time | dead flag
+    const int bi = list[blockIdx.x];
+    const AggBlk B = blks[bi];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t E = B.E, nc = B.nv;
+    const uint32_t Ecap = SMEM ? Ecap_ : ((max(E, 8u) + 7u) & ~7u), Ncap = SMEM ? Ncap_ : ((max(nc, 8u) + 7u) & ~7u);
+    const uint32_t QC = par_qc(Ecap);
+    unsigned char *work = SMEM ? smraw : gwork + gwoff[blockIdx.x];
+
+    SumT *esum = (SumT *)work;
+    float *escore = (float *)(esum + Ecap);
+    uint32_t *ecnt = (uint32_t *)(escore + Ecap);
+    uint32_t *occ = ecnt + Ecap;
+    IdxT *eu = (IdxT *)(occ + 8);
+    IdxT *ev = eu + Ecap, *etd = ev + Ecap, *anext = etd + Ecap;
+    IdxT *qent = anext + 2 * Ecap;
+    IdxT *qcnext = qent + QC * PQCH;
+    IdxT *ufp = qcnext + QC, *stamp = ufp + Ncap, *ahead = stamp + Ncap, *tnode = ahead + Ncap, *clevel = tnode + Ncap,
+         *mark = clevel + Ncap, *markgen = mark + Ncap;
+    IdxT *bhc = markgen + Ncap, *btc = bhc + NBINS, *bho = btc + NBINS, *btf = bho + NBINS;
+
+    const uint32_t *geu = A.eu + B.ebase, *gev = A.ev + B.ebase, *gcnt = A.ecnt + B.ebase;
+    const unsigned long long *gsum = A.esum + B.ebase;
+    uint32_t *tparent = A.tparent + 2 * (size_t)B.vbase, *tlevel = A.tlevel + 2 * (size_t)B.vbase;
+    float *tscore = A.tscore + 2 * (size_t)B.vbase;
+    uint32_t *ha = A.ha + B.vbase, *hb = A.hb + B.vbase;
+    float *hs = A.hs + B.vbase;
+
+    // ---- load the block's graph (all warps)
+    for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
+        ufp[i] = (IdxT)i;
+        stamp[i] = 0;
+        ahead[i] = N16;
+        tnode[i] = (IdxT)i;
+        clevel[i] = 0;
+        markgen[i] = 0;
+        tparent[i] = NONE32;
+        tlevel[i] = 0;
+        tscore[i] = 0.f;
+    }
+    for (int i = threadIdx.x; i < NBINS; i += blockDim.x) {
+        bhc[i] = N16;
+        btc[i] = N16;
+        bho[i] = 0;
+        btf[i] = 0;
+    }
+    if (threadIdx.x < 8) occ[threadIdx.x] = 0;
+    for (uint32_t e = threadIdx.x; e < E; e += blockDim.x) {
+        uint32_t u = geu[e], v = gev[e];
+        SumT s = (SumT)gsum[e];
+        uint32_t c = gcnt[e];
+        eu[e] = (IdxT)u;
+        ev[e] = (IdxT)v;
+        esum[e] = s;
+        ecnt[e] = c;
+        escore[e] = edge_score<U8>((unsigned long long)s, c);
+        etd[e] = 0;
+    }
+    if (threadIdx.x == 0) {
+        C.exit_ = 0;
+        C.fail = 0;
+        C.ncand = 0;
+    }
+    __syncthreads();
+
+    // warp 0 owns the queue; its replicated (uniform) state lives in registers
+    uint32_t q_bump = 0, q_free = N16;
+    bool fail = false;
+    if (warp == 0) {
+        // incidence lists (order is irrelevant): lanes that share a node chain their half-edges
+        for (uint32_t e0 = 0; e0 < E; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            const bool v = e < E;
+            const unsigned act = __ballot_sync(FULL, v);
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                uint32_t node = 0;
+                unsigned peers = 0;
+                if (v) {
+                    node = side ? ev[e] : eu[e];
+                    peers = __match_any_sync(act, node);
+                    const unsigned higher = peers & ~((2u << lane) - 1u);
+                    const uint32_t nxt = higher ? 2 * (e0 + (__ffs(higher) - 1)) + side : (uint32_t)ahead[node];
+                    anext[2 * e + side] = (IdxT)nxt;
+                }
+                __syncwarp();   // the old heads are read before any leader replaces them
+                if (v && lane == __ffs(peers) - 1) ahead[node] = (IdxT)(2 * e + side);
+                __syncwarp();
+            }
+        }
+        // initial queue: edges in creation order, placed by a counting pass
+        for (uint32_t e0 = 0; e0 < E; e0 += 32) {
+            uint32_t e = e0 + lane;
+            bool v = e < E;
+            int bin = v ? score_bin(escore[e], NBINS) : -1;
+            unsigned act = __ballot_sync(FULL, v);
+            if (v) {
+                unsigned peers = __match_any_sync(act, bin);
+                if (lane == __ffs(peers) - 1) btf[bin] = (IdxT)(btf[bin] + __popc(peers));
+            }
+            __syncwarp();
+        }
+        {
+            uint32_t cnt[8], nch[8], loc = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                cnt[j] = btf[lane * 8 + j];
+                nch[j] = (cnt[j] + PQCH - 1) / PQCH;
+                loc += nch[j];
+            }
+            uint32_t incl = loc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            q_bump = __shfl_sync(FULL, incl, 31);
+            uint32_t cs = incl - loc;
+            uint32_t bits = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                int bin = lane * 8 + j;
+                if (cnt[j]) {
+                    bhc[bin] = (IdxT)cs;
+                    btc[bin] = (IdxT)(cs + nch[j] - 1);
+                    btf[bin] = (IdxT)(cnt[j] - PQCH * (nch[j] - 1));
+                    for (uint32_t c = 0; c < nch[j]; c++) qcnext[cs + c] = (IdxT)(c + 1 < nch[j] ? cs + c + 1 : N16);
+                    bits |= 1u << j;
+                }
+                cs += nch[j];
+            }
+            uint32_t b0 = __shfl_sync(FULL, bits, (lane & 7) * 4 + 0), b1 = __shfl_sync(FULL, bits, (lane & 7) * 4 + 1),
+                     b2 = __shfl_sync(FULL, bits, (lane & 7) * 4 + 2), b3 = __shfl_sync(FULL, bits, (lane & 7) * 4 + 3);
+            if (lane < 8) occ[lane] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+        }
+        fail = q_bump > QC;
+        __syncwarp();
+        if (!fail)
+            for (uint32_t e0 = 0; e0 < E; e0 += 32) {
+                uint32_t e = e0 + lane;
+                bool v = e < E;
+                int bin = v ? score_bin(escore[e], NBINS) : -1;
+                unsigned act = __ballot_sync(FULL, v);
+                unsigned peers = 0;
+                uint32_t base = 0;
+                if (v) {
+                    peers = __match_any_sync(act, bin);
+                    base = bho[bin];
+                }
+                __syncwarp();
+                if (v) {
+                    uint32_t p = base + __popc(peers & lanemask_lt());
+                    qent[((uint32_t)bhc[bin] + p / PQCH) * PQCH + (p % PQCH)] = (IdxT)e;
+                    if (lane == __ffs(peers) - 1) bho[bin] = (IdxT)(base + __popc(peers));
+                }
+                __syncwarp();
+            }
+        for (int i = lane; i < NBINS; i += 32) bho[i] = 0;
+        __syncwarp();
+    }
+    __syncthreads();
+
+    uint32_t n_pops = 0, n_stale = 0, n_dead = 0, n_iter = 0, n_chunk = 0, n_append = 0;
+
+    auto alloc_chunk = [&]() -> uint32_t {
+        uint32_t c;
+        if (q_free != N16) {
+            c = q_free;
+            q_free = qcnext[c];
+        } else {
+            c = q_bump++;
+            if (c >= QC) {
+                fail = true;
+                c = 0;
+            }
+        }
+        return c;
+    };
+    // order-preserving (lane order) append of edge `e` to bin `bin` for lanes with `valid` (at most PQCH lanes); warp 0
+    auto bin_append = [&](bool valid, int bin, uint32_t e) {
+        for (;;) {
+            int mine = valid ? bin : 0x7fffffff;
+            int Bn = __reduce_min_sync(FULL, mine);
+            if (Bn == 0x7fffffff) break;
+            n_append++;
+            bool c = valid && bin == Bn;
+            unsigned m = __ballot_sync(FULL, c);
+            uint32_t total = __popc(m), off = __popc(m & lanemask_lt());
+            uint32_t tc = btc[Bn];
+            uint32_t tf = tc == N16 ? (uint32_t)PQCH : (uint32_t)btf[Bn];
+            bool need_new = tf + total > (uint32_t)PQCH;
+            uint32_t newc = N16;
+            if (need_new) newc = alloc_chunk();
+            __syncwarp();
+            if (c) {
+                uint32_t pos = tf + off;
+                if (pos < (uint32_t)PQCH)
+                    qent[tc * PQCH + pos] = (IdxT)e;
+                else
+                    qent[newc * PQCH + (pos - PQCH)] = (IdxT)e;
+                valid = false;
+            }
+            if (lane == 0) {
+                if (need_new) {
+                    qcnext[newc] = N16;
+                    if (tc != N16)
+                        qcnext[tc] = (IdxT)newc;
+                    else {
+                        bhc[Bn] = (IdxT)newc;
+                        bho[Bn] = 0;
+                        occ[Bn >> 5] |= 1u << (Bn & 31);
+                    }
+                    btc[Bn] = (IdxT)newc;
+                    btf[Bn] = (IdxT)(tf + total - PQCH);
+                } else {
+                    btf[Bn] = (IdxT)(tf + total);
+                }
+            }
+            __syncwarp();
+        }
+    };
+    // walk an incidence list (one warp): dead entries are unlinked, live ones handed to proc() 32 at a time
+    auto walk = [&](uint32_t &head, uint32_t &tail, auto proc) {
+        uint32_t h = head, prev = N16, guard = 0;
+        for (;;) {
+            int cnt = 0;
+            uint32_t mineh = N16;
+            while (h != N16 && cnt < 32) {
+                if (++guard > 2 * Ecap || h >= 2 * E) {   // a list can never hold more than the 2E half-edges
+                    fail = true;
+                    h = N16;
+                    break;
+                }
+                uint32_t nx = anext[h];
+                bool dead = (etd[h >> 1] & DEADBIT) != 0;
+                if (dead) {
+                    if (prev == N16)
+                        head = nx;
+                    else if (lane == 0)
+                        anext[prev] = (IdxT)nx;
+                } else {
+                    if (lane == cnt) mineh = h;
+                    cnt++;
+                    prev = h;
+                }
+                h = nx;
+            }
+            if (cnt == 0) break;
+            n_chunk++;
+            __syncwarp();
+            proc(mineh);
+            __syncwarp();
+            if (h == N16) break;
+        }
+        tail = prev;
+    };
+
+    uint32_t clock = 0, nmerge = 0;
+    int minbin = 0;
+    uint32_t *hkey = C.hkey[warp], *hval = C.hval[warp];
+    for (;;) {
+        // ================= phase A (warp 0): batch, classification, first cut, candidate merges
+        uint32_t e = 0, ru = 0, rv = 0, k = 0, hc = 0, ho = 0;
+        int cls = 1;   // 0 stop, 1 dead/inactive, 2 stale, 3 merge
+        float newsc = 0.f;
+        int nbin = 0, cb = 0;
+        unsigned mbits = 0;
+        bool act = false;
+        if (warp == 0) {
+            uint32_t w = lane < 8 ? occ[lane] : 0u;
+            if (lane == (minbin >> 5))
+                w &= ~((1u << (minbin & 31)) - 1u);
+            else if (lane < (minbin >> 5))
+                w = 0;
+            unsigned nzb = __ballot_sync(FULL, w != 0);
+            if (!nzb || fail || n_iter > 64u * E + 4096u) {
+                if (nzb) fail = true;
+                if (lane == 0) {
+                    C.exit_ = 1;
+                    C.ncand = 0;
+                    C.cut1 = 0;
+                    C.cut2 = NONE32;
+                }
+            } else {
+                const int wl = __ffs(nzb) - 1;
+                const uint32_t ww = __shfl_sync(FULL, w, wl);
+                cb = wl * 32 + __ffs(ww) - 1;
+                minbin = cb;
+                n_iter++;
+                hc = bhc[cb];
+                ho = bho[cb];
+                const uint32_t tc = btc[cb], tf = btf[cb];
+                k = (hc == tc ? tf : (uint32_t)PQCH) - ho;
+                act = (uint32_t)lane < k;
+                if (act) {
+                    e = qent[hc * PQCH + ho + lane];
+                    float sc = escore[e];
+                    uint32_t td = etd[e];
+                    if (sc >= threshold)
+                        cls = 0;
+                    else if (td & DEADBIT)
+                        cls = 1;
+                    else {
+                        ru = pfind<IdxT>(ufp, eu[e]);
+                        rv = pfind<IdxT>(ufp, ev[e]);
+                        if (stamp[ru] > td || stamp[rv] > td) {
+                            cls = 2;
+                            newsc = edge_score<U8>((unsigned long long)esum[e], ecnt[e]);
+                            nbin = score_bin(newsc, NBINS);
+                        } else
+                            cls = 3;
+                    }
+                }
+                // an entry that shares a cluster with an earlier merge of the batch must wait for it
+                bool conflict = false;
+                for (uint32_t j = 0; j + 1 < k; j++) {
+                    const int cj = __shfl_sync(FULL, cls, j);
+                    const uint32_t uj = __shfl_sync(FULL, ru, j), vj = __shfl_sync(FULL, rv, j);
+                    if (cj == 3 && (uint32_t)lane > j && act && (cls == 2 || cls == 3) &&
+                        (ru == uj || ru == vj || rv == uj || rv == vj))
+                        conflict = true;
+                }
+                mbits = __ballot_sync(FULL, act && cls == 3);
+                const bool over = act && cls == 3 && __popc(mbits & lanemask_lt()) >= PNW;
+                const bool cutf = act && (cls == 0 || (cls == 2 && nbin < cb) || conflict || over);
+                const unsigned cbits = __ballot_sync(FULL, cutf);
+                const uint32_t cut1 = cbits ? (uint32_t)(__ffs(cbits) - 1) : k;
+                const bool cand = act && cls == 3 && (uint32_t)lane < cut1;
+                const unsigned candbits = __ballot_sync(FULL, cand);
+                if (cand) {
+                    const int r = __popc(candbits & lanemask_lt());
+                    C.ce[r] = e;
+                    C.ca[r] = min(ru, rv);
+                    C.cb[r] = max(ru, rv);
+                    C.clane[r] = lane;
+                }
+                if (lane == 0) {
+                    C.ncand = __popc(candbits);
+                    C.cut1 = cut1;
+                    C.cut2 = NONE32;
+                    C.clock0 = clock;
+                    C.nmerge0 = nmerge;
+                }
+                // what stopped the batch (meaningful when the final cut stays at cut1)
+                const bool conf_at = __shfl_sync(FULL, (int)(conflict || over), cut1 & 31) != 0;
+                // keep for phase C: class at cut1 -- 0 stop, 2 re-queue into a lower bin, 4 wait, -1 batch exhausted
+                const int c1 = __shfl_sync(FULL, cls, cut1 & 31);
+                cls = (cls & 0xff) | ((cut1 < k ? (conf_at ? 4 : c1) : 0xff) << 8) | ((int)cut1 << 16);
+            }
+        }
+        __syncthreads();
+        // ================= phase B (candidate warps): read-only walks, private neighbour hash, adjacency conflicts
+        const uint32_t ncand = C.ncand;
+        uint32_t ma = 0, mb = 0, me = 0, head_b = N16, tail_b = N16;
+        bool big = false;
+        if ((uint32_t)warp < ncand) {
+            ma = C.ca[warp], mb = C.cb[warp], me = C.ce[warp];
+            for (int j = lane; j < PHASH; j += 32) hkey[j] = NONE32;
+            __syncwarp();
+            uint32_t deg = 0;
+            auto other_cand = [&](uint32_t x) {
+                for (uint32_t c = 0; c < ncand; c++)
+                    if (c != (uint32_t)warp && (x == C.ca[c] || x == C.cb[c])) atomicMin(&C.cut2, C.clane[max(c, (uint32_t)warp)]);
+            };
+            head_b = ahead[mb];
+            walk(head_b, tail_b, [&](uint32_t h) {
+                bool ins = false;
+                uint32_t x = 0, ne = 0;
+                if (h != N16) {
+                    ne = h >> 1;
+                    if (ne != me) {
+                        uint32_t x1 = pfind<IdxT>(ufp, eu[ne]), x2 = pfind<IdxT>(ufp, ev[ne]);
+                        x = x1 == mb ? x2 : x1;
+                        other_cand(x);
+                        ins = true;
+                    }
+                }
+                const unsigned ib = __ballot_sync(FULL, ins);
+                deg += __popc(ib);
+                if (deg > (uint32_t)PBIG) big = true;
+                if (ins && !big) {
+                    uint32_t s = (x * 2654435761u) >> 25;   // 7 bits
+                    for (;;) {
+                        uint32_t old = atomicCAS(&hkey[s], NONE32, x);
+                        if (old == NONE32) {
+                            hval[s] = ne;
+                            break;
+                        }
+                        s = (s + 1) & (PHASH - 1);
+                    }
+                }
+            });
+            uint32_t head_a = ahead[ma], tail_a = N16;
+            walk(head_a, tail_a, [&](uint32_t h) {
+                if (h != N16) {
+                    uint32_t ae = h >> 1;
+                    if (ae != me) {
+                        uint32_t x1 = pfind<IdxT>(ufp, eu[ae]), x2 = pfind<IdxT>(ufp, ev[ae]);
+                        other_cand(x1 == ma ? x2 : x1);
+                    }
+                }
+            });
+            if (lane == 0) {
+                ahead[ma] = (IdxT)head_a;   // dead entries at the front may have been unlinked
+                ahead[mb] = (IdxT)head_b;
+                if (big) {
+                    // runs alone: first candidate -> everybody else waits, otherwise it waits itself
+                    if (warp == 0) {
+                        if (ncand > 1) atomicMin(&C.cut2, C.clane[1]);
+                    } else
+                        atomicMin(&C.cut2, C.clane[warp]);
+                }
+                if (fail) C.fail = 1;
+            }
+        }
+        __syncthreads();
+        // ================= phase C (warp 0): commit the non-merge entries of the final prefix, advance the queue
+        const uint32_t cut = min(C.cut1, C.cut2);
+        if (warp == 0 && !C.exit_) {
+            const int mycls = cls & 0xff;
+            const uint32_t cut1 = (uint32_t)(cls >> 16);
+            int tcls = (cls >> 8) & 0xff;   // 0 stop, 2 lower, 4 wait, 0xff exhausted
+            if (cut < cut1) tcls = 4;
+            const bool lower_trig = tcls == 2;
+            const bool redo = act && mycls == 2 && ((uint32_t)lane < cut || ((uint32_t)lane == cut && lower_trig));
+            if (redo) {
+                escore[e] = newsc;
+                etd[e] = (IdxT)(clock + __popc(mbits & lanemask_lt()));   // merges committed before this pop
+            }
+            const uint32_t consumed = cut + (lower_trig ? 1u : 0u);
+            const unsigned mcommit = mbits & ((cut >= 32 ? 0u : (1u << cut)) - 1u);
+            n_pops += consumed;
+            n_stale += __popc(__ballot_sync(FULL, redo));
+            n_dead += __popc(__ballot_sync(FULL, act && mycls == 1 && (uint32_t)lane < cut));
+            __syncwarp();
+            bin_append(redo, nbin, e);
+            {
+                const uint32_t ho2 = ho + consumed;
+                const uint32_t tc2 = btc[cb], tf2 = btf[cb];
+                bool freed = false;
+                if (hc == tc2) {
+                    if (ho2 == tf2) {
+                        freed = true;
+                        if (lane == 0) {
+                            bhc[cb] = N16;
+                            btc[cb] = N16;
+                            bho[cb] = 0;
+                            btf[cb] = 0;
+                            occ[cb >> 5] &= ~(1u << (cb & 31));
+                        }
+                    } else if (lane == 0)
+                        bho[cb] = (IdxT)ho2;
+                } else if (ho2 == (uint32_t)PQCH) {
+                    freed = true;
+                    if (lane == 0) {
+                        bhc[cb] = qcnext[hc];
+                        bho[cb] = 0;
+                    }
+                } else if (lane == 0)
+                    bho[cb] = (IdxT)ho2;
+                if (freed) {
+                    if (lane == 0) qcnext[hc] = (IdxT)q_free;
+                    q_free = hc;
+                }
+                __syncwarp();
+            }
+            if (lower_trig) minbin = __shfl_sync(FULL, nbin, cut & 31);
+            const uint32_t nm = __popc(mcommit);
+            clock += nm;
+            nmerge += nm;
+            if (tcls == 0 || fail) {
+                if (lane == 0) C.exit_ = 1;   // stop after this round's merges
+            }
+        }
+        // ================= phase D (candidate warps whose lane lies before the final cut): the merges
+        if ((uint32_t)warp < ncand && C.clane[warp] < cut) {
+            const uint32_t myclock = C.clock0 + warp + 1, mynum = C.nmerge0 + warp;
+            const float msc = escore[me];
+            if (lane == 0) etd[me] = (IdxT)(etd[me] | DEADBIT);
+            __syncwarp();
+            if (big) {
+                // alone in this round: neighbours of the absorbed cluster go through the node marks
+                head_b = ahead[mb];
+                walk(head_b, tail_b, [&](uint32_t h) {
+                    if (h != N16) {
+                        uint32_t ne = h >> 1;
+                        uint32_t x1 = pfind<IdxT>(ufp, eu[ne]), x2 = pfind<IdxT>(ufp, ev[ne]);
+                        uint32_t x = x1 == mb ? x2 : x1;
+                        mark[x] = (IdxT)ne;
+                        markgen[x] = (IdxT)myclock;
+                    }
+                });
+            }
+            uint32_t head_a = ahead[ma], tail_a = N16;
+            walk(head_a, tail_a, [&](uint32_t h) {
+                if (h != N16) {
+                    uint32_t ae = h >> 1;
+                    uint32_t x1 = pfind<IdxT>(ufp, eu[ae]), x2 = pfind<IdxT>(ufp, ev[ae]);
+                    uint32_t x = x1 == ma ? x2 : x1;
+                    uint32_t ne = NONE32;
+                    if (big) {
+                        if (markgen[x] == (IdxT)myclock) ne = mark[x];
+                    } else {
+                        uint32_t s = (x * 2654435761u) >> 25;
+                        for (;;) {
+                            uint32_t kx = hkey[s];
+                            if (kx == x) {
+                                ne = hval[s];
+                                break;
+                            }
+                            if (kx == NONE32) break;
+                            s = (s + 1) & (PHASH - 1);
+                        }
+                    }
+                    if (ne != NONE32) {
+                        if (!keep_cheaper || escore[ne] > escore[ae]) {
+                            esum[ae] += esum[ne];
+                            ecnt[ae] += ecnt[ne];
+                            etd[ne] = (IdxT)(etd[ne] | DEADBIT);
+                        } else {
+                            esum[ne] += esum[ae];
+                            ecnt[ne] += ecnt[ae];
+                            etd[ae] = (IdxT)(etd[ae] | DEADBIT);
+                        }
+                    }
+                }
+            });
+            if (lane == 0) {
+                // b's list: its head may be the (now dead) merged edge -- it is unlinked lazily by a later walk
+                if (head_b != N16) {
+                    if (head_a == N16)
+                        head_a = head_b;
+                    else
+                        anext[tail_a] = (IdxT)head_b;
+                }
+                ahead[ma] = (IdxT)head_a;
+                ufp[mb] = (IdxT)ma;
+                stamp[ma] = (IdxT)myclock;
+                const uint32_t t = nc + mynum, ta = tnode[ma], tbn = tnode[mb];
+                const uint32_t lvl = max((uint32_t)clevel[ma], (uint32_t)clevel[mb]) + 1;
+                tparent[ta] = t;
+                tparent[tbn] = t;
+                tparent[t] = NONE32;
+                tlevel[t] = lvl;
+                tscore[t] = msc;
+                tnode[ma] = (IdxT)t;
+                clevel[ma] = (IdxT)lvl;
+                ha[mynum] = ma;
+                hb[mynum] = mb;
+                hs[mynum] = msc;
+                if (fail) C.fail = 1;
+            }
+        }
+        __syncthreads();
+        if (C.exit_ || C.fail) break;
+    }
+    if (threadIdx.x == 0) {
+        A.nmerges[bi] = nmerge;
+        A.counters[6 * bi + 0] = n_pops;
+        A.counters[6 * bi + 1] = n_stale;
+        A.counters[6 * bi + 2] = n_dead;
+        A.counters[6 * bi + 3] = n_iter;
+        A.counters[6 * bi + 4] = n_chunk;
+        A.counters[6 * bi + 5] = n_append;
+        if (fail || C.fail) atomicExch(A.error, 1u);
+    }
+}
+
+int agglom_par_launch(const AggBlk *blks, const int *list, int nlist, const AggArrays &A, float threshold, int keep_cheaper,
+                      bool u8, bool sum64, uint32_t Ecap, uint32_t Ncap, cudaStream_t s) {
+    if (nlist == 0) return BS_OK;
+    const size_t smem = agglom_par_bytes(Ecap, Ncap, sum64, 2);
+    BS_ARG(smem + agglom_par_static_smem() <= 227 * 1024 && Ecap <= 32760 && Ncap <= 32760 && (Ecap % 8) == 0 && (Ncap % 8) == 0,
+           "agglom_par_launch: block graph does not fit in shared memory");
+#define BS_AGG_PAR(U8_, SumT_)                                                                                             \
+    do {                                                                                                                   \
+        BS_CUDA(cudaFuncSetAttribute(k_agglomerate_par<U8_, SumT_, uint16_t, true>,                                        \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - agglom_par_static_smem()))); \
+        BS_LAUNCH((k_agglomerate_par<U8_, SumT_, uint16_t, true>), nlist, 32 * PNW, smem, s, blks, list, A, threshold,     \
+                  keep_cheaper, Ecap, Ncap, nullptr, nullptr);                                                             \
+    } while (0)
+    if (u8 && !sum64)
+        BS_AGG_PAR(true, uint32_t);
+    else if (u8)
+        BS_AGG_PAR(true, unsigned long long);
+    else
+        BS_AGG_PAR(false, unsigned long long);
+#undef BS_AGG_PAR
+    return BS_OK;
+}
+
+int agglom_par_global_launch(const AggBlk *blks, const int *list, int nlist, const AggArrays &A, float threshold, int keep_cheaper,
+                             bool u8, unsigned char *work, const unsigned long long *woff, cudaStream_t s) {
+    if (nlist == 0) return BS_OK;
+    if (u8)
+        BS_LAUNCH((k_agglomerate_par<true, unsigned long long, uint32_t, false>), nlist, 32 * PNW, 0, s, blks, list, A, threshold,
+                  keep_cheaper, 0u, 0u, work, woff);
+    else
+        BS_LAUNCH((k_agglomerate_par<false, unsigned long long, uint32_t, false>), nlist, 32 * PNW, 0, s, blks, list, A, threshold,
+                  keep_cheaper, 0u, 0u, work, woff);
+    return BS_OK;
+}
+
+}  // namespace bs

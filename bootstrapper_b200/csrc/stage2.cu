@@ -531,12 +531,17 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
         // u8 affinity sums of a whole block fit 32 bits when 3 * 255 * read voxels < 2^32
         if (u8 && 765.0 * hb[i].rs[0] * hb[i].rs[1] * hb[i].rs[2] >= 4294967295.0) sum64 = true;
     }
+    // g_agglom_version: 0 = parallel-merge kernels (shared memory when the block fits, else a global slab),
+    //                    1 = single-warp kernel on global slabs, 2 = single-warp kernel in shared memory when it fits,
+    //                    3 = parallel-merge kernel on global slabs
+    const bool par = g_agglom_version == 0 || g_agglom_version == 3;
     {
-        const size_t limit = 227 * 1024;
+        const size_t limit = 227 * 1024 - (par ? agglom_par_static_smem() : 0);
         for (int i = 0; i < nown; i++) {
             uint32_t Ec = (std::max<uint32_t>(ab[i].E, 8) + 7) & ~7u, Nc = (std::max<uint32_t>(ab[i].nv, 8) + 7) & ~7u;
-            bool fits = g_agglom_version != 1 && Ec <= 32760 && Nc <= 32760 && agglom_smem_bytes(Ec, Nc, sum64) <= limit;
-            if (fits && agglom_smem_bytes(std::max(Emax, Ec), std::max(Nmax, Nc), sum64) <= limit) {
+            auto bytes = [&](uint32_t e_, uint32_t n_) { return par ? agglom_par_bytes(e_, n_, sum64, 2) : agglom_smem_bytes(e_, n_, sum64); };
+            bool fits = (g_agglom_version == 0 || g_agglom_version == 2) && Ec <= 32760 && Nc <= 32760 && bytes(Ec, Nc) <= limit;
+            if (fits && bytes(std::max(Emax, Ec), std::max(Nmax, Nc)) <= limit) {
                 Emax = std::max(Emax, Ec);
                 Nmax = std::max(Nmax, Nc);
                 l_smem.push_back(i);
@@ -550,7 +555,7 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
     for (size_t k = 0; k < l_glob.size(); k++) {
         const AggBlk &a = ab[l_glob[k]];
         uint32_t Ec = (std::max<uint32_t>(a.E, 8) + 7) & ~7u, Nc = (std::max<uint32_t>(a.nv, 8) + 7) & ~7u;
-        h_woff[k + 1] = h_woff[k] + agglom_work_bytes(Ec, Nc, true, 4);
+        h_woff[k + 1] = h_woff[k] + (par ? agglom_par_bytes(Ec, Nc, true, 4) : agglom_work_bytes(Ec, Nc, true, 4));
     }
     const bool any_glob = !l_glob.empty();
 
@@ -586,11 +591,19 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
     A.counters = counters.as<uint32_t>();
     A.error = err.as<uint32_t>();
     BS_ARG(cfg.queue_bins == 256, "stage2: only the BinQueue<256> agglomeration of the blockwise path is implemented");
-    BS_TRY(agglom_smem_launch(d_ab.as<AggBlk>(), d_list.as<int>(), (int)l_smem.size(), A, 1.0f, cfg.keep_cheaper, u8, sum64,
-                              Emax, Nmax, s));
-    if (any_glob)
-        BS_TRY(agglom_global_launch(d_ab.as<AggBlk>(), d_list.as<int>() + l_smem.size(), (int)l_glob.size(), A, 1.0f,
-                                    cfg.keep_cheaper, u8, gwork.as<unsigned char>(), d_woff.as<unsigned long long>(), s));
+    if (par) {
+        BS_TRY(agglom_par_launch(d_ab.as<AggBlk>(), d_list.as<int>(), (int)l_smem.size(), A, 1.0f, cfg.keep_cheaper, u8, sum64, Emax,
+                                 Nmax, s));
+        if (any_glob)
+            BS_TRY(agglom_par_global_launch(d_ab.as<AggBlk>(), d_list.as<int>() + l_smem.size(), (int)l_glob.size(), A, 1.0f,
+                                            cfg.keep_cheaper, u8, gwork.as<unsigned char>(), d_woff.as<unsigned long long>(), s));
+    } else {
+        BS_TRY(agglom_smem_launch(d_ab.as<AggBlk>(), d_list.as<int>(), (int)l_smem.size(), A, 1.0f, cfg.keep_cheaper, u8, sum64,
+                                  Emax, Nmax, s));
+        if (any_glob)
+            BS_TRY(agglom_global_launch(d_ab.as<AggBlk>(), d_list.as<int>() + l_smem.size(), (int)l_glob.size(), A, 1.0f,
+                                        cfg.keep_cheaper, u8, gwork.as<unsigned char>(), d_woff.as<unsigned long long>(), s));
+    }
 
     // ---- merge-tree scores, ownership, output (host sync: number of owned edges)
     g_prof.mark("s2.lca", s);

@@ -183,7 +183,8 @@ int bs_debug_fetch(const bs_plan *p, const char *name, void *dst_host, int64_t *
 int bs_set_debug(int on);
 /* 0 = automatic (shared-memory flood for 2-D tiles when eligible), 1 = force the global-memory flood */
 int bs_set_flood_version(int v);
-/* 0 = automatic (shared-memory agglomeration when a block's graph fits), 1 = force the global-memory kernel */
+/* agglomeration kernel: 0 = automatic (parallel merges; shared memory when a block's graph fits, else a global slab),
+ * 1 = single warp on global slabs, 2 = single warp in shared memory, 3 = parallel merges on global slabs */
 int bs_set_agglom_version(int v);
 /* return the library's cached scratch memory (stream-ordered pool) to the driver */
 int bs_release_scratch(void);

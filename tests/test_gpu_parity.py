@@ -312,15 +312,16 @@ def test_cc_affs_golden_and_oracle():
 
 
 def test_agglomeration_kernels_agree():
-    """the shared-memory agglomeration and its global-memory form (large blocks) give identical graphs"""
+    """every form of the agglomeration kernel (default: parallel merges in shared memory) gives the same graph"""
     from bootstrapper_b200 import native
     from bootstrapper_b200.synth import synth_affs
     affs = synth_affs((20, 160, 160), seed=5)
     block, ctx = (10, 80, 80), (2, 10, 10)
     ref = _oracle(affs, {}, block, ctx)
-    try:
-        native.set_agglom_version(1)
-        r = _run_gpu(affs, {}, block, ctx)
-    finally:
-        native.set_agglom_version(0)
-    _check(r, ref)
+    for version in (1, 2, 3):   # single warp / global slab, single warp / shared memory, parallel merges / global slab
+        try:
+            native.set_agglom_version(version)
+            r = _run_gpu(affs, {}, block, ctx)
+        finally:
+            native.set_agglom_version(0)
+        _check(r, ref)
