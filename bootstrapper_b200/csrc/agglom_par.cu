@@ -24,7 +24,8 @@ namespace bs {
 static constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 static constexpr unsigned FULL = 0xFFFFFFFFu;
 static constexpr int PQCH = 16;      // entries per queue chunk = batch size of a round
-static constexpr int PNW = 4;        // warps per CTA = merges per round
+static constexpr int PNW = 8;        // warps per CTA
+static constexpr int PCAND = PNW / 2; // merges per round: warp c walks the absorbed cluster's list, warp PCAND + c the survivor's
 static constexpr int PHASH = 128;    // slots of a warp's private neighbour hash
 static constexpr int PBIG = 80;      // neighbours of the absorbed cluster the private hash takes
 static constexpr int NBINS = 256;
@@ -34,8 +35,8 @@ __host__ __device__ static inline uint32_t par_qc(uint32_t Ecap) { return Ecap /
 struct ParCtl {
     uint32_t ncand, cut1, cut2, clock0, nmerge0;
     int exit_, fail;
-    uint32_t ce[PNW], ca[PNW], cb[PNW], clane[PNW];
-    uint32_t hkey[PNW][PHASH], hval[PNW][PHASH];
+    uint32_t ce[PCAND], ca[PCAND], cb[PCAND], clane[PCAND], headb[PCAND], big[PCAND];
+    uint32_t hkey[PCAND][PHASH], hval[PCAND][PHASH];
 };
 
 size_t agglom_par_bytes(uint32_t Ecap, uint32_t Ncap, bool sum64, int idx) {
@@ -332,7 +333,6 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
 
     uint32_t clock = 0, nmerge = 0;
     int minbin = 0;
-    uint32_t *hkey = C.hkey[warp], *hval = C.hval[warp];
     for (;;) {
         // ================= phase A (warp 0): batch, classification, first cut, candidate merges
         uint32_t e = 0, ru = 0, rv = 0, k = 0, hc = 0, ho = 0;
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
                         conflict = true;
                 }
                 mbits = __ballot_sync(FULL, act && cls == 3);
-                const bool over = act && cls == 3 && __popc(mbits & lanemask_lt()) >= PNW;
+                const bool over = act && cls == 3 && __popc(mbits & lanemask_lt()) >= PCAND;
                 const bool cutf = act && (cls == 0 || (cls == 2 && nbin < cb) || conflict || over);
                 const unsigned cbits = __ballot_sync(FULL, cutf);
                 const uint32_t cut1 = cbits ? (uint32_t)(__ffs(cbits) - 1) : k;
@@ -424,20 +424,23 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
             }
         }
         __syncthreads();
-        // ================= phase B (candidate warps): read-only walks, private neighbour hash, adjacency conflicts
+        // ================= phase B: read-only walks (warp c: absorbed cluster b -> private neighbour hash; warp PCAND + c:
+        // surviving cluster a, first 32 entries kept in registers), adjacency conflicts with the other candidates
         const uint32_t ncand = C.ncand;
-        uint32_t ma = 0, mb = 0, me = 0, head_b = N16, tail_b = N16;
-        bool big = false;
-        if ((uint32_t)warp < ncand) {
-            ma = C.ca[warp], mb = C.cb[warp], me = C.ce[warp];
+        const int cidx = warp < PCAND ? warp : warp - PCAND;
+        const bool bwalker = warp < PCAND && (uint32_t)cidx < ncand, awalker = warp >= PCAND && (uint32_t)cidx < ncand;
+        uint32_t ma = 0, mb = 0, me = 0, head_a = N16, tail_a = N16, sa_h = N16, sa_x = 0, nbat = 0;
+        uint32_t *hkey = C.hkey[cidx], *hval = C.hval[cidx];
+        auto other_cand = [&](uint32_t x) {
+            for (uint32_t c = 0; c < ncand; c++)
+                if (c != (uint32_t)cidx && (x == C.ca[c] || x == C.cb[c])) atomicMin(&C.cut2, C.clane[max(c, (uint32_t)cidx)]);
+        };
+        if (bwalker || awalker) ma = C.ca[cidx], mb = C.cb[cidx], me = C.ce[cidx];
+        if (bwalker) {
             for (int j = lane; j < PHASH; j += 32) hkey[j] = NONE32;
             __syncwarp();
-            uint32_t deg = 0;
-            auto other_cand = [&](uint32_t x) {
-                for (uint32_t c = 0; c < ncand; c++)
-                    if (c != (uint32_t)warp && (x == C.ca[c] || x == C.cb[c])) atomicMin(&C.cut2, C.clane[max(c, (uint32_t)warp)]);
-            };
-            head_b = ahead[mb];
+            uint32_t deg = 0, head_b = ahead[mb], tail_b = N16;
+            bool big = false;
             walk(head_b, tail_b, [&](uint32_t h) {
                 bool ins = false;
                 uint32_t x = 0, ne = 0;
@@ -465,26 +468,38 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
                     }
                 }
             });
-            uint32_t head_a = ahead[ma], tail_a = N16;
+            if (lane == 0) {
+                ahead[mb] = (IdxT)head_b;   // dead entries at the front may have been unlinked
+                C.headb[cidx] = head_b;
+                C.big[cidx] = big ? 1u : 0u;
+                if (big) {
+                    // runs alone: first candidate -> everybody else waits, otherwise it waits itself
+                    if (cidx == 0) {
+                        if (ncand > 1) atomicMin(&C.cut2, C.clane[1]);
+                    } else
+                        atomicMin(&C.cut2, C.clane[cidx]);
+                }
+                if (fail) C.fail = 1;
+            }
+        }
+        if (awalker) {
+            head_a = ahead[ma];
             walk(head_a, tail_a, [&](uint32_t h) {
+                uint32_t x = 0;
                 if (h != N16) {
                     uint32_t ae = h >> 1;
                     if (ae != me) {
                         uint32_t x1 = pfind<IdxT>(ufp, eu[ae]), x2 = pfind<IdxT>(ufp, ev[ae]);
-                        other_cand(x1 == ma ? x2 : x1);
-                    }
+                        x = x1 == ma ? x2 : x1;
+                        other_cand(x);
+                    } else
+                        h = N16;
                 }
+                if (nbat == 0) sa_h = h, sa_x = x;
+                nbat++;
             });
             if (lane == 0) {
-                ahead[ma] = (IdxT)head_a;   // dead entries at the front may have been unlinked
-                ahead[mb] = (IdxT)head_b;
-                if (big) {
-                    // runs alone: first candidate -> everybody else waits, otherwise it waits itself
-                    if (warp == 0) {
-                        if (ncand > 1) atomicMin(&C.cut2, C.clane[1]);
-                    } else
-                        atomicMin(&C.cut2, C.clane[warp]);
-                }
+                ahead[ma] = (IdxT)head_a;
                 if (fail) C.fail = 1;
             }
         }
@@ -547,14 +562,45 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
                 if (lane == 0) C.exit_ = 1;   // stop after this round's merges
             }
         }
-        // ================= phase D (candidate warps whose lane lies before the final cut): the merges
-        if ((uint32_t)warp < ncand && C.clane[warp] < cut) {
-            const uint32_t myclock = C.clock0 + warp + 1, mynum = C.nmerge0 + warp;
+        // ================= phase D (the a-walkers of candidates before the final cut): the merges
+        if (awalker && C.clane[cidx] < cut) {
+            const uint32_t myclock = C.clock0 + cidx + 1, mynum = C.nmerge0 + cidx;
             const float msc = escore[me];
+            const bool big = C.big[cidx] != 0;
+            uint32_t head_b = C.headb[cidx];
             if (lane == 0) etd[me] = (IdxT)(etd[me] | DEADBIT);
             __syncwarp();
+            auto resolve = [&](uint32_t ae, uint32_t x) {
+                uint32_t ne = NONE32;
+                if (big) {
+                    if (markgen[x] == (IdxT)myclock) ne = mark[x];
+                } else {
+                    uint32_t s = (x * 2654435761u) >> 25;
+                    for (;;) {
+                        uint32_t kx = hkey[s];
+                        if (kx == x) {
+                            ne = hval[s];
+                            break;
+                        }
+                        if (kx == NONE32) break;
+                        s = (s + 1) & (PHASH - 1);
+                    }
+                }
+                if (ne != NONE32) {
+                    if (!keep_cheaper || escore[ne] > escore[ae]) {
+                        esum[ae] += esum[ne];
+                        ecnt[ae] += ecnt[ne];
+                        etd[ne] = (IdxT)(etd[ne] | DEADBIT);
+                    } else {
+                        esum[ne] += esum[ae];
+                        ecnt[ne] += ecnt[ae];
+                        etd[ae] = (IdxT)(etd[ae] | DEADBIT);
+                    }
+                }
+            };
             if (big) {
                 // alone in this round: neighbours of the absorbed cluster go through the node marks
+                uint32_t tail_b = N16;
                 head_b = ahead[mb];
                 walk(head_b, tail_b, [&](uint32_t h) {
                     if (h != N16) {
@@ -566,42 +612,22 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
                     }
                 });
             }
-            uint32_t head_a = ahead[ma], tail_a = N16;
-            walk(head_a, tail_a, [&](uint32_t h) {
-                if (h != N16) {
-                    uint32_t ae = h >> 1;
-                    uint32_t x1 = pfind<IdxT>(ufp, eu[ae]), x2 = pfind<IdxT>(ufp, ev[ae]);
-                    uint32_t x = x1 == ma ? x2 : x1;
-                    uint32_t ne = NONE32;
-                    if (big) {
-                        if (markgen[x] == (IdxT)myclock) ne = mark[x];
-                    } else {
-                        uint32_t s = (x * 2654435761u) >> 25;
-                        for (;;) {
-                            uint32_t kx = hkey[s];
-                            if (kx == x) {
-                                ne = hval[s];
-                                break;
-                            }
-                            if (kx == NONE32) break;
-                            s = (s + 1) & (PHASH - 1);
-                        }
+            if (nbat <= 1) {
+                // the survivor's whole list sits in registers since phase B (its clusters did not change since)
+                if (sa_h != N16) resolve(sa_h >> 1, sa_x);
+                __syncwarp();
+            } else {
+                head_a = ahead[ma];
+                walk(head_a, tail_a, [&](uint32_t h) {
+                    if (h != N16) {
+                        uint32_t ae = h >> 1;
+                        uint32_t x1 = pfind<IdxT>(ufp, eu[ae]), x2 = pfind<IdxT>(ufp, ev[ae]);
+                        resolve(ae, x1 == ma ? x2 : x1);
                     }
-                    if (ne != NONE32) {
-                        if (!keep_cheaper || escore[ne] > escore[ae]) {
-                            esum[ae] += esum[ne];
-                            ecnt[ae] += ecnt[ne];
-                            etd[ne] = (IdxT)(etd[ne] | DEADBIT);
-                        } else {
-                            esum[ne] += esum[ae];
-                            ecnt[ne] += ecnt[ae];
-                            etd[ae] = (IdxT)(etd[ae] | DEADBIT);
-                        }
-                    }
-                }
-            });
+                });
+            }
             if (lane == 0) {
-                // b's list: its head may be the (now dead) merged edge -- it is unlinked lazily by a later walk
+                // dead entries (the merged edge among them) stay linked until a later walk meets them
                 if (head_b != N16) {
                     if (head_a == N16)
                         head_a = head_b;
