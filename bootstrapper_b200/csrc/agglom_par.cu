@@ -24,11 +24,12 @@ namespace bs {
 static constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 static constexpr unsigned FULL = 0xFFFFFFFFu;
 static constexpr int PQCH = 16;      // entries per queue chunk = batch size of a round
-static constexpr int PNW = 8;        // warps per CTA
+static constexpr int PNW = 16;       // warps per CTA
 static constexpr int PCAND = PNW / 2; // merges per round: warp c walks the absorbed cluster's list, warp PCAND + c the survivor's
 static constexpr int PHASH = 128;    // slots of a warp's private neighbour hash
 static constexpr int PBIG = 80;      // neighbours of the absorbed cluster the private hash takes
 static constexpr int NBINS = 256;
+static_assert(PQCH == 16, "the conflict match packs the two endpoint slots of a 16-entry batch into one warp");
 
 __host__ __device__ static inline uint32_t par_qc(uint32_t Ecap) { return Ecap / PQCH + 2 * NBINS + 32; }
 
@@ -386,14 +387,20 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
                             cls = 3;
                     }
                 }
-                // an entry that shares a cluster with an earlier merge of the batch must wait for it
+                // an entry that shares a cluster with an earlier merge of the batch must wait for it.  One match over 32
+                // slots: slot i holds ru of entry i, slot 16 + i its rv (a batch has at most PQCH = 16 entries).
                 bool conflict = false;
-                for (uint32_t j = 0; j + 1 < k; j++) {
-                    const int cj = __shfl_sync(FULL, cls, j);
-                    const uint32_t uj = __shfl_sync(FULL, ru, j), vj = __shfl_sync(FULL, rv, j);
-                    if (cj == 3 && (uint32_t)lane > j && act && (cls == 2 || cls == 3) &&
-                        (ru == uj || ru == vj || rv == uj || rv == vj))
-                        conflict = true;
+                {
+                    const uint32_t rv_up = __shfl_sync(FULL, rv, lane & 15);
+                    const int cls_up = __shfl_sync(FULL, cls, lane & 15);
+                    const bool act_up = __shfl_sync(FULL, (int)act, lane & 15) != 0;
+                    const bool slot_ok = lane < 16 ? (act && (cls == 2 || cls == 3)) : (act_up && (cls_up == 2 || cls_up == 3));
+                    const uint32_t key = slot_ok ? (lane < 16 ? ru : rv_up) : (0xFFFF0000u | (uint32_t)lane);
+                    const unsigned mm = __match_any_sync(FULL, key);
+                    const unsigned mv = __shfl_sync(FULL, mm, (lane + 16) & 31);
+                    const unsigned m16 = __ballot_sync(FULL, act && cls == 3) & 0xFFFFu;
+                    const unsigned lower = (1u << (lane & 15)) - 1u;
+                    conflict = lane < 16 && slot_ok && ((mm | mv) & (m16 | (m16 << 16)) & (lower | (lower << 16))) != 0;
                 }
                 mbits = __ballot_sync(FULL, act && cls == 3);
                 const bool over = act && cls == 3 && __popc(mbits & lanemask_lt()) >= PCAND;
