@@ -27,6 +27,7 @@ static constexpr int PQCH = 16;      // entries per queue chunk = batch size of 
 static constexpr int PNW = 16;       // warps per CTA
 static constexpr int PCAND = PNW / 2; // merges per round: warp c walks the absorbed cluster's list, warp PCAND + c the survivor's
 static constexpr int PHASH = 128;    // slots of a warp's private neighbour hash
+static constexpr int PFILT = 64;     // slots of the round's cluster -> candidate table (at most 2 * PCAND entries)
 static constexpr int PBIG = 80;      // neighbours of the absorbed cluster the private hash takes
 static constexpr int NBINS = 256;
 static_assert(PQCH == 16, "the conflict match packs the two endpoint slots of a 16-entry batch into one warp");
@@ -38,6 +39,7 @@ struct ParCtl {
     int exit_, fail;
     uint32_t ce[PCAND], ca[PCAND], cb[PCAND], clane[PCAND], headb[PCAND], big[PCAND];
     uint32_t hkey[PCAND][PHASH], hval[PCAND][PHASH];
+    uint32_t fkey[PFILT], fval[PFILT];   // cluster -> candidate index of this round's merges (open addressing)
 };
 
 size_t agglom_par_bytes(uint32_t Ecap, uint32_t Ncap, bool sum64, int idx) {
@@ -334,6 +336,9 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
 
     uint32_t clock = 0, nmerge = 0;
     int minbin = 0;
+#ifdef BS_PROBE
+    long long tA = 0, tB = 0, tC = 0, tD = 0, t0 = clock64();
+#endif
     for (;;) {
         // ================= phase A (warp 0): batch, classification, first cut, candidate merges
         uint32_t e = 0, ru = 0, rv = 0, k = 0, hc = 0, ho = 0;
@@ -366,10 +371,14 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
                 hc = bhc[cb];
                 ho = bho[cb];
                 const uint32_t tc = btc[cb], tf = btf[cb];
-                k = (hc == tc ? tf : (uint32_t)PQCH) - ho;
+                // up to PQCH entries: the rest of the head chunk and, if the bin goes on, the start of the next chunk
+                const uint32_t k1 = (hc == tc ? tf : (uint32_t)PQCH) - ho;
+                const uint32_t nx = hc == tc ? N16 : (uint32_t)qcnext[hc];
+                const uint32_t k2 = hc == tc ? 0u : min((uint32_t)PQCH - k1, nx == tc ? tf : (uint32_t)PQCH);
+                k = k1 + k2;
                 act = (uint32_t)lane < k;
                 if (act) {
-                    e = qent[hc * PQCH + ho + lane];
+                    e = (uint32_t)lane < k1 ? qent[hc * PQCH + ho + lane] : qent[nx * PQCH + (lane - k1)];
                     float sc = escore[e];
                     uint32_t td = etd[e];
                     if (sc >= threshold)
@@ -409,12 +418,27 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
                 const uint32_t cut1 = cbits ? (uint32_t)(__ffs(cbits) - 1) : k;
                 const bool cand = act && cls == 3 && (uint32_t)lane < cut1;
                 const unsigned candbits = __ballot_sync(FULL, cand);
+                C.fkey[lane] = NONE32;
+                C.fkey[lane + 32] = NONE32;
+                __syncwarp();
                 if (cand) {
                     const int r = __popc(candbits & lanemask_lt());
                     C.ce[r] = e;
                     C.ca[r] = min(ru, rv);
                     C.cb[r] = max(ru, rv);
                     C.clane[r] = lane;
+#pragma unroll
+                    for (int side = 0; side < 2; side++) {
+                        const uint32_t node = side ? rv : ru;
+                        uint32_t sl = (node * 2654435761u) >> 26;   // 6 bits
+                        for (;;) {
+                            if (atomicCAS(&C.fkey[sl], NONE32, node) == NONE32) {
+                                C.fval[sl] = (uint32_t)r;
+                                break;
+                            }
+                            sl = (sl + 1) & (PFILT - 1);
+                        }
+                    }
                 }
                 if (lane == 0) {
                     C.ncand = __popc(candbits);
@@ -431,6 +455,9 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
             }
         }
         __syncthreads();
+#ifdef BS_PROBE
+        { long long t1 = clock64(); tA += t1 - t0; t0 = t1; }
+#endif
         // ================= phase B: read-only walks (warp c: absorbed cluster b -> private neighbour hash; warp PCAND + c:
         // surviving cluster a, first 32 entries kept in registers), adjacency conflicts with the other candidates
         const uint32_t ncand = C.ncand;
@@ -439,8 +466,18 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
         uint32_t ma = 0, mb = 0, me = 0, head_a = N16, tail_a = N16, sa_h = N16, sa_x = 0, nbat = 0;
         uint32_t *hkey = C.hkey[cidx], *hval = C.hval[cidx];
         auto other_cand = [&](uint32_t x) {
-            for (uint32_t c = 0; c < ncand; c++)
-                if (c != (uint32_t)cidx && (x == C.ca[c] || x == C.cb[c])) atomicMin(&C.cut2, C.clane[max(c, (uint32_t)cidx)]);
+            // is x a cluster of another merge of this round?  (the clusters of a round's merges are pairwise distinct)
+            uint32_t sl = (x * 2654435761u) >> 26;
+            for (;;) {
+                const uint32_t kx = C.fkey[sl];
+                if (kx == NONE32) return;
+                if (kx == x) {
+                    const uint32_t c = C.fval[sl];
+                    if (c != (uint32_t)cidx) atomicMin(&C.cut2, C.clane[max(c, (uint32_t)cidx)]);
+                    return;
+                }
+                sl = (sl + 1) & (PFILT - 1);
+            }
         };
         if (bwalker || awalker) ma = C.ca[cidx], mb = C.cb[cidx], me = C.ce[cidx];
         if (bwalker) {
@@ -511,6 +548,9 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
             }
         }
         __syncthreads();
+#ifdef BS_PROBE
+        { long long t1 = clock64(); tB += t1 - t0; t0 = t1; }
+#endif
         // ================= phase C (warp 0): commit the non-merge entries of the final prefix, advance the queue
         const uint32_t cut = min(C.cut1, C.cut2);
         if (warp == 0 && !C.exit_) {
@@ -532,32 +572,32 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
             __syncwarp();
             bin_append(redo, nbin, e);
             {
-                const uint32_t ho2 = ho + consumed;
+                // the head moves by `consumed` entries, possibly into the next chunk (the append may have grown the tail)
+                uint32_t hcur = hc, ho2 = ho + consumed;
+                if (ho2 >= (uint32_t)PQCH && hcur != (uint32_t)btc[cb]) {
+                    const uint32_t nx2 = qcnext[hcur];
+                    __syncwarp();
+                    if (lane == 0) qcnext[hcur] = (IdxT)q_free;
+                    q_free = hcur;
+                    hcur = nx2;
+                    ho2 -= PQCH;
+                }
+                __syncwarp();
                 const uint32_t tc2 = btc[cb], tf2 = btf[cb];
-                bool freed = false;
-                if (hc == tc2) {
-                    if (ho2 == tf2) {
-                        freed = true;
-                        if (lane == 0) {
-                            bhc[cb] = N16;
-                            btc[cb] = N16;
-                            bho[cb] = 0;
-                            btf[cb] = 0;
-                            occ[cb >> 5] &= ~(1u << (cb & 31));
-                        }
-                    } else if (lane == 0)
-                        bho[cb] = (IdxT)ho2;
-                } else if (ho2 == (uint32_t)PQCH) {
-                    freed = true;
+                if (hcur == tc2 && ho2 == tf2) {
+                    // bin exhausted
                     if (lane == 0) {
-                        bhc[cb] = qcnext[hc];
+                        qcnext[hcur] = (IdxT)q_free;
+                        bhc[cb] = N16;
+                        btc[cb] = N16;
                         bho[cb] = 0;
+                        btf[cb] = 0;
+                        occ[cb >> 5] &= ~(1u << (cb & 31));
                     }
-                } else if (lane == 0)
+                    q_free = hcur;
+                } else if (lane == 0) {
+                    bhc[cb] = (IdxT)hcur;
                     bho[cb] = (IdxT)ho2;
-                if (freed) {
-                    if (lane == 0) qcnext[hc] = (IdxT)q_free;
-                    q_free = hc;
                 }
                 __syncwarp();
             }
@@ -569,6 +609,9 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
                 if (lane == 0) C.exit_ = 1;   // stop after this round's merges
             }
         }
+#ifdef BS_PROBE
+        { long long t1 = clock64(); tC += t1 - t0; t0 = t1; }
+#endif
         // ================= phase D (the a-walkers of candidates before the final cut): the merges
         if (awalker && C.clane[cidx] < cut) {
             const uint32_t myclock = C.clock0 + cidx + 1, mynum = C.nmerge0 + cidx;
@@ -660,6 +703,9 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
             }
         }
         __syncthreads();
+#ifdef BS_PROBE
+        { long long t1 = clock64(); tD += t1 - t0; t0 = t1; }
+#endif
         if (C.exit_ || C.fail) break;
     }
     if (threadIdx.x == 0) {
@@ -670,6 +716,12 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
         A.counters[6 * bi + 3] = n_iter;
         A.counters[6 * bi + 4] = n_chunk;
         A.counters[6 * bi + 5] = n_append;
+#ifdef BS_PROBE
+        A.counters[6 * bi + 0] = (uint32_t)(tA / 16);
+        A.counters[6 * bi + 1] = (uint32_t)(tB / 16);
+        A.counters[6 * bi + 2] = (uint32_t)(tC / 16);
+        A.counters[6 * bi + 4] = (uint32_t)(tD / 16);
+#endif
         if (fail || C.fail) atomicExch(A.error, 1u);
     }
 }

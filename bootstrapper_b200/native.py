@@ -167,9 +167,9 @@ class Plan:
         _check(lib().bs_plan_create(C.byref(cfg), C.byref(self._h)))
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib().bs_plan_destroy(self._h)
-            self._h = C.c_void_p()
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:   # module globals may be gone at exit
+            _lib.bs_plan_destroy(self._h)
+            self._h = None
 
     # ---- geometry
     def num_blocks(self):
