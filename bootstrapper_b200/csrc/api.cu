@@ -17,6 +17,8 @@ int relabel(const uint64_t *frags, int64_t n, const uint64_t *keys, const uint64
             cudaStream_t s);
 int relabel_dense(Plan &P, const uint64_t *frags, int64_t n, const uint64_t *const *comps, int T, uint64_t *const *segs,
                   cudaStream_t s);
+int components_multi(Plan &P, const uint64_t *nodes, int64_t n, const uint64_t *eu, const uint64_t *ev, const float *scores,
+                     int64_t m, const float *thresholds, int T, uint64_t *const *comps, cudaStream_t s);
 int plan_node_ids(Plan &P, uint64_t *out, long long *n_out, cudaStream_t s);
 int cc_affs(const void *affs, int dtype, const uint8_t *mask, int Z, int Y, int X, float thr, int remove_debris, uint64_t *frags_out,
             uint64_t *seg_out, int64_t *n_out, cudaStream_t s);
@@ -230,6 +232,15 @@ int bs_connected_components(const uint64_t *nodes, int64_t n, const uint64_t *ed
     BS_ARG(n == 0 || (nodes && components_out), "bs_connected_components: null argument");
     BS_ARG(m == 0 || (edges_u && edges_v), "bs_connected_components: null edges");
     return connected_components(nodes, n, edges_u, edges_v, scores, m, threshold, components_out, (cudaStream_t)stream);
+}
+
+int bs_stage3_components(bs_plan *p, const uint64_t *nodes, int64_t n, const uint64_t *edges_u, const uint64_t *edges_v,
+                         const float *scores, int64_t m, const float *thresholds, int n_thresholds, uint64_t *const *components_out,
+                         void *stream) {
+    BS_ARG(p && thresholds && components_out && (n == 0 || nodes), "bs_stage3_components: null argument");
+    BS_ARG(m == 0 || (edges_u && edges_v && scores), "bs_stage3_components: null edges");
+    return components_multi(*p->p, nodes, n, edges_u, edges_v, scores, m, thresholds, n_thresholds, components_out,
+                            (cudaStream_t)stream);
 }
 
 int bs_relabel(const uint64_t *frags, int64_t n_vox, const uint64_t *lut_keys, const uint64_t *lut_vals, int64_t n_lut,

@@ -136,6 +136,100 @@ int relabel_dense(Plan &P, const uint64_t *frags, int64_t n, const uint64_t *con
     return BS_OK;
 }
 
+// ---- thresholded connected components for all thresholds of a run in one pass over the edges: node numbers come
+// from the id arithmetic of the plan (no search), one union-find forest per threshold
+struct CcSet {
+    float thr[8];
+    uint64_t *comp[8];
+    int T;
+};
+
+__global__ void k_cc_init_multi(uint32_t *__restrict__ parent, size_t n_total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_total) parent[i] = 0xFFFFFFFFu;   // "root" (own index implied)
+}
+
+__device__ __forceinline__ uint32_t ufm_find(const uint32_t *parent, uint32_t x) {
+    uint32_t p = __ldcg(&parent[x]);
+    while (p != NONE32) {
+        x = p;
+        p = __ldcg(&parent[x]);
+    }
+    return x;
+}
+__device__ __forceinline__ void ufm_union(uint32_t *parent, uint32_t a, uint32_t b) {
+    for (;;) {
+        a = ufm_find(parent, a);
+        b = ufm_find(parent, b);
+        if (a == b) return;
+        if (a < b) {
+            uint32_t t = a;
+            a = b;
+            b = t;
+        }
+        uint32_t old = atomicMin(&parent[a], b);   // a root holds NONE32: any index is smaller
+        if (old == NONE32) return;
+        a = old;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_cc_union_multi(const uint64_t *__restrict__ eu, const uint64_t *__restrict__ ev,
+                                                        const float *__restrict__ scores, size_t m, IdMap idm, uint32_t n, CcSet cs,
+                                                        uint32_t *__restrict__ parent) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    const float sc = scores[e];
+    if (!(sc <= cs.thr[cs.T - 1])) return;   // thresholds ascending; NaN (merge_score NULL) never passes
+    const uint32_t a = id_to_dense(idm, eu[e]), b = id_to_dense(idm, ev[e]);
+    if (a >= n || b >= n || a == b) return;
+#pragma unroll
+    for (int t = 0; t < 8; t++)
+        if (t < cs.T && sc <= cs.thr[t]) ufm_union(parent + (size_t)t * n, a, b);
+}
+
+__global__ void __launch_bounds__(256) k_cc_flatten_multi(const uint64_t *__restrict__ nodes, uint32_t n, const uint32_t *__restrict__ parent,
+                                                          CcSet cs) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int t = 0; t < 8; t++)
+        if (t < cs.T) cs.comp[t][i] = nodes[ufm_find(parent + (size_t)t * n, i)];
+}
+
+// nodes: ascending ids of all fragments of the task (bs_plan_node_ids); thresholds ascending
+int components_multi(Plan &P, const uint64_t *nodes, int64_t n, const uint64_t *eu, const uint64_t *ev, const float *scores,
+                     int64_t m, const float *thresholds, int T, uint64_t *const *comps, cudaStream_t s) {
+    BS_ARG(T >= 1 && T <= 8, "bs_stage3_components: 1..8 thresholds per call");
+    BS_ARG(n == P.block_nbase[P.blocks.size()], "bs_stage3_components: node list does not match the plan's fragment counts");
+    for (int t = 1; t < T; t++) BS_ARG(thresholds[t] >= thresholds[t - 1], "bs_stage3_components: thresholds must be ascending");
+    if (n == 0) return BS_OK;
+    const size_t nblocks = P.blocks.size();
+    long long max_bid = 0;
+    for (auto &b : P.blocks) max_bid = std::max(max_bid, b.block_id);
+    std::vector<uint32_t> c2d((size_t)max_bid + 1, NONE32);
+    for (size_t i = 0; i < nblocks; i++) c2d[P.blocks[i].block_id] = (uint32_t)P.block_nbase[i];
+    DevBuf d_c2d, parent;
+    BS_TRY(d_c2d.alloc(4 * c2d.size(), s));
+    BS_CUDA(cudaMemcpyAsync(d_c2d.p, c2d.data(), 4 * c2d.size(), cudaMemcpyHostToDevice, s));
+    IdMap idm;
+    idm.cantor2dense = d_c2d.as<uint32_t>();
+    idm.max_block_id = max_bid;
+    idm.set_divisor(P.nvox_block);
+    CcSet cs;
+    cs.T = T;
+    for (int t = 0; t < 8; t++) {
+        cs.thr[t] = t < T ? thresholds[t] : 0.f;
+        cs.comp[t] = t < T ? comps[t] : nullptr;
+    }
+    BS_TRY(parent.alloc(4 * (size_t)n * T, s));
+    BS_LAUNCH(k_cc_init_multi, cdiv((size_t)n * T, 256), 256, 0, s, parent.as<uint32_t>(), (size_t)n * T);
+    if (m) BS_LAUNCH(k_cc_union_multi, cdiv((size_t)m, 256), 256, 0, s, eu, ev, scores, (size_t)m, idm, (uint32_t)n, cs, parent.as<uint32_t>());
+    BS_LAUNCH(k_cc_flatten_multi, cdiv((size_t)n, 256), 256, 0, s, nodes, (uint32_t)n, parent.as<uint32_t>(), cs);
+    BS_CUDA(cudaStreamSynchronize(s));   // c2d is a host-staged copy
+    BS_CUDA(cudaGetLastError());
+    return BS_OK;
+}
+
 // ---- node ids of the whole task from the per-block fragment counts (ids are 1..n per block + block_id * prod(block_size),
 // watershed_frags.py:224; blocks ascending by id): the sorted key row of the fragment -> segment LUT
 __global__ void k_node_ids(const long long *__restrict__ nbase, const long long *__restrict__ bid, int nblocks,

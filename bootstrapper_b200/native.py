@@ -37,7 +37,7 @@ EXPORTS = [
     "bs_last_error", "bs_launch_count", "bs_version", "bs_plan_create", "bs_plan_destroy", "bs_plan_num_blocks",
     "bs_plan_block_info", "bs_plan_set_owned", "bs_stage1_fragments", "bs_stage1_num_nodes", "bs_stage1_get_nodes",
     "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_plan_node_ids", "bs_stage2_agglomerate", "bs_stage2_num_edges",
-    "bs_stage2_get_edges", "bs_waterz_segment", "bs_cc_affs", "bs_connected_components", "bs_relabel", "bs_stage3_relabel", "bs_watershed_from_affinities",
+    "bs_stage2_get_edges", "bs_waterz_segment", "bs_cc_affs", "bs_connected_components", "bs_stage3_components", "bs_relabel", "bs_stage3_relabel", "bs_watershed_from_affinities",
     "bs_synth_affs", "bs_debug_fetch", "bs_set_debug", "bs_set_profiling", "bs_get_profile",
     "bs_release_scratch", "bs_set_flood_version", "bs_set_agglom_version", "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
 ]
@@ -266,6 +266,24 @@ class Plan:
         return outs, [float(t) for t in thr], dict(pops=cnt[0], stale=cnt[1], deleted=cnt[2], merges=cnt[3])
 
     # ---- stage 3
+    def components(self, nodes, edges_u, edges_v, scores, thresholds):
+        """connected_components (post/watershed.py:182) for every threshold of the run in one pass over the edges.
+        Returns {threshold: components tensor} (component id = smallest node id of the component)."""
+        order = sorted(set(float(t) for t in thresholds))
+        out = {}
+        for i in range(0, len(order), 8):
+            thr = np.ascontiguousarray(order[i:i + 8], dtype=np.float32)
+            comps = [torch.empty_like(nodes) for _ in thr]
+            cp = (C.c_void_p * len(thr))(*[c.data_ptr() for c in comps])
+            m = edges_u.numel()
+            _check(lib().bs_stage3_components(self._h, _dev(nodes, torch.int64), C.c_int64(nodes.numel()),
+                                              _dev(edges_u, torch.int64) if m else None, _dev(edges_v, torch.int64) if m else None,
+                                              _dev(scores, torch.float32) if m else None, C.c_int64(m),
+                                              thr.ctypes.data_as(C.c_void_p), C.c_int(len(thr)), cp, _stream()))
+            for t, c in zip(order[i:i + 8], comps):
+                out[t] = c
+        return {t: out[float(t)] for t in thresholds}
+
     def relabel(self, frags, comps, outs=None):
         """all thresholds in one pass; comps: list of (N,) LUT value tensors in ascending node-id order"""
         T = len(comps)

@@ -107,7 +107,8 @@ def segment_blockwise(affs, params=None, block_size=None, context=None, roi=None
     plan.agglomerate(affs, frags)
     eu, ev, es = plan.edges(dev)
     thrs = list(p["thresholds"])
-    comps = [native.connected_components(node_ids, eu, ev, es, float(thr)) for thr in thrs]
+    cmap = plan.components(node_ids, eu, ev, es, thrs)
+    comps = [cmap[thr] for thr in thrs]
     luts = dict(zip(thrs, comps))
     segs = {}
     for i in range(0, len(thrs), 8):           # Relabel: up to 8 thresholds per pass over the fragments

@@ -181,7 +181,8 @@ class ShardedSegmenter:
         nodes = plan.node_ids(affs_win.device)
         own = frags[g["z0"] - g["w0"]:g["z1"] - g["w0"]]
         thrs = list(self.p["thresholds"])
-        comps = [native.connected_components(nodes, eu, ev, es, float(thr)) for thr in thrs]
+        cmap = plan.components(nodes, eu, ev, es, thrs)
+        comps = [cmap[thr] for thr in thrs]
         luts = dict(zip(thrs, comps))
         segs = {}
         own = own.contiguous()

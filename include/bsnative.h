@@ -139,6 +139,11 @@ int bs_waterz_segment(bs_plan *p, const void *affs, const uint64_t *frags, const
 int bs_connected_components(const uint64_t *nodes, int64_t n, const uint64_t *edges_u, const uint64_t *edges_v,
                             const float *scores, int64_t m, float threshold, uint64_t *components_out,
                             void *stream);
+/* the same for up to 8 (ascending) thresholds in one pass over the edges; `nodes` = bs_plan_node_ids of the plan (node
+ * numbers come from the id arithmetic, no search); thresholds host, components_out host array of device pointers. */
+int bs_stage3_components(bs_plan *p, const uint64_t *nodes, int64_t n, const uint64_t *edges_u, const uint64_t *edges_v,
+                         const float *scores, int64_t m, const float *thresholds, int n_thresholds, uint64_t *const *components_out,
+                         void *stream);
 /* seg[i] = lut_vals[k] if frags[i] == lut_keys[k] else frags[i]; lut_keys ascending */
 int bs_relabel(const uint64_t *frags, int64_t n_vox, const uint64_t *lut_keys, const uint64_t *lut_vals,
                int64_t n_lut, uint64_t *seg_out, void *stream);
