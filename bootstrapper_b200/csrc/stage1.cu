@@ -473,6 +473,83 @@ __global__ void __launch_bounds__(256) k_maxfilt_xy(const Tile *__restrict__ til
     }
 }
 
+// The same for a compile-time window (the default min_seed_distance = 10): every thread produces 4 neighbouring
+// outputs of a pass from SIZE + 3 shared-memory reads, which takes the kernel off the shared-memory bandwidth limit.
+template <int SIZE>
+__global__ void __launch_bounds__(256) k_maxfilt_xy_t(const Tile *__restrict__ tiles, const uint32_t *__restrict__ d2, int final2d,
+                                                      const uint8_t *__restrict__ msk, uint32_t *__restrict__ out,
+                                                      uint32_t *__restrict__ sbits) {
+    static_assert(SIZE >= 4 && MF_TW % 4 == 0 && MF_TH % 4 == 0, "window / tile shape");
+    constexpr int LO = SIZE / 2, PW = MF_TW + SIZE - 1, PH = MF_TH + SIZE - 1;
+    constexpr int AW = (PH * PW + 3) & ~3;
+    __shared__ __align__(16) uint32_t A[AW];            // [PH][PW] input patch
+    __shared__ __align__(16) uint32_t B[PH * MF_TW];    // [PH][MF_TW] row maxima
+    const Tile t = tiles[blockIdx.y];
+    const int W = t.W, H = t.H;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ntx = (W + MF_TW - 1) / MF_TW, nty = (H + MF_TH - 1) / MF_TH;
+    const int njobs = t.D * ntx * nty;
+    for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+        const int z = job / (ntx * nty), r = job - z * ntx * nty;
+        const int ty = r / ntx, tx = r - ty * ntx;
+        const int x0 = tx * MF_TW, y0 = ty * MF_TH;
+        const long long sbase = t.base + (long long)z * H * W;
+        __syncthreads();
+        for (int py = warp; py < PH; py += 8) {
+            const long long rowb = sbase + (long long)reflect_idx(y0 - LO + py, H) * W;
+            for (int px = lane; px < PW; px += 32) A[py * PW + px] = d2[rowb + reflect_idx(x0 - LO + px, W)];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < PH * (MF_TW / 4); i += 256) {
+            const int py = i / (MF_TW / 4), q = i % (MF_TW / 4);
+            const uint32_t *a = A + py * PW + 4 * q;
+            uint32_t v[SIZE + 3];
+#pragma unroll
+            for (int k = 0; k < SIZE + 3; k++) v[k] = a[k];
+            uint32_t c = v[3];
+#pragma unroll
+            for (int k = 4; k < SIZE; k++) c = max(c, v[k]);
+            uint4 o;
+            o.x = max(max(c, v[0]), max(v[1], v[2]));
+            o.y = max(max(c, v[1]), max(v[2], v[SIZE]));
+            o.z = max(max(c, v[2]), max(v[SIZE], v[SIZE + 1]));
+            o.w = max(max(c, v[SIZE]), max(v[SIZE + 1], v[SIZE + 2]));
+            *reinterpret_cast<uint4 *>(B + py * MF_TW + 4 * q) = o;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < (MF_TH / 4) * MF_TW; i += 256) {
+            const int pq = i / MF_TW, px = i % MF_TW;
+            const uint32_t *b = B + (4 * pq) * MF_TW + px;
+            uint32_t v[SIZE + 3];
+#pragma unroll
+            for (int k = 0; k < SIZE + 3; k++) v[k] = b[k * MF_TW];
+            uint32_t c = v[3];
+#pragma unroll
+            for (int k = 4; k < SIZE; k++) c = max(c, v[k]);
+            uint32_t o[4];
+            o[0] = max(max(c, v[0]), max(v[1], v[2]));
+            o[1] = max(max(c, v[1]), max(v[2], v[SIZE]));
+            o[2] = max(max(c, v[2]), max(v[SIZE], v[SIZE + 1]));
+            o[3] = max(max(c, v[SIZE]), max(v[SIZE + 1], v[SIZE + 2]));
+            const int x = x0 + px;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int py = 4 * pq + j, y = y0 + py;
+                if (y < H && x < W) {
+                    const long long p = sbase + (long long)y * W + x;
+                    if (!final2d) {
+                        out[p] = o[j];
+                    } else {
+                        bool seed = (o[j] == A[(py + LO) * PW + px + LO]) && msk[p];
+                        out[p] = seed ? (uint32_t)((long long)z * H * W + (long long)y * W + x) : NONE32;
+                        if (seed) atomicOr(&sbits[p >> 5], 1u << (p & 31));
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ seed connected components (conn-1)
 __global__ void __launch_bounds__(256) k_seed_union(const Tile *__restrict__ tiles, uint32_t *__restrict__ par) {
     const Tile t = tiles[blockIdx.y];
@@ -1370,14 +1447,18 @@ static int launch_seeds(const Tile *dt, const TileDims &td, bool three_d, int ms
         }
     }
     if (!three_d) {
-        if (use_mf) {
+        if (msd == 10) {
+            BS_LAUNCH(k_maxfilt_xy_t<10>, grid_mf, 256, 0, s, dt, d2, 1, msk, par, sbits);
+        } else if (use_mf) {
             BS_LAUNCH(k_maxfilt_xy, grid_mf, 256, mf_smem, s, dt, d2, msd, 1, msk, par, sbits);
         } else {
             BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, d2, tmpA, 2, msd, 0, nullptr, nullptr, nullptr, nullptr);
             BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, tmpA, nullptr, 1, msd, 1, d2, msk, par, sbits);
         }
     } else {
-        if (use_mf) {
+        if (msd == 10) {
+            BS_LAUNCH(k_maxfilt_xy_t<10>, grid_mf, 256, 0, s, dt, d2, 0, nullptr, tmpB, nullptr);
+        } else if (use_mf) {
             BS_LAUNCH(k_maxfilt_xy, grid_mf, 256, mf_smem, s, dt, d2, msd, 0, nullptr, tmpB, nullptr);
         } else {
             BS_LAUNCH(k_maxfilt, grid, 256, 0, s, dt, d2, tmpA, 2, msd, 0, nullptr, nullptr, nullptr, nullptr);
