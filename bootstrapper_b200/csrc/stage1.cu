@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(256) k_maxfilt(const Tile *__restrict__ tiles,
 static constexpr int CS_W = 32;
 __global__ void __launch_bounds__(256) k_coldist_strip(const Tile *__restrict__ tiles, const uint16_t *__restrict__ g,
                                                        uint32_t *__restrict__ out, uint32_t *__restrict__ tilemax) {
-    extern __shared__ uint16_t cs_g[];   // [H][CS_W]
+    extern __shared__ uint32_t cs_g2[];   // [H][CS_W] squared row distances (DBIG: no background in the row)
     const Tile t = tiles[blockIdx.y];
     const int W = t.W, H = t.H;
     const int nstrips = (W + CS_W - 1) / CS_W;
@@ -376,30 +376,23 @@ __global__ void __launch_bounds__(256) k_coldist_strip(const Tile *__restrict__ 
         const int x = x0 + lane;
         const long long sbase = t.base + (long long)z * H * W;
         __syncthreads();
-        for (int y = warp; y < H; y += 8) cs_g[y * CS_W + lane] = x < W ? g[sbase + (long long)y * W + x] : GINF;
+        for (int y = warp; y < H; y += 8) {
+            uint32_t gv = x < W ? g[sbase + (long long)y * W + x] : GINF;
+            cs_g2[y * CS_W + lane] = gv == GINF ? DBIG : gv * gv;
+        }
         __syncthreads();
         if (x < W)
             for (int y = warp; y < H; y += 8) {
-                const uint16_t *gp = cs_g + y * CS_W + lane;
-                uint32_t g0 = gp[0];
-                uint32_t best = g0 == GINF ? DBIG : g0 * g0;
+                const uint32_t *gp = cs_g2 + y * CS_W + lane;
+                uint32_t best = gp[0];
+                const int up = y, down = H - 1 - y;   // rows available above / below
                 for (int dy = 1;; dy++) {
-                    uint32_t dd = (uint32_t)dy * dy;
-                    if (dd >= best) break;
-                    bool any = false;
-                    if (y - dy >= 0) {
-                        any = true;
-                        uint32_t v = gp[-dy * CS_W];
-                        if (v != GINF) best = min(best, v * v + dd);
-                    }
-                    if (y + dy < H) {
-                        any = true;
-                        uint32_t v = gp[dy * CS_W];
-                        if (v != GINF) best = min(best, v * v + dd);
-                    }
-                    if (!any) break;
+                    const uint32_t dd = (uint32_t)dy * dy;
+                    if (dd >= best || (dy > up && dy > down)) break;
+                    if (dy <= up) best = min(best, gp[-dy * CS_W] + dd);
+                    if (dy <= down) best = min(best, gp[dy * CS_W] + dd);
                 }
-                if (final2d && best == DBIG) best = (uint32_t)(y + 1) * (y + 1) + (uint32_t)x * x;
+                if (best >= DBIG) best = final2d ? (uint32_t)(y + 1) * (y + 1) + (uint32_t)x * x : DBIG;
                 out[sbase + (long long)y * W + x] = best;
                 if (final2d) mymax = max(mymax, best);
             }
@@ -1411,7 +1404,7 @@ static dim3 pixel_grid(const TileDims &td) {
 static int launch_edt(const Tile *dt, const TileDims &td, bool three_d, const uint16_t *g, uint32_t *tmp, uint32_t *out,
                       uint32_t *tilemax, cudaStream_t s) {
     const dim3 grid = pixel_grid(td);
-    const size_t strip_smem = (size_t)td.maxH * CS_W * 2;
+    const size_t strip_smem = (size_t)td.maxH * CS_W * 4;
     const bool use_strip = strip_smem <= 96 * 1024;
     const dim3 grid_strip((unsigned)std::min<long long>((long long)td.maxD * ((td.maxW + CS_W - 1) / CS_W), 8192), td.ntiles);
     if (use_strip) {
