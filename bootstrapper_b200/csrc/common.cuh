@@ -168,6 +168,37 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// division of 32-bit indices by a run-time constant (tile / block extents): multiply-high with a precomputed magic
+// number (round-up method, exact for every 32-bit numerator)
+struct FastDiv {
+    uint32_t m, sh;   // m == 0: the divisor is a power of two, shift by sh
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    uint32_t l = 0;
+    while ((1ull << l) < d) l++;
+    if ((1ull << l) == d) {
+        f.m = 0;
+        f.sh = l;
+    } else {
+        f.m = (uint32_t)((((1ull << l) - d) << 32) / d) + 1;
+        f.sh = l - 1;
+    }
+    return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv &f) {
+    if (f.m == 0) return n >> f.sh;
+    uint32_t t = __umulhi(f.m, n);
+    return (t + ((n - t) >> 1)) >> f.sh;
+}
+__device__ __forceinline__ void unravel3f(uint32_t u, int W, int H, const FastDiv &fW, const FastDiv &fH, int &x, int &y, int &z) {
+    uint32_t row = fdiv(u, fW);
+    x = (int)(u - row * (uint32_t)W);
+    uint32_t zz = fdiv(row, fH);
+    y = (int)(row - zz * (uint32_t)H);
+    z = (int)zz;
+}
+
 // (x, y, z) of a raveled index inside a tile / block (all such indices are < 2^31): 32-bit divisions only
 __device__ __forceinline__ void unravel3(long long i, int W, int H, int &x, int &y, int &z) {
     uint32_t u = (uint32_t)i;

@@ -23,6 +23,11 @@ struct Tile {
     int ndim;            // 2 or 3 (array rank the reference hands to scipy / skimage)
     long long base;      // offset of this tile in the per-pixel scratch arrays (batch local)
     long long wbase;     // offset of this tile's write region in batch write order
+    FastDiv fW, fH, fwW, fwH;   // divisions by W, H, wW, wH
+    void set_divs() {
+        fW = make_fastdiv((uint32_t)W), fH = make_fastdiv((uint32_t)H);
+        fwW = make_fastdiv((uint32_t)wW), fwH = make_fastdiv((uint32_t)wH);
+    }
 };
 
 struct Blk {

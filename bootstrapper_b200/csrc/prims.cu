@@ -22,6 +22,12 @@ int Arena::begin(bool enable) {
         base = nullptr;
         cap = 0;
         size_t want = need_last + need_last / 8 + (64u << 20);
+        // the first run of this size went through the stream-ordered pool, which still caches those bytes
+        {
+            int dev = 0;
+            cudaMemPool_t pool;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        }
         if (cudaMalloc((void **)&base, want) == cudaSuccess) {
             cap = want;
         } else {

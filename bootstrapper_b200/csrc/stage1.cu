@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(256) k_seed_union(const Tile *__restrict__ til
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
         if (__ldcg(&pp[i]) == NONE32) continue;
         int x, y, z;
-        unravel3(i, W, H, x, y, z);
+        unravel3f((uint32_t)i, W, H, t.fW, t.fH, x, y, z);
         if (x > 0 && __ldcg(&pp[i - 1]) != NONE32) uf_union(pp, (uint32_t)i, (uint32_t)(i - 1));
         if (y > 0 && __ldcg(&pp[i - W]) != NONE32) uf_union(pp, (uint32_t)i, (uint32_t)(i - W));
         if (z > 0 && __ldcg(&pp[i - HW]) != NONE32) uf_union(pp, (uint32_t)i, (uint32_t)(i - HW));
@@ -1114,7 +1114,7 @@ __global__ void __launch_bounds__(256) k_fragstats(const Tile *__restrict__ tile
             if (l) {
                 // a labelled pixel is inside the mask, hence inside the volume and not masked out
                 int x, y, z;
-                unravel3(i, W, H, x, y, z);
+                unravel3f((uint32_t)i, W, H, t.fW, t.fH, x, y, z);
                 if (z >= t.wz && z < t.wz + t.wD && y >= t.wy && y < t.wy + t.wH && x >= t.wx && x < t.wx + t.wW)
                     w = (uint32_t)tile_widx(t, z, y, x);
                 else
@@ -1190,7 +1190,7 @@ __global__ void __launch_bounds__(256) k_crop_init(const Tile *__restrict__ tile
         long long i = 0;
         int x = 0, y = 0, z = 0;
         if (kk < nw) {
-            unravel3(kk, t.wW, t.wH, x, y, z);
+            unravel3f((uint32_t)kk, t.wW, t.wH, t.fwW, t.fwH, x, y, z);
             i = ((long long)(z + t.wz) * H + (y + t.wy)) * W + (x + t.wx);
             l = part_label(i);
         }
@@ -1221,7 +1221,7 @@ __global__ void __launch_bounds__(256) k_crop_union(const Tile *__restrict__ til
     const uint32_t *ll = lab + t.base;
     for (long long kk = (long long)blockIdx.x * blockDim.x + threadIdx.x; kk < nw; kk += (long long)gridDim.x * blockDim.x) {
         int x, y, z;
-        unravel3(kk, t.wW, t.wH, x, y, z);
+        unravel3f((uint32_t)kk, t.wW, t.wH, t.fwW, t.fwH, x, y, z);
         const long long i = ((long long)(z + t.wz) * H + (y + t.wy)) * W + (x + t.wx);
         if (__ldcg(&pp[i]) == NONE32) continue;
         const uint32_t l = ll[i];
@@ -1264,7 +1264,7 @@ __global__ void __launch_bounds__(256) k_root_bits_pix(const Tile *__restrict__ 
     const long long nw = (long long)t.wD * t.wH * t.wW;
     for (long long kk = (long long)blockIdx.x * blockDim.x + threadIdx.x; kk < nw; kk += (long long)gridDim.x * blockDim.x) {
         int x, y, z;
-        unravel3(kk, t.wW, t.wH, x, y, z);
+        unravel3f((uint32_t)kk, t.wW, t.wH, t.fwW, t.fwH, x, y, z);
         const long long i = ((long long)(z + t.wz) * H + (y + t.wy)) * W + (x + t.wx);
         if (cpar[t.base + i] == (uint32_t)i) {
             const uint32_t w = (uint32_t)(t.wbase + kk);
@@ -1495,6 +1495,7 @@ static int seed_distance_prepass(Plan &P, const std::vector<int> &bidx, AffView 
         long long np = (long long)t.D * t.H * t.W;
         Ppre += np;
         maxpix = std::max(maxpix, np);
+        t.set_divs();
         pt.push_back(t);
     }
     BS_ARG(Ppre < (1LL << 31), "stage1: seed_eps pre-pass too large for 32-bit tile indices (lower max_batch_voxels)");
@@ -1581,6 +1582,7 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
                 long long np = (long long)t.H * t.W;
                 P_pix += (np + 31) & ~31LL;   // 32-aligned tile bases (bitmap words of flood v2)
                 maxpix = std::max(maxpix, np);
+                t.set_divs();
                 tiles.push_back(t);
             }
         } else {
@@ -1596,7 +1598,8 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
             long long np = (long long)t.D * t.H * t.W;
             P_pix += np;
             maxpix = std::max(maxpix, np);
-            tiles.push_back(t);
+            t.set_divs();
+                tiles.push_back(t);
         }
         V_w += wv;
     }
