@@ -34,7 +34,7 @@ class WsConfig(C.Structure):
 
 
 EXPORTS = [
-    "bs_last_error", "bs_launch_count", "bs_version", "bs_plan_create", "bs_plan_destroy", "bs_plan_num_blocks",
+    "bs_last_error", "bs_launch_count", "bs_version", "bs_config_size", "bs_plan_create", "bs_plan_destroy", "bs_plan_num_blocks",
     "bs_plan_block_info", "bs_plan_set_owned", "bs_stage1_fragments", "bs_stage1_num_nodes", "bs_stage1_get_nodes",
     "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_plan_node_ids", "bs_stage2_agglomerate", "bs_stage2_num_edges",
     "bs_stage2_get_edges", "bs_waterz_segment", "bs_cc_affs", "bs_connected_components", "bs_stage3_components", "bs_relabel", "bs_stage3_relabel", "bs_watershed_from_affinities",
@@ -55,8 +55,11 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.bs_last_error.restype = C.c_char_p
         _lib.bs_launch_count.restype = C.c_ulonglong
+        _lib.bs_config_size.restype = C.c_ulonglong
         for name in EXPORTS:
             getattr(_lib, name)
+        if _lib.bs_config_size() != C.sizeof(WsConfig):
+            raise BsError(f"bs_ws_config layout mismatch: library {_lib.bs_config_size()} bytes, binding {C.sizeof(WsConfig)}")
     return _lib
 
 

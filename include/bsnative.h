@@ -65,6 +65,8 @@ const char *bs_last_error(void);
 /* number of kernels launched by this library in this process (bench.py gpu_launches) */
 unsigned long long bs_launch_count(void);
 int bs_version(void);
+/* sizeof(bs_ws_config) as this library was compiled: a binding checks its struct layout against it */
+unsigned long long bs_config_size(void);
 
 /* ---- plan: geometry of one `bs segment --ws -b` run ------------------------------- */
 /* replaces: volara BlockwiseTask geometry as used by WatershedFrags / WaterzAgglom

@@ -51,3 +51,24 @@ def test_no_cpu_fallback(built_lib):
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+
+
+def test_config_struct_layout(built_lib):
+    """the ctypes mirror of bs_ws_config has the size the library was compiled with (checked again at load time)"""
+    import ctypes as C
+    from bootstrapper_b200 import native
+    lib = native.lib()
+    assert lib.bs_config_size() == C.sizeof(native.WsConfig)
+    cfg = native.WsConfig()
+    assert C.sizeof(cfg.bias) == 24 and native.WsConfig.seed_eps.offset % 8 == 0
+
+
+def test_ws_params_resolution():
+    """which ws parameters the CUDA path accepts (the rest must raise, never silently run something else)"""
+    import pytest
+    from bootstrapper_b200.post.pipeline import resolve_ws_params
+    p = resolve_ws_params({"bias": [-0.1, -0.2, -0.2], "seed_eps": 0.01, "fragments_in_xy": False})
+    assert p["seed_eps"] == 0.01 and p["thresholds"] == [0.2, 0.35, 0.5]
+    for bad in ({"sigma": [1, 1, 1]}, {"noise_eps": 0.001}, {"epsilon_agglomerate": 0.05}, {"merge_function": "hist_quant_75"}):
+        with pytest.raises(NotImplementedError):
+            resolve_ws_params(bad)
