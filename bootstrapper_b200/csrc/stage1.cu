@@ -901,9 +901,12 @@ static constexpr int F2_HASH = 256;
 static constexpr uint32_t F2_PIXMASK = 0x1FFFFu;
 static constexpr int F2_MAXPIX = 1 << 17;
 
+// GAVAIL: the "floodable" bitmap stays in global memory (L2) instead of shared memory: 1 KB of shared memory per tile, so
+// every tile of a batch is resident at once (no second wave) and more warps hide the load latencies.
+template <bool GAVAIL>
 __global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict__ tiles, int ntiles,
                                                           const uint32_t *__restrict__ lab_all, const uint16_t *__restrict__ lv16_all,
-                                                          const uint32_t *__restrict__ availw_all, uint32_t *__restrict__ queue,
+                                                          uint32_t *__restrict__ availw_all, uint32_t *__restrict__ queue,
                                                           const uint32_t *__restrict__ lvl_qstart, uint32_t *__restrict__ lvl_head,
                                                           uint32_t *__restrict__ lvl_tail, const uint32_t *__restrict__ tile_lvl,
                                                           const uint32_t *__restrict__ seedlist, const uint32_t *__restrict__ tile_seed,
@@ -912,9 +915,9 @@ __global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wid = blockIdx.x * F2_WARPS + warp;
     if (wid >= ntiles) return;
-    uint32_t *avail = f2_smem + (size_t)warp * (nwords_max + F2_HASH);
-    uint32_t *claim = avail + nwords_max;
     const Tile t = tiles[wid];
+    uint32_t *avail = GAVAIL ? availw_all + (t.base >> 5) : f2_smem + (size_t)warp * (nwords_max + F2_HASH);
+    uint32_t *claim = GAVAIL ? f2_smem + (size_t)warp * F2_HASH : avail + nwords_max;
     const uint16_t *lv16 = lv16_all + t.base;
     const int W = t.W, H = t.H;
     const int npix = H * W, nwords = (npix + 31) >> 5;
@@ -922,8 +925,10 @@ __global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict
     if (lo == hi) return;
     const uint32_t sb = tile_seed[wid], se = tile_seed[wid + 1];
     if (sb == se) return;
-    for (int w = lane; w < nwords; w += 32) avail[w] = availw_all[(t.base >> 5) + w];
-    __syncwarp();
+    if (!GAVAIL) {
+        for (int w = lane; w < nwords; w += 32) avail[w] = availw_all[(t.base >> 5) + w];
+        __syncwarp();
+    }
     uint32_t steps = 0, intr = 0;
     uint32_t cur = lo, tailc = 0, headc = 0;
     {
@@ -993,7 +998,7 @@ __global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict
         for (int j = 0; j < F2_HASH / 32; j++) claim[lane + 32 * j] = NONE32;
 #pragma unroll
         for (int s = 0; s < 4; s++) {
-            cand[s] = nb[s] != NONE32 && ((avail[nb[s] >> 5] >> (nb[s] & 31)) & 1u);
+            cand[s] = nb[s] != NONE32 && (((GAVAIL ? __ldcg(&avail[nb[s] >> 5]) : avail[nb[s] >> 5]) >> (nb[s] & 31)) & 1u);
             pend[s] = cand[s];
             hs[s] = (nb[s] * 2654435761u) >> 24;
             lraw[s] = cand[s] ? lv16[nb[s]] : (uint16_t)0;   // issued early: the claim resolution hides the latency
@@ -1747,16 +1752,25 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     g_prof.mark("s1.flood", s);
     if (v2) {
         const int nwords_max = (int)((maxpix + 31) / 32);
-        const size_t smem = (size_t)F2_WARPS * (nwords_max + F2_HASH) * 4;
+        // bitmap in shared memory only when every tile of the batch is resident then anyway (16 tiles per SM); otherwise
+        // it stays in global memory and all tiles run in one wave
+        const bool gavail = g_flood_version == 3 || (g_flood_version != 2 && ntiles > 148 * 16);
+        const size_t smem = gavail ? (size_t)F2_WARPS * F2_HASH * 4 : (size_t)F2_WARPS * (nwords_max + F2_HASH) * 4;
         static bool attr_set = false;
         if (!attr_set) {
-            BS_CUDA(cudaFuncSetAttribute(k_flood2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            BS_CUDA(cudaFuncSetAttribute(k_flood2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             attr_set = true;
         }
-        BS_LAUNCH(k_flood2, cdiv(ntiles, F2_WARPS), 32 * F2_WARPS, smem, s, dt, ntiles, lab.as<uint32_t>(), lv16.as<uint16_t>(),
-                  availw.as<uint32_t>(), queue.as<uint32_t>(), lvl_qstart.as<uint32_t>(), lvl_head.as<uint32_t>(),
-                  lvl_tail.as<uint32_t>(), tile_lvl.as<uint32_t>(), seedlist.as<uint32_t>(), tile_seed.as<uint32_t>(),
-                  nwords_max, fstats.as<uint32_t>());
+        if (gavail)
+            BS_LAUNCH(k_flood2<true>, cdiv(ntiles, F2_WARPS), 32 * F2_WARPS, smem, s, dt, ntiles, lab.as<uint32_t>(), lv16.as<uint16_t>(),
+                      availw.as<uint32_t>(), queue.as<uint32_t>(), lvl_qstart.as<uint32_t>(), lvl_head.as<uint32_t>(),
+                      lvl_tail.as<uint32_t>(), tile_lvl.as<uint32_t>(), seedlist.as<uint32_t>(), tile_seed.as<uint32_t>(),
+                      nwords_max, fstats.as<uint32_t>());
+        else
+            BS_LAUNCH(k_flood2<false>, cdiv(ntiles, F2_WARPS), 32 * F2_WARPS, smem, s, dt, ntiles, lab.as<uint32_t>(), lv16.as<uint16_t>(),
+                      availw.as<uint32_t>(), queue.as<uint32_t>(), lvl_qstart.as<uint32_t>(), lvl_head.as<uint32_t>(),
+                      lvl_tail.as<uint32_t>(), tile_lvl.as<uint32_t>(), seedlist.as<uint32_t>(), tile_seed.as<uint32_t>(),
+                      nwords_max, fstats.as<uint32_t>());
         g_prof.mark("s1.flood_scatter", s);
         BS_LAUNCH(k_scatter_labels, dim3((unsigned)std::min<long long>(std::max<long long>((maxpix + 1023) / 1024, 1), 2048), ntiles), 256, 0, s, dt, tile_q.as<uint32_t>(), queue.as<uint32_t>(), lab.as<uint32_t>());
     } else {

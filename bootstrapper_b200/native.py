@@ -60,6 +60,11 @@ def lib():
             getattr(_lib, name)
         if _lib.bs_config_size() != C.sizeof(WsConfig):
             raise BsError(f"bs_ws_config layout mismatch: library {_lib.bs_config_size()} bytes, binding {C.sizeof(WsConfig)}")
+        # kernel-variant switches for experiments (see include/bsnative.h)
+        if os.environ.get("BS_FLOOD_VERSION"):
+            _lib.bs_set_flood_version(C.c_int(int(os.environ["BS_FLOOD_VERSION"])))
+        if os.environ.get("BS_AGGLOM_VERSION"):
+            _lib.bs_set_agglom_version(C.c_int(int(os.environ["BS_AGGLOM_VERSION"])))
     return _lib
 
 

@@ -188,7 +188,8 @@ int bs_debug_fetch(const bs_plan *p, const char *name, void *dst_host, int64_t *
 /* per-stage device times (ms) of the last run, measured with CUDA events on the caller's
  * stream when enabled via bs_set_profiling(1). names/values up to cap entries. */
 int bs_set_debug(int on);
-/* 0 = automatic (shared-memory flood for 2-D tiles when eligible), 1 = force the global-memory flood */
+/* flood kernel: 0 = automatic, 1 = global-memory flood (v1), 2 = v2 with the tile bitmap in shared memory,
+ * 3 = v2 with the tile bitmap in global memory (every tile resident at once) */
 int bs_set_flood_version(int v);
 /* agglomeration kernel: 0 = automatic (parallel merges; shared memory when a block's graph fits, else a global slab),
  * 1 = single warp on global slabs, 2 = single warp in shared memory, 3 = parallel merges on global slabs */
