@@ -632,6 +632,12 @@ __global__ void k_tile_ranges(const Tile *__restrict__ tiles, int ntiles, const 
     }
 }
 
+// largest number of priority levels in one tile (sizes the shared-memory level tables of flood v2)
+__global__ void k_tile_nlev_max(const uint32_t *__restrict__ tile_lvl, int ntiles, uint32_t *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ntiles) atomicMax(out, tile_lvl[i + 1] - tile_lvl[i]);
+}
+
 // largest number of seed pixels in one tile (decides whether 15-bit labels suffice for flood v2)
 __global__ void k_tile_seed_max(const Tile *__restrict__ tiles, int ntiles, const uint32_t *__restrict__ sbits,
                                 const uint32_t *__restrict__ swscan,
@@ -683,17 +689,20 @@ __global__ void __launch_bounds__(256) k_pixel_levels(const Tile *__restrict__ t
 // ------------------------------------------------------------------ the flood
 // Order-preserving append of up to NS candidates per lane (order: lane-major, slot-minor) to the
 // FIFO of their level.  `cur`/`tailc`: the current level's tail lives in a register.
-template <int NS>
+// ST: the tails of the tile's levels live in shared memory (stail[level - lo]) together with a bitmap of the levels that
+// hold entries (snz); otherwise they are read / written through L2 (lvl_tail).
+template <int NS, bool ST>
 __device__ __forceinline__ void warp_append(const bool (&valid_in)[NS], const uint32_t (&lvl)[NS], const uint32_t (&pix)[NS],
                                             uint32_t *__restrict__ queue, const uint32_t *__restrict__ lvl_qstart,
-                                            uint32_t *__restrict__ lvl_tail, uint32_t cur, uint32_t &tailc, int lane) {
+                                            uint32_t *__restrict__ lvl_tail, uint32_t cur, uint32_t &tailc, int lane,
+                                            uint32_t *stail = nullptr, uint32_t *snz = nullptr, uint32_t lo = 0) {
     bool valid[NS];
     uint32_t tl[NS];
 #pragma unroll
     for (int s = 0; s < NS; s++) {
         valid[s] = valid_in[s];
         tl[s] = 0;
-        if (valid[s] && lvl[s] != cur) tl[s] = __ldcg(&lvl_tail[lvl[s]]);
+        if (valid[s] && lvl[s] != cur) tl[s] = ST ? stail[lvl[s] - lo] : __ldcg(&lvl_tail[lvl[s]]);
     }
     for (;;) {
         uint32_t mylo = NONE32;
@@ -721,7 +730,7 @@ __device__ __forceinline__ void warp_append(const bool (&valid_in)[NS], const ui
             if (lane >= o) incl += v;
         }
         int total = __shfl_sync(FULL, incl, 31);
-        uint32_t pos = lvl_qstart[L] + base + (uint32_t)(incl - c);
+        uint32_t pos = __ldg(&lvl_qstart[L]) + base + (uint32_t)(incl - c);
 #pragma unroll
         for (int s = 0; s < NS; s++)
             if (valid[s] && lvl[s] == L) {
@@ -730,8 +739,14 @@ __device__ __forceinline__ void warp_append(const bool (&valid_in)[NS], const ui
             }
         if (L == cur)
             tailc = base + total;
-        else if (lane == 0)
-            __stcg(&lvl_tail[L], base + (uint32_t)total);
+        else if (lane == 0) {
+            if (ST) {
+                stail[L - lo] = base + (uint32_t)total;
+                snz[(L - lo) >> 5] |= 1u << ((L - lo) & 31);
+            } else
+                __stcg(&lvl_tail[L], base + (uint32_t)total);
+        }
+        if (ST) __syncwarp();
     }
 }
 
@@ -768,7 +783,7 @@ __global__ void __launch_bounds__(64) k_flood(const Tile *__restrict__ tiles, in
             px[0] = v[0] ? seedlist[s0 + lane] : 0;
             l[0] = v[0] ? lv[px[0]] : 0;
             if (v[0]) maxr = max(maxr, l[0]);
-            warp_append<1>(v, l, px, queue, lvl_qstart, lvl_tail, NONE32, dummy_tail, lane);
+            warp_append<1, false>(v, l, px, queue, lvl_qstart, lvl_tail, NONE32, dummy_tail, lane);
             __syncwarp();
         }
         cur = __reduce_max_sync(FULL, maxr);
@@ -864,7 +879,7 @@ __global__ void __launch_bounds__(64) k_flood(const Tile *__restrict__ tiles, in
                 if (cand[s]) __stcg(&lab[nb[s]], mylab);
         }
         headc += min(k, (uint32_t)rstar + 1u);
-        warp_append<6>(cand, l, nb, queue, lvl_qstart, lvl_tail, cur, tailc, lane);
+        warp_append<6, false>(cand, l, nb, queue, lvl_qstart, lvl_tail, cur, tailc, lane);
         __syncwarp();
         if (ball) {
             intr++;
@@ -903,21 +918,25 @@ static constexpr int F2_MAXPIX = 1 << 17;
 
 // GAVAIL: the "floodable" bitmap stays in global memory (L2) instead of shared memory: 1 KB of shared memory per tile, so
 // every tile of a batch is resident at once (no second wave) and more warps hide the load latencies.
-template <bool GAVAIL>
+// SLEV (with GAVAIL): the tails of the tile's level FIFOs and a bitmap of the levels that hold entries live in shared
+// memory (levcap levels per tile), so an append costs no L2 round trip and the next level is found by bit scans.
+template <bool GAVAIL, bool SLEV>
 __global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict__ tiles, int ntiles,
                                                           const uint32_t *__restrict__ lab_all, const uint16_t *__restrict__ lv16_all,
                                                           uint32_t *__restrict__ availw_all, uint32_t *__restrict__ queue,
                                                           const uint32_t *__restrict__ lvl_qstart, uint32_t *__restrict__ lvl_head,
                                                           uint32_t *__restrict__ lvl_tail, const uint32_t *__restrict__ tile_lvl,
                                                           const uint32_t *__restrict__ seedlist, const uint32_t *__restrict__ tile_seed,
-                                                          int nwords_max, uint32_t *__restrict__ stats) {
+                                                          int nwords_max, int levcap, uint32_t *__restrict__ stats) {
     extern __shared__ uint32_t f2_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wid = blockIdx.x * F2_WARPS + warp;
     if (wid >= ntiles) return;
     const Tile t = tiles[wid];
     uint32_t *avail = GAVAIL ? availw_all + (t.base >> 5) : f2_smem + (size_t)warp * (nwords_max + F2_HASH);
-    uint32_t *claim = GAVAIL ? f2_smem + (size_t)warp * F2_HASH : avail + nwords_max;
+    const int lvwords = (levcap + 31) >> 5;
+    uint32_t *claim = GAVAIL ? f2_smem + (size_t)warp * (F2_HASH + (SLEV ? levcap + lvwords : 0)) : avail + nwords_max;
+    uint32_t *stail = claim + F2_HASH, *snz = stail + levcap;   // SLEV only
     const uint16_t *lv16 = lv16_all + t.base;
     const int W = t.W, H = t.H;
     const int npix = H * W, nwords = (npix + 31) >> 5;
@@ -927,6 +946,10 @@ __global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict
     if (sb == se) return;
     if (!GAVAIL) {
         for (int w = lane; w < nwords; w += 32) avail[w] = availw_all[(t.base >> 5) + w];
+        __syncwarp();
+    }
+    if (SLEV) {
+        for (int j = lane; j < levcap + lvwords; j += 32) stail[j] = 0;
         __syncwarp();
     }
     uint32_t steps = 0, intr = 0;
@@ -941,40 +964,67 @@ __global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict
             l[0] = v[0] ? lo + lv16[px] : 0;
             ent[0] = v[0] ? ((lab_all[t.base + px] << 17) | px) : 0;
             if (v[0]) maxr = max(maxr, l[0]);
-            warp_append<1>(v, l, ent, queue, lvl_qstart, lvl_tail, NONE32, dummy_tail, lane);
+            warp_append<1, SLEV>(v, l, ent, queue, lvl_qstart, lvl_tail, NONE32, dummy_tail, lane, stail, snz, lo);
             __syncwarp();
         }
         cur = __reduce_max_sync(FULL, maxr);
         headc = 0;
-        tailc = __ldcg(&lvl_tail[cur]);
+        tailc = SLEV ? stail[cur - lo] : __ldcg(&lvl_tail[cur]);
     }
     uint32_t qs = lvl_qstart[cur];
     uint32_t pre_level = NONE32, pre_head = 0, pre_tail = 0, pre_entry = 0;
     for (;;) {
         if (headc == tailc) {
-            if (lane == 0) {
-                __stcg(&lvl_head[cur], headc);
-                __stcg(&lvl_tail[cur], tailc);
-            }
-            __syncwarp();
             bool found = false;
-            long long r0 = (long long)cur - 1;
-            while (r0 >= (long long)lo) {
-                long long r = r0 - lane;
-                bool ne = false;
-                if (r >= (long long)lo) ne = __ldcg(&lvl_tail[r]) != __ldcg(&lvl_head[r]);
-                unsigned b = __ballot_sync(FULL, ne);
-                if (b) {
-                    cur = (uint32_t)(r0 - (__ffs(b) - 1));
-                    found = true;
-                    break;
+            if (SLEV) {
+                // level exhausted: clear its bit, the next level is the highest set bit below it
+                if (lane == 0) {
+                    __stcg(&lvl_head[cur], headc);
+                    stail[cur - lo] = tailc;
+                    snz[(cur - lo) >> 5] &= ~(1u << ((cur - lo) & 31));
                 }
-                r0 -= 32;
+                __syncwarp();
+                const int r = (int)(cur - lo);
+                for (int wtop = (r - 1) >> 5; r > 0 && wtop >= 0; wtop -= 32) {
+                    const int wi = wtop - lane;
+                    uint32_t wv = wi >= 0 ? snz[wi] : 0u;
+                    if (wi == ((r - 1) >> 5) && (r & 31)) wv &= (1u << (r & 31)) - 1u;
+                    const unsigned bb = __ballot_sync(FULL, wv != 0);
+                    if (bb) {
+                        const int src = __ffs(bb) - 1;
+                        const uint32_t wsel = __shfl_sync(FULL, wv, src);
+                        cur = lo + (uint32_t)((wtop - src) * 32 + 31 - __clz(wsel));
+                        found = true;
+                        break;
+                    }
+                }
+                if (!found) break;
+                headc = __ldcg(&lvl_head[cur]);
+                tailc = stail[cur - lo];
+            } else {
+                if (lane == 0) {
+                    __stcg(&lvl_head[cur], headc);
+                    __stcg(&lvl_tail[cur], tailc);
+                }
+                __syncwarp();
+                long long r0 = (long long)cur - 1;
+                while (r0 >= (long long)lo) {
+                    long long r = r0 - lane;
+                    bool ne = false;
+                    if (r >= (long long)lo) ne = __ldcg(&lvl_tail[r]) != __ldcg(&lvl_head[r]);
+                    unsigned b = __ballot_sync(FULL, ne);
+                    if (b) {
+                        cur = (uint32_t)(r0 - (__ffs(b) - 1));
+                        found = true;
+                        break;
+                    }
+                    r0 -= 32;
+                }
+                if (!found) break;
+                headc = __ldcg(&lvl_head[cur]);
+                tailc = __ldcg(&lvl_tail[cur]);
             }
-            if (!found) break;
-            headc = __ldcg(&lvl_head[cur]);
-            tailc = __ldcg(&lvl_tail[cur]);
-            qs = lvl_qstart[cur];
+            qs = __ldg(&lvl_qstart[cur]);
             continue;
         }
         steps++;
@@ -1048,7 +1098,7 @@ __global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict
         // prefetch the next batch of this level (what is queued so far) behind the append
         pre_level = cur, pre_head = headc, pre_tail = tailc;
         pre_entry = headc + lane < tailc ? __ldcg(&queue[qs + headc + lane]) : 0;
-        warp_append<4>(cand, l, ent, queue, lvl_qstart, lvl_tail, cur, tailc, lane);
+        warp_append<4, SLEV>(cand, l, ent, queue, lvl_qstart, lvl_tail, cur, tailc, lane, stail, snz, lo);
         __syncwarp();
         if (ball) {
             intr++;
@@ -1059,13 +1109,20 @@ __global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict
             mx = __reduce_max_sync(FULL, mx);
             if (lane == 0) {
                 __stcg(&lvl_head[cur], headc);
-                __stcg(&lvl_tail[cur], tailc);
+                if (SLEV) {
+                    stail[cur - lo] = tailc;
+                    if (headc != tailc)
+                        snz[(cur - lo) >> 5] |= 1u << ((cur - lo) & 31);
+                    else
+                        snz[(cur - lo) >> 5] &= ~(1u << ((cur - lo) & 31));
+                } else
+                    __stcg(&lvl_tail[cur], tailc);
             }
             __syncwarp();
             cur = mx;
             headc = __ldcg(&lvl_head[cur]);
-            tailc = __ldcg(&lvl_tail[cur]);
-            qs = lvl_qstart[cur];
+            tailc = SLEV ? stail[cur - lo] : __ldcg(&lvl_tail[cur]);
+            qs = __ldg(&lvl_qstart[cur]);
         }
     }
     if (lane == 0 && stats) {
@@ -1754,23 +1811,40 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
         const int nwords_max = (int)((maxpix + 31) / 32);
         // bitmap in shared memory only when every tile of the batch is resident then anyway (16 tiles per SM); otherwise
         // it stays in global memory and all tiles run in one wave
-        const bool gavail = g_flood_version == 3 || (g_flood_version != 2 && ntiles > 148 * 16);
-        const size_t smem = gavail ? (size_t)F2_WARPS * F2_HASH * 4 : (size_t)F2_WARPS * (nwords_max + F2_HASH) * 4;
+        const bool gavail = g_flood_version == 3 || g_flood_version == 4 || (g_flood_version != 2 && ntiles > 148 * 16);
+        // level tails + occupancy bits in shared memory when they leave room for every tile of the batch to be resident
+        // (host sync: the largest number of levels in one tile)
+        int levcap = 0;
+        bool slev = false;
+        if (gavail && g_flood_version != 3) {
+            BS_LAUNCH(k_tile_nlev_max, cdiv(ntiles, 256), 256, 0, s, tile_lvl.as<uint32_t>(), ntiles, d_tot + 7);
+            uint32_t h_nlev = 0;
+            BS_CUDA(cudaMemcpyAsync(&h_nlev, d_tot + 7, 4, cudaMemcpyDeviceToHost, s));
+            BS_CUDA(cudaStreamSynchronize(s));
+            levcap = (int)h_nlev + 1;
+            const size_t per_tile = (size_t)(F2_HASH + levcap + (levcap + 31) / 32) * 4 + 1024;   // + 1 KB the driver reserves per CTA
+            const size_t tiles_per_sm = (size_t)(ntiles + 147) / 148;
+            slev = per_tile * std::min<size_t>(tiles_per_sm, 32) <= 227 * 1024;
+        }
+        const size_t smem = gavail ? (size_t)F2_WARPS * (F2_HASH + (slev ? levcap + (levcap + 31) / 32 : 0)) * 4
+                                   : (size_t)F2_WARPS * (nwords_max + F2_HASH) * 4;
         static bool attr_set = false;
         if (!attr_set) {
-            BS_CUDA(cudaFuncSetAttribute(k_flood2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            BS_CUDA(cudaFuncSetAttribute(k_flood2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             attr_set = true;
         }
-        if (gavail)
-            BS_LAUNCH(k_flood2<true>, cdiv(ntiles, F2_WARPS), 32 * F2_WARPS, smem, s, dt, ntiles, lab.as<uint32_t>(), lv16.as<uint16_t>(),
-                      availw.as<uint32_t>(), queue.as<uint32_t>(), lvl_qstart.as<uint32_t>(), lvl_head.as<uint32_t>(),
-                      lvl_tail.as<uint32_t>(), tile_lvl.as<uint32_t>(), seedlist.as<uint32_t>(), tile_seed.as<uint32_t>(),
-                      nwords_max, fstats.as<uint32_t>());
+#define BS_FLOOD2(G_, S_)                                                                                                    \
+    BS_LAUNCH((k_flood2<G_, S_>), cdiv(ntiles, F2_WARPS), 32 * F2_WARPS, smem, s, dt, ntiles, lab.as<uint32_t>(),             \
+              lv16.as<uint16_t>(), availw.as<uint32_t>(), queue.as<uint32_t>(), lvl_qstart.as<uint32_t>(),                   \
+              lvl_head.as<uint32_t>(), lvl_tail.as<uint32_t>(), tile_lvl.as<uint32_t>(), seedlist.as<uint32_t>(),            \
+              tile_seed.as<uint32_t>(), nwords_max, levcap, fstats.as<uint32_t>())
+        if (slev)
+            BS_FLOOD2(true, true);
+        else if (gavail)
+            BS_FLOOD2(true, false);
         else
-            BS_LAUNCH(k_flood2<false>, cdiv(ntiles, F2_WARPS), 32 * F2_WARPS, smem, s, dt, ntiles, lab.as<uint32_t>(), lv16.as<uint16_t>(),
-                      availw.as<uint32_t>(), queue.as<uint32_t>(), lvl_qstart.as<uint32_t>(), lvl_head.as<uint32_t>(),
-                      lvl_tail.as<uint32_t>(), tile_lvl.as<uint32_t>(), seedlist.as<uint32_t>(), tile_seed.as<uint32_t>(),
-                      nwords_max, fstats.as<uint32_t>());
+            BS_FLOOD2(false, false);
+#undef BS_FLOOD2
         g_prof.mark("s1.flood_scatter", s);
         BS_LAUNCH(k_scatter_labels, dim3((unsigned)std::min<long long>(std::max<long long>((maxpix + 1023) / 1024, 1), 2048), ntiles), 256, 0, s, dt, tile_q.as<uint32_t>(), queue.as<uint32_t>(), lab.as<uint32_t>());
     } else {

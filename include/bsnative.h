@@ -189,7 +189,7 @@ int bs_debug_fetch(const bs_plan *p, const char *name, void *dst_host, int64_t *
  * stream when enabled via bs_set_profiling(1). names/values up to cap entries. */
 int bs_set_debug(int on);
 /* flood kernel: 0 = automatic, 1 = global-memory flood (v1), 2 = v2 with the tile bitmap in shared memory,
- * 3 = v2 with the tile bitmap in global memory (every tile resident at once) */
+ * 3 = v2 with the tile bitmap in global memory (every tile resident at once), 4 = 3 + level tails in shared memory */
 int bs_set_flood_version(int v);
 /* agglomeration kernel: 0 = automatic (parallel merges; shared memory when a block's graph fits, else a global slab),
  * 1 = single warp on global slabs, 2 = single warp in shared memory, 3 = parallel merges on global slabs */

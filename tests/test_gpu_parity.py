@@ -144,13 +144,13 @@ def test_edt_and_flood_intermediates():
 
 def test_flood_versions_agree():
     """the flood kernels (1: global-memory v1, 2: v2 with the bitmap in shared memory, 3: v2 with the bitmap in global
-    memory, 0: automatic choice) are the same function"""
+    memory, 4: 3 + level tails in shared memory, 0: automatic choice) are the same function"""
     from bootstrapper_b200 import native
     from bootstrapper_b200.post.pipeline import segment_blockwise
     from bootstrapper_b200.synth import synth_affs
     affs = torch.from_numpy(synth_affs((6, 200, 200), seed=11)).cuda()
     out = []
-    for v in (1, 2, 3, 0):
+    for v in (1, 2, 3, 4, 0):
         native.set_flood_version(v)
         try:
             out.append(segment_blockwise(affs, {}, (3, 100, 100), (1, 12, 12))["fragments"].clone())
