@@ -227,6 +227,21 @@ def test_full_size_properties():
         prev = n
         # every segment id is the smallest fragment id it contains
         assert bool((seg <= frags).all())
+    # the kernel variants chosen by batch size (flood with the bitmap in shared / global memory, level tables in shared
+    # memory; agglomeration sequential / parallel merges) are the same function at this size too
+    for fv, av in ((2, 2), (4, 0), (3, 3)):
+        try:
+            native.set_flood_version(fv)
+            native.set_agglom_version(av)
+            r2 = segment_blockwise(affs, {}, (25, 250, 250), (3, 31, 31))
+        finally:
+            native.set_flood_version(0)
+            native.set_agglom_version(0)
+        assert torch.equal(r2["fragments"], frags)
+        assert all(torch.equal(a, b) for a, b in zip(r2["edges"][:2], r["edges"][:2]))
+        assert torch.equal(r2["edges"][2].view(torch.int32), es.view(torch.int32))      # NaN-safe bit comparison
+        for thr in r["segs"]:
+            assert torch.equal(r2["segs"][thr], r["segs"][thr])
 
 
 # ---------------------------------------------------------------- single-shot path (BASELINE config 1)
