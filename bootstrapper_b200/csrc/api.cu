@@ -22,6 +22,8 @@ int components_multi(Plan &P, const uint64_t *nodes, int64_t n, const uint64_t *
 int plan_node_ids(Plan &P, uint64_t *out, long long *n_out, cudaStream_t s);
 int cc_affs(const void *affs, int dtype, const uint8_t *mask, int Z, int Y, int X, float thr, int remove_debris, uint64_t *frags_out,
             uint64_t *seg_out, int64_t *n_out, cudaStream_t s);
+int shift_affinities(const void *affs, int dtype, const uint8_t *mask, int Z, int Y, int X, int has_sigma, const int *radius,
+                     const double *const *w_host, int has_bias, const double *bias, float *out, cudaStream_t s);
 int synth_affs(void *out, int dtype, const int32_t *shape, const int32_t *offset, uint64_t seed, cudaStream_t s);
 }  // namespace bs
 
@@ -292,6 +294,17 @@ int bs_cc_affs(const void *affs, int aff_dtype, const uint8_t *mask, int Z, int 
     BS_ARG(aff_dtype == BS_DTYPE_U8 || aff_dtype == BS_DTYPE_F32, "bs_cc_affs: aff_dtype must be u8 or f32");
     init_mempool();
     return cc_affs(affs, aff_dtype, mask, Z, Y, X, threshold, remove_debris, frags_out, seg_out, n_out, (cudaStream_t)stream);
+}
+
+int bs_shift_affinities(const void *affs, int aff_dtype, const uint8_t *mask, int Z, int Y, int X, const int32_t *radius,
+                        const double *const *weights, const double *bias, float *out, void *stream) {
+    BS_ARG(affs && out, "bs_shift_affinities: null argument");
+    BS_ARG(aff_dtype == BS_DTYPE_U8 || aff_dtype == BS_DTYPE_F32, "bs_shift_affinities: aff_dtype must be u8 or f32");
+    const int has_sigma = radius && weights && (radius[0] >= 0 || radius[1] >= 0 || radius[2] >= 0);
+    if (has_sigma)
+        for (int d = 0; d < 3; d++) BS_ARG(radius[d] < 0 || (radius[d] * 2 + 1 <= BS_SIGMA_MAXW && weights[d]), "bs_shift_affinities: bad gaussian kernel");
+    init_mempool();
+    return shift_affinities(affs, aff_dtype, mask, Z, Y, X, has_sigma, radius, weights, bias != nullptr, bias, out, (cudaStream_t)stream);
 }
 
 int bs_synth_affs(void *out, int aff_dtype, const int32_t *shape, const int32_t *offset, const int32_t *vol_shape,

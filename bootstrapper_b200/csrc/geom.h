@@ -30,6 +30,12 @@ struct Tile {
     }
 };
 
+// 1-D gaussian kernels of the sigma shift as scipy builds them (device pointers), per spatial axis; radius < 0: skipped
+struct GaussWeights {
+    int radius[3];
+    const double *w[3];
+};
+
 struct Blk {
     long long block_id;      // daisy block id (cantor number of the block index)
     int idx[3];              // block grid index

@@ -25,6 +25,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "geom.h"
 
@@ -93,26 +94,30 @@ struct PreRef {          // the seed_eps pre-pass tile (= read ROI of the block)
     int oz, oy, ox, H, W, pad_;
 };
 struct ShiftView {
-    int has_bias, has_eps;
+    int has_bias, has_eps, has_sigma;
     double bias[3];
     double eps;
     const uint32_t *D2;      // squared distance to the nearest seed, per pre-pass tile pixel
+    const void *G;           // gaussian-filtered affinities [3][gstride] in the pre-pass tile layout (double / float)
+    size_t gstride;
     const PreRef *pre;       // per main tile
 };
 
 // inmask: voxel inside the volume and not masked out (else the normalised affinity is 0.0, to which the shift is added)
 template <typename T>
 __device__ __forceinline__ bool boundary_shifted(const T *a, size_t n, size_t i, bool inmask, int ndim, const ShiftView &S,
-                                                 double dist);
+                                                 double dist, long long q);
 template <>
 __device__ __forceinline__ bool boundary_shifted<uint8_t>(const uint8_t *a, size_t n, size_t i, bool inmask, int ndim,
-                                                          const ShiftView &S, double dist) {
+                                                          const ShiftView &S, double dist, long long q) {
     double v[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         if (c == 0 && ndim == 2) continue;
         double x = inmask ? __ddiv_rn((double)a[(size_t)c * n + i], 255.0) : 0.0;
-        double sh = S.has_bias ? S.bias[c] : 0.0;                      // zeros += bias
+        double sh = 0.0;
+        if (S.has_sigma) sh = __dsub_rn(((const double *)S.G)[(size_t)c * S.gstride + q], x);   // zeros += gaussian - affs
+        if (S.has_bias) sh = __dadd_rn(sh, S.bias[c]);                 // shift += bias
         if (S.has_eps) sh = __dsub_rn(sh, __dmul_rn(S.eps, dist));     // shift -= seed_eps * D
         v[c] = __dadd_rn(x, sh);
     }
@@ -121,13 +126,15 @@ __device__ __forceinline__ bool boundary_shifted<uint8_t>(const uint8_t *a, size
 }
 template <>
 __device__ __forceinline__ bool boundary_shifted<float>(const float *a, size_t n, size_t i, bool inmask, int ndim,
-                                                        const ShiftView &S, double dist) {
+                                                        const ShiftView &S, double dist, long long q) {
     float v[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         if (c == 0 && ndim == 2) continue;
         float x = inmask ? a[(size_t)c * n + i] : 0.0f;
-        float sh = S.has_bias ? __double2float_rn(S.bias[c]) : 0.0f;                                     // float32(0 + bias)
+        float sh = 0.0f;
+        if (S.has_sigma) sh = __fsub_rn(((const float *)S.G)[(size_t)c * S.gstride + q], x);             // float32 arrays
+        if (S.has_bias) sh = __double2float_rn(__dadd_rn((double)sh, S.bias[c]));                        // float32(shift + bias)
         if (S.has_eps) sh = __double2float_rn(__dsub_rn((double)sh, __dmul_rn(S.eps, dist)));            // float32(shift - eps * D)
         v[c] = __fadd_rn(x, sh);
     }
@@ -173,12 +180,13 @@ __global__ void __launch_bounds__(256) k_mask_rowdist(const Tile *__restrict__ t
                     size_t i = inside ? rowoff + gx : 0;
                     bool inmask = inside && (!A.mask || A.mask[i] > 0);
                     double dist = 0.0;
-                    if (S.has_eps) {
+                    long long q = 0;
+                    if (S.has_eps || S.has_sigma) {
                         const PreRef pr = S.pre[blockIdx.y];
-                        long long q = pr.base + ((long long)(gz - pr.oz) * pr.H + (gy - pr.oy)) * pr.W + (gx - pr.ox);
-                        dist = __dsqrt_rn((double)S.D2[q]);
+                        q = pr.base + ((long long)(gz - pr.oz) * pr.H + (gy - pr.oy)) * pr.W + (gx - pr.ox);
+                        if (S.has_eps) dist = __dsqrt_rn((double)S.D2[q]);
                     }
-                    m = boundary_shifted<T>(a, nvol, i, inmask, t.ndim, S, dist);
+                    m = boundary_shifted<T>(a, nvol, i, inmask, t.ndim, S, dist, q);
                 }
             } else {
                 if (x < W) m = pred[pbase + x] == NONE32;
@@ -1530,16 +1538,17 @@ static int rowdist_grid_rows(const std::vector<Tile> &tiles) {
     return std::min(std::max((rows + 7) / 8, 1), 4096);
 }
 
-// seed_eps pre-pass (watershed_frags.py:131-139) on the 3-D read ROI of every block of the batch:
-//   boundary_mask = mean(affs) > 0.5; seeds = (maximum_filter(EDT(mask), msd) == EDT(mask)) & mask;
-//   D = EDT(seeds == 0)            -> D2 (exact squared distances; the sqrt is taken where the shift is applied)
-template <typename T>
-static int seed_distance_prepass(Plan &P, const std::vector<int> &bidx, AffView A, DevBuf &D2, std::vector<PreRef> &refs,
-                                 cudaStream_t s) {
-    const bs_ws_config &cfg = P.cfg;
+// 3-D tiles = read ROIs of the blocks of a batch: what the seed_eps and sigma pre-passes work on
+struct PreTiles {
     std::vector<Tile> pt;
-    long long Ppre = 0, maxpix = 0;
-    refs.clear();
+    std::vector<PreRef> refs;   // per block of the batch
+    long long Ppre = 0;
+    TileDims td;
+    DevBuf d_pt;
+};
+
+static int build_pretiles(Plan &P, const std::vector<int> &bidx, PreTiles &R, cudaStream_t s) {
+    long long maxpix = 0;
     for (size_t bi = 0; bi < bidx.size(); bi++) {
         const Blk &b = P.blocks[bidx[bi]];
         Tile t;
@@ -1549,28 +1558,39 @@ static int seed_distance_prepass(Plan &P, const std::vector<int> &bidx, AffView 
         t.wD = t.D, t.wH = t.H, t.wW = t.W;
         t.block = (int)bi;
         t.ndim = 3;
-        t.base = Ppre;
+        t.base = R.Ppre;
         t.wbase = 0;
         PreRef r;
-        r.base = Ppre, r.oz = t.gz, r.oy = t.gy, r.ox = t.gx, r.H = t.H, r.W = t.W, r.pad_ = 0;
-        refs.push_back(r);
+        r.base = R.Ppre, r.oz = t.gz, r.oy = t.gy, r.ox = t.gx, r.H = t.H, r.W = t.W, r.pad_ = 0;
+        R.refs.push_back(r);
         long long np = (long long)t.D * t.H * t.W;
-        Ppre += np;
+        R.Ppre += np;
         maxpix = std::max(maxpix, np);
         t.set_divs();
-        pt.push_back(t);
+        R.pt.push_back(t);
     }
-    BS_ARG(Ppre < (1LL << 31), "stage1: seed_eps pre-pass too large for 32-bit tile indices (lower max_batch_voxels)");
-    for (auto &t : pt) BS_ARG(t.W <= MAXW, "stage1: tile wider than 4096 voxels is not supported");
-    const int np_tiles = (int)pt.size();
-    TileDims td;
-    td.ntiles = np_tiles, td.maxpix = maxpix, td.maxD = td.maxH = td.maxW = 0;
-    for (auto &t : pt) td.maxH = std::max(td.maxH, t.H), td.maxW = std::max(td.maxW, t.W), td.maxD = std::max(td.maxD, t.D);
-    DevBuf d_pt, msk, g, d2, tmpA, tmpB, par, sb, flags, tmax;
-    BS_TRY(d_pt.alloc(sizeof(Tile) * np_tiles, s));
-    BS_CUDA(cudaMemcpyAsync(d_pt.p, pt.data(), sizeof(Tile) * np_tiles, cudaMemcpyHostToDevice, s));
+    BS_ARG(R.Ppre < (1LL << 31), "stage1: seed_eps / sigma pre-pass too large for 32-bit tile indices (lower max_batch_voxels)");
+    for (auto &t : R.pt) BS_ARG(t.W <= MAXW, "stage1: tile wider than 4096 voxels is not supported");
+    R.td.ntiles = (int)R.pt.size(), R.td.maxpix = maxpix, R.td.maxD = R.td.maxH = R.td.maxW = 0;
+    for (auto &t : R.pt)
+        R.td.maxH = std::max(R.td.maxH, t.H), R.td.maxW = std::max(R.td.maxW, t.W), R.td.maxD = std::max(R.td.maxD, t.D);
+    BS_TRY(R.d_pt.alloc(sizeof(Tile) * R.pt.size(), s));
+    BS_CUDA(cudaMemcpyAsync(R.d_pt.p, R.pt.data(), sizeof(Tile) * R.pt.size(), cudaMemcpyHostToDevice, s));
     BS_CUDA(cudaStreamSynchronize(s));   // pt is a host-staged copy
-    const Tile *dt = d_pt.as<Tile>();
+    return BS_OK;
+}
+
+// seed_eps pre-pass (watershed_frags.py:131-139) on the 3-D read ROI of every block of the batch:
+//   boundary_mask = mean(affs) > 0.5; seeds = (maximum_filter(EDT(mask), msd) == EDT(mask)) & mask;
+//   D = EDT(seeds == 0)            -> D2 (exact squared distances; the sqrt is taken where the shift is applied)
+template <typename T>
+static int seed_distance_prepass(Plan &P, const PreTiles &R, AffView A, DevBuf &D2, cudaStream_t s) {
+    const bs_ws_config &cfg = P.cfg;
+    const long long Ppre = R.Ppre;
+    const int np_tiles = (int)R.pt.size();
+    const TileDims &td = R.td;
+    const Tile *dt = R.d_pt.as<Tile>();
+    DevBuf msk, g, d2, tmpA, tmpB, par, sb, flags, tmax;
     BS_TRY(msk.alloc(Ppre, s));
     BS_TRY(g.alloc(Ppre * 2, s));
     BS_TRY(d2.alloc(Ppre * 4, s));
@@ -1583,13 +1603,40 @@ static int seed_distance_prepass(Plan &P, const std::vector<int> &bidx, AffView 
     BS_TRY(D2.alloc(Ppre * 4, s));
     ShiftView none;
     memset(&none, 0, sizeof(none));
-    const dim3 gr((unsigned)rowdist_grid_rows(pt), np_tiles);
+    const dim3 gr((unsigned)rowdist_grid_rows(R.pt), np_tiles);
     BS_LAUNCH((k_mask_rowdist<T, 0>), gr, 256, 0, s, dt, A, none, nullptr, msk.as<uint8_t>(), g.as<uint16_t>(), flags.as<uint32_t>());
     BS_TRY(launch_edt(dt, td, true, g.as<uint16_t>(), tmpA.as<uint32_t>(), d2.as<uint32_t>(), tmax.as<uint32_t>(), s));
     BS_TRY(launch_seeds(dt, td, true, cfg.min_seed_distance, d2.as<uint32_t>(), msk.as<uint8_t>(), tmpA.as<uint32_t>(),
                         tmpB.as<uint32_t>(), par.as<uint32_t>(), sb.as<uint32_t>(), s));
     BS_LAUNCH((k_mask_rowdist<T, 2>), gr, 256, 0, s, dt, A, none, par.as<uint32_t>(), nullptr, g.as<uint16_t>(), nullptr);
     BS_TRY(launch_edt(dt, td, true, g.as<uint16_t>(), tmpA.as<uint32_t>(), D2.as<uint32_t>(), tmax.as<uint32_t>(), s));
+    return BS_OK;
+}
+
+// sigma pre-pass (watershed_frags.py:121-122): gaussian_filter of the block's (normalised, masked, zero-filled) read-ROI
+// affinities in the dtype numpy holds them in (float64 for uint8 input, float32 for float32 input) -- gauss.cu
+template <typename T, typename Out>
+int gauss_tiles(const Tile *d_tiles, int ntiles, long long maxpix, const T *affs, const uint8_t *mask, int volZw, int volZ, int volY,
+                int volX, int z0, const GaussWeights &gw, size_t cstride, Out *bufA, Out *bufB, Out **result, cudaStream_t s);
+
+template <typename T>
+static int gauss_prepass(Plan &P, const PreTiles &R, AffView A, DevBuf &bufA, DevBuf &bufB, DevBuf &wdev, const void **G, cudaStream_t s) {
+    typedef typename std::conditional<sizeof(T) == 1, double, float>::type Out;
+    const bs_ws_config &cfg = P.cfg;
+    BS_TRY(bufA.alloc(sizeof(Out) * 3 * (size_t)R.Ppre, s));
+    BS_TRY(bufB.alloc(sizeof(Out) * 3 * (size_t)R.Ppre, s));
+    BS_TRY(wdev.alloc(sizeof(double) * 3 * BS_SIGMA_MAXW, s));
+    BS_CUDA(cudaMemcpyAsync(wdev.p, cfg.sigma_w, sizeof(double) * 3 * BS_SIGMA_MAXW, cudaMemcpyHostToDevice, s));
+    BS_CUDA(cudaStreamSynchronize(s));
+    GaussWeights gw;
+    for (int d = 0; d < 3; d++) {
+        gw.radius[d] = cfg.sigma_radius[d];
+        gw.w[d] = wdev.as<double>() + (size_t)d * BS_SIGMA_MAXW;
+    }
+    Out *res = nullptr;
+    BS_TRY((gauss_tiles<T, Out>(R.d_pt.as<Tile>(), (int)R.pt.size(), R.td.maxpix, (const T *)A.p, A.mask, A.Zw, A.Z, A.Y, A.X, A.z0, gw,
+                                (size_t)R.Ppre, bufA.as<Out>(), bufB.as<Out>(), &res, s)));
+    *G = res;
     return BS_OK;
 }
 
@@ -1703,20 +1750,29 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
         S.has_bias = cfg.has_bias, S.has_eps = cfg.has_seed_eps;
         for (int d = 0; d < 3; d++) S.bias[d] = cfg.bias[d];
         S.eps = cfg.seed_eps;
-        DevBuf D2, d_pre;
-        if (cfg.has_seed_eps) {
-            g_prof.mark("s1.seed_eps", s);
-            std::vector<PreRef> brefs, trefs(ntiles);
-            BS_TRY(seed_distance_prepass<T>(P, bidx, A, D2, brefs, s));
-            for (int i = 0; i < ntiles; i++) trefs[i] = brefs[tiles[i].block];
+        S.has_sigma = cfg.has_sigma;
+        DevBuf D2, d_pre, gA, gB, gW;
+        PreTiles R;
+        if (cfg.has_seed_eps || cfg.has_sigma) {
+            g_prof.mark("s1.shift_prepass", s);
+            BS_TRY(build_pretiles(P, bidx, R, s));
+            if (cfg.has_seed_eps) {
+                BS_TRY(seed_distance_prepass<T>(P, R, A, D2, s));
+                S.D2 = D2.as<uint32_t>();
+            }
+            if (cfg.has_sigma) {
+                BS_TRY(gauss_prepass<T>(P, R, A, gA, gB, gW, &S.G, s));
+                S.gstride = (size_t)R.Ppre;
+            }
+            std::vector<PreRef> trefs(ntiles);
+            for (int i = 0; i < ntiles; i++) trefs[i] = R.refs[tiles[i].block];
             BS_TRY(d_pre.alloc(sizeof(PreRef) * ntiles, s));
             BS_CUDA(cudaMemcpyAsync(d_pre.p, trefs.data(), sizeof(PreRef) * ntiles, cudaMemcpyHostToDevice, s));
             BS_CUDA(cudaStreamSynchronize(s));   // trefs is a host-staged copy
-            S.D2 = D2.as<uint32_t>();
             S.pre = d_pre.as<PreRef>();
             g_prof.mark("s1.mask_rowdist", s);
         }
-        if (cfg.has_bias || cfg.has_seed_eps)
+        if (cfg.has_bias || cfg.has_seed_eps || cfg.has_sigma)
             BS_LAUNCH((k_mask_rowdist<T, 1>), gr, 256, 0, s, dt, A, S, nullptr, msk.as<uint8_t>(), g.as<uint16_t>(),
                       tileflags.as<uint32_t>());
         else

@@ -14,6 +14,20 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbsnative.so")
 
 BS_DTYPE_U8, BS_DTYPE_F32 = 0, 1
+SIGMA_MAXW = 129
+
+
+def gaussian_weights(sigma, truncate=4.0):
+    """The 1-D kernel scipy.ndimage.gaussian_filter builds for one axis (order 0): radius = int(truncate * sigma + 0.5),
+    weights exp(-x^2 / (2 sigma^2)) normalised to sum 1 (float64).  Returns (radius, weights); radius -1 when scipy skips
+    the axis (sigma <= 1e-15)."""
+    sd = float(sigma)
+    if not sd > 1e-15:
+        return -1, np.zeros(0)
+    radius = int(truncate * sd + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sd * sd) * x ** 2)
+    return radius, phi / phi.sum()
 
 
 class BsError(RuntimeError):
@@ -30,6 +44,7 @@ class WsConfig(C.Structure):
         ("keep_cheaper", C.c_int32), ("crop_relabel", C.c_int32), ("block_begin", C.c_int32),
         ("block_end", C.c_int32), ("win_z0", C.c_int32), ("win_z", C.c_int32), ("filter_fragments", C.c_double), ("max_batch_voxels", C.c_int64),
         ("has_bias", C.c_int32), ("has_seed_eps", C.c_int32), ("bias", C.c_double * 3), ("seed_eps", C.c_double),
+        ("has_sigma", C.c_int32), ("sigma_radius", C.c_int32 * 3), ("sigma_w", (C.c_double * SIGMA_MAXW) * 3),
     ]
 
 
@@ -37,7 +52,7 @@ EXPORTS = [
     "bs_last_error", "bs_launch_count", "bs_version", "bs_config_size", "bs_plan_create", "bs_plan_destroy", "bs_plan_num_blocks",
     "bs_plan_block_info", "bs_plan_set_owned", "bs_stage1_fragments", "bs_stage1_num_nodes", "bs_stage1_get_nodes",
     "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_plan_node_ids", "bs_stage2_agglomerate", "bs_stage2_num_edges",
-    "bs_stage2_get_edges", "bs_waterz_segment", "bs_cc_affs", "bs_connected_components", "bs_stage3_components", "bs_relabel", "bs_stage3_relabel", "bs_watershed_from_affinities",
+    "bs_stage2_get_edges", "bs_waterz_segment", "bs_cc_affs", "bs_shift_affinities", "bs_connected_components", "bs_stage3_components", "bs_relabel", "bs_stage3_relabel", "bs_watershed_from_affinities",
     "bs_synth_affs", "bs_debug_fetch", "bs_set_debug", "bs_set_profiling", "bs_get_profile",
     "bs_release_scratch", "bs_set_flood_version", "bs_set_agglom_version", "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
 ]
@@ -134,7 +149,7 @@ class Plan:
     def __init__(self, vol_shape, block_size, context, aff_dtype, roi_offset=None, roi_shape=None, n_channels=3,
                  fragments_in_xy=True, min_seed_distance=10, filter_fragments=0.1, remove_debris=64,
                  queue_bins=256, keep_cheaper=True, block_begin=-1, block_end=-1, max_batch_voxels=0, win_z0=0, win_z=0,
-                 bias=None, seed_eps=None):
+                 bias=None, seed_eps=None, sigma=None):
         cfg = WsConfig()
         roi_offset = roi_offset if roi_offset is not None else (0, 0, 0)
         roi_shape = roi_shape if roi_shape is not None else vol_shape
@@ -167,6 +182,19 @@ class Plan:
                 cfg.bias[d] = float(b[d])
         cfg.has_seed_eps = 0 if seed_eps is None else 1
         cfg.seed_eps = float(seed_eps or 0.0)
+        cfg.has_sigma = 0
+        if sigma is not None:   # watershed_frags.py:121-122: gaussian_filter(affs, sigma=(0, *sigma))
+            if len(sigma) != 3:
+                raise BsError("sigma must have one entry per spatial axis (z, y, x)")
+            for d in range(3):
+                r, w = gaussian_weights(sigma[d])
+                if 2 * r + 1 > SIGMA_MAXW:
+                    raise BsError(f"sigma {sigma[d]} is too large (kernel radius {r} > {(SIGMA_MAXW - 1) // 2})")
+                cfg.sigma_radius[d] = r
+                for i, v in enumerate(w):
+                    cfg.sigma_w[d][i] = float(v)
+                if r >= 0:
+                    cfg.has_sigma = 1
         self.cfg = cfg
         self.roi_shape = tuple(int(v) for v in roi_shape)
         if win_z > 0:
@@ -346,6 +374,36 @@ def cc_affs(affs, threshold, remove_debris=0, mask=None):
                             Z, Y, X, C.c_float(float(threshold)), C.c_int(int(remove_debris or 0)), _dev(frags), _dev(seg),
                             C.byref(n), _stream()))
     return frags, seg, n.value
+
+
+def shift_affinities(affs, mask=None, sigma=None, bias=None):
+    """affs_data + shift of the single-shot paths (post/watershed.py:262-303, connected_components.py:52-77) as a
+    float32 tensor (3, Z, Y, X); affs: CUDA tensor (C >= 3, Z, Y, X) uint8 or float32."""
+    _, Z, Y, X = affs.shape
+    out = torch.empty((3, Z, Y, X), dtype=torch.float32, device=affs.device)
+    rad = (C.c_int32 * 3)(-1, -1, -1)
+    wptr = (C.c_void_p * 3)()
+    keep = []
+    if sigma is not None:
+        if len(sigma) != 3:
+            raise BsError("sigma must have one entry per spatial axis (z, y, x)")
+        for d in range(3):
+            r, w = gaussian_weights(sigma[d])
+            if 2 * r + 1 > SIGMA_MAXW:
+                raise BsError(f"sigma {sigma[d]} is too large")
+            rad[d] = r
+            w = np.ascontiguousarray(w, dtype=np.float64)
+            keep.append(w)
+            wptr[d] = w.ctypes.data if r >= 0 else None
+    b = None
+    if bias is not None:
+        bl = list(bias) if isinstance(bias, (list, tuple)) else [bias] * 3
+        if len(bl) != 3:
+            raise BsError("bias must be a scalar or have one entry per affinity channel (3)")
+        b = (C.c_double * 3)(*[float(v) for v in bl])
+    _check(lib().bs_shift_affinities(_dev(affs), C.c_int(_aff_dtype(affs)), _dev(mask, torch.uint8) if mask is not None else None,
+                                     Z, Y, X, rad, wptr, b, _dev(out), _stream()))
+    return out
 
 
 def watershed_from_affinities(affs, fragments_in_xy, min_seed_distance):

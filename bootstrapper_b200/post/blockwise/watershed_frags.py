@@ -57,7 +57,7 @@ class WatershedFrags(BlockwiseTask):
             p = self.params
             self._plan_obj = self._make_plan(fragments_in_xy=p["fragments_in_xy"], min_seed_distance=p["min_seed_distance"],
                                              filter_fragments=p["filter_fragments"], remove_debris=p["remove_debris"],
-                                             bias=p["bias"], seed_eps=p["seed_eps"])
+                                             bias=p["bias"], seed_eps=p["seed_eps"], sigma=p["sigma"])
         return self._plan_obj
 
     def _mask_dev(self):

@@ -20,11 +20,15 @@ def cc_blockwise(config):
 def cc_in_memory(affs, threshold=0.5, remove_debris=0, mask=None, sigma=None, noise_eps=None):
     """affs: CUDA tensor (C >= 3, Z, Y, X) uint8 or float32.  Returns (fragments, segmentation) as int64 tensors
     holding the reference's uint32 ids."""
-    if sigma is not None or noise_eps is not None:
-        raise NotImplementedError("cc parameters sigma / noise_eps are not implemented in the CUDA path yet")
+    if noise_eps is not None:
+        raise NotImplementedError("cc parameter noise_eps (an unseeded RNG in the reference) is not implemented in the CUDA path")
     if not affs.is_cuda:
         raise native.BsError("cc_in_memory needs the affinities on a CUDA device (no CPU fallback)")
-    frags, seg, _ = native.cc_affs(affs.contiguous(), threshold, remove_debris, mask)
+    affs = affs.contiguous()
+    if sigma is not None:   # affs_data += gaussian_filter(affs_data, (0, *sigma)) - affs_data, after the mask (:62-77)
+        affs = native.shift_affinities(affs, mask=mask, sigma=sigma)
+        mask = None
+    frags, seg, _ = native.cc_affs(affs, threshold, remove_debris, mask)
     return frags, seg
 
 

@@ -15,7 +15,7 @@ WS_DEFAULTS = dict(  # reference segment.py:11-23
     filter_fragments=0.1, remove_debris=64, thresholds=[0.2, 0.35, 0.5], merge_function="mean",
     sigma=None, noise_eps=None, bias=None)
 
-UNSUPPORTED = ("sigma", "noise_eps")   # sigma: scipy gaussian_filter replay; noise_eps: unseeded RNG in the reference
+UNSUPPORTED = ("noise_eps",)   # an unseeded RNG in the reference (watershed_frags.py:119-120): not reproducible
 
 
 def resolve_ws_params(params):
@@ -46,9 +46,8 @@ def segment_simple(affs, params=None, mask=None):
         raise native.BsError("segment_simple needs the affinities on a CUDA device (no CPU fallback)")
     p = dict(WS_DEFAULTS)
     p.update(params or {})
-    for k in ("sigma", "noise_eps", "bias"):
-        if p.get(k) is not None:
-            raise NotImplementedError(f"ws parameter {k!r} is not implemented in the CUDA path yet")
+    if p.get("noise_eps") is not None:
+        raise NotImplementedError("ws parameter 'noise_eps' (an unseeded RNG in the reference) is not implemented in the CUDA path")
     if p["merge_function"] not in SIMPLE_MERGE_FUNCTIONS:
         raise KeyError(p["merge_function"])
     if p["merge_function"] != "mean":
@@ -56,9 +55,14 @@ def segment_simple(affs, params=None, mask=None):
     affs = affs[:3]
     if affs.shape[0] == 2:   # post/watershed.py:305-308
         affs = torch.cat([torch.zeros_like(affs[:1]), affs], 0)
-    if mask is not None:     # affs_data *= (mask > 0)   (post/watershed.py:271-272)
-        affs = affs * (mask > 0).to(affs.dtype)
     affs = affs.contiguous()
+    if p.get("sigma") is not None or p.get("bias") is not None:
+        # affs_data += shift, in float32 as the reference computes it (post/watershed.py:284-303); the mask is applied
+        # before the shift, and everything downstream (fragments, waterz) sees the shifted affinities
+        affs = native.shift_affinities(affs, mask=None if mask is None else (mask > 0).to(torch.uint8).contiguous(),
+                                       sigma=p.get("sigma"), bias=p.get("bias"))
+    elif mask is not None:   # affs_data *= (mask > 0)   (post/watershed.py:271-272)
+        affs = (affs * (mask > 0).to(affs.dtype)).contiguous()
     vol_shape = tuple(affs.shape[1:])
     plan = native.Plan(vol_shape, vol_shape, (0, 0, 0), native._aff_dtype(affs), n_channels=3,
                        fragments_in_xy=p["fragments_in_xy"], min_seed_distance=p["min_seed_distance"],
@@ -87,7 +91,7 @@ def make_plan(affs, params, block_size, context=None, roi=None, **kw):
     return native.Plan(vol_shape, block_size, context, native._aff_dtype(affs), roi_offset=roi_offset,
                        roi_shape=roi_shape, n_channels=affs.shape[0], fragments_in_xy=p["fragments_in_xy"],
                        min_seed_distance=p["min_seed_distance"], filter_fragments=p["filter_fragments"],
-                       remove_debris=p["remove_debris"], bias=p["bias"], seed_eps=p["seed_eps"], **kw), p
+                       remove_debris=p["remove_debris"], bias=p["bias"], seed_eps=p["seed_eps"], sigma=p["sigma"], **kw), p
 
 
 def segment_blockwise(affs, params=None, block_size=None, context=None, roi=None, mask=None, plan=None,

@@ -136,7 +136,7 @@ class ShardedSegmenter:
             self.plan = native.Plan(self.vol_shape, self.block_size, self.context, dtype_code,
                                     fragments_in_xy=self.p["fragments_in_xy"], min_seed_distance=self.p["min_seed_distance"],
                                     filter_fragments=self.p["filter_fragments"], remove_debris=self.p["remove_debris"],
-                                    bias=self.p["bias"], seed_eps=self.p["seed_eps"],
+                                    bias=self.p["bias"], seed_eps=self.p["seed_eps"], sigma=self.p["sigma"],
                                     block_begin=g["l0"] if self.world > 1 else -1, block_end=g["l1"] if self.world > 1 else -1,
                                     **win)
             self.block_ids, _, _ = self.plan.block_info()

@@ -25,6 +25,7 @@ extern "C" {
 #define BS_ERR_OVERFLOW (-3)
 #define BS_ERR_STATE (-4)
 
+#define BS_SIGMA_MAXW 129   /* gaussian kernels up to radius 64 (sigma <= 16) */
 #define BS_DTYPE_U8 0
 #define BS_DTYPE_F32 1
 
@@ -57,6 +58,10 @@ typedef struct bs_ws_config {
     int32_t has_seed_eps;      /* ws_params.seed_eps given                                    */
     double bias[3];            /* per channel (a scalar bias is replicated by the caller)    */
     double seed_eps;           /* shift -= seed_eps * EDT(seeds == 0)                        */
+    /* ws_params.sigma: shift += gaussian_filter(affs, (0, *sigma)) - affs.  The caller passes scipy's kernel:   */
+    int32_t has_sigma;
+    int32_t sigma_radius[3];   /* per axis (z, y, x): int(4 * sigma + 0.5); -1 = sigma of that axis <= 1e-15 */
+    double sigma_w[3][BS_SIGMA_MAXW]; /* 2 * radius + 1 normalised weights per axis                          */
 } bs_ws_config;
 
 typedef struct bs_plan bs_plan;
@@ -166,6 +171,15 @@ int bs_stage3_relabel(bs_plan *p, const uint64_t *frags, int64_t n_vox, const ui
  *   (seg_out may be NULL); n_out (host) = number of components. */
 int bs_cc_affs(const void *affs, int aff_dtype, const uint8_t *mask, int Z, int Y, int X, float threshold, int remove_debris,
                uint64_t *frags_out, uint64_t *seg_out, int64_t *n_out, void *stream);
+
+/* ---- shifts of the single-shot paths ----------------------------------------------------
+ * replaces the numpy / scipy block of simple_watershed and cc_affs (post/watershed.py:262-303,
+ * connected_components.py:52-77): out = affs_data + shift in float32, with affs_data = affs[:3].astype(float32)
+ * (/ 255 for uint8) * (mask > 0) and shift = (gaussian_filter(affs_data, (0, *sigma)) - affs_data) + bias.
+ *   radius[3] / weights[3] (host): scipy's kernel per axis as in bs_ws_config (NULL / -1 = no sigma); bias[3] or NULL;
+ *   out device (3, Z, Y, X) float32. */
+int bs_shift_affinities(const void *affs, int aff_dtype, const uint8_t *mask, int Z, int Y, int X, const int32_t *radius,
+                        const double *const *weights, const double *bias, float *out, void *stream);
 
 /* ---- post/ws.py plug point ----------------------------------------------------------
  * replaces: watershed_from_affinities(affs, max_affinity_value, fragments_in_xy,

@@ -11,12 +11,17 @@ from scipy.sparse import coo_matrix
 from scipy.sparse.csgraph import connected_components
 
 
-def hard_affs(affs, threshold, mask=None):
-    """connected_components.py:52-56,66,81: float32 normalise, mask multiply, compare."""
+def hard_affs(affs, threshold, mask=None, sigma=None):
+    """connected_components.py:52-81: float32 normalise, mask multiply, optional gaussian shift, compare."""
+    from scipy.ndimage import gaussian_filter
     data = affs[:3]
     data = data.astype(np.float32) / 255.0 if data.dtype == np.uint8 else data.astype(np.float32)
     if mask is not None:
         data = data * (mask > 0).astype(np.uint8)
+    if sigma is not None:
+        shift = np.zeros_like(data)
+        shift += gaussian_filter(data, sigma=(0, *sigma)) - data
+        data = data + shift
     return data > threshold
 
 
@@ -56,8 +61,8 @@ def remove_small_objects(x, min_size):
     return out
 
 
-def cc_affs(affs, threshold=0.5, remove_debris=0, mask=None):
-    frags = compute_connected_component_segmentation(hard_affs(affs, threshold, mask))
+def cc_affs(affs, threshold=0.5, remove_debris=0, mask=None, sigma=None):
+    frags = compute_connected_component_segmentation(hard_affs(affs, threshold, mask, sigma))
     seg = frags
     if remove_debris > 0:
         seg = remove_small_objects(frags.astype(np.int64), remove_debris).astype(frags.dtype)

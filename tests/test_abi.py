@@ -69,6 +69,19 @@ def test_ws_params_resolution():
     from bootstrapper_b200.post.pipeline import resolve_ws_params
     p = resolve_ws_params({"bias": [-0.1, -0.2, -0.2], "seed_eps": 0.01, "fragments_in_xy": False})
     assert p["seed_eps"] == 0.01 and p["thresholds"] == [0.2, 0.35, 0.5]
-    for bad in ({"sigma": [1, 1, 1]}, {"noise_eps": 0.001}, {"epsilon_agglomerate": 0.05}, {"merge_function": "hist_quant_75"}):
+    assert resolve_ws_params({"sigma": [1, 2, 2]})["sigma"] == [1, 2, 2]
+    for bad in ({"noise_eps": 0.001}, {"epsilon_agglomerate": 0.05}, {"merge_function": "hist_quant_75"}):
         with pytest.raises(NotImplementedError):
             resolve_ws_params(bad)
+
+
+def test_gaussian_weights_match_scipy():
+    """the kernel handed to libbsnative is scipy's own (scipy.ndimage._filters._gaussian_kernel1d, order 0, truncate 4)"""
+    import numpy as np
+    from scipy.ndimage import _filters
+    from bootstrapper_b200.native import gaussian_weights
+    for sigma in (0.3, 0.7, 1.0, 2.0, 3.3, 8.0):
+        r, w = gaussian_weights(sigma)
+        assert r == int(4.0 * float(sigma) + 0.5)
+        assert np.array_equal(w, _filters._gaussian_kernel1d(float(sigma), 0, r)[::-1])
+    assert gaussian_weights(0)[0] == -1

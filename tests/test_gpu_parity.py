@@ -67,6 +67,10 @@ CASES = [
     ((16, 96, 96), (8, 48, 48), (2, 6, 6), {"fragments_in_xy": False, "seed_eps": 0.01}, np.uint8),
     ((12, 120, 120), (6, 60, 60), (1, 8, 8), {"seed_eps": 0.02}, np.uint8),
     ((12, 100, 100), (6, 50, 50), (2, 6, 6), {"seed_eps": 0.01, "bias": [-0.02, -0.03, -0.03], "fragments_in_xy": False}, np.float32),
+    # sigma: scipy's gaussian_filter replayed bit for bit (float64 for uint8 input, float32 for float32 input)
+    ((12, 120, 120), (6, 60, 60), (2, 8, 8), {"sigma": [1, 2, 2]}, np.uint8),
+    ((12, 100, 100), (6, 50, 50), (2, 6, 6), {"sigma": [0, 1.5, 0.8], "fragments_in_xy": False}, np.float32),
+    ((12, 100, 100), (6, 50, 50), (1, 6, 6), {"sigma": [3, 1, 1], "bias": [-0.05, -0.05, -0.05], "seed_eps": 0.01}, np.uint8),
 ]
 
 
@@ -255,6 +259,8 @@ def _same_partition(a, b):
 
 
 SIMPLE_CASES = [
+    ((10, 128, 128), {"sigma": [1, 2, 2], "bias": [-0.05, -0.1, -0.1]}, np.uint8),      # shifted affinities feed waterz too
+    ((8, 96, 96), {"sigma": [0, 1, 1.5]}, np.float32),
     ((10, 128, 128), {}, np.float32),
     ((10, 128, 128), {}, np.uint8),
     ((8, 96, 96), {"fragments_in_xy": False, "thresholds": [0.5, 0.1, 0.3]}, np.float32),    # unsorted thresholds
@@ -325,6 +331,35 @@ def test_cc_affs_golden_and_oracle():
         frags, seg, n = native.cc_affs(torch.from_numpy(affs).cuda(), thr, rd)
         assert np.array_equal(frags.cpu().numpy(), rf.astype(np.int64))
         assert np.array_equal(seg.cpu().numpy(), rs.astype(np.int64))
+    # sigma shift (connected_components.py:73-77) through the in-memory driver
+    from bootstrapper_b200.post.connected_components import cc_in_memory
+    affs = synth_affs((10, 90, 110), seed=8, dtype=np.uint8)
+    mask = (np.random.default_rng(3).random((10, 90, 110)) < 0.9).astype(np.uint8)
+    rf, rs = occ.cc_affs(affs, 0.55, 20, mask, sigma=[1, 1.5, 1.5])
+    frags, seg = cc_in_memory(torch.from_numpy(affs).cuda(), 0.55, 20, torch.from_numpy(mask).cuda(), sigma=[1, 1.5, 1.5])
+    assert np.array_equal(frags.cpu().numpy(), rf.astype(np.int64)) and np.array_equal(seg.cpu().numpy(), rs.astype(np.int64))
+
+
+def test_shift_affinities_matches_scipy():
+    """bs_shift_affinities against numpy + scipy.ndimage.gaussian_filter, bit for bit (float32 semantics of the single-shot paths)"""
+    from scipy.ndimage import gaussian_filter
+    from bootstrapper_b200 import native
+    rng = np.random.default_rng(0)
+    for dtype in (np.uint8, np.float32):
+        a = (rng.random((3, 9, 40, 37)) * (255 if dtype == np.uint8 else 1)).astype(dtype)
+        mask = (rng.random((9, 40, 37)) < 0.8).astype(np.uint8)
+        for sigma, bias in [([1, 2, 2], None), ([0, 0.7, 3.3], [-0.1, 0.05, 0.2]), (None, 0.25), ([4, 0, 0], None)]:
+            data = a.astype(np.float32) / 255.0 if dtype == np.uint8 else a.astype(np.float32)
+            data = data * (mask > 0).astype(np.uint8)
+            shift = np.zeros_like(data)
+            if sigma is not None:
+                shift += gaussian_filter(data, sigma=(0, *sigma)) - data
+            if bias is not None:
+                b = [bias] * 3 if isinstance(bias, float) else bias
+                shift += np.array([b]).reshape((-1, 1, 1, 1))
+            want = data + shift
+            got = native.shift_affinities(torch.from_numpy(a).cuda(), torch.from_numpy(mask).cuda(), sigma, bias).cpu().numpy()
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (dtype, sigma, bias)
 
 
 def test_agglomeration_kernels_agree():
