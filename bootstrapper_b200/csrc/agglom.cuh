@@ -55,7 +55,8 @@ size_t agglom_par_static_smem();
 int agglom_par_launch(const AggBlk *blks, const int *list, int nlist, const AggArrays &A, float threshold, int keep_cheaper,
                       bool u8, bool sum64, uint32_t Ecap, uint32_t Ncap, cudaStream_t s);
 int agglom_par_global_launch(const AggBlk *blks, const int *list, int nlist, const AggArrays &A, float threshold, int keep_cheaper,
-                             bool u8, unsigned char *work, const unsigned long long *woff, cudaStream_t s);
+                             bool u8, unsigned char *work, const unsigned long long *woff, uint32_t Ncap_max, bool hybrid,
+                             cudaStream_t s);
 
 // agglom_pq.cu: waterz with the non-discretised queue (single-shot ws path) on one region graph.
 struct PqRequest {

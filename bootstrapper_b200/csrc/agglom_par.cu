@@ -55,6 +55,10 @@ size_t agglom_par_bytes(uint32_t Ecap, uint32_t Ncap, bool sum64, int idx) {
     return (b + 255) & ~(size_t)255;
 }
 size_t agglom_par_static_smem() { return sizeof(ParCtl) + 64; }
+// hybrid layout of the global-slab kernel: queue bins, occupancy bits, union-find parents and cluster stamps (16 bit)
+// stay in shared memory -- they sit on every dependent-load chain of a round -- and only the edge / list arrays live in
+// the slab
+static size_t agglom_par_hyb_bytes(uint32_t Ncap) { return 32 + 4 * (size_t)NBINS * 4 + 2 * (size_t)Ncap * 2; }
 
 template <typename IdxT>
 __device__ __forceinline__ uint32_t pfind(IdxT *ufp, uint32_t x) {
@@ -69,13 +73,15 @@ __device__ __forceinline__ uint32_t pfind(IdxT *ufp, uint32_t x) {
     }
 }
 
-template <bool U8, typename SumT, typename IdxT, bool SMEM>
+template <bool U8, typename SumT, typename IdxT, bool SMEM, bool HYB>
 __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__restrict__ blks, const int *__restrict__ list,
                                                               AggArrays A, float threshold, int keep_cheaper, uint32_t Ecap_,
                                                               uint32_t Ncap_, unsigned char *__restrict__ gwork,
                                                               const unsigned long long *__restrict__ gwoff) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ ParCtl C;
+    static_assert(!(SMEM && HYB), "the hybrid layout belongs to the global-slab kernel");
+    using NodT = typename std::conditional<HYB, uint16_t, IdxT>::type;   // union-find parents, cluster stamps
     constexpr uint32_t N16 = (uint32_t)(IdxT)~(IdxT)0;                 // "none" in the index type
     constexpr uint32_t DEADBIT = 1u << (8 * sizeof(IdxT) - 1);        // etd = time | dead flag
     const int bi = list[blockIdx.x];
@@ -89,14 +95,17 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
     SumT *esum = (SumT *)work;
     float *escore = (float *)(esum + Ecap);
     uint32_t *ecnt = (uint32_t *)(escore + Ecap);
-    uint32_t *occ = ecnt + Ecap;
-    IdxT *eu = (IdxT *)(occ + 8);
+    uint32_t *occ = HYB ? (uint32_t *)smraw : ecnt + Ecap;
+    IdxT *eu = (IdxT *)(ecnt + Ecap + 8);
     IdxT *ev = eu + Ecap, *etd = ev + Ecap, *anext = etd + Ecap;
     IdxT *qent = anext + 2 * Ecap;
     IdxT *qcnext = qent + QC * PQCH;
-    IdxT *ufp = qcnext + QC, *stamp = ufp + Ncap, *ahead = stamp + Ncap, *tnode = ahead + Ncap, *clevel = tnode + Ncap,
-         *mark = clevel + Ncap, *markgen = mark + Ncap;
-    IdxT *bhc = markgen + Ncap, *btc = bhc + NBINS, *bho = btc + NBINS, *btf = bho + NBINS;
+    IdxT *nodes0 = qcnext + QC;
+    IdxT *ahead = nodes0 + 2 * Ncap, *tnode = ahead + Ncap, *clevel = tnode + Ncap, *mark = clevel + Ncap, *markgen = mark + Ncap;
+    IdxT *bhc = HYB ? (IdxT *)(smraw + 32) : markgen + Ncap;
+    IdxT *btc = bhc + NBINS, *bho = btc + NBINS, *btf = bho + NBINS;
+    NodT *ufp = HYB ? (NodT *)(smraw + 32 + 4 * NBINS * sizeof(IdxT)) : (NodT *)nodes0;
+    NodT *stamp = ufp + Ncap;
 
     const uint32_t *geu = A.eu + B.ebase, *gev = A.ev + B.ebase, *gcnt = A.ecnt + B.ebase;
     const unsigned long long *gsum = A.esum + B.ebase;
@@ -107,7 +116,7 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
 
     // ---- load the block's graph (all warps)
     for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
-        ufp[i] = (IdxT)i;
+        ufp[i] = (NodT)i;
         stamp[i] = 0;
         ahead[i] = N16;
         tnode[i] = (IdxT)i;
@@ -240,6 +249,9 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
     __syncthreads();
 
     uint32_t n_pops = 0, n_stale = 0, n_dead = 0, n_iter = 0, n_chunk = 0, n_append = 0;
+#if defined(BS_PROBE) && BS_PROBE == 2
+    uint32_t n_c2 = 0, n_full = 0, n_short = 0, n_low = 0, n_conf = 0;
+#endif
 
     auto alloc_chunk = [&]() -> uint32_t {
         uint32_t c;
@@ -336,26 +348,50 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
 
     uint32_t clock = 0, nmerge = 0;
     int minbin = 0;
+    // warp 0: the next round's batch -- lowest occupied bin from `minbin` on and up to PQCH entry ids (the rest of its head
+    // chunk and, if the bin goes on, the start of the next chunk).  Runs at the end of phase C, so the loads of the edge
+    // ids overlap the merges of phase D, which never touch the queue.
+    uint32_t e = 0, k = 0, hc = 0, ho = 0, nxc = N16;
+    int cb = 0;
+    bool act = false, have = false;
+    auto select = [&]() {
+        uint32_t w = lane < 8 ? occ[lane] : 0u;
+        if (lane == (minbin >> 5))
+            w &= ~((1u << (minbin & 31)) - 1u);
+        else if (lane < (minbin >> 5))
+            w = 0;
+        const unsigned nzb = __ballot_sync(FULL, w != 0);
+        have = nzb != 0;
+        act = false;
+        if (!have) return;
+        const int wl = __ffs(nzb) - 1;
+        const uint32_t ww = __shfl_sync(FULL, w, wl);
+        cb = wl * 32 + __ffs(ww) - 1;
+        minbin = cb;
+        hc = bhc[cb];
+        ho = bho[cb];
+        const uint32_t tc = btc[cb], tf = btf[cb];
+        const uint32_t k1 = (hc == tc ? tf : (uint32_t)PQCH) - ho;
+        nxc = hc == tc ? N16 : (uint32_t)qcnext[hc];
+        const uint32_t k2 = hc == tc ? 0u : min((uint32_t)PQCH - k1, nxc == tc ? tf : (uint32_t)PQCH);
+        k = k1 + k2;
+        act = (uint32_t)lane < k;
+        e = act ? ((uint32_t)lane < k1 ? (uint32_t)qent[hc * PQCH + ho + lane] : (uint32_t)qent[nxc * PQCH + (lane - k1)]) : 0u;
+    };
+    if (warp == 0) select();
 #ifdef BS_PROBE
     long long tA = 0, tB = 0, tC = 0, tD = 0, t0 = clock64();
 #endif
     for (;;) {
         // ================= phase A (warp 0): batch, classification, first cut, candidate merges
-        uint32_t e = 0, ru = 0, rv = 0, k = 0, hc = 0, ho = 0;
+        uint32_t ru = 0, rv = 0;
         int cls = 1;   // 0 stop, 1 dead/inactive, 2 stale, 3 merge
         float newsc = 0.f;
-        int nbin = 0, cb = 0;
+        int nbin = 0;
         unsigned mbits = 0;
-        bool act = false;
         if (warp == 0) {
-            uint32_t w = lane < 8 ? occ[lane] : 0u;
-            if (lane == (minbin >> 5))
-                w &= ~((1u << (minbin & 31)) - 1u);
-            else if (lane < (minbin >> 5))
-                w = 0;
-            unsigned nzb = __ballot_sync(FULL, w != 0);
-            if (!nzb || fail || n_iter > 64u * E + 4096u) {
-                if (nzb) fail = true;
+            if (!have || fail || n_iter > 64u * E + 4096u) {
+                if (have) fail = true;
                 if (lane == 0) {
                     C.exit_ = 1;
                     C.ncand = 0;
@@ -363,34 +399,22 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
                     C.cut2 = NONE32;
                 }
             } else {
-                const int wl = __ffs(nzb) - 1;
-                const uint32_t ww = __shfl_sync(FULL, w, wl);
-                cb = wl * 32 + __ffs(ww) - 1;
-                minbin = cb;
                 n_iter++;
-                hc = bhc[cb];
-                ho = bho[cb];
-                const uint32_t tc = btc[cb], tf = btf[cb];
-                // up to PQCH entries: the rest of the head chunk and, if the bin goes on, the start of the next chunk
-                const uint32_t k1 = (hc == tc ? tf : (uint32_t)PQCH) - ho;
-                const uint32_t nx = hc == tc ? N16 : (uint32_t)qcnext[hc];
-                const uint32_t k2 = hc == tc ? 0u : min((uint32_t)PQCH - k1, nx == tc ? tf : (uint32_t)PQCH);
-                k = k1 + k2;
-                act = (uint32_t)lane < k;
                 if (act) {
-                    e = (uint32_t)lane < k1 ? qent[hc * PQCH + ho + lane] : qent[nx * PQCH + (lane - k1)];
-                    float sc = escore[e];
-                    uint32_t td = etd[e];
+                    // every field of the entry in one round trip (the slab is L2 / HBM resident)
+                    const float sc = escore[e];
+                    const uint32_t td = etd[e], u0 = eu[e], v0 = ev[e], c0 = ecnt[e];
+                    const SumT s0 = esum[e];
                     if (sc >= threshold)
                         cls = 0;
                     else if (td & DEADBIT)
                         cls = 1;
                     else {
-                        ru = pfind<IdxT>(ufp, eu[e]);
-                        rv = pfind<IdxT>(ufp, ev[e]);
+                        ru = pfind<NodT>(ufp, u0);
+                        rv = pfind<NodT>(ufp, v0);
                         if (stamp[ru] > td || stamp[rv] > td) {
                             cls = 2;
-                            newsc = edge_score<U8>((unsigned long long)esum[e], ecnt[e]);
+                            newsc = edge_score<U8>((unsigned long long)s0, c0);
                             nbin = score_bin(newsc, NBINS);
                         } else
                             cls = 3;
@@ -491,7 +515,7 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
                 if (h != N16) {
                     ne = h >> 1;
                     if (ne != me) {
-                        uint32_t x1 = pfind<IdxT>(ufp, eu[ne]), x2 = pfind<IdxT>(ufp, ev[ne]);
+                        uint32_t x1 = pfind<NodT>(ufp, eu[ne]), x2 = pfind<NodT>(ufp, ev[ne]);
                         x = x1 == mb ? x2 : x1;
                         other_cand(x);
                         ins = true;
@@ -533,7 +557,7 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
                 if (h != N16) {
                     uint32_t ae = h >> 1;
                     if (ae != me) {
-                        uint32_t x1 = pfind<IdxT>(ufp, eu[ae]), x2 = pfind<IdxT>(ufp, ev[ae]);
+                        uint32_t x1 = pfind<NodT>(ufp, eu[ae]), x2 = pfind<NodT>(ufp, ev[ae]);
                         x = x1 == ma ? x2 : x1;
                         other_cand(x);
                     } else
@@ -557,6 +581,12 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
             const int mycls = cls & 0xff;
             const uint32_t cut1 = (uint32_t)(cls >> 16);
             int tcls = (cls >> 8) & 0xff;   // 0 stop, 2 lower, 4 wait, 0xff exhausted
+#if defined(BS_PROBE) && BS_PROBE == 2
+            if (cut < cut1) n_c2++;
+            else if (tcls == 0xff) { if (k == PQCH) n_full++; else n_short++; }
+            else if (tcls == 2) n_low++;
+            else if (tcls == 4) n_conf++;
+#endif
             if (cut < cut1) tcls = 4;
             const bool lower_trig = tcls == 2;
             const bool redo = act && mycls == 2 && ((uint32_t)lane < cut || ((uint32_t)lane == cut && lower_trig));
@@ -575,7 +605,7 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
                 // the head moves by `consumed` entries, possibly into the next chunk (the append may have grown the tail)
                 uint32_t hcur = hc, ho2 = ho + consumed;
                 if (ho2 >= (uint32_t)PQCH && hcur != (uint32_t)btc[cb]) {
-                    const uint32_t nx2 = qcnext[hcur];
+                    const uint32_t nx2 = nxc != N16 ? nxc : (uint32_t)qcnext[hcur];   // the append may have linked a new chunk
                     __syncwarp();
                     if (lane == 0) qcnext[hcur] = (IdxT)q_free;
                     q_free = hcur;
@@ -607,7 +637,8 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
             nmerge += nm;
             if (tcls == 0 || fail) {
                 if (lane == 0) C.exit_ = 1;   // stop after this round's merges
-            }
+            } else
+                select();
         }
 #ifdef BS_PROBE
         { long long t1 = clock64(); tC += t1 - t0; t0 = t1; }
@@ -655,7 +686,7 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
                 walk(head_b, tail_b, [&](uint32_t h) {
                     if (h != N16) {
                         uint32_t ne = h >> 1;
-                        uint32_t x1 = pfind<IdxT>(ufp, eu[ne]), x2 = pfind<IdxT>(ufp, ev[ne]);
+                        uint32_t x1 = pfind<NodT>(ufp, eu[ne]), x2 = pfind<NodT>(ufp, ev[ne]);
                         uint32_t x = x1 == mb ? x2 : x1;
                         mark[x] = (IdxT)ne;
                         markgen[x] = (IdxT)myclock;
@@ -671,7 +702,7 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
                 walk(head_a, tail_a, [&](uint32_t h) {
                     if (h != N16) {
                         uint32_t ae = h >> 1;
-                        uint32_t x1 = pfind<IdxT>(ufp, eu[ae]), x2 = pfind<IdxT>(ufp, ev[ae]);
+                        uint32_t x1 = pfind<NodT>(ufp, eu[ae]), x2 = pfind<NodT>(ufp, ev[ae]);
                         resolve(ae, x1 == ma ? x2 : x1);
                     }
                 });
@@ -685,8 +716,8 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
                         anext[tail_a] = (IdxT)head_b;
                 }
                 ahead[ma] = (IdxT)head_a;
-                ufp[mb] = (IdxT)ma;
-                stamp[ma] = (IdxT)myclock;
+                ufp[mb] = (NodT)ma;
+                stamp[ma] = (NodT)myclock;
                 const uint32_t t = nc + mynum, ta = tnode[ma], tbn = tnode[mb];
                 const uint32_t lvl = max((uint32_t)clevel[ma], (uint32_t)clevel[mb]) + 1;
                 tparent[ta] = t;
@@ -716,7 +747,13 @@ __global__ void __launch_bounds__(32 * PNW) k_agglomerate_par(const AggBlk *__re
         A.counters[6 * bi + 3] = n_iter;
         A.counters[6 * bi + 4] = n_chunk;
         A.counters[6 * bi + 5] = n_append;
-#ifdef BS_PROBE
+#if defined(BS_PROBE) && BS_PROBE == 2
+        A.counters[6 * bi + 0] = n_c2;
+        A.counters[6 * bi + 1] = n_full;
+        A.counters[6 * bi + 2] = n_short;
+        A.counters[6 * bi + 4] = n_low;
+        A.counters[6 * bi + 5] = n_conf;
+#elif defined(BS_PROBE)
         A.counters[6 * bi + 0] = (uint32_t)(tA / 16);
         A.counters[6 * bi + 1] = (uint32_t)(tB / 16);
         A.counters[6 * bi + 2] = (uint32_t)(tC / 16);
@@ -734,9 +771,9 @@ int agglom_par_launch(const AggBlk *blks, const int *list, int nlist, const AggA
            "agglom_par_launch: block graph does not fit in shared memory");
 #define BS_AGG_PAR(U8_, SumT_)                                                                                             \
     do {                                                                                                                   \
-        BS_CUDA(cudaFuncSetAttribute(k_agglomerate_par<U8_, SumT_, uint16_t, true>,                                        \
+        BS_CUDA(cudaFuncSetAttribute(k_agglomerate_par<U8_, SumT_, uint16_t, true, false>,                                 \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - agglom_par_static_smem()))); \
-        BS_LAUNCH((k_agglomerate_par<U8_, SumT_, uint16_t, true>), nlist, 32 * PNW, smem, s, blks, list, A, threshold,     \
+        BS_LAUNCH((k_agglomerate_par<U8_, SumT_, uint16_t, true, false>), nlist, 32 * PNW, smem, s, blks, list, A, threshold, \
                   keep_cheaper, Ecap, Ncap, nullptr, nullptr);                                                             \
     } while (0)
     if (u8 && !sum64)
@@ -750,14 +787,31 @@ int agglom_par_launch(const AggBlk *blks, const int *list, int nlist, const AggA
 }
 
 int agglom_par_global_launch(const AggBlk *blks, const int *list, int nlist, const AggArrays &A, float threshold, int keep_cheaper,
-                             bool u8, unsigned char *work, const unsigned long long *woff, cudaStream_t s) {
+                             bool u8, unsigned char *work, const unsigned long long *woff, uint32_t Ncap_max, bool hybrid,
+                             cudaStream_t s) {
     if (nlist == 0) return BS_OK;
-    if (u8)
-        BS_LAUNCH((k_agglomerate_par<true, unsigned long long, uint32_t, false>), nlist, 32 * PNW, 0, s, blks, list, A, threshold,
-                  keep_cheaper, 0u, 0u, work, woff);
+    // Ncap_max: the largest (padded) node count of the listed blocks.  16-bit parents / stamps hold node numbers and
+    // merge clocks below it.
+    const size_t hyb = agglom_par_hyb_bytes(Ncap_max);
+    const bool use_hyb = hybrid && Ncap_max <= 65528 && hyb + agglom_par_static_smem() <= 227 * 1024;
+#define BS_AGG_GLOB(U8_, HYB_, SM_)                                                                                         \
+    do {                                                                                                                    \
+        if (HYB_)                                                                                                           \
+            BS_CUDA(cudaFuncSetAttribute(k_agglomerate_par<U8_, unsigned long long, uint32_t, false, HYB_>,                 \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,                                       \
+                                         (int)(227 * 1024 - agglom_par_static_smem())));                                    \
+        BS_LAUNCH((k_agglomerate_par<U8_, unsigned long long, uint32_t, false, HYB_>), nlist, 32 * PNW, SM_, s, blks, list, \
+                  A, threshold, keep_cheaper, 0u, 0u, work, woff);                                                          \
+    } while (0)
+    if (u8 && use_hyb)
+        BS_AGG_GLOB(true, true, hyb);
+    else if (u8)
+        BS_AGG_GLOB(true, false, 0);
+    else if (use_hyb)
+        BS_AGG_GLOB(false, true, hyb);
     else
-        BS_LAUNCH((k_agglomerate_par<false, unsigned long long, uint32_t, false>), nlist, 32 * PNW, 0, s, blks, list, A, threshold,
-                  keep_cheaper, 0u, 0u, work, woff);
+        BS_AGG_GLOB(false, false, 0);
+#undef BS_AGG_GLOB
     return BS_OK;
 }
 

@@ -10,7 +10,7 @@ SOURCES = ["prims.cu", "plan.cu", "stage1.cu", "stage2.cu", "agglom_smem.cu", "a
 HEADERS = ["common.cuh", "geom.h", "agglom.cuh", os.path.join("..", "..", "include", "bsnative.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-         "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + (["-DBS_TRACE"] if os.environ.get("BS_TRACE") else []) + (["-DBS_PROBE"] if os.environ.get("BS_PROBE") else [])
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + (["-DBS_TRACE"] if os.environ.get("BS_TRACE") else []) + (["-DBS_PROBE=" + os.environ["BS_PROBE"]] if os.environ.get("BS_PROBE") else [])
 
 
 def needs_build():

@@ -534,7 +534,8 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
     // g_agglom_version: 0 = parallel-merge kernels (shared memory when the block fits, else a global slab),
     //                    1 = single-warp kernel on global slabs, 2 = single-warp kernel in shared memory when it fits,
     //                    3 = parallel-merge kernel on global slabs
-    const bool par = g_agglom_version == 0 || g_agglom_version == 3;
+    //                    4 = as 3 with every array in the slab (no shared-memory union-find / queue bins)
+    const bool par = g_agglom_version == 0 || g_agglom_version == 3 || g_agglom_version == 4;
     {
         const size_t limit = 227 * 1024 - (par ? agglom_par_static_smem() : 0);
         for (int i = 0; i < nown; i++) {
@@ -552,9 +553,11 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
     }
     // blocks too large for shared memory: a global-memory slab each (32-bit indices, 64-bit sums)
     std::vector<unsigned long long> h_woff(l_glob.size() + 1, 0);
+    uint32_t Nglob_max = 8;
     for (size_t k = 0; k < l_glob.size(); k++) {
         const AggBlk &a = ab[l_glob[k]];
         uint32_t Ec = (std::max<uint32_t>(a.E, 8) + 7) & ~7u, Nc = (std::max<uint32_t>(a.nv, 8) + 7) & ~7u;
+        Nglob_max = std::max(Nglob_max, Nc);
         h_woff[k + 1] = h_woff[k] + (par ? agglom_par_bytes(Ec, Nc, true, 4) : agglom_work_bytes(Ec, Nc, true, 4));
     }
     const bool any_glob = !l_glob.empty();
@@ -596,7 +599,8 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
                                  Nmax, s));
         if (any_glob)
             BS_TRY(agglom_par_global_launch(d_ab.as<AggBlk>(), d_list.as<int>() + l_smem.size(), (int)l_glob.size(), A, 1.0f,
-                                            cfg.keep_cheaper, u8, gwork.as<unsigned char>(), d_woff.as<unsigned long long>(), s));
+                                            cfg.keep_cheaper, u8, gwork.as<unsigned char>(), d_woff.as<unsigned long long>(),
+                                            Nglob_max, g_agglom_version != 4, s));
     } else {
         BS_TRY(agglom_smem_launch(d_ab.as<AggBlk>(), d_list.as<int>(), (int)l_smem.size(), A, 1.0f, cfg.keep_cheaper, u8, sum64,
                                   Emax, Nmax, s));

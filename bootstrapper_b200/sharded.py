@@ -174,14 +174,16 @@ class ShardedSegmenter:
             exchange_halos(frags, g, self.geos, self.rank, self.world, self.group)
         plan.agglomerate(affs_win, frags)
         prof.update(native.get_profile())
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        evs[0].record()
         eu, ev, es = plan.edges(affs_win.device)
         eu, ev, es = allgather_edges(eu, ev, es, self.world, self.group)
         nodes = plan.node_ids(affs_win.device)
         own = frags[g["z0"] - g["w0"]:g["z1"] - g["w0"]]
         thrs = list(self.p["thresholds"])
+        evs[1].record()
         cmap = plan.components(nodes, eu, ev, es, thrs)
+        evs[2].record()
         comps = [cmap[thr] for thr in thrs]
         luts = dict(zip(thrs, comps))
         segs = {}
@@ -189,16 +191,19 @@ class ShardedSegmenter:
         for i in range(0, len(thrs), 8):
             for thr, sg in zip(thrs[i:i + 8], plan.relabel(own, comps[i:i + 8], None if out is None else out[i:i + 8])):
                 segs[thr] = sg
-        ev1.record()
-        ev1.synchronize()
-        prof["s3.cc_relabel"] = ev0.elapsed_time(ev1)
+        evs[3].record()
+        evs[3].synchronize()
+        prof["s3.graph"] = evs[0].elapsed_time(evs[1])          # edge / node tables (+ the all-gather when sharded)
+        prof["s3.components"] = evs[1].elapsed_time(evs[2])
+        prof["s3.relabel"] = evs[2].elapsed_time(evs[3])
         self.last_profile = prof
         return dict(fragments=frags, own_fragments=own, segs=segs, luts=luts, nodes=nodes, edges=(eu, ev, es))
 
-    def run_host(self, host_affs, host_out):
-        """end-to-end with HOST buffers: pinned affinities in, fragments + segmentations out (pinned)."""
+    def run_host(self, host_affs, host_out, out=None):
+        """end-to-end with HOST buffers: pinned affinities in, fragments + segmentations out (pinned).
+        out: optional device staging buffers for the segmentations (one per threshold)"""
         affs = host_affs.to(self.device, non_blocking=True)
-        r = self.run(affs, frag_sink=host_out[0])
+        r = self.run(affs, out=out, frag_sink=host_out[0])
         for i, thr in enumerate(self.p["thresholds"]):
             host_out[1 + i].copy_(r["segs"][thr], non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -369,7 +369,7 @@ def test_agglomeration_kernels_agree():
     affs = synth_affs((20, 160, 160), seed=5)
     block, ctx = (10, 80, 80), (2, 10, 10)
     ref = _oracle(affs, {}, block, ctx)
-    for version in (1, 2, 3):   # single warp / global slab, single warp / shared memory, parallel merges / global slab
+    for version in (1, 2, 3, 4):   # single warp / global slab, single warp / shared memory, parallel merges / global slab (hybrid, plain)
         try:
             native.set_agglom_version(version)
             r = _run_gpu(affs, {}, block, ctx)
