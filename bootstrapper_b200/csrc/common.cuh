@@ -186,6 +186,19 @@ static inline FastDiv make_fastdiv(uint32_t d) {
     }
     return f;
 }
+// the same magic number computed on the device (one 64-bit division per call: hoist it out of loops)
+__device__ __forceinline__ FastDiv make_fastdiv_dev(uint32_t d) {
+    FastDiv f;
+    const uint32_t l = d <= 1 ? 0u : 32u - (uint32_t)__clz((int)(d - 1));   // ceil(log2(d))
+    if ((1ull << l) == d) {
+        f.m = 0;
+        f.sh = l;
+    } else {
+        f.m = (uint32_t)((((1ull << l) - d) << 32) / d) + 1;
+        f.sh = l - 1;
+    }
+    return f;
+}
 __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv &f) {
     if (f.m == 0) return n >> f.sh;
     uint32_t t = __umulhi(f.m, n);

@@ -914,6 +914,294 @@ __global__ void __launch_bounds__(64) k_flood(const Tile *__restrict__ tiles, in
     }
 }
 
+// ------------------------------------------------------------------ flood v3 (any tile; one CTA per tile)
+// The step semantics of k_flood with F3_NT queue entries per step instead of 32: tiles that flood v2 cannot take (3-D
+// read ROIs, slices beyond 2^17 pixels) hold millions of pixels in a few thousand levels, so a level's FIFO feeds a whole
+// CTA.  Claims resolve by the lowest (thread, slot) key -- exactly what the lowest (lane, slot) key does in one warp --
+// in a shared-memory table keyed by pixel, so nothing is written to global memory before the step's cut is known; the
+// step is cut after the first entry (in FIFO order) that queued a pixel above the current level; the ordered append
+// goes through a per-step table level -> (queue position, entries per warp).  Heads, tails and an occupancy bitmap of
+// the tile's levels live in shared memory: per level and step the dependent global accesses are the entry, the labels of
+// its neighbours and their levels.
+static constexpr int F3_NT = 512, F3_NW = F3_NT / 32, F3_SLOTS = 1024, F3_CLAIMS = 8192;
+struct F3Shared {
+    uint32_t hk[F3_SLOTS];             // level of the slot (NONE32: free)
+    uint32_t hbase[F3_SLOTS];          // queue position where this step's entries of the level start
+    uint16_t hcnt[F3_SLOTS][F3_NW];    // entries per warp, then their exclusive prefix over the warps
+    uint32_t ck[F3_CLAIMS];            // claim table: pixel ...
+    uint32_t cm[F3_CLAIMS];            // ... -> lowest (thread * 8 + slot) that wants it
+    uint32_t rstar, mx, tailc, next;
+};
+static size_t flood3_smem(int levcap) { return sizeof(F3Shared) + 4 * (size_t)(2 * levcap + (levcap + 31) / 32 + 1); }
+
+// ordered (thread-major, slot-minor) append of the block's candidates to the FIFOs of their levels.  All threads call it.
+// Every warp ranks its candidates level by level (a step touches few distinct levels per warp) and leaves one count per
+// (level slot, warp); a prefix over the warps then places the warps' runs behind the level's tail.
+// On return `tailc` is the tail of level `cur` and `mx_out` the value of S.mx.
+template <int NS>
+__device__ __forceinline__ void block_append(F3Shared &S, const bool (&valid)[NS], const uint32_t (&lvl)[NS], const uint32_t (&pix)[NS],
+                                             uint32_t *__restrict__ queue, const uint32_t *__restrict__ lvl_qstart,
+                                             uint32_t *ltail, uint32_t *lnz, uint32_t lo, uint32_t cur, uint32_t &tailc,
+                                             uint32_t &mx_out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool rem[NS];
+    uint32_t rank[NS], slot[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) rem[s] = valid[s], rank[s] = 0, slot[s] = 0;
+    for (;;) {
+        uint32_t mylo = NONE32;
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+            if (rem[s]) mylo = min(mylo, lvl[s]);
+        const uint32_t L = __reduce_min_sync(FULL, mylo);
+        if (L == NONE32) break;
+        int c = 0;
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+            if (rem[s] && lvl[s] == L) c++;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        uint32_t sl = 0;
+        if (lane == 0) {
+            uint32_t h = (L * 2654435761u) >> 22;   // 10 bits
+            for (int probes = 0;; probes++) {
+                const uint32_t old = atomicCAS(&S.hk[h], NONE32, L);
+                if (old == NONE32 || old == L) break;
+                if (probes > F3_SLOTS) __trap();    // more distinct levels in one step than the table holds
+                h = (h + 1) & (F3_SLOTS - 1);
+            }
+            S.hcnt[h][warp] = (uint16_t)total;
+            sl = h;
+        }
+        sl = __shfl_sync(FULL, sl, 0);
+        uint32_t r = (uint32_t)(incl - c);
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+            if (rem[s] && lvl[s] == L) {
+                rank[s] = r++;
+                slot[s] = sl;
+                rem[s] = false;
+            }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < F3_SLOTS; j += F3_NT) {
+        const uint32_t L = S.hk[j];
+        if (L != NONE32) {
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < F3_NW; w++) {
+                const uint32_t cw = S.hcnt[j][w];
+                S.hcnt[j][w] = (uint16_t)run;
+                run += cw;
+            }
+            const uint32_t base = L == cur ? tailc : ltail[L - lo];
+            S.hbase[j] = __ldg(&lvl_qstart[L]) + base;
+            if (L == cur)
+                S.tailc = base + run;
+            else {
+                ltail[L - lo] = base + run;
+                atomicOr(&lnz[(L - lo) >> 5], 1u << ((L - lo) & 31));
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < NS; s++)
+        if (valid[s]) __stcg(&queue[S.hbase[slot[s]] + S.hcnt[slot[s]][warp] + rank[s]], pix[s]);
+    tailc = S.tailc;
+    mx_out = S.mx;
+    __syncthreads();
+    for (int j = threadIdx.x; j < F3_SLOTS; j += F3_NT)
+        if (S.hk[j] != NONE32) {
+            S.hk[j] = NONE32;
+#pragma unroll
+            for (int w = 0; w < F3_NW; w += 2) *(uint32_t *)&S.hcnt[j][w] = 0u;
+        }
+    // the callers pass a barrier before the table is used again
+}
+
+__global__ void __launch_bounds__(F3_NT) k_flood3(const Tile *__restrict__ tiles, int ntiles, uint32_t *__restrict__ lab_all,
+                                                  const uint32_t *__restrict__ lv_all, uint32_t *__restrict__ queue,
+                                                  const uint32_t *__restrict__ lvl_qstart, const uint32_t *__restrict__ tile_lvl,
+                                                  const uint32_t *__restrict__ seedlist, const uint32_t *__restrict__ tile_seed,
+                                                  int levcap, uint32_t *__restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char f3_raw[];
+    F3Shared &S = *(F3Shared *)f3_raw;
+    uint32_t *lhead = (uint32_t *)(f3_raw + sizeof(F3Shared)), *ltail = lhead + levcap, *lnz = ltail + levcap;
+    const int wid = blockIdx.x, tid = threadIdx.x;
+    const Tile t = tiles[wid];
+    uint32_t *lab = lab_all + t.base;
+    const uint32_t *lv = lv_all + t.base;
+    const int W = t.W, H = t.H, D = t.D;
+    const uint32_t HW = (uint32_t)H * W;
+    const FastDiv fHW = make_fastdiv_dev(HW);
+    const uint32_t lo = tile_lvl[wid], hi = tile_lvl[wid + 1];
+    const uint32_t sb = tile_seed[wid], se = tile_seed[wid + 1];
+    if (lo == hi || sb == se) return;
+    for (int j = tid; j < F3_SLOTS; j += F3_NT) {
+        S.hk[j] = NONE32;
+#pragma unroll
+        for (int w = 0; w < F3_NW; w++) S.hcnt[j][w] = 0;
+    }
+    for (int j = tid; j < F3_CLAIMS; j += F3_NT) S.ck[j] = NONE32, S.cm[j] = NONE32;
+    for (int j = tid; j < 2 * levcap + (levcap + 31) / 32; j += F3_NT) lhead[j] = 0;
+    if (tid == 0) S.mx = lo, S.tailc = 0, S.rstar = NONE32, S.next = 0;
+    __syncthreads();
+    uint32_t steps = 0, intr = 0;
+    uint32_t cur = lo, tailc = 0, headc = 0, mx = 0;
+    // ---- seeds, ascending raveled index (oracle seed_tie = "index")
+    for (uint32_t s0 = sb; s0 < se; s0 += F3_NT) {
+        bool v[1];
+        uint32_t l[1], px[1];
+        v[0] = s0 + tid < se;
+        px[0] = v[0] ? seedlist[s0 + tid] : 0;
+        l[0] = v[0] ? lv[px[0]] : 0;
+        if (v[0]) atomicMax(&S.mx, l[0]);
+        uint32_t dummy_tail = 0;
+        block_append<1>(S, v, l, px, queue, lvl_qstart, ltail, lnz, lo, NONE32, dummy_tail, mx);
+        __syncthreads();
+    }
+    cur = S.mx;
+    headc = 0;
+    tailc = ltail[cur - lo];
+    uint32_t qs = lvl_qstart[cur];
+    __syncthreads();
+
+    for (;;) {
+        if (headc == tailc) {
+            // level exhausted: the next one is the highest occupied level below it (levels above are always empty)
+            if (tid == 0) {
+                lhead[cur - lo] = headc;
+                ltail[cur - lo] = tailc;
+                lnz[(cur - lo) >> 5] &= ~(1u << ((cur - lo) & 31));
+                S.next = 0;
+            }
+            __syncthreads();
+            const int r = (int)(cur - lo);
+            bool found = false;
+            for (int wtop = (r - 1) >> 5; r > 0 && wtop >= 0; wtop -= F3_NT) {
+                const int wi = wtop - tid;
+                uint32_t wv = wi >= 0 ? lnz[wi] : 0u;
+                if (wi == ((r - 1) >> 5) && (r & 31)) wv &= (1u << (r & 31)) - 1u;
+                if (wv) atomicMax(&S.next, (uint32_t)(wi * 32 + 31 - __clz(wv)) + 1u);
+                __syncthreads();
+                const uint32_t nx = S.next;
+                __syncthreads();
+                if (nx) {
+                    cur = lo + nx - 1;
+                    found = true;
+                    break;
+                }
+            }
+            if (!found) break;
+            headc = lhead[cur - lo];
+            tailc = ltail[cur - lo];
+            qs = __ldg(&lvl_qstart[cur]);
+            continue;
+        }
+        steps++;
+        const uint32_t k = min((uint32_t)F3_NT, tailc - headc);
+        const bool act = (uint32_t)tid < k;
+        uint32_t p = 0, mylab = 0;
+        if (act) p = __ldcg(&queue[qs + headc + tid]);
+        const int z = (int)fdiv(p, fHW);
+        const uint32_t rem = p - (uint32_t)z * HW;
+        const int y = (int)fdiv(rem, t.fW), x = (int)rem - y * W;
+        // neighbour order of skimage (connectivity 1): -z, -y, -x, +x, +y, +z
+        uint32_t nb[6], cslot[6], l[6];
+        bool cand[6];
+        nb[0] = (act && z > 0) ? p - HW : NONE32;
+        nb[1] = (act && y > 0) ? p - W : NONE32;
+        nb[2] = (act && x > 0) ? p - 1 : NONE32;
+        nb[3] = (act && x + 1 < W) ? p + 1 : NONE32;
+        nb[4] = (act && y + 1 < H) ? p + W : NONE32;
+        nb[5] = (act && z + 1 < D) ? p + HW : NONE32;
+        if (act) mylab = __ldcg(&lab[p]);
+#pragma unroll
+        for (int s = 0; s < 6; s++) cand[s] = nb[s] != NONE32 && __ldcg(&lab[nb[s]]) == UNLAB;
+#pragma unroll
+        for (int s = 0; s < 6; s++) l[s] = cand[s] ? lv[nb[s]] : 0u;   // in flight while the claims resolve
+        const uint32_t keybase = (uint32_t)tid << 3;
+#pragma unroll
+        for (int s = 0; s < 6; s++) {
+            cslot[s] = 0;
+            if (cand[s]) {
+                uint32_t h = (nb[s] * 2654435761u) >> 19;   // 13 bits
+                for (;;) {
+                    const uint32_t old = atomicCAS(&S.ck[h], NONE32, nb[s]);
+                    if (old == NONE32 || old == nb[s]) break;
+                    h = (h + 1) & (F3_CLAIMS - 1);
+                }
+                cslot[s] = h;
+                atomicMin(&S.cm[h], keybase | s);
+            }
+        }
+        if (tid == 0) S.rstar = NONE32, S.mx = 0, S.tailc = tailc;
+        __syncthreads();
+        bool up = false;
+        bool mine[6];
+#pragma unroll
+        for (int s = 0; s < 6; s++) {
+            mine[s] = cand[s];
+            if (cand[s]) {
+                cand[s] = S.cm[cslot[s]] == (keybase | s);
+                if (cand[s])
+                    up |= l[s] > cur;
+                else
+                    l[s] = 0;
+            }
+        }
+        if (up) atomicMin(&S.rstar, (uint32_t)tid);
+        __syncthreads();
+        const uint32_t rstar = S.rstar;   // NONE32: nothing above the current level was queued
+#pragma unroll
+        for (int s = 0; s < 6; s++)
+            if (mine[s]) S.ck[cslot[s]] = NONE32, S.cm[cslot[s]] = NONE32;
+        if ((uint32_t)tid > rstar) {
+#pragma unroll
+            for (int s = 0; s < 6; s++) cand[s] = false;
+        } else {
+            uint32_t m = 0;
+#pragma unroll
+            for (int s = 0; s < 6; s++)
+                if (cand[s]) {
+                    __stcg(&lab[nb[s]], mylab);
+                    m = max(m, l[s]);
+                }
+            if (rstar != NONE32 && m > cur) atomicMax(&S.mx, m);
+        }
+        headc += rstar == NONE32 ? k : min(k, rstar + 1u);
+        block_append<6>(S, cand, l, nb, queue, lvl_qstart, ltail, lnz, lo, cur, tailc, mx);
+        if (rstar != NONE32) {
+            intr++;
+            if (tid == 0) {
+                lhead[cur - lo] = headc;
+                ltail[cur - lo] = tailc;
+                if (headc != tailc)
+                    lnz[(cur - lo) >> 5] |= 1u << ((cur - lo) & 31);
+                else
+                    lnz[(cur - lo) >> 5] &= ~(1u << ((cur - lo) & 31));
+            }
+            cur = mx;
+            __syncthreads();
+            headc = lhead[cur - lo];
+            tailc = ltail[cur - lo];
+            qs = __ldg(&lvl_qstart[cur]);
+        } else
+            __syncthreads();
+    }
+    if (tid == 0 && stats) {
+        atomicAdd(&stats[0], steps);
+        atomicAdd(&stats[1], intr);
+        atomicMax(&stats[2], steps);
+    }
+}
+
 // ------------------------------------------------------------------ flood v2 (2-D tiles up to 2^17 pixels)
 // Same step semantics as k_flood, but the per-pixel state the hot loop touches lives on chip: the
 // "in mask, not labelled yet" bitmap of the tile and a small claim table sit in shared memory (no global
@@ -1863,6 +2151,18 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     }
     // ---- flood
     g_prof.mark("s1.flood", s);
+    // tiles flood v2 cannot take go to the CTA-per-tile kernel when the tile's level tables fit in shared memory
+    // (host sync: the largest number of levels in one tile), else to the one-warp kernel
+    int levcap3 = 0;
+    bool flood3 = false;
+    if (!v2 && g_flood_version != 1) {
+        BS_LAUNCH(k_tile_nlev_max, cdiv(ntiles, 256), 256, 0, s, tile_lvl.as<uint32_t>(), ntiles, d_tot + 7);
+        uint32_t h_nlev = 0;
+        BS_CUDA(cudaMemcpyAsync(&h_nlev, d_tot + 7, 4, cudaMemcpyDeviceToHost, s));
+        BS_CUDA(cudaStreamSynchronize(s));
+        levcap3 = (int)h_nlev + 1;
+        flood3 = flood3_smem(levcap3) <= 227 * 1024;
+    }
     if (v2) {
         const int nwords_max = (int)((maxpix + 31) / 32);
         // bitmap in shared memory only when every tile of the batch is resident then anyway (16 tiles per SM); otherwise
@@ -1903,6 +2203,11 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
 #undef BS_FLOOD2
         g_prof.mark("s1.flood_scatter", s);
         BS_LAUNCH(k_scatter_labels, dim3((unsigned)std::min<long long>(std::max<long long>((maxpix + 1023) / 1024, 1), 2048), ntiles), 256, 0, s, dt, tile_q.as<uint32_t>(), queue.as<uint32_t>(), lab.as<uint32_t>());
+    } else if (flood3) {
+        BS_CUDA(cudaFuncSetAttribute(k_flood3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flood3_smem(levcap3)));
+        BS_LAUNCH(k_flood3, ntiles, F3_NT, flood3_smem(levcap3), s, dt, ntiles, lab.as<uint32_t>(), lv.as<uint32_t>(),
+                  queue.as<uint32_t>(), lvl_qstart.as<uint32_t>(), tile_lvl.as<uint32_t>(), seedlist.as<uint32_t>(),
+                  tile_seed.as<uint32_t>(), levcap3, fstats.as<uint32_t>());
     } else {
         BS_LAUNCH(k_flood, cdiv((size_t)ntiles * 32, 64), 64, 0, s, dt, ntiles, lab.as<uint32_t>(), lv.as<uint32_t>(),
                   queue.as<uint32_t>(), lvl_qstart.as<uint32_t>(), lvl_head.as<uint32_t>(), lvl_tail.as<uint32_t>(),

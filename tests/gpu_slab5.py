@@ -3,6 +3,7 @@ context 32) on a single GPU: time, memory and self-consistency properties (the o
     python tests/gpu_slab5.py [--z 256] [--yx 2048]
 """
 import argparse
+import json
 import os
 import sys
 import time
@@ -21,11 +22,12 @@ def main():
     ap.add_argument("--yx", type=int, default=2048)
     ap.add_argument("--block", type=int, default=256)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--params", default="{}", help='ws_params as JSON, e.g. \'{"fragments_in_xy": false, "seed_eps": 0.01}\' (config 4)')
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     shape = (a.z, a.yx, a.yx)
     block, ctx = (a.block,) * 3, (a.block // 8,) * 3
-    seg = ShardedSegmenter(shape, block, ctx, {}, rank=0, world=1, device=dev)
+    seg = ShardedSegmenter(shape, block, ctx, json.loads(a.params), rank=0, world=1, device=dev)
     t0 = time.time()
     affs = seg.synth_local_affs(seed=0)
     torch.cuda.synchronize()

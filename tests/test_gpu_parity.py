@@ -163,6 +163,33 @@ def test_flood_versions_agree():
     assert all(torch.equal(out[0], o) for o in out[1:]) and int((out[0] != 0).sum()) > 0
 
 
+def test_flood_block_wide_matches_warp_flood():
+    """3-D read ROIs (and slices beyond 2^17 pixels) take the CTA-per-tile flood (v3); version 1 forces the one-warp
+    kernel: same fragments, also with steps cut by pixels queued above the current level (seed_eps shifts)"""
+    from bootstrapper_b200 import native
+    from bootstrapper_b200.post.pipeline import segment_blockwise, segment_simple
+    from bootstrapper_b200.synth import synth_affs
+    affs = torch.from_numpy(synth_affs((40, 120, 120), seed=5)).cuda()
+    for params in ({"fragments_in_xy": False}, {"fragments_in_xy": False, "seed_eps": 0.01}):
+        out = []
+        for v in (1, 0):
+            native.set_flood_version(v)
+            try:
+                out.append(segment_blockwise(affs, params, (20, 60, 60), (4, 8, 8))["fragments"].clone())
+            finally:
+                native.set_flood_version(0)
+        assert torch.equal(out[0], out[1]) and int((out[0] != 0).sum()) > 0
+    big = torch.from_numpy(synth_affs((2, 400, 400), seed=6)).cuda()     # 160000 pixels per slice > 2^17
+    out = []
+    for v in (1, 0):
+        native.set_flood_version(v)
+        try:
+            out.append(segment_simple(big, {})["fragments"].clone())
+        finally:
+            native.set_flood_version(0)
+    assert torch.equal(out[0], out[1]) and int((out[0] != 0).sum()) > 0
+
+
 def test_watershed_from_affinities_plug():
     """post/ws.py:38 signature; partition equality (ids are a relabelling, see the module docstring)"""
     from bootstrapper_b200.post.ws import watershed_from_affinities
