@@ -34,6 +34,9 @@ BLOCK = (25, 250, 250)
 CONTEXT = (3, 31, 31)
 # --config 5 (not the driver's default): BASELINE configs[4], 2048^3 over 8 GPUs = a (256, 2048, 2048) slab per rank
 SHAPE5, BLOCK5, CONTEXT5 = (256, 2048, 2048), (256, 256, 256), (32, 32, 32)
+# --config 4: BASELINE configs[3], 1024^3 with 3-D seeded fragments + seed_eps over 4 GPUs = a (256, 1024, 1024) slab per rank
+SHAPE4, BLOCK4, CONTEXT4 = (256, 1024, 1024), (128, 128, 128), (16, 16, 16)
+PARAMS4 = {"fragments_in_xy": False, "seed_eps": 0.01}
 THRESHOLDS = [0.2, 0.35, 0.5]
 BYTES_PER_VOXEL = 3 * 1 + 8 + 8 * len(THRESHOLDS)      # u8 affs in, u64 fragments + T u64 segmentations out
 CPU_SAMPLE = (100, 1000, 1000)                         # 64 blocks of the same geometry (~15 s of CPU work on 16 cores)
@@ -159,9 +162,11 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    slab, block, context = (SHAPE5, BLOCK5, CONTEXT5) if args.config == 5 else (SHAPE, BLOCK, CONTEXT)
+    slab, block, context = {5: (SHAPE5, BLOCK5, CONTEXT5), 4: (SHAPE4, BLOCK4, CONTEXT4)}.get(args.config, (SHAPE, BLOCK, CONTEXT))
     shape = (slab[0] * world, slab[1], slab[2]) if not args.quick else (50 * world, 500, 500)
     params = {"thresholds": THRESHOLDS}
+    if args.config == 4:
+        params.update(PARAMS4)
     seg = ShardedSegmenter(shape, block, context, params, rank=rank, world=world, device=dev)
     affs = seg.synth_local_affs(seed=0)                    # this rank's slab + z halo, generated on the device
     torch.cuda.synchronize()
@@ -202,7 +207,7 @@ def run_ours(args):
     value = V_total / (ms_step * 1e-3)
 
     # ---- end to end through the public API with host buffers (pinned), copies inside the timed region
-    if args.config == 5:   # 69 GB of outputs per rank: the host-buffer leg is measured on the default workload only
+    if args.config != 2:   # (69 GB of outputs per rank for config 5) the host-buffer leg is measured on the default workload only
         args.no_e2e = True
     if args.no_e2e:
         e2e_ms, h2d, d2h = None, 0, 0
@@ -253,7 +258,7 @@ def report(args, seg, shape, slab, block, context, world, ms_step, value, V_tota
     if os.path.exists(tp) and args.config == 2 and not args.quick:   # the captures are of the default workload
         traffic = json.load(open(tp)).get(dom)
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and args.config == 2:   # the CPU leg samples the default workload
         sample = (50, 500, 500) if args.quick else CPU_SAMPLE
         r, tm = cpu_oracle_rate(sample)
         cpu = {"value": r, "unit": "voxels/s", "cores": tm["workers"], "kind": "port",
@@ -263,8 +268,9 @@ def report(args, seg, shape, slab, block, context, world, ms_step, value, V_tota
         "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": f"{'CREMI-sized ' if args.config != 5 else ''}synthetic uint8 affinities 3x{shape} ({world} z-slab(s) of {slab}), "
-                               f"block {block}, context {context}, ws defaults, thresholds [0.2,0.35,0.5]",
+        "config": {"workload": f"{'CREMI-sized ' if args.config == 2 else ''}synthetic uint8 affinities 3x{shape} ({world} z-slab(s) of {slab}), "
+                               f"block {block}, context {context}, "
+                               f"{'ws defaults' if args.config != 4 else 'fragments_in_xy=false, seed_eps=0.01'}, thresholds [0.2,0.35,0.5]",
                    "l2": f"inputs larger than L2 ({3 * int(np.prod(slab)) / 1e6:.0f} MB affinities, "
                          f"{32 * int(np.prod(slab)) / 1e9:.1f} GB outputs per step per GPU)",
                    "parity": "bit-exact vs oracle (seed_tie=index, stats_mode=canonical), tests/test_gpu_parity.py"},
@@ -290,8 +296,9 @@ def main():
     ap.add_argument("--quick", action="store_true", help="small volume (smoke / CI), not a valid bench number")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 5],
-                    help="2 = BASELINE configs[1] (default, the metric's workload); 5 = 2048^3 over 8 GPUs (a 256x2048x2048 slab per rank)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
+                    help="2 = BASELINE configs[1] (default, the metric's workload); 4 = 1024^3 3-D seeded + seed_eps over 4 GPUs (a 256x1024x1024 "
+                         "slab per rank); 5 = 2048^3 over 8 GPUs (a 256x2048x2048 slab per rank)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -924,6 +924,7 @@ __global__ void __launch_bounds__(64) k_flood(const Tile *__restrict__ tiles, in
 // the tile's levels live in shared memory: per level and step the dependent global accesses are the entry, the labels of
 // its neighbours and their levels.
 static constexpr int F3_NT = 512, F3_NW = F3_NT / 32, F3_SLOTS = 1024, F3_CLAIMS = 8192;
+static constexpr uint32_t F3_PIXMASK = (1u << 29) - 1u;
 struct F3Shared {
     uint32_t hk[F3_SLOTS];             // level of the slot (NONE32: free)
     uint32_t hbase[F3_SLOTS];          // queue position where this step's entries of the level start
@@ -1107,8 +1108,13 @@ __global__ void __launch_bounds__(F3_NT) k_flood3(const Tile *__restrict__ tiles
         steps++;
         const uint32_t k = min((uint32_t)F3_NT, tailc - headc);
         const bool act = (uint32_t)tid < k;
-        uint32_t p = 0, mylab = 0;
-        if (act) p = __ldcg(&queue[qs + headc + tid]);
+        // entry = pixel | (slot it was claimed through + 1) << 29 (0: a seed)
+        uint32_t p = 0, mylab = 0, from = 0;
+        if (act) {
+            const uint32_t e = __ldcg(&queue[qs + headc + tid]);
+            p = e & F3_PIXMASK;
+            from = e >> 29;
+        }
         const int z = (int)fdiv(p, fHW);
         const uint32_t rem = p - (uint32_t)z * HW;
         const int y = (int)fdiv(rem, t.fW), x = (int)rem - y * W;
@@ -1121,9 +1127,24 @@ __global__ void __launch_bounds__(F3_NT) k_flood3(const Tile *__restrict__ tiles
         nb[3] = (act && x + 1 < W) ? p + 1 : NONE32;
         nb[4] = (act && y + 1 < H) ? p + W : NONE32;
         nb[5] = (act && z + 1 < D) ? p + HW : NONE32;
-        if (act) mylab = __ldcg(&lab[p]);
+        // the pixel this entry was claimed from is labelled: slot s was entered from its opposite, slot 5 - s
 #pragma unroll
-        for (int s = 0; s < 6; s++) cand[s] = nb[s] != NONE32 && __ldcg(&lab[nb[s]]) == UNLAB;
+        for (int s = 0; s < 6; s++)
+            if (from == (uint32_t)(6 - s)) nb[s] = NONE32;
+        // one 16-byte load covers the pixel's own label and, mostly, both x neighbours (tile bases are 32-aligned)
+        uint32_t lx0 = 0, lx1 = 0;
+        if (act) {
+            const uint4 v = __ldcg((const uint4 *)(lab + (p & ~3u)));
+            const uint32_t q = p & 3u;
+            mylab = q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w));
+            lx0 = q == 0 ? (nb[2] != NONE32 ? __ldcg(&lab[p - 1]) : 0u) : (q == 1 ? v.x : (q == 2 ? v.y : v.z));
+            lx1 = q == 3 ? (nb[3] != NONE32 ? __ldcg(&lab[p + 1]) : 0u) : (q == 0 ? v.y : (q == 1 ? v.z : v.w));
+        }
+        cand[2] = nb[2] != NONE32 && lx0 == UNLAB;
+        cand[3] = nb[3] != NONE32 && lx1 == UNLAB;
+#pragma unroll
+        for (int s = 0; s < 6; s++)
+            if (s != 2 && s != 3) cand[s] = nb[s] != NONE32 && __ldcg(&lab[nb[s]]) == UNLAB;
 #pragma unroll
         for (int s = 0; s < 6; s++) l[s] = cand[s] ? lv[nb[s]] : 0u;   // in flight while the claims resolve
         const uint32_t keybase = (uint32_t)tid << 3;
@@ -1176,6 +1197,8 @@ __global__ void __launch_bounds__(F3_NT) k_flood3(const Tile *__restrict__ tiles
             if (rstar != NONE32 && m > cur) atomicMax(&S.mx, m);
         }
         headc += rstar == NONE32 ? k : min(k, rstar + 1u);
+#pragma unroll
+        for (int s = 0; s < 6; s++) nb[s] |= (uint32_t)(s + 1) << 29;
         block_append<6>(S, cand, l, nb, queue, lvl_qstart, ltail, lnz, lo, cur, tailc, mx);
         if (rstar != NONE32) {
             intr++;
@@ -2161,7 +2184,7 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
         BS_CUDA(cudaMemcpyAsync(&h_nlev, d_tot + 7, 4, cudaMemcpyDeviceToHost, s));
         BS_CUDA(cudaStreamSynchronize(s));
         levcap3 = (int)h_nlev + 1;
-        flood3 = flood3_smem(levcap3) <= 227 * 1024;
+        flood3 = flood3_smem(levcap3) <= 227 * 1024 && maxpix <= (long long)F3_PIXMASK;
     }
     if (v2) {
         const int nwords_max = (int)((maxpix + 31) / 32);
