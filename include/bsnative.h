@@ -202,11 +202,13 @@ int bs_debug_fetch(const bs_plan *p, const char *name, void *dst_host, int64_t *
 /* per-stage device times (ms) of the last run, measured with CUDA events on the caller's
  * stream when enabled via bs_set_profiling(1). names/values up to cap entries. */
 int bs_set_debug(int on);
-/* flood kernel: 0 = automatic, 1 = global-memory flood (v1), 2 = v2 with the tile bitmap in shared memory,
- * 3 = v2 with the tile bitmap in global memory (every tile resident at once), 4 = 3 + level tails in shared memory */
+/* flood kernel: 0 = automatic (v2 for 2-D tiles up to 2^17 pixels, else the CTA-per-tile kernel v3), 1 = one-warp
+ * global-memory flood (v1) everywhere, 2 = v2 with the tile bitmap in shared memory, 3 = v2 with the tile bitmap in
+ * global memory (every tile resident at once), 4 = 3 + level tails in shared memory */
 int bs_set_flood_version(int v);
 /* agglomeration kernel: 0 = automatic (parallel merges; shared memory when a block's graph fits, else a global slab),
- * 1 = single warp on global slabs, 2 = single warp in shared memory, 3 = parallel merges on global slabs */
+ * 1 = single warp on global slabs, 2 = single warp in shared memory, 3 = parallel merges on global slabs (queue bins,
+ * parents and stamps in shared memory), 4 = parallel merges with every array in the global slab */
 int bs_set_agglom_version(int v);
 /* return the library's cached scratch memory (stream-ordered pool) to the driver */
 int bs_release_scratch(void);
