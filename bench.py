@@ -160,6 +160,14 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # pinned host buffers of the host-buffer leg should live on the NUMA node next to this rank's GPU
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        except Exception:  # noqa: BLE001
+            pass
+    if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     slab, block, context = {5: (SHAPE5, BLOCK5, CONTEXT5), 4: (SHAPE4, BLOCK4, CONTEXT4)}.get(args.config, (SHAPE, BLOCK, CONTEXT))
@@ -258,7 +266,7 @@ def report(args, seg, shape, slab, block, context, world, ms_step, value, V_tota
     if os.path.exists(tp) and args.config == 2 and not args.quick:   # the captures are of the default workload
         traffic = json.load(open(tp)).get(dom)
     cpu = None
-    if not args.no_cpu and args.config == 2:   # the CPU leg samples the default workload
+    if not args.no_cpu and args.config == 2 and world == 1:   # the CPU leg samples the default workload, on rank 0 at N=1 only
         sample = (50, 500, 500) if args.quick else CPU_SAMPLE
         r, tm = cpu_oracle_rate(sample)
         cpu = {"value": r, "unit": "voxels/s", "cores": tm["workers"], "kind": "port",
