@@ -52,7 +52,7 @@ EXPORTS = [
     "bs_last_error", "bs_launch_count", "bs_version", "bs_config_size", "bs_plan_create", "bs_plan_destroy", "bs_plan_num_blocks",
     "bs_plan_block_info", "bs_plan_set_owned", "bs_stage1_fragments", "bs_stage1_num_nodes", "bs_stage1_get_nodes",
     "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_plan_node_ids", "bs_stage2_agglomerate", "bs_stage2_num_edges",
-    "bs_stage2_get_edges", "bs_waterz_segment", "bs_cc_affs", "bs_shift_affinities", "bs_connected_components", "bs_stage3_components", "bs_relabel", "bs_stage3_relabel", "bs_watershed_from_affinities",
+    "bs_stage2_get_edges", "bs_waterz_segment", "bs_cc_affs", "bs_aff_errors", "bs_shift_affinities", "bs_connected_components", "bs_stage3_components", "bs_relabel", "bs_stage3_relabel", "bs_watershed_from_affinities",
     "bs_synth_affs", "bs_debug_fetch", "bs_set_debug", "bs_set_profiling", "bs_get_profile",
     "bs_release_scratch", "bs_set_flood_version", "bs_set_agglom_version", "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
 ]
@@ -374,6 +374,25 @@ def cc_affs(affs, threshold, remove_debris=0, mask=None):
                             Z, Y, X, C.c_float(float(threshold)), C.c_int(int(remove_debris or 0)), _dev(frags), _dev(seg),
                             C.byref(n), _stream()))
     return frags, seg, n.value
+
+
+def aff_errors(seg, pred_affs, neighborhood, labels_mask=None, thresholds=(0.1, 1.0), return_seg_affs=True):
+    """AddAffErrors.process on one device array (gp/add_aff_errors.py:128-183): seg (Z,Y,X) int64/uint64 ids, pred_affs
+    (C,Z,Y,X) float32 or uint8, neighborhood C x 3 offsets.  Returns (seg_affs float32 or None, error_map float32,
+    error_mask uint8)."""
+    nh = np.ascontiguousarray(np.asarray(neighborhood, dtype=np.int32).reshape(-1, 3))
+    Cn = nh.shape[0]
+    if pred_affs.shape[0] != Cn or tuple(pred_affs.shape[1:]) != tuple(seg.shape):
+        raise BsError("pred_affs must be (len(neighborhood),) + seg.shape")
+    shape = (C.c_int32 * 3)(*[int(v) for v in seg.shape])
+    seg_affs = torch.empty((Cn,) + tuple(seg.shape), dtype=torch.float32, device=seg.device) if return_seg_affs else None
+    err = torch.empty(tuple(seg.shape), dtype=torch.float32, device=seg.device)
+    emask = torch.empty(tuple(seg.shape), dtype=torch.uint8, device=seg.device)
+    _check(lib().bs_aff_errors(_dev(seg, torch.int64), _dev(pred_affs), C.c_int(_aff_dtype(pred_affs)), C.c_int(Cn), shape,
+                               nh.ctypes.data_as(C.c_void_p), _dev(labels_mask, torch.uint8) if labels_mask is not None else None,
+                               C.c_float(float(thresholds[0])), C.c_float(float(thresholds[1])),
+                               _dev(seg_affs) if seg_affs is not None else None, _dev(err), _dev(emask), _stream()))
+    return seg_affs, err, emask
 
 
 def shift_affinities(affs, mask=None, sigma=None, bias=None):

@@ -172,6 +172,17 @@ int bs_stage3_relabel(bs_plan *p, const uint64_t *frags, int64_t n_vox, const ui
 int bs_cc_affs(const void *affs, int aff_dtype, const uint8_t *mask, int Z, int Y, int X, float threshold, int remove_debris,
                uint64_t *frags_out, uint64_t *seg_out, int64_t *n_out, void *stream);
 
+/* ---- affinity self-consistency error (`bs evaluate`) ------------------------
+ * replaces: the compute of AddAffErrors.process (gp/add_aff_errors.py:128-183) on one array: seg -> affinities on
+ * `neighborhood` (gunpowder seg_to_affgraph: same id, both > 0, 0 where the neighbour is outside), float32
+ * error = sum_c (seg_aff - pred)^2 in channel order, * mask, / max, error_mask = floor < error < ceil.
+ *   seg (Z,Y,X) uint64; pred (C,Z,Y,X) float32 (BS_DTYPE_F32) or uint8 (BS_DTYPE_U8, normalised * 1/255 as gp.Normalize
+ *   does, eval/compute_errors.py:146); shape[3], neighborhood[C*3] host; mask (Z,Y,X) u8 or NULL;
+ *   seg_affs_out (C,Z,Y,X) float32 or NULL; error_map_out (Z,Y,X) float32; error_mask_out (Z,Y,X) uint8. */
+int bs_aff_errors(const uint64_t *seg, const void *pred, int pred_dtype, int n_offsets, const int32_t *shape, const int32_t *neighborhood,
+                  const uint8_t *mask, float floor_, float ceil_, float *seg_affs_out, float *error_map_out, uint8_t *error_mask_out,
+                  void *stream);
+
 /* ---- shifts of the single-shot paths ----------------------------------------------------
  * replaces the numpy / scipy block of simple_watershed and cc_affs (post/watershed.py:262-303,
  * connected_components.py:52-77): out = affs_data + shift in float32, with affs_data = affs[:3].astype(float32)

@@ -7,6 +7,7 @@ Writes tests/golden/*.npz / *.json.  Nothing at test time reads /root/reference.
 Sources executed (unmodified, loaded by path):
   bootstrapper/post/merge_tree.py   -> merge_tree.npz   (MergeTree.merge / find_merges)
   bootstrapper/post/cc.py           -> cc_flood.npz, cc_affs.npz (compute_connected_component_segmentation)
+  bootstrapper/gp/add_aff_errors.py -> aff_errors.npz  (_create_diff / _create_mask; gunpowder + skimage imports stubbed)
   bootstrapper/post/naming.py       -> naming.json      (build_name; `import zarr` stubbed)
   bootstrapper/segment.py           -> seg_config.json  (DEFAULTS, get_seg_config)
 """
@@ -121,6 +122,41 @@ NAMING_CASES = [
 ]
 
 
+def golden_aff_errors():
+    """AddAffErrors._create_diff / _create_mask (gp/add_aff_errors.py:163-183) executed from the reference file; the
+    gunpowder / skimage imports of the module are stubbed (the two functions are plain numpy)."""
+    gp = types.ModuleType("gunpowder")
+    for n in ("BatchFilter", "Array", "BatchRequest", "Batch", "Coordinate"):
+        setattr(gp, n, type(n, (), {}))
+    nodes = types.ModuleType("gunpowder.nodes")
+    addaff = types.ModuleType("gunpowder.nodes.add_affinities")
+    addaff.seg_to_affgraph = None
+    morph = types.ModuleType("skimage.morphology")
+    morph.ball = morph.disk = None
+    sk = types.ModuleType("skimage")
+    for name, mod in (("gunpowder", gp), ("gunpowder.nodes", nodes), ("gunpowder.nodes.add_affinities", addaff),
+                      ("skimage", sk), ("skimage.morphology", morph)):
+        sys.modules.setdefault(name, mod)
+    ref = load("ref_add_aff_errors", f"{REF}/gp/add_aff_errors.py").AddAffErrors
+    rng = np.random.default_rng(23)
+    out = {}
+    for ci, (C, shape, use_mask, thr) in enumerate([(3, (5, 17, 19), False, (0.1, 1.0)), (9, (4, 12, 11), True, (0.05, 0.7)),
+                                                    (3, (3, 8, 8), True, (0.1, 1.0))]):
+        a = (rng.random((C,) + shape) < 0.7).astype(np.float32)
+        b = rng.random((C,) + shape).astype(np.float32)
+        if ci == 2:
+            b = a.copy()                                               # zero error everywhere: the max == 0 branch
+        m = (rng.random(shape) < 0.8).astype(np.uint8) if use_mask else None
+        diff = ref._create_diff(None, a.copy(), b.copy(), None if m is None else m.copy())
+        msk = ref._create_mask(None, diff, thr)
+        out[f"a{ci}"], out[f"b{ci}"], out[f"diff{ci}"], out[f"mask{ci}"] = a, b, diff, msk
+        out[f"thr{ci}"] = np.array(thr)
+        if m is not None:
+            out[f"m{ci}"] = m
+    np.savez_compressed(os.path.join(OUT, "aff_errors.npz"), **out)
+    print("aff_errors.npz", len(out))
+
+
 def golden_naming():
     sys.modules.setdefault("zarr", types.ModuleType("zarr"))       # naming.py only uses zarr in dump_params
     nm = load("ref_naming", f"{REF}/post/naming.py")
@@ -198,6 +234,7 @@ if __name__ == "__main__":
     golden_merge_tree()
     golden_cc()
     golden_cc_affs()
+    golden_aff_errors()
     golden_naming()
     golden_config()
     print("golden fixtures written to", OUT)

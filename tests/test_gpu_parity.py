@@ -403,3 +403,37 @@ def test_agglomeration_kernels_agree():
         finally:
             native.set_agglom_version(0)
         _check(r, ref)
+
+
+# ---------------------------------------------------------------- affinity self-consistency error
+@pytest.mark.parametrize("shape,dtype,use_mask,nhood", [
+    ((10, 90, 70), np.float32, False, [[-1, 0, 0], [0, -1, 0], [0, 0, -1]]),
+    ((10, 90, 70), np.uint8, True, [[-1, 0, 0], [0, -1, 0], [0, 0, -1], [-2, 0, 0], [0, -8, 0], [0, 0, -8], [0, 5, -3], [1, 0, 0], [0, 0, 4]]),
+    ((7, 45, 31), np.uint8, True, [[-1, 0, 0], [0, -1, 0], [0, 0, -1], [0, -3, 2]]),       # odd voxel count: the scalar kernels
+    ((7, 45, 31), np.float32, False, [[-1, 0, 0], [0, -1, 0], [0, 0, -1]]),
+])
+def test_aff_errors_matches_oracle(shape, dtype, use_mask, nhood):
+    """AddAffErrors.process (gp/add_aff_errors.py:128-183): float32 error map and masks bit for bit"""
+    from bootstrapper_b200.eval import add_aff_errors
+    from bootstrapper_b200.post.pipeline import segment_blockwise
+    from bootstrapper_b200.synth import synth_affs
+    from oracle import aff_errors as oa
+    affs = synth_affs(shape, seed=4)
+    r = segment_blockwise(torch.from_numpy(affs).cuda(), {}, tuple(-(-v // 2) for v in shape), (1, 5, 5))
+    seg = r["segs"][0.35].cpu().numpy().view(np.uint64)
+    rng = np.random.default_rng(9)
+    pred = rng.integers(0, 256, (len(nhood),) + seg.shape, dtype=np.uint8)
+    if dtype == np.float32:
+        pred = (pred.astype(np.float32) / np.float32(255)).astype(np.float32)
+    mask = (rng.random(seg.shape) < 0.85).astype(np.uint8) if use_mask else None
+    ref_affs, ref_err, ref_mask = oa.aff_errors(seg, pred, nhood, mask, (0.1, 1.0))
+    got = add_aff_errors(r["segs"][0.35], torch.from_numpy(pred).cuda(), nhood,
+                         None if mask is None else torch.from_numpy(mask).cuda(), (0.1, 1.0))
+    assert np.array_equal(got["seg_affs"].cpu().numpy(), ref_affs)
+    assert np.array_equal(got["error_map"].cpu().numpy().view(np.uint32), ref_err.view(np.uint32))
+    assert np.array_equal(got["error_mask"].cpu().numpy(), ref_mask)
+    assert np.array_equal(got["error_map_u8"].cpu().numpy(), oa.error_map_u8(ref_err))
+    assert ref_mask.any() and not ref_mask.all()
+    # a perfect prediction: zero error everywhere, empty mask (the max == 0 branch)
+    z = add_aff_errors(r["segs"][0.35], torch.from_numpy(ref_affs).cuda(), nhood)
+    assert not z["error_map"].any() and not z["error_mask"].any()

@@ -188,3 +188,22 @@ def test_cc_restatement_matches_reference_goldens():
         mask = g[f"c{ci}_mask"] if g[f"c{ci}_mask"].size else None
         frags, _ = occ.cc_affs(g[f"c{ci}_affs"], float(g[f"c{ci}_thr"]), 0, mask)
         assert np.array_equal(frags, g[f"c{ci}_seg"])
+
+
+def test_aff_errors_restatement_matches_reference_goldens():
+    """create_diff / create_mask against AddAffErrors._create_diff / _create_mask executed from the reference file;
+    seg_to_affgraph (gunpowder, unpinned) on hand-checkable cases"""
+    from oracle import aff_errors as oa
+    g = np.load(os.path.join(GOLD, "aff_errors.npz"))
+    for ci in range(3):
+        m = g[f"m{ci}"] if f"m{ci}" in g.files else None
+        diff = oa.create_diff(g[f"a{ci}"].copy(), g[f"b{ci}"].copy(), None if m is None else m.copy())
+        assert diff.dtype == np.float32 and np.array_equal(diff, g[f"diff{ci}"])
+        assert np.array_equal(oa.create_mask(diff, tuple(g[f"thr{ci}"])), g[f"mask{ci}"])
+    assert not g["diff2"].any()                                   # the max == 0 branch
+    seg = np.array([[[1, 1, 2], [0, 1, 2], [3, 3, 0]]], dtype=np.uint64)
+    aff = oa.seg_to_affgraph(seg, [[0, -1, 0], [0, 0, -1], [0, 0, 2]])
+    assert aff.shape == (3, 1, 3, 3)
+    assert aff[0, 0].tolist() == [[0, 0, 0], [0, 1, 1], [0, 0, 0]]     # p and p - e_y: same id, both > 0; row 0 has no neighbour
+    assert aff[1, 0].tolist() == [[0, 1, 0], [0, 0, 0], [0, 1, 0]]
+    assert aff[2, 0].tolist() == [[0, 0, 0], [0, 0, 0], [0, 0, 0]]     # (0,0)->(0,2): 1 vs 2; (2,0)->(2,2): 3 vs background
