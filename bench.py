@@ -11,8 +11,10 @@ A step = one pass of the whole path over one volume: stage 1 fragments, stage 2 
 stage 3 thresholded CC + relabel for every threshold.
 
 `value`   device-timed (CUDA events, max over ranks), affinities already resident in HBM.
-`e2e`     the same through the public API with HOST buffers: pinned host affinities -> device, the path,
-          fragments + all segmentations -> pinned host memory, copies inside the timed region.
+`e2e`     the same through the public API with HOST buffers (ShardedSegmenter.run_host, streaming form): every
+          step uploads its affinities from pinned host memory and downloads fragments + all segmentations into
+          pinned host memory, all copies inside the timed region; the downloads of one volume overlap the upload
+          and compute of the next (two buffer sets), the region ends when the last download is through.
 `--impl reference` times the CPU oracle (a port of the reference path; the reference itself cannot be
           installed here) with one process per block on all host cores, on a bounded sample.
 """
@@ -218,30 +220,45 @@ def run_ours(args):
     if args.config != 2:   # (69 GB of outputs per rank for config 5) the host-buffer leg is measured on the default workload only
         args.no_e2e = True
     if args.no_e2e:
-        e2e_ms, h2d, d2h = None, 0, 0
+        e2e_ms, h2d, d2h, e2e_stream = None, 0, 0, False
     else:
-        e2e_ms, h2d, d2h = run_e2e(args, seg, affs, barrier, dev, world, out)
+        e2e_ms, h2d, d2h, e2e_stream = run_e2e(args, seg, affs, barrier, dev, world, out)
 
     if rank == 0:
-        report(args, seg, shape, slab, block, context, world, ms_step, value, V_total, prof_acc, launches, clocks, e2e_ms, h2d, d2h)
+        report(args, seg, shape, slab, block, context, world, ms_step, value, V_total, prof_acc, launches, clocks, e2e_ms, h2d, d2h, e2e_stream)
     if world > 1:
         dist.destroy_process_group()
 
 
 def run_e2e(args, seg, affs, barrier, dev, world, out):
+    """host-buffer leg through ShardedSegmenter.run_host in its streaming form: every step uploads the step's
+    affinities from pinned memory and downloads fragments + all segmentations into pinned memory; the downloads of
+    step k overlap the upload and compute of step k + 1 (two buffer sets); the timed region ends when the last
+    download is through."""
     import torch
     import torch.distributed as dist
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     host_affs = torch.empty(affs.shape, dtype=affs.dtype, pin_memory=True)
     host_affs.copy_(affs)
     own_shape = seg.own_shape
-    host_out = [torch.empty(own_shape, dtype=torch.int64, pin_memory=True) for _ in range(1 + len(THRESHOLDS))]
-    e2e_steps = max(1, min(args.steps, 3))
-    seg.run_host(host_affs, host_out, out=out)             # warm-up
+    n_out = 1 + len(THRESHOLDS)
+    host_sets = [[torch.empty(own_shape, dtype=torch.int64, pin_memory=True) for _ in range(n_out)]]
+    dev_sets = [out]
+    try:
+        host_sets.append([torch.empty(own_shape, dtype=torch.int64, pin_memory=True) for _ in range(n_out)])
+        dev_sets.append([torch.empty_like(o) for o in out])
+    except RuntimeError:       # not enough pinned / device memory for the second set: one volume in flight
+        host_sets, dev_sets = host_sets[:1], dev_sets[:1]
+    streaming = len(host_sets) == 2
+    e2e_steps = max(2, min(args.steps, 8))
+    for k in range(4):                                     # warm-up (touches both buffer sets, fills the allocator caches)
+        seg.run_host(host_affs, host_sets[k % len(host_sets)], out=dev_sets[k % len(dev_sets)], wait=not streaming)
+    seg.drain()
     barrier()
     ev0.record()
-    for _ in range(e2e_steps):
-        seg.run_host(host_affs, host_out, out=out)
+    for k in range(e2e_steps):
+        seg.run_host(host_affs, host_sets[k % len(host_sets)], out=dev_sets[k % len(dev_sets)], wait=not streaming)
+    seg.drain()
     ev1.record()
     barrier()
     t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
@@ -249,11 +266,11 @@ def run_e2e(args, seg, affs, barrier, dev, world, out):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item()) / e2e_steps
     h2d = host_affs.numel() * host_affs.element_size()
-    d2h = sum(o.numel() * 8 for o in host_out)
-    return e2e_ms, h2d, d2h
+    d2h = sum(o.numel() * 8 for o in host_sets[0])
+    return e2e_ms, h2d, d2h, streaming
 
 
-def report(args, seg, shape, slab, block, context, world, ms_step, value, V_total, prof_acc, launches, clocks, e2e_ms, h2d, d2h):
+def report(args, seg, shape, slab, block, context, world, ms_step, value, V_total, prof_acc, launches, clocks, e2e_ms, h2d, d2h, e2e_stream):
     peak, peak_src = measured_peak()
     steps = args.steps
     prof = {k: v / steps for k, v in prof_acc.items()}
@@ -289,7 +306,9 @@ def report(args, seg, shape, slab, block, context, world, ms_step, value, V_tota
         "stage_ms": {k: round(v, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])},
         "cpu_baseline": cpu,
         "e2e": None if e2e_ms is None else {"value": V_total / (e2e_ms * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": h2d,
-                                            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+                                            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                                            "mode": ("streaming: downloads of step k overlap upload + compute of step k+1, two buffer sets"
+                                                     if e2e_stream else "one volume in flight")},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

@@ -127,6 +127,7 @@ class ShardedSegmenter:
         self.nvox_block = int(np.prod(self.block_size))
         self.plan = None
         self._copy_stream = None
+        self._inflight = []
         self.last_profile = {}
 
     def _plan(self, dtype_code):
@@ -147,7 +148,7 @@ class ShardedSegmenter:
         g = self.geo
         return native.synth_affs(self.win_shape, seed=seed, dtype=dtype, offset=(g["w0"], 0, 0), device=self.device)
 
-    def run(self, affs_win, out=None, frag_sink=None):
+    def run(self, affs_win, out=None, frag_sink=None, out_ready=None):
         """affs_win: (C, w1-w0, Y, X) on this rank's device.  Returns dict with the fragment window, the
         segmentations of the own planes per threshold and the global graph."""
         plan = self._plan(native._aff_dtype(affs_win))
@@ -188,6 +189,9 @@ class ShardedSegmenter:
         luts = dict(zip(thrs, comps))
         segs = {}
         own = own.contiguous()
+        if out_ready is not None:
+            # `out` is still being read by an earlier volume's device->host copies: only the relabel waits for them
+            torch.cuda.current_stream().wait_event(out_ready)
         for i in range(0, len(thrs), 8):
             for thr, sg in zip(thrs[i:i + 8], plan.relabel(own, comps[i:i + 8], None if out is None else out[i:i + 8])):
                 segs[thr] = sg
@@ -199,13 +203,31 @@ class ShardedSegmenter:
         self.last_profile = prof
         return dict(fragments=frags, own_fragments=own, segs=segs, luts=luts, nodes=nodes, edges=(eu, ev, es))
 
-    def run_host(self, host_affs, host_out, out=None):
+    def run_host(self, host_affs, host_out, out=None, wait=True):
         """end-to-end with HOST buffers: pinned affinities in, fragments + segmentations out (pinned).
-        out: optional device staging buffers for the segmentations (one per threshold)"""
+        out: optional device staging buffers for the segmentations (one per threshold).
+        wait=False: streaming use over many volumes -- the call returns once the copies are queued; the device->host
+        copies of this volume then overlap the next calls' upload and compute (the copy stream is FIFO, and a relabel that
+        writes into `out` buffers an earlier volume is still being copied from waits for those copies).  Alternate
+        between two sets of `out` / `host_out` buffers and call `drain()` before reading the last results."""
         affs = host_affs.to(self.device, non_blocking=True)
-        r = self.run(affs, out=out, frag_sink=host_out[0])
-        for i, thr in enumerate(self.p["thresholds"]):
-            host_out[1 + i].copy_(r["segs"][thr], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        self._copy_stream.synchronize()
+        key = out[0].data_ptr() if out else None
+        busy = [f[0] for f in self._inflight if key is not None and f[3] == key]
+        r = self.run(affs, out=out, frag_sink=host_out[0], out_ready=busy[-1] if busy else None)
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ready)
+            for i, thr in enumerate(self.p["thresholds"]):
+                host_out[1 + i].copy_(r["segs"][thr], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._copy_stream)
+        self._inflight.append((done, r, affs, key))     # the device arrays stay referenced until their copies are through
+        while len(self._inflight) > (0 if wait else 2):
+            self._inflight.pop(0)[0].synchronize()
         return r
+
+    def drain(self):
+        """wait for the device->host copies of every volume queued by run_host(wait=False)"""
+        while self._inflight:
+            self._inflight.pop(0)[0].synchronize()
