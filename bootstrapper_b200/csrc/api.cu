@@ -10,6 +10,8 @@ int g_debug = 0;
 int g_agglom_version = 0;  // 0 = auto (shared-memory kernel when the block fits), 1 = force the global-memory kernel
 int g_flood_version = 0;   // 0 = auto (v2 when eligible), 1 = force the global-memory flood
 int stage1_run(Plan &P, const void *affs, const uint8_t *mask, uint64_t *frags_out, cudaStream_t s);
+int label_stats(const uint64_t *seg, const int32_t *shape, int64_t capacity, uint64_t *ids, int64_t *sizes, int32_t *zlo,
+                int32_t *zhi, int64_t *n_out, cudaStream_t s);
 int aff_errors(const uint64_t *seg, const void *pred, int pred_dtype, int C, const int32_t *shape, const int32_t *nhood,
                const uint8_t *mask, float floor_, float ceil_, float *seg_affs, float *err, uint8_t *emask, cudaStream_t s);
 int stage2_run(Plan &P, const void *affs, const uint64_t *frags, cudaStream_t s, PqRequest *pq);
@@ -296,6 +298,12 @@ int bs_cc_affs(const void *affs, int aff_dtype, const uint8_t *mask, int Z, int 
     BS_ARG(aff_dtype == BS_DTYPE_U8 || aff_dtype == BS_DTYPE_F32, "bs_cc_affs: aff_dtype must be u8 or f32");
     init_mempool();
     return cc_affs(affs, aff_dtype, mask, Z, Y, X, threshold, remove_debris, frags_out, seg_out, n_out, (cudaStream_t)stream);
+}
+
+int bs_label_stats(const uint64_t *seg, const int32_t *shape, int64_t capacity, uint64_t *ids_out, int64_t *sizes_out,
+                   int32_t *zmin_out, int32_t *zmax_out, int64_t *n_out, void *stream) {
+    init_mempool();
+    return label_stats(seg, shape, capacity, ids_out, sizes_out, zmin_out, zmax_out, n_out, (cudaStream_t)stream);
 }
 
 int bs_aff_errors(const uint64_t *seg, const void *pred, int pred_dtype, int n_offsets, const int32_t *shape, const int32_t *neighborhood,

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbsnative.so")
 
 BS_DTYPE_U8, BS_DTYPE_F32 = 0, 1
+BS_ERR_OVERFLOW = -3
 SIGMA_MAXW = 129
 
 
@@ -52,7 +53,7 @@ EXPORTS = [
     "bs_last_error", "bs_launch_count", "bs_version", "bs_config_size", "bs_plan_create", "bs_plan_destroy", "bs_plan_num_blocks",
     "bs_plan_block_info", "bs_plan_set_owned", "bs_stage1_fragments", "bs_stage1_num_nodes", "bs_stage1_get_nodes",
     "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_plan_node_ids", "bs_stage2_agglomerate", "bs_stage2_num_edges",
-    "bs_stage2_get_edges", "bs_waterz_segment", "bs_cc_affs", "bs_aff_errors", "bs_shift_affinities", "bs_connected_components", "bs_stage3_components", "bs_relabel", "bs_stage3_relabel", "bs_watershed_from_affinities",
+    "bs_stage2_get_edges", "bs_waterz_segment", "bs_cc_affs", "bs_aff_errors", "bs_label_stats", "bs_shift_affinities", "bs_connected_components", "bs_stage3_components", "bs_relabel", "bs_stage3_relabel", "bs_watershed_from_affinities",
     "bs_synth_affs", "bs_debug_fetch", "bs_set_debug", "bs_set_profiling", "bs_get_profile",
     "bs_release_scratch", "bs_set_flood_version", "bs_set_agglom_version", "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
 ]
@@ -374,6 +375,26 @@ def cc_affs(affs, threshold, remove_debris=0, mask=None):
                             Z, Y, X, C.c_float(float(threshold)), C.c_int(int(remove_debris or 0)), _dev(frags), _dev(seg),
                             C.byref(n), _stream()))
     return frags, seg, n.value
+
+
+def label_stats(seg, capacity=1 << 20):
+    """ids (ascending), voxel counts, first / last z plane of every non-zero id of a CUDA label volume (Z,Y,X) int64.
+    The table grows until it holds every id."""
+    shape = (C.c_int32 * 3)(*[int(v) for v in seg.shape])
+    while True:
+        ids = torch.empty(capacity, dtype=torch.int64, device=seg.device)
+        sizes = torch.empty(capacity, dtype=torch.int64, device=seg.device)
+        zlo = torch.empty(capacity, dtype=torch.int32, device=seg.device)
+        zhi = torch.empty(capacity, dtype=torch.int32, device=seg.device)
+        n = C.c_int64()
+        rc = lib().bs_label_stats(_dev(seg, torch.int64), shape, C.c_int64(capacity), _dev(ids), _dev(sizes), _dev(zlo), _dev(zhi),
+                                  C.byref(n), _stream())
+        if rc == BS_ERR_OVERFLOW and capacity < (1 << 29):
+            capacity *= 4
+            continue
+        _check(rc)
+        k = n.value
+        return ids[:k], sizes[:k], zlo[:k], zhi[:k]
 
 
 def aff_errors(seg, pred_affs, neighborhood, labels_mask=None, thresholds=(0.1, 1.0), return_seg_affs=True):

@@ -172,6 +172,16 @@ int bs_stage3_relabel(bs_plan *p, const uint64_t *frags, int64_t n_vox, const ui
 int bs_cc_affs(const void *affs, int aff_dtype, const uint8_t *mask, int Z, int Y, int X, float threshold, int remove_debris,
                uint64_t *frags_out, uint64_t *seg_out, int64_t *n_out, void *stream);
 
+/* ---- per-label statistics (`bs refine`) --------------------------------------
+ * replaces: the tile scans of refine.py -- `_global_sizes` (:98-108, fastremap.unique + bincount) and the z-extent loop
+ * of `z_filter` (:236-255): voxel count, first and last z plane of every non-zero id of a label volume, ids ascending
+ * (the order np.unique gives the reference).  The filters' decisions stay host arithmetic on these tables; masking and
+ * remapping (`fastremap.mask` / `fastremap.remap(preserve_missing_labels=True)`, :111-116, :265-270) are bs_relabel.
+ *   seg (Z,Y,X) uint64; *_out device arrays of `capacity` entries; n_out (host) = number of ids.
+ *   BS_ERR_OVERFLOW when the volume holds more than `capacity` distinct ids (retry with a larger capacity). */
+int bs_label_stats(const uint64_t *seg, const int32_t *shape, int64_t capacity, uint64_t *ids_out, int64_t *sizes_out,
+                   int32_t *zmin_out, int32_t *zmax_out, int64_t *n_out, void *stream);
+
 /* ---- affinity self-consistency error (`bs evaluate`) ------------------------
  * replaces: the compute of AddAffErrors.process (gp/add_aff_errors.py:128-183) on one array: seg -> affinities on
  * `neighborhood` (gunpowder seg_to_affgraph: same id, both > 0, 0 where the neighbour is outside), float32

@@ -24,3 +24,13 @@ for dt, with_affs in ((torch.float32, True), (torch.float32, False), (torch.uint
     ms = e0.elapsed_time(e1) / 10
     byt = n * (8 + 3 * pred.element_size() + 5 + (12 if with_affs else 0))
     print(f"pred {str(dt):14s} seg_affs {with_affs!s:5s}: {ms:.3f} ms  {byt / ms / 1e6:.0f} GB/s algorithmic = {byt / ms / 1e6 / peak:.1%} of {peak:.0f} GB/s  ({n / ms / 1e6:.1f} Gvox/s)")
+# per-label statistics of the same volume (bs refine): 8 bytes read per voxel
+for _ in range(2):
+    native.label_stats(seg)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5):
+    ids, sizes, zlo, zhi = native.label_stats(seg)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 5
+print(f"label_stats: {ids.numel()} ids, {ms:.3f} ms  {8 * n / ms / 1e6:.0f} GB/s = {8 * n / ms / 1e6 / peak:.1%} of peak")

@@ -437,3 +437,71 @@ def test_aff_errors_matches_oracle(shape, dtype, use_mask, nhood):
     # a perfect prediction: zero error everywhere, empty mask (the max == 0 branch)
     z = add_aff_errors(r["segs"][0.35], torch.from_numpy(ref_affs).cuda(), nhood)
     assert not z["error_map"].any() and not z["error_mask"].any()
+
+
+def test_run_host_streaming_matches_blocking():
+    """ShardedSegmenter.run_host(wait=False): volumes streamed through two buffer sets give the blocking call's bytes"""
+    from bootstrapper_b200.sharded import ShardedSegmenter
+    from bootstrapper_b200.synth import synth_affs
+    shape, block, ctx = (12, 120, 120), (6, 60, 60), (1, 8, 8)
+    seg = ShardedSegmenter(shape, block, ctx, {"thresholds": [0.2, 0.5]}, device=torch.device("cuda"))
+    vols = [torch.from_numpy(synth_affs(shape, seed=s)).pin_memory() for s in (1, 2, 3, 4, 5)]
+    ref = []
+    for v in vols:
+        ho = [torch.empty(shape, dtype=torch.int64).pin_memory() for _ in range(3)]
+        seg.run_host(v, ho)
+        ref.append([h.clone() for h in ho])
+    host_sets = [[torch.empty(shape, dtype=torch.int64).pin_memory() for _ in range(3)] for _ in range(2)]
+    dev_sets = [[torch.empty(shape, dtype=torch.int64, device="cuda") for _ in range(2)] for _ in range(2)]
+    got = []
+    for k, v in enumerate(vols):
+        if k >= 2:
+            # the set is about to be reused: its volume (k - 2) must be read first
+            seg.drain()
+            got.append([h.clone() for h in host_sets[k % 2]])
+        seg.run_host(v, host_sets[k % 2], out=dev_sets[k % 2], wait=False)
+    seg.drain()
+    got.append([h.clone() for h in host_sets[len(vols) % 2]])
+    got.append([h.clone() for h in host_sets[(len(vols) + 1) % 2]])
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+    assert int((ref[0][0] != 0).sum()) > 0 and not torch.equal(ref[0][1], ref[1][1])
+
+
+# ---------------------------------------------------------------- `bs refine` filters (SURVEY 8f N4)
+def test_refine_filters_match_oracle():
+    """per-id table (sizes, z-extents) and the four filters of refine.py against the numpy restatement"""
+    from bootstrapper_b200 import native, refine
+    from bootstrapper_b200.post.pipeline import segment_blockwise
+    from bootstrapper_b200.synth import synth_affs
+    from oracle import refine as orf
+    affs = synth_affs((14, 150, 130), seed=8)
+    r = segment_blockwise(torch.from_numpy(affs).cuda(), {}, (7, 75, 65), (1, 9, 9))
+    for seg_t in (r["fragments"], r["segs"][0.5]):
+        seg = seg_t.cpu().numpy().view(np.uint64)
+        uniq, sizes = refine.global_sizes(seg_t)
+        ou, os_ = orf.global_sizes(seg)
+        assert np.array_equal(uniq, ou) and np.array_equal(sizes, os_) and uniq.size > 10
+        # a table that starts too small grows until every id fits
+        ids_small = native.label_stats(seg_t.contiguous(), capacity=8)[0]
+        assert np.array_equal(ids_small.cpu().numpy().view(np.uint64), ou)
+        got, rem = refine.size_filter(seg_t, min_size=int(np.median(sizes)), max_size=int(np.percentile(sizes, 90)))
+        ref, orem = orf.size_filter(seg, min_size=int(np.median(sizes)), max_size=int(np.percentile(sizes, 90)))
+        assert np.array_equal(rem, orem) and 0 < rem.size < uniq.size
+        assert np.array_equal(got.cpu().numpy().view(np.uint64), ref)
+        got, rem, st = refine.outlier_filter(seg_t, num_std=1.0, min_size=5)
+        ref, orem = orf.outlier_filter(seg, num_std=1.0, min_size=5)
+        assert np.array_equal(rem, orem) and rem.size > 0
+        assert np.array_equal(got.cpu().numpy().view(np.uint64), ref)
+        got, rem = refine.z_filter(seg_t, min_z=2)
+        ref, orem = orf.z_filter(seg, min_z=2)
+        assert np.array_equal(np.sort(rem), np.sort(orem))
+        assert np.array_equal(got.cpu().numpy().view(np.uint64), ref)
+        a, b, c, d = (int(v) for v in uniq[[0, 3, 5, 7]])
+        got = refine.remap(seg_t, remove_ids=[a], merge_groups=[[b, c, d]])
+        assert np.array_equal(got.cpu().numpy().view(np.uint64), orf.remap(seg, {a: 0, b: b, c: b, d: b}))
+    with pytest.raises(ValueError):
+        refine.remap(r["fragments"], remove_ids=[5], merge_groups=[[5, 6]])
+    empty = torch.zeros((3, 8, 8), dtype=torch.int64, device="cuda")
+    assert refine.global_sizes(empty)[0].size == 0
