@@ -207,3 +207,24 @@ def test_aff_errors_restatement_matches_reference_goldens():
     assert aff[0, 0].tolist() == [[0, 0, 0], [0, 1, 1], [0, 0, 0]]     # p and p - e_y: same id, both > 0; row 0 has no neighbour
     assert aff[1, 0].tolist() == [[0, 1, 0], [0, 0, 0], [0, 1, 0]]
     assert aff[2, 0].tolist() == [[0, 0, 0], [0, 0, 0], [0, 0, 0]]     # (0,0)->(0,2): 1 vs 2; (2,0)->(2,2): 3 vs background
+
+
+def test_refine_restatement_on_a_hand_checked_volume():
+    """oracle/refine.py (bs refine filters, refine.py:98-307) on a volume small enough to check by eye"""
+    from oracle import refine as orf
+    seg = np.zeros((4, 3, 4), dtype=np.uint64)
+    seg[0, 0, :] = 7          # 4 voxels, one plane
+    seg[1:4, 1, 0:2] = 9      # 6 voxels, three planes
+    seg[2, 2, 3] = 5          # 1 voxel
+    seg[0:2, 2, 0] = 11       # 2 voxels, two planes
+    uniq, sizes = orf.global_sizes(seg)
+    assert uniq.tolist() == [5, 7, 9, 11] and sizes.tolist() == [1, 4, 6, 2]
+    out, rem = orf.size_filter(seg, min_size=2, max_size=4)
+    assert rem.tolist() == [5, 9] and sorted(np.unique(out).tolist()) == [0, 7, 11]
+    out, rem = orf.z_filter(seg, min_z=1)
+    assert sorted(rem.tolist()) == [5, 7] and sorted(np.unique(out).tolist()) == [0, 9, 11]
+    # sizes 1,4,6,2: mean 3.25, population std 1.92 -> a 1-sigma cut keeps [1.33, 5.17]
+    out, rem = orf.outlier_filter(seg, num_std=1.0)
+    assert rem.tolist() == [5, 9]
+    out = orf.remap(seg, {7: 0, 9: 9, 11: 9})
+    assert sorted(np.unique(out).tolist()) == [0, 5, 9] and int((out == 9).sum()) == 8
