@@ -1353,7 +1353,7 @@ __global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict
         uint32_t entry = 0;
         if (act) entry = (pre_level == cur && pre_head == headc && headc + lane < pre_tail) ? pre_entry : __ldcg(&queue[qs + headc + lane]);
         const uint32_t p = entry & F2_PIXMASK, mylab = entry >> 17;
-        const int y = p / W, x = p - y * W;
+        const int y = (int)fdiv(p, t.fW), x = (int)p - y * W;
         // neighbour order of skimage (connectivity 1, 2-D): -y, -x, +x, +y
         uint32_t nb[4];
         bool cand[4], pend[4];
