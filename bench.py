@@ -244,11 +244,14 @@ def run_e2e(args, seg, affs, barrier, dev, world, out):
     n_out = 1 + len(THRESHOLDS)
     host_sets = [[torch.empty(own_shape, dtype=torch.int64, pin_memory=True) for _ in range(n_out)]]
     dev_sets = [out]
-    try:
-        host_sets.append([torch.empty(own_shape, dtype=torch.int64, pin_memory=True) for _ in range(n_out)])
-        dev_sets.append([torch.empty_like(o) for o in out])
-    except RuntimeError:       # not enough pinned / device memory for the second set: one volume in flight
-        host_sets, dev_sets = host_sets[:1], dev_sets[:1]
+    # the second buffer set doubles the page-locked host memory (6.25 GB per set and rank for the default workload): keep the
+    # whole job at or below the 50 GB that one set per rank takes on 8 GPUs
+    if world * 2 * n_out * int(np.prod(own_shape)) * 8 <= 50e9:
+        try:
+            host_sets.append([torch.empty(own_shape, dtype=torch.int64, pin_memory=True) for _ in range(n_out)])
+            dev_sets.append([torch.empty_like(o) for o in out])
+        except RuntimeError:       # not enough pinned / device memory for the second set: one volume in flight
+            host_sets, dev_sets = host_sets[:1], dev_sets[:1]
     streaming = len(host_sets) == 2
     e2e_steps = max(2, min(args.steps, 8))
     for k in range(4):                                     # warm-up (touches both buffer sets, fills the allocator caches)
