@@ -1071,6 +1071,7 @@ __global__ void __launch_bounds__(F3_NT) k_flood3(const Tile *__restrict__ tiles
     headc = 0;
     tailc = ltail[cur - lo];
     uint32_t qs = lvl_qstart[cur];
+    uint32_t pre_level = NONE32, pre_head = 0, pre_tail = 0, pre_e = 0;
     __syncthreads();
 
     for (;;) {
@@ -1108,13 +1109,17 @@ __global__ void __launch_bounds__(F3_NT) k_flood3(const Tile *__restrict__ tiles
         steps++;
         const uint32_t k = min((uint32_t)F3_NT, tailc - headc);
         const bool act = (uint32_t)tid < k;
-        // entry = pixel | (slot it was claimed through + 1) << 29 (0: a seed)
+        // entry = pixel | (slot it was claimed through + 1) << 29 (0: a seed); the entries that were queued when the
+        // previous step started were fetched then
         uint32_t p = 0, mylab = 0, from = 0;
         if (act) {
-            const uint32_t e = __ldcg(&queue[qs + headc + tid]);
+            const uint32_t e = (pre_level == cur && pre_head == headc && headc + tid < pre_tail) ? pre_e : __ldcg(&queue[qs + headc + tid]);
             p = e & F3_PIXMASK;
             from = e >> 29;
         }
+        // fetch ahead: the batch after this one, as far as it is queued already (used if this step consumes all F3_NT)
+        pre_level = cur, pre_head = headc + F3_NT, pre_tail = tailc;
+        pre_e = headc + F3_NT + tid < tailc ? __ldcg(&queue[qs + headc + F3_NT + tid]) : 0u;
         const int z = (int)fdiv(p, fHW);
         const uint32_t rem = p - (uint32_t)z * HW;
         const int y = (int)fdiv(rem, t.fW), x = (int)rem - y * W;
