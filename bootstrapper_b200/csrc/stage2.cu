@@ -56,9 +56,18 @@ __device__ __forceinline__ unsigned long long aff_fixed<float>(float v) {
     return (unsigned long long)__double2ll_rn(ldexp((double)v, 38));
 }
 
+// fragment ids of the task window -> dense node numbers + 1 (0: background or an id outside the plan), once per voxel:
+// the RAG pass below then compares and keys 32-bit numbers instead of translating ids at every fragment boundary (in
+// xy mode every voxel lies on one: the fragments of consecutive planes are different objects)
+__global__ void __launch_bounds__(256) k_frags_dense(const uint64_t *__restrict__ frags, size_t n, IdMap idm,
+                                                     uint32_t *__restrict__ dense) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dense[i] = id_to_dense(idm, frags[i]) + 1u;   // NONE32 + 1 == 0
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_rag_accumulate(const S2Blk *__restrict__ blks, const T *__restrict__ affs,
-                                                        const uint64_t *__restrict__ frags, IdMap idm, int volZ, int volY,
+                                                        const uint32_t *__restrict__ frags, int volZ, int volY,
                                                         int volX, int wz0, int roz, int roy, int rox, int rsz, int rsy, int rsx,
                                                         unsigned long long *hkeys, unsigned long long *hsum, uint32_t *hcnt,
                                                         uint32_t *hfirst, uint32_t *overflow) {
@@ -76,37 +85,27 @@ __global__ void __launch_bounds__(256) k_rag_accumulate(const S2Blk *__restrict_
         // fragments array covers the task ROI; outside: zero fill
         const int fz = gz - roz, fy = gy - roy;
         const bool row_in = fz >= 0 && fz < rsz && fy >= 0 && fy < rsy;
-        const uint64_t *rowp = frags + (row_in ? ((size_t)fz * rsy + fy) * rsx : 0);
+        const uint32_t *rowp = frags + (row_in ? ((size_t)fz * rsy + fy) * rsx : 0);
         const bool up_ok = row_in && y > 0 && fy > 0, zm_ok = row_in && z > 0 && fz > 0;
-        uint64_t carry = 0;
+        uint32_t carry = 0;
       for (int x0 = 0; x0 < RX; x0 += 32) {
         const int x = x0 + lane;
         const int gx = b.ro[2] + x, fx = gx - rox;
         const bool in = x < RX && row_in && fx >= 0 && fx < rsx;
         const long long i = (long long)r * RX + x;
-        const uint64_t f1 = in ? rowp[fx] : 0;
-        uint64_t fxm = __shfl_up_sync(FULL, f1, 1);
+        const uint32_t f1 = in ? rowp[fx] : 0;
+        uint32_t fxm = __shfl_up_sync(FULL, f1, 1);
         if (lane == 0) fxm = carry;
         carry = __shfl_sync(FULL, f1, 31);
-        const uint64_t fym = (in && up_ok && f1) ? rowp[(long long)fx - rsx] : 0;
-        const uint64_t fzm = (in && zm_ok && f1) ? rowp[(long long)fx - (long long)plane] : 0;
-        // raw ids are compared first: only voxels on a fragment boundary pay for the id -> node translation
-        uint32_t id1 = NONE32;
-        bool id1_done = false;
+        const uint32_t fym = (in && up_ok && f1) ? rowp[(long long)fx - rsx] : 0;
+        const uint32_t fzm = (in && zm_ok && f1) ? rowp[(long long)fx - (long long)plane] : 0;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-            const uint64_t f2 = f1 == 0 ? 0 : (d == 0 ? fzm : (d == 1 ? fym : fxm));
-            uint32_t id2 = NONE32;
-            if (f2 != 0 && f2 != f1) {
-                if (!id1_done) {
-                    id1 = id_to_dense(idm, f1);
-                    id1_done = true;
-                }
-                id2 = id_to_dense(idm, f2);
-            }
-            bool has = id1 != NONE32 && id2 != NONE32 && id2 != id1;
+            const uint32_t f2 = f1 == 0 ? 0 : (d == 0 ? fzm : (d == 1 ? fym : fxm));
+            const bool has = f2 != 0 && f2 != f1;
             unsigned act = __ballot_sync(FULL, has);
             if (has) {
+                const uint32_t id1 = f1 - 1, id2 = f2 - 1;
                 uint32_t lo = min(id1, id2), hi = max(id1, id2);
                 unsigned long long key = ((unsigned long long)lo << 32) | hi;
                 unsigned long long a = aff_fixed<T>(affs[(size_t)d * nvol + ((size_t)(gz - wz0) * volY + gy) * volX + gx]);
@@ -398,6 +397,7 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
     const S2Blk *db = d_blks.as<S2Blk>();
 
     g_prof.mark("s2.rag", s);
+    DevBuf fdense;
     long long maxread = 0;
     for (auto &d : hb) {
         long long rv = (long long)d.rs[0] * d.rs[1] * d.rs[2];
@@ -408,7 +408,10 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
         int maxrows = 1;
         for (auto &d : hb) maxrows = std::max(maxrows, d.rs[0] * d.rs[1]);
         dim3 gr((unsigned)std::min(std::max((maxrows + 15) / 16, 1), 4096), nown);
-        BS_LAUNCH((k_rag_accumulate<T>), gr, 256, 0, s, db, (const T *)affs, frags, idm, cfg.win_z > 0 ? cfg.win_z : cfg.vol_shape[0],
+        const size_t nfr = (size_t)(cfg.win_z > 0 ? cfg.win_z : cfg.roi_shape[0]) * cfg.roi_shape[1] * cfg.roi_shape[2];
+        BS_TRY(fdense.alloc(4 * nfr, s));
+        BS_LAUNCH(k_frags_dense, (unsigned)std::min<size_t>(cdiv(nfr, 256), 148 * 32), 256, 0, s, frags, nfr, idm, fdense.as<uint32_t>());
+        BS_LAUNCH((k_rag_accumulate<T>), gr, 256, 0, s, db, (const T *)affs, fdense.as<uint32_t>(), cfg.win_z > 0 ? cfg.win_z : cfg.vol_shape[0],
                   cfg.vol_shape[1], cfg.vol_shape[2], cfg.win_z > 0 ? cfg.win_z0 : 0,
                   cfg.roi_offset[0] + (cfg.win_z > 0 ? cfg.win_z0 : 0), cfg.roi_offset[1], cfg.roi_offset[2],
                   cfg.win_z > 0 ? cfg.win_z : cfg.roi_shape[0], cfg.roi_shape[1], cfg.roi_shape[2], hkeys.as<unsigned long long>(), hsum.as<unsigned long long>(),
