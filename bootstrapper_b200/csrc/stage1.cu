@@ -390,19 +390,42 @@ __global__ void __launch_bounds__(256) k_coldist_strip(const Tile *__restrict__ 
         }
         __syncthreads();
         if (x < W)
-            for (int y = warp; y < H; y += 8) {
-                const uint32_t *gp = cs_g2 + y * CS_W + lane;
-                uint32_t best = gp[0];
-                const int up = y, down = H - 1 - y;   // rows available above / below
-                for (int dy = 1;; dy++) {
-                    const uint32_t dd = (uint32_t)dy * dy;
-                    if (dd >= best || (dy > up && dy > down)) break;
-                    if (dy <= up) best = min(best, gp[-dy * CS_W] + dd);
-                    if (dy <= down) best = min(best, gp[dy * CS_W] + dd);
+            for (int ya = 2 * warp; ya < H; ya += 16) {
+                // two vertically adjacent pixels share every row they look at: the row k above the pair lies at distance k
+                // from the upper pixel and k + 1 from the lower one, and the other way round below
+                const uint32_t *col = cs_g2 + lane;
+                const int yb = ya + 1;
+                const bool hasb = yb < H;
+                uint32_t ba = col[ya * CS_W], bb = hasb ? col[yb * CS_W] : 0u;
+                if (hasb) {
+                    const uint32_t a0 = ba;
+                    ba = min(ba, bb + 1u);
+                    bb = min(bb, a0 + 1u);
                 }
-                if (best >= DBIG) best = final2d ? (uint32_t)(y + 1) * (y + 1) + (uint32_t)x * x : DBIG;
-                out[sbase + (long long)y * W + x] = best;
-                if (final2d) mymax = max(mymax, best);
+                for (int k = 1;; k++) {
+                    const uint32_t kk = (uint32_t)k * k;
+                    const int ru = ya - k, rd = yb + k;
+                    if (kk >= max(ba, bb) || (ru < 0 && rd >= H)) break;
+                    const uint32_t k1 = kk + 2u * k + 1u;
+                    if (ru >= 0) {
+                        const uint32_t g2 = col[ru * CS_W];
+                        ba = min(ba, g2 + kk);
+                        bb = min(bb, g2 + k1);
+                    }
+                    if (rd < H) {
+                        const uint32_t g2 = col[rd * CS_W];
+                        bb = min(bb, g2 + kk);
+                        ba = min(ba, g2 + k1);
+                    }
+                }
+                if (ba >= DBIG) ba = final2d ? (uint32_t)(ya + 1) * (ya + 1) + (uint32_t)x * x : DBIG;
+                out[sbase + (long long)ya * W + x] = ba;
+                if (final2d) mymax = max(mymax, ba);
+                if (hasb) {
+                    if (bb >= DBIG) bb = final2d ? (uint32_t)(yb + 1) * (yb + 1) + (uint32_t)x * x : DBIG;
+                    out[sbase + (long long)yb * W + x] = bb;
+                    if (final2d) mymax = max(mymax, bb);
+                }
             }
     }
     if (final2d) {
