@@ -390,42 +390,48 @@ __global__ void __launch_bounds__(256) k_coldist_strip(const Tile *__restrict__ 
         }
         __syncthreads();
         if (x < W)
-            for (int ya = 2 * warp; ya < H; ya += 16) {
-                // two vertically adjacent pixels share every row they look at: the row k above the pair lies at distance k
-                // from the upper pixel and k + 1 from the lower one, and the other way round below
+            for (int ya = 4 * warp; ya < H; ya += 32) {
+                // four vertically adjacent pixels share every row they look at: the row k above the group lies at distance
+                // k + j from its j-th pixel, the row k below at distance k + 3 - j
                 const uint32_t *col = cs_g2 + lane;
-                const int yb = ya + 1;
-                const bool hasb = yb < H;
-                uint32_t ba = col[ya * CS_W], bb = hasb ? col[yb * CS_W] : 0u;
-                if (hasb) {
-                    const uint32_t a0 = ba;
-                    ba = min(ba, bb + 1u);
-                    bb = min(bb, a0 + 1u);
+                uint32_t g0[4], b[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) g0[j] = ya + j < H ? col[(ya + j) * CS_W] : DBIG;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    b[j] = g0[j];
+#pragma unroll
+                    for (int i2 = 0; i2 < 4; i2++)
+                        if (i2 != j) b[j] = min(b[j], g0[i2] + (uint32_t)((i2 - j) * (i2 - j)));
                 }
                 for (int k = 1;; k++) {
                     const uint32_t kk = (uint32_t)k * k;
-                    const int ru = ya - k, rd = yb + k;
-                    if (kk >= max(ba, bb) || (ru < 0 && rd >= H)) break;
-                    const uint32_t k1 = kk + 2u * k + 1u;
+                    const int ru = ya - k, rd = ya + 3 + k;
+                    // rows of the group beyond the tile never win: their pixels are not stored
+                    uint32_t bm = b[0];
+#pragma unroll
+                    for (int j = 1; j < 4; j++)
+                        if (ya + j < H) bm = max(bm, b[j]);
+                    if (kk >= bm || (ru < 0 && rd >= H)) break;
                     if (ru >= 0) {
                         const uint32_t g2 = col[ru * CS_W];
-                        ba = min(ba, g2 + kk);
-                        bb = min(bb, g2 + k1);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) b[j] = min(b[j], g2 + kk + (uint32_t)(2 * k * j + j * j));
                     }
                     if (rd < H) {
                         const uint32_t g2 = col[rd * CS_W];
-                        bb = min(bb, g2 + kk);
-                        ba = min(ba, g2 + k1);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) b[j] = min(b[j], g2 + kk + (uint32_t)(2 * k * (3 - j) + (3 - j) * (3 - j)));
                     }
                 }
-                if (ba >= DBIG) ba = final2d ? (uint32_t)(ya + 1) * (ya + 1) + (uint32_t)x * x : DBIG;
-                out[sbase + (long long)ya * W + x] = ba;
-                if (final2d) mymax = max(mymax, ba);
-                if (hasb) {
-                    if (bb >= DBIG) bb = final2d ? (uint32_t)(yb + 1) * (yb + 1) + (uint32_t)x * x : DBIG;
-                    out[sbase + (long long)yb * W + x] = bb;
-                    if (final2d) mymax = max(mymax, bb);
-                }
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (ya + j < H) {
+                        uint32_t v = b[j];
+                        if (v >= DBIG) v = final2d ? (uint32_t)(ya + j + 1) * (ya + j + 1) + (uint32_t)x * x : DBIG;
+                        out[sbase + (long long)(ya + j) * W + x] = v;
+                        if (final2d) mymax = max(mymax, v);
+                    }
             }
     }
     if (final2d) {
