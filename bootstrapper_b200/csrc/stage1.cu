@@ -1731,7 +1731,9 @@ __global__ void __launch_bounds__(256) k_finalize(const Tile *__restrict__ tiles
     const BlkDev b = blks[t.block];
     const int W = t.W, H = t.H;
     const long long nw = (long long)t.wD * t.wH * t.wW;
-    const long long koff = t.wbase - b.wbase;
+    // a tile's write region is the block's write ROI (3-D mode) or one z plane of it (xy mode): block coordinates are the
+    // tile's write coordinates plus the plane number
+    const int zoff = (int)((t.wbase - b.wbase) / ((long long)t.wH * t.wW));
     const uint32_t first = blk_first[t.block];
     const uint32_t fb = fbase[blockIdx.y];
     const uint32_t *pp = cpar + t.base;
@@ -1741,9 +1743,9 @@ __global__ void __launch_bounds__(256) k_finalize(const Tile *__restrict__ tiles
         int x = 0, y = 0, z = 0;
         if (kk < nw) {
             int tx, ty, tz;
-            unravel3(kk, t.wW, t.wH, tx, ty, tz);
+            unravel3f((uint32_t)kk, t.wW, t.wH, t.fwW, t.fwH, tx, ty, tz);
             const long long i = ((long long)(tz + t.wz) * H + (ty + t.wy)) * W + (tx + t.wx);
-            unravel3(koff + kk, b.ws[2], b.ws[1], x, y, z);
+            x = tx, y = ty, z = tz + zoff;
             uint32_t l = lab[t.base + i];
             uint64_t id = 0;
             if (l && l < CLAIM) {
@@ -1754,7 +1756,7 @@ __global__ void __launch_bounds__(256) k_finalize(const Tile *__restrict__ tiles
                     if (fl & FF_CROSS) {
                         uint32_t root = uf_find(pp, (uint32_t)i);
                         int rx, ry, rz;
-                        unravel3(root, W, H, rx, ry, rz);
+                        unravel3f(root, W, H, t.fW, t.fH, rx, ry, rz);
                         rw = (uint32_t)tile_widx(t, rz, ry, rx);
                     } else {
                         rw = fmin[fi];
@@ -2050,7 +2052,7 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
             t.base = P_pix;
             t.wbase = V_w;
             long long np = (long long)t.D * t.H * t.W;
-            P_pix += np;
+            P_pix += (np + 31) & ~31LL;   // 32-aligned tile bases (16-byte label loads of flood v3)
             maxpix = std::max(maxpix, np);
             t.set_divs();
                 tiles.push_back(t);

@@ -57,6 +57,7 @@ CASES = [
     ((20, 160, 160), (10, 80, 80), (2, 10, 10), {}, np.uint8),
     ((24, 130, 170), (10, 64, 64), (1, 8, 8), {}, np.uint8),                                  # ragged: trailing blocks shrink
     ((16, 96, 96), (8, 48, 48), (1, 6, 6), {"fragments_in_xy": False}, np.uint8),             # 3-D seeded mode
+    ((14, 45, 31), (7, 23, 16), (1, 3, 3), {"fragments_in_xy": False, "min_seed_distance": 4}, np.uint8),   # odd tile sizes
     ((12, 120, 120), (6, 60, 60), (1, 8, 8), {"filter_fragments": 0.0, "remove_debris": 0}, np.uint8),
     ((12, 120, 120), (6, 60, 60), (1, 8, 8), {"min_seed_distance": 5, "thresholds": [0.1, 0.9]}, np.uint8),
     ((12, 120, 120), (6, 60, 60), (1, 8, 8), {}, np.float32),
