@@ -1496,6 +1496,27 @@ __global__ void __launch_bounds__(256) k_scatter_labels(const Tile *__restrict__
     }
 }
 
+// the same through shared memory when a tile's 16-bit labels fit there (one CTA per tile): the scattered writes stay on
+// chip and the label plane leaves with coalesced stores; mask pixels the flood did not reach get 0 instead of UNLAB (every
+// consumer treats both as "no fragment")
+static constexpr int SCAT_NT = 1024;
+__global__ void __launch_bounds__(SCAT_NT) k_scatter_labels_tile(const Tile *__restrict__ tiles, const uint32_t *__restrict__ tile_q,
+                                                                 const uint32_t *__restrict__ queue, uint32_t *__restrict__ lab) {
+    extern __shared__ uint16_t sc_lab[];
+    const Tile t = tiles[blockIdx.x];
+    const int npix = t.H * t.W;
+    for (int i = threadIdx.x; i < (npix + 1) / 2; i += SCAT_NT) ((uint32_t *)sc_lab)[i] = 0u;
+    __syncthreads();
+    const uint32_t qb = tile_q[blockIdx.x], qe = tile_q[blockIdx.x + 1];
+    for (uint32_t q = qb + threadIdx.x; q < qe; q += SCAT_NT) {
+        const uint32_t e = __ldcs(&queue[q]);
+        if (e != NONE32) sc_lab[e & F2_PIXMASK] = (uint16_t)(e >> 17);
+    }
+    __syncthreads();
+    uint32_t *out = lab + t.base;
+    for (int i = threadIdx.x; i < npix; i += SCAT_NT) out[i] = sc_lab[i];
+}
+
 // ------------------------------------------------------------------ fragment statistics
 // One table entry per watershed fragment (index = fbase[tile] + label - 1): affinity sum + voxel count over the
 // whole read-ROI tile (filter_avg_fragments / remove_small_objects see the uncropped array,
@@ -2261,6 +2282,11 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
             BS_FLOOD2(false, false);
 #undef BS_FLOOD2
         g_prof.mark("s1.flood_scatter", s);
+        const size_t scat_smem = (((size_t)maxpix + 1) / 2) * 4;
+        if (scat_smem <= 220 * 1024) {
+            BS_CUDA(cudaFuncSetAttribute(k_scatter_labels_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scat_smem));
+            BS_LAUNCH(k_scatter_labels_tile, ntiles, SCAT_NT, scat_smem, s, dt, tile_q.as<uint32_t>(), queue.as<uint32_t>(), lab.as<uint32_t>());
+        } else
         BS_LAUNCH(k_scatter_labels, dim3((unsigned)std::min<long long>(std::max<long long>((maxpix + 1023) / 1024, 1), 2048), ntiles), 256, 0, s, dt, tile_q.as<uint32_t>(), queue.as<uint32_t>(), lab.as<uint32_t>());
     } else if (flood3) {
         BS_CUDA(cudaFuncSetAttribute(k_flood3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flood3_smem(levcap3)));
