@@ -627,7 +627,9 @@ __global__ void __launch_bounds__(256) k_seed_label_hist(const Tile *__restrict_
             else
                 atomicAdd(&hist[hb + d], 1u);
         }
-        lab[t.base + i] = l;
+        // compact_labels == 2: the label plane is rewritten as a whole after the flood (k_scatter_labels_tile), only the
+        // seeds' labels are read before that
+        if (compact_labels != 2 || (l != 0 && l != UNLAB)) lab[t.base + i] = l;
     }
     __syncthreads();
     for (int j = threadIdx.x; j < SH; j += blockDim.x)
@@ -2203,8 +2205,12 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     else
         BS_TRY(queue.alloc(4 * (size_t)P_pix, s));
     BS_TRY(fstats.alloc_zero(16, s));
+    // flood v2 labels of a tile fit shared memory as 16-bit values: the scatter after the flood rewrites the whole plane
+    const size_t scat_smem = (((size_t)maxpix + 1) / 2) * 4;
+    const bool tile_scatter = v2 && scat_smem <= 220 * 1024;
     BS_LAUNCH(k_seed_label_hist, grid, 256, 0, s, dt, lv.as<uint32_t>(), msk.as<uint8_t>(), d2.as<uint32_t>(),
-              lab.as<uint32_t>(), hbase.as<uint32_t>(), hist.as<uint32_t>(), sbits.as<uint32_t>(), swscan.as<uint32_t>(), v2 ? 1 : 0);
+              lab.as<uint32_t>(), hbase.as<uint32_t>(), hist.as<uint32_t>(), sbits.as<uint32_t>(), swscan.as<uint32_t>(),
+              v2 ? (tile_scatter && !g_debug ? 2 : 1) : 0);
     if (Htot) {
         BS_LAUNCH(k_nzflag, cdiv(Htot, 256), 256, 0, s, hist.as<uint32_t>(), nz.as<uint8_t>(), Htot);
         BS_TRY(scan_exclusive_u8(nz.as<uint8_t>(), lrank.as<uint32_t>(), Htot, d_tot + 2, s));
@@ -2282,8 +2288,7 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
             BS_FLOOD2(false, false);
 #undef BS_FLOOD2
         g_prof.mark("s1.flood_scatter", s);
-        const size_t scat_smem = (((size_t)maxpix + 1) / 2) * 4;
-        if (scat_smem <= 220 * 1024) {
+        if (tile_scatter) {
             BS_CUDA(cudaFuncSetAttribute(k_scatter_labels_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scat_smem));
             BS_LAUNCH(k_scatter_labels_tile, ntiles, SCAT_NT, scat_smem, s, dt, tile_q.as<uint32_t>(), queue.as<uint32_t>(), lab.as<uint32_t>());
         } else
