@@ -228,3 +228,26 @@ def test_refine_restatement_on_a_hand_checked_volume():
     assert rem.tolist() == [5, 9]
     out = orf.remap(seg, {7: 0, 9: 9, 11: 9})
     assert sorted(np.unique(out).tolist()) == [0, 5, 9] and int((out == 9).sum()) == 8
+
+
+def test_flood_of_a_mask_component_does_not_depend_on_the_others(tie="index"):
+    """the priority flood only moves through mask pixels, so the (level, age) order restricted to one connected
+    component of the mask is that component's own order: flooding a component alone (same image, same seeds, the
+    other components masked out) gives exactly its part of the whole-slice result.  (Ground for splitting a tile's
+    flood by component)  This holds for the index rule of the CUDA path (D1); under skimage's own
+    tie behaviour the seeds all carry age 0 and their order follows the heap's layout history, which the other
+    components' seeds take part in."""
+    from scipy.ndimage import distance_transform_edt, label, maximum_filter
+    from bootstrapper_b200.synth import synth_affs
+    affs = synth_affs((2, 150, 170), seed=13).astype(np.float64) / 255
+    for z in range(2):
+        mask = 0.5 * (affs[1, z] + affs[2, z]) > 0.5
+        dist = distance_transform_edt(mask)
+        seeds, n = label(maximum_filter(dist, 10) == dist)
+        whole = sk_watershed(dist.max() - dist, seeds, mask, seed_tie=tie)
+        comps, nc = label(mask)
+        assert nc > 10
+        for c in range(1, nc + 1, max(1, nc // 12)):
+            sub = comps == c
+            alone = sk_watershed(dist.max() - dist, seeds, sub, seed_tie=tie)
+            assert np.array_equal(alone[sub], whole[sub]) and not alone[~sub].any()
