@@ -77,9 +77,10 @@ def exchange_halos(frags_win, geo, geos, rank, world, group=None):
 
 def allgather_counts(counts, world, device, group=None):
     """per-block fragment counts: every block is owned by exactly one rank -> element-wise sum"""
+    if world == 1:
+        return np.asarray(counts, dtype=np.int64)
     t = torch.as_tensor(counts, dtype=torch.int64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t.cpu().numpy()
 
 
