@@ -8,6 +8,12 @@ Sources executed (unmodified, loaded by path):
   bootstrapper/post/merge_tree.py   -> merge_tree.npz   (MergeTree.merge / find_merges)
   bootstrapper/post/cc.py           -> cc_flood.npz, cc_affs.npz (compute_connected_component_segmentation)
   bootstrapper/gp/add_aff_errors.py -> aff_errors.npz  (_create_diff / _create_mask; gunpowder + skimage imports stubbed)
+  bootstrapper/post/blockwise/watershed_frags.py -> filter_fragments.npz (filter_avg_fragments, method body via ast)
+  bootstrapper/post/blockwise/watershed_frags.py -> compute_fragments_shift.npz (compute_fragments with the watershed call recorded)
+  bootstrapper/post/ws.py           -> ws_glue.npz      (whole file; skimage's watershed replaced by the oracle's restatement)
+  bootstrapper/post/blockwise/waterz_agglom.py -> agglomerate_glue.npz (agglomerate_in_block around the reference's MergeTree;
+                                       waterz / funlib relabel replaced by the oracle's restatements)
+  bootstrapper/post/blockwise/watershed_frags.py -> watershed_in_block_glue.npz (get_fragments / watershed_in_block over all blocks)
   bootstrapper/post/naming.py       -> naming.json      (build_name; `import zarr` stubbed)
   bootstrapper/segment.py           -> seg_config.json  (DEFAULTS, get_seg_config)
 """
@@ -157,6 +163,308 @@ def golden_aff_errors():
     print("aff_errors.npz", len(out))
 
 
+def golden_filter_fragments():
+    """WatershedFrags.filter_avg_fragments (post/blockwise/watershed_frags.py:148-156), the method body executed as it
+    stands in the reference file (extracted by ast: the module itself needs volara / funlib / skimage to import);
+    volara.tmp.replace_values is stubbed by its documented in-place value map."""
+    import ast
+    from scipy.ndimage import mean as ndi_mean
+    src = open(f"{REF}/post/blockwise/watershed_frags.py").read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "filter_avg_fragments")
+    mod = ast.Module(body=[fn], type_ignores=[])
+
+    def replace_values(arr, old, new):
+        lut = dict(zip(old.tolist(), new.tolist()))
+        flat = arr.reshape(-1)
+        for i, v in enumerate(flat.tolist()):
+            if v in lut:
+                flat[i] = lut[v]
+
+    ns = {"np": np, "ndi_mean": ndi_mean, "replace_values": replace_values}
+    exec(compile(mod, "watershed_frags.filter_avg_fragments", "exec"), ns)
+    rng = np.random.default_rng(31)
+    out = {}
+    for ci, (shape, dtype, thr) in enumerate([((4, 24, 20), np.float64, 0.5), ((3, 16, 16), np.float32, 0.35)]):
+        frags = np.zeros(shape, dtype=np.uint64)
+        ids = rng.permutation(np.arange(1, 40))
+        for k, (z, y, x) in enumerate(np.ndindex(shape[0], shape[1] // 4, shape[2] // 4)):
+            frags[z, 4 * y:4 * y + 4, 4 * x:4 * x + 4] = ids[k % len(ids)] if rng.random() < 0.9 else 0
+        level = rng.random(int(frags.max()) + 1)
+        affs = np.clip(level[frags.astype(np.int64)][None] + 0.15 * rng.standard_normal((3,) + shape), 0, 1).astype(dtype)
+        got = frags.copy()
+        ns["filter_avg_fragments"](None, affs, got, thr)
+        out[f"affs{ci}"], out[f"frags{ci}"], out[f"out{ci}"], out[f"thr{ci}"] = affs, frags, got, np.array(thr)
+        assert 0 < np.unique(got).size < np.unique(frags).size
+    np.savez_compressed(os.path.join(OUT, "filter_fragments.npz"), **out)
+    print("filter_fragments.npz", len(out))
+
+
+SHIFT_CASES = [
+    dict(sigma=None, bias=[-0.05, -0.1, -0.1], seed_eps=None, min_seed_distance=10, fragments_in_xy=True),
+    dict(sigma=[1, 2, 2], bias=None, seed_eps=None, min_seed_distance=10, fragments_in_xy=True),
+    dict(sigma=None, bias=0.07, seed_eps=0.01, min_seed_distance=6, fragments_in_xy=False),
+    dict(sigma=[0, 1.5, 0.8], bias=[-0.02, -0.03, -0.03], seed_eps=0.02, min_seed_distance=10, fragments_in_xy=False),
+]
+
+
+def golden_compute_fragments_shift():
+    """WatershedFrags.compute_fragments (post/blockwise/watershed_frags.py:115-146), the method body executed as it
+    stands in the reference file (extracted by ast), with `watershed_from_affinities` replaced by a recorder: pins the
+    array the reference hands to the watershed (sigma / bias / seed_eps shifts; scipy is the real scipy)."""
+    import ast
+    from scipy.ndimage import distance_transform_edt, gaussian_filter, label, maximum_filter
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from bootstrapper_b200.synth import synth_affs
+    src = open(f"{REF}/post/blockwise/watershed_frags.py").read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "compute_fragments")
+    seen = {}
+
+    def recorder(affs, fragments_in_xy=False, min_seed_distance=10):
+        seen["affs"], seen["xy"], seen["msd"] = affs, fragments_in_xy, min_seed_distance
+        return np.zeros(affs.shape[1:], dtype=np.uint64), 0
+
+    ns = {"np": np, "gaussian_filter": gaussian_filter, "distance_transform_edt": distance_transform_edt,
+          "maximum_filter": maximum_filter, "label": label, "watershed_from_affinities": recorder}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "watershed_frags.compute_fragments", "exec"), ns)
+    out = {}
+    for ci, case in enumerate(SHIFT_CASES):
+        dtype = np.float64 if ci % 2 == 0 else np.float32          # uint8 input arrives as float64 / 255, float32 as is
+        affs = (synth_affs((8, 40, 36), seed=40 + ci).astype(np.float64) / 255).astype(dtype)
+        me = types.SimpleNamespace(noise_eps=None, **case)
+        ns["compute_fragments"](me, affs.copy())
+        assert seen["xy"] == case["fragments_in_xy"] and seen["msd"] == case["min_seed_distance"]
+        out[f"in{ci}"], out[f"shifted{ci}"] = affs, seen["affs"]
+    np.savez_compressed(os.path.join(OUT, "compute_fragments_shift.npz"), **out)
+    with open(os.path.join(OUT, "compute_fragments_shift.json"), "w") as f:
+        json.dump(SHIFT_CASES, f, indent=1)
+    print("compute_fragments_shift.npz", len(out))
+
+
+def golden_ws_glue():
+    """post/ws.py executed unmodified, with skimage.segmentation.watershed (absent here) replaced by the oracle's
+    restatement of it: pins everything AROUND the flood -- mean affinities, the > 0.5 * max threshold, scipy's EDT /
+    maximum filter / label, the per-slice id offsets and the seed output (ws.py:8-112) -- given that flood."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from bootstrapper_b200.synth import synth_affs
+    from oracle.native import sk_watershed
+    seg = types.ModuleType("skimage.segmentation")
+    seg.watershed = lambda image, markers, mask=None: sk_watershed(image, markers, mask, seed_tie="heap")
+    sys.modules["skimage"] = sys.modules.get("skimage") or types.ModuleType("skimage")
+    sys.modules["skimage.segmentation"] = seg
+    ws = load("ref_ws", f"{REF}/post/ws.py")
+    out = {}
+    for ci, (shape, dtype, maxv, xy, msd) in enumerate([((5, 60, 50), np.float64, 255.0, True, 10), ((6, 40, 44), np.float32, 1.0, False, 6),
+                                                         ((3, 64, 64), np.float32, 1.0, True, 10)]):
+        a8 = synth_affs(shape, seed=50 + ci)
+        affs = a8.astype(dtype) if maxv == 255.0 else (a8.astype(np.float32) / np.float32(255)).astype(dtype)
+        frags, max_id, seeds = ws.watershed_from_affinities(affs, max_affinity_value=maxv, fragments_in_xy=xy, return_seeds=True,
+                                                            min_seed_distance=msd)
+        out[f"affs{ci}"], out[f"frags{ci}"], out[f"seeds{ci}"] = affs, frags, seeds
+        out[f"meta{ci}"] = np.array([maxv, int(xy), msd, max_id], dtype=np.float64)
+        assert frags.dtype == np.uint64 and frags.any()
+    np.savez_compressed(os.path.join(OUT, "ws_glue.npz"), **out)
+    print("ws_glue.npz", len(out))
+
+
+def golden_agglomerate_glue():
+    """WaterzAgglom.agglomerate_in_block (post/blockwise/waterz_agglom.py:106-170), the method body executed as it
+    stands in the reference file (extracted by ast) around the reference's own MergeTree; `waterz.agglomerate` and
+    funlib's `relabel` (absent) are the oracle's restatements, arrays / graph store are small in-memory stand-ins.
+    Pins the glue: float32 normalisation, dense relabel + backwards map, initial RAG at threshold 0, history -> merge
+    tree, merge_score per initial edge (NaN -> None)."""
+    import ast
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from bootstrapper_b200.synth import synth_affs
+    from oracle import blockwise as ob
+    from oracle.native import Waterz
+    mt_mod = load("ref_merge_tree2", f"{REF}/post/merge_tree.py")
+
+    def agglomerate(affs, thresholds, fragments, scoring_function, discretize_queue, return_merge_history, return_region_graph):
+        assert scoring_function == "OneMinus<MeanAffinity<RegionGraphType, ScoreValue>>" and discretize_queue == 256
+        wz = Waterz(affs, fragments, 256, "faithful", True)
+        for thr in thresholds:
+            a, b, c, sc = wz.merge_until(float(thr))
+            u, v, s, _, _ = wz.region_graph()
+            yield (wz.segmentation(),
+                   [dict(a=int(x), b=int(y), c=int(z), score=float(w)) for x, y, z, w in zip(a, b, c, sc)],
+                   [dict(u=int(x), v=int(y), score=float(w)) for x, y, w in zip(u, v, s)])
+
+    waterz = types.ModuleType("waterz")
+    waterz.agglomerate = agglomerate
+    arrays = types.ModuleType("funlib.segment.arrays")
+    arrays.relabel = lambda a, return_backwards_map=True: ob.funlib_relabel(a)
+    for name, mod in (("waterz", waterz), ("funlib", types.ModuleType("funlib")), ("funlib.segment", types.ModuleType("funlib.segment")),
+                      ("funlib.segment.arrays", arrays)):
+        sys.modules[name] = mod
+    src = open(f"{REF}/post/blockwise/waterz_agglom.py").read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "agglomerate_in_block")
+    ns = {"np": np, "MergeTree": mt_mod.MergeTree}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "waterz_agglom.agglomerate_in_block", "exec"), ns)
+
+    class Arr:
+        def __init__(self, a):
+            self.a = a
+
+        def to_ndarray(self, roi, fill_value=0):
+            return ob.to_ndarray(self.a, roi[0], roi[1], fill_value)
+
+    class Graph:
+        def __init__(self):
+            self.e = {}
+
+        def add_edge(self, u, v, **data):
+            self.e[(u, v)] = dict(data)
+
+        def edges(self, data=True):
+            return [(u, v, d) for (u, v), d in self.e.items()]
+
+    class Provider:
+        def __getitem__(self, roi):
+            return Graph()
+
+        def write_graph(self, rag, roi, write_nodes=False):
+            self.written = [(u, v, d["merge_score"]) for u, v, d in rag.edges(data=True)]
+
+    out = {}
+    for ci, (shape, dtype) in enumerate([((6, 48, 40), np.uint8), ((5, 40, 40), np.float32)]):
+        a8 = synth_affs(shape, seed=60 + ci)
+        affs = a8 if dtype == np.uint8 else (a8.astype(np.float32) / np.float32(255))
+        frags, _ = __import__("oracle.ws", fromlist=["x"]).watershed_from_affinities(
+            a8.astype(np.float64) / 255, fragments_in_xy=True, seed_tie="index")
+        frags[frags > 0] += np.uint64(1000 * (ci + 1))                  # ids far from dense: the backwards map matters
+        roi = ((0, 0, 0), shape)
+        prov = Provider()
+        me = types.SimpleNamespace(merge_function="OneMinus<MeanAffinity<RegionGraphType, ScoreValue>>")
+        ns["agglomerate_in_block"](me, types.SimpleNamespace(read_roi=roi, write_roi=roi), Arr(affs), Arr(frags), prov)
+        e = prov.written
+        out[f"affs{ci}"], out[f"frags{ci}"] = affs, frags
+        out[f"u{ci}"] = np.array([x[0] for x in e], dtype=np.uint64)
+        out[f"v{ci}"] = np.array([x[1] for x in e], dtype=np.uint64)
+        out[f"score{ci}"] = np.array([np.nan if x[2] is None else x[2] for x in e], dtype=np.float64)
+        assert len(e) > 20 and np.isfinite(out[f"score{ci}"]).any()
+    np.savez_compressed(os.path.join(OUT, "agglomerate_glue.npz"), **out)
+    print("agglomerate_glue.npz", len(out))
+
+
+def golden_watershed_in_block_glue():
+    """WatershedFrags.get_fragments / watershed_in_block (post/blockwise/watershed_frags.py:178-246), the method bodies
+    executed as they stand in the reference file (extracted by ast) together with compute_fragments /
+    filter_avg_fragments and the reference's post/ws.py; skimage's watershed / label / remove_small_objects are the
+    oracle's restatements, funlib's Array / Roi / Coordinate and the graph store small in-memory stand-ins
+    (Coordinate truncates floats like funlib.geometry does [3P-recall]).  Pins the glue of stage 1: normalisation,
+    the empty-block early-out, mask handling, crop to the write ROI, relabel + block id offset, node positions / sizes."""
+    import ast
+    from scipy.ndimage import center_of_mass, distance_transform_edt, gaussian_filter, label, maximum_filter
+    from scipy.ndimage import mean as ndi_mean
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from bootstrapper_b200.synth import synth_affs
+    from oracle import blockwise as ob
+    from oracle.native import sk_label, sk_watershed
+    seg = types.ModuleType("skimage.segmentation")
+    seg.watershed = lambda image, markers, mask=None: sk_watershed(image, markers, mask, seed_tie="heap")
+    sys.modules["skimage"] = sys.modules.get("skimage") or types.ModuleType("skimage")
+    sys.modules["skimage.segmentation"] = seg
+    ws = load("ref_ws2", f"{REF}/post/ws.py")
+
+    class Coord(tuple):
+        def __new__(cls, v):
+            return super().__new__(cls, (int(x) for x in v))
+
+        def __mul__(self, o):
+            return Coord(a * b for a, b in zip(self, o))
+
+        __rmul__ = __mul__
+
+        def __add__(self, o):
+            return Coord(a + b for a, b in zip(self, o))
+
+        __radd__ = __add__
+
+    class Roi:
+        def __init__(self, offset, shape):
+            self.offset, self.shape, self.dims = Coord(offset), Coord(shape), len(shape)
+
+    class Vol:
+        def __init__(self, a, voxel_size=(1, 1, 1)):
+            self.a, self.dtype, self.voxel_size = a, a.dtype, Coord(voxel_size)
+
+        def to_ndarray(self, roi, fill_value=0):
+            return ob.to_ndarray(self.a, roi.offset, roi.shape, fill_value)
+
+        def __setitem__(self, roi, data):
+            self.a[tuple(slice(o, o + s) for o, s in zip(roi.offset, roi.shape))] = data
+
+    class Array:                                   # funlib.persistence.arrays.Array(data, offset=, voxel_size=)
+        def __init__(self, data, offset, voxel_size):
+            self.data, self.offset = data, offset
+
+        def to_ndarray(self, roi):
+            return self.data[tuple(slice(o - b, o - b + s) for o, b, s in zip(roi.offset, self.offset, roi.shape))]
+
+    class Graph:
+        def __init__(self):
+            self.nodes = {}
+
+        def add_node(self, i, **data):
+            self.nodes[i] = data
+
+    class Provider:
+        def __init__(self):
+            self.nodes = {}
+
+        def __getitem__(self, roi):
+            return Graph()
+
+        def write_graph(self, rag, roi):
+            self.nodes.update(rag.nodes)
+
+    src = open(f"{REF}/post/blockwise/watershed_frags.py").read()
+    tree = ast.parse(src)
+    wanted = ("compute_fragments", "filter_avg_fragments", "get_fragments", "watershed_in_block")
+    fns = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    cls = ast.ClassDef(name="Frags", bases=[], keywords=[], body=fns, decorator_list=[])
+    mod = ast.fix_missing_locations(ast.Module(body=[cls], type_ignores=[]))
+    ns = {"np": np, "gaussian_filter": gaussian_filter, "distance_transform_edt": distance_transform_edt,
+          "maximum_filter": maximum_filter, "label": label, "ndi_mean": ndi_mean, "center_of_mass": center_of_mass,
+          "watershed_from_affinities": ws.watershed_from_affinities, "Array": Array, "Coordinate": Coord,
+          "relabel": lambda x, return_num=True: sk_label(x),
+          "remove_small_objects": lambda x, min_size: ob.remove_small_objects(x, min_size),
+          "replace_values": lambda arr, old, new: arr.__setitem__(np.isin(arr, old), 0),
+          "logger": types.SimpleNamespace(info=lambda *a, **k: None)}
+    exec(compile(mod, "watershed_frags.Frags", "exec"), ns)
+    out = {}
+    shape, bs, ctx = (8, 64, 56), (4, 32, 28), (1, 6, 6)
+    for ci, (dtype, use_mask, xy) in enumerate([(np.uint8, False, True), (np.float32, True, True), (np.uint8, True, False)]):
+        a8 = synth_affs(shape, seed=70 + ci)
+        affs = a8 if dtype == np.uint8 else (a8.astype(np.float32) / np.float32(255))
+        mask = None
+        if use_mask:
+            mask = np.ones(shape, dtype=np.uint8) * (255 if ci == 1 else 1)
+            mask[:, :10, :12] = 0
+        frags = np.zeros(shape, dtype=np.uint64)
+        prov = Provider()
+        me = ns["Frags"]()
+        for k, v in dict(noise_eps=None, sigma=None, bias=None, seed_eps=None, min_seed_distance=10, fragments_in_xy=xy,
+                         epsilon_agglomerate=0, filter_fragments=0.1, remove_debris=16, num_voxels_in_block=int(np.prod(bs)),
+                         voxel_size=Coord((1, 1, 1))).items():
+            setattr(me, k, v)
+        blocks = ob.enumerate_blocks((0, 0, 0), shape, bs, ctx)
+        for b in blocks:
+            blk = types.SimpleNamespace(read_roi=Roi(b.read_offset, b.read_shape), write_roi=Roi(b.write_offset, b.write_shape),
+                                        block_id=("task", b.block_id))
+            me.watershed_in_block(blk, Vol(affs), Vol(frags), prov, mask=None if mask is None else Vol(mask))
+        ids = np.array(sorted(prov.nodes), dtype=np.uint64)
+        out[f"affs{ci}"], out[f"frags{ci}"], out[f"ids{ci}"] = affs, frags, ids
+        out[f"pos{ci}"] = np.array([prov.nodes[int(i)]["position"] for i in ids], dtype=np.int64)
+        out[f"size{ci}"] = np.array([prov.nodes[int(i)]["size"] for i in ids], dtype=np.int64)
+        if mask is not None:
+            out[f"mask{ci}"] = mask
+        out[f"meta{ci}"] = np.array([int(xy)] + list(bs) + list(ctx), dtype=np.int64)
+        assert ids.size > 10 and np.array_equal(np.unique(frags[frags > 0]), ids)
+    np.savez_compressed(os.path.join(OUT, "watershed_in_block_glue.npz"), **out)
+    print("watershed_in_block_glue.npz", len(out))
+
+
 def golden_naming():
     sys.modules.setdefault("zarr", types.ModuleType("zarr"))       # naming.py only uses zarr in dump_params
     nm = load("ref_naming", f"{REF}/post/naming.py")
@@ -235,6 +543,11 @@ if __name__ == "__main__":
     golden_cc()
     golden_cc_affs()
     golden_aff_errors()
+    golden_filter_fragments()
+    golden_compute_fragments_shift()
+    golden_ws_glue()
+    golden_agglomerate_glue()
+    golden_watershed_in_block_glue()
     golden_naming()
     golden_config()
     print("golden fixtures written to", OUT)

@@ -251,3 +251,85 @@ def test_flood_of_a_mask_component_does_not_depend_on_the_others(tie="index"):
             sub = comps == c
             alone = sk_watershed(dist.max() - dist, seeds, sub, seed_tie=tie)
             assert np.array_equal(alone[sub], whole[sub]) and not alone[~sub].any()
+
+
+def test_filter_avg_fragments_pinned_against_reference():
+    """oracle.blockwise.filter_avg_fragments against the reference's own method body (watershed_frags.py:148-156)"""
+    g = np.load(os.path.join(GOLD, "filter_fragments.npz"))
+    for ci in range(2):
+        frags = g[f"frags{ci}"].copy()
+        ob.filter_avg_fragments(g[f"affs{ci}"], frags, float(g[f"thr{ci}"]))
+        assert np.array_equal(frags, g[f"out{ci}"])
+
+
+def test_compute_fragments_shift_pinned_against_reference(monkeypatch):
+    """the array oracle.blockwise.compute_fragments hands to the watershed (sigma / bias / seed_eps shifts) against the
+    one the reference's own method body produces (watershed_frags.py:115-146, tests/golden/make_golden.py)"""
+    import json
+    g = np.load(os.path.join(GOLD, "compute_fragments_shift.npz"))
+    cases = json.load(open(os.path.join(GOLD, "compute_fragments_shift.json")))
+    seen = {}
+
+    def recorder(affs, fragments_in_xy=False, min_seed_distance=10, seed_tie="heap"):
+        seen["affs"] = affs
+        return np.zeros(affs.shape[1:], dtype=np.uint64), 0
+
+    monkeypatch.setattr(ob, "watershed_from_affinities", recorder)
+    for ci, case in enumerate(cases):
+        p = dict(case, noise_eps=None)
+        ob.compute_fragments(g[f"in{ci}"].copy(), p)
+        ref = g[f"shifted{ci}"]
+        assert seen["affs"].dtype == ref.dtype and np.array_equal(seen["affs"], ref)
+
+
+def test_ws_glue_pinned_against_reference():
+    """oracle.ws.watershed_from_affinities against the reference's post/ws.py run on the same flood (ws.py:8-112):
+    fragments, seeds and max id, 2-D per-slice and 3-D mode"""
+    from oracle.ws import watershed_from_affinities
+    g = np.load(os.path.join(GOLD, "ws_glue.npz"))
+    for ci in range(3):
+        maxv, xy, msd, max_id = g[f"meta{ci}"]
+        frags, mid, seeds = watershed_from_affinities(g[f"affs{ci}"], max_affinity_value=float(maxv), fragments_in_xy=bool(xy),
+                                                      return_seeds=True, min_seed_distance=int(msd), seed_tie="heap")
+        assert mid == int(max_id)
+        assert np.array_equal(frags, g[f"frags{ci}"]) and np.array_equal(seeds, g[f"seeds{ci}"])
+
+
+def test_agglomerate_glue_pinned_against_reference():
+    """oracle.blockwise.agglomerate_in_block against the reference's own method body run around the reference's
+    MergeTree and the same restated waterz (waterz_agglom.py:106-170): every initial RAG edge and its merge score"""
+    g = np.load(os.path.join(GOLD, "agglomerate_glue.npz"))
+    for ci in range(2):
+        affs, frags = g[f"affs{ci}"], g[f"frags{ci}"]
+        shape = frags.shape
+        blk = ob.Block(index=(0, 0, 0), block_id=0, read_offset=(0, 0, 0), read_shape=shape, write_offset=(0, 0, 0), write_shape=shape)
+        dbg = ob.agglomerate_in_block(blk, affs, frags, ob.Rag(), (0, 0, 0), stats_mode="faithful", return_debug=True)
+        us, vs, _ = dbg["initial"]
+        got = {(min(int(u), int(v)), max(int(u), int(v))): s for u, v, s in zip(us, vs, dbg["lca"])}
+        ref = {(min(int(u), int(v)), max(int(u), int(v))): s for u, v, s in zip(g[f"u{ci}"], g[f"v{ci}"], g[f"score{ci}"])}
+        assert got.keys() == ref.keys() and len(ref) > 20
+        for k, s in ref.items():
+            assert (np.isnan(s) and np.isnan(got[k])) or float(got[k]) == float(s), (k, got[k], s)
+
+
+def test_watershed_in_block_glue_pinned_against_reference():
+    """oracle.blockwise.watershed_in_block over all blocks of a small volume against the reference's own method bodies
+    (watershed_frags.py:178-246) run on the same restated skimage pieces: fragment array, node ids / positions / sizes;
+    uint8 and float32 input, 1- and 255-valued masks, 2-D and 3-D mode"""
+    g = np.load(os.path.join(GOLD, "watershed_in_block_glue.npz"))
+    for ci in range(3):
+        meta = g[f"meta{ci}"]
+        xy, bs, ctx = bool(meta[0]), tuple(int(v) for v in meta[1:4]), tuple(int(v) for v in meta[4:7])
+        affs = g[f"affs{ci}"]
+        mask = g[f"mask{ci}"] if f"mask{ci}" in g.files else None
+        shape = affs.shape[1:]
+        p = dict(ob.WS_DEFAULTS, fragments_in_xy=xy, filter_fragments=0.1, remove_debris=16, min_seed_distance=10)
+        frags = np.zeros(shape, dtype=np.uint64)
+        rag = ob.Rag()
+        for b in ob.enumerate_blocks((0, 0, 0), shape, bs, ctx):
+            ob.watershed_in_block(b, affs, frags, rag, p, (0, 0, 0), bs, mask=mask, seed_tie="heap", stats_mode="faithful")
+        assert np.array_equal(frags, g[f"frags{ci}"])
+        ids = g[f"ids{ci}"]
+        assert sorted(rag.node_pos) == [int(i) for i in ids]
+        assert np.array_equal(np.array([rag.node_pos[int(i)] for i in ids], dtype=np.int64), g[f"pos{ci}"])
+        assert np.array_equal(np.array([rag.node_size[int(i)] for i in ids], dtype=np.int64), g[f"size{ci}"])
