@@ -14,6 +14,7 @@ Sources executed (unmodified, loaded by path):
   bootstrapper/post/blockwise/waterz_agglom.py -> agglomerate_glue.npz (agglomerate_in_block around the reference's MergeTree;
                                        waterz / funlib relabel replaced by the oracle's restatements)
   bootstrapper/post/blockwise/watershed_frags.py -> watershed_in_block_glue.npz (get_fragments / watershed_in_block over all blocks)
+  bootstrapper/post/watershed.py    -> simple_watershed_glue.npz (simple_watershed with in-memory datasets)
   bootstrapper/post/naming.py       -> naming.json      (build_name; `import zarr` stubbed)
   bootstrapper/segment.py           -> seg_config.json  (DEFAULTS, get_seg_config)
 """
@@ -465,6 +466,99 @@ def golden_watershed_in_block_glue():
     print("watershed_in_block_glue.npz", len(out))
 
 
+def golden_simple_watershed_glue():
+    """post/watershed.py `simple_watershed` (:206-354), the function executed as it stands in the reference file
+    (extracted by ast) with the reference's own naming.py and ws.py; funlib's open_ds / prepare_ds / Roi are in-memory
+    stand-ins, skimage's watershed and `waterz.agglomerate` (default queue) the oracle's restatements.  Pins the glue
+    of the single-shot path: float32 normalisation, mask, sigma / bias shift, fragments, one segmentation per threshold,
+    dataset names."""
+    import ast
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from bootstrapper_b200.synth import synth_affs
+    from oracle.native import Waterz, sk_watershed
+    seg = types.ModuleType("skimage.segmentation")
+    seg.watershed = lambda image, markers, mask=None: sk_watershed(image, markers, mask, seed_tie="heap")
+    sys.modules["skimage"] = sys.modules.get("skimage") or types.ModuleType("skimage")
+    sys.modules["skimage.segmentation"] = seg
+    sys.modules.setdefault("zarr", types.ModuleType("zarr"))
+    store, written = {}, {}
+
+    class Roi:
+        def __init__(self, offset, shape):
+            self.offset, self.shape = tuple(offset), tuple(shape)
+
+        def sl(self):
+            return tuple(slice(o, o + s) for o, s in zip(self.offset, self.shape))
+
+    class DS:
+        def __init__(self, a, name=None):
+            self.a, self.name, self.shape, self.dtype = a, name, a.shape, a.dtype
+            self.roi = Roi((0, 0, 0), a.shape[-3:])
+            self.voxel_size, self.axis_names, self.units = (1, 1, 1), ["c^", "z", "y", "x"][-a.ndim:], ["nm"] * 3
+
+        def __getitem__(self, roi):
+            return self.a[(Ellipsis,) + roi.sl()]
+
+        def __setitem__(self, roi, data):
+            self.a[roi.sl()] = data
+            written[self.name] = self.a
+
+    persistence = types.ModuleType("funlib.persistence")
+    persistence.open_ds = lambda path: DS(store[path])
+    persistence.prepare_ds = lambda name, shape, offset, voxel_size, axis_names, dtype, units: DS(np.zeros(shape, dtype=dtype), name)
+    geometry = types.ModuleType("funlib.geometry")
+    geometry.Roi = Roi
+
+    def agglomerate(affs, thresholds, fragments, scoring_function):
+        assert scoring_function == "OneMinus<MeanAffinity<RegionGraphType, ScoreValue>>"
+        wz = Waterz(affs, fragments, 0, "faithful", True)
+        for thr in sorted(thresholds):
+            wz.merge_until(float(thr))
+            yield wz.segmentation()
+
+    waterz = types.ModuleType("waterz")
+    waterz.agglomerate = agglomerate
+    pkg = types.ModuleType("refpost")
+    pkg.__path__ = []
+    for name, mod in (("funlib", types.ModuleType("funlib")), ("funlib.persistence", persistence), ("funlib.geometry", geometry),
+                      ("waterz", waterz), ("refpost", pkg)):
+        sys.modules[name] = mod
+    naming = load("refpost.naming", f"{REF}/post/naming.py")
+    naming.dump_params = lambda *a, **k: None
+    sys.modules["refpost.naming"] = naming
+    sys.modules["refpost.ws"] = load("refpost.ws", f"{REF}/post/ws.py")
+    src = open(f"{REF}/post/watershed.py").read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "simple_watershed")
+    ns = {"__package__": "refpost", "__name__": "refpost.watershed"}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "watershed.simple_watershed", "exec"), ns)
+    out, names = {}, {}
+    cases = [dict(dtype="uint8", mask=False, cfg={}),
+             dict(dtype="float32", mask=True, cfg={"sigma": [0, 1.5, 1.0], "bias": [-0.05, -0.1, -0.1], "thresholds": [0.1, 0.3, 0.6]}),
+             dict(dtype="uint8", mask=False, cfg={"fragments_in_xy": False, "min_seed_distance": 6, "bias": [-0.03, -0.03, -0.03]})]
+    for ci, case in enumerate(cases):
+        shape = (5, 56, 48)
+        a8 = synth_affs(shape, seed=80 + ci)
+        store["affs"] = a8 if case["dtype"] == "uint8" else (a8.astype(np.float32) / np.float32(255))
+        cfg = dict(affs_dataset="affs", fragments_dataset="frags", seg_dataset_prefix="segs", **case["cfg"])
+        if case["mask"]:
+            m = np.ones(shape, dtype=np.uint8)
+            m[:, 40:, :20] = 0
+            store["mask"] = m
+            cfg["mask_dataset"] = "mask"
+            out[f"mask{ci}"] = m
+        written.clear()
+        ns["simple_watershed"](cfg)
+        names[str(ci)] = sorted(written)
+        out[f"affs{ci}"] = store["affs"]
+        for k, name in enumerate(sorted(written)):
+            out[f"out{ci}_{k}"] = written[name].copy()
+        assert len(written) == 1 + len(cfg.get("thresholds", [0.2, 0.35, 0.5]))
+    np.savez_compressed(os.path.join(OUT, "simple_watershed_glue.npz"), **out)
+    with open(os.path.join(OUT, "simple_watershed_glue.json"), "w") as f:
+        json.dump(dict(cases=cases, names=names), f, indent=1)
+    print("simple_watershed_glue.npz", len(out), names["1"])
+
+
 def golden_naming():
     sys.modules.setdefault("zarr", types.ModuleType("zarr"))       # naming.py only uses zarr in dump_params
     nm = load("ref_naming", f"{REF}/post/naming.py")
@@ -548,6 +642,7 @@ if __name__ == "__main__":
     golden_ws_glue()
     golden_agglomerate_glue()
     golden_watershed_in_block_glue()
+    golden_simple_watershed_glue()
     golden_naming()
     golden_config()
     print("golden fixtures written to", OUT)

@@ -333,3 +333,23 @@ def test_watershed_in_block_glue_pinned_against_reference():
         assert sorted(rag.node_pos) == [int(i) for i in ids]
         assert np.array_equal(np.array([rag.node_pos[int(i)] for i in ids], dtype=np.int64), g[f"pos{ci}"])
         assert np.array_equal(np.array([rag.node_size[int(i)] for i in ids], dtype=np.int64), g[f"size{ci}"])
+
+
+def test_simple_watershed_glue_pinned_against_reference():
+    """oracle.blockwise.simple_watershed against the reference's own `simple_watershed` (post/watershed.py:206-354)
+    executed on in-memory datasets around the same restated skimage / waterz pieces: fragments and one segmentation
+    per threshold; uint8 / float32 input, mask, sigma + bias, 3-D mode"""
+    import json
+    g = np.load(os.path.join(GOLD, "simple_watershed_glue.npz"))
+    meta = json.load(open(os.path.join(GOLD, "simple_watershed_glue.json")))
+    for ci, case in enumerate(meta["cases"]):
+        mask = g[f"mask{ci}"] if case["mask"] else None
+        r = ob.simple_watershed(g[f"affs{ci}"], dict(case["cfg"]), mask=mask, seed_tie="heap", stats_mode="faithful")
+        names = meta["names"][str(ci)]
+        assert names[0].startswith("frags/") and all(n.startswith("segs/") for n in names[1:])
+        assert np.array_equal(r["fragments"], g[f"out{ci}_0"])
+        thrs = sorted(r["segs"])
+        assert len(thrs) == len(names) - 1
+        for k, thr in enumerate(thrs):
+            assert f"--t{thr:g}--" in names[1 + k]
+            assert np.array_equal(r["segs"][thr], g[f"out{ci}_{1 + k}"])
