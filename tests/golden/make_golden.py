@@ -15,6 +15,7 @@ Sources executed (unmodified, loaded by path):
                                        waterz / funlib relabel replaced by the oracle's restatements)
   bootstrapper/post/blockwise/watershed_frags.py -> watershed_in_block_glue.npz (get_fragments / watershed_in_block over all blocks)
   bootstrapper/post/watershed.py    -> simple_watershed_glue.npz (simple_watershed with in-memory datasets)
+  bootstrapper/post/watershed.py    -> waterz_pipeline_glue.npz (waterz_pipeline; task stand-ins run the oracle's per-block stages)
   bootstrapper/post/naming.py       -> naming.json      (build_name; `import zarr` stubbed)
   bootstrapper/segment.py           -> seg_config.json  (DEFAULTS, get_seg_config)
 """
@@ -559,6 +560,140 @@ def golden_simple_watershed_glue():
     print("simple_watershed_glue.npz", len(out), names["1"])
 
 
+def golden_waterz_pipeline_glue():
+    """post/watershed.py `waterz_pipeline` (:8-203), the function executed as it stands in the reference file (extracted
+    by ast) with the reference's own naming.py.  The volara tasks are stand-ins that record their arguments and run the
+    oracle's (separately pinned) per-block stages; the graph store, LUT and datasets are in memory; funlib's
+    `connected_components` is the oracle's restatement.  Pins the orchestration: parameter defaults, block size and the
+    `// 8` context rule, task arguments, and stage 3 -- unscored edges skipped, float32 scores, one component array and
+    LUT per threshold, relabel -- plus the dataset / LUT names."""
+    import ast
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from bootstrapper_b200.synth import synth_affs
+    from oracle import blockwise as ob
+    from oracle.native import connected_components
+    sys.modules.setdefault("zarr", types.ModuleType("zarr"))
+    store, luts, segs, tasks = {}, {}, {}, []
+
+    class Coordinate(tuple):
+        def __new__(cls, v):
+            return super().__new__(cls, (int(x) for x in v))
+
+    class Roi:
+        def __init__(self, offset, shape):
+            self.offset, self.shape, self.dims = Coordinate(offset), Coordinate(shape), len(shape)
+
+    class DS:
+        def __init__(self, a):
+            self.a, self.shape, self.roi, self.chunk_shape = a, a.shape, Roi((0, 0, 0), a.shape[1:]), (a.shape[0], 4, 32, 28)
+
+    class Holder:
+        def __init__(self, **kw):
+            self.__dict__.update(kw)
+
+    rag = ob.Rag()
+
+    class Graph:
+        nodes = property(lambda self: list(rag.node_pos))
+
+        def edges(self, data=True):
+            return [(u, v, {"merge_score": sc}) for (u, v), sc in rag.edges.items()]
+
+    class DB(Holder):
+        def open(self, mode):
+            return self
+
+        def read_graph(self, roi, edge_attrs=None):
+            return Graph()
+
+    class LUT(Holder):
+        def save(self, arr):
+            luts[os.path.basename(self.path)] = np.array(arr)
+
+    class Task(Holder):
+        pass
+
+    def make(name):
+        return type(name, (Task,), {})
+
+    WatershedFrags, WaterzAgglom, Relabel = make("WatershedFrags"), make("WaterzAgglom"), make("Relabel")
+
+    def run_volara_task(task, blockwise):
+        tasks.append((type(task).__name__, dict(task.__dict__), blockwise))
+        affs = store[task.affs_data.store] if hasattr(task, "affs_data") else None
+        if isinstance(task, Relabel):
+            lut = luts[os.path.basename(task.lut.path)]
+            frags = store["frags:" + task.frags_data.store]
+            seg = frags.copy()
+            idx = np.searchsorted(np.sort(lut[0]), frags)
+            order = np.argsort(lut[0])
+            idx[idx >= lut.shape[1]] = 0
+            hit = lut[0][order][idx] == frags
+            seg[hit] = lut[1][order][idx[hit]]
+            segs[os.path.basename(task.seg_data.store)] = seg
+            return
+        off, shape = task.roi
+        blocks = ob.enumerate_blocks(tuple(off), tuple(shape), tuple(task.block_size), tuple(task.context))
+        if isinstance(task, WatershedFrags):
+            p = dict(ob.WS_DEFAULTS, **{k: getattr(task, k) for k in ("fragments_in_xy", "min_seed_distance", "seed_eps", "epsilon_agglomerate",
+                                                                       "sigma", "noise_eps", "bias", "filter_fragments", "remove_debris")})
+            frags = store.setdefault("frags:" + task.frags_data.store, np.zeros(tuple(shape), dtype=np.uint64))
+            for b in blocks:
+                ob.watershed_in_block(b, affs, frags, rag, p, tuple(off), tuple(task.block_size), None, "heap", "faithful")
+        else:
+            frags = store["frags:" + task.frags_data.store]
+            for b in blocks:
+                ob.agglomerate_in_block(b, affs, frags, rag, tuple(off), "faithful", True)
+
+    src_agg = open(f"{REF}/post/blockwise/waterz_agglom.py").read()
+    mf = next(n for n in ast.walk(ast.parse(src_agg)) if isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "") == "WATERZ_MERGE_FUNCTIONS")
+    mods = {
+        "funlib": types.ModuleType("funlib"), "funlib.geometry": Holder(Coordinate=Coordinate, Roi=Roi),
+        "funlib.persistence": Holder(open_ds=lambda path: DS(store[path])),
+        "funlib.segment": types.ModuleType("funlib.segment"), "funlib.segment.graphs": types.ModuleType("funlib.segment.graphs"),
+        "funlib.segment.graphs.impl": Holder(connected_components=connected_components),
+        "volara": types.ModuleType("volara"), "volara.blockwise": Holder(Relabel=Relabel),
+        "volara.datasets": Holder(Labels=Holder, Raw=Holder), "volara.dbs": Holder(SQLite=DB, PostgreSQL=DB),
+        "volara.lut": Holder(LUT=LUT), "volara.logging": Holder(set_log_basedir=lambda p: None),
+        "refpkg": types.ModuleType("refpkg"), "refpkg.post": types.ModuleType("refpkg.post"),
+        "refpkg.post.blockwise": types.ModuleType("refpkg.post.blockwise"),
+        "refpkg.post.blockwise.watershed_frags": Holder(WatershedFrags=WatershedFrags),
+        "refpkg.post.blockwise.waterz_agglom": Holder(WaterzAgglom=WaterzAgglom, WATERZ_MERGE_FUNCTIONS=ast.literal_eval(mf.value)),
+        "refpkg.blockwise": Holder(run_volara_task=run_volara_task),
+    }
+    for n in ("refpkg", "refpkg.post", "refpkg.post.blockwise"):
+        mods[n].__path__ = []
+    sys.modules.update(mods)
+    naming = load("refpkg.post.naming", f"{REF}/post/naming.py")
+    naming.dump_params = naming.dump_lut_params = lambda *a, **k: None
+    sys.modules["refpkg.post.naming"] = naming
+    src = open(f"{REF}/post/watershed.py").read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "waterz_pipeline")
+    ns = {"__package__": "refpkg.post", "__name__": "refpkg.post.watershed", "logger": types.SimpleNamespace(warning=lambda *a: None)}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "watershed.waterz_pipeline", "exec"), ns)
+    shape = (8, 64, 56)
+    store["affs.zarr/affs"] = synth_affs(shape, seed=90)
+    tmp = tempfile.mkdtemp()
+    cfg = dict(affs_dataset="affs.zarr/affs", fragments_dataset="out.zarr/frags", seg_dataset_prefix="out.zarr/segs",
+               lut_dir=os.path.join(tmp, "luts"), db={"db_file": os.path.join(tmp, "rag.db")}, blockwise=True, num_workers=3,
+               filter_fragments=0.1, remove_debris=16, thresholds=[0.2, 0.35, 0.5])          # block_shape / context left to the defaults
+    ns["waterz_pipeline"](cfg)
+    kinds = [t[0] for t in tasks]
+    assert kinds == ["WatershedFrags", "WaterzAgglom", "Relabel", "Relabel", "Relabel"], kinds
+    t0 = tasks[0][1]
+    assert tuple(t0["block_size"]) == (4, 32, 28) and tuple(t0["context"]) == (1, 4, 3) and t0["num_workers"] == 3
+    out = {"affs": store["affs.zarr/affs"], "frags": next(v for k, v in store.items() if k.startswith("frags:"))}
+    meta = dict(block_size=list(t0["block_size"]), context=list(t0["context"]), frags_name=next(k for k in store if k.startswith("frags:"))[6:],
+                names=sorted(luts), cfg={k: v for k, v in cfg.items() if k in ("filter_fragments", "remove_debris", "thresholds")})
+    assert sorted(luts) == sorted(segs)
+    for k, name in enumerate(sorted(luts)):
+        out[f"lut{k}"], out[f"seg{k}"] = luts[name], segs[name]
+    np.savez_compressed(os.path.join(OUT, "waterz_pipeline_glue.npz"), **out)
+    with open(os.path.join(OUT, "waterz_pipeline_glue.json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    print("waterz_pipeline_glue.npz", len(out), meta["frags_name"], meta["names"])
+
+
 def golden_naming():
     sys.modules.setdefault("zarr", types.ModuleType("zarr"))       # naming.py only uses zarr in dump_params
     nm = load("ref_naming", f"{REF}/post/naming.py")
@@ -643,6 +778,7 @@ if __name__ == "__main__":
     golden_agglomerate_glue()
     golden_watershed_in_block_glue()
     golden_simple_watershed_glue()
+    golden_waterz_pipeline_glue()
     golden_naming()
     golden_config()
     print("golden fixtures written to", OUT)

@@ -353,3 +353,22 @@ def test_simple_watershed_glue_pinned_against_reference():
         for k, thr in enumerate(thrs):
             assert f"--t{thr:g}--" in names[1 + k]
             assert np.array_equal(r["segs"][thr], g[f"out{ci}_{1 + k}"])
+
+
+def test_waterz_pipeline_glue_pinned_against_reference():
+    """oracle.blockwise.waterz_pipeline against the reference's own `waterz_pipeline` (post/watershed.py:8-203) executed
+    with task stand-ins: block size / `// 8` context defaults, fragments, and stage 3 (LUT + segmentation per threshold)"""
+    import json
+    g = np.load(os.path.join(GOLD, "waterz_pipeline_glue.npz"))
+    meta = json.load(open(os.path.join(GOLD, "waterz_pipeline_glue.json")))
+    r = ob.waterz_pipeline(g["affs"], dict(meta["cfg"]), block_size=tuple(meta["block_size"]), context=None,
+                           seed_tie="heap", stats_mode="faithful")
+    assert [tuple(meta["context"])] == [tuple(max(1, s // 8) for s in meta["block_size"])]
+    assert np.array_equal(r["fragments"], g["frags"])
+    thrs = sorted(r["segs"])
+    assert len(thrs) == len(meta["names"])
+    for k, thr in enumerate(thrs):
+        assert f"--t{thr:g}--" in meta["names"][k]
+        assert np.array_equal(r["segs"][thr]["seg"], g[f"seg{k}"])
+        ref_lut, lut = g[f"lut{k}"], r["segs"][thr]["lut"]
+        assert dict(zip(ref_lut[0].tolist(), ref_lut[1].tolist())) == dict(zip(lut[0].tolist(), lut[1].tolist()))
