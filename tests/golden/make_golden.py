@@ -16,6 +16,7 @@ Sources executed (unmodified, loaded by path):
   bootstrapper/post/blockwise/watershed_frags.py -> watershed_in_block_glue.npz (get_fragments / watershed_in_block over all blocks)
   bootstrapper/post/watershed.py    -> simple_watershed_glue.npz (simple_watershed with in-memory datasets)
   bootstrapper/post/watershed.py    -> waterz_pipeline_glue.npz (waterz_pipeline; task stand-ins run the oracle's per-block stages)
+  bootstrapper/post/connected_components.py -> cc_affs_func.npz (cc_affs with in-memory datasets)
   bootstrapper/post/naming.py       -> naming.json      (build_name; `import zarr` stubbed)
   bootstrapper/segment.py           -> seg_config.json  (DEFAULTS, get_seg_config)
 """
@@ -694,6 +695,81 @@ def golden_waterz_pipeline_glue():
     print("waterz_pipeline_glue.npz", len(out), meta["frags_name"], meta["names"])
 
 
+def golden_cc_affs_func():
+    """post/connected_components.py `cc_affs` (:12-119), the function executed as it stands in the reference file
+    (extracted by ast) with the reference's own cc.py and naming.py; funlib's open_ds / prepare_ds / Roi are in-memory
+    stand-ins, skimage's remove_small_objects the oracle's restatement.  Covers mask, sigma and remove_debris."""
+    import ast
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from bootstrapper_b200.synth import synth_affs
+    from oracle import cc as occ
+    sys.modules.setdefault("zarr", types.ModuleType("zarr"))
+    store, written = {}, {}
+
+    class Roi:
+        def __init__(self, offset, shape):
+            self.offset, self.shape = tuple(offset), tuple(shape)
+
+        def sl(self):
+            return tuple(slice(o, o + s) for o, s in zip(self.offset, self.shape))
+
+    class DS:
+        def __init__(self, a, name=None):
+            self.a, self.name, self.shape = a, name, a.shape
+            self.roi = Roi((0, 0, 0), a.shape[-3:])
+            self.voxel_size, self.axis_names, self.units = (1, 1, 1), ["c^", "z", "y", "x"][-a.ndim:], ["nm"] * 3
+
+        def __getitem__(self, roi):
+            return self.a[(Ellipsis,) + roi.sl()]
+
+        def __setitem__(self, roi, data):
+            self.a[roi.sl()] = data
+            written[self.name] = self.a
+
+    holder = lambda **kw: types.SimpleNamespace(**kw)  # noqa: E731
+    pkg = types.ModuleType("refcc")
+    pkg.__path__ = []
+    sys.modules.update({
+        "funlib": types.ModuleType("funlib"), "funlib.geometry": holder(Roi=Roi),
+        "funlib.persistence": holder(open_ds=lambda path: DS(store[path]),
+                                     prepare_ds=lambda name, shape, offset, voxel_size, axis_names, dtype, units: DS(np.zeros(shape, dtype=dtype), name)),
+        "skimage": sys.modules.get("skimage") or types.ModuleType("skimage"),
+        "skimage.morphology": holder(remove_small_objects=lambda x, min_size: occ.remove_small_objects(x, min_size)),
+        "refcc": pkg})
+    naming = load("refcc.naming", f"{REF}/post/naming.py")
+    naming.dump_params = lambda *a, **k: None
+    sys.modules["refcc.naming"] = naming
+    sys.modules["refcc.cc"] = load("refcc.cc", f"{REF}/post/cc.py")
+    src = open(f"{REF}/post/connected_components.py").read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "cc_affs")
+    ns = {"__package__": "refcc", "__name__": "refcc.connected_components"}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "connected_components.cc_affs", "exec"), ns)
+    out, names = {}, {}
+    cases = [dict(dtype="uint8", mask=False, cfg={"threshold": 0.5}),
+             dict(dtype="uint8", mask=True, cfg={"threshold": 0.7, "sigma": [0, 1.0, 1.5], "remove_debris": 40}),
+             dict(dtype="float32", mask=True, cfg={"threshold": 0.4, "remove_debris": 12})]
+    for ci, case in enumerate(cases):
+        shape = (5, 44, 40)
+        a8 = synth_affs(shape, seed=95 + ci)
+        store["affs"] = a8 if case["dtype"] == "uint8" else (a8.astype(np.float32) / np.float32(255))
+        cfg = dict(affs_dataset="affs", fragments_dataset="frags", seg_dataset_prefix="segs", **case["cfg"])
+        if case["mask"]:
+            m = np.ones(shape, dtype=np.uint8)
+            m[:, :9, 30:] = 0
+            store["mask"] = m
+            cfg["mask_dataset"] = "mask"
+            out[f"mask{ci}"] = m
+        written.clear()
+        ns["cc_affs"](cfg)
+        names[str(ci)] = sorted(written)
+        assert len(written) == 2 and names[str(ci)][0].startswith("frags/")
+        out[f"affs{ci}"], out[f"frags{ci}"], out[f"seg{ci}"] = store["affs"], written[names[str(ci)][0]].copy(), written[names[str(ci)][1]].copy()
+    np.savez_compressed(os.path.join(OUT, "cc_affs_func.npz"), **out)
+    with open(os.path.join(OUT, "cc_affs_func.json"), "w") as f:
+        json.dump(dict(cases=cases, names=names), f, indent=1)
+    print("cc_affs_func.npz", len(out), names["1"])
+
+
 def golden_naming():
     sys.modules.setdefault("zarr", types.ModuleType("zarr"))       # naming.py only uses zarr in dump_params
     nm = load("ref_naming", f"{REF}/post/naming.py")
@@ -779,6 +855,7 @@ if __name__ == "__main__":
     golden_watershed_in_block_glue()
     golden_simple_watershed_glue()
     golden_waterz_pipeline_glue()
+    golden_cc_affs_func()
     golden_naming()
     golden_config()
     print("golden fixtures written to", OUT)

@@ -372,3 +372,18 @@ def test_waterz_pipeline_glue_pinned_against_reference():
         assert np.array_equal(r["segs"][thr]["seg"], g[f"seg{k}"])
         ref_lut, lut = g[f"lut{k}"], r["segs"][thr]["lut"]
         assert dict(zip(ref_lut[0].tolist(), ref_lut[1].tolist())) == dict(zip(lut[0].tolist(), lut[1].tolist()))
+
+
+def test_cc_affs_function_pinned_against_reference():
+    """oracle.cc.cc_affs against the reference's own `cc_affs` (post/connected_components.py:12-119) executed on in-memory
+    datasets with the reference's cc.py: fragments and the remove_debris segmentation; mask, sigma"""
+    import json
+    from oracle import cc as occ
+    g = np.load(os.path.join(GOLD, "cc_affs_func.npz"))
+    meta = json.load(open(os.path.join(GOLD, "cc_affs_func.json")))
+    for ci, case in enumerate(meta["cases"]):
+        cfg = case["cfg"]
+        mask = g[f"mask{ci}"] if case["mask"] else None
+        frags, seg = occ.cc_affs(g[f"affs{ci}"], cfg["threshold"], cfg.get("remove_debris", 0), mask, cfg.get("sigma"))
+        assert np.array_equal(frags, g[f"frags{ci}"]) and np.array_equal(seg, g[f"seg{ci}"])
+        assert frags.any() and (cfg.get("remove_debris", 0) == 0 or not np.array_equal(frags, seg))
