@@ -3,7 +3,9 @@
 Follows bootstrapper/refine.py: `_global_sizes` :98-108, `outlier_filter` :147-172, `size_filter` :190-213, `z_filter`
 :229-258, `_mask_block` :111-116, `remap` / `_remap_block` :265-307.  The reference calls fastremap (unique / mask /
 remap; absent here, unpinned dependency) on zarr tiles; their documented behaviour is restated with numpy
-[3P-recall]: **parity unpinned** (the decision arithmetic itself is the reference's numpy, line by line)."""
+[3P-recall].  The decision arithmetic is PINNED: `_global_sizes` (over z tiles), the three filters and the remap table
+are checked against the reference's own functions executed on an in-memory array
+(tests/golden/refine_filters.npz); only fastremap's mask / remap of the rewrite stay recalled."""
 import numpy as np
 
 

@@ -17,6 +17,7 @@ Sources executed (unmodified, loaded by path):
   bootstrapper/post/watershed.py    -> simple_watershed_glue.npz (simple_watershed with in-memory datasets)
   bootstrapper/post/watershed.py    -> waterz_pipeline_glue.npz (waterz_pipeline; task stand-ins run the oracle's per-block stages)
   bootstrapper/post/connected_components.py -> cc_affs_func.npz (cc_affs with in-memory datasets)
+  bootstrapper/refine.py            -> refine_filters.npz (_global_sizes and the outlier / size / z filters, remap)
   bootstrapper/post/naming.py       -> naming.json      (build_name; `import zarr` stubbed)
   bootstrapper/segment.py           -> seg_config.json  (DEFAULTS, get_seg_config)
 """
@@ -770,6 +771,89 @@ def golden_cc_affs_func():
     print("cc_affs_func.npz", len(out), names["1"])
 
 
+def golden_refine_filters():
+    """refine.py `_scan_tiles`, `_global_sizes`, `outlier_filter`, `size_filter`, `z_filter`, `remap` (:79-108, :147-307),
+    the functions executed as they stand in the reference file (extracted by ast, click decorators dropped); the zarr
+    array is an in-memory stand-in, fastremap.unique is numpy's, the blockwise rewrite is replaced by a recorder of the
+    ids to remove / the id mapping.  Pins the decision arithmetic of the filters (sizes over z tiles, mean / std cut,
+    ranges, z extents, remap table)."""
+    import ast
+    import contextlib
+    import io
+    import click
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from bootstrapper_b200.synth import synth_affs
+    from oracle.ws import watershed_from_affinities
+
+    class Coordinate(tuple):
+        def __new__(cls, *v):
+            v = v[0] if len(v) == 1 else v
+            return super().__new__(cls, (int(x) for x in v))
+
+        def __mul__(self, o):
+            return Coordinate(a * b for a, b in zip(self, o))
+
+        def __add__(self, o):
+            return Coordinate(a + b for a, b in zip(self, o))
+
+        __radd__ = __add__
+
+    class Roi:
+        def __init__(self, offset, shape):
+            self.offset, self.shape = Coordinate(offset), Coordinate(shape)
+
+    class DS:
+        def __init__(self, a):
+            self.a, self.shape, self.dtype = a, a.shape, a.dtype
+            self.roi, self.voxel_size, self.chunk_shape = Roi((0, 0, 0), a.shape), Coordinate(1, 1, 1), (2, 16, 16)
+
+        def to_ndarray(self, roi):
+            return self.a[tuple(slice(o, o + s) for o, s in zip(roi.offset, roi.shape))]
+
+    seen = {}
+
+    def finish(in_ds, in_array, out_array, remove_ids, num_workers, dry_run, suffix, name):
+        seen[name] = np.array(remove_ids)
+
+    def run_blockwise(name, in_ds, out_ds, process_block, num_workers, **kw):
+        seen[name] = process_block.args[2]
+
+    fastremap = types.SimpleNamespace(unique=lambda a, return_counts=False: np.unique(a, return_counts=return_counts))
+    src = open(f"{REF}/refine.py").read()
+    wanted = ("_scan_tiles", "_global_sizes", "outlier_filter", "size_filter", "z_filter", "remap", "_remap_block")
+    fns = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    for f in fns:
+        f.decorator_list = []
+    vol = {}
+    ns = {"np": np, "click": click, "Roi": Roi, "Coordinate": Coordinate, "fastremap": fastremap, "partial": __import__("functools").partial,
+          "open_ds": lambda path: DS(vol["seg"]), "_finish_filter": finish, "_run_blockwise": run_blockwise,
+          "_default_out": lambda a, sfx: a + "_" + sfx, "_prepare_like": lambda in_ds, out: None}
+    exec(compile(ast.fix_missing_locations(ast.Module(body=fns, type_ignores=[])), "refine", "exec"), ns)
+    a8 = synth_affs((9, 72, 64), seed=99)
+    frags, _ = watershed_from_affinities(a8.astype(np.float64) / 255, fragments_in_xy=False, seed_tie="index", min_seed_distance=6)
+    frags[frags > 0] += np.uint64(5000)
+    frags[4:, :, :20][frags[4:, :, :20] % 3 == 0] = 0          # uneven sizes and z extents
+    vol["seg"] = frags
+    out = {"seg": frags}
+    with contextlib.redirect_stdout(io.StringIO()):
+        ns["outlier_filter"]("seg", None, 1.0, 20, 1, False)
+        ns["size_filter"]("seg", None, 60, 900, 1, False)
+        ns["z_filter"]("seg", None, 2, 1, False)
+        ids = np.unique(frags[frags > 0])
+        rm, grp = [int(ids[1])], [[int(ids[2]), int(ids[5]), int(ids[7])], [int(ids[9]), int(ids[3])]]
+        ns["remap"]("seg", None, ",".join(map(str, rm)), tuple(",".join(map(str, g)) for g in grp), 1)
+    out["outlier"], out["size"], out["z"] = np.sort(seen["OutlierFilter"]), np.sort(seen["SizeFilter"]), np.sort(seen["ZFilter"])
+    mapping = seen["Remap"]
+    out["remap_keys"] = np.array(sorted(mapping), dtype=np.uint64)
+    out["remap_vals"] = np.array([mapping[k] for k in sorted(mapping)], dtype=np.uint64)
+    out["remap_remove"], out["remap_groups"] = np.array(rm, dtype=np.uint64), np.array([g + [0] * (3 - len(g)) for g in grp], dtype=np.uint64)
+    uniq, sizes = ns["_global_sizes"](DS(frags))
+    out["uniq"], out["sizes"] = uniq, sizes
+    assert 0 < out["outlier"].size < uniq.size and 0 < out["size"].size < uniq.size and 0 < out["z"].size < uniq.size
+    np.savez_compressed(os.path.join(OUT, "refine_filters.npz"), **out)
+    print("refine_filters.npz", {k: v.shape for k, v in out.items() if k != "seg"})
+
+
 def golden_naming():
     sys.modules.setdefault("zarr", types.ModuleType("zarr"))       # naming.py only uses zarr in dump_params
     nm = load("ref_naming", f"{REF}/post/naming.py")
@@ -856,6 +940,7 @@ if __name__ == "__main__":
     golden_simple_watershed_glue()
     golden_waterz_pipeline_glue()
     golden_cc_affs_func()
+    golden_refine_filters()
     golden_naming()
     golden_config()
     print("golden fixtures written to", OUT)

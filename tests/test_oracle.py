@@ -387,3 +387,26 @@ def test_cc_affs_function_pinned_against_reference():
         frags, seg = occ.cc_affs(g[f"affs{ci}"], cfg["threshold"], cfg.get("remove_debris", 0), mask, cfg.get("sigma"))
         assert np.array_equal(frags, g[f"frags{ci}"]) and np.array_equal(seg, g[f"seg{ci}"])
         assert frags.any() and (cfg.get("remove_debris", 0) == 0 or not np.array_equal(frags, seg))
+
+
+def test_refine_filters_pinned_against_reference():
+    """oracle/refine.py against the reference's own refine.py functions (`_global_sizes` over z tiles, outlier / size / z
+    filters, remap table) executed on an in-memory array (tests/golden/make_golden.py::golden_refine_filters)"""
+    from oracle import refine as orf
+    g = np.load(os.path.join(GOLD, "refine_filters.npz"))
+    seg = g["seg"]
+    uniq, sizes = orf.global_sizes(seg)
+    assert np.array_equal(uniq, g["uniq"]) and np.array_equal(sizes, g["sizes"])
+    assert np.array_equal(np.sort(orf.outlier_filter(seg, 1.0, 20)[1]), g["outlier"])
+    assert np.array_equal(np.sort(orf.size_filter(seg, 60, 900)[1]), g["size"])
+    assert np.array_equal(np.sort(orf.z_filter(seg, 2)[1]), g["z"])
+    # the remap table the host mirror builds (bootstrapper_b200/refine.py::remap follows refine.py:281-300)
+    remove = {int(x) for x in g["remap_remove"]}
+    merge = {}
+    for grp in g["remap_groups"]:
+        ids = [int(x) for x in grp if x]
+        for mid in ids:
+            merge[mid] = ids[0]
+    mapping = {i: 0 for i in remove} | merge
+    assert sorted(mapping) == [int(k) for k in g["remap_keys"]]
+    assert [mapping[int(k)] for k in g["remap_keys"]] == [int(v) for v in g["remap_vals"]]
