@@ -18,6 +18,7 @@ Sources executed (unmodified, loaded by path):
   bootstrapper/post/watershed.py    -> waterz_pipeline_glue.npz (waterz_pipeline; task stand-ins run the oracle's per-block stages)
   bootstrapper/post/connected_components.py -> cc_affs_func.npz (cc_affs with in-memory datasets)
   bootstrapper/refine.py            -> refine_filters.npz (_global_sizes and the outlier / size / z filters, remap)
+  bootstrapper/blockwise.py         -> task_states.json (check_task_states messages)
   bootstrapper/post/naming.py       -> naming.json      (build_name; `import zarr` stubbed)
   bootstrapper/segment.py           -> seg_config.json  (DEFAULTS, get_seg_config)
 """
@@ -854,6 +855,35 @@ def golden_refine_filters():
     print("refine_filters.npz", {k: v.shape for k, v in out.items() if k != "seg"})
 
 
+TASK_STATE_CASES = [
+    {"a": (4, 0, 0)},
+    {"a": (4, 0, 0), "b": (4, 2, 0)},
+    {"frags": (125, 3, 1), "agglom": (125, 0, 0), "relabel": (64, 0, 7)},
+]
+
+
+def golden_task_states():
+    """blockwise.py `check_task_states` (:11-22), the function executed as it stands (extracted by ast: the module
+    imports daisy): the RuntimeError message for failed / orphaned blocks."""
+    import ast
+    src = open(f"{REF}/blockwise.py").read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "check_task_states")
+    ns = {}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "blockwise.check_task_states", "exec"), ns)
+    out = []
+    for case in TASK_STATE_CASES:
+        states = {k: types.SimpleNamespace(total_block_count=t, failed_count=f, orphaned_count=o) for k, (t, f, o) in case.items()}
+        try:
+            ns["check_task_states"](states)
+            msg = None
+        except RuntimeError as e:
+            msg = str(e)
+        out.append(dict(states=case, message=msg))
+    with open(os.path.join(OUT, "task_states.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("task_states.json", [o["message"] for o in out])
+
+
 def golden_naming():
     sys.modules.setdefault("zarr", types.ModuleType("zarr"))       # naming.py only uses zarr in dump_params
     nm = load("ref_naming", f"{REF}/post/naming.py")
@@ -941,6 +971,7 @@ if __name__ == "__main__":
     golden_waterz_pipeline_glue()
     golden_cc_affs_func()
     golden_refine_filters()
+    golden_task_states()
     golden_naming()
     golden_config()
     print("golden fixtures written to", OUT)
