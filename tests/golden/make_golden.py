@@ -37,8 +37,11 @@ os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
 
 
 def load(name, path):
+    if name in sys.modules and getattr(sys.modules[name], "__file__", None) == path:
+        return sys.modules[name]
     spec = importlib.util.spec_from_file_location(name, path)
     mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod                 # numba's on-disk cache re-imports the defining module by name
     spec.loader.exec_module(mod)
     return mod
 
@@ -741,7 +744,7 @@ def golden_cc_affs_func():
     naming = load("refcc.naming", f"{REF}/post/naming.py")
     naming.dump_params = lambda *a, **k: None
     sys.modules["refcc.naming"] = naming
-    sys.modules["refcc.cc"] = load("refcc.cc", f"{REF}/post/cc.py")
+    sys.modules["refcc.cc"] = load("ref_cc", f"{REF}/post/cc.py")          # one module name per file (numba cache)
     src = open(f"{REF}/post/connected_components.py").read()
     fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "cc_affs")
     ns = {"__package__": "refcc", "__name__": "refcc.connected_components"}
