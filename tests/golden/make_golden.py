@@ -19,6 +19,7 @@ Sources executed (unmodified, loaded by path):
   bootstrapper/post/connected_components.py -> cc_affs_func.npz (cc_affs with in-memory datasets)
   bootstrapper/refine.py            -> refine_filters.npz (_global_sizes and the outlier / size / z filters, remap)
   bootstrapper/blockwise.py         -> task_states.json (check_task_states messages)
+  bootstrapper/post/blockwise/*.py  -> task_fields.json (field names / defaults / methods of the two task classes)
   bootstrapper/post/naming.py       -> naming.json      (build_name; `import zarr` stubbed)
   bootstrapper/segment.py           -> seg_config.json  (DEFAULTS, get_seg_config)
 """
@@ -887,6 +888,29 @@ def golden_task_states():
     print("task_states.json", [o["message"] for o in out])
 
 
+def golden_task_fields():
+    """field names, defaults and task_type of the two volara task classes (post/blockwise/watershed_frags.py:30-62,
+    waterz_agglom.py:39-75), read from the class bodies by ast (the modules need volara / pydantic models to import)."""
+    import ast
+    out = {}
+    for fname, cname in (("watershed_frags.py", "WatershedFrags"), ("waterz_agglom.py", "WaterzAgglom")):
+        tree = ast.parse(open(f"{REF}/post/blockwise/{fname}").read())
+        cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cname)
+        fields = {}
+        for n in cls.body:
+            if isinstance(n, ast.AnnAssign) and isinstance(n.target, ast.Name):
+                try:
+                    default = ast.literal_eval(n.value) if n.value is not None else "<required>"
+                except ValueError:
+                    default = "<expr>"
+                fields[n.target.id] = default
+        props = [n.name for n in cls.body if isinstance(n, ast.FunctionDef)]
+        out[cname] = dict(fields=fields, methods=props)
+    with open(os.path.join(OUT, "task_fields.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("task_fields.json", {k: len(v["fields"]) for k, v in out.items()})
+
+
 def golden_naming():
     sys.modules.setdefault("zarr", types.ModuleType("zarr"))       # naming.py only uses zarr in dump_params
     nm = load("ref_naming", f"{REF}/post/naming.py")
@@ -975,6 +999,7 @@ if __name__ == "__main__":
     golden_cc_affs_func()
     golden_refine_filters()
     golden_task_states()
+    golden_task_fields()
     golden_naming()
     golden_config()
     print("golden fixtures written to", OUT)
