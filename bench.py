@@ -43,6 +43,15 @@ THRESHOLDS = [0.2, 0.35, 0.5]
 BYTES_PER_VOXEL = 3 * 1 + 8 + 8 * len(THRESHOLDS)      # u8 affs in, u64 fragments + T u64 segmentations out
 CPU_SAMPLE = (100, 1000, 1000)                         # 64 blocks of the same geometry (~15 s of CPU work on 16 cores)
 METRIC = "voxels/sec affs->segmentation (blockwise ws, fragments + RAG + agglomeration at 3 thresholds)"
+PARITY_NOTE = ("bit-exact vs the CPU oracle (fragments incl. ids, nodes, RAG edges, f32 merge scores, LUTs, segmentations): "
+               "tests/test_gpu_fullsize.py runs this workload at full size; parity unpinned for the third-party cores the oracle "
+               "restates, declared deviations D1-D3 (DESIGN.md 4; D1 census profiles/r02_d1_census.json)")
+
+
+def workload_string(config, shape, world, slab, block, context):
+    return (f"{'CREMI-sized ' if config == 2 else ''}synthetic uint8 affinities 3x{tuple(shape)} ({world} z-slab(s) of {tuple(slab)}), "
+            f"block {tuple(block)}, context {tuple(context)}, "
+            f"{'ws defaults' if config != 4 else 'fragments_in_xy=false, seed_eps=0.01'}, thresholds [0.2,0.35,0.5]")
 
 
 class ClockSampler:
@@ -98,223 +107,338 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def sample_affs(shape, seed):
-    """the synthetic input of the CPU leg: the device generator (bit-identical to the numpy one, ~1000x faster) when a
-    GPU is present -- input generation is outside every timed region"""
-    try:
+def sample_affs(shape, seed, in_process=True):
+    """the synthetic input of a CPU leg (generation is outside every timed region).  in_process=False (the reference arm):
+    a CHILD process runs the device generator and leaves the array under /dev/shm, so that the process that times the CPU
+    implementation never maps libbsnative.so; without a GPU the numpy generator (bit-identical) runs on all cores."""
+    if in_process:
         import torch
-        if torch.cuda.is_available():
-            from bootstrapper_b200 import native
-            return native.synth_affs(shape, seed=seed).cpu().numpy()
-    except Exception:  # noqa: BLE001
-        pass
-    from bootstrapper_b200.synth import synth_affs
-    return synth_affs(shape, seed=seed)
+        from bootstrapper_b200 import native
+        return native.synth_affs(shape, seed=seed).cpu().numpy()
+    cache = f"/dev/shm/bs_bench_affs_{'x'.join(str(v) for v in shape)}_s{seed}.npy"
+    if not os.path.exists(cache):
+        code = ("import sys, numpy as np, torch\n"
+                f"sys.path.insert(0, {ROOT!r})\n"
+                "assert torch.cuda.is_available()\n"
+                "from bootstrapper_b200 import native\n"
+                f"np.save({cache!r} + '.tmp.npy', native.synth_affs({tuple(shape)!r}, seed={seed}).cpu().numpy())\n")
+        rc = subprocess.run([sys.executable, "-c", code], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL).returncode
+        if rc == 0:
+            os.replace(cache + ".tmp.npy", cache)
+        else:
+            import multiprocessing as mp
+            from bootstrapper_b200.synth import synth_affs
+            out = np.empty((3,) + tuple(shape), np.uint8)
+            jobs = [(z, min(5, shape[0] - z)) for z in range(0, shape[0], 5)]
+            with mp.get_context("fork").Pool(os.cpu_count()) as pool:
+                for z, a in zip(jobs, pool.starmap(synth_affs, [((n, shape[1], shape[2]), seed, np.uint8, (z0, 0, 0), tuple(shape))
+                                                               for z0, n in jobs])):
+                    out[:, z[0]:z[0] + z[1]] = a
+            np.save(cache, out)
+            return out
+    return np.load(cache)
 
 
-def cpu_oracle_rate(sample_shape, workers=None, seed=0):
-    """voxels/s of the CPU oracle (one process per block) on a bounded sample of the workload"""
+def cpu_oracle_run(affs, workers=None):
+    """the CPU oracle (one process per block) on `affs`; returns (voxels/s, timings, result)"""
     from oracle.parallel import waterz_pipeline_parallel
-    affs = sample_affs(sample_shape, seed)
     tm = {}
-    waterz_pipeline_parallel(affs, {"thresholds": THRESHOLDS}, block_size=BLOCK, context=CONTEXT, timings=tm, workers=workers)
-    return float(np.prod(sample_shape)) / tm["total"], tm
+    ref = waterz_pipeline_parallel(affs, {"thresholds": THRESHOLDS}, block_size=BLOCK, context=CONTEXT, timings=tm, workers=workers)
+    return float(np.prod(affs.shape[1:])) / tm["total"], tm, ref
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path = the oracle port (kind 'port')."""
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (kind 'port'; the reference itself
+    is pure Python over third-party packages that are not in the image), one process per block on all host
+    cores, on the SAME volume as the GPU arm's N=1 workload.  Each step is one pass over the whole volume; the number of
+    timed passes is bounded so that the run ends within a few minutes (steps_run says how many)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count()
-    sample = (50, 500, 500) if args.quick else CPU_SAMPLE
-    for _ in range(1 if args.warmup > 0 else 0):
-        cpu_oracle_rate((25, 250, 250), cores)
+    shape = (50, 500, 500) if args.quick else SHAPE
+    affs = sample_affs(shape, 0, in_process=False)
+    if args.warmup > 0:
+        cpu_oracle_run(np.ascontiguousarray(affs[:, :25, :250, :250]), cores)
     rates, ms = [], []
+    t_start = time.time()
     for _ in range(max(1, args.steps)):
-        r, tm = cpu_oracle_rate(sample, cores)
+        r, tm, _ref = cpu_oracle_run(affs, cores)
         rates.append(r)
         ms.append(tm["total"] * 1e3)
+        if time.time() - t_start + tm["total"] > 150.0:
+            break
     v = float(np.mean(rates))
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak",
+        "steps_run": len(rates), "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "CREMI-sized synthetic uint8 affinities 3x(125,1250,1250), block (25,250,250), context (3,31,31), "
-                               "ws defaults, thresholds [0.2,0.35,0.5]", "l2": "inputs larger than L2"},
+        "config": {"workload": workload_string(2, shape, 1, shape, BLOCK, CONTEXT), "l2": "inputs larger than L2"},
         "cpu_baseline": {"value": v, "unit": "voxels/s", "cores": cores, "kind": "port",
-                         "sample": f"sub-volume {sample} of the workload ({int(np.prod(sample) / np.prod(BLOCK))} blocks, same "
-                                   "block geometry), one process per block"},
+                         "sample": f"the whole volume {tuple(shape)} ({int(np.prod(shape) / np.prod(BLOCK))} blocks), one process per block, "
+                                   f"{len(rates)} timed pass(es) of {np.mean(ms) / 1e3:.1f} s"},
         "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args):
+def compare_with_oracle(r, ref):
+    """GPU result dict (segment_blockwise / ShardedSegmenter.run layout) vs an oracle result: what matches, bit for bit"""
+    f = r["fragments"].cpu().numpy().view(np.uint64)
+    ok_f = bool(np.array_equal(f, ref["fragments"]))
+    eu, ev, es = [t.cpu().numpy() for t in r["edges"]]
+    got = np.stack([eu.view(np.uint64), ev.view(np.uint64)], 1)
+    order = np.lexsort((got[:, 1], got[:, 0]))
+    got, gs = got[order], es[order]
+    keys = sorted(ref["rag"].edges)
+    want = np.array(keys, dtype=np.uint64).reshape(-1, 2)
+    ok_e = bool(np.array_equal(got, want))
+    ok_s = False
+    if ok_e:
+        ws = np.array([np.nan if ref["rag"].edges[k] is None else ref["rag"].edges[k] for k in keys], dtype=np.float64)
+        nan = np.isnan(ws)
+        ok_s = bool(np.array_equal(np.isnan(gs), nan) and np.all(np.abs(gs[~nan] - ws[~nan]) <= 1e-6 * np.abs(ws[~nan])))
+    ok_g = all(bool(np.array_equal(seg.cpu().numpy().view(np.uint64), ref["segs"][thr]["seg"])) for thr, seg in r["segs"].items())
+    return {"fragments": ok_f, "edges": ok_e, "scores_1e-6": ok_s, "segs": ok_g,
+            "n_fragments": int(len(ref["rag"].node_pos)), "n_edges": int(len(keys))}
+
+
+CONFIGS = {2: (SHAPE, BLOCK, CONTEXT, {}), 4: (SHAPE4, BLOCK4, CONTEXT4, PARAMS4), 5: (SHAPE5, BLOCK5, CONTEXT5, {})}
+
+
+class Job:
+    """process-wide state of one bench run: ranks, device, collectives"""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            # pinned host buffers of the host-buffer leg should live on the NUMA node next to this rank's GPU
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(self.local_rank))
+            except Exception:  # noqa: BLE001
+                pass
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([float(x)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def time_workload(job, config, steps, warmup, quick=False, clocks=False):
+    """device-timed steps of one configuration on all ranks (CUDA events on the launching stream, barrier + synchronize
+    on both sides, max over ranks).  Returns the segmenter, its resident inputs / outputs and the measurements."""
     import torch
-    import torch.distributed as dist
     from bootstrapper_b200 import native
     from bootstrapper_b200.sharded import ShardedSegmenter
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        # pinned host buffers of the host-buffer leg should live on the NUMA node next to this rank's GPU
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
-        except Exception:  # noqa: BLE001
-            pass
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    slab, block, context = {5: (SHAPE5, BLOCK5, CONTEXT5), 4: (SHAPE4, BLOCK4, CONTEXT4)}.get(args.config, (SHAPE, BLOCK, CONTEXT))
-    shape = (slab[0] * world, slab[1], slab[2]) if not args.quick else (50 * world, 500, 500)
-    params = {"thresholds": THRESHOLDS}
-    if args.config == 4:
-        params.update(PARAMS4)
-    seg = ShardedSegmenter(shape, block, context, params, rank=rank, world=world, device=dev)
+    slab, block, context, extra = CONFIGS[config]
+    shape = (slab[0] * job.world, slab[1], slab[2]) if not quick else (50 * job.world, 500, 500)
+    params = dict({"thresholds": THRESHOLDS}, **extra)
+    seg = ShardedSegmenter(shape, block, context, params, rank=job.rank, world=job.world, device=job.dev)
     affs = seg.synth_local_affs(seed=0)                    # this rank's slab + z halo, generated on the device
     torch.cuda.synchronize()
-    V_total = float(np.prod(shape))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     native.set_profiling(True)
     # the segmentations land in caller-provided buffers (as the C ABI has it), allocated once
-    out = [torch.empty(seg.own_shape, dtype=torch.int64, device=dev) for _ in THRESHOLDS]
-    for _ in range(args.warmup):
+    out = [torch.empty(seg.own_shape, dtype=torch.int64, device=job.dev) for _ in THRESHOLDS]
+    for _ in range(warmup):
         seg.run(affs, out=out)
-    barrier()
+    job.barrier()
     l0 = native.launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(job.local_rank) if clocks and job.rank == 0 else None
+    if sampler:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     prof_acc = {}
-    barrier()
+    job.barrier()
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         seg.run(affs, out=out)
         for k, v in seg.last_profile.items():
             prof_acc[k] = prof_acc.get(k, 0.0) + v
     ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = native.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    value = V_total / (ms_step * 1e-3)
-
-    # ---- end to end through the public API with host buffers (pinned), copies inside the timed region
-    if args.config != 2:   # (69 GB of outputs per rank for config 5) the host-buffer leg is measured on the default workload only
-        args.no_e2e = True
-    if args.no_e2e:
-        e2e_ms, h2d, d2h, e2e_stream = None, 0, 0, False
-    else:
-        e2e_ms, h2d, d2h, e2e_stream = run_e2e(args, seg, affs, barrier, dev, world, out)
-
-    if rank == 0:
-        report(args, seg, shape, slab, block, context, world, ms_step, value, V_total, prof_acc, launches, clocks, e2e_ms, h2d, d2h, e2e_stream)
-    if world > 1:
-        dist.destroy_process_group()
+    job.barrier()
+    ms_step = job.max_over_ranks(ev0.elapsed_time(ev1)) / steps
+    res = dict(config=config, shape=shape, slab=slab if not quick else (50, 500, 500), block=block, context=context, seg=seg, affs=affs,
+               out=out, ms_step=ms_step, value=float(np.prod(shape)) / (ms_step * 1e-3),
+               stage_ms={k: v / steps for k, v in prof_acc.items()}, launches=int(native.launch_count() - l0),
+               clocks=sampler.stop() if sampler else None)
+    return res
 
 
-def run_e2e(args, seg, affs, barrier, dev, world, out):
-    """host-buffer leg through ShardedSegmenter.run_host in its streaming form: every step uploads the step's
-    affinities from pinned memory and downloads fragments + all segmentations into pinned memory; the downloads of
-    step k overlap the upload and compute of step k + 1 (two buffer sets); the timed region ends when the last
-    download is through."""
-    import torch
-    import torch.distributed as dist
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    host_affs = torch.empty(affs.shape, dtype=affs.dtype, pin_memory=True)
-    host_affs.copy_(affs)
-    own_shape = seg.own_shape
-    n_out = 1 + len(THRESHOLDS)
-    host_sets = [[torch.empty(own_shape, dtype=torch.int64, pin_memory=True) for _ in range(n_out)]]
-    dev_sets = [out]
-    # the second buffer set doubles the page-locked host memory (6.25 GB per set and rank for the default workload): keep the
-    # whole job at or below the 50 GB that one set per rank takes on 8 GPUs
-    if world * 2 * n_out * int(np.prod(own_shape)) * 8 <= 50e9:
-        try:
-            host_sets.append([torch.empty(own_shape, dtype=torch.int64, pin_memory=True) for _ in range(n_out)])
-            dev_sets.append([torch.empty_like(o) for o in out])
-        except RuntimeError:       # not enough pinned / device memory for the second set: one volume in flight
-            host_sets, dev_sets = host_sets[:1], dev_sets[:1]
-    streaming = len(host_sets) == 2
-    e2e_steps = max(2, min(args.steps, 8))
-    for k in range(4):                                     # warm-up (touches both buffer sets, fills the allocator caches)
-        seg.run_host(host_affs, host_sets[k % len(host_sets)], out=dev_sets[k % len(dev_sets)], wait=not streaming)
-    seg.drain()
-    barrier()
-    ev0.record()
-    for k in range(e2e_steps):
-        seg.run_host(host_affs, host_sets[k % len(host_sets)], out=dev_sets[k % len(dev_sets)], wait=not streaming)
-    seg.drain()
-    ev1.record()
-    barrier()
-    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item()) / e2e_steps
-    h2d = host_affs.numel() * host_affs.element_size()
-    d2h = sum(o.numel() * 8 for o in host_sets[0])
-    return e2e_ms, h2d, d2h, streaming
-
-
-def report(args, seg, shape, slab, block, context, world, ms_step, value, V_total, prof_acc, launches, clocks, e2e_ms, h2d, d2h, e2e_stream):
+def roofline_of(res, traffic_ok):
     peak, peak_src = measured_peak()
-    steps = args.steps
-    prof = {k: v / steps for k, v in prof_acc.items()}
+    prof = res["stage_ms"]
     dom = max(prof, key=prof.get)
     # algorithmic bytes of one launch of the dominant kernel = 35 B/voxel x the voxels this rank's launch covers
-    alg_bytes = BYTES_PER_VOXEL * float(np.prod(seg.own_shape))
+    alg_bytes = BYTES_PER_VOXEL * float(np.prod(res["seg"].own_shape))
     achieved = alg_bytes / (prof[dom] * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp) and args.config == 2 and not args.quick:   # the captures are of the default workload
+    if traffic_ok and os.path.exists(tp):   # the captures are of the default workload
         traffic = json.load(open(tp)).get(dom)
-    cpu = None
-    if not args.no_cpu and args.config == 2 and world == 1:   # the CPU leg samples the default workload, on rank 0 at N=1 only
+    return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": prof[dom],
+            "whole_path_frac": (alg_bytes / (res["ms_step"] * 1e-3) / 1e9) / peak}
+
+
+def run_e2e(job, res, steps):
+    """host-buffer leg through ShardedSegmenter.run_host in its streaming form: every step uploads the step's affinities
+    from pinned memory and downloads fragments + all segmentations into pinned memory (a bounded ring of z-chunk staging
+    buffers, < 2 GB page-locked per rank, drained by a downloader thread); the downloads of step k overlap the upload and
+    compute of step k + 1 (two device buffer sets); the timed region ends when the last chunk of the last step has landed."""
+    import torch
+    from bootstrapper_b200.sharded import HostRing
+    seg, affs, out = res["seg"], res["affs"], res["out"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    host_affs = torch.empty(affs.shape, dtype=affs.dtype, pin_memory=True)
+    host_affs.copy_(affs)
+    n_out = 1 + len(THRESHOLDS)
+    ring = HostRing(seg.own_shape, device=job.dev)
+    dev_sets = [out, [torch.empty_like(o) for o in out]]
+    e2e_steps = max(2, min(steps, 8))
+    for k in range(3):                                     # warm-up (touches both buffer sets, fills the allocator caches)
+        seg.run_host(host_affs, None, out=dev_sets[k % 2], wait=False, ring=ring)
+    seg.drain()
+    job.barrier()
+    ev0.record()
+    for k in range(e2e_steps):
+        seg.run_host(host_affs, None, out=dev_sets[k % 2], wait=False, ring=ring)
+    seg.drain()
+    ev1.record()
+    job.barrier()
+    e2e_ms = job.max_over_ranks(ev0.elapsed_time(ev1)) / e2e_steps
+    h2d = host_affs.numel() * host_affs.element_size()
+    d2h = n_out * int(np.prod(seg.own_shape)) * 8
+    info = dict(ms=e2e_ms, h2d=h2d, d2h=d2h, pinned_bytes=ring.pinned_bytes + h2d, chunks=ring.chunks_done,
+                mode=f"streaming: downloads of step k overlap upload + compute of step k+1; results land in a ring of {ring.n_slots} "
+                     f"page-locked z-chunk buffers ({ring.pinned_bytes / 1e9:.2f} GB per rank) drained by a downloader thread")
+    ring.close()
+    return info
+
+
+def multi_gpu_parity(job):
+    """N > 1: a small volume through the sharded path on all ranks, then rank 0 runs the same volume alone (single-GPU
+    path, bit-exact vs the oracle in the tests) and compares its own slab + the global graph.  Outside every timed region."""
+    import torch
+    from bootstrapper_b200 import native
+    from bootstrapper_b200.post.pipeline import segment_blockwise
+    from bootstrapper_b200.sharded import ShardedSegmenter
+    shape, block, context = (20 * job.world, 500, 500), (10, 250, 250), (2, 31, 31)
+    params = {"thresholds": THRESHOLDS}
+    seg = ShardedSegmenter(shape, block, context, params, rank=job.rank, world=job.world, device=job.dev)
+    r = seg.run(seg.synth_local_affs(seed=3))
+    job.barrier()
+    if job.rank != 0:
+        return None
+    full = segment_blockwise(native.synth_affs(shape, seed=3, device=job.dev), params, block, context)
+    g = seg.geo
+    own = slice(g["z0"], g["z1"])
+    ok_f = bool(torch.equal(r["own_fragments"], full["fragments"][own]))
+    def canon(e):
+        u, v, sc = [t.cpu().numpy() for t in e]
+        o = np.lexsort((v, u))
+        return u[o], v[o], sc[o].view(np.int32)
+    a, b = canon(r["edges"]), canon(full["edges"])
+    ok_e = all(x.shape == y.shape and bool(np.array_equal(x, y)) for x, y in zip(a, b))
+    ok_s = all(bool(torch.equal(r["segs"][t], full["segs"][t][own])) for t in THRESHOLDS)
+    return {"volume": f"3x{shape}, block {block}, context {context}, {job.world} slabs vs one GPU", "fragments": ok_f, "edges": ok_e,
+            "segs": ok_s}
+
+
+def run_ours(args):
+    import torch
+    from bootstrapper_b200 import native
+    job = Job()
+    res = time_workload(job, args.config, args.steps, args.warmup, quick=args.quick, clocks=True)
+    # ---- end to end through the public API with host buffers (pinned), copies inside the timed region
+    e2e = None
+    if args.config == 2 and not args.no_e2e:   # (69 GB of outputs per rank for config 5) measured on the default workload only
+        e2e = run_e2e(job, res, args.steps)
+    line = None
+    if job.rank == 0:
+        line = report(args, job, res, e2e)
+    # ---- parity, outside the timed regions: CPU oracle vs GPU on the cpu_baseline sample (N=1), sharded vs single GPU (N>1)
+    parity = {}
+    if job.world > 1 and not args.no_parity:
+        mg = multi_gpu_parity(job)
+        if mg is not None:
+            parity["multi_gpu"] = mg
+    if job.world == 1 and not args.no_cpu and args.config == 2:
+        from bootstrapper_b200.post.pipeline import segment_blockwise
         sample = (50, 500, 500) if args.quick else CPU_SAMPLE
-        r, tm = cpu_oracle_rate(sample)
-        cpu = {"value": r, "unit": "voxels/s", "cores": tm["workers"], "kind": "port",
-               "sample": f"sub-volume {sample} of the workload ({tm['blocks']} blocks, same block geometry), "
-                         f"one process per block, {tm['total']:.1f} s"}
+        saffs = native.synth_affs(sample, seed=0, device=job.dev)
+        rate, tm, ref = cpu_oracle_run(saffs.cpu().numpy())
+        got = segment_blockwise(saffs, {"thresholds": THRESHOLDS}, BLOCK, CONTEXT)
+        parity["cpu_oracle"] = dict(compare_with_oracle(got, ref), sample=f"sub-volume {sample} ({tm['blocks']} blocks)")
+        line["cpu_baseline"] = {"value": rate, "unit": "voxels/s", "cores": tm["workers"], "kind": "port",
+                                "sample": f"sub-volume {sample} of the workload ({tm['blocks']} blocks, same block geometry), "
+                                          f"one process per block, {tm['total']:.1f} s"}
+        del got, saffs, ref
+    # ---- the BASELINE multi-GPU target configurations, driver-run: config 5 on 8 GPUs, config 4 on 4 / 2
+    extra = {}
+    want = {8: [5], 4: [4], 2: [4]}.get(job.world, []) if (args.config == 2 and not args.quick and not args.no_extra) else []
+    if want:
+        del res["seg"], res["affs"], res["out"]
+        res = None
+        torch.cuda.empty_cache()
+        native.release_scratch()
+    for c in want:
+        r2 = time_workload(job, c, 3, 2)
+        if job.rank == 0:
+            rf = roofline_of(r2, False)
+            extra[f"config{c}"] = {"workload": workload_string(c, r2["shape"], job.world, r2["slab"], r2["block"], r2["context"]),
+                                   "ms_per_step": r2["ms_step"], "value": r2["value"], "unit": "voxels/s", "steps": 3, "warmup": 2,
+                                   "whole_path_frac": rf["whole_path_frac"], "dominant": rf["kernel"],
+                                   "stage_ms": {k: round(v, 3) for k, v in sorted(r2["stage_ms"].items(), key=lambda kv: -kv[1])},
+                                   "gpu_launches": r2["launches"]}
+        del r2
+        torch.cuda.empty_cache()
+        native.release_scratch()
+    if job.rank == 0:
+        line["parity_checked"] = parity or None
+        if extra:
+            line["extra"] = extra
+        print(json.dumps(line), flush=True)
+    if job.world > 1:
+        job.dist.destroy_process_group()
+
+
+def report(args, job, res, e2e):
+    world = job.world
+    V_total = float(np.prod(res["shape"]))
     line = {
-        "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "metric": METRIC, "value": res["value"], "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": res["ms_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": f"{'CREMI-sized ' if args.config == 2 else ''}synthetic uint8 affinities 3x{shape} ({world} z-slab(s) of {slab}), "
-                               f"block {block}, context {context}, "
-                               f"{'ws defaults' if args.config != 4 else 'fragments_in_xy=false, seed_eps=0.01'}, thresholds [0.2,0.35,0.5]",
-                   "l2": f"inputs larger than L2 ({3 * int(np.prod(slab)) / 1e6:.0f} MB affinities, "
-                         f"{32 * int(np.prod(slab)) / 1e9:.1f} GB outputs per step per GPU)",
-                   "parity": "bit-exact vs oracle (seed_tie=index, stats_mode=canonical), tests/test_gpu_parity.py"},
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": prof[dom],
-                     "whole_path_frac": (BYTES_PER_VOXEL * V_total / world / (ms_step * 1e-3) / 1e9) / peak},
-        "stage_ms": {k: round(v, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])},
-        "cpu_baseline": cpu,
-        "e2e": None if e2e_ms is None else {"value": V_total / (e2e_ms * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": h2d,
-                                            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                                            "mode": ("streaming: downloads of step k overlap upload + compute of step k+1, two buffer sets"
-                                                     if e2e_stream else "one volume in flight")},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "config": {"workload": workload_string(args.config, res["shape"], world, res["slab"], res["block"], res["context"]),
+                   "l2": f"inputs larger than L2 ({3 * int(np.prod(res['slab'])) / 1e6:.0f} MB affinities, "
+                         f"{32 * int(np.prod(res['slab'])) / 1e9:.1f} GB outputs per step per GPU)",
+                   "parity": PARITY_NOTE},
+        "roofline": roofline_of(res, args.config == 2 and not args.quick),
+        "stage_ms": {k: round(v, 3) for k, v in sorted(res["stage_ms"].items(), key=lambda kv: -kv[1])},
+        "cpu_baseline": None,
+        "e2e": None if e2e is None else {"value": V_total / (e2e["ms"] * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": e2e["h2d"],
+                                         "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["ms"], "mode": e2e["mode"],
+                                         "pinned_bytes_per_rank": e2e["pinned_bytes"]},
+        "gpu_launches": res["launches"], "clocks": res["clocks"],
     }
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def main():
@@ -324,8 +448,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--quick", action="store_true", help="small volume (smoke / CI), not a valid bench number")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (and its parity comparison)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra BASELINE configurations (config 5 at 8 GPUs, config 4 at 4 / 2)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity comparison")
     ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
                     help="2 = BASELINE configs[1] (default, the metric's workload); 4 = 1024^3 3-D seeded + seed_eps over 4 GPUs (a 256x1024x1024 "
                          "slab per rank); 5 = 2048^3 over 8 GPUs (a 256x2048x2048 slab per rank)")

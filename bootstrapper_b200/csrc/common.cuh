@@ -226,8 +226,8 @@ __device__ __forceinline__ void unravel3(long long i, int W, int H, int &x, int 
 // The division by the run-constant prod(block_size) is a multiply-high with a precomputed magic number
 // (round-up method, exact for every 64-bit id): q = (((n - mulhi(m, n)) >> 1) + mulhi(m, n)) >> sh.
 struct IdMap {
-    const uint32_t *cantor2dense;   // block_id -> dense base of that block (0xFFFFFFFF if unknown)
-    long long max_block_id;
+    const uint32_t *cantor2dense;   // block_id - min_block_id -> dense base of that block (0xFFFFFFFF if unknown)
+    long long min_block_id, max_block_id;
     long long nvox_block;
     unsigned long long magic;       // 0: nvox_block is a power of two, divide by shifting `sh`
     int sh;
@@ -254,8 +254,8 @@ __device__ __forceinline__ uint64_t id_block(const IdMap &m, uint64_t id) {
 __device__ __forceinline__ uint32_t id_to_dense(const IdMap &m, uint64_t id) {
     if (id == 0) return 0xFFFFFFFFu;
     uint64_t bid = id_block(m, id);
-    if ((long long)bid > m.max_block_id) return 0xFFFFFFFFu;
-    uint32_t base = m.cantor2dense[bid];
+    if ((long long)bid > m.max_block_id || (long long)bid < m.min_block_id) return 0xFFFFFFFFu;
+    uint32_t base = m.cantor2dense[bid - (uint64_t)m.min_block_id];
     if (base == 0xFFFFFFFFu) return 0xFFFFFFFFu;
     return base + (uint32_t)(id - bid * (uint64_t)m.nvox_block) - 1u;
 }

@@ -69,5 +69,7 @@ struct Plan {
 };
 
 int plan_build(const bs_ws_config &cfg, Plan **out);
+// fragment id -> dense node number map of the plan's current fragment counts (table in `buf`, uploaded on `s`)
+int plan_idmap(const Plan &P, DevBuf &buf, IdMap *idm, cudaStream_t s);
 
 }  // namespace bs

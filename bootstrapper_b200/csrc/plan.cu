@@ -36,6 +36,7 @@ int plan_build(const bs_ws_config &cfg, Plan **out) {
                "bs_plan_create: shapes must be positive");
         BS_ARG(cfg.roi_offset[d] >= 0 && cfg.roi_offset[d] + cfg.roi_shape[d] <= cfg.vol_shape[d],
                "bs_plan_create: roi must lie inside the affinity array");
+        BS_ARG(cfg.block_index_offset[d] >= 0, "bs_plan_create: block_index_offset (absolute ROI offset in voxels) must be >= 0");
     }
     BS_ARG(cfg.aff_dtype == BS_DTYPE_U8 || cfg.aff_dtype == BS_DTYPE_F32, "bs_plan_create: aff_dtype must be u8 or f32");
     BS_ARG(cfg.n_channels >= 3, "bs_plan_create: need at least 3 affinity channels");
@@ -68,7 +69,10 @@ int plan_build(const bs_ws_config &cfg, Plan **out) {
                 b.idx[0] = i;
                 b.idx[1] = j;
                 b.idx[2] = k;
-                b.block_id = cantor_number(b.idx, 3);
+                // daisy numbers the ABSOLUTE block index write_roi.offset / write_roi.shape (floor division)
+                int aidx[3];
+                for (int d = 0; d < 3; d++) aidx[d] = (int)(((long long)cfg.block_index_offset[d] + (long long)b.idx[d] * cfg.block_size[d]) / cfg.block_size[d]);
+                b.block_id = cantor_number(aidx, 3);
                 for (int d = 0; d < 3; d++) {
                     b.wo[d] = cfg.roi_offset[d] + b.idx[d] * cfg.block_size[d];
                     b.ws[d] = std::min(cfg.block_size[d], cfg.roi_offset[d] + cfg.roi_shape[d] - b.wo[d]);
@@ -103,6 +107,26 @@ int plan_build(const bs_ws_config &cfg, Plan **out) {
     p->block_count.assign(blocks.size(), 0);
     p->block_nbase.assign(blocks.size() + 1, 0);
     *out = p;
+    return BS_OK;
+}
+
+int plan_idmap(const Plan &P, DevBuf &buf, IdMap *idm, cudaStream_t s) {
+    long long lo = 0, hi = 0;
+    for (size_t i = 0; i < P.blocks.size(); i++) {
+        lo = i ? std::min(lo, P.blocks[i].block_id) : P.blocks[i].block_id;
+        hi = std::max(hi, P.blocks[i].block_id);
+    }
+    // cantor numbers of a block grid far from the origin are sparse: the table spans [lo, hi]
+    BS_ARG(hi - lo < (1LL << 28), "block ids span more than 2^28 values (absolute block index too large for the id table)");
+    std::vector<uint32_t> c2d((size_t)(hi - lo) + 1, 0xFFFFFFFFu);
+    for (size_t i = 0; i < P.blocks.size(); i++) c2d[P.blocks[i].block_id - lo] = (uint32_t)P.block_nbase[i];
+    BS_TRY(buf.alloc(4 * c2d.size(), s));
+    BS_CUDA(cudaMemcpyAsync(buf.p, c2d.data(), 4 * c2d.size(), cudaMemcpyHostToDevice, s));
+    BS_CUDA(cudaStreamSynchronize(s));   // c2d is a host-staged copy
+    idm->cantor2dense = buf.as<uint32_t>();
+    idm->min_block_id = lo;
+    idm->max_block_id = hi;
+    idm->set_divisor(P.nvox_block);
     return BS_OK;
 }
 

@@ -338,10 +338,6 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
     BS_ARG(nown <= 65535, "stage2: too many owned blocks for one launch");
     // dense numbering of all blocks
     const size_t nblocks = P.blocks.size();
-    long long max_bid = 0;
-    for (auto &b : P.blocks) max_bid = std::max(max_bid, b.block_id);
-    std::vector<uint32_t> c2d((size_t)max_bid + 1, NONE32);
-    for (size_t i = 0; i < nblocks; i++) c2d[P.blocks[i].block_id] = (uint32_t)P.block_nbase[i];
     BS_ARG(P.block_nbase[nblocks] < (1LL << 32) - 2, "stage2: more than 2^32 fragments");
 
     std::vector<S2Blk> hb(nown);
@@ -383,17 +379,13 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
     DevBuf d_blks, d_c2d, hkeys, hsum, hcnt, hfirst, ovf;
     BS_TRY(d_blks.alloc(sizeof(S2Blk) * nown, s));
     BS_CUDA(cudaMemcpyAsync(d_blks.p, hb.data(), sizeof(S2Blk) * nown, cudaMemcpyHostToDevice, s));
-    BS_TRY(d_c2d.alloc(4 * c2d.size(), s));
-    BS_CUDA(cudaMemcpyAsync(d_c2d.p, c2d.data(), 4 * c2d.size(), cudaMemcpyHostToDevice, s));
     BS_TRY(hkeys.alloc_fill(8 * Ttot, 0xFF, s));
     BS_TRY(hsum.alloc_zero(8 * Ttot, s));
     BS_TRY(hcnt.alloc_zero(4 * Ttot, s));
     BS_TRY(hfirst.alloc_fill(4 * Ttot, 0xFF, s));
     BS_TRY(ovf.alloc_zero(16, s));
     IdMap idm;
-    idm.cantor2dense = d_c2d.as<uint32_t>();
-    idm.max_block_id = max_bid;
-    idm.set_divisor(P.nvox_block);
+    BS_TRY(plan_idmap(P, d_c2d, &idm, s));
     const S2Blk *db = d_blks.as<S2Blk>();
 
     g_prof.mark("s2.rag", s);

@@ -112,17 +112,9 @@ int relabel_dense(Plan &P, const uint64_t *frags, int64_t n, const uint64_t *con
     BS_ARG(T >= 1 && T <= 8, "bs_stage3_relabel: 1..8 thresholds per call");
     if (n == 0) return BS_OK;
     const size_t nblocks = P.blocks.size();
-    long long max_bid = 0;
-    for (auto &b : P.blocks) max_bid = std::max(max_bid, b.block_id);
-    std::vector<uint32_t> c2d((size_t)max_bid + 1, NONE32);
-    for (size_t i = 0; i < nblocks; i++) c2d[P.blocks[i].block_id] = (uint32_t)P.block_nbase[i];
     DevBuf d_c2d;
-    BS_TRY(d_c2d.alloc(4 * c2d.size(), s));
-    BS_CUDA(cudaMemcpyAsync(d_c2d.p, c2d.data(), 4 * c2d.size(), cudaMemcpyHostToDevice, s));
     IdMap idm;
-    idm.cantor2dense = d_c2d.as<uint32_t>();
-    idm.max_block_id = max_bid;
-    idm.set_divisor(P.nvox_block);
+    BS_TRY(plan_idmap(P, d_c2d, &idm, s));
     RelabelSet rs;
     rs.T = T;
     for (int t = 0; t < 8; t++) {
@@ -204,17 +196,9 @@ int components_multi(Plan &P, const uint64_t *nodes, int64_t n, const uint64_t *
     for (int t = 1; t < T; t++) BS_ARG(thresholds[t] >= thresholds[t - 1], "bs_stage3_components: thresholds must be ascending");
     if (n == 0) return BS_OK;
     const size_t nblocks = P.blocks.size();
-    long long max_bid = 0;
-    for (auto &b : P.blocks) max_bid = std::max(max_bid, b.block_id);
-    std::vector<uint32_t> c2d((size_t)max_bid + 1, NONE32);
-    for (size_t i = 0; i < nblocks; i++) c2d[P.blocks[i].block_id] = (uint32_t)P.block_nbase[i];
     DevBuf d_c2d, parent;
-    BS_TRY(d_c2d.alloc(4 * c2d.size(), s));
-    BS_CUDA(cudaMemcpyAsync(d_c2d.p, c2d.data(), 4 * c2d.size(), cudaMemcpyHostToDevice, s));
     IdMap idm;
-    idm.cantor2dense = d_c2d.as<uint32_t>();
-    idm.max_block_id = max_bid;
-    idm.set_divisor(P.nvox_block);
+    BS_TRY(plan_idmap(P, d_c2d, &idm, s));
     CcSet cs;
     cs.T = T;
     for (int t = 0; t < 8; t++) {

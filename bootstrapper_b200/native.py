@@ -46,6 +46,7 @@ class WsConfig(C.Structure):
         ("block_end", C.c_int32), ("win_z0", C.c_int32), ("win_z", C.c_int32), ("filter_fragments", C.c_double), ("max_batch_voxels", C.c_int64),
         ("has_bias", C.c_int32), ("has_seed_eps", C.c_int32), ("bias", C.c_double * 3), ("seed_eps", C.c_double),
         ("has_sigma", C.c_int32), ("sigma_radius", C.c_int32 * 3), ("sigma_w", (C.c_double * SIGMA_MAXW) * 3),
+        ("block_index_offset", C.c_int32 * 3), ("pad_tail_", C.c_int32),
     ]
 
 
@@ -150,7 +151,9 @@ class Plan:
     def __init__(self, vol_shape, block_size, context, aff_dtype, roi_offset=None, roi_shape=None, n_channels=3,
                  fragments_in_xy=True, min_seed_distance=10, filter_fragments=0.1, remove_debris=64,
                  queue_bins=256, keep_cheaper=True, block_begin=-1, block_end=-1, max_batch_voxels=0, win_z0=0, win_z=0,
-                 bias=None, seed_eps=None, sigma=None):
+                 bias=None, seed_eps=None, sigma=None, block_index_offset=None):
+        """block_index_offset: absolute offset of the task ROI in voxels (dataset offset / voxel_size + roi_offset), which
+        daisy's block ids are numbered from; default: roi_offset, i.e. a dataset at world offset 0."""
         cfg = WsConfig()
         roi_offset = roi_offset if roi_offset is not None else (0, 0, 0)
         roi_shape = roi_shape if roi_shape is not None else vol_shape
@@ -160,6 +163,7 @@ class Plan:
             cfg.roi_shape[d] = int(roi_shape[d])
             cfg.block_size[d] = int(block_size[d])
             cfg.context[d] = int(context[d])
+            cfg.block_index_offset[d] = int((block_index_offset if block_index_offset is not None else roi_offset)[d])
         cfg.aff_dtype = aff_dtype
         cfg.n_channels = n_channels
         cfg.fragments_in_xy = 1 if fragments_in_xy else 0
@@ -233,6 +237,14 @@ class Plan:
         stored as torch.int64 bit patterns."""
         if frags_out is None:
             frags_out = torch.zeros(self.roi_shape, dtype=torch.int64, device=affs.device)
+        vol = tuple(int(self.cfg.vol_shape[d]) for d in range(3))
+        if self.cfg.win_z > 0:
+            vol = (int(self.cfg.win_z),) + vol[1:]
+        if tuple(affs.shape[1:]) != vol:
+            raise BsError(f"affinities have spatial shape {tuple(affs.shape[1:])}, the plan was made for {vol}")
+        if mask is not None and tuple(mask.shape) != vol:
+            raise BsError(f"mask shape {tuple(mask.shape)} must equal the affinities' spatial shape {vol} "
+                          "(crop / zero-pad it onto the affinity grid first)")
         _check(lib().bs_stage1_fragments(self._h, _dev(affs), _dev(mask, torch.uint8) if mask is not None else None,
                                          _dev(frags_out, torch.int64), _stream()))
         return frags_out

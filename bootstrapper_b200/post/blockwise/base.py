@@ -66,8 +66,10 @@ class BlockwiseTask:
     def _make_plan(self, **kw):
         affs = self._load_affs()
         off, shp = self._voxel_roi()
+        # daisy block ids come from the ABSOLUTE write-ROI offset: world offset / voxel size
+        absolute = tuple(int(o) // int(v) for o, v in zip(self.write_roi.offset, self.voxel_size))
         return native.Plan(tuple(affs.shape[1:]), tuple(self.block_size), tuple(self.context), native._aff_dtype(affs),
-                           roi_offset=off, roi_shape=shp, n_channels=affs.shape[0], **kw)
+                           roi_offset=off, roi_shape=shp, n_channels=affs.shape[0], block_index_offset=absolute, **kw)
 
     def blocks(self):
         """daisy blocks (ascending block id), world-unit ROIs."""

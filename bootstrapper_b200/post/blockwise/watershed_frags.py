@@ -27,6 +27,7 @@ class WatershedFrags(BlockwiseTask):
             filter_fragments=filter_fragments, remove_debris=remove_debris))
         self._plan_obj = None
         self._frags_dev = None
+        self._mask_cache = None
 
     @property
     def task_name(self):
@@ -61,12 +62,35 @@ class WatershedFrags(BlockwiseTask):
         return self._plan_obj
 
     def _mask_dev(self):
+        """the mask on the affinity array's voxel grid (watershed_frags.py:207-213 reads mask.to_ndarray(block.read_roi,
+        fill_value=0)): cropped / zero-padded in world units, so a smaller or shifted mask dataset lines up; a different
+        voxel size is refused.  The reference multiplies the affinities by the mask's raw values unless they are 0 / 255 or
+        the mask has channels; masks holding other values than 0, 1, 255 are refused rather than silently binarised."""
         if self.mask_data is None:
             return None
-        m = self.mask_data.array("r").read()
+        if getattr(self, "_mask_cache", None) is not None:
+            return self._mask_cache
+        ma, a = self.mask_data.array("r"), self._affs_array()
+        vs = tuple(a.voxel_size)
+        if tuple(ma.voxel_size) != vs:
+            raise ValueError(f"mask voxel size {tuple(ma.voxel_size)} differs from the affinities' {vs}")
+        if any((ao - mo) % v for ao, mo, v in zip(a.offset, ma.offset, vs)):
+            raise ValueError("mask offset is not aligned with the affinity voxel grid")
+        start = tuple((ao - mo) // v for ao, mo, v in zip(a.offset, ma.offset, vs))
+        m = ma.to_ndarray(start, a.spatial_shape, fill_value=0)
         if m.ndim == 4:                                   # watershed_frags.py:209-210
-            m = m.min(axis=0)
-        return torch.from_numpy(np.ascontiguousarray((m > 0).astype(np.uint8))).cuda()
+            m = (m.min(axis=0) > 0).astype(np.uint8)
+        else:
+            vals = np.unique(m)
+            if not np.isin(vals, (0, 1, 255)).all():
+                raise NotImplementedError("mask values other than 0 / 1 / 255 scale the affinities in the reference "
+                                          "(watershed_frags.py:211-213); binarise the mask first")
+            if vals.size and vals.max() == 255 and (vals == 1).any():
+                raise NotImplementedError("a mask mixing the values 1 and 255 is binarised per block in the reference; "
+                                          "binarise the mask first")
+            m = (m > 0).astype(np.uint8)
+        self._mask_cache = torch.from_numpy(np.ascontiguousarray(m)).cuda()
+        return self._mask_cache
 
     def _frags(self):
         if self._frags_dev is None:

@@ -12,6 +12,9 @@ three small exchanges over torch.distributed (NCCL on GPUs, gloo in the CPU test
 Block geometry never depends on the rank count, so results are identical for any number of GPUs.
 The exchange helpers are device-agnostic so that the N > 1 host logic is covered by gloo tests on CPU.
 """
+import queue
+import threading
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -113,6 +116,93 @@ def global_node_ids(block_ids, counts, nvox_block, device):
     return torch.cat(parts) if parts else torch.zeros(0, dtype=torch.int64, device=device)
 
 
+class HostRing:
+    """Device -> host streaming of (Z, Y, X) int64 result arrays through a bounded ring of page-locked z-chunk buffers.
+
+    A downloader thread owns a copy stream: every submitted device array is cut into chunks of whole z planes, each chunk
+    is copied into the next ring slot as soon as the slot's previous content has landed and been handed to `sink(name,
+    z0, z1, pinned_view)` (the consumer: a zarr writer, a checksum, nothing).  Page-locked memory is n_slots * chunk_bytes
+    per rank whatever the volume size, so streaming stays on with 8 ranks on one host."""
+
+    def __init__(self, plane_shape, device, chunk_bytes=64 << 20, n_slots=16, sink=None):
+        Y, X = int(plane_shape[-2]), int(plane_shape[-1])
+        self.planes = max(1, int(chunk_bytes) // (Y * X * 8))
+        self.n_slots = int(n_slots)
+        self.slots = [torch.empty((self.planes, Y, X), dtype=torch.int64, pin_memory=True) for _ in range(self.n_slots)]
+        self.pinned_bytes = self.n_slots * self.planes * Y * X * 8
+        self.pending = [None] * self.n_slots       # (cuda event of the copy into the slot, (name, z0, z1))
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self.sink = sink
+        self.next = 0
+        self.chunks_done = 0
+        self.error = None
+        self.q = queue.Queue()
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def _consume(self, k):
+        if self.pending[k] is not None:
+            ev, meta = self.pending[k]
+            ev.synchronize()
+            if self.sink is not None:
+                self.sink(meta[0], meta[1], meta[2], self.slots[k][:meta[2] - meta[1]])
+            self.pending[k] = None
+            self.chunks_done += 1
+
+    def _loop(self):
+        torch.cuda.set_device(self.device)
+        while True:
+            job = self.q.get()
+            if job is None:
+                return
+            kind, name, tensor, ready, issued = job
+            try:
+                if kind == "flush":
+                    for i in range(self.n_slots):
+                        self._consume((self.next + i) % self.n_slots)
+                else:
+                    with torch.cuda.stream(self.stream):
+                        self.stream.wait_event(ready)
+                        Z = tensor.shape[0]
+                        ev = None
+                        for z0 in range(0, Z, self.planes):
+                            z1 = min(Z, z0 + self.planes)
+                            k = self.next % self.n_slots
+                            self.next += 1
+                            self._consume(k)
+                            self.slots[k][:z1 - z0].copy_(tensor[z0:z1], non_blocking=True)
+                            ev = torch.cuda.Event()
+                            ev.record(self.stream)
+                            self.pending[k] = (ev, (name, z0, z1))
+                        issued["event"] = ev          # the device array is free again once its last chunk has left
+            except Exception as e:  # noqa: BLE001
+                self.error = e
+            finally:
+                issued["flag"].set()
+
+    def submit(self, name, tensor, ready):
+        """queue the download of `tensor` (Z, Y, X) int64 once the cuda event `ready` has fired; returns a handle whose
+        `flag` is set when every chunk has been issued and whose `event` then marks the end of the last copy"""
+        issued = {"flag": threading.Event(), "event": None}
+        self.q.put(("copy", name, tensor, ready, issued))
+        return issued
+
+    def flush(self):
+        """wait until every queued array has landed and been handed to the sink"""
+        issued = {"flag": threading.Event(), "event": None}
+        self.q.put(("flush", None, None, None, issued))
+        issued["flag"].wait()
+        if self.error is not None:
+            raise self.error
+
+    def close(self):
+        self.flush()
+        self.q.put(None)
+        self.thread.join()
+        self.slots = []
+
+
 class ShardedSegmenter:
     def __init__(self, vol_shape, block_size, context, params=None, rank=0, world=1, device=None, group=None):
         self.vol_shape = tuple(int(v) for v in vol_shape)
@@ -167,9 +257,12 @@ class ShardedSegmenter:
                 self._copy_stream = torch.cuda.Stream(device=affs_win.device)
             ev = torch.cuda.Event()
             ev.record()
-            with torch.cuda.stream(self._copy_stream):
-                self._copy_stream.wait_event(ev)
-                frag_sink.copy_(frags[g["z0"] - g["w0"]:g["z1"] - g["w0"]], non_blocking=True)
+            if isinstance(frag_sink, HostRing):
+                frag_sink.submit(("fragments", None), frags[g["z0"] - g["w0"]:g["z1"] - g["w0"]], ev)
+            else:
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(ev)
+                    frag_sink.copy_(frags[g["z0"] - g["w0"]:g["z1"] - g["w0"]], non_blocking=True)
         counts = allgather_counts(plan.block_counts(), self.world, affs_win.device, self.group)
         if self.world > 1:
             plan.set_block_counts(counts)
@@ -204,31 +297,54 @@ class ShardedSegmenter:
         self.last_profile = prof
         return dict(fragments=frags, own_fragments=own, segs=segs, luts=luts, nodes=nodes, edges=(eu, ev, es))
 
-    def run_host(self, host_affs, host_out, out=None, wait=True):
-        """end-to-end with HOST buffers: pinned affinities in, fragments + segmentations out (pinned).
+    def run_host(self, host_affs, host_out, out=None, wait=True, ring=None):
+        """end-to-end with HOST buffers: pinned affinities in, fragments + segmentations out.
+        host_out: pinned (own_shape) int64 arrays [fragments, seg per threshold] the results are copied into, or None with
+        ring: a HostRing -- the results stream through its bounded set of page-locked z-chunk buffers to its sink instead.
         out: optional device staging buffers for the segmentations (one per threshold).
         wait=False: streaming use over many volumes -- the call returns once the copies are queued; the device->host
         copies of this volume then overlap the next calls' upload and compute (the copy stream is FIFO, and a relabel that
         writes into `out` buffers an earlier volume is still being copied from waits for those copies).  Alternate
-        between two sets of `out` / `host_out` buffers and call `drain()` before reading the last results."""
+        between two sets of `out` (and `host_out`) buffers and call `drain()` before reading the last results."""
         affs = host_affs.to(self.device, non_blocking=True)
         key = out[0].data_ptr() if out else None
         busy = [f[0] for f in self._inflight if key is not None and f[3] == key]
-        r = self.run(affs, out=out, frag_sink=host_out[0], out_ready=busy[-1] if busy else None)
+        out_ready = busy[-1] if busy else None
+        if isinstance(out_ready, dict):          # ring handle: the downloader thread records the event
+            out_ready["flag"].wait()
+            out_ready = out_ready["event"]
+        self._ring = ring
+        r = self.run(affs, out=out, frag_sink=host_out[0] if ring is None else ring, out_ready=out_ready)
         ready = torch.cuda.Event()
         ready.record()
-        with torch.cuda.stream(self._copy_stream):
-            self._copy_stream.wait_event(ready)
-            for i, thr in enumerate(self.p["thresholds"]):
-                host_out[1 + i].copy_(r["segs"][thr], non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(self._copy_stream)
+        if ring is not None:
+            done = None
+            for thr in self.p["thresholds"]:
+                done = ring.submit(("seg", thr), r["segs"][thr], ready)
+        else:
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(ready)
+                for i, thr in enumerate(self.p["thresholds"]):
+                    host_out[1 + i].copy_(r["segs"][thr], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(self._copy_stream)
         self._inflight.append((done, r, affs, key))     # the device arrays stay referenced until their copies are through
         while len(self._inflight) > (0 if wait else 2):
-            self._inflight.pop(0)[0].synchronize()
+            self._wait_done(self._inflight.pop(0)[0])
         return r
+
+    @staticmethod
+    def _wait_done(done):
+        if isinstance(done, dict):
+            done["flag"].wait()
+            if done["event"] is not None:
+                done["event"].synchronize()
+        elif done is not None:
+            done.synchronize()
 
     def drain(self):
         """wait for the device->host copies of every volume queued by run_host(wait=False)"""
         while self._inflight:
-            self._inflight.pop(0)[0].synchronize()
+            self._wait_done(self._inflight.pop(0)[0])
+        if getattr(self, "_ring", None) is not None:
+            self._ring.flush()

@@ -93,6 +93,21 @@ class ZarrArray:
             out[tuple(dst)] = self._read_chunk(cidx)[tuple(src)]
         return out
 
+    def to_ndarray(self, start, shape, fill_value=0):
+        """funlib.persistence Array.to_ndarray(roi, fill_value): the spatial window [start, start + shape) in voxel
+        indices of this array (may reach outside it), all leading (channel) dims, filled with fill_value outside."""
+        nsp = len(self.voxel_size)
+        lead = self.shape[:-nsp]
+        out = np.full(tuple(lead) + tuple(int(v) for v in shape), fill_value, dtype=self.dtype)
+        lo = [max(int(a), 0) for a in start]
+        hi = [min(int(a) + int(n), s) for a, n, s in zip(start, shape, self.spatial_shape)]
+        if any(h <= l for l, h in zip(lo, hi)):
+            return out
+        data = self.read(tuple([0] * len(lead)) + tuple(lo), tuple(lead) + tuple(hi))
+        dst = tuple(slice(l - int(a), h - int(a)) for l, h, a in zip(lo, hi, start))
+        out[(Ellipsis,) + dst] = data
+        return out
+
     def write(self, data, start=None):
         start = tuple(start) if start is not None else (0,) * len(self.shape)
         stop = tuple(a + s for a, s in zip(start, data.shape))

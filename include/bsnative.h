@@ -64,6 +64,11 @@ typedef struct bs_ws_config {
     int32_t has_sigma;
     int32_t sigma_radius[3];   /* per axis (z, y, x): int(4 * sigma + 0.5); -1 = sigma of that axis <= 1e-15 */
     double sigma_w[3][BS_SIGMA_MAXW]; /* 2 * radius + 1 normalised weights per axis                          */
+    /* daisy block ids: block.block_id[1] = cantor_number(write_roi.offset / write_roi.shape) with ABSOLUTE
+     * offsets.  block_index_offset = the task ROI's absolute offset in voxels (dataset offset / voxel_size + roi_offset);
+     * the grid index that is numbered is floor((block_index_offset + i * block_size) / block_size) per axis.           */
+    int32_t block_index_offset[3];
+    int32_t pad_tail_;
 } bs_ws_config;
 
 typedef struct bs_plan bs_plan;

@@ -58,11 +58,14 @@ class Block:
     read_shape: tuple
 
 
-def enumerate_blocks(roi_offset, roi_shape, block_size, context):
+def enumerate_blocks(roi_offset, roi_shape, block_size, context, index_offset=None):
     """daisy blocks of a volara BlockwiseTask with fit='shrink' (U10):
     write ROIs tile the task's write_roi from its offset in steps of block_size, the
-    trailing blocks are clipped; read_roi = write_roi grown by context."""
+    trailing blocks are clipped; read_roi = write_roi grown by context.
+    Block ids number the ABSOLUTE block index write_roi.offset / write_roi.shape (floor division, U10): index_offset is
+    the task ROI's absolute offset in voxels (dataset offset / voxel_size + roi_offset; default roi_offset)."""
     roi_offset = tuple(int(v) for v in roi_offset)
+    index_offset = roi_offset if index_offset is None else tuple(int(v) for v in index_offset)
     roi_shape = tuple(int(v) for v in roi_shape)
     nb = [-(-s // b) for s, b in zip(roi_shape, block_size)]
     blocks = []
@@ -74,7 +77,8 @@ def enumerate_blocks(roi_offset, roi_shape, block_size, context):
                 ws = tuple(min(b, o + s - w) for b, o, s, w in zip(block_size, roi_offset, roi_shape, wo))
                 ro = tuple(w - c for w, c in zip(wo, context))
                 rs = tuple(s + 2 * c for s, c in zip(ws, context))
-                blocks.append(Block(idx, cantor_number(idx), wo, ws, ro, rs))
+                aidx = tuple((io + n * b) // b for io, n, b in zip(index_offset, idx, block_size))
+                blocks.append(Block(idx, cantor_number(aidx), wo, ws, ro, rs))
     return blocks
 
 
@@ -290,8 +294,9 @@ def global_segmentation(frags, rag, thresholds):
 
 
 def waterz_pipeline(affs, params=None, block_size=None, context=None, roi=None, mask=None,
-                    seed_tie="heap", stats_mode="faithful", keep_cheaper=True):
-    """post/watershed.py:8-203 on in-memory arrays.  affs: (C,Z,Y,X) uint8 or float."""
+                    seed_tie="heap", stats_mode="faithful", keep_cheaper=True, index_offset=None):
+    """post/watershed.py:8-203 on in-memory arrays.  affs: (C,Z,Y,X) uint8 or float.
+    index_offset: absolute offset of the ROI in voxels (block ids, U10); default roi_offset."""
     p = dict(WS_DEFAULTS)
     p.update(params or {})
     vol_shape = affs.shape[1:]
@@ -301,7 +306,7 @@ def waterz_pipeline(affs, params=None, block_size=None, context=None, roi=None, 
         context = (0, 0, 0)
     elif context is None:         # watershed.py:79-83
         context = tuple(max(1, s // 8) for s in block_size)
-    blocks = enumerate_blocks(roi_offset, roi_shape, block_size, context)
+    blocks = enumerate_blocks(roi_offset, roi_shape, block_size, context, index_offset)
     frags = np.zeros(roi_shape, dtype=np.uint64)
     rag = Rag()
     for blk in blocks:

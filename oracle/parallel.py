@@ -30,7 +30,8 @@ def _stage2(i):
 
 
 def waterz_pipeline_parallel(affs, params=None, block_size=None, context=None, roi=None, mask=None, seed_tie="index",
-                             stats_mode="canonical", keep_cheaper=True, workers=None, block_subset=None, timings=None):
+                             stats_mode="canonical", keep_cheaper=True, workers=None, block_subset=None, timings=None,
+                             index_offset=None):
     """Same result as oracle.blockwise.waterz_pipeline, blocks distributed over a fork pool."""
     p = dict(ob.WS_DEFAULTS)
     p.update(params or {})
@@ -40,7 +41,7 @@ def waterz_pipeline_parallel(affs, params=None, block_size=None, context=None, r
         block_size, context = tuple(vol_shape), (0, 0, 0)
     elif context is None:
         context = tuple(max(1, s // 8) for s in block_size)
-    blocks = ob.enumerate_blocks(roi_offset, roi_shape, block_size, context)
+    blocks = ob.enumerate_blocks(roi_offset, roi_shape, block_size, context, index_offset)
     if block_subset is not None:
         blocks = [blocks[i] for i in block_subset]
     workers = workers or os.cpu_count()

@@ -470,6 +470,45 @@ def test_run_host_streaming_matches_blocking():
     assert int((ref[0][0] != 0).sum()) > 0 and not torch.equal(ref[0][1], ref[1][1])
 
 
+def test_run_host_ring_matches_blocking():
+    """ShardedSegmenter.run_host(ring=HostRing): results streamed through a small ring of page-locked z-chunk buffers (a
+    few planes per chunk, fewer slots than chunks per volume) reach the sink complete and in the blocking call's bytes"""
+    from bootstrapper_b200.sharded import HostRing, ShardedSegmenter
+    from bootstrapper_b200.synth import synth_affs
+    shape, block, ctx = (12, 120, 120), (6, 60, 60), (1, 8, 8)
+    thrs = [0.2, 0.5]
+    seg = ShardedSegmenter(shape, block, ctx, {"thresholds": thrs}, device=torch.device("cuda"))
+    vols = [torch.from_numpy(synth_affs(shape, seed=s)).pin_memory() for s in (1, 2, 3, 4)]
+    ref = []
+    for v in vols:
+        ho = [torch.empty(shape, dtype=torch.int64).pin_memory() for _ in range(3)]
+        seg.run_host(v, ho)
+        ref.append([h.clone() for h in ho])
+    got = {}
+    counter = {"vol": {}}
+
+    def sink(name, z0, z1, view):
+        # chunks of one array arrive in z order, arrays of one volume in submission order, volumes in order
+        n = counter["vol"].get(name, 0)
+        arr = got.setdefault((name, n), torch.zeros(shape, dtype=torch.int64))
+        arr[z0:z1] = view
+        if z1 == shape[0]:
+            counter["vol"][name] = n + 1
+
+    ring = HostRing(shape, torch.device("cuda"), chunk_bytes=5 * 120 * 120 * 8, n_slots=4, sink=sink)
+    assert ring.planes == 5 and ring.pinned_bytes == 4 * 5 * 120 * 120 * 8
+    dev_sets = [[torch.empty(shape, dtype=torch.int64, device="cuda") for _ in thrs] for _ in range(2)]
+    for k, v in enumerate(vols):
+        seg.run_host(v, None, out=dev_sets[k % 2], wait=False, ring=ring)
+    seg.drain()
+    ring.close()
+    for k in range(len(vols)):
+        assert torch.equal(got[(("fragments", None), k)], ref[k][0])
+        for i, t in enumerate(thrs):
+            assert torch.equal(got[(("seg", t), k)], ref[k][1 + i])
+    assert ring.chunks_done == len(vols) * 3 * 3
+
+
 # ---------------------------------------------------------------- `bs refine` filters (SURVEY 8f N4)
 def test_refine_filters_match_oracle():
     """per-id table (sizes, z-extents) and the four filters of refine.py against the numpy restatement"""
