@@ -8,6 +8,7 @@
 namespace bs {
 int g_debug = 0;
 int g_agglom_version = 0;  // 0 = auto (shared-memory kernel when the block fits), 1 = force the global-memory kernel
+int g_front_version = 0;   // stage-1 front end: 0 = auto (fused when eligible), 1 = unfused chain, 2 = fused without TMA, 3 = fused, TMA required
 int g_flood_version = 0;   // 0 = auto (v2 when eligible), 1 = force the global-memory flood
 int stage1_run(Plan &P, const void *affs, const uint8_t *mask, uint64_t *frags_out, cudaStream_t s);
 int label_stats(const uint64_t *seg, const int32_t *shape, int64_t capacity, uint64_t *ids, int64_t *sizes, int32_t *zlo,
@@ -71,6 +72,11 @@ static void init_mempool() {
 
 int bs_set_flood_version(int v) {
     g_flood_version = v;
+    return BS_OK;
+}
+
+int bs_set_front_version(int v) {
+    g_front_version = v;
     return BS_OK;
 }
 

@@ -21,6 +21,7 @@
 //   k_fragstats      per-fragment affinity sum + voxel count (warp-aggregated atomics)
 //   k_crop_*         keep/drop decision, 8/26-connected relabel of the cropped write ROI
 //   k_finalize       raster-order ids (+ block_id * prod(block_size)), uint64 output, node statistics
+#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -1275,14 +1276,19 @@ static constexpr int F2_MAXPIX = 1 << 17;
 // every tile of a batch is resident at once (no second wave) and more warps hide the load latencies.
 // SLEV (with GAVAIL): the tails of the tile's level FIFOs and a bitmap of the levels that hold entries live in shared
 // memory (levcap levels per tile), so an append costs no L2 round trip and the next level is found by bit scans.
-template <bool GAVAIL, bool SLEV>
+// FR: inputs of the fused front end (front2d.cuh): the tile's seeds are ready-made queue entries seedent[t.base + k]
+// (k < t_nseeds[tile]), its levels occupy the fixed slots [tile * levtab, tile * levtab + t_nlev[tile]).
+template <bool GAVAIL, bool SLEV, bool FR = false>
 __global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict__ tiles, int ntiles,
                                                           const uint32_t *__restrict__ lab_all, const uint16_t *__restrict__ lv16_all,
                                                           uint32_t *__restrict__ availw_all, uint32_t *__restrict__ queue,
                                                           const uint32_t *__restrict__ lvl_qstart, uint32_t *__restrict__ lvl_head,
                                                           uint32_t *__restrict__ lvl_tail, const uint32_t *__restrict__ tile_lvl,
                                                           const uint32_t *__restrict__ seedlist, const uint32_t *__restrict__ tile_seed,
-                                                          int nwords_max, int levcap, uint32_t *__restrict__ stats) {
+                                                          int nwords_max, int levcap, uint32_t *__restrict__ stats,
+                                                          const uint32_t *__restrict__ seedent = nullptr,
+                                                          const uint32_t *__restrict__ t_nlev = nullptr,
+                                                          const uint32_t *__restrict__ t_nseeds = nullptr, int levtab = 0) {
     extern __shared__ uint32_t f2_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wid = blockIdx.x * F2_WARPS + warp;
@@ -1295,9 +1301,9 @@ __global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict
     const uint16_t *lv16 = lv16_all + t.base;
     const int W = t.W, H = t.H;
     const int npix = H * W, nwords = (npix + 31) >> 5;
-    const uint32_t lo = tile_lvl[wid], hi = tile_lvl[wid + 1];
+    const uint32_t lo = FR ? (uint32_t)wid * (uint32_t)levtab : tile_lvl[wid], hi = FR ? lo + t_nlev[wid] : tile_lvl[wid + 1];
     if (lo == hi) return;
-    const uint32_t sb = tile_seed[wid], se = tile_seed[wid + 1];
+    const uint32_t sb = FR ? 0u : tile_seed[wid], se = FR ? t_nseeds[wid] : tile_seed[wid + 1];
     if (sb == se) return;
     if (!GAVAIL) {
         for (int w = lane; w < nwords; w += 32) avail[w] = availw_all[(t.base >> 5) + w];
@@ -1315,9 +1321,10 @@ __global__ void __launch_bounds__(32 * F2_WARPS) k_flood2(const Tile *__restrict
             bool v[1];
             uint32_t l[1], ent[1];
             v[0] = s0 + lane < se;
-            uint32_t px = v[0] ? seedlist[s0 + lane] : 0;
+            const uint32_t e0 = (FR && v[0]) ? seedent[t.base + s0 + lane] : 0u;
+            uint32_t px = FR ? (e0 & F2_PIXMASK) : (v[0] ? seedlist[s0 + lane] : 0);
             l[0] = v[0] ? lo + lv16[px] : 0;
-            ent[0] = v[0] ? ((lab_all[t.base + px] << 17) | px) : 0;
+            ent[0] = FR ? e0 : (v[0] ? ((lab_all[t.base + px] << 17) | px) : 0);
             if (v[0]) maxr = max(maxr, l[0]);
             warp_append<1, SLEV>(v, l, ent, queue, lvl_qstart, lvl_tail, NONE32, dummy_tail, lane, stail, snz, lo);
             __syncwarp();
@@ -1530,8 +1537,15 @@ __device__ __forceinline__ long long tile_widx(const Tile &t, int z, int y, int 
     return t.wbase + ((long long)(z - t.wz) * t.wH + (y - t.wy)) * t.wW + (x - t.wx);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) k_fragstats(const Tile *__restrict__ tiles, AffView A, const uint32_t *__restrict__ lab,
+// label planes: u32 (unfused chain; may hold claim keys / UNLAB = no fragment) or u16 (fused front end; 0 = no fragment)
+__device__ __forceinline__ uint32_t lab_get(const uint32_t *lab, long long i) {
+    const uint32_t l = lab[i];
+    return l >= CLAIM ? 0u : l;
+}
+__device__ __forceinline__ uint32_t lab_get(const uint16_t *lab, long long i) { return lab[i]; }
+
+template <typename T, typename LT>
+__global__ void __launch_bounds__(256) k_fragstats(const Tile *__restrict__ tiles, AffView A, const LT *__restrict__ lab,
                                                    const uint32_t *__restrict__ fbase, int need_stats,
                                                    typename AffOps<T>::acc_t *__restrict__ fsum, uint32_t *__restrict__ fcnt,
                                                    uint32_t *__restrict__ fmin, uint8_t *__restrict__ fflag) {
@@ -1547,8 +1561,7 @@ __global__ void __launch_bounds__(256) k_fragstats(const Tile *__restrict__ tile
         unsigned outside = 0;
         typename AffOps<T>::acc_t val = 0;
         if (i < npix) {
-            l = lab[t.base + i];
-            if (l >= CLAIM) l = 0;
+            l = lab_get(lab, t.base + i);
             if (l) {
                 // a labelled pixel is inside the mask, hence inside the volume and not masked out
                 int x, y, z;
@@ -1609,17 +1622,20 @@ __global__ void __launch_bounds__(256) k_frag_decide(const ACC *__restrict__ fsu
 // Write-ROI voxels of kept crossing fragments take part in a pixel-level union-find (cpar, tile-local indices):
 // parent = start of the voxel's row run of equal labels inside its warp chunk (pre-linked runs keep chains
 // short), NONE32 for every other write-ROI voxel.  Fragments entirely inside the write ROI stay connected.
-__global__ void __launch_bounds__(256) k_crop_init(const Tile *__restrict__ tiles, const uint32_t *__restrict__ lab,
+// xbits: one bit per write-ROI voxel (batch write order): the voxel takes part in the union-find.  Only those voxels'
+// cpar entries are ever written or read.
+template <typename LT>
+__global__ void __launch_bounds__(256) k_crop_init(const Tile *__restrict__ tiles, const LT *__restrict__ lab,
                                                    const uint32_t *__restrict__ fbase, const uint8_t *__restrict__ fflag,
-                                                   uint32_t *__restrict__ cpar) {
+                                                   uint32_t *__restrict__ cpar, uint32_t *__restrict__ xbits) {
     const Tile t = tiles[blockIdx.y];
     const int W = t.W, H = t.H;
     const long long nw = (long long)t.wD * t.wH * t.wW;
     const int lane = threadIdx.x & 31;
     const uint32_t fb = fbase[blockIdx.y];
     auto part_label = [&](long long i) -> uint32_t {
-        uint32_t l = lab[t.base + i];
-        if (l && l < CLAIM && (fflag[(size_t)fb + l - 1] & (FF_CROSS | FF_KEEP)) == (FF_CROSS | FF_KEEP)) return l;
+        uint32_t l = lab_get(lab, t.base + i);
+        if (l && (fflag[(size_t)fb + l - 1] & (FF_CROSS | FF_KEEP)) == (FF_CROSS | FF_KEEP)) return l;
         return 0;
     };
     for (long long k0 = (long long)blockIdx.x * blockDim.x; k0 < nw; k0 += (long long)gridDim.x * blockDim.x) {
@@ -1636,34 +1652,41 @@ __global__ void __launch_bounds__(256) k_crop_init(const Tile *__restrict__ tile
         if (lane == 0) ll = (l && x > 0) ? part_label(i - 1) : 0;
         bool sl = l && x > 0 && ll == l;
         unsigned startbits = __ballot_sync(FULL, l && !sl);
-        if (kk < nw) {
-            uint32_t v = NONE32;
-            if (l) {
-                unsigned m = startbits & (FULL >> (31 - lane));
-                v = m ? (uint32_t)(i - (lane - (31 - __clz(m)))) : (uint32_t)(i - lane);
-            }
-            cpar[t.base + i] = v;
+        if (kk < nw && l) {
+            unsigned m = startbits & (FULL >> (31 - lane));
+            cpar[t.base + i] = m ? (uint32_t)(i - (lane - (31 - __clz(m)))) : (uint32_t)(i - lane);
+        }
+        const unsigned part = __ballot_sync(FULL, l != 0);
+        if (lane == 0 && part) {
+            const unsigned long long w0 = (unsigned long long)(t.wbase + k0 + (threadIdx.x & ~31));
+            const unsigned sh = (unsigned)(w0 & 31);
+            atomicOr(&xbits[w0 >> 5], part << sh);
+            if (sh && (part >> (32 - sh))) atomicOr(&xbits[(w0 >> 5) + 1], part >> (32 - sh));
         }
     }
 }
 
 // union with the raster-preceding neighbours of the full (8 / 26) neighbourhood inside the write ROI that
 // carry the same label; links implied by row adjacency of equal labels are skipped
-__global__ void __launch_bounds__(256) k_crop_union(const Tile *__restrict__ tiles, const uint32_t *__restrict__ lab,
-                                                    uint32_t *__restrict__ cpar) {
+template <typename LT>
+__global__ void __launch_bounds__(256) k_crop_union(const Tile *__restrict__ tiles, const LT *__restrict__ lab,
+                                                    uint32_t *__restrict__ cpar, const uint32_t *__restrict__ xbits) {
     const Tile t = tiles[blockIdx.y];
     const int W = t.W, H = t.H;
     const long long HW = (long long)H * W;
     const long long nw = (long long)t.wD * t.wH * t.wW;
     uint32_t *pp = cpar + t.base;
-    const uint32_t *ll = lab + t.base;
+    const LT *ll = lab + t.base;
     for (long long kk = (long long)blockIdx.x * blockDim.x + threadIdx.x; kk < nw; kk += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long wq = (unsigned long long)(t.wbase + kk);
+        if (!((xbits[wq >> 5] >> (wq & 31)) & 1u)) continue;
         int x, y, z;
         unravel3f((uint32_t)kk, t.wW, t.wH, t.fwW, t.fwH, x, y, z);
         const long long i = ((long long)(z + t.wz) * H + (y + t.wy)) * W + (x + t.wx);
-        if (__ldcg(&pp[i]) == NONE32) continue;
         const uint32_t l = ll[i];
-        auto same = [&](long long j) -> bool { return ll[j] == l && __ldcg(&pp[j]) != NONE32; };
+        // every neighbour tested below lies inside the write ROI, where "same label" means "same fragment" and hence
+        // "takes part too" (crossing / kept are properties of the fragment)
+        auto same = [&](long long j) -> bool { return (uint32_t)ll[j] == l; };
         const bool left = x > 0 && same(i - 1);
         // row link across a warp-chunk boundary (inside a chunk k_crop_init linked the run already)
         if (left && (kk & 31) == 0) uf_union(pp, (uint32_t)i, (uint32_t)(i - 1));
@@ -1696,18 +1719,17 @@ __global__ void __launch_bounds__(256) k_crop_union(const Tile *__restrict__ til
 
 // one bit per write-ROI voxel (batch write order): set for the first voxel of every output fragment
 __global__ void __launch_bounds__(256) k_root_bits_pix(const Tile *__restrict__ tiles, const uint32_t *__restrict__ cpar,
-                                                       uint32_t *__restrict__ bits) {
+                                                       const uint32_t *__restrict__ xbits, uint32_t *__restrict__ bits) {
     const Tile t = tiles[blockIdx.y];
     const int W = t.W, H = t.H;
     const long long nw = (long long)t.wD * t.wH * t.wW;
     for (long long kk = (long long)blockIdx.x * blockDim.x + threadIdx.x; kk < nw; kk += (long long)gridDim.x * blockDim.x) {
+        const uint32_t w = (uint32_t)(t.wbase + kk);
+        if (!((xbits[w >> 5] >> (w & 31)) & 1u)) continue;
         int x, y, z;
         unravel3f((uint32_t)kk, t.wW, t.wH, t.fwW, t.fwH, x, y, z);
         const long long i = ((long long)(z + t.wz) * H + (y + t.wy)) * W + (x + t.wx);
-        if (cpar[t.base + i] == (uint32_t)i) {
-            const uint32_t w = (uint32_t)(t.wbase + kk);
-            atomicOr(&bits[w >> 5], 1u << (w & 31));
-        }
+        if (cpar[t.base + i] == (uint32_t)i) atomicOr(&bits[w >> 5], 1u << (w & 31));
     }
 }
 
@@ -1742,8 +1764,9 @@ __global__ void k_blk_first(const BlkDev *__restrict__ blks, int nblk, const uin
 
 // ids (raster order of each fragment's first voxel, + block_id * prod(block_size)), uint64 output, node
 // statistics.  One CTA column per tile (blockIdx.y).
+template <typename LT>
 __global__ void __launch_bounds__(256) k_finalize(const Tile *__restrict__ tiles, const BlkDev *__restrict__ blks,
-                                                  const uint32_t *__restrict__ lab, const uint32_t *__restrict__ cpar,
+                                                  const LT *__restrict__ lab, const uint32_t *__restrict__ cpar,
                                                   const uint32_t *__restrict__ fbase, const uint8_t *__restrict__ fflag,
                                                   const uint32_t *__restrict__ fmin, const uint32_t *__restrict__ bits,
                                                   const uint32_t *__restrict__ wscan, const uint32_t *__restrict__ blk_first,
@@ -1769,9 +1792,9 @@ __global__ void __launch_bounds__(256) k_finalize(const Tile *__restrict__ tiles
             unravel3f((uint32_t)kk, t.wW, t.wH, t.fwW, t.fwH, tx, ty, tz);
             const long long i = ((long long)(tz + t.wz) * H + (ty + t.wy)) * W + (tx + t.wx);
             x = tx, y = ty, z = tz + zoff;
-            uint32_t l = lab[t.base + i];
+            const uint32_t l = lab_get(lab, t.base + i);
             uint64_t id = 0;
-            if (l && l < CLAIM) {
+            if (l) {
                 const size_t fi = (size_t)fb + l - 1;
                 const uint8_t fl = fflag[fi];
                 if (fl & FF_KEEP) {
@@ -2026,78 +2049,26 @@ static int keep_debug(Plan &P, const char *name, DevBuf &buf, int elem, long lon
 extern int g_debug;
 extern int g_flood_version;
 
+#include "front2d.cuh"
+
+// what the front end (mask ... flood) leaves for the back end (fragment statistics ... ids)
+struct S1Front {
+    DevBuf lab, lv, tile_seed, totals, fstats;   // label plane, a scratch plane (cpar), fragment-table base per tile
+    size_t nseeds = 0;                           // fragment table entries (labels are ranks of seed pixels when v2)
+    bool v2 = false;
+    bool lab16 = false;                          // the label plane holds 16-bit labels (fused front end)
+};
+
+// the unfused chain: one kernel per step, every intermediate plane in HBM.  Serves 3-D tiles, shifted affinities, tiles the
+// fused front end cannot hold on chip, and debug runs (the intermediates are kept for bs_debug_fetch).
 template <typename T>
-static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64_t *frags_out, long long node_base,
-                        long long *n_new_nodes, cudaStream_t s) {
-    typedef typename AffOps<T>::acc_t acc_t;
+static int stage1_front_unfused(Plan &P, const std::vector<int> &bidx, AffView A, const std::vector<Tile> &tiles, const Tile *dt,
+                                long long P_pix, long long maxpix, dim3 grid, S1Front &F, cudaStream_t s) {
     const bs_ws_config &cfg = P.cfg;
     const bool xy = cfg.fragments_in_xy != 0;
-    // ---- tiles
-    std::vector<Tile> tiles;
-    std::vector<BlkDev> blks;
-    long long P_pix = 0, V_w = 0, maxpix = 0, maxw = 0;
-    for (size_t bi = 0; bi < bidx.size(); bi++) {
-        const Blk &b = P.blocks[bidx[bi]];
-        BlkDev bd;
-        bd.block_id = b.block_id;
-        bd.wbase = V_w;
-        for (int d = 0; d < 3; d++) bd.wo[d] = b.wo[d], bd.ws[d] = b.ws[d];
-        bd.plan_index = bidx[bi];
-        bd.pad_ = 0;
-        blks.push_back(bd);
-        long long wv = (long long)b.ws[0] * b.ws[1] * b.ws[2];
-        maxw = std::max(maxw, wv);
-        if (xy) {
-            for (int z = 0; z < b.ws[0]; z++) {
-                Tile t;
-                t.gz = b.wo[0] + z, t.gy = b.ro[1], t.gx = b.ro[2];
-                t.D = 1, t.H = b.rs[1], t.W = b.rs[2];
-                t.wz = 0, t.wy = cfg.context[1], t.wx = cfg.context[2];
-                t.wD = 1, t.wH = b.ws[1], t.wW = b.ws[2];
-                t.block = (int)bi;
-                t.ndim = 2;
-                t.base = P_pix;
-                t.wbase = V_w + (long long)z * b.ws[1] * b.ws[2];
-                long long np = (long long)t.H * t.W;
-                P_pix += (np + 31) & ~31LL;   // 32-aligned tile bases (bitmap words of flood v2)
-                maxpix = std::max(maxpix, np);
-                t.set_divs();
-                tiles.push_back(t);
-            }
-        } else {
-            Tile t;
-            t.gz = b.ro[0], t.gy = b.ro[1], t.gx = b.ro[2];
-            t.D = b.rs[0], t.H = b.rs[1], t.W = b.rs[2];
-            t.wz = cfg.context[0], t.wy = cfg.context[1], t.wx = cfg.context[2];
-            t.wD = b.ws[0], t.wH = b.ws[1], t.wW = b.ws[2];
-            t.block = (int)bi;
-            t.ndim = 3;
-            t.base = P_pix;
-            t.wbase = V_w;
-            long long np = (long long)t.D * t.H * t.W;
-            P_pix += (np + 31) & ~31LL;   // 32-aligned tile bases (16-byte label loads of flood v3)
-            maxpix = std::max(maxpix, np);
-            t.set_divs();
-                tiles.push_back(t);
-        }
-        V_w += wv;
-    }
     const int ntiles = (int)tiles.size();
-    BS_ARG(ntiles > 0 && ntiles <= 65535, "stage1: batch has too many tiles (lower max_batch_voxels)");
-    BS_ARG(P_pix < (1LL << 31) && maxpix < (1LL << 31), "stage1: batch too large for 32-bit tile indices");
-    for (auto &t : tiles) BS_ARG(t.W <= MAXW && t.W < 65535, "stage1: tile wider than 4096 voxels is not supported");
-
-    DevBuf d_tiles, d_blks;
-    BS_TRY(d_tiles.alloc(sizeof(Tile) * ntiles, s));
-    BS_TRY(d_blks.alloc(sizeof(BlkDev) * blks.size(), s));
-    BS_CUDA(cudaMemcpyAsync(d_tiles.p, tiles.data(), sizeof(Tile) * ntiles, cudaMemcpyHostToDevice, s));
-    BS_CUDA(cudaMemcpyAsync(d_blks.p, blks.data(), sizeof(BlkDev) * blks.size(), cudaMemcpyHostToDevice, s));
-    const Tile *dt = d_tiles.as<Tile>();
-
-    const unsigned gx = (unsigned)std::min<long long>(std::max<long long>((maxpix + PIX_PER_CTA - 1) / PIX_PER_CTA, 1), 2048);
-    const dim3 grid(gx, ntiles);
-
-    DevBuf msk, g, d2, tmpA, tmpB, lab, lv, sbits, swcnt, swscan, tileflags, tilemax;
+    DevBuf msk, g, d2, tmpA, tmpB, sbits, swcnt, swscan, tileflags, tilemax;
+    DevBuf &lab = F.lab, &lv = F.lv, &tile_seed = F.tile_seed, &totals = F.totals, &fstats = F.fstats;
     BS_TRY(msk.alloc(P_pix, s));
     BS_TRY(g.alloc(P_pix * 2, s));
     BS_TRY(d2.alloc(P_pix * 4, s));
@@ -2164,7 +2135,7 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     BS_LAUNCH(k_seed_union, grid, 256, 0, s, dt, lv.as<uint32_t>());
 
     // ---- histogram sizes (host sync #1: total histogram entries, number of seed pixels)
-    DevBuf hsize, hbase, totals;
+    DevBuf hsize, hbase;
     BS_TRY(hsize.alloc(4 * (ntiles + 1), s));
     BS_TRY(hbase.alloc(4 * (ntiles + 1), s));
     BS_TRY(totals.alloc_zero(4 * 8, s));
@@ -2179,12 +2150,13 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     BS_CUDA(cudaMemcpyAsync(h_tot, d_tot, 32, cudaMemcpyDeviceToHost, s));
     BS_CUDA(cudaStreamSynchronize(s));
     const size_t Htot = h_tot[0], nseeds = h_tot[1];
+    F.nseeds = nseeds;
     // flood v2 (on-chip state) needs 2-D tiles of <= 2^17 pixels, 15-bit labels and 16-bit levels
     const bool v2 = xy && g_flood_version != 1 && maxpix <= F2_MAXPIX && h_tot[5] < 32767 && h_tot[6] < 65535;
+    F.v2 = v2;
 
     g_prof.mark("s1.levels", s);
-    DevBuf hist, nz, lrank, qoff, lvl_qstart, lvl_head, lvl_tail, tile_lvl, tile_seed, seedlist, queue, fstats, tile_q, lv16,
-        availw;
+    DevBuf hist, nz, lrank, qoff, lvl_qstart, lvl_head, lvl_tail, tile_lvl, seedlist, queue, tile_q, lv16, availw;
     BS_TRY(tile_q.alloc(4 * (ntiles + 1), s));
     if (v2) {
         BS_TRY(lv16.alloc(2 * (size_t)P_pix, s));
@@ -2318,6 +2290,265 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
         keep_debug(P, "flood", c1, 4, P_pix);
         keep_debug(P, "flood_stats", fstats, 4, 4);
     }
+    return BS_OK;
+}
+
+extern int g_front_version;   // 0 = automatic, 1 = unfused chain only, 2 = fused without TMA, 3 = fused, TMA required when eligible
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn get_tmap_encode() {
+    static tmap_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (tmap_encode_fn)sym;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// The fused front end (front2d.cuh) for batches of 2-D tiles of unshifted affinities whose 16-bit planes fit one CTA's
+// shared memory.  *done = false: not eligible, or a tile overflowed one of the on-chip tables (the caller then runs the
+// unfused chain on the same batch).
+template <typename T>
+static int stage1_front_fused(Plan &P, AffView A, const std::vector<Tile> &tiles, const Tile *dt, long long P_pix, long long maxpix,
+                              S1Front &F, bool *done, cudaStream_t s) {
+    const bs_ws_config &cfg = P.cfg;
+    *done = false;
+    const int ntiles = (int)tiles.size();
+    if (!cfg.fragments_in_xy || cfg.has_bias || cfg.has_seed_eps || cfg.has_sigma || g_debug || g_front_version == 1 ||
+        g_flood_version != 0 || maxpix > F2_MAXPIX)
+        return BS_OK;
+    int maxH = 0, maxW = 0;
+    for (auto &t : tiles) maxH = std::max(maxH, t.H), maxW = std::max(maxW, t.W);
+    if (maxH > 128 * FR_MAXG || cfg.min_seed_distance > 64) return BS_OK;
+    // shared memory of one tile CTA: 16-bit plane + bitmap + scratch (seed ranks / union-find, then level tables)
+    size_t need_fixed = 0, nwords_max = 0;
+    for (auto &t : tiles) {
+        const size_t nw = (size_t)t.H * ((t.W + 31) / 32);
+        need_fixed = std::max(need_fixed, (((size_t)t.H * fr_pitch(t.W) * 2 + 15) & ~(size_t)15) + nw * 4);
+        nwords_max = std::max(nwords_max, nw);
+    }
+    if (need_fixed + 3072 + 4 * 512 > (size_t)FR_SMEM_TOTAL) return BS_OK;
+    const int scr_bytes = (int)(((size_t)FR_SMEM_TOTAL - need_fixed) & ~(size_t)15);
+    if ((size_t)scr_bytes < ((nwords_max * 2 + 15) & ~(size_t)15) + 4 * 512) return BS_OK;
+    if (scr_bytes / (2 * fr_pitch(maxW)) < cfg.min_seed_distance - 1 + 8) return BS_OK;   // rows of the maximum filter's band buffer
+    const int levtab = std::min(4096, (scr_bytes - 3072) / 4);
+
+    // ---- mask bitmap
+    g_prof.mark("s1.mask_bits", s);
+    std::vector<uint32_t> h_mbase(ntiles + 1);
+    size_t mwords = 0;
+    for (int i = 0; i < ntiles; i++) {
+        h_mbase[i] = (uint32_t)mwords;
+        mwords += (size_t)tiles[i].H * ((tiles[i].W + 31) / 32);
+    }
+    h_mbase[ntiles] = (uint32_t)mwords;
+    BS_ARG(mwords < (1ull << 32), "stage1: mask bitmap exceeds 32-bit indexing");
+    DevBuf d_amap, mbase, mbits, lv16, availw, seedent, queue, lvl_qstart, lvl_head, t_nseeds, t_nlev, t_nmask, flags;
+    BS_TRY(mbase.alloc(4 * (size_t)(ntiles + 1), s));
+    BS_CUDA(cudaMemcpyAsync(mbase.p, h_mbase.data(), 4 * (size_t)(ntiles + 1), cudaMemcpyHostToDevice, s));
+    BS_TRY(mbits.alloc(4 * mwords, s));
+    BS_TRY(lv16.alloc(2 * (size_t)P_pix + 64, s));
+    BS_TRY(availw.alloc(4 * ((size_t)P_pix / 32 + 2), s));
+    BS_TRY(seedent.alloc(4 * (size_t)P_pix, s));
+    BS_TRY(queue.alloc_fill(4 * (size_t)P_pix, 0xFF, s));
+    BS_TRY(lvl_qstart.alloc(4 * (size_t)ntiles * levtab, s));
+    BS_TRY(lvl_head.alloc(4 * (size_t)ntiles * levtab, s));
+    BS_TRY(t_nseeds.alloc_zero(4 * (size_t)(ntiles + 1), s));
+    BS_TRY(t_nlev.alloc(4 * (size_t)(ntiles + 1), s));
+    BS_TRY(t_nmask.alloc(4 * (size_t)(ntiles + 1), s));
+    BS_TRY(flags.alloc_zero(32, s));
+    BS_TRY(F.totals.alloc_zero(32, s));
+    BS_TRY(F.fstats.alloc_zero(16, s));
+    BS_TRY(F.tile_seed.alloc(4 * (size_t)(ntiles + 1), s));
+    const uint32_t *d_mbase = mbase.as<uint32_t>();
+    bool used_tma = false;
+    // TMA boxes: rows of uint32 elements, pitch = the tile width + 15 bytes of misalignment + 16 bytes for the consumer's
+    // second aligned read, rounded up to 16 bytes (box rows are dense in shared memory)
+    const int tma_pitch = ((maxW + 31) + 15) & ~15;
+    if (sizeof(T) == 1 && g_front_version != 2 && !A.mask && A.X % 16 == 0 && ((uintptr_t)A.p & 15) == 0 && tma_pitch <= 1024 &&
+        (size_t)A.Zw * A.Y * A.X < (1ull << 32)) {
+        tmap_encode_fn enc = get_tmap_encode();
+        if (enc) {
+            CUtensorMap amap;
+            const cuuint64_t gdim[4] = {(cuuint64_t)A.X / 4, (cuuint64_t)A.Y, (cuuint64_t)A.Zw, (cuuint64_t)A.C};
+            const cuuint64_t gstr[3] = {(cuuint64_t)A.X, (cuuint64_t)A.X * A.Y, (cuuint64_t)A.X * A.Y * A.Zw};
+            const cuuint32_t box[4] = {(cuuint32_t)(tma_pitch / 4), (cuuint32_t)TB_ROWS, 1, 1};
+            const cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult r = enc(&amap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void *>(A.p), gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r == CUDA_SUCCESS) {
+                // the descriptor lives in global memory (64-byte aligned), the kernel gets its address
+                BS_TRY(d_amap.alloc(sizeof(CUtensorMap) + 64, s));
+                CUtensorMap *dmap = (CUtensorMap *)(((uintptr_t)d_amap.p + 63) & ~(uintptr_t)63);
+                BS_CUDA(cudaMemcpyAsync(dmap, &amap, sizeof(CUtensorMap), cudaMemcpyHostToDevice, s));
+                BS_CUDA(cudaStreamSynchronize(s));   // amap is a host-staged copy
+                const int strips = (maxH + TB_ROWS - 1) / TB_ROWS;
+                const size_t smem = (size_t)TB_STAGES * 2 * TB_ROWS * tma_pitch;
+                const int nbricks = ntiles * strips;
+                const int grid_tma = std::min(nbricks, 148 * 4);
+                BS_CUDA(cudaFuncSetAttribute(k_mask_bits_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                BS_LAUNCH(k_mask_bits_tma, grid_tma, 256, smem, s, dmap, dt, d_mbase, ntiles, strips, A.z0, tma_pitch, mbits.as<uint32_t>());
+                used_tma = true;
+            }
+        }
+        BS_ARG(used_tma || g_front_version != 3, "stage1: the TMA mask kernel was required (front version 3) but the tensor map could not be encoded");
+    }
+    if (!used_tma) {
+        const dim3 gr((unsigned)std::min(std::max((maxH + 7) / 8, 1), 64), ntiles);
+        const dim3 gr4((unsigned)std::min(std::max((maxH + 31) / 32, 1), 16), ntiles);
+        if (sizeof(T) == 1)
+            BS_LAUNCH(k_mask_bits_u8, gr4, 256, 0, s, dt, d_mbase, A, mbits.as<uint32_t>());
+        else
+            BS_LAUNCH((k_mask_bits_generic<T>), gr, 256, 0, s, dt, d_mbase, A, mbits.as<uint32_t>());
+    }
+    // ---- the tile front end
+    g_prof.mark("s1.tile_front", s);
+    FrontOut O;
+    O.lv16 = lv16.as<uint16_t>();
+    O.availw = availw.as<uint32_t>();
+    O.seedent = seedent.as<uint32_t>();
+    O.lvl_qstart = lvl_qstart.as<uint32_t>();
+    O.lvl_head = lvl_head.as<uint32_t>();
+    O.t_nseeds = t_nseeds.as<uint32_t>();
+    O.t_nlev = t_nlev.as<uint32_t>();
+    O.t_nmask = t_nmask.as<uint32_t>();
+    O.flags = flags.as<uint32_t>();
+    O.levtab = levtab;
+    const size_t fr_smem = need_fixed + (size_t)scr_bytes;
+    BS_CUDA(cudaFuncSetAttribute(k_tile_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fr_smem));
+    BS_LAUNCH(k_tile_front, ntiles, FR_NT, fr_smem, s, dt, d_mbase, mbits.as<uint32_t>(), cfg.min_seed_distance, scr_bytes, O);
+    // fragment-table base per tile = seed pixels before the tile
+    uint32_t *d_tot = F.totals.as<uint32_t>();
+    BS_TRY(scan_exclusive_u32(t_nseeds.as<uint32_t>(), F.tile_seed.as<uint32_t>(), (size_t)ntiles + 1, d_tot + 1, s));
+    // host sync: overflow flags, total seed pixels, the largest level count of a tile
+    uint32_t h_flags[8], h_tot[8];
+    BS_CUDA(cudaMemcpyAsync(h_flags, flags.p, 32, cudaMemcpyDeviceToHost, s));
+    BS_CUDA(cudaMemcpyAsync(h_tot, d_tot, 32, cudaMemcpyDeviceToHost, s));
+    BS_CUDA(cudaStreamSynchronize(s));
+    if (h_flags[0] != 0) {
+        // a tile did not fit the on-chip tables (squared distance >= 16384, too many seed pixels or levels): unfused chain
+        F.tile_seed.release();
+        F.totals.release();
+        F.fstats.release();
+        return BS_OK;
+    }
+    F.nseeds = h_tot[1];
+    F.v2 = true;
+    // ---- flood
+    g_prof.mark("s1.flood", s);
+    {
+        const int levcap = (int)h_flags[1] + 1;
+        const size_t smem = (size_t)(F2_HASH + levcap + (levcap + 31) / 32) * 4;
+        BS_LAUNCH((k_flood2<true, true, true>), ntiles, 32, smem, s, dt, ntiles, nullptr, lv16.as<uint16_t>(), availw.as<uint32_t>(),
+                  queue.as<uint32_t>(), lvl_qstart.as<uint32_t>(), lvl_head.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, 0, levcap,
+                  F.fstats.as<uint32_t>(), seedent.as<uint32_t>(), t_nlev.as<uint32_t>(), t_nseeds.as<uint32_t>(), levtab);
+    }
+    g_prof.mark("s1.flood_scatter", s);
+    BS_TRY(F.lab.alloc(2 * (size_t)P_pix + 64, s));
+    BS_TRY(F.lv.alloc(4 * (size_t)P_pix, s));
+    F.lab16 = true;
+    {
+        const size_t scat_smem = (((size_t)maxpix + 1) / 2) * 4;
+        BS_CUDA(cudaFuncSetAttribute(k_scatter_labels_tile5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scat_smem));
+        BS_LAUNCH(k_scatter_labels_tile5, ntiles, SCAT_NT, scat_smem, s, dt, t_nmask.as<uint32_t>(), queue.as<uint32_t>(),
+                  F.lab.as<uint16_t>());
+    }
+    *done = true;
+    return BS_OK;
+}
+
+template <typename T>
+static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64_t *frags_out, long long node_base,
+                        long long *n_new_nodes, cudaStream_t s) {
+    typedef typename AffOps<T>::acc_t acc_t;
+    const bs_ws_config &cfg = P.cfg;
+    const bool xy = cfg.fragments_in_xy != 0;
+    // ---- tiles
+    std::vector<Tile> tiles;
+    std::vector<BlkDev> blks;
+    long long P_pix = 0, V_w = 0, maxpix = 0, maxw = 0;
+    for (size_t bi = 0; bi < bidx.size(); bi++) {
+        const Blk &b = P.blocks[bidx[bi]];
+        BlkDev bd;
+        bd.block_id = b.block_id;
+        bd.wbase = V_w;
+        for (int d = 0; d < 3; d++) bd.wo[d] = b.wo[d], bd.ws[d] = b.ws[d];
+        bd.plan_index = bidx[bi];
+        bd.pad_ = 0;
+        blks.push_back(bd);
+        long long wv = (long long)b.ws[0] * b.ws[1] * b.ws[2];
+        maxw = std::max(maxw, wv);
+        if (xy) {
+            for (int z = 0; z < b.ws[0]; z++) {
+                Tile t;
+                t.gz = b.wo[0] + z, t.gy = b.ro[1], t.gx = b.ro[2];
+                t.D = 1, t.H = b.rs[1], t.W = b.rs[2];
+                t.wz = 0, t.wy = cfg.context[1], t.wx = cfg.context[2];
+                t.wD = 1, t.wH = b.ws[1], t.wW = b.ws[2];
+                t.block = (int)bi;
+                t.ndim = 2;
+                t.base = P_pix;
+                t.wbase = V_w + (long long)z * b.ws[1] * b.ws[2];
+                long long np = (long long)t.H * t.W;
+                P_pix += (np + 31) & ~31LL;   // 32-aligned tile bases (bitmap words of flood v2)
+                maxpix = std::max(maxpix, np);
+                t.set_divs();
+                tiles.push_back(t);
+            }
+        } else {
+            Tile t;
+            t.gz = b.ro[0], t.gy = b.ro[1], t.gx = b.ro[2];
+            t.D = b.rs[0], t.H = b.rs[1], t.W = b.rs[2];
+            t.wz = cfg.context[0], t.wy = cfg.context[1], t.wx = cfg.context[2];
+            t.wD = b.ws[0], t.wH = b.ws[1], t.wW = b.ws[2];
+            t.block = (int)bi;
+            t.ndim = 3;
+            t.base = P_pix;
+            t.wbase = V_w;
+            long long np = (long long)t.D * t.H * t.W;
+            P_pix += (np + 31) & ~31LL;   // 32-aligned tile bases (16-byte label loads of flood v3)
+            maxpix = std::max(maxpix, np);
+            t.set_divs();
+                tiles.push_back(t);
+        }
+        V_w += wv;
+    }
+    const int ntiles = (int)tiles.size();
+    BS_ARG(ntiles > 0 && ntiles <= 65535, "stage1: batch has too many tiles (lower max_batch_voxels)");
+    BS_ARG(P_pix < (1LL << 31) && maxpix < (1LL << 31), "stage1: batch too large for 32-bit tile indices");
+    for (auto &t : tiles) BS_ARG(t.W <= MAXW && t.W < 65535, "stage1: tile wider than 4096 voxels is not supported");
+
+    DevBuf d_tiles, d_blks;
+    BS_TRY(d_tiles.alloc(sizeof(Tile) * ntiles, s));
+    BS_TRY(d_blks.alloc(sizeof(BlkDev) * blks.size(), s));
+    BS_CUDA(cudaMemcpyAsync(d_tiles.p, tiles.data(), sizeof(Tile) * ntiles, cudaMemcpyHostToDevice, s));
+    BS_CUDA(cudaMemcpyAsync(d_blks.p, blks.data(), sizeof(BlkDev) * blks.size(), cudaMemcpyHostToDevice, s));
+    const Tile *dt = d_tiles.as<Tile>();
+
+    const unsigned gx = (unsigned)std::min<long long>(std::max<long long>((maxpix + PIX_PER_CTA - 1) / PIX_PER_CTA, 1), 2048);
+    const dim3 grid(gx, ntiles);
+
+    S1Front F;
+    bool front_done = false;
+    BS_TRY((stage1_front_fused<T>(P, A, tiles, dt, P_pix, maxpix, F, &front_done, s)));
+    if (!front_done) BS_TRY((stage1_front_unfused<T>(P, bidx, A, tiles, dt, P_pix, maxpix, grid, F, s)));
+    DevBuf &lab = F.lab, &lv = F.lv, &tile_seed = F.tile_seed, &totals = F.totals;
+    uint32_t *d_tot = totals.as<uint32_t>();
+    uint32_t h_tot[8];
+    const size_t nseeds = F.nseeds;
+    const bool v2 = F.v2;
+
 
     // ---- fragment statistics, keep/drop, crop relabel
     g_prof.mark("s1.fragstats", s);
@@ -2338,8 +2569,13 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     BS_TRY(fcnt.alloc_zero(nF * 4, s));
     BS_TRY(fmin.alloc_fill(nF * 4, 0xFF, s));
     BS_TRY(fflag.alloc_zero(nF, s));
-    BS_LAUNCH((k_fragstats<T>), grid, 256, 0, s, dt, A, lab.as<uint32_t>(), d_fbase, need_stats ? 1 : 0, fsum.as<acc_t>(),
-              fcnt.as<uint32_t>(), fmin.as<uint32_t>(), fflag.as<uint8_t>());
+    const bool lab16 = F.lab16;
+    if (lab16)
+        BS_LAUNCH((k_fragstats<T, uint16_t>), grid, 256, 0, s, dt, A, lab.as<uint16_t>(), d_fbase, need_stats ? 1 : 0, fsum.as<acc_t>(),
+                  fcnt.as<uint32_t>(), fmin.as<uint32_t>(), fflag.as<uint8_t>());
+    else
+        BS_LAUNCH((k_fragstats<T, uint32_t>), grid, 256, 0, s, dt, A, lab.as<uint32_t>(), d_fbase, need_stats ? 1 : 0, fsum.as<acc_t>(),
+                  fcnt.as<uint32_t>(), fmin.as<uint32_t>(), fflag.as<uint8_t>());
     BS_LAUNCH((k_frag_decide<acc_t>), cdiv(nF, 256), 256, 0, s, fsum.as<acc_t>(), fcnt.as<uint32_t>(), fflag.as<uint8_t>(), nF,
               need_stats ? cfg.filter_fragments : 0.0, need_stats ? cfg.remove_debris : 0, sizeof(T) == 1 ? 1 : 0);
     g_prof.mark("s1.crop_cc", s);
@@ -2349,13 +2585,20 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     const dim3 gridw((unsigned)std::min<long long>(std::max<long long>((maxwt + 1023) / 1024, 1), 2048), ntiles);
     const dim3 gridf((unsigned)std::min<long long>(std::max<long long>((maxwt + PIX_PER_CTA - 1) / PIX_PER_CTA, 1), 2048), ntiles);
     // cpar reuses lv
-    BS_LAUNCH(k_crop_init, gridw, 256, 0, s, dt, lab.as<uint32_t>(), d_fbase, fflag.as<uint8_t>(), lv.as<uint32_t>());
-    BS_LAUNCH(k_crop_union, gridw, 256, 0, s, dt, lab.as<uint32_t>(), lv.as<uint32_t>());
     const size_t nwords = ((size_t)V_w + 31) / 32 + 1;
+    DevBuf xbits;
+    BS_TRY(xbits.alloc_zero(4 * (nwords + 1), s));
+    if (lab16) {
+        BS_LAUNCH(k_crop_init<uint16_t>, gridw, 256, 0, s, dt, lab.as<uint16_t>(), d_fbase, fflag.as<uint8_t>(), lv.as<uint32_t>(), xbits.as<uint32_t>());
+        BS_LAUNCH(k_crop_union<uint16_t>, gridw, 256, 0, s, dt, lab.as<uint16_t>(), lv.as<uint32_t>(), xbits.as<uint32_t>());
+    } else {
+        BS_LAUNCH(k_crop_init<uint32_t>, gridw, 256, 0, s, dt, lab.as<uint32_t>(), d_fbase, fflag.as<uint8_t>(), lv.as<uint32_t>(), xbits.as<uint32_t>());
+        BS_LAUNCH(k_crop_union<uint32_t>, gridw, 256, 0, s, dt, lab.as<uint32_t>(), lv.as<uint32_t>(), xbits.as<uint32_t>());
+    }
     BS_TRY(bits.alloc_zero(4 * nwords, s));
     BS_TRY(wcnt.alloc(4 * nwords, s));
     BS_TRY(wscan.alloc(4 * nwords, s));
-    BS_LAUNCH(k_root_bits_pix, gridw, 256, 0, s, dt, lv.as<uint32_t>(), bits.as<uint32_t>());
+    BS_LAUNCH(k_root_bits_pix, gridw, 256, 0, s, dt, lv.as<uint32_t>(), xbits.as<uint32_t>(), bits.as<uint32_t>());
     BS_LAUNCH(k_root_bits_frag, cdiv(nF, 256), 256, 0, s, fcnt.as<uint32_t>(), fflag.as<uint8_t>(), fmin.as<uint32_t>(), nF,
               bits.as<uint32_t>());
     BS_LAUNCH(k_popc_words, cdiv(nwords, 256), 256, 0, s, bits.as<uint32_t>(), wcnt.as<uint32_t>(), nwords);
@@ -2373,10 +2616,16 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     BS_TRY(blk_first.alloc(4 * blks.size(), s));
     BS_LAUNCH(k_blk_first, cdiv(blks.size(), 256), 256, 0, s, d_blks.as<BlkDev>(), (int)blks.size(), bits.as<uint32_t>(),
               wscan.as<uint32_t>(), blk_first.as<uint32_t>());
-    BS_LAUNCH(k_finalize, gridf, 256, 0, s, dt, d_blks.as<BlkDev>(), lab.as<uint32_t>(), lv.as<uint32_t>(), d_fbase,
-              fflag.as<uint8_t>(), fmin.as<uint32_t>(), bits.as<uint32_t>(), wscan.as<uint32_t>(), blk_first.as<uint32_t>(),
-              P.nvox_block, cfg.roi_offset[0] + (cfg.win_z > 0 ? cfg.win_z0 : 0), cfg.roi_offset[1], cfg.roi_offset[2],
-              cfg.roi_shape[1], cfg.roi_shape[2], frags_out, ncnt.as<uint32_t>(), nsum.as<unsigned long long>());
+#define BS_FINALIZE(LT_)                                                                                                              \
+    BS_LAUNCH(k_finalize<LT_>, gridf, 256, 0, s, dt, d_blks.as<BlkDev>(), lab.as<LT_>(), lv.as<uint32_t>(), d_fbase,                   \
+              fflag.as<uint8_t>(), fmin.as<uint32_t>(), bits.as<uint32_t>(), wscan.as<uint32_t>(), blk_first.as<uint32_t>(),           \
+              P.nvox_block, cfg.roi_offset[0] + (cfg.win_z > 0 ? cfg.win_z0 : 0), cfg.roi_offset[1], cfg.roi_offset[2],                 \
+              cfg.roi_shape[1], cfg.roi_shape[2], frags_out, ncnt.as<uint32_t>(), nsum.as<unsigned long long>())
+    if (lab16)
+        BS_FINALIZE(uint16_t);
+    else
+        BS_FINALIZE(uint32_t);
+#undef BS_FINALIZE
     // ---- grow the plan's node table
     {
         DevBuf nid, npos, nsz;

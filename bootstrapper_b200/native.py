@@ -56,7 +56,7 @@ EXPORTS = [
     "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_plan_node_ids", "bs_stage2_agglomerate", "bs_stage2_num_edges",
     "bs_stage2_get_edges", "bs_waterz_segment", "bs_cc_affs", "bs_aff_errors", "bs_label_stats", "bs_shift_affinities", "bs_connected_components", "bs_stage3_components", "bs_relabel", "bs_stage3_relabel", "bs_watershed_from_affinities",
     "bs_synth_affs", "bs_debug_fetch", "bs_set_debug", "bs_set_profiling", "bs_get_profile",
-    "bs_release_scratch", "bs_set_flood_version", "bs_set_agglom_version", "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
+    "bs_release_scratch", "bs_set_flood_version", "bs_set_front_version", "bs_set_agglom_version", "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
 ]
 
 _lib = None
@@ -80,6 +80,8 @@ def lib():
         # kernel-variant switches for experiments (see include/bsnative.h)
         if os.environ.get("BS_FLOOD_VERSION"):
             _lib.bs_set_flood_version(C.c_int(int(os.environ["BS_FLOOD_VERSION"])))
+        if os.environ.get("BS_FRONT_VERSION"):
+            _lib.bs_set_front_version(C.c_int(int(os.environ["BS_FRONT_VERSION"])))
         if os.environ.get("BS_AGGLOM_VERSION"):
             _lib.bs_set_agglom_version(C.c_int(int(os.environ["BS_AGGLOM_VERSION"])))
     return _lib
@@ -122,6 +124,10 @@ def set_debug(on):
 
 def set_flood_version(v):
     _check(lib().bs_set_flood_version(C.c_int(int(v))))
+
+
+def set_front_version(v):
+    _check(lib().bs_set_front_version(C.c_int(int(v))))
 
 
 def set_agglom_version(v):

@@ -131,6 +131,9 @@ class HostRing:
         self.slots = [torch.empty((self.planes, Y, X), dtype=torch.int64, pin_memory=True) for _ in range(self.n_slots)]
         self.pinned_bytes = self.n_slots * self.planes * Y * X * 8
         self.pending = [None] * self.n_slots       # (cuda event of the copy into the slot, (name, z0, z1))
+        device = torch.device(device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         self.device = device
         self.stream = torch.cuda.Stream(device=device)
         self.sink = sink
@@ -150,8 +153,21 @@ class HostRing:
             self.pending[k] = None
             self.chunks_done += 1
 
+    def wait(self, issued):
+        """block until the downloader has issued every chunk of a submitted array; a dead downloader raises instead of
+        hanging the caller"""
+        while not issued["flag"].wait(0.5):
+            if self.error is not None or not self.thread.is_alive():
+                raise RuntimeError(f"HostRing downloader stopped: {self.error!r}")
+        if self.error is not None:
+            raise RuntimeError(f"HostRing downloader failed: {self.error!r}")
+
     def _loop(self):
-        torch.cuda.set_device(self.device)
+        try:
+            torch.cuda.set_device(self.device)
+        except Exception as e:  # noqa: BLE001
+            self.error = e
+            return
         while True:
             job = self.q.get()
             if job is None:
@@ -192,9 +208,7 @@ class HostRing:
         """wait until every queued array has landed and been handed to the sink"""
         issued = {"flag": threading.Event(), "event": None}
         self.q.put(("flush", None, None, None, issued))
-        issued["flag"].wait()
-        if self.error is not None:
-            raise self.error
+        self.wait(issued)
 
     def close(self):
         self.flush()
@@ -311,7 +325,7 @@ class ShardedSegmenter:
         busy = [f[0] for f in self._inflight if key is not None and f[3] == key]
         out_ready = busy[-1] if busy else None
         if isinstance(out_ready, dict):          # ring handle: the downloader thread records the event
-            out_ready["flag"].wait()
+            ring.wait(out_ready)
             out_ready = out_ready["event"]
         self._ring = ring
         r = self.run(affs, out=out, frag_sink=host_out[0] if ring is None else ring, out_ready=out_ready)
@@ -333,10 +347,9 @@ class ShardedSegmenter:
             self._wait_done(self._inflight.pop(0)[0])
         return r
 
-    @staticmethod
-    def _wait_done(done):
+    def _wait_done(self, done):
         if isinstance(done, dict):
-            done["flag"].wait()
+            self._ring.wait(done)
             if done["event"] is not None:
                 done["event"].synchronize()
         elif done is not None:

@@ -234,6 +234,10 @@ int bs_set_debug(int on);
  * global-memory flood (v1) everywhere, 2 = v2 with the tile bitmap in shared memory, 3 = v2 with the tile bitmap in
  * global memory (every tile resident at once), 4 = 3 + level tails in shared memory */
 int bs_set_flood_version(int v);
+/* stage-1 front end (mask ... priority levels): 0 = automatic (the fused on-chip kernels for 2-D tiles of unshifted affinities
+ * that fit one CTA's shared memory, else the unfused chain), 1 = unfused chain, 2 = fused with vector loads only,
+ * 3 = fused, the TMA mask kernel required where the affinity rows are 16-byte aligned */
+int bs_set_front_version(int v);
 /* agglomeration kernel: 0 = automatic (parallel merges; shared memory when a block's graph fits, else a global slab),
  * 1 = single warp on global slabs, 2 = single warp in shared memory, 3 = parallel merges on global slabs (queue bins,
  * parents and stamps in shared memory), 4 = parallel merges with every array in the global slab */

@@ -181,9 +181,10 @@ def test_waterz_pipeline_files_offset_roi_mask(tmp_path):
         name = build_name(dict(segment.DEFAULTS["ws"], thresholds=None, threshold=thr))
         seg = zarrio.open_ds(os.path.join(store, "post/segmentations", name))
         assert np.array_equal(seg.read(), ref["segs"][thr]["seg"])
-    # a mask with a different voxel size is refused (no silent misalignment)
+    # a mask with a different voxel size is refused (no silent misalignment): the task fails, run_volara_task reports it as
+    # the reference's check_task_states does (blockwise.py:15-22)
     zarrio.prepare_ds(os.path.join(store, "mask2"), mshape, moff, (40, 8, 8), np.uint8, chunk_shape=(5, 70, 75)).write(mask)
     cfg["mask_dataset"] = os.path.join(store, "mask2")
     p.write_text(toml.dumps(cfg))
-    with pytest.raises(ValueError):
+    with pytest.raises(RuntimeError):
         segment.run_segmentation(str(p), "ws")

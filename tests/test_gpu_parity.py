@@ -147,6 +147,70 @@ def test_edt_and_flood_intermediates():
         assert len(np.unique(pairs[:, 0])) == len(pairs) == len(np.unique(pairs[:, 1]))
 
 
+FRONT_CASES = [
+    # shape, block, context, params, dtype, with volume mask
+    ((12, 120, 120), (6, 60, 60), (1, 8, 8), {}, np.uint8, False),
+    ((12, 128, 160), (6, 64, 80), (1, 8, 8), {}, np.uint8, False),                 # rows 16-byte aligned: the TMA mask kernel
+    ((9, 131, 173), (5, 64, 64), (1, 8, 8), {"min_seed_distance": 4}, np.uint8, False),   # ragged blocks, odd sizes
+    ((8, 96, 112), (4, 48, 56), (1, 6, 6), {"min_seed_distance": 13, "filter_fragments": 0.0, "remove_debris": 0}, np.uint8, True),
+    ((10, 100, 100), (5, 50, 50), (1, 6, 6), {}, np.float32, False),
+    ((4, 400, 330), (2, 400, 330), (0, 0, 0), {}, np.uint8, False),               # one large tile per slice (>= 2^17 pixels: unfused only)
+    ((4, 300, 320), (2, 300, 320), (0, 0, 0), {}, np.uint8, False),               # one tile per slice, near the shared-memory limit
+]
+
+
+@pytest.mark.parametrize("shape,block,ctx,params,dtype,use_mask", FRONT_CASES)
+def test_front_versions_agree(shape, block, ctx, params, dtype, use_mask):
+    """the fused stage-1 front end (mask bits -> on-chip EDT / seeds / levels -> flood on packed records; vector-load and
+    TMA variants) gives the unfused chain's fragments, nodes, edges and segmentations bit for bit -- and the oracle's"""
+    from bootstrapper_b200 import native
+    from bootstrapper_b200.synth import synth_affs
+    affs = synth_affs(shape, seed=11, dtype=dtype)
+    mask = None
+    if use_mask:
+        mask = np.ones(shape, np.uint8)
+        mask[:, 30:50, 20:70] = 0
+        mask[2] = 0
+    res = {}
+    for fv in (1, 0, 2, 3):
+        try:
+            native.set_front_version(fv)
+            res[fv] = _run_gpu(affs, params, block, ctx, mask_np=mask)
+        finally:
+            native.set_front_version(0)
+    _check(res[1], _oracle(affs, params, block, ctx, mask=mask))
+    for fv in (0, 2, 3):
+        assert torch.equal(res[fv]["fragments"], res[1]["fragments"]), f"front version {fv}: fragments"
+        for a, b in zip(res[fv]["nodes"], res[1]["nodes"]):
+            assert torch.equal(a, b)
+        assert all(torch.equal(a, b) for a, b in zip(res[fv]["edges"][:2], res[1]["edges"][:2]))
+        assert torch.equal(res[fv]["edges"][2].view(torch.int32), res[1]["edges"][2].view(torch.int32))
+        for thr in res[1]["segs"]:
+            assert torch.equal(res[fv]["segs"][thr], res[1]["segs"][thr])
+
+
+def test_front_saturated_tiles():
+    """all-foreground tiles (scipy's background-at-(-1, 0) rule, squared distances beyond the fused path's 16-bit planes)
+    and empty tiles take the same results through the automatic front-end choice as through the unfused chain"""
+    from bootstrapper_b200 import native
+    p = {"filter_fragments": 0.0, "remove_debris": 0}
+    full = np.full((3, 4, 200, 200), 255, np.uint8)           # d2 up to 200^2 + 200^2: overflows the fused tables -> falls back
+    full[:, 1] = 0                                            # an empty slice
+    full[:, 2, :, 100:] = 0                                   # half a slice: d2 up to 100^2 fits
+    out = {}
+    for fv in (1, 0):
+        try:
+            native.set_front_version(fv)
+            out[fv] = _run_gpu(full, p, (2, 200, 200), (0, 0, 0))
+        finally:
+            native.set_front_version(0)
+    assert torch.equal(out[0]["fragments"], out[1]["fragments"])
+    _check(out[0], _oracle(full, p, (2, 200, 200), (0, 0, 0)))
+    half = full[:, 2:3].copy()
+    r = _run_gpu(half, p, (1, 200, 200), (0, 0, 0))          # every tile fits: the fused path itself
+    _check(r, _oracle(half, p, (1, 200, 200), (0, 0, 0)))
+
+
 def test_flood_versions_agree():
     """the flood kernels (1: global-memory v1, 2: v2 with the bitmap in shared memory, 3: v2 with the bitmap in global
     memory, 4: 3 + level tails in shared memory, 0: automatic choice) are the same function"""
