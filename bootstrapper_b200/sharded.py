@@ -87,25 +87,41 @@ def allgather_counts(counts, world, device, group=None):
     return t.cpu().numpy()
 
 
-def allgather_edges(u, v, s, world, group=None):
-    """variable-size all-gather of the owned edges (size exchange + padded all_gather)"""
+def allgather_edges(u, v, s, world, group=None, state=None):
+    """variable-size all-gather of the owned edges in ONE collective: every rank contributes a fixed-capacity record
+    [n, u[0..n), v[0..n), score bits[0..n)] (int64 words) to all_gather_into_tensor; the edge count travels in the record's
+    header, so no separate size exchange is needed.  The capacity is remembered in `state` (a dict the caller keeps between
+    calls) and grown -- with one extra round -- when some rank's edges do not fit."""
     if world == 1:
         return u, v, s
-    n = torch.tensor([u.numel()], dtype=torch.int64, device=u.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(x.item()) for x in sizes]
-    m = max(max(sizes), 1)
-    pack = torch.zeros((3, m), dtype=torch.int64, device=u.device)
-    pack[0, :u.numel()] = u
-    pack[1, :u.numel()] = v
-    pack[2, :u.numel()] = s.view(torch.int32).to(torch.int64)
-    out = [torch.empty_like(pack) for _ in range(world)]
-    dist.all_gather(out, pack, group=group)
-    U = torch.cat([o[0, :k] for o, k in zip(out, sizes)])
-    V = torch.cat([o[1, :k] for o, k in zip(out, sizes)])
-    S = torch.cat([o[2, :k] for o, k in zip(out, sizes)]).to(torch.int32).view(torch.float32)
-    return U, V, S
+    state = state if state is not None else {}
+    n = u.numel()
+    dev = u.device
+    while True:
+        cap = int(state.get("cap", 0))
+        if cap == 0:
+            # first call: agree on a capacity
+            t = torch.tensor([n], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            cap = int(t.item()) * 5 // 4 + 1024
+            state["cap"] = cap
+        rec = torch.empty(1 + 3 * cap, dtype=torch.int64, device=dev)
+        k = min(n, cap)
+        rec[0] = n
+        rec[1:1 + k] = u[:k]
+        rec[1 + cap:1 + cap + k] = v[:k]
+        rec[1 + 2 * cap:1 + 2 * cap + k] = s[:k].view(torch.int32).to(torch.int64)
+        out = torch.empty(world * (1 + 3 * cap), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(out, rec, group=group)
+        out = out.view(world, 1 + 3 * cap)
+        sizes = out[:, 0].cpu().tolist()
+        if max(sizes) > cap:                 # somebody overflowed: every rank sees it, grow and repeat
+            state["cap"] = max(sizes) * 5 // 4 + 1024
+            continue
+        U = torch.cat([out[r, 1:1 + sizes[r]] for r in range(world)])
+        V = torch.cat([out[r, 1 + cap:1 + cap + sizes[r]] for r in range(world)])
+        S = torch.cat([out[r, 1 + 2 * cap:1 + 2 * cap + sizes[r]] for r in range(world)]).to(torch.int32).view(torch.float32)
+        return U, V, S
 
 
 def global_node_ids(block_ids, counts, nvox_block, device):
@@ -232,6 +248,7 @@ class ShardedSegmenter:
         self.nvox_block = int(np.prod(self.block_size))
         self.plan = None
         self._copy_stream = None
+        self._edge_state = {}
         self._inflight = []
         self.last_profile = {}
 
@@ -286,7 +303,7 @@ class ShardedSegmenter:
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         evs[0].record()
         eu, ev, es = plan.edges(affs_win.device)
-        eu, ev, es = allgather_edges(eu, ev, es, self.world, self.group)
+        eu, ev, es = allgather_edges(eu, ev, es, self.world, self.group, self._edge_state)
         nodes = plan.node_ids(affs_win.device)
         own = frags[g["z0"] - g["w0"]:g["z1"] - g["w0"]]
         thrs = list(self.p["thresholds"])

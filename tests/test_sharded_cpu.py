@@ -55,9 +55,22 @@ def _worker(rank, world, port, shape, block, ctx, frags_ref, edges_ref, owner_ra
         u = torch.tensor([edges_ref[i][0] for i in mine], dtype=torch.int64)
         v = torch.tensor([edges_ref[i][1] for i in mine], dtype=torch.int64)
         s = torch.tensor([edges_ref[i][2] for i in mine], dtype=torch.float32)
-        U, V, S = sharded.allgather_edges(u, v, s, world)
+        state = {}
+        U, V, S = sharded.allgather_edges(u, v, s, world, state=state)
         got = sorted(zip(U.tolist(), V.tolist(), [x if x == x else None for x in S.tolist()]), key=lambda t: t[:2])
         want = sorted([(a, b, None if c != c else float(np.float32(c))) for a, b, c in edges_ref], key=lambda t: t[:2])
+        # the remembered capacity serves the next call without a size exchange; a rank whose edges outgrow it (here: every
+        # edge three times over) makes all ranks grow the capacity and repeat
+        cap0 = state["cap"]
+        U2, V2, S2 = sharded.allgather_edges(u, v, s, world, state=state)
+        ok_again = U2.tolist() == U.tolist() and state["cap"] == cap0
+        state["cap"] = max(1, u.numel() // 2) if rank == 0 else state["cap"]
+        caps = torch.tensor([state["cap"]], dtype=torch.int64)
+        dist.all_reduce(caps, op=dist.ReduceOp.MIN)
+        state["cap"] = int(caps.item())
+        U3, V3, S3 = sharded.allgather_edges(u, v, s, world, state=state)
+        ok_grow = U3.tolist() == U.tolist() and V3.tolist() == V.tolist() and state["cap"] > int(caps.item())
+        assert ok_again and ok_grow
         counts = np.zeros(4, np.int64)
         counts[rank] = rank + 1
         tot = sharded.allgather_counts(counts, world, "cpu")
