@@ -358,44 +358,52 @@ __global__ void __launch_bounds__(FR_NT, 1) k_tile_front(const Tile *__restrict_
     uint16_t *D = (uint16_t *)fr_smem;                                    // [H][Wp] row distance, then squared EDT
     uint32_t *B = (uint32_t *)(fr_smem + (((size_t)H * Wp * 2 + 15) & ~(size_t)15));   // [H][WW] mask bits, then seed bits
     uint8_t *SCR = (uint8_t *)(B + nwords);
+    // the last 3 KB of the scratch area live through all phases: bitmap of the d2 values present in the mask (filled by the
+    // column pass) and its prefix popcounts; the rest is phase-local (maximum-filter band, seed ranks / union-find, level counts)
+    const int scr_work = scr_bytes - 3072;
+    uint32_t *pres = (uint32_t *)(SCR + scr_work);              // [512] bitmap of the d2 values present
+    uint16_t *ppre = (uint16_t *)(SCR + scr_work + 2048);       // [512] values present before the word
+    for (int i = tid; i < 512; i += FR_NT) pres[i] = 0;
     if (tid == 0) s_flags = 0, s_tmax = 0;
     // ---- P0: mask bits; the pad columns of D stay 0 (= outside the mask) throughout
     for (int i = tid; i < nwords; i += FR_NT) B[i] = mbits[(size_t)mbase[blockIdx.x] + i];
     for (int i = tid; i < H * (Wp - W); i += FR_NT) D[(i / (Wp - W)) * Wp + W + i % (Wp - W)] = 0;
     __syncthreads();
-    // ---- P1: distance to the nearest background pixel along x (GINF: none in the row)
+    // ---- P1: distance to the nearest background pixel along x (GINF: none in the row).  Lane c first holds word c of the
+    //          row (W <= 1024): the last background pixel before each word / the first after it follow from a prefix
+    //          maximum / suffix minimum over the lanes, then every pixel needs its own word and those two positions
     for (int y = warp; y < H; y += FR_NT / 32) {
         const uint32_t *row = B + y * WW;
+        uint32_t myw = 0;
+        if (lane < WW) {
+            const int rem = W - lane * 32;
+            myw = ~row[lane] & (rem >= 32 ? FULL : ((1u << rem) - 1u));     // background bits
+        }
+        // position + 1 of the last background pixel in words <= lane (0: none); first in words >= lane (0x7FFFFFFF: none)
+        int last = myw ? lane * 32 + 32 - __clz(myw) : 0;
+        int first = myw ? lane * 32 + __ffs(myw) - 1 : 0x7FFFFFFF;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync(FULL, last, o), bq = __shfl_down_sync(FULL, first, o);
+            if (lane >= o) last = max(last, a);
+            if (lane + o < 32) first = min(first, bq);
+        }
+        int last_prev = __shfl_up_sync(FULL, last, 1), first_next = __shfl_down_sync(FULL, first, 1);
+        if (lane == 0) last_prev = 0;
+        if (lane == 31) first_next = 0x7FFFFFFF;
         for (int c = 0; c < WW; c++) {
             const int x = c * 32 + lane;
+            const uint32_t word = __shfl_sync(FULL, myw, c);
+            const int lp = __shfl_sync(FULL, last_prev, c), fn = __shfl_sync(FULL, first_next, c);
             if (x < W) {
-                const int rem = W - c * 32;
-                const uint32_t valid = rem >= 32 ? FULL : ((1u << rem) - 1u);
-                const uint32_t word = ~row[c] & valid;     // background bits
-                uint32_t dist;
-                if ((word >> lane) & 1u) {
-                    dist = 0;
-                } else {
-                    uint32_t dl = GINF, dr = GINF;
-                    uint32_t wl = word & ((1u << lane) - 1u);
-                    for (int ww = c;;) {
-                        if (wl) {
-                            dl = x - (ww * 32 + 31 - __clz(wl));
-                            break;
-                        }
-                        if (--ww < 0) break;
-                        wl = ~row[ww];                     // words left of the last one are full
-                    }
-                    uint32_t wr = word & ~((2u << lane) - 1u);
-                    for (int ww = c;;) {
-                        if (wr) {
-                            dr = (ww * 32 + __ffs(wr) - 1) - x;
-                            break;
-                        }
-                        if (++ww >= WW) break;
-                        const int rem2 = W - ww * 32;
-                        wr = ~row[ww] & (rem2 >= 32 ? FULL : ((1u << rem2) - 1u));
-                    }
+                uint32_t dist = 0;
+                if (!((word >> lane) & 1u)) {
+                    const uint32_t wl = word & ((1u << lane) - 1u);
+                    const uint32_t wr = word & ~((2u << lane) - 1u);
+                    const int pl = wl ? c * 32 + 32 - __clz(wl) : lp;                 // position + 1, 0: none
+                    const int pr = wr ? c * 32 + __ffs(wr) - 1 : fn;                  // position, 0x7FFFFFFF: none
+                    const uint32_t dl = pl ? (uint32_t)(x - (pl - 1)) : (uint32_t)GINF;
+                    const uint32_t dr = pr != 0x7FFFFFFF ? (uint32_t)(pr - x) : (uint32_t)GINF;
                     dist = min(dl, dr);
                 }
                 D[y * Wp + x] = (uint16_t)dist;
@@ -477,7 +485,10 @@ __global__ void __launch_bounds__(FR_NT, 1) k_tile_front(const Tile *__restrict_
                         const int y = grp * 4 + j;
                         if (y < H) {
                             const uint32_t v = res[gi][j];
-                            if (v >= FR_D2CAP) myflags |= FR_OVF_D2;
+                            if (v >= FR_D2CAP)
+                                myflags |= FR_OVF_D2;
+                            else if (v && !((pres[v >> 5] >> (v & 31)) & 1u))
+                                atomicOr(&pres[v >> 5], 1u << (v & 31));
                             mymax = max(mymax, v);
                             D[y * Wp + x] = (uint16_t)min(v, 65535u);
                         }
@@ -501,7 +512,7 @@ __global__ void __launch_bounds__(FR_NT, 1) k_tile_front(const Tile *__restrict_
     {
         const int lo = msd / 2;
         uint16_t *R = (uint16_t *)SCR;
-        const int rows_fit = scr_bytes / (2 * Wp);
+        const int rows_fit = scr_work / (2 * Wp);
         const int RB = ((rows_fit - (msd - 1)) / 8) * 8;           // rows per band (the host guarantees RB >= 8)
         for (int yb = 0; yb < H; yb += RB) {
             const int nb = min(RB, H - yb), nrows = nb + msd - 1;
@@ -592,7 +603,7 @@ __global__ void __launch_bounds__(FR_NT, 1) k_tile_front(const Tile *__restrict_
     // ---- P4: raster ranks of the seed pixels
     uint16_t *wpre = (uint16_t *)SCR;                                             // [nwords] seeds before the word
     uint32_t *par = (uint32_t *)(SCR + (((size_t)nwords * 2 + 15) & ~(size_t)15));   // [seedcap] union-find over seed ranks
-    const int seedcap = (int)((scr_bytes - (((size_t)nwords * 2 + 15) & ~(size_t)15)) / 4);
+    const int seedcap = (int)((scr_work - (((size_t)nwords * 2 + 15) & ~(size_t)15)) / 4);
     uint32_t nseeds = 0;
     {
         const int per = (nwords + FR_NT - 1) / FR_NT;
@@ -653,19 +664,10 @@ __global__ void __launch_bounds__(FR_NT, 1) k_tile_front(const Tile *__restrict_
     }
     __syncthreads();
     // ---- P6: dense priority levels (rank of d2 among the values present in the mask), per-level counts -> FIFO segments
-    uint32_t *pres = (uint32_t *)SCR;                       // [512] bitmap of the d2 values present
-    uint16_t *ppre = (uint16_t *)(SCR + 2048);              // [512] values present before the word
-    uint32_t *cnt = (uint32_t *)(SCR + 3072);               // [levcap] mask pixels per level
-    const int levcap = (scr_bytes - 3072) / 4;
-    for (int i = tid; i < 512; i += FR_NT) pres[i] = 0;
+    uint32_t *cnt = (uint32_t *)SCR;                        // [levcap] mask pixels per level
+    const int levcap = scr_work / 4;
     for (int i = tid; i < levcap; i += FR_NT) cnt[i] = 0;
-    __syncthreads();
     const bool d2_ok = !(s_flags & FR_OVF_D2);
-    if (d2_ok)
-        for (int i = tid; i < H * Wp; i += FR_NT) {
-            const uint32_t v = D[i];
-            if (v && !((pres[v >> 5] >> (v & 31)) & 1u)) atomicOr(&pres[v >> 5], 1u << (v & 31));
-        }
     __syncthreads();
     uint32_t nlev = 0;
     {

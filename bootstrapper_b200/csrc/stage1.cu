@@ -2329,7 +2329,7 @@ static int stage1_front_fused(Plan &P, AffView A, const std::vector<Tile> &tiles
         return BS_OK;
     int maxH = 0, maxW = 0;
     for (auto &t : tiles) maxH = std::max(maxH, t.H), maxW = std::max(maxW, t.W);
-    if (maxH > 128 * FR_MAXG || cfg.min_seed_distance > 64) return BS_OK;
+    if (maxH > 128 * FR_MAXG || maxW > 1024 || cfg.min_seed_distance > 64) return BS_OK;
     // shared memory of one tile CTA: 16-bit plane + bitmap + scratch (seed ranks / union-find, then level tables)
     size_t need_fixed = 0, nwords_max = 0;
     for (auto &t : tiles) {
@@ -2339,9 +2339,9 @@ static int stage1_front_fused(Plan &P, AffView A, const std::vector<Tile> &tiles
     }
     if (need_fixed + 3072 + 4 * 512 > (size_t)FR_SMEM_TOTAL) return BS_OK;
     const int scr_bytes = (int)(((size_t)FR_SMEM_TOTAL - need_fixed) & ~(size_t)15);
-    if ((size_t)scr_bytes < ((nwords_max * 2 + 15) & ~(size_t)15) + 4 * 512) return BS_OK;
-    if (scr_bytes / (2 * fr_pitch(maxW)) < cfg.min_seed_distance - 1 + 8) return BS_OK;   // rows of the maximum filter's band buffer
-    const int levtab = std::min(4096, (scr_bytes - 3072) / 4);
+    if ((size_t)scr_bytes < 3072 + ((nwords_max * 2 + 15) & ~(size_t)15) + 4 * 512) return BS_OK;
+    if ((scr_bytes - 3072) / (2 * fr_pitch(maxW)) < cfg.min_seed_distance - 1 + 8) return BS_OK;   // rows of the maximum filter's band buffer
+    const int levtab = std::min(4096, (scr_bytes - 3072) / 4);   // the kernel's level-count table (scr_work / 4 entries)
 
     // ---- mask bitmap
     g_prof.mark("s1.mask_bits", s);

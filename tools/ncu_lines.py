@@ -17,11 +17,16 @@ from collections import defaultdict
 def main():
     rep, cubin, kern = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     H = {n: i for i, n in enumerate(rows[hdr])}
-    inst = [(r[H["Source"]].strip(), int(r[H["Instructions Executed"]] or 0), int(r[H["# Samples"]] or 0)) for r in rows[hdr + 1:] if len(r) > 5]
+    inst = []
+    for r in rows[hdr + 1:]:
+        if not r or r[0] in ("Kernel Name", "Address"):     # the next kernel instance of the report
+            break
+        if len(r) > 5:
+            inst.append((r[H["Source"]].strip(), int(r[H["Instructions Executed"]] or 0), int(r[H["# Samples"]] or 0)))
     dis = subprocess.run(["nvdisasm", "-g", cubin], capture_output=True, text=True).stdout.split("\n")
     # locate the kernel's section
     start = next(i for i, l in enumerate(dis) if l.startswith(".text.") and kern in l)
@@ -33,7 +38,7 @@ def main():
         m = re.search(r'//## File "([^"]+)", line (\d+)', l)
         if m:
             cur = (m.group(1).split("/")[-1], int(m.group(2)))
-        elif re.search(r"/\*[0-9a-f]{4}\*/", l):
+        elif re.search(r"/\*[0-9a-f]{4,}\*/", l):
             lines.append(cur)
     n = min(len(lines), len(inst))
     if len(lines) != len(inst):
