@@ -203,6 +203,33 @@ def compare_with_oracle(r, ref):
             "n_fragments": int(len(ref["rag"].node_pos)), "n_edges": int(len(keys))}
 
 
+# --config 3: BASELINE configs[2], mutex-watershed fragments from a 9-offset long-range neighbourhood at 512^3 on one GPU
+MWS_NBH = [[-1, 0, 0], [0, -1, 0], [0, 0, -1], [-2, 0, 0], [0, -9, 0], [0, 0, -9], [-3, 0, 0], [0, -27, 0], [0, 0, -27]]   # segment.py:24-34
+MWS_BIAS = [-0.4] * 3 + [-0.7] * 6
+MWS_STRIDES = [[1, 1, 1]] * 3 + [[2, 9, 9]] * 3 + [[3, 27, 27]] * 3
+
+
+def mws_affs9(shape, seed=0):
+    """nine-channel synthetic affinities on the device: the three nearest-neighbour channels of the block-addressable
+    generator, and for every long-range offset the minimum of the nearest-neighbour affinity along the offset's path"""
+    import torch
+    from bootstrapper_b200 import native
+    a = native.synth_affs(shape, seed=seed)
+    out = [a[0], a[1], a[2]]
+    for off in MWS_NBH[3:]:
+        axis = [i for i, o in enumerate(off) if o][0]
+        acc = a[axis].clone()
+        for k in range(1, -off[axis]):
+            sh = torch.zeros_like(acc)
+            dst = [slice(None)] * 3
+            src = [slice(None)] * 3
+            dst[axis], src[axis] = slice(k, None), slice(0, -k)
+            sh[tuple(dst)] = a[axis][tuple(src)]
+            acc = torch.minimum(acc, sh)
+        out.append(acc)
+    return torch.stack(out).contiguous()
+
+
 CONFIGS = {2: (SHAPE, BLOCK, CONTEXT, {}), 4: (SHAPE4, BLOCK4, CONTEXT4, PARAMS4), 5: (SHAPE5, BLOCK5, CONTEXT5, {})}
 
 

@@ -306,6 +306,16 @@ int bs_cc_affs(const void *affs, int aff_dtype, const uint8_t *mask, int Z, int 
     return cc_affs(affs, aff_dtype, mask, Z, Y, X, threshold, remove_debris, frags_out, seg_out, n_out, (cudaStream_t)stream);
 }
 
+int bs_mws_agglom(const void *affs, int aff_dtype, const uint8_t *mask, int n_channels, int Z, int Y, int X, const int32_t *offsets,
+                  const int32_t *strides, const double *bias, double noise_eps, unsigned long long noise_seed, int remove_debris,
+                  uint64_t *frags_out, uint64_t *seg_out, int64_t *counters_out, void *stream) {
+    BS_ARG(affs && offsets && frags_out, "bs_mws_agglom: null argument");
+    BS_ARG(aff_dtype == BS_DTYPE_U8 || aff_dtype == BS_DTYPE_F32, "bs_mws_agglom: aff_dtype must be u8 or f32");
+    init_mempool();
+    return bs::mws_agglom(affs, aff_dtype, mask, n_channels, Z, Y, X, offsets, strides, bias, noise_eps, noise_seed, 1, remove_debris,
+                          frags_out, seg_out, counters_out, (cudaStream_t)stream);
+}
+
 int bs_label_stats(const uint64_t *seg, const int32_t *shape, int64_t capacity, uint64_t *ids_out, int64_t *sizes_out,
                    int32_t *zmin_out, int32_t *zmax_out, int64_t *n_out, void *stream) {
     init_mempool();

@@ -160,6 +160,11 @@ int scan_exclusive_u8(const uint8_t *in, uint32_t *out, size_t n, uint32_t *tota
 int radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, size_t n,
                      int bit_lo, int bit_hi, cudaStream_t s);
 
+// mutex watershed (mws.cu)
+int mws_agglom(const void *affs, int aff_dtype, const uint8_t *mask, int C, int Z, int Y, int X, const int32_t *offsets,
+               const int32_t *strides, const double *bias, double noise_eps, unsigned long long noise_seed, int zero_is_repulsive,
+               int remove_debris, uint64_t *labels_out, uint64_t *seg_out, int64_t *counters_out, cudaStream_t s);
+
 // ---- device helpers ----
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;

@@ -1,0 +1,495 @@
+// Mutex watershed on the device: the `bs segment --mws` fragmenter (sm_100a).
+//
+// Replaces mwatershed.agglom as post/mws.py:52-57 calls it (mwatershed_from_affinities: shift = noise + bias, weights =
+// affs + shift in float64; every (offset c, voxel p) with p + offset_c inside the volume -- and p on the stride lattice of c
+// -- is an edge; w > 0 attractive, w <= 0 repulsive; edges visited by descending |w|; attractive: union unless a mutex
+// separates the clusters, repulsive: mutex unless already one cluster).  Declared tie rule D4: equal |w| are
+// visited by ascending (channel, raveled voxel) -- the upstream Rust sort is unstable, so no order is defined there.
+//
+// The sequential pass is reproduced EXACTLY by rounds of locally safe edges.  All edges are ranked once (stable LSD radix
+// sort of the float64 |w| bits, descending); rank = position in the sequential order.  In a round, with bestA[c] = the
+// smallest rank of a live attractive edge at cluster c:
+//   * a repulsive edge (A, B) of rank r is executed when r < bestA[A] and r < bestA[B]: no pending attractive edge of higher
+//     priority touches either cluster, so A and B are the clusters the sequential pass would see -- insert mutex (A, B);
+//   * an attractive edge (A, B) is executed when it IS bestA[A] and bestA[B]: every higher-priority edge at A or B is done
+//     (the repulsive ones of this round first), so the mutex test and the union happen in the state the sequential pass has.
+//   * an attractive edge that is bestA[A] only is executed as well when A is FREE: A carries no mutex and no live repulsive
+//     edge.  Nothing can then block this edge before its sequential turn (a block needs a mutex at A; A's other attractive
+//     edges come later than its top edge; A gets no mutex without a repulsive edge of its own), and A brings neither
+//     mutexes nor repulsive edges into B, so B's own decisions are what they would have been.  This is what lets the
+//     interior of an object assemble in a few rounds instead of one voxel per round around its growing core.
+// Executed edges at different clusters commute; a cluster that is not free takes part in at most one union per round.  Mutexes are kept as
+// a list of voxel pairs and a hash set of (root, root) pairs rebuilt (deduplicated) after the unions of a round.
+// Distinct weights (the reference adds noise by default for this reason, post/mws.py:28-31) give O(log V)-ish rounds;
+// long runs of equal weights zip up one voxel per round along the tie order.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "../../include/bsnative.h"
+
+namespace bs {
+
+static constexpr uint32_t NONE32 = 0xFFFFFFFFu;
+static constexpr unsigned long long EMPTY64 = 0xFFFFFFFFFFFFFFFFull;
+static constexpr uint32_t ATTR_BIT = 0x80000000u;
+
+struct MwsGeom {
+    int C, Z, Y, X;
+    int off[32][3], st[32][3];
+    // stride lattice of channel c: z in [z0, z0 + nz * sz) step sz, ... (voxels whose partner lies inside the volume)
+    int z0[32], y0[32], x0[32], nz[32], ny[32], nx[32];
+    unsigned long long ebase[33];   // first edge slot of channel c (slots enumerate the lattice in raster order)
+    double bias[32];
+    int has_noise;
+    double noise_eps, noise_k;
+    unsigned long long seed;
+};
+
+__device__ __forceinline__ uint64_t mws_splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t mws_mixw(uint64_t x, long long w) { return mws_splitmix64(x ^ ((uint64_t)w * 0x9E3779B97F4A7C15ull)); }
+
+// slot -> (channel, voxel p, partner q)
+__device__ __forceinline__ void mws_slot(const MwsGeom &G, unsigned long long e, int &c, uint32_t &p, uint32_t &q) {
+    c = 0;
+    while (c + 1 < G.C && e >= G.ebase[c + 1]) c++;
+    unsigned long long k = e - G.ebase[c];
+    const int ix = (int)(k % (unsigned)G.nx[c]);
+    k /= (unsigned)G.nx[c];
+    const int iy = (int)(k % (unsigned)G.ny[c]);
+    const int iz = (int)(k / (unsigned)G.ny[c]);
+    const int z = G.z0[c] + iz * G.st[c][0], y = G.y0[c] + iy * G.st[c][1], x = G.x0[c] + ix * G.st[c][2];
+    p = (uint32_t)(((long long)z * G.Y + y) * G.X + x);
+    q = (uint32_t)(((long long)(z + G.off[c][0]) * G.Y + (y + G.off[c][1])) * G.X + (x + G.off[c][2]));
+}
+
+// weight of edge (c, p) exactly as numpy computes it (post/mws.py:33-57): affs_data (float64; uint8 input / 255.0; * mask),
+// shift = zeros; shift += noise * eps; shift += bias; w = affs_data + shift
+template <typename T>
+__device__ __forceinline__ double mws_weight(const MwsGeom &G, const T *affs, const uint8_t *mask, int c, uint32_t p) {
+    const size_t V = (size_t)G.Z * G.Y * G.X;
+    double a;
+    if constexpr (sizeof(T) == 1)
+        a = __ddiv_rn((double)affs[(size_t)c * V + p], 255.0);
+    else
+        a = (double)affs[(size_t)c * V + p];
+    if (mask && mask[p] == 0) a = __dmul_rn(a, 0.0);
+    double sh = 0.0;
+    if (G.has_noise) {
+        // seeded stand-in for numpy's unseeded randn: sum of four 16-bit uniforms, centred and scaled to unit variance
+        const uint64_t h = mws_mixw(mws_mixw(mws_mixw(G.seed, c), (long long)p), 11);
+        const long long sum = (long long)(h & 0xFFFF) + (long long)((h >> 16) & 0xFFFF) + (long long)((h >> 32) & 0xFFFF) + (long long)(h >> 48);
+        const double n = __dmul_rn((double)(sum - 131070), G.noise_k);
+        sh = __dadd_rn(sh, __dmul_rn(n, G.noise_eps));
+    }
+    sh = __dadd_rn(sh, G.bias[c]);
+    return __dadd_rn(a, sh);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_mws_keys(MwsGeom G, const T *__restrict__ affs, const uint8_t *__restrict__ mask,
+                                                  unsigned long long E, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (unsigned long long)gridDim.x * blockDim.x) {
+        int c;
+        uint32_t p, q;
+        mws_slot(G, e, c, p, q);
+        const double w = mws_weight<T>(G, affs, mask, c, p);
+        // descending |w|: invert the bits of the non-negative double; NaN edges sort last and are dropped later
+        uint64_t k = w != w ? EMPTY64 : ~(uint64_t)__double_as_longlong(fabs(w));
+        keys[e] = k;
+        vals[e] = (uint32_t)e;
+    }
+}
+
+// sorted position -> endpoints (+ attractive bit); NaN edges get NONE32 / NONE32
+template <typename T>
+__global__ void __launch_bounds__(256) k_mws_endpoints(MwsGeom G, const T *__restrict__ affs, const uint8_t *__restrict__ mask,
+                                                       unsigned long long E, const uint32_t *__restrict__ vals, int zero_is_repulsive,
+                                                       uint32_t *__restrict__ eu, uint32_t *__restrict__ ev,
+                                                       unsigned long long *__restrict__ counts) {
+    unsigned long long nrep = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += (unsigned long long)gridDim.x * blockDim.x) {
+        int c;
+        uint32_t p, q;
+        mws_slot(G, vals[i], c, p, q);
+        const double w = mws_weight<T>(G, affs, mask, c, p);
+        if (w != w) {
+            eu[i] = NONE32, ev[i] = NONE32;
+        } else {
+            const bool attractive = w > 0.0 || (w == 0.0 && !zero_is_repulsive);
+            eu[i] = p | (attractive ? ATTR_BIT : 0u);
+            ev[i] = q;
+            nrep += attractive ? 0 : 1;
+        }
+    }
+    nrep = __reduce_add_sync(0xFFFFFFFFu, (unsigned)nrep);
+    if ((threadIdx.x & 31) == 0 && nrep) atomicAdd(&counts[0], nrep);
+}
+
+__global__ void k_mws_init(uint32_t *__restrict__ parent, size_t V) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (size_t)gridDim.x * blockDim.x) parent[i] = (uint32_t)i;
+}
+
+// The rounds work on a WINDOW of the live edges: the lowest-ranked edges not executed yet (survivors of earlier rounds plus a
+// refill from the sorted order).  A cluster with an edge in the window has its top edge in the window, so the tests above are
+// exact on the window alone; edges beyond it simply wait.
+// phase A: roots of the window's edges (stored for the later phases: parent[] is rewritten by the unions); dead edges (one
+// cluster, NaN) are flagged; bestA over the attractive ones
+__global__ void __launch_bounds__(256) k_mws_best(const uint32_t *__restrict__ win, size_t nwin, const uint32_t *__restrict__ eu,
+                                                  const uint32_t *__restrict__ ev, const uint32_t *__restrict__ root,
+                                                  uint32_t *__restrict__ bestA, uint8_t *__restrict__ keep, uint2 *__restrict__ wroots) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < nwin; j += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t i = win[j];
+        const uint32_t u = eu[i], v = ev[i];
+        uint32_t ru = NONE32, rv = NONE32;
+        if (v != NONE32) ru = root[u & ~ATTR_BIT], rv = root[v];
+        wroots[j] = make_uint2(ru, rv);
+        if (ru == rv) {          // also the NaN edges (NONE32, NONE32)
+            keep[j] = 0;
+            continue;
+        }
+        keep[j] = 1;
+        if (u & ATTR_BIT) {
+            atomicMin(&bestA[ru], i);
+            atomicMin(&bestA[rv], i);
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t mws_hash(uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return k;
+}
+// returns true if the key was new
+__device__ __forceinline__ bool mws_set_insert(unsigned long long *tab, uint64_t mask, unsigned long long key) {
+    uint64_t s = mws_hash(key) & mask;
+    for (;;) {
+        unsigned long long k = tab[s];
+        if (k == key) return false;
+        if (k == EMPTY64) {
+            k = atomicCAS(&tab[s], EMPTY64, key);
+            if (k == EMPTY64) return true;
+            if (k == key) return false;
+        }
+        s = (s + 1) & mask;
+    }
+}
+__device__ __forceinline__ bool mws_set_has(const unsigned long long *tab, uint64_t mask, unsigned long long key) {
+    uint64_t s = mws_hash(key) & mask;
+    for (;;) {
+        const unsigned long long k = tab[s];
+        if (k == key) return true;
+        if (k == EMPTY64) return false;
+        s = (s + 1) & mask;
+    }
+}
+
+// phase B: repulsive edges with no pending higher-priority attractive edge at either cluster become mutexes
+__global__ void __launch_bounds__(256) k_mws_repulsive(const uint32_t *__restrict__ win, size_t nwin, const uint32_t *__restrict__ eu,
+                                                       const uint32_t *__restrict__ ev, const uint2 *__restrict__ wroots,
+                                                       const uint32_t *__restrict__ bestA, uint8_t *__restrict__ keep,
+                                                       unsigned long long *__restrict__ tab, uint64_t tmask, uint2 *__restrict__ mlist,
+                                                       unsigned long long *__restrict__ counts) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < nwin; j += (size_t)gridDim.x * blockDim.x) {
+        if (!keep[j]) continue;
+        const uint32_t i = win[j];
+        const uint32_t u = eu[i], v = ev[i];
+        if (u & ATTR_BIT) continue;
+        const uint2 r = wroots[j];
+        if (i < bestA[r.x] && i < bestA[r.y]) {
+            keep[j] = 0;
+            const unsigned long long key = ((unsigned long long)min(r.x, r.y) << 32) | max(r.x, r.y);
+            if (mws_set_insert(tab, tmask, key)) {
+                const unsigned long long slot = atomicAdd(&counts[1], 1ull);    // mutex list length
+                mlist[slot] = make_uint2(u, v);
+            }
+            atomicAdd(&counts[3], 1ull);
+        }
+    }
+}
+
+// phase C: attractive edges that are the top edge of both their clusters (union unless a mutex separates them), or the top
+// edge of a FREE cluster (no mutex, no live repulsive edge: nothing can block it)
+__global__ void __launch_bounds__(256) k_mws_attractive(const uint32_t *__restrict__ win, size_t nwin, const uint32_t *__restrict__ eu,
+                                                        const uint2 *__restrict__ wroots, uint32_t *__restrict__ parent,
+                                                        const uint32_t *__restrict__ bestA, const uint8_t *__restrict__ nonfree,
+                                                        uint8_t *__restrict__ keep, const unsigned long long *__restrict__ tab,
+                                                        uint64_t tmask, unsigned long long *__restrict__ counts) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < nwin; j += (size_t)gridDim.x * blockDim.x) {
+        if (!keep[j]) continue;
+        const uint32_t i = win[j];
+        if (!(eu[i] & ATTR_BIT)) continue;
+        const uint32_t ru = wroots[j].x, rv = wroots[j].y;      // the roots as of the start of the round
+        const bool top_u = bestA[ru] == i, top_v = bestA[rv] == i;
+        if (!top_u && !top_v) continue;
+        const bool free_u = top_u && !nonfree[ru], free_v = top_v && !nonfree[rv];
+        if (!(top_u && top_v) && !free_u && !free_v) continue;
+        keep[j] = 0;
+        bool blocked = false;
+        if (!free_u && !free_v) {
+            const unsigned long long key = ((unsigned long long)min(ru, rv) << 32) | max(ru, rv);
+            blocked = mws_set_has(tab, tmask, key);
+        }
+        if (blocked) {
+            atomicAdd(&counts[4], 1ull);        // blocked by a mutex
+        } else {
+            uf_union(parent, ru, rv);           // lock-free, the smaller index becomes the root
+            atomicAdd(&counts[2], 1ull);        // merges (all rounds) ...
+            atomicAdd(&counts[5], 1ull);        // ... and of this round
+        }
+    }
+}
+
+// bestA back to "none" for the clusters the window touched (instead of clearing the whole array every round)
+__global__ void __launch_bounds__(256) k_mws_reset_best(const uint2 *__restrict__ wroots, size_t nwin, uint32_t *__restrict__ bestA) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < nwin; j += (size_t)gridDim.x * blockDim.x) {
+        const uint2 r = wroots[j];
+        if (r.x != NONE32) bestA[r.x] = NONE32, bestA[r.y] = NONE32;
+    }
+}
+
+// survivors keep their order at the front of the next window, the refill continues the sorted order behind them
+__global__ void k_mws_next_window(const uint32_t *__restrict__ win, const uint8_t *__restrict__ keep, const uint32_t *__restrict__ pos,
+                                  size_t nwin, const uint32_t *__restrict__ nkeep_dev, uint32_t cursor, uint32_t wcap, uint32_t E,
+                                  uint32_t *__restrict__ out) {
+    const uint32_t nkeep = *nkeep_dev;
+    const uint32_t nfill = min(wcap - nkeep, E - cursor);
+    const size_t n = max(nwin, (size_t)nfill);
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
+        if (j < nwin && keep[j]) out[pos[j]] = win[j];
+        if (j < nfill) out[nkeep + j] = cursor + (uint32_t)j;
+    }
+}
+
+// roots of all voxels after the unions of a round (chains of unions: walk to the root), written to a second array so that
+// the walks never see a half-updated forest.  A cluster that absorbs a non-free one is not free.
+__global__ void k_mws_flatten(const uint32_t *__restrict__ parent, uint32_t *__restrict__ out, uint8_t *__restrict__ nonfree, size_t V) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t x = (uint32_t)i, p = parent[x];
+        while (p != x) {
+            x = p;
+            p = parent[x];
+        }
+        out[i] = x;
+        if (x != (uint32_t)i && nonfree[i]) nonfree[x] = 1;
+    }
+}
+
+// every voxel with a repulsive edge starts non-free
+__global__ void __launch_bounds__(256) k_mws_mark_repulsive(const uint32_t *__restrict__ eu, const uint32_t *__restrict__ ev, size_t E,
+                                                            uint8_t *__restrict__ nonfree) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t u = eu[i], v = ev[i];
+        if (v != NONE32 && !(u & ATTR_BIT)) nonfree[u] = 1, nonfree[v] = 1;
+    }
+}
+
+// re-key the mutexes by the clusters' new roots; duplicates leave the list
+__global__ void __launch_bounds__(256) k_mws_rekey(const uint2 *__restrict__ mlist, size_t nm, const uint32_t *__restrict__ root,
+                                                   unsigned long long *__restrict__ tab, uint64_t tmask, uint2 *__restrict__ mlist_out,
+                                                   unsigned long long *__restrict__ n_out) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < nm; j += (size_t)gridDim.x * blockDim.x) {
+        const uint2 m = mlist[j];
+        const uint32_t ru = root[m.x], rv = root[m.y];
+        const unsigned long long key = ((unsigned long long)min(ru, rv) << 32) | max(ru, rv);
+        if (mws_set_insert(tab, tmask, key)) mlist_out[atomicAdd(n_out, 1ull)] = m;
+    }
+}
+
+__global__ void k_mws_labels(const uint32_t *__restrict__ parent, size_t V, uint64_t *__restrict__ labels) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (size_t)gridDim.x * blockDim.x) labels[i] = (uint64_t)parent[i] + 1u;
+}
+
+// remove_small_objects(labels, min_size) of simple_mutex (post/watershed_mutex.py:272-277): labels with fewer voxels -> 0
+__global__ void k_mws_count(const uint64_t *__restrict__ labels, size_t V, uint32_t *__restrict__ cnt) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (size_t)gridDim.x * blockDim.x)
+        if (labels[i]) atomicAdd(&cnt[labels[i] - 1], 1u);
+}
+__global__ void k_mws_debris(const uint64_t *__restrict__ labels, size_t V, const uint32_t *__restrict__ cnt, uint32_t min_size,
+                             uint64_t *__restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t l = labels[i];
+        out[i] = (l && cnt[l - 1] >= min_size) ? l : 0;
+    }
+}
+
+// edges per round (BS_MWS_WINDOW overrides; the result does not depend on it)
+static unsigned long long g_mws_window = getenv("BS_MWS_WINDOW") ? strtoull(getenv("BS_MWS_WINDOW"), nullptr, 10) : (1ull << 21);
+
+static unsigned grid_for(size_t n) { return (unsigned)std::min<size_t>(std::max<size_t>((n + 255) / 256, 1), 148 * 16); }
+
+template <typename T>
+static int mws_run(const T *affs, const uint8_t *mask, MwsGeom &G, int zero_is_repulsive, int remove_debris, uint64_t *labels_out,
+                   uint64_t *seg_out, int64_t *counters_out, cudaStream_t s) {
+    const size_t V = (size_t)G.Z * G.Y * G.X;
+    const unsigned long long E = G.ebase[G.C];
+    BS_ARG(V < (1ull << 31), "bs_mws_agglom: volume too large for 31-bit voxel indices");
+    BS_ARG(E < (1ull << 32) - 1, "bs_mws_agglom: more than 2^32 edges");
+    DevBuf parent, root, nonfree, keys, keys2, vals, vals2, eu, ev, win, win2, wroots, keep, pos, bestA, counts, tab, mlist, mlist2;
+    BS_TRY(parent.alloc(4 * V, s));
+    BS_LAUNCH(k_mws_init, grid_for(V), 256, 0, s, parent.as<uint32_t>(), V);
+    BS_TRY(counts.alloc_zero(64, s));
+    unsigned long long *d_cnt = counts.as<unsigned long long>();   // [0] repulsive edges [1] mutex list length [2] merges
+                                                                   // [3] repulsive executed [4] blocked [5] merges this round [6] survivors
+    unsigned long long h_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (E) {
+        BS_TRY(keys.alloc(8 * (size_t)E, s));
+        BS_TRY(keys2.alloc(8 * (size_t)E, s));
+        BS_TRY(vals.alloc(4 * (size_t)E, s));
+        BS_TRY(vals2.alloc(4 * (size_t)E, s));
+        BS_LAUNCH((k_mws_keys<T>), grid_for(E), 256, 0, s, G, affs, mask, E, keys.as<uint64_t>(), vals.as<uint32_t>());
+        BS_TRY(radix_sort_pairs(keys.as<uint64_t>(), vals.as<uint32_t>(), keys2.as<uint64_t>(), vals2.as<uint32_t>(), (size_t)E, 0, 64, s));
+        keys.release();
+        keys2.release();
+        vals2.release();
+        BS_TRY(eu.alloc(4 * (size_t)E, s));
+        BS_TRY(ev.alloc(4 * (size_t)E, s));
+        BS_LAUNCH((k_mws_endpoints<T>), grid_for(E), 256, 0, s, G, affs, mask, E, vals.as<uint32_t>(), zero_is_repulsive, eu.as<uint32_t>(),
+                  ev.as<uint32_t>(), d_cnt);
+        vals.release();
+        BS_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 64, cudaMemcpyDeviceToHost, s));
+        BS_CUDA(cudaStreamSynchronize(s));
+        const unsigned long long nrep = h_cnt[0];
+        // mutex set: at most one entry per executed repulsive edge
+        uint64_t tcap = 1024;
+        while (tcap < 2 * nrep + 16) tcap <<= 1;
+        BS_TRY(tab.alloc_fill(8 * tcap, 0xFF, s));
+        BS_TRY(mlist.alloc(8 * (size_t)(nrep + 1), s));
+        BS_TRY(mlist2.alloc(8 * (size_t)(nrep + 1), s));
+        BS_TRY(bestA.alloc_fill(4 * V, 0xFF, s));
+        BS_TRY(root.alloc(4 * V, s));
+        BS_TRY(nonfree.alloc_zero(V, s));
+        BS_CUDA(cudaMemcpyAsync(root.p, parent.p, 4 * V, cudaMemcpyDeviceToDevice, s));
+        BS_LAUNCH(k_mws_mark_repulsive, grid_for(E), 256, 0, s, eu.as<uint32_t>(), ev.as<uint32_t>(), (size_t)E, nonfree.as<uint8_t>());
+        const uint32_t wcap = (uint32_t)std::min<unsigned long long>(E, g_mws_window);
+        BS_TRY(win.alloc(4 * (size_t)wcap, s));
+        BS_TRY(win2.alloc(4 * (size_t)wcap, s));
+        BS_TRY(wroots.alloc(8 * (size_t)wcap, s));
+        BS_TRY(keep.alloc((size_t)wcap, s));
+        BS_TRY(pos.alloc(4 * (size_t)wcap, s));
+        // first window: the wcap best edges
+        uint32_t cursor = 0;
+        size_t nwin = 0;
+        BS_CUDA(cudaMemsetAsync(d_cnt + 6, 0, 8, s));
+        BS_LAUNCH(k_mws_next_window, grid_for(wcap), 256, 0, s, win.as<uint32_t>(), keep.as<uint8_t>(), pos.as<uint32_t>(), (size_t)0,
+                  (const uint32_t *)(d_cnt + 6), cursor, wcap, (uint32_t)E, win.as<uint32_t>());
+        nwin = wcap;
+        cursor = wcap;
+        int rounds = 0;
+        while (nwin > 0) {
+            rounds++;
+            BS_CUDA(cudaMemsetAsync(d_cnt + 5, 0, 8, s));
+            BS_LAUNCH(k_mws_best, grid_for(nwin), 256, 0, s, win.as<uint32_t>(), nwin, eu.as<uint32_t>(), ev.as<uint32_t>(), root.as<uint32_t>(),
+                      bestA.as<uint32_t>(), keep.as<uint8_t>(), wroots.as<uint2>());
+            BS_LAUNCH(k_mws_repulsive, grid_for(nwin), 256, 0, s, win.as<uint32_t>(), nwin, eu.as<uint32_t>(), ev.as<uint32_t>(),
+                      wroots.as<uint2>(), bestA.as<uint32_t>(), keep.as<uint8_t>(), tab.as<unsigned long long>(), tcap - 1, mlist.as<uint2>(),
+                      d_cnt);
+            BS_LAUNCH(k_mws_attractive, grid_for(nwin), 256, 0, s, win.as<uint32_t>(), nwin, eu.as<uint32_t>(), wroots.as<uint2>(),
+                      parent.as<uint32_t>(), bestA.as<uint32_t>(), nonfree.as<uint8_t>(), keep.as<uint8_t>(), tab.as<unsigned long long>(),
+                      tcap - 1, d_cnt);
+            BS_LAUNCH(k_mws_reset_best, grid_for(nwin), 256, 0, s, wroots.as<uint2>(), nwin, bestA.as<uint32_t>());
+            // next window: survivors (order preserved) + refill
+            BS_TRY(scan_exclusive_u8(keep.as<uint8_t>(), pos.as<uint32_t>(), nwin, (uint32_t *)(d_cnt + 6), s));
+            BS_LAUNCH(k_mws_next_window, grid_for(wcap), 256, 0, s, win.as<uint32_t>(), keep.as<uint8_t>(), pos.as<uint32_t>(), nwin,
+                      (const uint32_t *)(d_cnt + 6), cursor, wcap, (uint32_t)E, win2.as<uint32_t>());
+            win.swap(win2);
+            BS_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 64, cudaMemcpyDeviceToHost, s));
+            BS_CUDA(cudaStreamSynchronize(s));
+            const uint32_t nkeep = (uint32_t)h_cnt[6];
+            const uint32_t nfill = std::min<uint32_t>(wcap - nkeep, (uint32_t)E - cursor);
+            BS_ARG(nkeep < nwin || nfill > 0, "bs_mws_agglom: a round executed no edge (internal error)");
+            cursor += nfill;
+            nwin = (size_t)nkeep + nfill;
+            if (h_cnt[5] > 0) {
+                // unions happened: roots of all voxels, then the mutex set re-keyed by the new roots
+                BS_LAUNCH(k_mws_flatten, grid_for(V), 256, 0, s, parent.as<uint32_t>(), root.as<uint32_t>(), nonfree.as<uint8_t>(), V);
+                BS_CUDA(cudaMemcpyAsync(parent.p, root.p, 4 * V, cudaMemcpyDeviceToDevice, s));
+                const size_t nm = (size_t)h_cnt[1];
+                if (nm) {
+                    BS_CUDA(cudaMemsetAsync(tab.p, 0xFF, 8 * tcap, s));
+                    BS_CUDA(cudaMemsetAsync(d_cnt + 1, 0, 8, s));
+                    BS_LAUNCH(k_mws_rekey, grid_for(nm), 256, 0, s, mlist.as<uint2>(), nm, root.as<uint32_t>(), tab.as<unsigned long long>(),
+                              tcap - 1, mlist2.as<uint2>(), d_cnt + 1);
+                    mlist.swap(mlist2);
+                }
+            }
+        }
+        h_cnt[7] = (unsigned long long)rounds;
+    }
+    BS_LAUNCH(k_mws_labels, grid_for(V), 256, 0, s, parent.as<uint32_t>(), V, labels_out);   // flat: parent == roots
+    if (seg_out) {
+        if (remove_debris > 0) {
+            DevBuf cnt;
+            BS_TRY(cnt.alloc_zero(4 * V, s));
+            BS_LAUNCH(k_mws_count, grid_for(V), 256, 0, s, labels_out, V, cnt.as<uint32_t>());
+            BS_LAUNCH(k_mws_debris, grid_for(V), 256, 0, s, labels_out, V, cnt.as<uint32_t>(), (uint32_t)remove_debris, seg_out);
+            BS_CUDA(cudaStreamSynchronize(s));
+        } else {
+            BS_CUDA(cudaMemcpyAsync(seg_out, labels_out, 8 * V, cudaMemcpyDeviceToDevice, s));
+        }
+    }
+    BS_CUDA(cudaStreamSynchronize(s));
+    BS_CUDA(cudaGetLastError());
+    if (counters_out) {
+        counters_out[0] = (int64_t)E;
+        counters_out[1] = (int64_t)h_cnt[2];
+        counters_out[2] = (int64_t)h_cnt[3];
+        counters_out[3] = (int64_t)h_cnt[4];
+        counters_out[4] = (int64_t)h_cnt[7];
+    }
+    return BS_OK;
+}
+
+int mws_agglom(const void *affs, int aff_dtype, const uint8_t *mask, int C, int Z, int Y, int X, const int32_t *offsets,
+               const int32_t *strides, const double *bias, double noise_eps, unsigned long long noise_seed, int zero_is_repulsive,
+               int remove_debris, uint64_t *labels_out, uint64_t *seg_out, int64_t *counters_out, cudaStream_t s) {
+    BS_ARG(C >= 1 && C <= 32, "bs_mws_agglom: 1..32 affinity channels");
+    BS_ARG(Z > 0 && Y > 0 && X > 0, "bs_mws_agglom: empty volume");
+    MwsGeom G;
+    memset(&G, 0, sizeof(G));
+    G.C = C, G.Z = Z, G.Y = Y, G.X = X;
+    const int dims[3] = {Z, Y, X};
+    unsigned long long e = 0;
+    for (int c = 0; c < C; c++) {
+        int first[3], count[3];
+        for (int d = 0; d < 3; d++) {
+            G.off[c][d] = offsets[3 * c + d];
+            G.st[c][d] = strides ? strides[3 * c + d] : 1;
+            BS_ARG(G.st[c][d] >= 1, "bs_mws_agglom: strides must be >= 1");
+            // voxels v with 0 <= v + off < n and v % stride == 0
+            const int lo = std::max(0, -G.off[c][d]), hi = std::min(dims[d], dims[d] - G.off[c][d]);   // [lo, hi)
+            const int f = ((lo + G.st[c][d] - 1) / G.st[c][d]) * G.st[c][d];
+            first[d] = f;
+            count[d] = hi > f ? (hi - f + G.st[c][d] - 1) / G.st[c][d] : 0;
+        }
+        G.z0[c] = first[0], G.y0[c] = first[1], G.x0[c] = first[2];
+        G.nz[c] = count[0], G.ny[c] = count[1], G.nx[c] = count[2];
+        G.ebase[c] = e;
+        e += (unsigned long long)count[0] * count[1] * count[2];
+        if (count[0] == 0 || count[1] == 0 || count[2] == 0) G.nz[c] = 0, G.ny[c] = 1, G.nx[c] = 1;   // empty lattice, no division by zero
+        G.bias[c] = bias ? bias[c] : 0.0;
+    }
+    G.ebase[C] = e;
+    G.has_noise = noise_eps != 0.0;
+    G.noise_eps = noise_eps;
+    G.noise_k = 1.7320508075688772 / 65536.0;    // sqrt(3) / 2^16: unit variance for the sum of four 16-bit uniforms
+    G.seed = noise_seed;
+    if (aff_dtype == BS_DTYPE_U8)
+        return mws_run<uint8_t>((const uint8_t *)affs, mask, G, zero_is_repulsive, remove_debris, labels_out, seg_out, counters_out, s);
+    return mws_run<float>((const float *)affs, mask, G, zero_is_repulsive, remove_debris, labels_out, seg_out, counters_out, s);
+}
+
+}  // namespace bs

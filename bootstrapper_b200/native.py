@@ -54,7 +54,7 @@ EXPORTS = [
     "bs_last_error", "bs_launch_count", "bs_version", "bs_config_size", "bs_plan_create", "bs_plan_destroy", "bs_plan_num_blocks",
     "bs_plan_block_info", "bs_plan_set_owned", "bs_stage1_fragments", "bs_stage1_num_nodes", "bs_stage1_get_nodes",
     "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_plan_node_ids", "bs_stage2_agglomerate", "bs_stage2_num_edges",
-    "bs_stage2_get_edges", "bs_waterz_segment", "bs_cc_affs", "bs_aff_errors", "bs_label_stats", "bs_shift_affinities", "bs_connected_components", "bs_stage3_components", "bs_relabel", "bs_stage3_relabel", "bs_watershed_from_affinities",
+    "bs_stage2_get_edges", "bs_waterz_segment", "bs_cc_affs", "bs_mws_agglom", "bs_aff_errors", "bs_label_stats", "bs_shift_affinities", "bs_connected_components", "bs_stage3_components", "bs_relabel", "bs_stage3_relabel", "bs_watershed_from_affinities",
     "bs_synth_affs", "bs_debug_fetch", "bs_set_debug", "bs_set_profiling", "bs_get_profile",
     "bs_release_scratch", "bs_set_flood_version", "bs_set_front_version", "bs_set_agglom_version", "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
 ]
@@ -393,6 +393,31 @@ def cc_affs(affs, threshold, remove_debris=0, mask=None):
                             Z, Y, X, C.c_float(float(threshold)), C.c_int(int(remove_debris or 0)), _dev(frags), _dev(seg),
                             C.byref(n), _stream()))
     return frags, seg, n.value
+
+
+def mws_agglom(affs, offsets, bias, strides=None, mask=None, noise_eps=None, noise_seed=0, remove_debris=0):
+    """mutex watershed of post/mws.py on one device array (C, Z, Y, X) uint8 / float32 (bs_mws_agglom).
+    Returns (fragments, fragments after remove_debris, counters)."""
+    Cn, Z, Y, X = affs.shape
+    off = np.ascontiguousarray(np.asarray(offsets, dtype=np.int32).reshape(-1, 3))
+    if off.shape[0] != Cn:
+        raise BsError("Number of offsets must match number of affinities channels")
+    b = np.ascontiguousarray(np.asarray(bias, dtype=np.float64).reshape(-1))
+    if b.shape[0] != Cn:
+        raise BsError("Number of biases must match number of affinities channels")
+    st = None
+    if strides is not None:
+        st = np.ascontiguousarray(np.asarray(strides, dtype=np.int32).reshape(-1, 3))
+        if st.shape[0] != Cn:
+            raise BsError("Number of strides must match number of affinities channels")
+    frags = torch.empty((Z, Y, X), dtype=torch.int64, device=affs.device)
+    seg = torch.empty_like(frags)
+    cnt = (C.c_int64 * 5)()
+    _check(lib().bs_mws_agglom(_dev(affs), C.c_int(_aff_dtype(affs)), _dev(mask, torch.uint8) if mask is not None else None,
+                               C.c_int(Cn), Z, Y, X, off.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p) if st is not None else None,
+                               b.ctypes.data_as(C.c_void_p), C.c_double(float(noise_eps or 0.0)), C.c_ulonglong(int(noise_seed)),
+                               C.c_int(int(remove_debris or 0)), _dev(frags), _dev(seg), cnt, _stream()))
+    return frags, seg, dict(edges=cnt[0], merges=cnt[1], mutexes=cnt[2], blocked=cnt[3], rounds=cnt[4])
 
 
 def label_stats(seg, capacity=1 << 20):

@@ -3,7 +3,7 @@
 Same key set, defaults, override order and error behaviour as the reference's
 bootstrapper/segment.py (DEFAULTS :10-62, get_seg_config :95-135, run_segmentation :138-163);
 pinned by tests/golden/seg_config.json, which was produced by executing the reference file.
-The ws and cc methods run on the CUDA path; mws is not built yet and raises.
+The ws, cc and (non-blockwise) mws methods run on the CUDA path; blockwise mws raises.
 """
 import ast
 import copy
@@ -88,6 +88,7 @@ def run_segmentation(config_file, mode="ws", **kwargs):
     if mode == "cc":
         from .post.connected_components import cc_segmentation
         return cc_segmentation(config)
-    if mode in ("mws",):
-        raise NotImplementedError(f"segmentation mode {mode!r} is not part of the CUDA hot path yet (SURVEY §8)")
+    if mode == "mws":
+        from .post.watershed_mutex import mutex_watershed_segmentation
+        return mutex_watershed_segmentation(config)
     raise ValueError(f"Unknown segmentation mode: {mode}")

@@ -179,6 +179,22 @@ int bs_stage3_relabel(bs_plan *p, const uint64_t *frags, int64_t n_vox, const ui
 int bs_cc_affs(const void *affs, int aff_dtype, const uint8_t *mask, int Z, int Y, int X, float threshold, int remove_debris,
                uint64_t *frags_out, uint64_t *seg_out, int64_t *n_out, void *stream);
 
+/* ---- `bs segment --mws`: mutex watershed fragments --------------------------------------------
+ * replaces: mwatershed_from_affinities + mwatershed.agglom (post/mws.py:12-59) as simple_mutex drives it
+ * (post/watershed_mutex.py:177-291): weights = affs (uint8 / 255 in float64, or float32 widened; * (mask > 0)) + shift with
+ * shift = noise * noise_eps + bias[c]; every (offset c, voxel p) with p + offset_c inside the volume and p on the stride
+ * lattice of c is an edge; mutex watershed over the edges by descending |w| (ties: ascending (channel, raveled voxel),
+ * declared deviation D4 -- the upstream sort is unstable); remove_debris > 0 additionally writes the
+ * remove_small_objects result to seg_out.
+ *   affs (C, Z, Y, X) u8 / f32; mask (Z,Y,X) u8 or NULL; offsets, strides (or NULL) host int32 [C*3]; bias host double [C];
+ *   noise_eps != 0: a seeded counter-based generator stands in for the reference's unseeded np.random.randn (same
+ *   generator in the oracle); sigma shifts and randomized_strides are not implemented.
+ *   frags_out, seg_out (may be NULL) device (Z,Y,X) uint64: label = 1 + smallest raveled voxel index of the cluster;
+ *   counters_out host[5] or NULL: edges, merges, mutex edges, attractive edges blocked by a mutex, rounds. */
+int bs_mws_agglom(const void *affs, int aff_dtype, const uint8_t *mask, int n_channels, int Z, int Y, int X, const int32_t *offsets,
+                  const int32_t *strides, const double *bias, double noise_eps, unsigned long long noise_seed, int remove_debris,
+                  uint64_t *frags_out, uint64_t *seg_out, int64_t *counters_out, void *stream);
+
 /* ---- per-label statistics (`bs refine`) --------------------------------------
  * replaces: the tile scans of refine.py -- `_global_sizes` (:98-108, fastremap.unique + bincount) and the z-extent loop
  * of `z_filter` (:236-255): voxel count, first and last z plane of every non-zero id of a label volume, ids ascending

@@ -8,6 +8,7 @@ LIB = os.path.join(OUT_DIR, "liboracle.so")
 SOURCES = [
     os.path.join(HERE, "csrc", "skimage_restated.c"),
     os.path.join(HERE, "csrc", "waterz_restated.cpp"),
+    os.path.join(HERE, "csrc", "mws_restated.cpp"),
 ]
 
 

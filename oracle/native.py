@@ -26,6 +26,26 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def mws_agglom(affs, offsets, strides=None, zero_is_repulsive=True, counters=None):
+    """mwatershed.agglom(affs float64 (C, Z, Y, X), offsets, strides) restated (post/mws.py:52-57); declared tie rule D4.
+    Returns uint64 labels (1 + smallest raveled voxel index of the cluster)."""
+    affs = np.ascontiguousarray(affs, dtype=np.float64)
+    assert affs.ndim == 4
+    Cn = affs.shape[0]
+    off = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64).reshape(Cn, 3))
+    st = None if strides is None else np.ascontiguousarray(np.asarray(strides, dtype=np.int64).reshape(Cn, 3))
+    shape = np.asarray(affs.shape[1:], dtype=np.int64)
+    out = np.empty(affs.shape[1:], dtype=np.uint64)
+    cnt = np.zeros(4, dtype=np.int64)
+    lib().mws_agglom.restype = C.c_int64
+    rc = lib().mws_agglom(_p(affs), C.c_int(Cn), _p(shape), _p(off), _p(st) if st is not None else None,
+                          C.c_int(1 if zero_is_repulsive else 0), _p(out), _p(cnt))
+    assert rc == 0, "volume too large for the oracle's 32-bit voxel indices"
+    if counters is not None:
+        counters.update(edges=int(cnt[0]), merges=int(cnt[1]), mutexes=int(cnt[2]), blocked=int(cnt[3]))
+    return out
+
+
 def sk_watershed(image, markers, mask, seed_tie="heap"):
     """skimage.segmentation.watershed(image, markers, mask=mask) restated (post/ws.py:26-28)."""
     image = np.ascontiguousarray(image, dtype=np.float64)

@@ -275,6 +275,53 @@ def golden_ws_glue():
     print("ws_glue.npz", len(out))
 
 
+def golden_mws_glue():
+    """post/mws.py executed unmodified, with the `mwatershed` package (absent here) replaced by the oracle's restatement of
+    mwatershed.agglom: pins the glue of mwatershed_from_affinities (mws.py:12-59) -- the gaussian shift, the bias broadcast,
+    the float64 cast, the offsets / strides hand-over -- given that mutex watershed.  noise_eps is None (unseeded upstream)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from bootstrapper_b200.synth import synth_affs
+    from oracle.native import mws_agglom
+    calls = []
+
+    def agglom(affs, offsets, strides=None, randomized_strides=False):
+        assert affs.dtype == np.float64 and not randomized_strides
+        calls.append((offsets, strides))
+        return mws_agglom(affs, offsets, strides)
+
+    mod = types.ModuleType("mwatershed")
+    mod.agglom = agglom
+    sys.modules["mwatershed"] = mod
+    if "scipy.ndimage.filters" not in sys.modules:
+        try:
+            import scipy.ndimage.filters  # noqa: F401
+        except Exception:  # noqa: BLE001  (removed namespace: the reference imports gaussian_filter from it)
+            import scipy.ndimage as ndi
+            f = types.ModuleType("scipy.ndimage.filters")
+            f.gaussian_filter = ndi.gaussian_filter
+            sys.modules["scipy.ndimage.filters"] = f
+    ref = load("ref_mws", f"{REF}/post/mws.py")
+    nbh = [[-1, 0, 0], [0, -1, 0], [0, 0, -1], [-2, 0, 0], [0, -5, 0], [0, 0, -5]]
+    out = {}
+    cases = [((6, 40, 36), [-0.4] * 3 + [-0.7] * 3, None, None),
+             ((5, 32, 32), [-0.5, -0.4, -0.45, -0.7, -0.6, -0.7], [1, 2, 2], [[1, 1, 1]] * 3 + [[2, 3, 3]] * 3),
+             ((4, 30, 28), [-0.3] * 3 + [-0.8] * 3, [0, 1.5, 1.5], None)]
+    for ci, (shape, bias, sigma, strides) in enumerate(cases):
+        a8 = synth_affs(shape, seed=70 + ci)
+        # six channels: the three nearest-neighbour ones twice (the long-range copies get their own weights below)
+        affs = np.concatenate([a8, a8[:, ::-1, :, :]], 0).astype(np.float64) / 255.0
+        frags = ref.mwatershed_from_affinities(affs.copy(), nbh, bias, sigma=sigma, noise_eps=None, strides=strides, randomized_strides=False)
+        out[f"affs{ci}"], out[f"frags{ci}"] = affs, frags
+        out[f"bias{ci}"] = np.array(bias, dtype=np.float64)
+        out[f"sigma{ci}"] = np.array(sigma if sigma is not None else [-1, -1, -1], dtype=np.float64)
+        out[f"strides{ci}"] = np.array(strides if strides is not None else [], dtype=np.int64)
+        assert frags.dtype == np.uint64 and len(np.unique(frags)) > 3
+    out["nbh"] = np.array(nbh, dtype=np.int64)
+    assert len(calls) == len(cases)
+    np.savez_compressed(os.path.join(OUT, "mws_glue.npz"), **out)
+    print("mws_glue.npz", len(out))
+
+
 def golden_agglomerate_glue():
     """WaterzAgglom.agglomerate_in_block (post/blockwise/waterz_agglom.py:106-170), the method body executed as it
     stands in the reference file (extracted by ast) around the reference's own MergeTree; `waterz.agglomerate` and
@@ -992,6 +1039,7 @@ if __name__ == "__main__":
     golden_filter_fragments()
     golden_compute_fragments_shift()
     golden_ws_glue()
+    golden_mws_glue()
     golden_agglomerate_glue()
     golden_watershed_in_block_glue()
     golden_simple_watershed_glue()

@@ -410,3 +410,55 @@ def test_refine_filters_pinned_against_reference():
     mapping = {i: 0 for i in remove} | merge
     assert sorted(mapping) == [int(k) for k in g["remap_keys"]]
     assert [mapping[int(k)] for k in g["remap_keys"]] == [int(v) for v in g["remap_vals"]]
+
+
+# ---------------------------------------------------------------- mutex watershed (A12)
+def test_mws_oracle_hand_cases():
+    """mwatershed.agglom restated: attractive / repulsive / mutex-blocked edges on a 4-voxel row, the declared tie rule D4
+    (equal |w|: ascending (channel, voxel)), strides, NaN edges"""
+    from oracle import native as on
+    # 0-1 attractive 0.9, 1-2 repulsive -0.8, 2-3 attractive 0.7, long range 0-2 attractive 0.6 (blocked by the 1|2 mutex)
+    a = np.zeros((2, 1, 1, 4))
+    a[0, 0, 0, 1], a[0, 0, 0, 2], a[0, 0, 0, 3] = 0.9, -0.8, 0.7
+    a[1, 0, 0, 2], a[1, 0, 0, 3] = 0.6, 0.05
+    c = {}
+    assert on.mws_agglom(a, [[0, 0, -1], [0, 0, -2]], counters=c).ravel().tolist() == [1, 1, 3, 3]
+    assert c["merges"] == 2 and c["mutexes"] == 1 and c["blocked"] == 2
+    # the same with the long-range attraction stronger than the repulsion: 0-2 merge first, then 1|2 finds one cluster
+    a[1, 0, 0, 2] = 0.95
+    assert on.mws_agglom(a, [[0, 0, -1], [0, 0, -2]]).ravel().tolist() == [1, 1, 1, 1]
+    # tie rule: 1-2 attractive 0.5 (channel 0) and 1-2... a repulsive -0.5 on channel 1 between 0 and 2 ties with the
+    # attractive 0.5 edges of channel 0: channel 0 goes first, so 0-1-2 merge before the mutex arrives
+    t = np.zeros((2, 1, 1, 3))
+    t[0, 0, 0, 1], t[0, 0, 0, 2] = 0.5, 0.5
+    t[1, 0, 0, 2] = -0.5
+    assert on.mws_agglom(t, [[0, 0, -1], [0, 0, -2]]).ravel().tolist() == [1, 1, 1]
+    assert on.mws_agglom(t[::-1].copy(), [[0, 0, -2], [0, 0, -1]]).ravel().tolist() == [1, 1, 3]   # mutex first now
+    # strides: the offset -1 edges exist only at even x
+    s = np.full((1, 1, 1, 6), 0.9)
+    assert on.mws_agglom(s, [[0, 0, -1]], strides=[[1, 1, 2]]).ravel().tolist() == [1, 2, 2, 4, 4, 6]
+    # NaN edges are skipped, zero weight is repulsive
+    s[0, 0, 0, 3] = np.nan
+    s[0, 0, 0, 4] = 0.0
+    assert on.mws_agglom(s, [[0, 0, -1]]).ravel().tolist() == [1, 1, 1, 4, 5, 5]
+
+
+def test_mws_glue_pinned_against_reference():
+    """oracle.mws.mwatershed_from_affinities == the reference's own post/mws.py run with the oracle's agglom
+    (tests/golden/mws_glue.npz, make_golden.golden_mws_glue): sigma shift, bias, strides"""
+    from oracle import mws as om
+    g = np.load(os.path.join(GOLD, "mws_glue.npz"))
+    nbh = g["nbh"].tolist()
+    for ci in range(3):
+        sigma = g[f"sigma{ci}"]
+        strides = g[f"strides{ci}"]
+        got = om.mwatershed_from_affinities(g[f"affs{ci}"].copy(), nbh, g[f"bias{ci}"].tolist(), sigma=None if sigma[0] < 0 else sigma.tolist(),
+                                            strides=None if strides.size == 0 else strides.tolist())
+        assert got.dtype == np.uint64 and np.array_equal(got, g[f"frags{ci}"])
+
+
+def test_mws_seeded_noise_is_standard_normal_like():
+    from oracle import mws as om
+    n = om.seeded_noise((3, 20, 40, 40), seed=5)
+    assert abs(n.mean()) < 0.01 and abs(n.std() - 1.0) < 0.01 and n.min() > -3.5 and n.max() < 3.5
+    assert not np.array_equal(n[0], n[1]) and np.array_equal(n, om.seeded_noise((3, 20, 40, 40), seed=5))
