@@ -275,6 +275,8 @@ def time_workload(job, config, steps, warmup, quick=False, clocks=False):
     from bootstrapper_b200 import native
     from bootstrapper_b200.sharded import ShardedSegmenter
     slab, block, context, extra = CONFIGS[config]
+    if config == 4 and job.world in (1, 2, 4):
+        slab = (1024 // max(job.world, 2) if job.world > 1 else 256, slab[1], slab[2])   # the 1024^3 volume over 2 / 4 ranks
     shape = (slab[0] * job.world, slab[1], slab[2]) if not quick else (50 * job.world, 500, 500)
     params = dict({"thresholds": THRESHOLDS}, **extra)
     seg = ShardedSegmenter(shape, block, context, params, rank=job.rank, world=job.world, device=job.dev)
@@ -359,6 +361,47 @@ def run_e2e(job, res, steps):
     return info
 
 
+def run_e2e_compact(job, res, steps):
+    """the host-buffer leg in the compact result form (include/bsnative.h): per step the affinities go up, and ONE int32 plane
+    of dense fragment numbers + the node-id table + a LUT row per threshold come down (4 bytes per voxel instead of 32);
+    the host decoder (bs_expand_compact, all host threads of this rank) is timed separately, outside the streamed region."""
+    import torch
+    from bootstrapper_b200 import native
+    seg, affs = res["seg"], res["affs"]
+    host_affs = torch.empty(affs.shape, dtype=affs.dtype, pin_memory=True)
+    host_affs.copy_(affs)
+    T = len(THRESHOLDS)
+    cap = int(np.prod(seg.vol_shape)) // 256 + 4096          # node-table capacity (the run raises if it is too small)
+    sets = [dict(dense=torch.empty(seg.own_shape, dtype=torch.int32, pin_memory=True), nodes=torch.empty(cap, dtype=torch.int64, pin_memory=True),
+                 luts=[torch.empty(cap, dtype=torch.int64, pin_memory=True) for _ in range(T)]) for _ in range(2)]
+    e_steps = max(2, min(steps, 8))
+    info = None
+    for k in range(3):
+        info = seg.run_host_compact(host_affs, sets[k % 2], wait=False)
+    seg.drain()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    job.barrier()
+    ev0.record()
+    for k in range(e_steps):
+        info = seg.run_host_compact(host_affs, sets[k % 2], wait=False)
+    seg.drain()
+    ev1.record()
+    job.barrier()
+    ms = job.max_over_ranks(ev0.elapsed_time(ev1)) / e_steps
+    n = info["n_nodes"]
+    d2h = int(np.prod(seg.own_shape)) * 4 + n * 8 * (1 + T)
+    # the decoder, on this rank's share of the host cores
+    threads = max(1, (os.cpu_count() or 1) // job.world)
+    hs = sets[(e_steps - 1) % 2]
+    outs = [torch.empty(seg.own_shape, dtype=torch.int64) for _ in range(1 + T)]
+    job.barrier()
+    t0 = time.time()
+    native.expand_compact(hs["dense"], hs["nodes"][:n].contiguous(), [l[:n].contiguous() for l in hs["luts"]], outs[0], outs[1:], threads=threads)
+    job.barrier()
+    expand_ms = job.max_over_ranks((time.time() - t0) * 1e3)
+    return dict(ms=ms, d2h=d2h, h2d=host_affs.numel(), expand_ms=expand_ms, threads=threads, n_nodes=n)
+
+
 def multi_gpu_parity(job):
     """N > 1: a small volume through the sharded path on all ranks, then rank 0 runs the same volume alone (single-GPU
     path, bit-exact vs the oracle in the tests) and compares its own slab + the global graph.  Outside every timed region."""
@@ -397,9 +440,21 @@ def run_ours(args):
     e2e = None
     if args.config == 2 and not args.no_e2e:   # (69 GB of outputs per rank for config 5) measured on the default workload only
         e2e = run_e2e(job, res, args.steps)
+    e2e_c = None
+    if args.config == 2 and not args.no_e2e:
+        e2e_c = run_e2e_compact(job, res, args.steps)
     line = None
     if job.rank == 0:
         line = report(args, job, res, e2e)
+        if e2e_c is not None:
+            V_total = float(np.prod(res["shape"]))
+            line["e2e_compact"] = {
+                "value": V_total / (e2e_c["ms"] * 1e-3), "unit": "voxels/s", "ms_per_step": e2e_c["ms"], "h2d_bytes_per_step": e2e_c["h2d"],
+                "d2h_bytes_per_step": e2e_c["d2h"], "host_decode_ms_per_volume": e2e_c["expand_ms"], "host_decode_threads_per_rank": e2e_c["threads"],
+                "what": "the same streamed host-buffer leg with the results in the library's compact form: one int32 plane of dense fragment "
+                        "numbers + node-id table + one LUT row per threshold (frags[i] = node_ids[d[i]-1], seg_t[i] = lut_t[d[i]-1]); "
+                        "host_decode_ms = bs_expand_compact rebuilding the four uint64 arrays on the host, all ranks at once, timed "
+                        "separately (not inside ms_per_step)"}
     # ---- parity, outside the timed regions: CPU oracle vs GPU on the cpu_baseline sample (N=1), sharded vs single GPU (N>1)
     parity = {}
     if job.world > 1 and not args.no_parity:

@@ -3,6 +3,10 @@
 
 #include <algorithm>
 
+#include <atomic>
+#include <thread>
+#include <vector>
+
 #include "agglom.cuh"
 
 namespace bs {
@@ -25,6 +29,7 @@ int relabel_dense(Plan &P, const uint64_t *frags, int64_t n, const uint64_t *con
 int components_multi(Plan &P, const uint64_t *nodes, int64_t n, const uint64_t *eu, const uint64_t *ev, const float *scores,
                      int64_t m, const float *thresholds, int T, uint64_t *const *comps, cudaStream_t s);
 int plan_node_ids(Plan &P, uint64_t *out, long long *n_out, cudaStream_t s);
+int dense_fragments(Plan &P, const uint64_t *frags, int64_t n, uint32_t *dense_out, cudaStream_t s);
 int cc_affs(const void *affs, int dtype, const uint8_t *mask, int Z, int Y, int X, float thr, int remove_debris, uint64_t *frags_out,
             uint64_t *seg_out, int64_t *n_out, cudaStream_t s);
 int shift_affinities(const void *affs, int dtype, const uint8_t *mask, int Z, int Y, int X, int has_sigma, const int *radius,
@@ -267,6 +272,41 @@ int bs_stage3_relabel(bs_plan *p, const uint64_t *frags, int64_t n_vox, const ui
                       uint64_t *const *segs_out, void *stream) {
     BS_ARG(p && (n_vox == 0 || (frags && components && segs_out)), "bs_stage3_relabel: null argument");
     return relabel_dense(*p->p, frags, n_vox, components, n_thresholds, segs_out, (cudaStream_t)stream);
+}
+
+int bs_stage3_dense_fragments(bs_plan *p, const uint64_t *frags, int64_t n_vox, uint32_t *dense_out, void *stream) {
+    BS_ARG(p && (n_vox == 0 || (frags && dense_out)), "bs_stage3_dense_fragments: null argument");
+    return dense_fragments(*p->p, frags, n_vox, dense_out, (cudaStream_t)stream);
+}
+
+// host side of the compact result form: dense ids + node-id table + LUT rows -> the uint64 arrays the reference writes
+int bs_expand_compact(const uint32_t *dense, int64_t n_vox, const uint64_t *node_ids, int64_t n_nodes, const uint64_t *const *luts,
+                      int n_thresholds, uint64_t *frags_out, uint64_t *const *segs_out, int n_threads) {
+    BS_ARG(n_vox == 0 || (dense && node_ids), "bs_expand_compact: null argument");
+    BS_ARG(n_thresholds >= 0 && n_thresholds <= 8, "bs_expand_compact: 0..8 thresholds");
+    for (int t = 0; t < n_thresholds; t++) BS_ARG(luts && luts[t] && segs_out && segs_out[t], "bs_expand_compact: null LUT / output");
+    const int nt = std::max(1, std::min(n_threads, 256));
+    std::vector<std::thread> pool;
+    std::atomic<int> bad(0);
+    const int64_t chunk = (n_vox + nt - 1) / nt;
+    for (int k = 0; k < nt; k++) {
+        const int64_t a = (int64_t)k * chunk, b = std::min<int64_t>(n_vox, a + chunk);
+        if (a >= b) break;
+        pool.emplace_back([=, &bad]() {
+            for (int64_t i = a; i < b; i++) {
+                const uint32_t d = dense[i];
+                if ((int64_t)d > n_nodes) {
+                    bad.store(1);
+                    continue;
+                }
+                if (frags_out) frags_out[i] = d ? node_ids[d - 1] : 0;
+                for (int t = 0; t < n_thresholds; t++) segs_out[t][i] = d ? luts[t][d - 1] : 0;
+            }
+        });
+    }
+    for (auto &th : pool) th.join();
+    BS_ARG(bad.load() == 0, "bs_expand_compact: a dense id exceeds the node table");
+    return BS_OK;
 }
 
 int bs_watershed_from_affinities(const void *affs, int aff_dtype, int Z, int Y, int X, int fragments_in_xy,

@@ -507,13 +507,14 @@ __global__ void __launch_bounds__(FR_NT, 1) k_tile_front(const Tile *__restrict_
     __syncthreads();
     // ---- P3: seeds = (maximum_filter(d2, msd, mode='reflect') == d2) & mask, separable: bands of rows whose x-filtered rows
     //          (msd - 1 extra rows, reflected at the tile border) sit in the scratch area, then the y pass per pixel.
-    //          msd == 10 (the default): a thread produces 8 neighbouring maxima from 17 inputs by doubling
-    //          (max over 2, 4, 8, then 8 + 2), lanes walk down rows (x pass) / along rows (y pass): no bank conflicts
+    //          msd == 10 (the default): a thread produces G = 8 (or 4, when the scratch area holds fewer rows) neighbouring
+    //          maxima from G + 9 inputs by doubling (max over 2, 4, 8, then 8 + 2), lanes walk down rows (x pass) / along
+    //          rows (y pass): no bank conflicts
     {
         const int lo = msd / 2;
         uint16_t *R = (uint16_t *)SCR;
         const int rows_fit = scr_work / (2 * Wp);
-        const int RB = ((rows_fit - (msd - 1)) / 8) * 8;           // rows per band (the host guarantees RB >= 8)
+        const int RB = ((rows_fit - (msd - 1)) / 4) * 4;           // rows per band (the host guarantees RB >= 4)
         for (int yb = 0; yb < H; yb += RB) {
             const int nb = min(RB, H - yb), nrows = nb + msd - 1;
             if (msd == 10) {
@@ -544,24 +545,25 @@ __global__ void __launch_bounds__(FR_NT, 1) k_tile_front(const Tile *__restrict_
                         if (x0 + k < W) dst[k] = (uint16_t)max(m8[k], m2[k + 8]);
                 }
                 __syncthreads();
-                const int ngrp = (nb + 7) >> 3;
+                // groups of 4 output rows from 13 x-filtered rows
+                const int ngrp = (nb + 3) >> 2;
                 for (int wi = warp; wi < ngrp * WW; wi += FR_NT / 32) {
                     const int rg = wi / WW, c = wi - rg * WW;
                     const int x = c * 32 + lane;
-                    uint32_t in[17];
-                    const uint16_t *colp = R + (rg * 8) * Wp + min(x, W - 1);
+                    uint32_t in[13];
+                    const uint16_t *colp = R + (rg * 4) * Wp + min(x, W - 1);
 #pragma unroll
-                    for (int k = 0; k < 17; k++) in[k] = colp[k * Wp];     // rows past the band: stale values, results unused
-                    uint32_t m2[16], m4[14], m8[10];
+                    for (int k = 0; k < 13; k++) in[k] = colp[k * Wp];     // rows past the band: stale values, results unused
+                    uint32_t m2[12], m4[10], m8[6];
 #pragma unroll
-                    for (int k = 0; k < 16; k++) m2[k] = max(in[k], in[k + 1]);
+                    for (int k = 0; k < 12; k++) m2[k] = max(in[k], in[k + 1]);
 #pragma unroll
-                    for (int k = 0; k < 14; k++) m4[k] = max(m2[k], m2[k + 2]);
+                    for (int k = 0; k < 10; k++) m4[k] = max(m2[k], m2[k + 2]);
 #pragma unroll
-                    for (int k = 0; k < 10; k++) m8[k] = max(m4[k], m4[k + 4]);
+                    for (int k = 0; k < 6; k++) m8[k] = max(m4[k], m4[k + 4]);
 #pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const int yr = rg * 8 + k;
+                    for (int k = 0; k < 4; k++) {
+                        const int yr = rg * 4 + k;
                         bool seed = false;
                         if (x < W && yr < nb) {
                             const uint32_t v = D[(yb + yr) * Wp + x];
@@ -600,27 +602,26 @@ __global__ void __launch_bounds__(FR_NT, 1) k_tile_front(const Tile *__restrict_
         }
     }
     __syncthreads();
-    // ---- P4: raster ranks of the seed pixels
-    uint16_t *wpre = (uint16_t *)SCR;                                             // [nwords] seeds before the word
-    uint32_t *par = (uint32_t *)(SCR + (((size_t)nwords * 2 + 15) & ~(size_t)15));   // [seedcap] union-find over seed ranks
-    const int seedcap = (int)((scr_work - (((size_t)nwords * 2 + 15) & ~(size_t)15)) / 4);
+    // ---- P4: raster ranks of the seed pixels: seeds before every row (a word's own offset is summed over the row's few words)
+    uint16_t *rpre = (uint16_t *)SCR;                                             // [H] seeds before the row
+    uint32_t *par = (uint32_t *)(SCR + (((size_t)H * 2 + 15) & ~(size_t)15));     // [seedcap] union-find over seed ranks
+    const int seedcap = (int)((scr_work - (((size_t)H * 2 + 15) & ~(size_t)15)) / 4);
     uint32_t nseeds = 0;
     {
-        const int per = (nwords + FR_NT - 1) / FR_NT;
-        const int w0 = tid * per;
         uint32_t c = 0;
-        for (int i = 0; i < per; i++)
-            if (w0 + i < nwords) c += __popc(B[w0 + i]);
-        uint32_t run = block_excl_scan_1024(c, wsum, nseeds);
-        for (int i = 0; i < per; i++)
-            if (w0 + i < nwords) {
-                wpre[w0 + i] = (uint16_t)min(run, 65535u);
-                run += __popc(B[w0 + i]);
-            }
+        if (tid < H)
+            for (int w = 0; w < WW; w++) c += __popc(B[tid * WW + w]);
+        const uint32_t run = block_excl_scan_1024(c, wsum, nseeds);     // H <= 512 rows, one per thread
+        if (tid < H) rpre[tid] = (uint16_t)min(run, 65535u);
     }
     const bool seeds_ok = nseeds <= (uint32_t)seedcap && nseeds < 32767u;
     if (!seeds_ok && tid == 0) atomicOr(&s_flags, FR_OVF_SEEDS);
     __syncthreads();
+    auto word_base = [&](int y, int c) -> uint32_t {      // seeds before word (y, c)
+        uint32_t b = rpre[y];
+        for (int w = 0; w < c; w++) b += __popc(B[y * WW + w]);
+        return b;
+    };
     // ---- P5: conn-1 components of the seed pixels; label = raster rank of the component's first pixel + 1
     if (seeds_ok) {
         for (uint32_t r = tid; r < nseeds; r += FR_NT) par[r] = r;
@@ -630,7 +631,8 @@ __global__ void __launch_bounds__(FR_NT, 1) k_tile_front(const Tile *__restrict_
             if (!word) continue;
             const int y = wi / WW, c = wi - y * WW;
             const uint32_t up = y > 0 ? B[wi - WW] : 0u;
-            const uint32_t base = wpre[wi];
+            const uint32_t base = word_base(y, c);
+            const uint32_t upbase = (up & word) ? word_base(y - 1, c) : 0u;   // only needed where a seed sits above a seed
             uint32_t rem = word;
             while (rem) {
                 const int bpos = __ffs(rem) - 1;
@@ -642,7 +644,7 @@ __global__ void __launch_bounds__(FR_NT, 1) k_tile_front(const Tile *__restrict_
                 } else if (c > 0 && (B[wi - 1] >> 31)) {
                     uf_union_s(par, r, r - 1);     // the previous seed in raster order is the pixel to the left
                 }
-                if ((up >> bpos) & 1u) uf_union_s(par, r, (uint32_t)wpre[wi - WW] + __popc(up & ((1u << bpos) - 1u)));
+                if ((up >> bpos) & 1u) uf_union_s(par, r, upbase + __popc(up & ((1u << bpos) - 1u)));
             }
         }
         __syncthreads();
@@ -651,7 +653,7 @@ __global__ void __launch_bounds__(FR_NT, 1) k_tile_front(const Tile *__restrict_
             const uint32_t word = B[wi];
             if (!word) continue;
             const int y = wi / WW, c = wi - y * WW;
-            const uint32_t base = wpre[wi];
+            const uint32_t base = word_base(y, c);
             uint32_t rem = word;
             while (rem) {
                 const int bpos = __ffs(rem) - 1;

@@ -92,10 +92,27 @@ struct AffOps<float> {
 // float32 for float32 input (the shift array is zeros_like(affs), in-place updates round to float32).
 struct PreRef {          // the seed_eps pre-pass tile (= read ROI of the block) a main tile looks its distances up in
     long long base;
-    int oz, oy, ox, H, W, pad_;
+    int oz, oy, ox, H, W, D;
+    long long block_id;
 };
+// seeded stand-in for numpy's unseeded randn (bsnative.h): unit-variance sum of four 16-bit uniforms
+__device__ __forceinline__ uint64_t nz_splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t nz_mixw(uint64_t x, long long w) { return nz_splitmix64(x ^ ((uint64_t)w * 0x9E3779B97F4A7C15ull)); }
+__device__ __forceinline__ double seeded_normal(uint64_t seed, long long block_id, int c, long long idx) {
+    const uint64_t h = nz_mixw(nz_mixw(nz_mixw(nz_mixw(seed, block_id), c), idx), 13);
+    const long long sum = (long long)(h & 0xFFFF) + (long long)((h >> 16) & 0xFFFF) + (long long)((h >> 32) & 0xFFFF) + (long long)(h >> 48);
+    return __dmul_rn((double)(sum - 131070), 1.7320508075688772 / 65536.0);
+}
 struct ShiftView {
-    int has_bias, has_eps, has_sigma;
+    int has_bias, has_eps, has_sigma, has_noise;
+    double noise_eps;
+    unsigned long long noise_seed;
     double bias[3];
     double eps;
     const uint32_t *D2;      // squared distance to the nearest seed, per pre-pass tile pixel
@@ -107,17 +124,19 @@ struct ShiftView {
 // inmask: voxel inside the volume and not masked out (else the normalised affinity is 0.0, to which the shift is added)
 template <typename T>
 __device__ __forceinline__ bool boundary_shifted(const T *a, size_t n, size_t i, bool inmask, int ndim, const ShiftView &S,
-                                                 double dist, long long q);
+                                                 double dist, long long q, long long block_id, long long ridx, long long rvox);
 template <>
 __device__ __forceinline__ bool boundary_shifted<uint8_t>(const uint8_t *a, size_t n, size_t i, bool inmask, int ndim,
-                                                          const ShiftView &S, double dist, long long q) {
+                                                          const ShiftView &S, double dist, long long q, long long block_id,
+                                                          long long ridx, long long rvox) {
     double v[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         if (c == 0 && ndim == 2) continue;
         double x = inmask ? __ddiv_rn((double)a[(size_t)c * n + i], 255.0) : 0.0;
         double sh = 0.0;
-        if (S.has_sigma) sh = __dsub_rn(((const double *)S.G)[(size_t)c * S.gstride + q], x);   // zeros += gaussian - affs
+        if (S.has_noise) sh = __dmul_rn(seeded_normal(S.noise_seed, block_id, c, (long long)c * rvox + ridx), S.noise_eps);   // zeros += randn * eps
+        if (S.has_sigma) sh = __dadd_rn(sh, __dsub_rn(((const double *)S.G)[(size_t)c * S.gstride + q], x));   // shift += gaussian - affs
         if (S.has_bias) sh = __dadd_rn(sh, S.bias[c]);                 // shift += bias
         if (S.has_eps) sh = __dsub_rn(sh, __dmul_rn(S.eps, dist));     // shift -= seed_eps * D
         v[c] = __dadd_rn(x, sh);
@@ -127,14 +146,17 @@ __device__ __forceinline__ bool boundary_shifted<uint8_t>(const uint8_t *a, size
 }
 template <>
 __device__ __forceinline__ bool boundary_shifted<float>(const float *a, size_t n, size_t i, bool inmask, int ndim,
-                                                        const ShiftView &S, double dist, long long q) {
+                                                        const ShiftView &S, double dist, long long q, long long block_id,
+                                                        long long ridx, long long rvox) {
     float v[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         if (c == 0 && ndim == 2) continue;
         float x = inmask ? a[(size_t)c * n + i] : 0.0f;
         float sh = 0.0f;
-        if (S.has_sigma) sh = __fsub_rn(((const float *)S.G)[(size_t)c * S.gstride + q], x);             // float32 arrays
+        // float32 shift array += float64 noise: float32(0 + n * eps)
+        if (S.has_noise) sh = __double2float_rn(__dmul_rn(seeded_normal(S.noise_seed, block_id, c, (long long)c * rvox + ridx), S.noise_eps));
+        if (S.has_sigma) sh = __fadd_rn(sh, __fsub_rn(((const float *)S.G)[(size_t)c * S.gstride + q], x));   // float32 arrays
         if (S.has_bias) sh = __double2float_rn(__dadd_rn((double)sh, S.bias[c]));                        // float32(shift + bias)
         if (S.has_eps) sh = __double2float_rn(__dsub_rn((double)sh, __dmul_rn(S.eps, dist)));            // float32(shift - eps * D)
         v[c] = __fadd_rn(x, sh);
@@ -181,13 +203,16 @@ __global__ void __launch_bounds__(256) k_mask_rowdist(const Tile *__restrict__ t
                     size_t i = inside ? rowoff + gx : 0;
                     bool inmask = inside && (!A.mask || A.mask[i] > 0);
                     double dist = 0.0;
-                    long long q = 0;
-                    if (S.has_eps || S.has_sigma) {
+                    long long q = 0, ridx = 0, rvox = 0, bid = 0;
+                    if (S.has_eps || S.has_sigma || S.has_noise) {
                         const PreRef pr = S.pre[blockIdx.y];
-                        q = pr.base + ((long long)(gz - pr.oz) * pr.H + (gy - pr.oy)) * pr.W + (gx - pr.ox);
+                        ridx = ((long long)(gz - pr.oz) * pr.H + (gy - pr.oy)) * pr.W + (gx - pr.ox);   // raveled read-ROI voxel
+                        rvox = (long long)pr.D * pr.H * pr.W;
+                        bid = pr.block_id;
+                        q = pr.base + ridx;
                         if (S.has_eps) dist = __dsqrt_rn((double)S.D2[q]);
                     }
-                    m = boundary_shifted<T>(a, nvol, i, inmask, t.ndim, S, dist, q);
+                    m = boundary_shifted<T>(a, nvol, i, inmask, t.ndim, S, dist, q, bid, ridx, rvox);
                 }
             } else {
                 if (x < W) m = pred[pbase + x] == NONE32;
@@ -1954,7 +1979,8 @@ static int build_pretiles(Plan &P, const std::vector<int> &bidx, PreTiles &R, cu
         t.base = R.Ppre;
         t.wbase = 0;
         PreRef r;
-        r.base = R.Ppre, r.oz = t.gz, r.oy = t.gy, r.ox = t.gx, r.H = t.H, r.W = t.W, r.pad_ = 0;
+        r.base = R.Ppre, r.oz = t.gz, r.oy = t.gy, r.ox = t.gx, r.H = t.H, r.W = t.W, r.D = t.D;
+        r.block_id = b.block_id;
         R.refs.push_back(r);
         long long np = (long long)t.D * t.H * t.W;
         R.Ppre += np;
@@ -2094,7 +2120,8 @@ static int stage1_front_unfused(Plan &P, const std::vector<int> &bidx, AffView A
         S.has_sigma = cfg.has_sigma;
         DevBuf D2, d_pre, gA, gB, gW;
         PreTiles R;
-        if (cfg.has_seed_eps || cfg.has_sigma) {
+        S.has_noise = cfg.has_noise, S.noise_eps = cfg.noise_eps, S.noise_seed = cfg.noise_seed;
+        if (cfg.has_seed_eps || cfg.has_sigma || cfg.has_noise) {
             g_prof.mark("s1.shift_prepass", s);
             BS_TRY(build_pretiles(P, bidx, R, s));
             if (cfg.has_seed_eps) {
@@ -2113,7 +2140,7 @@ static int stage1_front_unfused(Plan &P, const std::vector<int> &bidx, AffView A
             S.pre = d_pre.as<PreRef>();
             g_prof.mark("s1.mask_rowdist", s);
         }
-        if (cfg.has_bias || cfg.has_seed_eps || cfg.has_sigma)
+        if (cfg.has_bias || cfg.has_seed_eps || cfg.has_sigma || cfg.has_noise)
             BS_LAUNCH((k_mask_rowdist<T, 1>), gr, 256, 0, s, dt, A, S, nullptr, msk.as<uint8_t>(), g.as<uint16_t>(),
                       tileflags.as<uint32_t>());
         else
@@ -2324,7 +2351,7 @@ static int stage1_front_fused(Plan &P, AffView A, const std::vector<Tile> &tiles
     const bs_ws_config &cfg = P.cfg;
     *done = false;
     const int ntiles = (int)tiles.size();
-    if (!cfg.fragments_in_xy || cfg.has_bias || cfg.has_seed_eps || cfg.has_sigma || g_debug || g_front_version == 1 ||
+    if (!cfg.fragments_in_xy || cfg.has_bias || cfg.has_seed_eps || cfg.has_sigma || cfg.has_noise || g_debug || g_front_version == 1 ||
         g_flood_version != 0 || maxpix > F2_MAXPIX)
         return BS_OK;
     int maxH = 0, maxW = 0;
@@ -2339,8 +2366,8 @@ static int stage1_front_fused(Plan &P, AffView A, const std::vector<Tile> &tiles
     }
     if (need_fixed + 3072 + 4 * 512 > (size_t)FR_SMEM_TOTAL) return BS_OK;
     const int scr_bytes = (int)(((size_t)FR_SMEM_TOTAL - need_fixed) & ~(size_t)15);
-    if ((size_t)scr_bytes < 3072 + ((nwords_max * 2 + 15) & ~(size_t)15) + 4 * 512) return BS_OK;
-    if ((scr_bytes - 3072) / (2 * fr_pitch(maxW)) < cfg.min_seed_distance - 1 + 8) return BS_OK;   // rows of the maximum filter's band buffer
+    if ((size_t)scr_bytes < 3072 + (((size_t)maxH * 2 + 15) & ~(size_t)15) + 4 * 512) return BS_OK;
+    if ((scr_bytes - 3072) / (2 * fr_pitch(maxW)) < cfg.min_seed_distance - 1 + 4) return BS_OK;   // rows of the maximum filter's band buffer
     const int levtab = std::min(4096, (scr_bytes - 3072) / 4);   // the kernel's level-count table (scr_work / 4 entries)
 
     // ---- mask bitmap

@@ -231,6 +231,28 @@ __global__ void k_node_ids(const long long *__restrict__ nbase, const long long 
     out[i] = (uint64_t)(i - nbase[lo] + 1) + (uint64_t)bid[lo] * (uint64_t)nvox_block;
 }
 
+// fragment ids -> dense node numbers + 1 (0: background / unknown id): the compact form of a fragment volume (4 bytes per
+// voxel); together with the node-id table and one LUT row per threshold it determines fragments and all segmentations
+__global__ void __launch_bounds__(256) k_dense_ids(const uint64_t *__restrict__ frags, size_t n, IdMap idm, uint32_t n_nodes,
+                                                   uint32_t *__restrict__ dense) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t d = id_to_dense(idm, frags[i]);
+        dense[i] = (d != 0xFFFFFFFFu && d < n_nodes) ? d + 1u : 0u;
+    }
+}
+
+int dense_fragments(Plan &P, const uint64_t *frags, int64_t n, uint32_t *dense_out, cudaStream_t s) {
+    if (n == 0) return BS_OK;
+    DevBuf d_c2d;
+    IdMap idm;
+    BS_TRY(plan_idmap(P, d_c2d, &idm, s));
+    BS_LAUNCH(k_dense_ids, (unsigned)std::min<size_t>(cdiv((size_t)n, 256), 148 * 32), 256, 0, s, frags, (size_t)n, idm,
+              (uint32_t)P.block_nbase[P.blocks.size()], dense_out);
+    BS_CUDA(cudaGetLastError());
+    BS_CUDA(cudaStreamSynchronize(s));   // the id table is call-local scratch
+    return BS_OK;
+}
+
 int plan_node_ids(Plan &P, uint64_t *out, long long *n_out, cudaStream_t s) {
     const size_t nb = P.blocks.size();
     const long long n = P.block_nbase[nb];

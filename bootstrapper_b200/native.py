@@ -46,7 +46,7 @@ class WsConfig(C.Structure):
         ("block_end", C.c_int32), ("win_z0", C.c_int32), ("win_z", C.c_int32), ("filter_fragments", C.c_double), ("max_batch_voxels", C.c_int64),
         ("has_bias", C.c_int32), ("has_seed_eps", C.c_int32), ("bias", C.c_double * 3), ("seed_eps", C.c_double),
         ("has_sigma", C.c_int32), ("sigma_radius", C.c_int32 * 3), ("sigma_w", (C.c_double * SIGMA_MAXW) * 3),
-        ("block_index_offset", C.c_int32 * 3), ("pad_tail_", C.c_int32),
+        ("block_index_offset", C.c_int32 * 3), ("has_noise", C.c_int32), ("noise_eps", C.c_double), ("noise_seed", C.c_uint64),
     ]
 
 
@@ -54,7 +54,7 @@ EXPORTS = [
     "bs_last_error", "bs_launch_count", "bs_version", "bs_config_size", "bs_plan_create", "bs_plan_destroy", "bs_plan_num_blocks",
     "bs_plan_block_info", "bs_plan_set_owned", "bs_stage1_fragments", "bs_stage1_num_nodes", "bs_stage1_get_nodes",
     "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_plan_node_ids", "bs_stage2_agglomerate", "bs_stage2_num_edges",
-    "bs_stage2_get_edges", "bs_waterz_segment", "bs_cc_affs", "bs_mws_agglom", "bs_aff_errors", "bs_label_stats", "bs_shift_affinities", "bs_connected_components", "bs_stage3_components", "bs_relabel", "bs_stage3_relabel", "bs_watershed_from_affinities",
+    "bs_stage2_get_edges", "bs_waterz_segment", "bs_cc_affs", "bs_mws_agglom", "bs_aff_errors", "bs_label_stats", "bs_shift_affinities", "bs_connected_components", "bs_stage3_components", "bs_relabel", "bs_stage3_relabel", "bs_stage3_dense_fragments", "bs_expand_compact", "bs_watershed_from_affinities",
     "bs_synth_affs", "bs_debug_fetch", "bs_set_debug", "bs_set_profiling", "bs_get_profile",
     "bs_release_scratch", "bs_set_flood_version", "bs_set_front_version", "bs_set_agglom_version", "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
 ]
@@ -157,7 +157,7 @@ class Plan:
     def __init__(self, vol_shape, block_size, context, aff_dtype, roi_offset=None, roi_shape=None, n_channels=3,
                  fragments_in_xy=True, min_seed_distance=10, filter_fragments=0.1, remove_debris=64,
                  queue_bins=256, keep_cheaper=True, block_begin=-1, block_end=-1, max_batch_voxels=0, win_z0=0, win_z=0,
-                 bias=None, seed_eps=None, sigma=None, block_index_offset=None):
+                 bias=None, seed_eps=None, sigma=None, block_index_offset=None, noise_eps=None, noise_seed=0):
         """block_index_offset: absolute offset of the task ROI in voxels (dataset offset / voxel_size + roi_offset), which
         daisy's block ids are numbered from; default: roi_offset, i.e. a dataset at world offset 0."""
         cfg = WsConfig()
@@ -193,6 +193,9 @@ class Plan:
                 cfg.bias[d] = float(b[d])
         cfg.has_seed_eps = 0 if seed_eps is None else 1
         cfg.seed_eps = float(seed_eps or 0.0)
+        cfg.has_noise = 0 if noise_eps is None else 1     # watershed_frags.py:119-120, seeded (see bsnative.h)
+        cfg.noise_eps = float(noise_eps or 0.0)
+        cfg.noise_seed = int(noise_seed)
         cfg.has_sigma = 0
         if sigma is not None:   # watershed_frags.py:121-122: gaussian_filter(affs, sigma=(0, *sigma))
             if len(sigma) != 3:
@@ -351,6 +354,13 @@ class Plan:
         _check(lib().bs_stage3_relabel(self._h, _dev(frags, torch.int64), C.c_int64(frags.numel()), cp, C.c_int(T), sp, _stream()))
         return outs
 
+    def dense_fragments(self, frags, out=None):
+        """compact form of a fragment volume: int32 plane of 1 + node rank (0 = background), see include/bsnative.h"""
+        if out is None:
+            out = torch.empty(frags.shape, dtype=torch.int32, device=frags.device)
+        _check(lib().bs_stage3_dense_fragments(self._h, _dev(frags, torch.int64), C.c_int64(frags.numel()), _dev(out, torch.int32), _stream()))
+        return out
+
     # ---- debug
     def debug_fetch(self, name, dtype):
         n = C.c_int64()
@@ -380,6 +390,25 @@ def relabel(frags, lut_keys, lut_vals, out=None):
                             _dev(lut_vals, torch.int64) if lut_vals.numel() else None,
                             C.c_int64(lut_keys.numel()), _dev(out, torch.int64), _stream()))
     return out
+
+
+def expand_compact(dense, node_ids, luts, frags_out=None, segs_out=None, threads=None):
+    """HOST decoder of the compact result form (bs_expand_compact): dense int32 plane + node-id table + LUT rows (all CPU
+    tensors) -> the uint64 fragments / segmentations, written into the given CPU tensors (allocated when None)."""
+    for t in [dense, node_ids] + list(luts):
+        if t.is_cuda or not t.is_contiguous():
+            raise BsError("expand_compact works on contiguous host tensors")
+    T = len(luts)
+    if frags_out is None:
+        frags_out = torch.empty(dense.shape, dtype=torch.int64)
+    if segs_out is None:
+        segs_out = [torch.empty(dense.shape, dtype=torch.int64) for _ in range(T)]
+    lp = (C.c_void_p * max(T, 1))(*[l.data_ptr() for l in luts])
+    sp = (C.c_void_p * max(T, 1))(*[o.data_ptr() for o in segs_out])
+    _check(lib().bs_expand_compact(C.c_void_p(dense.data_ptr()), C.c_int64(dense.numel()), C.c_void_p(node_ids.data_ptr()),
+                                   C.c_int64(node_ids.numel()), lp, C.c_int(T), C.c_void_p(frags_out.data_ptr()), sp,
+                                   C.c_int(int(threads or os.cpu_count() or 1))))
+    return frags_out, segs_out
 
 
 def cc_affs(affs, threshold, remove_debris=0, mask=None):

@@ -17,13 +17,13 @@ class WatershedFrags(BlockwiseTask):
 
     def __init__(self, db, affs_data, frags_data, block_size, context, mask_data=None, num_workers=1, roi=None,
                  fragments_in_xy=True, min_seed_distance=10, seed_eps=None, epsilon_agglomerate=0.0, sigma=None,
-                 noise_eps=None, bias=None, filter_fragments=0.0, remove_debris=0):
+                 noise_eps=None, bias=None, filter_fragments=0.0, remove_debris=0, noise_seed=0):
         self.db, self.affs_data, self.frags_data, self.mask_data = db, affs_data, frags_data, mask_data
         self.block_size, self.context = tuple(int(v) for v in block_size), tuple(int(v) for v in context)
         self.num_workers, self.roi = num_workers, roi
         self.params = resolve_ws_params(dict(
             fragments_in_xy=fragments_in_xy, min_seed_distance=min_seed_distance, seed_eps=seed_eps,
-            epsilon_agglomerate=epsilon_agglomerate, sigma=sigma, noise_eps=noise_eps, bias=bias,
+            epsilon_agglomerate=epsilon_agglomerate, sigma=sigma, noise_eps=noise_eps, noise_seed=noise_seed, bias=bias,
             filter_fragments=filter_fragments, remove_debris=remove_debris))
         self._plan_obj = None
         self._frags_dev = None
@@ -58,7 +58,8 @@ class WatershedFrags(BlockwiseTask):
             p = self.params
             self._plan_obj = self._make_plan(fragments_in_xy=p["fragments_in_xy"], min_seed_distance=p["min_seed_distance"],
                                              filter_fragments=p["filter_fragments"], remove_debris=p["remove_debris"],
-                                             bias=p["bias"], seed_eps=p["seed_eps"], sigma=p["sigma"])
+                                             bias=p["bias"], seed_eps=p["seed_eps"], sigma=p["sigma"],
+                                             noise_eps=p["noise_eps"], noise_seed=p.get("noise_seed", 0) or 0)
         return self._plan_obj
 
     def _mask_dev(self):

@@ -13,9 +13,11 @@ from .. import native
 WS_DEFAULTS = dict(  # reference segment.py:11-23
     fragments_in_xy=True, min_seed_distance=10, seed_eps=None, epsilon_agglomerate=0.0,
     filter_fragments=0.1, remove_debris=64, thresholds=[0.2, 0.35, 0.5], merge_function="mean",
-    sigma=None, noise_eps=None, bias=None)
+    sigma=None, noise_eps=None, bias=None, noise_seed=0)
 
-UNSUPPORTED = ("noise_eps",)   # an unseeded RNG in the reference (watershed_frags.py:119-120): not reproducible
+UNSUPPORTED = ()
+# noise_eps: the reference draws an UNSEEDED np.random.randn per block (watershed_frags.py:119-120); the CUDA path uses a seeded
+# counter-based generator instead (extra parameter noise_seed, default 0; include/bsnative.h) that the oracle mirrors
 
 
 def resolve_ws_params(params):
@@ -91,7 +93,8 @@ def make_plan(affs, params, block_size, context=None, roi=None, **kw):
     return native.Plan(vol_shape, block_size, context, native._aff_dtype(affs), roi_offset=roi_offset,
                        roi_shape=roi_shape, n_channels=affs.shape[0], fragments_in_xy=p["fragments_in_xy"],
                        min_seed_distance=p["min_seed_distance"], filter_fragments=p["filter_fragments"],
-                       remove_debris=p["remove_debris"], bias=p["bias"], seed_eps=p["seed_eps"], sigma=p["sigma"], **kw), p
+                       remove_debris=p["remove_debris"], bias=p["bias"], seed_eps=p["seed_eps"], sigma=p["sigma"],
+                       noise_eps=p["noise_eps"], noise_seed=p.get("noise_seed", 0) or 0, **kw), p
 
 
 def segment_blockwise(affs, params=None, block_size=None, context=None, roi=None, mask=None, plan=None,

@@ -62,7 +62,8 @@ def waterz_pipeline(config):
 
     # stage 1: fragments via seeded watershed
     frags_task = WatershedFrags(db=db, affs_data=affinities, frags_data=fragments, mask_data=mask_data,
-                                block_size=block_size, context=ctx, num_workers=num_workers, roi=total_roi, **frag_params)
+                                block_size=block_size, context=ctx, num_workers=num_workers, roi=total_roi,
+                                noise_seed=config.get("noise_seed", 0), **frag_params)
     run_volara_task(frags_task, blockwise)
     dump_params(frags_ds_name, {"method": "ws", "blockwise": blockwise, **frag_params})
 

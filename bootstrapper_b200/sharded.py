@@ -260,6 +260,7 @@ class ShardedSegmenter:
                                     fragments_in_xy=self.p["fragments_in_xy"], min_seed_distance=self.p["min_seed_distance"],
                                     filter_fragments=self.p["filter_fragments"], remove_debris=self.p["remove_debris"],
                                     bias=self.p["bias"], seed_eps=self.p["seed_eps"], sigma=self.p["sigma"],
+                                    noise_eps=self.p["noise_eps"], noise_seed=self.p.get("noise_seed", 0) or 0,
                                     block_begin=g["l0"] if self.world > 1 else -1, block_end=g["l1"] if self.world > 1 else -1,
                                     **win)
             self.block_ids, _, _ = self.plan.block_info()
@@ -270,7 +271,7 @@ class ShardedSegmenter:
         g = self.geo
         return native.synth_affs(self.win_shape, seed=seed, dtype=dtype, offset=(g["w0"], 0, 0), device=self.device)
 
-    def run(self, affs_win, out=None, frag_sink=None, out_ready=None):
+    def run(self, affs_win, out=None, frag_sink=None, out_ready=None, relabel=True):
         """affs_win: (C, w1-w0, Y, X) on this rank's device.  Returns dict with the fragment window, the
         segmentations of the own planes per threshold and the global graph."""
         plan = self._plan(native._aff_dtype(affs_win))
@@ -317,7 +318,7 @@ class ShardedSegmenter:
         if out_ready is not None:
             # `out` is still being read by an earlier volume's device->host copies: only the relabel waits for them
             torch.cuda.current_stream().wait_event(out_ready)
-        for i in range(0, len(thrs), 8):
+        for i in range(0, len(thrs) if relabel else 0, 8):
             for thr, sg in zip(thrs[i:i + 8], plan.relabel(own, comps[i:i + 8], None if out is None else out[i:i + 8])):
                 segs[thr] = sg
         evs[3].record()
@@ -372,9 +373,43 @@ class ShardedSegmenter:
         elif done is not None:
             done.synchronize()
 
+    def run_host_compact(self, host_affs, host_out, wait=True):
+        """end-to-end with HOST buffers in the compact result form (include/bsnative.h): pinned affinities in; out come ONE
+        int32 plane of dense fragment numbers for the own planes, the node-id table and a LUT row per threshold -- 4 bytes
+        per voxel across the bus instead of 8 (T + 1).  native.expand_compact rebuilds the uint64 arrays on the host.
+        host_out: dict(dense=pinned int32 (own_shape), nodes=pinned int64 (capacity,), luts=[pinned int64 (capacity,)] * T),
+        filled in place; returns dict(n_nodes=...) (the tables hold n_nodes valid entries).
+        wait=False: as run_host -- alternate between two sets of host_out and call drain() before reading the last one."""
+        affs = host_affs.to(self.device, non_blocking=True)
+        r = self.run(affs, relabel=False)
+        g = self.geo
+        dense = self.plan.dense_fragments(r["own_fragments"])
+        n = r["nodes"].numel()
+        if n > host_out["nodes"].numel():
+            raise native.BsError(f"compact host tables hold {host_out['nodes'].numel()} nodes, the volume has {n}")
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ready)
+            host_out["dense"].copy_(dense, non_blocking=True)
+            host_out["nodes"][:n].copy_(r["nodes"], non_blocking=True)
+            for i, thr in enumerate(self.p["thresholds"]):
+                host_out["luts"][i][:n].copy_(r["luts"][thr], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._copy_stream)
+        self._inflight.append((done, (r, dense), affs, None))
+        while len(self._inflight) > (0 if wait else 2):
+            self._wait_done(self._inflight.pop(0)[0])
+        return dict(n_nodes=n)
+
     def drain(self):
         """wait for the device->host copies of every volume queued by run_host(wait=False)"""
         while self._inflight:
             self._wait_done(self._inflight.pop(0)[0])
         if getattr(self, "_ring", None) is not None:
-            self._ring.flush()
+            if self._ring.thread.is_alive():
+                self._ring.flush()
+            else:
+                self._ring = None          # closed by its owner

@@ -68,7 +68,12 @@ typedef struct bs_ws_config {
      * offsets.  block_index_offset = the task ROI's absolute offset in voxels (dataset offset / voxel_size + roi_offset);
      * the grid index that is numbered is floor((block_index_offset + i * block_size) / block_size) per axis.           */
     int32_t block_index_offset[3];
-    int32_t pad_tail_;
+    /* ws_params.noise_eps (watershed_frags.py:119-120: shift += np.random.randn(*affs.shape) * noise_eps, an UNSEEDED draw per
+     * block upstream): a seeded counter-based generator stands in -- unit-variance sum of four 16-bit uniforms from a SplitMix64
+     * hash of (noise_seed, block id, channel, raveled read-ROI voxel) -- mirrored bit for bit by the oracle */
+    int32_t has_noise;
+    double noise_eps;
+    uint64_t noise_seed;
 } bs_ws_config;
 
 typedef struct bs_plan bs_plan;
@@ -168,6 +173,17 @@ int bs_relabel(const uint64_t *frags, int64_t n_vox, const uint64_t *lut_keys, c
  * `components` / `segs_out` are HOST arrays of device pointers. */
 int bs_stage3_relabel(bs_plan *p, const uint64_t *frags, int64_t n_vox, const uint64_t *const *components, int n_thresholds,
                       uint64_t *const *segs_out, void *stream);
+
+/* ---- compact results (not in the reference: a transport form for callers on the far side of PCIe) ----------------------
+ * Fragments and all T segmentations of a volume are functions of ONE 32-bit plane: dense[i] = 1 + the rank of frags[i] in the
+ * ascending node list (0 = background), plus the node-id table (bs_plan_node_ids) and the T LUT rows of bs_stage3_components:
+ *     frags[i] = node_ids[dense[i] - 1],   seg_t[i] = components_t[dense[i] - 1].
+ * 4 bytes per voxel cross the bus instead of 8 (T + 1).  bs_expand_compact rebuilds the uint64 arrays on the HOST (plain
+ * host pointers, n_threads worker threads); it is a decoder of this library's own format, not a CPU implementation of
+ * the path. */
+int bs_stage3_dense_fragments(bs_plan *p, const uint64_t *frags, int64_t n_vox, uint32_t *dense_out, void *stream);
+int bs_expand_compact(const uint32_t *dense, int64_t n_vox, const uint64_t *node_ids, int64_t n_nodes, const uint64_t *const *luts,
+                      int n_thresholds, uint64_t *frags_out, uint64_t *const *segs_out, int n_threads);
 
 /* ---- `bs segment --cc` -----------------------------------------------------------------
  * replaces: cc_affs + compute_connected_component_segmentation (post/connected_components.py:15-127,

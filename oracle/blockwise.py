@@ -99,11 +99,27 @@ def to_ndarray(vol, offset, shape, fill_value=0):
 
 
 # --------------------------------------------------------------------------- stage 1
-def compute_fragments(affs_data, p, seed_tie="heap"):
-    """watershed_frags.py:115-146 (noise_eps is unseeded in the reference -> must be None)."""
+def seeded_noise_block(shape, seed, block_id):
+    """float64 (3, Z, Y, X): the seeded stand-in for the reference's unseeded np.random.randn(*affs_data.shape) of one block
+    (watershed_frags.py:119-120): unit-variance sum of four 16-bit uniforms from a SplitMix64 hash of (seed, block id,
+    channel, raveled voxel of the 4-D array), the generator csrc/stage1.cu implements bit for bit"""
+    from bootstrapper_b200.synth import _hash
+    n = int(np.prod(shape))
+    nv = int(np.prod(shape[1:]))
+    idx = np.arange(n, dtype=np.int64)
+    h = _hash(seed, np.full(n, int(block_id), dtype=np.int64), idx // nv, idx, np.full(n, 13, dtype=np.int64))
+    s = ((h & np.uint64(0xFFFF)).astype(np.int64) + ((h >> np.uint64(16)) & np.uint64(0xFFFF)).astype(np.int64)
+         + ((h >> np.uint64(32)) & np.uint64(0xFFFF)).astype(np.int64) + (h >> np.uint64(48)).astype(np.int64))
+    return ((s - 131070).astype(np.float64) * (np.sqrt(3.0) / 65536.0)).reshape(shape)
+
+
+def compute_fragments(affs_data, p, seed_tie="heap", block_id=0):
+    """watershed_frags.py:115-146; noise_eps draws from the seeded generator (p["noise_seed"], block id) instead of the
+    reference's unseeded np.random.randn."""
     affs_data = affs_data[:3]
     shift = np.zeros_like(affs_data)
-    assert p.get("noise_eps") is None, "noise_eps is an unseeded RNG in the reference"
+    if p.get("noise_eps") is not None:
+        shift += seeded_noise_block(affs_data.shape, p.get("noise_seed", 0) or 0, block_id) * p["noise_eps"]
     if p.get("sigma") is not None:
         shift += gaussian_filter(affs_data, sigma=(0, *p["sigma"])) - affs_data
     if p.get("bias") is not None:
@@ -152,9 +168,9 @@ def remove_small_objects(x, min_size):
     return out
 
 
-def get_fragments(affs_data, p, seed_tie="heap", stats_mode="faithful"):
+def get_fragments(affs_data, p, seed_tie="heap", stats_mode="faithful", block_id=0):
     """watershed_frags.py:179-194."""
-    fragments_data = compute_fragments(affs_data, p, seed_tie)
+    fragments_data = compute_fragments(affs_data, p, seed_tie, block_id)
     if p["epsilon_agglomerate"] > 0:
         fragments_data = epsilon_agglomerate_fragments(affs_data, fragments_data,
                                                        p["epsilon_agglomerate"], stats_mode)
@@ -194,7 +210,7 @@ def watershed_in_block(block, affs, frags_out, rag, p, roi_offset, block_size, m
         if np.max(mask_data) == 255:
             mask_data = (mask_data > 0).astype(np.uint8)
         affs_data *= mask_data
-    fragments_data = get_fragments(affs_data, p, seed_tie, stats_mode)
+    fragments_data = get_fragments(affs_data, p, seed_tie, stats_mode, block.block_id)
     # crop to the write roi
     c0 = [w - r for w, r in zip(block.write_offset, block.read_offset)]
     sl = tuple(slice(c, c + s) for c, s in zip(c0, block.write_shape))

@@ -72,6 +72,9 @@ CASES = [
     ((12, 120, 120), (6, 60, 60), (2, 8, 8), {"sigma": [1, 2, 2]}, np.uint8),
     ((12, 100, 100), (6, 50, 50), (2, 6, 6), {"sigma": [0, 1.5, 0.8], "fragments_in_xy": False}, np.float32),
     ((12, 100, 100), (6, 50, 50), (1, 6, 6), {"sigma": [3, 1, 1], "bias": [-0.05, -0.05, -0.05], "seed_eps": 0.01}, np.uint8),
+    # noise_eps: a seeded generator (noise_seed) stands in for the reference's unseeded randn, drawn per block read ROI
+    ((12, 120, 120), (6, 60, 60), (1, 8, 8), {"noise_eps": 0.05, "noise_seed": 3}, np.uint8),
+    ((12, 100, 100), (6, 50, 50), (2, 6, 6), {"noise_eps": 0.02, "sigma": [0, 1, 1], "bias": 0.03, "fragments_in_xy": False}, np.float32),
 ]
 
 
@@ -156,6 +159,7 @@ FRONT_CASES = [
     ((10, 100, 100), (5, 50, 50), (1, 6, 6), {}, np.float32, False),
     ((4, 400, 330), (2, 400, 330), (0, 0, 0), {}, np.uint8, False),               # one large tile per slice (>= 2^17 pixels: unfused only)
     ((4, 300, 320), (2, 300, 320), (0, 0, 0), {}, np.uint8, False),               # one tile per slice, near the shared-memory limit
+    ((2, 320, 320), (1, 256, 256), (0, 32, 32), {}, np.uint8, False),             # BASELINE config-5 tiles: 320 x 320, the smallest scratch area
 ]
 
 
@@ -571,6 +575,31 @@ def test_run_host_ring_matches_blocking():
         for i, t in enumerate(thrs):
             assert torch.equal(got[(("seg", t), k)], ref[k][1 + i])
     assert ring.chunks_done == len(vols) * 3 * 3
+
+
+def test_run_host_compact_expands_to_the_blocking_result():
+    """ShardedSegmenter.run_host_compact: one int32 plane + node table + LUT rows cross the bus; the host decoder
+    (bs_expand_compact) rebuilds exactly the uint64 arrays run_host delivers"""
+    from bootstrapper_b200 import native
+    from bootstrapper_b200.sharded import ShardedSegmenter
+    from bootstrapper_b200.synth import synth_affs
+    shape, block, ctx = (12, 120, 120), (6, 60, 60), (1, 8, 8)
+    thrs = [0.2, 0.5]
+    seg = ShardedSegmenter(shape, block, ctx, {"thresholds": thrs}, device=torch.device("cuda"))
+    cap = 1 << 16
+    for s_ in (1, 2):
+        v = torch.from_numpy(synth_affs(shape, seed=s_)).pin_memory()
+        ho = [torch.empty(shape, dtype=torch.int64).pin_memory() for _ in range(3)]
+        seg.run_host(v, ho)
+        comp = dict(dense=torch.empty(shape, dtype=torch.int32).pin_memory(), nodes=torch.empty(cap, dtype=torch.int64).pin_memory(),
+                    luts=[torch.empty(cap, dtype=torch.int64).pin_memory() for _ in thrs])
+        info = seg.run_host_compact(v, comp)
+        n = info["n_nodes"]
+        assert n > 0 and int(comp["dense"].max()) == n
+        frags, segs = native.expand_compact(comp["dense"], comp["nodes"][:n].contiguous(), [l[:n].contiguous() for l in comp["luts"]], threads=3)
+        assert torch.equal(frags, ho[0])
+        for a, b in zip(segs, ho[1:]):
+            assert torch.equal(a, b)
 
 
 # ---------------------------------------------------------------- `bs refine` filters (SURVEY 8f N4)
