@@ -971,6 +971,93 @@ __global__ void __launch_bounds__(64) k_flood(const Tile *__restrict__ tiles, in
     }
 }
 
+// ------------------------------------------------------------------ faithful flood (bs_set_flood_version(6))
+// skimage's watershed loop replayed literally, one thread per tile: a binary heap ordered by (value, age) -- here (level
+// descending, age ascending) -- with skimage's own layout rules (parent = (child + 1) / 2 - 1; pop = swap the last element
+// to the root, sift down preferring the left child unless the right one is strictly smaller than the smaller so far), all
+// seeds pushed with age 0 in ascending raveled index.  Equal-valued seeds therefore leave the heap in the order its
+// layout history dictates, which is what the reference does and what the default floods replace by the index rule
+// (declared deviation D1).  Sequential and latency bound (~10^2 slower than the default flood): for parity runs.
+struct HeapRef {
+    uint32_t *lv, *age, *pix;
+};
+__device__ __forceinline__ bool heap_smaller(const HeapRef &h, uint32_t a, uint32_t b) {
+    const uint32_t la = h.lv[a], lb = h.lv[b];
+    if (la != lb) return la > lb;          // larger level = smaller skimage value
+    return h.age[a] < h.age[b];
+}
+__device__ __forceinline__ void heap_swap(const HeapRef &h, uint32_t a, uint32_t b) {
+    const uint32_t l = h.lv[a], g = h.age[a], p = h.pix[a];
+    h.lv[a] = h.lv[b], h.age[a] = h.age[b], h.pix[a] = h.pix[b];
+    h.lv[b] = l, h.age[b] = g, h.pix[b] = p;
+}
+__global__ void __launch_bounds__(32) k_flood_heap(const Tile *__restrict__ tiles, int ntiles, uint32_t *__restrict__ lab_all,
+                                                   const uint32_t *__restrict__ lv_all, const uint32_t *__restrict__ seedlist,
+                                                   const uint32_t *__restrict__ tile_seed, uint32_t *__restrict__ hlv,
+                                                   uint32_t *__restrict__ hage, uint32_t *__restrict__ hpix) {
+    const int wid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wid >= ntiles) return;
+    const Tile t = tiles[wid];
+    uint32_t *lab = lab_all + t.base;
+    const uint32_t *lv = lv_all + t.base;
+    HeapRef h;
+    h.lv = hlv + t.base, h.age = hage + t.base, h.pix = hpix + t.base;
+    const int W = t.W, H = t.H, D = t.D;
+    const uint32_t HW = (uint32_t)H * W;
+    uint32_t n = 0;
+    auto push = [&](uint32_t level, uint32_t age, uint32_t p) {
+        uint32_t child = n++;
+        h.lv[child] = level, h.age[child] = age, h.pix[child] = p;
+        while (child > 0) {
+            const uint32_t parent = (child + 1) / 2 - 1;
+            if (!heap_smaller(h, child, parent)) break;
+            heap_swap(h, child, parent);
+            child = parent;
+        }
+    };
+    for (uint32_t s0 = tile_seed[wid]; s0 < tile_seed[wid + 1]; s0++) {
+        const uint32_t p = seedlist[s0];
+        push(lv[p], 0u, p);
+    }
+    uint32_t age = 1;
+    while (n > 0) {
+        const uint32_t p = h.pix[0];
+        n--;
+        if (n > 0) {
+            heap_swap(h, 0, n);
+            uint32_t i = 0, smallest = 0;
+            for (;;) {
+                const uint32_t l = 2 * i + 1, r = 2 * i + 2;
+                if (l >= n) break;
+                if (heap_smaller(h, l, i)) smallest = l;
+                if (r < n && heap_smaller(h, r, smallest)) smallest = r;
+                if (smallest == i) break;
+                heap_swap(h, i, smallest);
+                i = smallest;
+            }
+        }
+        const uint32_t mylab = lab[p];
+        const int z = (int)(p / HW);
+        const uint32_t rem = p - (uint32_t)z * HW;
+        const int y = (int)(rem / (uint32_t)W), x = (int)(rem - (uint32_t)y * W);
+        // neighbour order of skimage (connectivity 1): -z, -y, -x, +x, +y, +z
+        uint32_t nb[6];
+        nb[0] = z > 0 ? p - HW : NONE32;
+        nb[1] = y > 0 ? p - W : NONE32;
+        nb[2] = x > 0 ? p - 1 : NONE32;
+        nb[3] = x + 1 < W ? p + 1 : NONE32;
+        nb[4] = y + 1 < H ? p + W : NONE32;
+        nb[5] = z + 1 < D ? p + HW : NONE32;
+        for (int k = 0; k < 6; k++) {
+            const uint32_t q = nb[k];
+            if (q == NONE32 || lab[q] != UNLAB) continue;    // outside the mask or labelled already
+            age++;
+            lab[q] = mylab;                                  // labelled at push time
+            push(lv[q], age, q);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ flood v3 (any tile; one CTA per tile)
 // The step semantics of k_flood with F3_NT queue entries per step instead of 32: tiles that flood v2 cannot take (3-D
 // read ROIs, slices beyond 2^17 pixels) hold millions of pixels in a few thousand levels, so a level's FIFO feeds a whole
@@ -2179,7 +2266,7 @@ static int stage1_front_unfused(Plan &P, const std::vector<int> &bidx, AffView A
     const size_t Htot = h_tot[0], nseeds = h_tot[1];
     F.nseeds = nseeds;
     // flood v2 (on-chip state) needs 2-D tiles of <= 2^17 pixels, 15-bit labels and 16-bit levels
-    const bool v2 = xy && g_flood_version != 1 && maxpix <= F2_MAXPIX && h_tot[5] < 32767 && h_tot[6] < 65535;
+    const bool v2 = xy && g_flood_version != 1 && g_flood_version != 6 && maxpix <= F2_MAXPIX && h_tot[5] < 32767 && h_tot[6] < 65535;
     F.v2 = v2;
 
     g_prof.mark("s1.levels", s);
@@ -2240,7 +2327,7 @@ static int stage1_front_unfused(Plan &P, const std::vector<int> &bidx, AffView A
     // (host sync: the largest number of levels in one tile), else to the one-warp kernel
     int levcap3 = 0;
     bool flood3 = false;
-    if (!v2 && g_flood_version != 1) {
+    if (!v2 && g_flood_version != 1 && g_flood_version != 6) {
         BS_LAUNCH(k_tile_nlev_max, cdiv(ntiles, 256), 256, 0, s, tile_lvl.as<uint32_t>(), ntiles, d_tot + 7);
         uint32_t h_nlev = 0;
         BS_CUDA(cudaMemcpyAsync(&h_nlev, d_tot + 7, 4, cudaMemcpyDeviceToHost, s));
@@ -2297,6 +2384,15 @@ static int stage1_front_unfused(Plan &P, const std::vector<int> &bidx, AffView A
         BS_LAUNCH(k_flood3, ntiles, F3_NT, flood3_smem(levcap3), s, dt, ntiles, lab.as<uint32_t>(), lv.as<uint32_t>(),
                   queue.as<uint32_t>(), lvl_qstart.as<uint32_t>(), tile_lvl.as<uint32_t>(), seedlist.as<uint32_t>(),
                   tile_seed.as<uint32_t>(), levcap3, fstats.as<uint32_t>());
+    } else if (g_flood_version == 6) {
+        // the faithful heap (skimage's own seed ties): three 32-bit planes of heap storage, a tile's heap at its pixel base
+        DevBuf hl, ha, hp;
+        BS_TRY(hl.alloc(4 * (size_t)P_pix, s));
+        BS_TRY(ha.alloc(4 * (size_t)P_pix, s));
+        BS_TRY(hp.alloc(4 * (size_t)P_pix, s));
+        BS_LAUNCH(k_flood_heap, cdiv((size_t)ntiles, 32), 32, 0, s, dt, ntiles, lab.as<uint32_t>(), lv.as<uint32_t>(), seedlist.as<uint32_t>(),
+                  tile_seed.as<uint32_t>(), hl.as<uint32_t>(), ha.as<uint32_t>(), hp.as<uint32_t>());
+        BS_CUDA(cudaStreamSynchronize(s));
     } else {
         BS_LAUNCH(k_flood, cdiv((size_t)ntiles * 32, 64), 64, 0, s, dt, ntiles, lab.as<uint32_t>(), lv.as<uint32_t>(),
                   queue.as<uint32_t>(), lvl_qstart.as<uint32_t>(), lvl_head.as<uint32_t>(), lvl_tail.as<uint32_t>(),

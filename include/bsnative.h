@@ -264,7 +264,8 @@ int bs_debug_fetch(const bs_plan *p, const char *name, void *dst_host, int64_t *
 int bs_set_debug(int on);
 /* flood kernel: 0 = automatic (v2 for 2-D tiles up to 2^17 pixels, else the CTA-per-tile kernel v3), 1 = one-warp
  * global-memory flood (v1) everywhere, 2 = v2 with the tile bitmap in shared memory, 3 = v2 with the tile bitmap in
- * global memory (every tile resident at once), 4 = 3 + level tails in shared memory */
+ * global memory (every tile resident at once), 4 = 3 + level tails in shared memory, 6 = the FAITHFUL flood: skimage's binary heap
+ * replayed literally, one thread per tile (seed ties as the reference resolves them: no deviation D1; ~10^2 slower) */
 int bs_set_flood_version(int v);
 /* stage-1 front end (mask ... priority levels): 0 = automatic (the fused on-chip kernels for 2-D tiles of unshifted affinities
  * that fit one CTA's shared memory, else the unfused chain), 1 = unfused chain, 2 = fused with vector loads only,

@@ -215,6 +215,30 @@ def test_front_saturated_tiles():
     _check(r, _oracle(half, p, (1, 200, 200), (0, 0, 0)))
 
 
+@pytest.mark.parametrize("shape,block,ctx,params,differs", [
+    ((10, 250, 250), (5, 125, 125), (1, 16, 16), {}, True),        # large enough for heap-history seed ties to show
+    ((9, 131, 173), (5, 64, 64), (1, 8, 8), {"min_seed_distance": 4}, False),
+    ((16, 96, 96), (8, 48, 48), (1, 6, 6), {"fragments_in_xy": False}, True),
+])
+def test_faithful_flood_matches_heap_oracle(shape, block, ctx, params, differs):
+    """bs_set_flood_version(6): skimage's binary heap replayed literally on the device -- the whole pipeline then equals
+    the oracle's FAITHFUL mode (seed_tie="heap"), i.e. without declared deviation D1"""
+    from bootstrapper_b200 import native
+    from bootstrapper_b200.synth import synth_affs
+    from oracle.blockwise import waterz_pipeline
+    affs = synth_affs(shape, seed=23)
+    try:
+        native.set_flood_version(6)
+        r = _run_gpu(affs, params, block, ctx)
+    finally:
+        native.set_flood_version(0)
+    ref = waterz_pipeline(affs, params, block_size=block, context=ctx, seed_tie="heap", stats_mode="canonical")
+    _check(r, ref)
+    if differs:   # the heap order does differ from the index rule on this input (else the case would prove nothing)
+        ref_index = waterz_pipeline(affs, params, block_size=block, context=ctx, seed_tie="index", stats_mode="canonical")
+        assert not np.array_equal(ref["fragments"], ref_index["fragments"])
+
+
 def test_flood_versions_agree():
     """the flood kernels (1: global-memory v1, 2: v2 with the bitmap in shared memory, 3: v2 with the bitmap in global
     memory, 4: 3 + level tails in shared memory, 0: automatic choice) are the same function"""
