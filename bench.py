@@ -393,7 +393,7 @@ def run_e2e_compact(job, res, steps):
     # the decoder, on this rank's share of the host cores
     threads = max(1, (os.cpu_count() or 1) // job.world)
     hs = sets[(e_steps - 1) % 2]
-    outs = [torch.empty(seg.own_shape, dtype=torch.int64) for _ in range(1 + T)]
+    outs = [torch.zeros(seg.own_shape, dtype=torch.int64) for _ in range(1 + T)]    # touched: no first-use page faults in the timing
     job.barrier()
     t0 = time.time()
     native.expand_compact(hs["dense"], hs["nodes"][:n].contiguous(), [l[:n].contiguous() for l in hs["luts"]], outs[0], outs[1:], threads=threads)

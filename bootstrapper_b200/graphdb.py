@@ -52,11 +52,21 @@ class SQLiteRag:
             con.executemany("INSERT OR REPLACE INTO edges VALUES (?, ?, ?)",
                             zip(u.astype(np.int64).tolist(), v.astype(np.int64).tolist(), sc))
 
-    def read_graph(self):
-        """-> nodes (N,) uint64 ascending, edges (E,2) uint64, scores (E,) float32 (NaN = NULL)"""
+    def read_graph(self, roi=None):
+        """-> nodes (N,) uint64 ascending, edges (E,2) uint64, scores (E,) float32 (NaN = NULL).
+        roi = (offset, shape) in world units: only the nodes positioned inside it and the edges whose node u lies inside it
+        (funlib.persistence read_graph(roi) as post/watershed.py:156 calls it with total_roi)."""
         with self._con() as con:
-            nodes = np.array([r[0] for r in con.execute("SELECT id FROM nodes ORDER BY id")], dtype=np.int64)
-            rows = list(con.execute("SELECT u, v, merge_score FROM edges"))
+            if roi is None:
+                nodes = np.array([r[0] for r in con.execute("SELECT id FROM nodes ORDER BY id")], dtype=np.int64)
+                rows = list(con.execute("SELECT u, v, merge_score FROM edges"))
+            else:
+                lo = [int(v) for v in roi[0]]
+                hi = [int(o) + int(n) for o, n in zip(roi[0], roi[1])]
+                cond = " AND ".join(f"position_{d} >= ? AND position_{d} < ?" for d in range(3))
+                args = [v for d in range(3) for v in (lo[d], hi[d])]
+                nodes = np.array([r[0] for r in con.execute(f"SELECT id FROM nodes WHERE {cond} ORDER BY id", args)], dtype=np.int64)
+                rows = list(con.execute(f"SELECT u, v, merge_score FROM edges WHERE u IN (SELECT id FROM nodes WHERE {cond})", args))
         edges = np.array([(r[0], r[1]) for r in rows], dtype=np.int64).reshape(-1, 2)
         scores = np.array([np.nan if r[2] is None else r[2] for r in rows], dtype=np.float32)
         return nodes.view(np.uint64), edges.view(np.uint64), scores
@@ -70,14 +80,15 @@ def open_db(db_config):
 
 
 class LUT:
-    """volara.lut.LUT: `<path>.npz` with `fragment_segment_lut` = (2, N) uint64."""
+    """volara.lut.LUT: `<path>.npz` with `fragment_segment_lut` = (2, N) uint64 and the `edges` key volara's
+    save(lut, edges=None) always writes (None for the ws pipeline, post/watershed.py:187-188)."""
 
     def __init__(self, path):
         self.path = path
 
-    def save(self, lut):
+    def save(self, lut, edges=None):
         os.makedirs(os.path.dirname(os.path.abspath(self.path)), exist_ok=True)
-        np.savez_compressed(self.path + ".npz", fragment_segment_lut=np.asarray(lut, dtype=np.uint64))
+        np.savez_compressed(self.path + ".npz", fragment_segment_lut=np.asarray(lut, dtype=np.uint64), edges=edges)
 
     def load(self):
         return np.load(self.path + ".npz")["fragment_segment_lut"]

@@ -75,7 +75,7 @@ def waterz_pipeline(config):
     run_volara_task(agglom_task, blockwise)
 
     # stage 3: thresholded connected components -> LUT -> relabel
-    nodes, edges, scores = db.read_graph()
+    nodes, edges, scores = db.read_graph(total_roi)          # post/watershed.py:156: read_graph(total_roi)
     if nodes.size == 0:
         logger.warning("empty RAG; no fragments to agglomerate")
         return

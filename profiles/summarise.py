@@ -32,7 +32,8 @@ METRICS = [
     "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
 ]
-STAGE = {"k_flood2": "s1.flood", "k_rag_accumulate": "s2.rag", "k_agglomerate_par": "s2.agglomerate"}
+STAGE = {"k_flood2": "s1.flood", "k_rag_accumulate": "s2.rag", "k_agglomerate_par": "s2.agglomerate", "k_tile_front": "s1.tile_front",
+         "k_mask_bits_u8": "s1.mask_bits", "k_finalize": "s1.finalize", "k_fragstats": "s1.fragstats", "k_relabel_dense": "s3.relabel"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 

@@ -58,6 +58,24 @@ def test_config2_full_size_matches_oracle():
     assert n["fragments"] > 100_000 and n["edges"] > n["fragments"]
 
 
+def test_config2_full_size_faithful_flood_matches_heap_oracle():
+    """the same workload through the FAITHFUL flood (bs_set_flood_version(6): skimage's binary heap replayed literally, seed
+    ties as the reference resolves them) against the oracle's faithful mode seed_tie="heap": no declared deviation D1"""
+    from bootstrapper_b200 import native
+    from bootstrapper_b200.post.pipeline import segment_blockwise
+    from oracle.parallel import waterz_pipeline_parallel
+    shape, block, ctx = (125, 1250, 1250), (25, 250, 250), (3, 31, 31)
+    affs = native.synth_affs(shape, seed=0)
+    try:
+        native.set_flood_version(6)
+        r = segment_blockwise(affs, {}, block, ctx)
+        torch.cuda.synchronize()
+    finally:
+        native.set_flood_version(0)
+    ref = waterz_pipeline_parallel(affs.cpu().numpy(), {}, block_size=block, context=ctx, seed_tie="heap", stats_mode="canonical")
+    check_vectorised(r, ref)
+
+
 def test_config4_block_layer_matches_oracle():
     """BASELINE configs[3] geometry: 3-D seeded fragments + seed_eps, 128^3 blocks, context 16 -- one layer of 16 blocks."""
     r, ref = _both((128, 512, 512), (128, 128, 128), (16, 16, 16), {"fragments_in_xy": False, "seed_eps": 0.01})
