@@ -1,8 +1,9 @@
 """Minimal zarr-v2 array I/O with the attrs funlib.persistence writes (offset, voxel_size, axis_names,
 units, types) — `zarr` / `numcodecs` / `funlib.persistence` are not available in this image.
 
-Supports C-order arrays, compressor null or zlib, '.' or '/' chunk keys.  Blosc-compressed inputs (the
-funlib default) are rejected with a clear error rather than read wrongly.
+Supports C-order arrays, '.' or '/' chunk keys, compressor null, zlib, or blosc (the zarr / funlib default, what
+`bs predict` writes): blosc frames are parsed in bootstrapper_b200/blosc1.py with LZ4 / Zstandard payloads decoded through
+pyarrow and zlib through the standard library; bit-shuffle and BloscLZ / Snappy payloads raise.
 """
 import json
 import os
@@ -19,8 +20,11 @@ class ZarrArray:
         if meta.get("zarr_format") != 2 or meta.get("order", "C") != "C" or meta.get("filters"):
             raise ValueError(f"{path}: only zarr v2, C order, no filters is supported")
         comp = meta.get("compressor")
-        if comp is not None and comp.get("id") != "zlib":
-            raise ValueError(f"{path}: compressor {comp.get('id')!r} is not supported (null or zlib only)")
+        if comp is not None and comp.get("id") not in ("zlib", "blosc"):
+            raise ValueError(f"{path}: compressor {comp.get('id')!r} is not supported (null, zlib or blosc)")
+        if comp is not None and comp.get("id") == "blosc" and (comp.get("shuffle", 1) == 2 or
+                                                               (comp.get("shuffle", 1) == -1 and np.dtype(meta["dtype"]).itemsize == 1)):
+            raise ValueError(f"{path}: blosc bit-shuffle is not supported")
         self.compressor = comp
         self.shape = tuple(meta["shape"])
         self.chunks = tuple(meta["chunks"])
@@ -63,7 +67,11 @@ class ZarrArray:
         with open(p, "rb") as f:
             raw = f.read()
         if self.compressor is not None:
-            raw = zlib.decompress(raw)
+            if self.compressor["id"] == "blosc":
+                from . import blosc1
+                raw = blosc1.decode(raw)
+            else:
+                raw = zlib.decompress(raw)
         return np.frombuffer(raw, dtype=self.dtype).reshape(self.chunks)
 
     def _write_chunk(self, idx, data):
@@ -71,7 +79,13 @@ class ZarrArray:
         os.makedirs(os.path.dirname(p), exist_ok=True)
         raw = np.ascontiguousarray(data, dtype=self.dtype).tobytes()
         if self.compressor is not None:
-            raw = zlib.compress(raw, self.compressor.get("level", 1))
+            if self.compressor["id"] == "blosc":
+                from . import blosc1
+                raw = blosc1.encode(raw, typesize=self.dtype.itemsize, cname=self.compressor.get("cname", "lz4"),
+                                    shuffle=1 if self.compressor.get("shuffle", 1) in (1, -1) else 0,
+                                    blocksize=self.compressor.get("blocksize", 0))
+            else:
+                raw = zlib.compress(raw, self.compressor.get("level", 1))
         with open(p, "wb") as f:
             f.write(raw)
 
