@@ -14,7 +14,8 @@ int g_debug = 0;
 int g_agglom_version = 0;  // 0 = auto (shared-memory kernel when the block fits), 1 = force the global-memory kernel
 int g_front_version = 0;   // stage-1 front end: 0 = auto (fused when eligible), 1 = unfused chain, 2 = fused without TMA, 3 = fused, TMA required
 int g_flood_version = 0;   // 0 = auto (v2 when eligible), 1 = force the global-memory flood
-int stage1_run(Plan &P, const void *affs, const uint8_t *mask, uint64_t *frags_out, cudaStream_t s);
+int stage1_run(Plan &P, const void *affs, const uint8_t *mask, uint64_t *frags_out, cudaStream_t s, const uint32_t *ext_labels = nullptr,
+               size_t ext_nlabels = 0);
 int label_stats(const uint64_t *seg, const int32_t *shape, int64_t capacity, uint64_t *ids, int64_t *sizes, int32_t *zlo,
                 int32_t *zhi, int64_t *n_out, cudaStream_t s);
 int aff_errors(const uint64_t *seg, const void *pred, int pred_dtype, int C, const int32_t *shape, const int32_t *nhood,
@@ -272,6 +273,24 @@ int bs_stage3_relabel(bs_plan *p, const uint64_t *frags, int64_t n_vox, const ui
                       uint64_t *const *segs_out, void *stream) {
     BS_ARG(p && (n_vox == 0 || (frags && components && segs_out)), "bs_stage3_relabel: null argument");
     return relabel_dense(*p->p, frags, n_vox, components, n_thresholds, segs_out, (cudaStream_t)stream);
+}
+
+int bs_stage1_from_labels(bs_plan *p, const void *affs, const uint8_t *mask, const uint32_t *labels, int64_t n_labels, uint64_t *frags_out,
+                          void *stream) {
+    BS_ARG(p && affs && labels && frags_out, "bs_stage1_from_labels: null argument");
+    BS_ARG(n_labels >= 0 && n_labels < (1LL << 31), "bs_stage1_from_labels: label count out of range");
+    init_mempool();
+    return stage1_run(*p->p, affs, mask, frags_out, (cudaStream_t)stream, labels, (size_t)n_labels);
+}
+
+int bs_stage2_agglomerate_until(bs_plan *p, const void *affs, const uint64_t *frags, float threshold, void *stream) {
+    BS_ARG(p && affs && frags, "bs_stage2_agglomerate_until: null argument");
+    BS_ARG(threshold >= 0.0f && threshold <= 1.0f, "bs_stage2_agglomerate_until: threshold must lie in [0, 1]");
+    init_mempool();
+    p->p->agg_threshold = threshold;
+    const int rc = stage2_run(*p->p, affs, frags, (cudaStream_t)stream, nullptr);
+    p->p->agg_threshold = 1.0f;
+    return rc;
 }
 
 int bs_stage3_dense_fragments(bs_plan *p, const uint64_t *frags, int64_t n_vox, uint32_t *dense_out, void *stream) {

@@ -62,6 +62,7 @@ struct Plan {
     // ---- stage 2 results
     DevBuf edge_u, edge_v, edge_score;   // owned edges
     long long n_edges = 0;
+    float agg_threshold = 1.0f;          // waterz mergeUntil threshold of the next stage-2 call (1.0: the blockwise path; epsilon_agglomerate: eps)
     // ---- debug scratch kept from the last run (name -> buffer)
     std::map<std::string, DevBuf *> dbg;
     std::map<std::string, std::pair<int, long long>> dbg_meta;  // name -> (element bytes, count)

@@ -2593,10 +2593,13 @@ static int stage1_front_fused(Plan &P, AffView A, const std::vector<Tile> &tiles
 
 template <typename T>
 static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64_t *frags_out, long long node_base,
-                        long long *n_new_nodes, cudaStream_t s) {
+                        long long *n_new_nodes, cudaStream_t s, const uint32_t *ext_labels = nullptr, size_t ext_nlabels = 0) {
     typedef typename AffOps<T>::acc_t acc_t;
     const bs_ws_config &cfg = P.cfg;
-    const bool xy = cfg.fragments_in_xy != 0;
+    // ext_labels: the fragments of every block's read ROI are given (bs_stage1_from_labels: one (rz, ry, rx) u32 volume
+    // per block of the batch, packed back to back, values 0 or 1..ext_nlabels unique over the batch) -- the blocks are
+    // then 3-D tiles whatever fragments_in_xy says: the given fragments may span z slices
+    const bool xy = cfg.fragments_in_xy != 0 && !ext_labels;
     // ---- tiles
     std::vector<Tile> tiles;
     std::vector<BlkDev> blks;
@@ -2664,7 +2667,23 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
 
     S1Front F;
     bool front_done = false;
-    BS_TRY((stage1_front_fused<T>(P, A, tiles, dt, P_pix, maxpix, F, &front_done, s)));
+    if (ext_labels) {
+        BS_TRY(F.lab.alloc(4 * (size_t)P_pix, s));
+        BS_TRY(F.lv.alloc(4 * (size_t)P_pix, s));
+        BS_TRY(F.tile_seed.alloc_zero(4 * (size_t)(ntiles + 1), s));   // one fragment table for the batch: index = label - 1
+        BS_TRY(F.totals.alloc_zero(32, s));
+        BS_TRY(F.fstats.alloc_zero(16, s));
+        size_t src = 0;
+        for (auto &t : tiles) {
+            const size_t np = (size_t)t.D * t.H * t.W;
+            BS_CUDA(cudaMemcpyAsync(F.lab.as<uint32_t>() + t.base, ext_labels + src, 4 * np, cudaMemcpyDeviceToDevice, s));
+            src += np;
+        }
+        F.nseeds = ext_nlabels;
+        F.v2 = true;
+        front_done = true;
+    }
+    if (!front_done) BS_TRY((stage1_front_fused<T>(P, A, tiles, dt, P_pix, maxpix, F, &front_done, s)));
     if (!front_done) BS_TRY((stage1_front_unfused<T>(P, bidx, A, tiles, dt, P_pix, maxpix, grid, F, s)));
     DevBuf &lab = F.lab, &lv = F.lv, &tile_seed = F.tile_seed, &totals = F.totals;
     uint32_t *d_tot = totals.as<uint32_t>();
@@ -2781,7 +2800,8 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     return BS_OK;
 }
 
-int stage1_run(Plan &P, const void *affs, const uint8_t *mask, uint64_t *frags_out, cudaStream_t s) {
+int stage1_run(Plan &P, const void *affs, const uint8_t *mask, uint64_t *frags_out, cudaStream_t s, const uint32_t *ext_labels,
+               size_t ext_nlabels) {
     const bs_ws_config &cfg = P.cfg;
     AffView A;
     A.p = affs;
@@ -2805,8 +2825,9 @@ int stage1_run(Plan &P, const void *affs, const uint8_t *mask, uint64_t *frags_o
         int tiles = 0;
         while (i < P.owned.size()) {
             const Blk &b = P.blocks[P.owned[i]];
-            long long bp = cfg.fragments_in_xy ? (long long)b.ws[0] * b.rs[1] * b.rs[2] : (long long)b.rs[0] * b.rs[1] * b.rs[2];
-            int bt = cfg.fragments_in_xy ? b.ws[0] : 1;
+            const bool xy_tiles = cfg.fragments_in_xy && !ext_labels;
+            long long bp = xy_tiles ? (long long)b.ws[0] * b.rs[1] * b.rs[2] : (long long)b.rs[0] * b.rs[1] * b.rs[2];
+            int bt = xy_tiles ? b.ws[0] : 1;
             if (!batch.empty() && (pix + bp > cap || tiles + bt > 65535)) break;
             batch.push_back(P.owned[i]);
             pix += bp;
@@ -2815,8 +2836,11 @@ int stage1_run(Plan &P, const void *affs, const uint8_t *mask, uint64_t *frags_o
         }
         long long nn = 0;
         BS_TRY(g_arena.begin(!g_debug));
-        int rc = cfg.aff_dtype == BS_DTYPE_U8 ? stage1_batch<uint8_t>(P, batch, A, frags_out, node_base, &nn, s)
-                                               : stage1_batch<float>(P, batch, A, frags_out, node_base, &nn, s);
+        int rc = cfg.aff_dtype == BS_DTYPE_U8 ? stage1_batch<uint8_t>(P, batch, A, frags_out, node_base, &nn, s, ext_labels, ext_nlabels)
+                                               : stage1_batch<float>(P, batch, A, frags_out, node_base, &nn, s, ext_labels, ext_nlabels);
+        if (ext_labels) {
+            BS_ARG(i >= P.owned.size(), "bs_stage1_from_labels: the owned blocks do not fit one batch (lower the number of blocks per call)");
+        }
         g_arena.end();
         if (rc != BS_OK) return rc;
         node_base += nn;

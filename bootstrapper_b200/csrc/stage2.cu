@@ -590,17 +590,17 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
     A.error = err.as<uint32_t>();
     BS_ARG(cfg.queue_bins == 256, "stage2: only the BinQueue<256> agglomeration of the blockwise path is implemented");
     if (par) {
-        BS_TRY(agglom_par_launch(d_ab.as<AggBlk>(), d_list.as<int>(), (int)l_smem.size(), A, 1.0f, cfg.keep_cheaper, u8, sum64, Emax,
+        BS_TRY(agglom_par_launch(d_ab.as<AggBlk>(), d_list.as<int>(), (int)l_smem.size(), A, P.agg_threshold, cfg.keep_cheaper, u8, sum64, Emax,
                                  Nmax, s));
         if (any_glob)
-            BS_TRY(agglom_par_global_launch(d_ab.as<AggBlk>(), d_list.as<int>() + l_smem.size(), (int)l_glob.size(), A, 1.0f,
+            BS_TRY(agglom_par_global_launch(d_ab.as<AggBlk>(), d_list.as<int>() + l_smem.size(), (int)l_glob.size(), A, P.agg_threshold,
                                             cfg.keep_cheaper, u8, gwork.as<unsigned char>(), d_woff.as<unsigned long long>(),
                                             Nglob_max, g_agglom_version != 4, s));
     } else {
-        BS_TRY(agglom_smem_launch(d_ab.as<AggBlk>(), d_list.as<int>(), (int)l_smem.size(), A, 1.0f, cfg.keep_cheaper, u8, sum64,
+        BS_TRY(agglom_smem_launch(d_ab.as<AggBlk>(), d_list.as<int>(), (int)l_smem.size(), A, P.agg_threshold, cfg.keep_cheaper, u8, sum64,
                                   Emax, Nmax, s));
         if (any_glob)
-            BS_TRY(agglom_global_launch(d_ab.as<AggBlk>(), d_list.as<int>() + l_smem.size(), (int)l_glob.size(), A, 1.0f,
+            BS_TRY(agglom_global_launch(d_ab.as<AggBlk>(), d_list.as<int>() + l_smem.size(), (int)l_glob.size(), A, P.agg_threshold,
                                         cfg.keep_cheaper, u8, gwork.as<unsigned char>(), d_woff.as<unsigned long long>(), s));
     }
 

@@ -53,7 +53,7 @@ class WsConfig(C.Structure):
 EXPORTS = [
     "bs_last_error", "bs_launch_count", "bs_version", "bs_config_size", "bs_plan_create", "bs_plan_destroy", "bs_plan_num_blocks",
     "bs_plan_block_info", "bs_plan_set_owned", "bs_stage1_fragments", "bs_stage1_num_nodes", "bs_stage1_get_nodes",
-    "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_plan_node_ids", "bs_stage2_agglomerate", "bs_stage2_num_edges",
+    "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_plan_node_ids", "bs_stage2_agglomerate", "bs_stage2_agglomerate_until", "bs_stage1_from_labels", "bs_stage2_num_edges",
     "bs_stage2_get_edges", "bs_waterz_segment", "bs_cc_affs", "bs_mws_agglom", "bs_aff_errors", "bs_label_stats", "bs_shift_affinities", "bs_connected_components", "bs_stage3_components", "bs_relabel", "bs_stage3_relabel", "bs_stage3_dense_fragments", "bs_expand_compact", "bs_watershed_from_affinities",
     "bs_synth_affs", "bs_debug_fetch", "bs_set_debug", "bs_set_profiling", "bs_get_profile",
     "bs_release_scratch", "bs_set_flood_version", "bs_set_front_version", "bs_set_agglom_version", "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
@@ -293,6 +293,18 @@ class Plan:
     # ---- stage 2
     def agglomerate(self, affs, frags):
         _check(lib().bs_stage2_agglomerate(self._h, _dev(affs), _dev(frags, torch.int64), _stream()))
+
+    def agglomerate_until(self, affs, frags, threshold):
+        """waterz mergeUntil(threshold) instead of the blockwise 1.0 (epsilon_agglomerate, watershed_frags.py:158-176): the
+        edges of merged pairs carry their merge score, all others NaN"""
+        _check(lib().bs_stage2_agglomerate_until(self._h, _dev(affs), _dev(frags, torch.int64), C.c_float(float(threshold)), _stream()))
+
+    def fragments_from_labels(self, affs, labels, n_labels, frags_out, mask=None):
+        """the back half of WatershedFrags on given fragments (bs_stage1_from_labels): labels int32, one read-ROI volume per
+        owned block packed back to back, values 0 or 1..n_labels"""
+        _check(lib().bs_stage1_from_labels(self._h, _dev(affs), _dev(mask, torch.uint8) if mask is not None else None,
+                                           _dev(labels, torch.int32), C.c_int64(int(n_labels)), _dev(frags_out, torch.int64), _stream()))
+        return frags_out
 
     def num_edges(self):
         n = C.c_int64()

@@ -122,6 +122,18 @@ class WatershedFrags(BlockwiseTask):
         plan = self._plan()
         n, _ = plan.num_blocks()
         plan.set_owned(np.arange(n))
+        if self.params["epsilon_agglomerate"] and self.params["epsilon_agglomerate"] > 0:
+            # watershed_frags.py:158-176, 182-183: waterz merges of every block's fragments before filter / crop / relabel
+            from ..pipeline import epsilon_fragments
+            if tuple(self._voxel_roi()[0]) != (0, 0, 0):
+                raise NotImplementedError("epsilon_agglomerate with a ROI offset is not implemented")
+            nid, npos, nsz = epsilon_fragments(plan, self._load_affs(), self.params, self._frags(), mask=self._mask_dev())
+            self.frags_data.array("r+").write(self._frags().cpu().numpy().view(np.uint64))
+            if nid.numel():
+                a = self._affs_array()
+                world = npos.cpu().numpy().astype(np.int64) * np.array(self.voxel_size) + np.array(a.offset)
+                self.db.write_nodes(nid.cpu().numpy().view(np.uint64), world, nsz.cpu().numpy().astype(np.int64))
+            return
         plan.fragments(self._load_affs(), frags_out=self._frags(), mask=self._mask_dev())
         self._store(plan)
 
@@ -131,6 +143,8 @@ class WatershedFrags(BlockwiseTask):
         affs, mask = self._load_affs(), self._mask_dev()
 
         def process_block(block):
+            if self.params["epsilon_agglomerate"] and self.params["epsilon_agglomerate"] > 0:
+                raise NotImplementedError("epsilon_agglomerate runs through run_all() (all blocks in one batch), not block by block")
             plan.set_owned([block.plan_index])
             plan.fragments(affs, frags_out=self._frags(), mask=mask)
             self._store(plan, [block.plan_index])

@@ -26,8 +26,8 @@ def resolve_ws_params(params):
     for k in UNSUPPORTED:
         if p.get(k) is not None:
             raise NotImplementedError(f"ws parameter {k!r} is not implemented in the CUDA path yet")
-    if p["epsilon_agglomerate"]:
-        raise NotImplementedError("epsilon_agglomerate > 0 is not implemented in the CUDA path yet")
+    if p["epsilon_agglomerate"] and p.get("noise_eps") is not None:
+        raise NotImplementedError("epsilon_agglomerate > 0 together with noise_eps is not implemented in the CUDA path")
     if p["merge_function"] != "mean":
         raise NotImplementedError("blockwise agglomeration supports merge_function='mean' only "
                                   "(as the reference: post/blockwise/waterz_agglom.py:24-36)")
@@ -97,6 +97,79 @@ def make_plan(affs, params, block_size, context=None, roi=None, **kw):
                        noise_eps=p["noise_eps"], noise_seed=p.get("noise_seed", 0) or 0, **kw), p
 
 
+def epsilon_fragments(plan, affs, p, frags_out, mask=None):
+    """WatershedFrags with epsilon_agglomerate > 0 (watershed_frags.py:158-176, 182-183) for all blocks of `plan`:
+    per block, the watershed fragments of its read ROI are merged by waterz (mean affinity, BinQueue<256>, float32
+    affinities as the reference passes them) up to the threshold before they are filtered, cropped and relabelled.
+
+    Orchestration over the library's own kernels: the read ROIs of all blocks of one shape are stacked into an auxiliary
+    volume whose blocks have no context (zero fill outside the array, mask applied: exactly the arrays the reference's
+    get_fragments sees); an auxiliary plan makes their fragments and scores their RAG with mergeUntil(eps)
+    (bs_stage2_agglomerate_until); the connected components of the scored edges are the merged fragments; the back half of
+    stage 1 then runs on those labels (bs_stage1_from_labels).  Returns (node ids, positions, sizes) of all blocks."""
+    dev = affs.device
+    eps = float(p["epsilon_agglomerate"])
+    ids, wo, ws = plan.block_info()
+    ctx = [int(plan.cfg.context[d]) for d in range(3)]
+    vol = tuple(affs.shape[1:])
+    groups = {}
+    for i in range(len(ids)):
+        groups.setdefault(tuple(int(ws[i][d]) + 2 * ctx[d] for d in range(3)), []).append(i)
+    counts = np.zeros(len(ids), np.int64)
+    nodes_all = []
+    a3 = affs[:3]
+    for rs, members in sorted(groups.items()):
+        rz, ry, rx = rs
+        nb = len(members)
+        fake = torch.zeros((3, nb * rz, ry, rx), dtype=a3.dtype, device=dev)
+        for k, bi in enumerate(members):
+            ro = [int(wo[bi][d]) - ctx[d] for d in range(3)]
+            lo = [max(ro[d], 0) for d in range(3)]
+            hi = [min(ro[d] + rs[d], vol[d]) for d in range(3)]
+            if any(h <= l for l, h in zip(lo, hi)):
+                continue
+            src = (slice(None),) + tuple(slice(l, h) for l, h in zip(lo, hi))
+            dz, dy, dx = (lo[d] - ro[d] for d in range(3))
+            piece = a3[src]
+            if mask is not None:   # affs_data *= mask_data (watershed_frags.py:207-213)
+                piece = piece * (mask[src[1:]] > 0).to(piece.dtype)
+            fake[:, k * rz + dz:k * rz + dz + (hi[0] - lo[0]), dy:dy + (hi[1] - lo[1]), dx:dx + (hi[2] - lo[2])] = piece
+        common = dict(fragments_in_xy=p["fragments_in_xy"], min_seed_distance=p["min_seed_distance"], filter_fragments=0.0,
+                      remove_debris=0)
+        aux = native.Plan((nb * rz, ry, rx), rs, (0, 0, 0), native._aff_dtype(fake), bias=p["bias"], seed_eps=p["seed_eps"],
+                          sigma=p["sigma"], **common)
+        frags_a = aux.fragments(fake)
+        nodes_a = aux.nodes(dev)[0]
+        if fake.dtype == torch.uint8:
+            # the reference hands waterz affs_data[:3].astype(float32) of the float64-normalised array (watershed_frags.py:163)
+            fake32 = (fake.to(torch.float64) / 255.0).to(torch.float32)
+            aux2 = native.Plan((nb * rz, ry, rx), rs, (0, 0, 0), native.BS_DTYPE_F32, **common)
+            aux2.set_block_counts(aux.block_counts())
+        else:
+            fake32, aux2 = fake, aux
+        aux2.agglomerate_until(fake32, frags_a, eps)
+        eu, ev, es = aux2.edges(dev)
+        ok = ~torch.isnan(es)
+        comp = native.connected_components(nodes_a, eu[ok].contiguous(), ev[ok].contiguous(), es[ok].contiguous(), 2.0) \
+            if nodes_a.numel() else nodes_a
+        merged = native.relabel(frags_a, nodes_a, comp) if nodes_a.numel() else frags_a
+        labels = aux.dense_fragments(merged)              # 1 + rank of the merged fragment's id among the auxiliary nodes
+        plan.set_owned(members)
+        plan.fragments_from_labels(affs, labels, nodes_a.numel(), frags_out)
+        c = plan.block_counts()
+        counts[members] = c[members]
+        if plan.num_nodes():
+            nodes_all.append(plan.nodes(dev))
+    plan.set_owned(np.arange(len(ids)))
+    plan.set_block_counts(counts)
+    if not nodes_all:
+        return (torch.zeros(0, dtype=torch.int64, device=dev), torch.zeros((0, 3), dtype=torch.int32, device=dev),
+                torch.zeros(0, dtype=torch.int32, device=dev))
+    nid = torch.cat([n[0] for n in nodes_all])
+    order = torch.argsort(nid)
+    return nid[order], torch.cat([n[1] for n in nodes_all])[order], torch.cat([n[2] for n in nodes_all])[order]
+
+
 def segment_blockwise(affs, params=None, block_size=None, context=None, roi=None, mask=None, plan=None,
                       out=None):
     """affs: CUDA tensor (C, Z, Y, X) uint8 or float32.  Returns a dict of CUDA tensors:
@@ -109,8 +182,14 @@ def segment_blockwise(affs, params=None, block_size=None, context=None, roi=None
     else:
         p = resolve_ws_params(params)
     dev = affs.device
-    frags = plan.fragments(affs, frags_out=None if out is None else out.get("fragments"), mask=mask)
-    node_ids, node_pos, node_size = plan.nodes(dev)
+    if p["epsilon_agglomerate"] and p["epsilon_agglomerate"] > 0:
+        if roi is not None and tuple(roi[0]) != (0, 0, 0):
+            raise NotImplementedError("epsilon_agglomerate with a ROI offset is not implemented")
+        frags = out.get("fragments") if out is not None else torch.zeros(plan.roi_shape, dtype=torch.int64, device=dev)
+        node_ids, node_pos, node_size = epsilon_fragments(plan, affs, p, frags, mask=mask)
+    else:
+        frags = plan.fragments(affs, frags_out=None if out is None else out.get("fragments"), mask=mask)
+        node_ids, node_pos, node_size = plan.nodes(dev)
     plan.agglomerate(affs, frags)
     eu, ev, es = plan.edges(dev)
     thrs = list(p["thresholds"])

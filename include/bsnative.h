@@ -138,6 +138,22 @@ int bs_stage2_num_edges(const bs_plan *p, int64_t *n);
 /* edges persisted by the owned blocks: u < v (fragment ids), merge_score (NaN = NULL) */
 int bs_stage2_get_edges(const bs_plan *p, uint64_t *u, uint64_t *v, float *score, void *stream);
 
+/* ---- epsilon_agglomerate (watershed_frags.py:158-176, 182-183) -------------------------------------------------------
+ * The reference merges a block's watershed fragments with waterz (mean affinity, BinQueue<256>) up to a low threshold before it
+ * filters, crops and relabels them.  Two entry points let a host driver do the same with the kernels above
+ * (bootstrapper_b200/post/pipeline.py:segment_blockwise):
+ *   bs_stage2_agglomerate_until  bs_stage2_agglomerate with waterz's mergeUntil(threshold) instead of the blockwise 1.0: edges
+ *                                of merged pairs carry their merge score, all others NaN -- the connected components of the
+ *                                scored edges are the merged fragments;
+ *   bs_stage1_from_labels        the back half of bs_stage1_fragments (filter_avg_fragments, remove_small_objects, crop,
+ *                                skimage.measure.label, ids, nodes) on GIVEN fragments: `labels` holds one (rz, ry, rx) uint32
+ *                                volume per owned block (its read ROI, ascending block order, packed back to back), values 0
+ *                                or 1..n_labels, unique over the call.  The blocks are treated as 3-D arrays (the given
+ *                                fragments may span z slices). */
+int bs_stage2_agglomerate_until(bs_plan *p, const void *affs, const uint64_t *frags, float threshold, void *stream);
+int bs_stage1_from_labels(bs_plan *p, const void *affs, const uint8_t *mask, const uint32_t *labels, int64_t n_labels, uint64_t *frags_out,
+                          void *stream);
+
 /* ---- single-shot path: waterz with the default (non-discretised) queue ------------------
  * replaces: waterz.agglomerate(affs, thresholds, fragments=..., scoring_function=OneMinus<MeanAffinity>)
  * as simple_watershed drives it (post/watershed.py:333-340): region graph of the whole ROI, priority

@@ -71,7 +71,8 @@ def test_ws_params_resolution():
     assert p["seed_eps"] == 0.01 and p["thresholds"] == [0.2, 0.35, 0.5]
     assert resolve_ws_params({"sigma": [1, 2, 2]})["sigma"] == [1, 2, 2]
     assert resolve_ws_params({"noise_eps": 0.001})["noise_seed"] == 0      # seeded stand-in for the reference's unseeded noise
-    for bad in ({"epsilon_agglomerate": 0.05}, {"merge_function": "hist_quant_75"}):
+    assert resolve_ws_params({"epsilon_agglomerate": 0.05})["epsilon_agglomerate"] == 0.05
+    for bad in ({"epsilon_agglomerate": 0.05, "noise_eps": 0.01}, {"merge_function": "hist_quant_75"}):
         with pytest.raises(NotImplementedError):
             resolve_ws_params(bad)
 

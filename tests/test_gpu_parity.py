@@ -75,6 +75,10 @@ CASES = [
     # noise_eps: a seeded generator (noise_seed) stands in for the reference's unseeded randn, drawn per block read ROI
     ((12, 120, 120), (6, 60, 60), (1, 8, 8), {"noise_eps": 0.05, "noise_seed": 3}, np.uint8),
     ((12, 100, 100), (6, 50, 50), (2, 6, 6), {"noise_eps": 0.02, "sigma": [0, 1, 1], "bias": 0.03, "fragments_in_xy": False}, np.float32),
+    # epsilon_agglomerate (watershed_frags.py:158-176): waterz merges of the block's fragments before filter / crop / relabel
+    ((12, 120, 120), (6, 60, 60), (2, 8, 8), {"epsilon_agglomerate": 0.1}, np.uint8),
+    ((16, 96, 96), (8, 48, 48), (2, 6, 6), {"epsilon_agglomerate": 0.15, "fragments_in_xy": False}, np.float32),
+    ((14, 130, 110), (6, 64, 64), (1, 8, 8), {"epsilon_agglomerate": 0.05, "filter_fragments": 0.0, "remove_debris": 0}, np.uint8),   # ragged
 ]
 
 
@@ -106,6 +110,18 @@ def test_mask():
     mask[:, 40:70, 30:90] = 0
     mask[3:5] = 0
     _check(_run_gpu(affs, {}, (5, 60, 60), (1, 8, 8), mask_np=mask), _oracle(affs, {}, (5, 60, 60), (1, 8, 8), mask=mask))
+
+
+def test_epsilon_agglomerate_with_mask_and_shifts():
+    """epsilon_agglomerate on masked affinities (affs_data *= mask before the fragments and before waterz) with bias and
+    seed_eps shifts of the watershed"""
+    from bootstrapper_b200.synth import synth_affs
+    affs = synth_affs((10, 120, 120), seed=6)
+    mask = np.ones((10, 120, 120), np.uint8)
+    mask[:, 40:70, 30:90] = 0
+    mask[3:5] = 0
+    p = {"epsilon_agglomerate": 0.12, "bias": [-0.02, -0.05, -0.05], "seed_eps": 0.01}
+    _check(_run_gpu(affs, p, (5, 60, 60), (1, 8, 8), mask_np=mask), _oracle(affs, p, (5, 60, 60), (1, 8, 8), mask=mask))
 
 
 def test_empty_and_saturated_inputs():
