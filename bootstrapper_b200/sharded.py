@@ -89,14 +89,18 @@ def allgather_counts(counts, world, device, group=None):
 
 def allgather_edges(u, v, s, world, group=None, state=None):
     """variable-size all-gather of the owned edges in ONE collective: every rank contributes a fixed-capacity record
-    [n, u[0..n), v[0..n), score bits[0..n)] (int64 words) to all_gather_into_tensor; the edge count travels in the record's
-    header, so no separate size exchange is needed.  The capacity is remembered in `state` (a dict the caller keeps between
-    calls) and grown -- with one extra round -- when some rank's edges do not fit."""
+    [n, u[0..n), v[0..n), score bits[0..n)] to all_gather_into_tensor; the edge count travels in the record's header, so no
+    separate size exchange is needed.  u, v: int64 ids, or int32 dense node numbers (12 instead of 24 bytes per edge: the
+    dense numbering is global once the block counts are exchanged); the record's word type follows them.  The capacity is
+    remembered in `state` (a dict the caller keeps between calls) and grown -- with one extra round -- when some rank's
+    edges do not fit."""
     if world == 1:
         return u, v, s
     state = state if state is not None else {}
     n = u.numel()
     dev = u.device
+    wt = u.dtype
+    sbits = s.view(torch.int32) if wt == torch.int32 else s.view(torch.int32).to(torch.int64)
     while True:
         cap = int(state.get("cap", 0))
         if cap == 0:
@@ -105,13 +109,13 @@ def allgather_edges(u, v, s, world, group=None, state=None):
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
             cap = int(t.item()) * 5 // 4 + 1024
             state["cap"] = cap
-        rec = torch.empty(1 + 3 * cap, dtype=torch.int64, device=dev)
+        rec = torch.empty(1 + 3 * cap, dtype=wt, device=dev)
         k = min(n, cap)
         rec[0] = n
         rec[1:1 + k] = u[:k]
         rec[1 + cap:1 + cap + k] = v[:k]
-        rec[1 + 2 * cap:1 + 2 * cap + k] = s[:k].view(torch.int32).to(torch.int64)
-        out = torch.empty(world * (1 + 3 * cap), dtype=torch.int64, device=dev)
+        rec[1 + 2 * cap:1 + 2 * cap + k] = sbits[:k]
+        out = torch.empty(world * (1 + 3 * cap), dtype=wt, device=dev)
         dist.all_gather_into_tensor(out, rec, group=group)
         out = out.view(world, 1 + 3 * cap)
         sizes = out[:, 0].cpu().tolist()
@@ -302,10 +306,18 @@ class ShardedSegmenter:
         plan.agglomerate(affs_win, frags)
         prof.update(native.get_profile())
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        sub = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         evs[0].record()
         eu, ev, es = plan.edges(affs_win.device)
-        eu, ev, es = allgather_edges(eu, ev, es, self.world, self.group, self._edge_state)
         nodes = plan.node_ids(affs_win.device)
+        sub[0].record()
+        if self.world > 1 and nodes.numel() < (1 << 31) - 1:
+            # ship dense node numbers (int32) instead of ids: 12 bytes per edge on the wire
+            du, dv, es = allgather_edges(plan.dense_fragments(eu), plan.dense_fragments(ev), es, self.world, self.group, self._edge_state)
+            eu, ev = nodes[(du - 1).long()], nodes[(dv - 1).long()]
+        else:
+            eu, ev, es = allgather_edges(eu, ev, es, self.world, self.group, self._edge_state)
+        sub[1].record()
         own = frags[g["z0"] - g["w0"]:g["z1"] - g["w0"]]
         thrs = list(self.p["thresholds"])
         evs[1].record()
@@ -324,6 +336,8 @@ class ShardedSegmenter:
         evs[3].record()
         evs[3].synchronize()
         prof["s3.graph"] = evs[0].elapsed_time(evs[1])          # edge / node tables (+ the all-gather when sharded)
+        if self.world > 1:
+            prof["s3.graph.gather"] = sub[0].elapsed_time(sub[1])   # part of s3.graph: the edge all-gather and its repacking
         prof["s3.components"] = evs[1].elapsed_time(evs[2])
         prof["s3.relabel"] = evs[2].elapsed_time(evs[3])
         self.last_profile = prof
