@@ -64,10 +64,13 @@ struct PqRequest {
     int T;
     uint64_t *const *segs;     // host array of T device pointers (roi-shaped uint64)
     uint32_t counters[4];      // out: pops, stale, deleted, merges
+    int quantile = 0;          // 0: OneMinus<MeanAffinity>; Q: OneMinus<HistogramQuantileAffinity<Q, 256 bins, initmax>>
+    int initmax = 0;
 };
+// hist: nullptr (mean affinity) or [E][256] affinity histograms of the edges (quantile = Q)
 int agglom_pq_run(bool u8, uint32_t E, uint32_t Nc, const uint32_t *ceu, const uint32_t *cev, unsigned long long *esum,
-                  uint32_t *ecnt, const float *thresholds_host, int T, int keep_cheaper, uint32_t *roots_out,
-                  uint32_t *counters_host, cudaStream_t s);
+                  uint32_t *ecnt, uint32_t *hist, int quantile, const float *thresholds_host, int T, int keep_cheaper,
+                  uint32_t *roots_out, uint32_t *counters_host, cudaStream_t s);
 int agglom_pq_relabel(const uint64_t *frags, size_t n, IdMap idm, const uint32_t *roots, const uint32_t *cscan, const uint8_t *used,
                       uint32_t Nc, uint32_t nview, uint32_t dense0, long long block_id, long long nvox_block, int T,
                       uint64_t *const *segs, cudaStream_t s);

@@ -9,6 +9,11 @@
 // log32(E) levels.  The merge itself is the list-splicing / node-mark scheme of agglom_smem.cu on 32-bit indices.
 // Thresholds are processed in ascending order; after each one the root of every node is written out, which is
 // the segmentation waterz yields at that threshold.
+//
+// Scoring functions (post/watershed.py:232-244): OneMinus<MeanAffinity> on exact integer sums, or -- HIST --
+// OneMinus<HistogramQuantileAffinity<Q, 256 bins>>: every edge owns a 256-bin histogram of its contact affinities (built
+// by stage2.cu), a merge of two parallel edges adds the histograms (the warp adds 256 bins in 8 coalesced steps) and the
+// score is 1 - (bin + 0.5) / 256 of the first bin whose running count reaches Q * sum / 100 + 1.
 #include "agglom.cuh"
 
 namespace bs {
@@ -32,6 +37,53 @@ __global__ void k_pq_keys(const unsigned long long *__restrict__ esum, const uin
     escore[e] = sc;
     keys[e] = ((uint64_t)score_bits(sc) << 32) | e;
     vals[e] = e;
+}
+
+// quantile score of one histogram, computed by the whole warp (lane l owns bins 8l .. 8l+7)
+__device__ __forceinline__ float hist_score(const uint32_t *h, int Q, int lane) {   // no __restrict__: the kernel updates histograms
+    const uint4 p0 = *reinterpret_cast<const uint4 *>(h + lane * 8), p1 = *reinterpret_cast<const uint4 *>(h + lane * 8 + 4);
+    const uint32_t b[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    unsigned long long mine = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) mine += b[k];
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const unsigned long long sum = __shfl_sync(FULL, incl, 31);
+    const unsigned long long pivot = (unsigned long long)((long long)Q * (long long)sum / 100 + 1);
+    const unsigned hit = __ballot_sync(FULL, incl >= pivot);
+    int bin = 255;
+    if (hit) {
+        const int l = __ffs(hit) - 1;
+        unsigned long long run = incl - mine;
+        int mybin = 8 * lane + 7;
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+            unsigned long long upto = run;
+#pragma unroll
+            for (int j = 0; j <= k; j++) upto += b[j];
+            if (upto >= pivot) mybin = 8 * lane + k;
+        }
+        bin = __shfl_sync(FULL, mybin, l);
+    }
+    const float q = __double2float_rn(((double)(float)bin + 0.5) / 256.0);   // undiscretize()
+    return __double2float_rn(1.0 - (double)q);                               // OneMinus
+}
+
+__global__ void __launch_bounds__(256) k_pq_keys_hist(const uint32_t *__restrict__ hist, int Q, uint32_t E, float *__restrict__ escore,
+                                                      uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t e = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (e >= E) return;
+    const float sc = hist_score(hist + (size_t)e * 256, Q, lane);
+    if (lane == 0) {
+        escore[e] = sc;
+        keys[e] = ((uint64_t)score_bits(sc) << 32) | e;
+        vals[e] = e;
+    }
 }
 
 __device__ __forceinline__ uint32_t pq_find(uint32_t *ufp, uint32_t x) {
@@ -67,6 +119,8 @@ struct PqArgs {
     const uint32_t *eu, *ev;           // compact endpoints
     unsigned long long *esum;
     uint32_t *ecnt;
+    uint32_t *hist;                    // HIST: [E][256]
+    int quantile;
     float *escore;
     uint32_t *etime;
     uint8_t *edead;
@@ -81,7 +135,7 @@ struct PqArgs {
     int keep_cheaper;
 };
 
-template <bool U8>
+template <bool U8, bool HIST>
 __global__ void __launch_bounds__(32) k_agglomerate_pq(PqArgs a) {
     const int lane = threadIdx.x;
     const uint32_t E = a.E, N = a.N;
@@ -203,7 +257,11 @@ __global__ void __launch_bounds__(32) k_agglomerate_pq(PqArgs a) {
             const uint32_t te = a.etime[e];
             if (stamp[ru] > te || stamp[rv] > te) {
                 // stale: re-score, push back
-                const float ns = edge_score<U8>(a.esum[e], a.ecnt[e]);
+                float ns;
+                if constexpr (HIST)
+                    ns = hist_score(a.hist + (size_t)e * 256, a.quantile, lane);
+                else
+                    ns = edge_score<U8>(a.esum[e], a.ecnt[e]);
                 if (lane == 0) {
                     a.escore[e] = ns;
                     a.etime[e] = clock;
@@ -231,21 +289,35 @@ __global__ void __launch_bounds__(32) k_agglomerate_pq(PqArgs a) {
             });
             uint32_t head_a = ahead[ca], tail_a = NONE32;
             walk(head_a, tail_a, [&](uint32_t h) {
+                uint32_t dst = NONE32, src = NONE32;
                 if (h != NONE32) {
                     const uint32_t ae = h >> 1;
                     const uint32_t x1 = pq_find(ufp, a.eu[ae]), x2 = pq_find(ufp, a.ev[ae]);
                     const uint32_t x = x1 == ca ? x2 : x1;
                     if (markgen[x] == gen) {
                         const uint32_t ne = mark[x];
-                        if (!a.keep_cheaper || a.escore[ne] > a.escore[ae]) {
-                            a.esum[ae] += a.esum[ne];
-                            a.ecnt[ae] += a.ecnt[ne];
-                            a.edead[ne] = 1;
-                        } else {
-                            a.esum[ne] += a.esum[ae];
-                            a.ecnt[ne] += a.ecnt[ae];
-                            a.edead[ae] = 1;
+                        if (!a.keep_cheaper || a.escore[ne] > a.escore[ae])
+                            dst = ae, src = ne;
+                        else
+                            dst = ne, src = ae;
+                        a.edead[src] = 1;
+                        if constexpr (!HIST) {
+                            a.esum[dst] += a.esum[src];
+                            a.ecnt[dst] += a.ecnt[src];
                         }
+                    }
+                }
+                if constexpr (HIST) {
+                    // notifyEdgeMerge: the histograms add; one pair at a time, 256 bins across the warp
+                    unsigned m = __ballot_sync(FULL, dst != NONE32);
+                    while (m) {
+                        const int l = __ffs(m) - 1;
+                        m &= m - 1;
+                        const uint32_t d = __shfl_sync(FULL, dst, l), sr = __shfl_sync(FULL, src, l);
+                        uint32_t *hd = a.hist + (size_t)d * 256;
+                        const uint32_t *hs = a.hist + (size_t)sr * 256;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) hd[lane + 32 * k] += hs[lane + 32 * k];
                     }
                 }
             });
@@ -317,8 +389,8 @@ __global__ void k_pq_cmap(const uint8_t *__restrict__ used, const uint32_t *__re
 }
 
 int agglom_pq_run(bool u8, uint32_t E, uint32_t Nc, const uint32_t *ceu, const uint32_t *cev, unsigned long long *esum,
-                  uint32_t *ecnt, const float *thresholds_host, int T, int keep_cheaper, uint32_t *roots_out,
-                  uint32_t *counters_host, cudaStream_t s) {
+                  uint32_t *ecnt, uint32_t *hist, int quantile, const float *thresholds_host, int T, int keep_cheaper,
+                  uint32_t *roots_out, uint32_t *counters_host, cudaStream_t s) {
     DevBuf escore, etime, edead, anext, ahead, ufp, stamp, mark, markgen, keys, vals, keys2, vals2, thr, counters, err;
     BS_TRY(escore.alloc(4 * ((size_t)E + 1), s));
     BS_TRY(etime.alloc(4 * ((size_t)E + 1), s));
@@ -338,7 +410,9 @@ int agglom_pq_run(bool u8, uint32_t E, uint32_t Nc, const uint32_t *ceu, const u
     BS_TRY(err.alloc_zero(16, s));
     BS_CUDA(cudaMemcpyAsync(thr.p, thresholds_host, 4 * (size_t)T, cudaMemcpyHostToDevice, s));
     if (E) {
-        if (u8)
+        if (hist)
+            BS_LAUNCH(k_pq_keys_hist, cdiv(E, 8), 256, 0, s, hist, quantile, E, escore.as<float>(), keys.as<uint64_t>(), vals.as<uint32_t>());
+        else if (u8)
             BS_LAUNCH((k_pq_keys<true>), cdiv(E, 256), 256, 0, s, esum, ecnt, E, escore.as<float>(), keys.as<uint64_t>(),
                       vals.as<uint32_t>());
         else
@@ -351,6 +425,7 @@ int agglom_pq_run(bool u8, uint32_t E, uint32_t Nc, const uint32_t *ceu, const u
     a.E = E, a.N = Nc;
     a.eu = ceu, a.ev = cev;
     a.esum = esum, a.ecnt = ecnt;
+    a.hist = hist, a.quantile = quantile;
     a.escore = escore.as<float>(), a.etime = etime.as<uint32_t>(), a.edead = edead.as<uint8_t>();
     a.anext = anext.as<uint32_t>(), a.ahead = ahead.as<uint32_t>();
     a.ufp = ufp.as<uint32_t>(), a.stamp = stamp.as<uint32_t>(), a.mark = mark.as<uint32_t>(), a.markgen = markgen.as<uint32_t>();
@@ -361,10 +436,12 @@ int agglom_pq_run(bool u8, uint32_t E, uint32_t Nc, const uint32_t *ceu, const u
     a.counters = counters.as<uint32_t>();
     a.error = err.as<uint32_t>();
     a.keep_cheaper = keep_cheaper;
-    if (u8)
-        BS_LAUNCH((k_agglomerate_pq<true>), 1, 32, 0, s, a);
+    if (hist)
+        BS_LAUNCH((k_agglomerate_pq<true, true>), 1, 32, 0, s, a);
+    else if (u8)
+        BS_LAUNCH((k_agglomerate_pq<true, false>), 1, 32, 0, s, a);
     else
-        BS_LAUNCH((k_agglomerate_pq<false>), 1, 32, 0, s, a);
+        BS_LAUNCH((k_agglomerate_pq<false, false>), 1, 32, 0, s, a);
     uint32_t h[5] = {0, 0, 0, 0, 0};
     BS_CUDA(cudaMemcpyAsync(h, counters.p, 16, cudaMemcpyDeviceToHost, s));
     BS_CUDA(cudaMemcpyAsync(h + 4, err.p, 4, cudaMemcpyDeviceToHost, s));

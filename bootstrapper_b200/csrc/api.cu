@@ -214,7 +214,13 @@ int bs_stage2_agglomerate(bs_plan *p, const void *affs, const uint64_t *frags, v
 
 int bs_waterz_segment(bs_plan *p, const void *affs, const uint64_t *frags, const float *thresholds, int n_thresholds,
                       uint64_t *const *segs_out, uint32_t *counters_out, void *stream) {
+    return bs_waterz_segment_quantile(p, affs, frags, thresholds, n_thresholds, 0, 0, segs_out, counters_out, stream);
+}
+
+int bs_waterz_segment_quantile(bs_plan *p, const void *affs, const uint64_t *frags, const float *thresholds, int n_thresholds,
+                               int quantile, int init_with_max, uint64_t *const *segs_out, uint32_t *counters_out, void *stream) {
     BS_ARG(p && affs && frags && thresholds && segs_out && n_thresholds >= 1, "bs_waterz_segment: null argument");
+    BS_ARG(quantile >= 0 && quantile < 100, "bs_waterz_segment_quantile: quantile must lie in 0..99");
     for (int t = 1; t < n_thresholds; t++)
         BS_ARG(thresholds[t] >= thresholds[t - 1], "bs_waterz_segment: thresholds must be ascending (waterz sorts them)");
     Plan &P = *p->p;
@@ -223,6 +229,8 @@ int bs_waterz_segment(bs_plan *p, const void *affs, const uint64_t *frags, const
     rq.thresholds = thresholds;
     rq.T = n_thresholds;
     rq.segs = segs_out;
+    rq.quantile = quantile;
+    rq.initmax = init_with_max ? 1 : 0;
     for (int i = 0; i < 4; i++) rq.counters[i] = 0;
     int rc = stage2_run(P, affs, frags, (cudaStream_t)stream, &rq);
     if (rc == BS_OK && counters_out)

@@ -154,6 +154,72 @@ __global__ void __launch_bounds__(256) k_rag_accumulate(const S2Blk *__restrict_
     }
 }
 
+// ------------------------------------------------------------------ affinity histograms of the edges (single-shot path)
+// waterz HistogramQuantileProvider::addAffinity (post/watershed.py:232-244): bin = min((int)(a * 256), 255) of the float32
+// affinity the reference hands to waterz (uint8 input is normalised by / 255 first, post/watershed.py:254-257); bins below
+// 0 (a shifted affinity < 0, undefined upstream) clamp to 0
+template <typename T>
+__device__ __forceinline__ int aff_bin(T v);
+template <>
+__device__ __forceinline__ int aff_bin<uint8_t>(uint8_t v) {
+    return min(max((int)__fmul_rn(__fdiv_rn((float)v, 255.0f), 256.0f), 0), 255);
+}
+template <>
+__device__ __forceinline__ int aff_bin<float>(float v) {
+    return min(max((int)__fmul_rn(v, 256.0f), 0), 255);
+}
+
+__global__ void k_slot_edge(const uint32_t *__restrict__ svals, uint32_t E, uint32_t *__restrict__ slot_edge) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < E) slot_edge[svals[e]] = e;
+}
+
+// second pass over the contacts of block 0's read ROI: look the pair up in the (now complete) hash table, count the
+// affinity's bin (or keep the largest bin, InitWithMax)
+template <typename T>
+__global__ void __launch_bounds__(256) k_rag_hist(const S2Blk *__restrict__ blks, const T *__restrict__ affs,
+                                                  const uint32_t *__restrict__ frags, int volZ, int volY, int volX, int wz0, int roz,
+                                                  int roy, int rox, int rsz, int rsy, int rsx,
+                                                  const unsigned long long *__restrict__ hkeys, const uint32_t *__restrict__ slot_edge,
+                                                  uint32_t *__restrict__ hist, int *__restrict__ emax) {
+    const S2Blk &b = blks[0];
+    const int RY = b.rs[1], RX = b.rs[2];
+    const size_t n = (size_t)b.rs[0] * RY * RX, nvol = (size_t)volZ * volY * volX;
+    const uint32_t tmask = b.tcap - 1;
+    const int st[3] = {rsy * rsx, rsx, 1};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % RX), y = (int)((i / RX) % RY), z = (int)(i / ((size_t)RX * RY));
+        const int gz = b.ro[0] + z, gy = b.ro[1] + y, gx = b.ro[2] + x;
+        const int f[3] = {gz - roz, gy - roy, gx - rox};
+        if (f[0] < 0 || f[0] >= rsz || f[1] < 0 || f[1] >= rsy || f[2] < 0 || f[2] >= rsx) continue;
+        const size_t fi = ((size_t)f[0] * rsy + f[1]) * rsx + f[2];
+        const uint32_t f1 = frags[fi];
+        if (f1 == 0) continue;
+        const int loc[3] = {z, y, x};
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            if (loc[d] == 0 || f[d] == 0) continue;
+            const uint32_t f2 = frags[fi - st[d]];
+            if (f2 == 0 || f2 == f1) continue;
+            const uint32_t lo = min(f1, f2) - 1, hi = max(f1, f2) - 1;
+            const unsigned long long key = ((unsigned long long)lo << 32) | hi;
+            uint32_t slot = (uint32_t)hash64(key) & tmask;
+            while (hkeys[(size_t)b.tbase + slot] != key) slot = (slot + 1) & tmask;   // present by construction
+            const uint32_t e = slot_edge[(size_t)b.tbase + slot];
+            const int bin = aff_bin<T>(affs[(size_t)d * nvol + ((size_t)(gz - wz0) * volY + gy) * volX + gx]);
+            if (emax)
+                atomicMax(&emax[e], bin);
+            else
+                atomicAdd(&hist[(size_t)e * 256 + bin], 1u);
+        }
+    }
+}
+
+__global__ void k_hist_initmax(const int *__restrict__ emax, uint32_t E, uint32_t *__restrict__ hist) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < E) hist[(size_t)e * 256 + emax[e]] = 1u;
+}
+
 __global__ void k_flag_keys(const unsigned long long *__restrict__ hkeys, uint8_t *__restrict__ flag, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) flag[i] = hkeys[i] != EMPTY64 ? 1 : 0;
@@ -466,6 +532,23 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
                   hkeys.as<unsigned long long>(), hsum.as<unsigned long long>(), hcnt.as<uint32_t>(), E, eu.as<uint32_t>(),
                   ev.as<uint32_t>(), esum.as<unsigned long long>(), ecnt.as<uint32_t>(), eblk.as<uint32_t>(),
                   deg.as<uint32_t>());
+    DevBuf ehist;
+    if (pq && pq->quantile > 0 && E) {
+        // single-shot path with a HistogramQuantileAffinity scoring function: per-edge affinity histograms
+        BS_ARG(nown == 1, "histogram scoring needs a single-block plan");
+        BS_ARG((size_t)E * 1024 <= ((size_t)64 << 30), "histogram scoring: more than 64 GB of edge histograms");
+        DevBuf slot_edge, emax;
+        BS_TRY(slot_edge.alloc(4 * Ttot, s));
+        BS_TRY(ehist.alloc_zero((size_t)E * 1024, s));
+        if (pq->initmax) BS_TRY(emax.alloc_zero(4 * ((size_t)E + 1), s));
+        BS_LAUNCH(k_slot_edge, cdiv(E, 256), 256, 0, s, svals.as<uint32_t>(), E, slot_edge.as<uint32_t>());
+        BS_LAUNCH((k_rag_hist<T>), (unsigned)std::min<size_t>(cdiv((size_t)maxread, 256), 148 * 32), 256, 0, s, db, (const T *)affs,
+                  fdense.as<uint32_t>(), cfg.win_z > 0 ? cfg.win_z : cfg.vol_shape[0], cfg.vol_shape[1], cfg.vol_shape[2],
+                  cfg.win_z > 0 ? cfg.win_z0 : 0, cfg.roi_offset[0] + (cfg.win_z > 0 ? cfg.win_z0 : 0), cfg.roi_offset[1],
+                  cfg.roi_offset[2], cfg.win_z > 0 ? cfg.win_z : cfg.roi_shape[0], cfg.roi_shape[1], cfg.roi_shape[2],
+                  hkeys.as<unsigned long long>(), slot_edge.as<uint32_t>(), ehist.as<uint32_t>(), pq->initmax ? emax.as<int>() : nullptr);
+        if (pq->initmax) BS_LAUNCH(k_hist_initmax, cdiv(E, 256), 256, 0, s, emax.as<int>(), E, ehist.as<uint32_t>());
+    }
     hkeys.release();
     hsum.release();
     hcnt.release();
@@ -503,7 +586,8 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
         DevBuf roots;
         BS_TRY(roots.alloc(4 * ((size_t)pq->T * (Ctot + 1)), s));
         BS_TRY(agglom_pq_run(sizeof(T) == 1, E, (uint32_t)Ctot, ceu.as<uint32_t>(), cev.as<uint32_t>(), esum.as<unsigned long long>(),
-                             ecnt.as<uint32_t>(), pq->thresholds, pq->T, cfg.keep_cheaper, roots.as<uint32_t>(), pq->counters, s));
+                             ecnt.as<uint32_t>(), ehist.p ? ehist.as<uint32_t>() : nullptr, pq->quantile, pq->thresholds, pq->T, cfg.keep_cheaper,
+                             roots.as<uint32_t>(), pq->counters, s));
         g_prof.mark("s2.relabel", s);
         const size_t nvox = (size_t)(cfg.win_z > 0 ? cfg.win_z : cfg.roi_shape[0]) * cfg.roi_shape[1] * cfg.roi_shape[2];
         BS_TRY(agglom_pq_relabel(frags, nvox, idm, roots.as<uint32_t>(), cscan.as<uint32_t>(), used.as<uint8_t>(), (uint32_t)Ctot,

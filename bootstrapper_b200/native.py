@@ -54,7 +54,7 @@ EXPORTS = [
     "bs_last_error", "bs_launch_count", "bs_version", "bs_config_size", "bs_plan_create", "bs_plan_destroy", "bs_plan_num_blocks",
     "bs_plan_block_info", "bs_plan_set_owned", "bs_stage1_fragments", "bs_stage1_num_nodes", "bs_stage1_get_nodes",
     "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_plan_node_ids", "bs_stage2_agglomerate", "bs_stage2_agglomerate_until", "bs_stage1_from_labels", "bs_stage2_num_edges",
-    "bs_stage2_get_edges", "bs_waterz_segment", "bs_cc_affs", "bs_mws_agglom", "bs_aff_errors", "bs_label_stats", "bs_shift_affinities", "bs_connected_components", "bs_stage3_components", "bs_relabel", "bs_stage3_relabel", "bs_stage3_dense_fragments", "bs_expand_compact", "bs_watershed_from_affinities",
+    "bs_stage2_get_edges", "bs_waterz_segment", "bs_waterz_segment_quantile", "bs_cc_affs", "bs_mws_agglom", "bs_aff_errors", "bs_label_stats", "bs_shift_affinities", "bs_connected_components", "bs_stage3_components", "bs_relabel", "bs_stage3_relabel", "bs_stage3_dense_fragments", "bs_expand_compact", "bs_watershed_from_affinities",
     "bs_synth_affs", "bs_debug_fetch", "bs_set_debug", "bs_set_profiling", "bs_get_profile",
     "bs_release_scratch", "bs_set_flood_version", "bs_set_front_version", "bs_set_agglom_version", "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
 ]
@@ -320,8 +320,9 @@ class Plan:
         return u, v, s
 
     # ---- single-shot path (waterz with the non-discretised queue)
-    def waterz_segment(self, affs, frags, thresholds, outs=None):
-        """waterz.agglomerate(affs, thresholds, fragments) on a single-block plan (post/watershed.py:333-340).
+    def waterz_segment(self, affs, frags, thresholds, outs=None, quantile=0, init_with_max=False):
+        """waterz.agglomerate(affs, thresholds, fragments, scoring_function) on a single-block plan (post/watershed.py:333-340);
+        quantile = 0: OneMinus<MeanAffinity>, Q: OneMinus<HistogramQuantileAffinity<Q, 256, init_with_max>> (:232-244).
         Returns ([segmentation per ascending threshold], sorted thresholds, counters dict)."""
         thr = np.ascontiguousarray(sorted(float(t) for t in thresholds), dtype=np.float32)
         T = len(thr)
@@ -331,8 +332,8 @@ class Plan:
             _dev(t, torch.int64)
         sp = (C.c_void_p * T)(*[o.data_ptr() for o in outs])
         cnt = (C.c_uint32 * 4)()
-        _check(lib().bs_waterz_segment(self._h, _dev(affs), _dev(frags, torch.int64), thr.ctypes.data_as(C.c_void_p),
-                                       C.c_int(T), sp, cnt, _stream()))
+        _check(lib().bs_waterz_segment_quantile(self._h, _dev(affs), _dev(frags, torch.int64), thr.ctypes.data_as(C.c_void_p),
+                                                C.c_int(T), C.c_int(int(quantile)), C.c_int(1 if init_with_max else 0), sp, cnt, _stream()))
         return outs, [float(t) for t in thr], dict(pops=cnt[0], stale=cnt[1], deleted=cnt[2], merges=cnt[3])
 
     # ---- stage 3

@@ -39,6 +39,17 @@ SIMPLE_MERGE_FUNCTIONS = (  # post/watershed.py:232-244
     "hist_quant_50_initmax", "hist_quant_75", "hist_quant_75_initmax", "hist_quant_90", "hist_quant_90_initmax")
 
 
+def merge_function_code(name):
+    """post/watershed.py:232-244: "mean" -> (0, False); "hist_quant_Q[_initmax]" -> (Q, init_with_max), the template
+    arguments of OneMinus<HistogramQuantileAffinity<RegionGraphType, Q, ScoreValue, 256, init_with_max>>"""
+    if name not in SIMPLE_MERGE_FUNCTIONS:
+        raise KeyError(name)
+    if name == "mean":
+        return 0, False
+    parts = name.split("_")
+    return int(parts[2]), len(parts) == 4
+
+
 def segment_simple(affs, params=None, mask=None):
     """In-memory core of `simple_watershed` (post/watershed.py:206-354): fragments of the whole ROI, then waterz
     with the default (non-discretised) queue, one segmentation per threshold.  affs: CUDA tensor (C, Z, Y, X)
@@ -52,8 +63,7 @@ def segment_simple(affs, params=None, mask=None):
         raise NotImplementedError("ws parameter 'noise_eps' (an unseeded RNG in the reference) is not implemented in the CUDA path")
     if p["merge_function"] not in SIMPLE_MERGE_FUNCTIONS:
         raise KeyError(p["merge_function"])
-    if p["merge_function"] != "mean":
-        raise NotImplementedError("only merge_function='mean' (OneMinus<MeanAffinity>) is implemented in the CUDA path")
+    quantile, initmax = merge_function_code(p["merge_function"])
     affs = affs[:3]
     if affs.shape[0] == 2:   # post/watershed.py:305-308
         affs = torch.cat([torch.zeros_like(affs[:1]), affs], 0)
@@ -70,7 +80,7 @@ def segment_simple(affs, params=None, mask=None):
                        fragments_in_xy=p["fragments_in_xy"], min_seed_distance=p["min_seed_distance"],
                        filter_fragments=0.0, remove_debris=0)
     frags = plan.fragments(affs)
-    outs, thr, counters = plan.waterz_segment(affs, frags, p["thresholds"])
+    outs, thr, counters = plan.waterz_segment(affs, frags, p["thresholds"], quantile=quantile, init_with_max=initmax)
     segs = {}
     for t in p["thresholds"]:
         segs[t] = outs[thr.index(float(np.float32(t)))]

@@ -164,6 +164,12 @@ int bs_stage1_from_labels(bs_plan *p, const void *affs, const uint8_t *mask, con
  */
 int bs_waterz_segment(bs_plan *p, const void *affs, const uint64_t *frags, const float *thresholds, int n_thresholds,
                       uint64_t *const *segs_out, uint32_t *counters_out, void *stream);
+/* the same call with one of the histogram scoring functions of post/watershed.py:232-244,
+ * scoring_function=OneMinus<HistogramQuantileAffinity<RegionGraphType, Q, ScoreValue, 256, init_with_max>>
+ * ("hist_quant_Q" / "hist_quant_Q_initmax"): quantile = Q in 1..99 (the reference offers 10, 25, 50, 75, 90);
+ * quantile = 0 is bs_waterz_segment.  1 KB of device scratch per region-graph edge. */
+int bs_waterz_segment_quantile(bs_plan *p, const void *affs, const uint64_t *frags, const float *thresholds, int n_thresholds,
+                               int quantile, int init_with_max, uint64_t *const *segs_out, uint32_t *counters_out, void *stream);
 
 /* ---- stage 3: global thresholded connected components + relabel --------------------
  * replaces: funlib.segment.graphs.impl.connected_components (post/watershed.py:182),

@@ -334,6 +334,15 @@ def waterz_pipeline(affs, params=None, block_size=None, context=None, roi=None, 
 
 
 # --------------------------------------------------------------------------- single shot
+def merge_function_code(name):
+    """post/watershed.py:232-244: 'mean' -> (0, False); 'hist_quant_Q[_initmax]' -> (Q, initmax)"""
+    if name == "mean":
+        return 0, False
+    parts = name.split("_")
+    assert parts[:2] == ["hist", "quant"] and int(parts[2]) in (10, 25, 50, 75, 90), name
+    return int(parts[2]), len(parts) == 4 and parts[3] == "initmax"
+
+
 def simple_watershed(affs, params=None, mask=None, seed_tie="heap", stats_mode="faithful",
                      keep_cheaper=True):
     """post/watershed.py:206-354 on in-memory arrays: float32 normalise, fragments,
@@ -364,8 +373,9 @@ def simple_watershed(affs, params=None, mask=None, seed_tie="heap", stats_mode="
         affs_data, fragments_in_xy=p["fragments_in_xy"], return_seeds=False,
         min_seed_distance=p["min_seed_distance"], seed_tie=seed_tie)
     thresholds = sorted(p["thresholds"])
+    quantile, initmax = merge_function_code(p["merge_function"])
     wz = Waterz(raw_u8 if (raw_u8 is not None and stats_mode == "canonical") else affs_data,
-                fragments_data, 0, stats_mode, keep_cheaper)
+                fragments_data, 0, stats_mode, keep_cheaper, quantile=quantile, initmax=initmax)
     segs = {}
     for thr in thresholds:
         wz.merge_until(thr)

@@ -7,7 +7,18 @@
  *   post/watershed.py:333-338                (discretize_queue=0, user thresholds)
  *   post/blockwise/watershed_frags.py:165-173 (epsilon agglomeration, discretize_queue=256)
  * scoring function: OneMinus<MeanAffinity<RegionGraphType, ScoreValue>> (the only one
- * the blockwise path enables, waterz_agglom.py:24-36).
+ * the blockwise path enables, waterz_agglom.py:24-36), and -- single-shot path only,
+ * post/watershed.py:232-244 -- OneMinus<HistogramQuantileAffinity<RegionGraphType, Q,
+ * ScoreValue, 256, InitWithMax>> (quantile = Q > 0):
+ *   recalled from waterz's HistogramQuantileProvider.hpp / Histogram.hpp / discretize.hpp:
+ *   - addAffinity(e, a): bin = min((int)(a * 256), 255) [float multiply]; without
+ *     InitWithMax the bin's count goes up by one; with it the histogram keeps ONE sample,
+ *     the largest bin seen  [switch U12a]
+ *   - notifyEdgeMerge(from, to): histograms add, the edge is re-scored (stale)
+ *   - value: pivot = Q * sum / 100 + 1 (integer arithmetic, "1-based pivot element"); the
+ *     first bin whose running count reaches the pivot; (bin + 0.5) / 256  [switch U12b]
+ *   - affinities below 0 (possible after a bias / sigma shift) would index before the
+ *     histogram upstream (undefined); bins are clamped at 0 here and in the CUDA path.
  *
  * waterz (git+https://github.com/ZettaAI/waterz, no commit pin, pyproject.toml:54) is a
  * third-party C++ dependency that is NOT in /root/reference and cannot be built here
@@ -56,6 +67,9 @@ struct State {
     // switch U6c: when a and b share a neighbour, keep the cheaper edge (1, recalled
     // "lucky / bummer" rule) or always keep a's edge (0, simpler description)
     int keep_cheaper;
+    int quantile;     // 0 = MeanAffinity, Q = HistogramQuantileAffinity<Q, 256 bins>
+    int initmax;      // InitWithMax of the histogram provider
+    std::vector<uint32_t> hist;   // [edge][256]
 
     std::vector<Edge> edges;
     std::vector<std::vector<EdgeId>> inc;
@@ -91,8 +105,29 @@ inline float edge_mean(const State &s, EdgeId e) {
     return sum / (float)s.cnt[e];
 }
 
+inline int aff_bin(float a) {
+    int b = (int)(a * 256);   // discretize(): float * int -> float, truncated
+    return std::min(std::max(b, 0), 255);
+}
+
+inline float edge_quantile(const State &s, EdgeId e) {
+    const uint32_t *h = &s.hist[(size_t)e * 256];
+    long long sum = 0;
+    for (int b = 0; b < 256; b++) sum += h[b];
+    int pivot = (int)((long long)s.quantile * sum / 100 + 1);
+    long long run = 0;
+    int bin = 0;
+    for (bin = 0; bin < 256; bin++) {
+        run += h[bin];
+        if (run >= pivot) break;
+    }
+    bin = std::min(bin, 255);
+    return (float)(((float)bin + 0.5) / 256);   // undiscretize()
+}
+
 inline float edge_score(const State &s, EdgeId e) {
-    // OneMinus<MeanAffinity>: (ScoreValue)(1.0 - mean)
+    // OneMinus<...>: (ScoreValue)(1.0 - value)
+    if (s.quantile > 0) return (float)(1.0 - (double)edge_quantile(s, e));
     return (float)(1.0 - (double)edge_mean(s, e));
 }
 
@@ -166,6 +201,8 @@ void stats_merge(State &s, EdgeId from, EdgeId to) {
     s.fsum[to] += s.fsum[from];
     s.isum[to] += s.isum[from];
     s.cnt[to] += s.cnt[from];
+    if (s.quantile > 0)
+        for (int b = 0; b < 256; b++) s.hist[(size_t)to * 256 + b] += s.hist[(size_t)from * 256 + b];
 }
 
 void merge_regions(State &s, EdgeId e) {
@@ -243,9 +280,11 @@ extern "C" {
 
 /* affs: (3,Z,Y,X) uint8 or float32 (aff_dtype); frags: (Z,Y,X) uint64 with ids 0..max_id
  * (caller relabels densely first, as waterz_agglom.py:116 does). */
-void *wz_create(const void *affs, int aff_dtype, const uint64_t *frags, int64_t Z, int64_t Y,
-                int64_t X, int queue_bins, int stats_mode, int keep_cheaper) {
+void *wz_create_q(const void *affs, int aff_dtype, const uint64_t *frags, int64_t Z, int64_t Y,
+                  int64_t X, int queue_bins, int stats_mode, int keep_cheaper, int quantile, int initmax) {
     State *s = new State();
+    s->quantile = quantile;
+    s->initmax = initmax;
     s->queue_bins = queue_bins;
     s->stats_mode = stats_mode;
     s->aff_dtype = aff_dtype;
@@ -295,6 +334,7 @@ void *wz_create(const void *affs, int aff_dtype, const uint64_t *frags, int64_t 
                         s->fsum.push_back(0.f);
                         s->isum.push_back(0);
                         s->cnt.push_back(0);
+                        if (quantile > 0) s->hist.resize(s->hist.size() + 256, 0u);
                     } else
                         e = it->second;
                     int64_t ai = d * n + i;
@@ -306,6 +346,16 @@ void *wz_create(const void *affs, int aff_dtype, const uint64_t *frags, int64_t 
                         s->isum[e] += (int64_t)std::llrint(std::ldexp((double)a32[ai], 38));
                     }
                     s->cnt[e]++;
+                    if (quantile > 0) {
+                        const int b = aff_bin(aff_dtype == 0 ? (float)a8[ai] / 255.0f : a32[ai]);
+                        uint32_t *h = &s->hist[(size_t)e * 256];
+                        if (initmax && s->cnt[e] > 1) {
+                            int cur = 0;
+                            while (h[cur] == 0) cur++;   // the single sample kept so far
+                            if (b > cur) h[cur] = 0, h[b] = 1;
+                        } else
+                            h[b]++;
+                    }
                 }
             }
     (void)dims;
@@ -314,6 +364,11 @@ void *wz_create(const void *affs, int aff_dtype, const uint64_t *frags, int64_t 
     s->stale.assign(E, 0);
     s->deleted.assign(E, 0);
     return s;
+}
+
+void *wz_create(const void *affs, int aff_dtype, const uint64_t *frags, int64_t Z, int64_t Y,
+                int64_t X, int queue_bins, int stats_mode, int keep_cheaper) {
+    return wz_create_q(affs, aff_dtype, frags, Z, Y, X, queue_bins, stats_mode, keep_cheaper, 0, 0);
 }
 
 void wz_free(void *h) { delete (State *)h; }

@@ -15,6 +15,7 @@ def lib():
         _lib.sk_watershed.restype = C.c_int64
         _lib.sk_label.restype = C.c_int64
         _lib.wz_create.restype = C.c_void_p
+        _lib.wz_create_q.restype = C.c_void_p
         _lib.wz_num_edges.restype = C.c_int64
         _lib.wz_num_nodes.restype = C.c_int64
         _lib.wz_merge_until.restype = C.c_int64
@@ -70,7 +71,7 @@ def sk_label(x):
 class Waterz:
     """State of one waterz.agglomerate call (restated)."""
 
-    def __init__(self, affs, frags, queue_bins, stats_mode="faithful", keep_cheaper=True):
+    def __init__(self, affs, frags, queue_bins, stats_mode="faithful", keep_cheaper=True, quantile=0, initmax=False):
         assert affs.ndim == 4 and affs.shape[0] == 3
         if affs.dtype == np.uint8:
             dt = 0
@@ -80,10 +81,10 @@ class Waterz:
         self.affs = np.ascontiguousarray(affs)
         self.frags = np.ascontiguousarray(frags, dtype=np.uint64)
         Z, Y, X = self.frags.shape
-        self.h = C.c_void_p(lib().wz_create(
+        self.h = C.c_void_p(lib().wz_create_q(
             _p(self.affs), C.c_int(dt), _p(self.frags), C.c_int64(Z), C.c_int64(Y), C.c_int64(X),
             C.c_int(queue_bins), C.c_int({"faithful": 0, "canonical": 1}[stats_mode]),
-            C.c_int(1 if keep_cheaper else 0)))
+            C.c_int(1 if keep_cheaper else 0), C.c_int(int(quantile)), C.c_int(1 if initmax else 0)))
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -565,8 +565,10 @@ def golden_simple_watershed_glue():
     geometry.Roi = Roi
 
     def agglomerate(affs, thresholds, fragments, scoring_function):
-        assert scoring_function == "OneMinus<MeanAffinity<RegionGraphType, ScoreValue>>"
-        wz = Waterz(affs, fragments, 0, "faithful", True)
+        import re
+        m = re.fullmatch(r"OneMinus<HistogramQuantileAffinity<RegionGraphType, (\d+), ScoreValue, 256, (true|false)>>", scoring_function)
+        assert m or scoring_function == "OneMinus<MeanAffinity<RegionGraphType, ScoreValue>>"
+        wz = Waterz(affs, fragments, 0, "faithful", True, quantile=int(m.group(1)) if m else 0, initmax=bool(m) and m.group(2) == "true")
         for thr in sorted(thresholds):
             wz.merge_until(float(thr))
             yield wz.segmentation()
@@ -589,7 +591,9 @@ def golden_simple_watershed_glue():
     out, names = {}, {}
     cases = [dict(dtype="uint8", mask=False, cfg={}),
              dict(dtype="float32", mask=True, cfg={"sigma": [0, 1.5, 1.0], "bias": [-0.05, -0.1, -0.1], "thresholds": [0.1, 0.3, 0.6]}),
-             dict(dtype="uint8", mask=False, cfg={"fragments_in_xy": False, "min_seed_distance": 6, "bias": [-0.03, -0.03, -0.03]})]
+             dict(dtype="uint8", mask=False, cfg={"fragments_in_xy": False, "min_seed_distance": 6, "bias": [-0.03, -0.03, -0.03]}),
+             dict(dtype="uint8", mask=False, cfg={"merge_function": "hist_quant_75_initmax", "thresholds": [0.3, 0.6]}),
+             dict(dtype="float32", mask=True, cfg={"merge_function": "hist_quant_25", "bias": [-0.1, -0.2, -0.2], "thresholds": [0.5]})]
     for ci, case in enumerate(cases):
         shape = (5, 56, 48)
         a8 = synth_affs(shape, seed=80 + ci)

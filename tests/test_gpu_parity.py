@@ -401,6 +401,12 @@ SIMPLE_CASES = [
     ((10, 128, 128), {}, np.uint8),
     ((8, 96, 96), {"fragments_in_xy": False, "thresholds": [0.5, 0.1, 0.3]}, np.float32),    # unsorted thresholds
     ((6, 140, 90), {"min_seed_distance": 6, "thresholds": [0.05, 0.95]}, np.uint8),
+    # histogram-quantile scoring functions (post/watershed.py:232-244)
+    ((10, 128, 128), {"merge_function": "hist_quant_50"}, np.uint8),
+    ((10, 128, 128), {"merge_function": "hist_quant_75_initmax", "thresholds": [0.3, 0.5, 0.8]}, np.float32),
+    ((8, 96, 96), {"merge_function": "hist_quant_10", "fragments_in_xy": False, "thresholds": [0.6, 0.9]}, np.float32),
+    ((8, 96, 96), {"merge_function": "hist_quant_90", "bias": [-0.3, -0.4, -0.4], "thresholds": [0.4, 0.99]}, np.uint8),   # bins clamp at 0
+    ((6, 140, 90), {"merge_function": "hist_quant_25_initmax", "sigma": [0, 1, 1], "thresholds": [0.7]}, np.uint8),
 ]
 
 

@@ -462,3 +462,33 @@ def test_mws_seeded_noise_is_standard_normal_like():
     n = om.seeded_noise((3, 20, 40, 40), seed=5)
     assert abs(n.mean()) < 0.01 and abs(n.std() - 1.0) < 0.01 and n.min() > -3.5 and n.max() < 3.5
     assert not np.array_equal(n[0], n[1]) and np.array_equal(n, om.seeded_noise((3, 20, 40, 40), seed=5))
+
+
+def test_histogram_quantile_scores_against_brute_force():
+    """the oracle's HistogramQuantileAffinity scores of the initial region graph == a numpy brute force over the contact
+    affinities of every fragment pair (bin = min(int(a * 256), 255), pivot = Q * n // 100 + 1, (bin + 0.5) / 256); initmax
+    keeps the largest bin only"""
+    from oracle.native import Waterz
+    rng = np.random.default_rng(4)
+    frags = rng.integers(1, 12, (4, 9, 10)).astype(np.uint64)
+    frags = np.repeat(np.repeat(frags, 2, 1), 2, 2)
+    affs = rng.random((3,) + frags.shape, dtype=np.float32)
+    pairs = {}
+    for d in range(3):
+        a = np.moveaxis(frags, d, 0)
+        lo, hi, av = a[:-1], a[1:], np.moveaxis(affs[d], d, 0)[1:]
+        m = lo != hi
+        for u, v, x in zip(lo[m], hi[m], av[m]):
+            pairs.setdefault((min(u, v), max(u, v)), []).append(min(int(np.float32(x) * np.float32(256)), 255))
+    for q, initmax in ((50, False), (10, False), (90, True), (25, False)):
+        wz = Waterz(affs, frags, 0, "faithful", True, quantile=q, initmax=initmax)
+        wz.merge_until(1e-6)                       # scores every edge, merges nothing (scores >= 1/512)
+        u, v, sc = wz.region_graph()[:3]
+        assert len(u) == len(pairs)
+        for a, b, s_ in zip(u, v, sc):
+            bins = sorted(pairs[(a, b)])
+            if initmax:
+                bins = bins[-1:]
+            pivot = q * len(bins) // 100 + 1
+            want = np.float32(1.0 - (bins[pivot - 1] + 0.5) / 256)
+            assert s_ == want, (a, b, s_, want)
