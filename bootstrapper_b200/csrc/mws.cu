@@ -18,10 +18,18 @@
 //     edges come later than its top edge; A gets no mutex without a repulsive edge of its own), and A brings neither
 //     mutexes nor repulsive edges into B, so B's own decisions are what they would have been.  This is what lets the
 //     interior of an object assemble in a few rounds instead of one voxel per round around its growing core.
-// Executed edges at different clusters commute; a cluster that is not free takes part in at most one union per round.  Mutexes are kept as
-// a list of voxel pairs and a hash set of (root, root) pairs rebuilt (deduplicated) after the unions of a round.
+// Executed edges at different clusters commute; a cluster that is not free takes part in at most one union per round.
+//
+// A round costs O(window): roots come from finds on the forest (path halving), and the mutex set is keyed by EPOCH roots --
+// the roots as of the last rebuild.  Every cluster keeps the list of the non-free epoch clusters it is made of (a union of
+// two non-free clusters concatenates two lists; free clusters carry no mutex and are never listed), a mutex goes in under
+// the epoch roots of its two voxels, and the test "is there a mutex between A and B" probes the pairs of the two lists.
+// Every BS_MWS_EPOCH rounds (or when the probes of a round exceed a budget) the set is rebuilt: all voxels get their roots,
+// the lists collapse to one entry per cluster and the mutex list is re-keyed and deduplicated -- the only O(V) + O(mutexes)
+// step, which used to run every round.
 // Distinct weights (the reference adds noise by default for this reason, post/mws.py:28-31) give O(log V)-ish rounds;
 // long runs of equal weights zip up one voxel per round along the tie order.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -135,6 +143,18 @@ __global__ void __launch_bounds__(256) k_mws_endpoints(MwsGeom G, const T *__res
     if ((threadIdx.x & 31) == 0 && nrep) atomicAdd(&counts[0], nrep);
 }
 
+// root of x with path halving; safe while no union runs (phase A) and benign beside concurrent finds
+__device__ __forceinline__ uint32_t mws_find(uint32_t *parent, uint32_t x) {
+    for (;;) {
+        const uint32_t p = __ldcg(&parent[x]);
+        if (p == x) return x;
+        const uint32_t gp = __ldcg(&parent[p]);
+        if (gp == p) return p;
+        parent[x] = gp;
+        x = gp;
+    }
+}
+
 __global__ void k_mws_init(uint32_t *__restrict__ parent, size_t V) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (size_t)gridDim.x * blockDim.x) parent[i] = (uint32_t)i;
 }
@@ -145,14 +165,16 @@ __global__ void k_mws_init(uint32_t *__restrict__ parent, size_t V) {
 // phase A: roots of the window's edges (stored for the later phases: parent[] is rewritten by the unions); dead edges (one
 // cluster, NaN) are flagged; bestA over the attractive ones
 __global__ void __launch_bounds__(256) k_mws_best(const uint32_t *__restrict__ win, size_t nwin, const uint32_t *__restrict__ eu,
-                                                  const uint32_t *__restrict__ ev, const uint32_t *__restrict__ root,
-                                                  uint32_t *__restrict__ bestA, uint8_t *__restrict__ keep, uint2 *__restrict__ wroots) {
+                                                  const uint32_t *__restrict__ ev, uint32_t *parent,
+                                                  uint32_t *__restrict__ bestA, uint8_t *__restrict__ keep, uint8_t *__restrict__ did,
+                                                  uint2 *__restrict__ wroots) {
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < nwin; j += (size_t)gridDim.x * blockDim.x) {
         const uint32_t i = win[j];
         const uint32_t u = eu[i], v = ev[i];
         uint32_t ru = NONE32, rv = NONE32;
-        if (v != NONE32) ru = root[u & ~ATTR_BIT], rv = root[v];
+        if (v != NONE32) ru = mws_find(parent, u & ~ATTR_BIT), rv = mws_find(parent, v);
         wroots[j] = make_uint2(ru, rv);
+        did[j] = 0;
         if (ru == rv) {          // also the NaN edges (NONE32, NONE32)
             keep[j] = 0;
             continue;
@@ -200,9 +222,9 @@ __device__ __forceinline__ bool mws_set_has(const unsigned long long *tab, uint6
 // phase B: repulsive edges with no pending higher-priority attractive edge at either cluster become mutexes
 __global__ void __launch_bounds__(256) k_mws_repulsive(const uint32_t *__restrict__ win, size_t nwin, const uint32_t *__restrict__ eu,
                                                        const uint32_t *__restrict__ ev, const uint2 *__restrict__ wroots,
-                                                       const uint32_t *__restrict__ bestA, uint8_t *__restrict__ keep,
-                                                       unsigned long long *__restrict__ tab, uint64_t tmask, uint2 *__restrict__ mlist,
-                                                       unsigned long long *__restrict__ counts) {
+                                                       const uint32_t *__restrict__ bestA, const uint32_t *__restrict__ eroot,
+                                                       uint8_t *__restrict__ keep, unsigned long long *__restrict__ tab, uint64_t tmask,
+                                                       uint2 *__restrict__ mlist, unsigned long long *__restrict__ counts) {
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < nwin; j += (size_t)gridDim.x * blockDim.x) {
         if (!keep[j]) continue;
         const uint32_t i = win[j];
@@ -211,7 +233,8 @@ __global__ void __launch_bounds__(256) k_mws_repulsive(const uint32_t *__restric
         const uint2 r = wroots[j];
         if (i < bestA[r.x] && i < bestA[r.y]) {
             keep[j] = 0;
-            const unsigned long long key = ((unsigned long long)min(r.x, r.y) << 32) | max(r.x, r.y);
+            const uint32_t ea = eroot[u], eb = eroot[v];     // epoch clusters of the two voxels (different: r.x != r.y)
+            const unsigned long long key = ((unsigned long long)min(ea, eb) << 32) | max(ea, eb);
             if (mws_set_insert(tab, tmask, key)) {
                 const unsigned long long slot = atomicAdd(&counts[1], 1ull);    // mutex list length
                 mlist[slot] = make_uint2(u, v);
@@ -226,7 +249,9 @@ __global__ void __launch_bounds__(256) k_mws_repulsive(const uint32_t *__restric
 __global__ void __launch_bounds__(256) k_mws_attractive(const uint32_t *__restrict__ win, size_t nwin, const uint32_t *__restrict__ eu,
                                                         const uint2 *__restrict__ wroots, uint32_t *__restrict__ parent,
                                                         const uint32_t *__restrict__ bestA, const uint8_t *__restrict__ nonfree,
-                                                        uint8_t *__restrict__ keep, const unsigned long long *__restrict__ tab,
+                                                        const uint32_t *__restrict__ ehead, const uint32_t *__restrict__ enext,
+                                                        uint32_t *__restrict__ pairmark, uint32_t round, uint8_t *__restrict__ keep,
+                                                        uint8_t *__restrict__ did, const unsigned long long *__restrict__ tab,
                                                         uint64_t tmask, unsigned long long *__restrict__ counts) {
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < nwin; j += (size_t)gridDim.x * blockDim.x) {
         if (!keep[j]) continue;
@@ -235,21 +260,70 @@ __global__ void __launch_bounds__(256) k_mws_attractive(const uint32_t *__restri
         const uint32_t ru = wroots[j].x, rv = wroots[j].y;      // the roots as of the start of the round
         const bool top_u = bestA[ru] == i, top_v = bestA[rv] == i;
         if (!top_u && !top_v) continue;
-        const bool free_u = top_u && !nonfree[ru], free_v = top_v && !nonfree[rv];
+        const bool nf_u = nonfree[ru], nf_v = nonfree[rv];
+        const bool free_u = top_u && !nf_u, free_v = top_v && !nf_v;
         if (!(top_u && top_v) && !free_u && !free_v) continue;
         keep[j] = 0;
         bool blocked = false;
-        if (!free_u && !free_v) {
-            const unsigned long long key = ((unsigned long long)min(ru, rv) << 32) | max(ru, rv);
-            blocked = mws_set_has(tab, tmask, key);
+        if (nf_u && nf_v) {
+            // a mutex between any epoch cluster of one side and any of the other
+            unsigned long long probes = 0;
+            for (uint32_t ea = ehead[ru]; ea != NONE32 && !blocked; ea = enext[ea])
+                for (uint32_t eb = ehead[rv]; eb != NONE32; eb = enext[eb]) {
+                    probes++;
+                    if (mws_set_has(tab, tmask, ((unsigned long long)min(ea, eb) << 32) | max(ea, eb))) {
+                        blocked = true;
+                        break;
+                    }
+                }
+            atomicAdd(&counts[8], probes);
         }
         if (blocked) {
             atomicAdd(&counts[4], 1ull);        // blocked by a mutex
         } else {
+            if (nf_u && nf_v) pairmark[ru] = round, pairmark[rv] = round;   // the one union of two non-free clusters of their component
+            did[j] = 1;
             uf_union(parent, ru, rv);           // lock-free, the smaller index becomes the root
             atomicAdd(&counts[2], 1ull);        // merges (all rounds) ...
             atomicAdd(&counts[5], 1ull);        // ... and of this round
         }
+    }
+}
+
+// after the unions of a round: the epoch-cluster list of every new cluster.  A component of this round's unions holds at most
+// one union of two non-free clusters (its thread concatenates the two lists) plus free clusters that joined (they carry no
+// list); where the root moved to a free cluster's voxel the list moves with it.
+__global__ void __launch_bounds__(256) k_mws_post_lists(const uint2 *__restrict__ wroots, const uint8_t *__restrict__ did, size_t nwin,
+                                                        uint32_t *parent, const uint8_t *__restrict__ nonfree,
+                                                        const uint32_t *__restrict__ pairmark, uint32_t round, uint32_t *ehead,
+                                                        uint32_t *etail, uint32_t *enext) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < nwin; j += (size_t)gridDim.x * blockDim.x) {
+        if (!did[j]) continue;
+        const uint32_t x = wroots[j].x, y = wroots[j].y;
+        const bool nfx = nonfree[x], nfy = nonfree[y];
+        if (!nfx && !nfy) continue;
+        const uint32_t R = mws_find(parent, x);
+        if (nfx && nfy) {
+            const uint32_t hx = ehead[x], tx = etail[x], hy = ehead[y], ty = etail[y];
+            enext[tx] = hy;
+            ehead[R] = hx;
+            etail[R] = ty;
+        } else {
+            const uint32_t n = nfx ? x : y;
+            if (pairmark[n] == round || R == n) continue;
+            const uint32_t h = ehead[n], t = etail[n];
+            ehead[R] = h;
+            etail[R] = t;
+        }
+    }
+}
+// ... and its flag: a cluster that absorbed a non-free one is not free
+__global__ void __launch_bounds__(256) k_mws_post_flags(const uint2 *__restrict__ wroots, const uint8_t *__restrict__ did, size_t nwin,
+                                                        uint32_t *parent, uint8_t *nonfree) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < nwin; j += (size_t)gridDim.x * blockDim.x) {
+        if (!did[j]) continue;
+        const uint32_t x = wroots[j].x, y = wroots[j].y;
+        if (nonfree[x] || nonfree[y]) nonfree[mws_find(parent, x)] = 1;
     }
 }
 
@@ -274,9 +348,10 @@ __global__ void k_mws_next_window(const uint32_t *__restrict__ win, const uint8_
     }
 }
 
-// roots of all voxels after the unions of a round (chains of unions: walk to the root), written to a second array so that
-// the walks never see a half-updated forest.  A cluster that absorbs a non-free one is not free.
-__global__ void k_mws_flatten(const uint32_t *__restrict__ parent, uint32_t *__restrict__ out, uint8_t *__restrict__ nonfree, size_t V) {
+// rebuild, part 1: roots of all voxels (= their epoch roots until the next rebuild), written to a second array so that the
+// walks never see a half-updated forest; every cluster's epoch list collapses to the cluster itself
+__global__ void k_mws_flatten(const uint32_t *__restrict__ parent, uint32_t *__restrict__ out, uint32_t *__restrict__ ehead,
+                              uint32_t *__restrict__ etail, uint32_t *__restrict__ enext, size_t V) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (size_t)gridDim.x * blockDim.x) {
         uint32_t x = (uint32_t)i, p = parent[x];
         while (p != x) {
@@ -284,7 +359,9 @@ __global__ void k_mws_flatten(const uint32_t *__restrict__ parent, uint32_t *__r
             p = parent[x];
         }
         out[i] = x;
-        if (x != (uint32_t)i && nonfree[i]) nonfree[x] = 1;
+        ehead[i] = (uint32_t)i;
+        etail[i] = (uint32_t)i;
+        enext[i] = NONE32;
     }
 }
 
@@ -310,7 +387,8 @@ __global__ void __launch_bounds__(256) k_mws_rekey(const uint2 *__restrict__ mli
 }
 
 __global__ void k_mws_labels(const uint32_t *__restrict__ parent, size_t V, uint64_t *__restrict__ labels) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (size_t)gridDim.x * blockDim.x) labels[i] = (uint64_t)parent[i] + 1u;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (size_t)gridDim.x * blockDim.x)
+        labels[i] = (uint64_t)uf_find(parent, (uint32_t)i) + 1u;
 }
 
 // remove_small_objects(labels, min_size) of simple_mutex (post/watershed_mutex.py:272-277): labels with fewer voxels -> 0
@@ -329,6 +407,10 @@ __global__ void k_mws_debris(const uint64_t *__restrict__ labels, size_t V, cons
 // edges per round (BS_MWS_WINDOW overrides; the result does not depend on it)
 static unsigned long long g_mws_window = getenv("BS_MWS_WINDOW") ? strtoull(getenv("BS_MWS_WINDOW"), nullptr, 10) : (1ull << 21);
 
+// rounds between two rebuilds of the mutex set (BS_MWS_EPOCH), and the number of set probes in one round that forces one early
+static unsigned long long g_mws_epoch = getenv("BS_MWS_EPOCH") ? strtoull(getenv("BS_MWS_EPOCH"), nullptr, 10) : 64;
+static unsigned long long g_mws_probe_budget = getenv("BS_MWS_PROBES") ? strtoull(getenv("BS_MWS_PROBES"), nullptr, 10) : (1ull << 23);
+
 static unsigned grid_for(size_t n) { return (unsigned)std::min<size_t>(std::max<size_t>((n + 255) / 256, 1), 148 * 16); }
 
 template <typename T>
@@ -338,13 +420,17 @@ static int mws_run(const T *affs, const uint8_t *mask, MwsGeom &G, int zero_is_r
     const unsigned long long E = G.ebase[G.C];
     BS_ARG(V < (1ull << 31), "bs_mws_agglom: volume too large for 31-bit voxel indices");
     BS_ARG(E < (1ull << 32) - 1, "bs_mws_agglom: more than 2^32 edges");
-    DevBuf parent, root, nonfree, keys, keys2, vals, vals2, eu, ev, win, win2, wroots, keep, pos, bestA, counts, tab, mlist, mlist2;
+    DevBuf parent, root, nonfree, keys, keys2, vals, vals2, eu, ev, win, win2, wroots, keep, did, pos, bestA, counts, tab, mlist, mlist2, ehead,
+        etail, enext, pairmark;
     BS_TRY(parent.alloc(4 * V, s));
     BS_LAUNCH(k_mws_init, grid_for(V), 256, 0, s, parent.as<uint32_t>(), V);
-    BS_TRY(counts.alloc_zero(64, s));
+    BS_TRY(counts.alloc_zero(128, s));
     unsigned long long *d_cnt = counts.as<unsigned long long>();   // [0] repulsive edges [1] mutex list length [2] merges
                                                                    // [3] repulsive executed [4] blocked [5] merges this round [6] survivors
-    unsigned long long h_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                                                                   // [8] mutex-set probes of this round
+    unsigned long long h_cnt[16];
+    memset(h_cnt, 0, sizeof(h_cnt));
+    int rounds = 0, rebuilds = 0;
     if (E) {
         BS_TRY(keys.alloc(8 * (size_t)E, s));
         BS_TRY(keys2.alloc(8 * (size_t)E, s));
@@ -360,7 +446,7 @@ static int mws_run(const T *affs, const uint8_t *mask, MwsGeom &G, int zero_is_r
         BS_LAUNCH((k_mws_endpoints<T>), grid_for(E), 256, 0, s, G, affs, mask, E, vals.as<uint32_t>(), zero_is_repulsive, eu.as<uint32_t>(),
                   ev.as<uint32_t>(), d_cnt);
         vals.release();
-        BS_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 64, cudaMemcpyDeviceToHost, s));
+        BS_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 128, cudaMemcpyDeviceToHost, s));
         BS_CUDA(cudaStreamSynchronize(s));
         const unsigned long long nrep = h_cnt[0];
         // mutex set: at most one entry per executed repulsive edge
@@ -371,14 +457,21 @@ static int mws_run(const T *affs, const uint8_t *mask, MwsGeom &G, int zero_is_r
         BS_TRY(mlist2.alloc(8 * (size_t)(nrep + 1), s));
         BS_TRY(bestA.alloc_fill(4 * V, 0xFF, s));
         BS_TRY(root.alloc(4 * V, s));
+        BS_TRY(ehead.alloc(4 * V, s));
+        BS_TRY(etail.alloc(4 * V, s));
+        BS_TRY(enext.alloc(4 * V, s));
+        BS_TRY(pairmark.alloc_zero(4 * V, s));
         BS_TRY(nonfree.alloc_zero(V, s));
-        BS_CUDA(cudaMemcpyAsync(root.p, parent.p, 4 * V, cudaMemcpyDeviceToDevice, s));
+        // epoch 0: every voxel is its own cluster
+        BS_LAUNCH(k_mws_flatten, grid_for(V), 256, 0, s, parent.as<uint32_t>(), root.as<uint32_t>(), ehead.as<uint32_t>(), etail.as<uint32_t>(),
+                  enext.as<uint32_t>(), V);
         BS_LAUNCH(k_mws_mark_repulsive, grid_for(E), 256, 0, s, eu.as<uint32_t>(), ev.as<uint32_t>(), (size_t)E, nonfree.as<uint8_t>());
         const uint32_t wcap = (uint32_t)std::min<unsigned long long>(E, g_mws_window);
         BS_TRY(win.alloc(4 * (size_t)wcap, s));
         BS_TRY(win2.alloc(4 * (size_t)wcap, s));
         BS_TRY(wroots.alloc(8 * (size_t)wcap, s));
         BS_TRY(keep.alloc((size_t)wcap, s));
+        BS_TRY(did.alloc((size_t)wcap, s));
         BS_TRY(pos.alloc(4 * (size_t)wcap, s));
         // first window: the wcap best edges
         uint32_t cursor = 0;
@@ -388,34 +481,48 @@ static int mws_run(const T *affs, const uint8_t *mask, MwsGeom &G, int zero_is_r
                   (const uint32_t *)(d_cnt + 6), cursor, wcap, (uint32_t)E, win.as<uint32_t>());
         nwin = wcap;
         cursor = wcap;
-        int rounds = 0;
+        int since_rebuild = 0;
+        bool unions_since_rebuild = false;
         while (nwin > 0) {
             rounds++;
+            since_rebuild++;
             BS_CUDA(cudaMemsetAsync(d_cnt + 5, 0, 8, s));
-            BS_LAUNCH(k_mws_best, grid_for(nwin), 256, 0, s, win.as<uint32_t>(), nwin, eu.as<uint32_t>(), ev.as<uint32_t>(), root.as<uint32_t>(),
-                      bestA.as<uint32_t>(), keep.as<uint8_t>(), wroots.as<uint2>());
+            BS_CUDA(cudaMemsetAsync(d_cnt + 8, 0, 8, s));
+            BS_LAUNCH(k_mws_best, grid_for(nwin), 256, 0, s, win.as<uint32_t>(), nwin, eu.as<uint32_t>(), ev.as<uint32_t>(), parent.as<uint32_t>(),
+                      bestA.as<uint32_t>(), keep.as<uint8_t>(), did.as<uint8_t>(), wroots.as<uint2>());
             BS_LAUNCH(k_mws_repulsive, grid_for(nwin), 256, 0, s, win.as<uint32_t>(), nwin, eu.as<uint32_t>(), ev.as<uint32_t>(),
-                      wroots.as<uint2>(), bestA.as<uint32_t>(), keep.as<uint8_t>(), tab.as<unsigned long long>(), tcap - 1, mlist.as<uint2>(),
-                      d_cnt);
+                      wroots.as<uint2>(), bestA.as<uint32_t>(), root.as<uint32_t>(), keep.as<uint8_t>(), tab.as<unsigned long long>(), tcap - 1,
+                      mlist.as<uint2>(), d_cnt);
             BS_LAUNCH(k_mws_attractive, grid_for(nwin), 256, 0, s, win.as<uint32_t>(), nwin, eu.as<uint32_t>(), wroots.as<uint2>(),
-                      parent.as<uint32_t>(), bestA.as<uint32_t>(), nonfree.as<uint8_t>(), keep.as<uint8_t>(), tab.as<unsigned long long>(),
-                      tcap - 1, d_cnt);
+                      parent.as<uint32_t>(), bestA.as<uint32_t>(), nonfree.as<uint8_t>(), ehead.as<uint32_t>(), enext.as<uint32_t>(),
+                      pairmark.as<uint32_t>(), (uint32_t)rounds, keep.as<uint8_t>(), did.as<uint8_t>(), tab.as<unsigned long long>(), tcap - 1,
+                      d_cnt);
+            BS_LAUNCH(k_mws_post_lists, grid_for(nwin), 256, 0, s, wroots.as<uint2>(), did.as<uint8_t>(), nwin, parent.as<uint32_t>(),
+                      nonfree.as<uint8_t>(), pairmark.as<uint32_t>(), (uint32_t)rounds, ehead.as<uint32_t>(), etail.as<uint32_t>(),
+                      enext.as<uint32_t>());
+            BS_LAUNCH(k_mws_post_flags, grid_for(nwin), 256, 0, s, wroots.as<uint2>(), did.as<uint8_t>(), nwin, parent.as<uint32_t>(),
+                      nonfree.as<uint8_t>());
             BS_LAUNCH(k_mws_reset_best, grid_for(nwin), 256, 0, s, wroots.as<uint2>(), nwin, bestA.as<uint32_t>());
             // next window: survivors (order preserved) + refill
             BS_TRY(scan_exclusive_u8(keep.as<uint8_t>(), pos.as<uint32_t>(), nwin, (uint32_t *)(d_cnt + 6), s));
             BS_LAUNCH(k_mws_next_window, grid_for(wcap), 256, 0, s, win.as<uint32_t>(), keep.as<uint8_t>(), pos.as<uint32_t>(), nwin,
                       (const uint32_t *)(d_cnt + 6), cursor, wcap, (uint32_t)E, win2.as<uint32_t>());
             win.swap(win2);
-            BS_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 64, cudaMemcpyDeviceToHost, s));
+            BS_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 128, cudaMemcpyDeviceToHost, s));
             BS_CUDA(cudaStreamSynchronize(s));
             const uint32_t nkeep = (uint32_t)h_cnt[6];
             const uint32_t nfill = std::min<uint32_t>(wcap - nkeep, (uint32_t)E - cursor);
             BS_ARG(nkeep < nwin || nfill > 0, "bs_mws_agglom: a round executed no edge (internal error)");
             cursor += nfill;
             nwin = (size_t)nkeep + nfill;
-            if (h_cnt[5] > 0) {
-                // unions happened: roots of all voxels, then the mutex set re-keyed by the new roots
-                BS_LAUNCH(k_mws_flatten, grid_for(V), 256, 0, s, parent.as<uint32_t>(), root.as<uint32_t>(), nonfree.as<uint8_t>(), V);
+            if (h_cnt[5] > 0) unions_since_rebuild = true;
+            if (nwin > 0 && unions_since_rebuild && ((unsigned long long)since_rebuild >= g_mws_epoch || h_cnt[8] > g_mws_probe_budget)) {
+                // rebuild: roots of all voxels become the epoch roots, the lists collapse, the mutex set is re-keyed
+                rebuilds++;
+                since_rebuild = 0;
+                unions_since_rebuild = false;
+                BS_LAUNCH(k_mws_flatten, grid_for(V), 256, 0, s, parent.as<uint32_t>(), root.as<uint32_t>(), ehead.as<uint32_t>(),
+                          etail.as<uint32_t>(), enext.as<uint32_t>(), V);
                 BS_CUDA(cudaMemcpyAsync(parent.p, root.p, 4 * V, cudaMemcpyDeviceToDevice, s));
                 const size_t nm = (size_t)h_cnt[1];
                 if (nm) {
@@ -427,8 +534,9 @@ static int mws_run(const T *affs, const uint8_t *mask, MwsGeom &G, int zero_is_r
                 }
             }
         }
-        h_cnt[7] = (unsigned long long)rounds;
     }
+    h_cnt[7] = (unsigned long long)rounds;
+    if (getenv("BS_MWS_VERBOSE")) fprintf(stderr, "[bs mws] edges %llu rounds %d rebuilds %d\n", (unsigned long long)E, rounds, rebuilds);
     BS_LAUNCH(k_mws_labels, grid_for(V), 256, 0, s, parent.as<uint32_t>(), V, labels_out);   // flat: parent == roots
     if (seg_out) {
         if (remove_debris > 0) {
