@@ -492,6 +492,32 @@ def run_ours(args):
         del r2
         torch.cuda.empty_cache()
         native.release_scratch()
+    if job.world == 1 and args.config == 2 and not args.quick and not args.no_extra:
+        # BASELINE configs[2]: mutex-watershed fragments from the 9-offset default neighbourhood at 512^3 on one GPU
+        if res is not None:
+            del res["seg"], res["affs"], res["out"]
+            res = None
+        torch.cuda.empty_cache()
+        native.release_scratch()
+        kw = dict(strides=MWS_STRIDES, noise_eps=0.001, noise_seed=0)
+        native.mws_agglom(mws_affs9((64, 64, 64), seed=0), MWS_NBH, MWS_BIAS, **kw)          # warm-up (module load, allocator)
+        a9 = mws_affs9((512, 512, 512), seed=0)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        torch.cuda.synchronize()
+        ev[0].record()
+        frags9, _, cnt9 = native.mws_agglom(a9, MWS_NBH, MWS_BIAS, **kw)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms9 = ev[0].elapsed_time(ev[1])
+        extra["config3"] = {"workload": "mutex-watershed fragments (bs segment --mws, simple_mutex), 9x(512,512,512) uint8 affinities, offsets / biases / "
+                                        "strides = the reference defaults (segment.py:24-51), seeded noise 0.001, one GPU",
+                            "ms_per_step": ms9, "value": 512.0 ** 3 / (ms9 * 1e-3), "unit": "voxels/s", "steps": 1, "warmup": "one 64^3 call",
+                            "counters": {k: int(v) for k, v in cnt9.items()},
+                            "parity": "bit-identical to the sequential restatement of mwatershed.agglom at oracle-sized cases "
+                                      "(tests/test_gpu_mws.py; declared tie rule D4, parity unpinned)"}
+        del a9, frags9
+        torch.cuda.empty_cache()
+        native.release_scratch()
     if job.rank == 0:
         line["parity_checked"] = parity or None
         if extra:
@@ -532,7 +558,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="small volume (smoke / CI), not a valid bench number")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (and its parity comparison)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg")
-    ap.add_argument("--no-extra", action="store_true", help="skip the extra BASELINE configurations (config 5 at 8 GPUs, config 4 at 4 / 2)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra BASELINE configurations (config 3 at 1 GPU, config 5 at 8 GPUs, config 4 at 4 / 2)")
     ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity comparison")
     ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
                     help="2 = BASELINE configs[1] (default, the metric's workload); 4 = 1024^3 3-D seeded + seed_eps over 4 GPUs (a 256x1024x1024 "

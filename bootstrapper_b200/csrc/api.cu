@@ -30,6 +30,7 @@ int relabel_dense(Plan &P, const uint64_t *frags, int64_t n, const uint64_t *con
 int components_multi(Plan &P, const uint64_t *nodes, int64_t n, const uint64_t *eu, const uint64_t *ev, const float *scores,
                      int64_t m, const float *thresholds, int T, uint64_t *const *comps, cudaStream_t s);
 int plan_node_ids(Plan &P, uint64_t *out, long long *n_out, cudaStream_t s);
+int aff_agglom(Plan &P, const void *affs, const uint64_t *frags, int C, const int32_t *offsets, cudaStream_t s);
 int dense_fragments(Plan &P, const uint64_t *frags, int64_t n, uint32_t *dense_out, cudaStream_t s);
 int cc_affs(const void *affs, int dtype, const uint8_t *mask, int Z, int Y, int X, float thr, int remove_debris, uint64_t *frags_out,
             uint64_t *seg_out, int64_t *n_out, cudaStream_t s);
@@ -381,6 +382,37 @@ int bs_mws_agglom(const void *affs, int aff_dtype, const uint8_t *mask, int n_ch
     init_mempool();
     return bs::mws_agglom(affs, aff_dtype, mask, n_channels, Z, Y, X, offsets, strides, bias, noise_eps, noise_seed, 1, remove_debris,
                           frags_out, seg_out, counters_out, (cudaStream_t)stream);
+}
+
+int bs_mws_agglom_blocks(const void *affs, int aff_dtype, const uint8_t *mask, int n_channels, int n_blocks, int Z, int Y, int X,
+                         const int32_t *offsets, const int32_t *strides, const double *bias, double noise_eps, const uint64_t *block_seeds,
+                         uint32_t *labels_out, int64_t *counters_out, void *stream) {
+    BS_ARG(affs && offsets && labels_out, "bs_mws_agglom_blocks: null argument");
+    BS_ARG(aff_dtype == BS_DTYPE_U8 || aff_dtype == BS_DTYPE_F32, "bs_mws_agglom_blocks: aff_dtype must be u8 or f32");
+    BS_ARG(noise_eps == 0.0 || block_seeds, "bs_mws_agglom_blocks: noise needs one seed per block");
+    init_mempool();
+    return bs::mws_agglom_blocks(affs, aff_dtype, mask, n_channels, n_blocks, Z, Y, X, offsets, strides, bias, noise_eps,
+                                 (const unsigned long long *)block_seeds, 1, labels_out, counters_out, (cudaStream_t)stream);
+}
+
+int bs_aff_agglom(bs_plan *p, const void *affs, const uint64_t *frags, int n_channels, const int32_t *offsets, void *stream) {
+    BS_ARG(p && affs && frags && offsets, "bs_aff_agglom: null argument");
+    Plan &P = *p->p;
+    if (P.owned.size() != P.blocks.size() && !P.counts_global) {
+        set_error("bs_aff_agglom: multi-rank plan needs bs_stage1_set_block_counts first");
+        return BS_ERR_STATE;
+    }
+    BS_ARG(n_channels == P.cfg.n_channels, "bs_aff_agglom: n_channels differs from the plan's");
+    init_mempool();
+    return aff_agglom(P, affs, frags, n_channels, offsets, (cudaStream_t)stream);
+}
+
+int bs_graph_mws(const uint64_t *nodes, int64_t n, const uint64_t *edges_u, const uint64_t *edges_v, const float *scores, int64_t m,
+                 double weight, double bias, uint64_t *clusters_out, int64_t *counters_out, void *stream) {
+    BS_ARG(n == 0 || (nodes && clusters_out), "bs_graph_mws: null argument");
+    BS_ARG(m == 0 || (edges_u && edges_v && scores), "bs_graph_mws: null edges");
+    init_mempool();
+    return bs::graph_mws(nodes, n, edges_u, edges_v, scores, m, weight, bias, clusters_out, counters_out, (cudaStream_t)stream);
 }
 
 int bs_label_stats(const uint64_t *seg, const int32_t *shape, int64_t capacity, uint64_t *ids_out, int64_t *sizes_out,

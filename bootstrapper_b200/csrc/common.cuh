@@ -164,6 +164,11 @@ int radix_sort_pairs(uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_
 int mws_agglom(const void *affs, int aff_dtype, const uint8_t *mask, int C, int Z, int Y, int X, const int32_t *offsets,
                const int32_t *strides, const double *bias, double noise_eps, unsigned long long noise_seed, int zero_is_repulsive,
                int remove_debris, uint64_t *labels_out, uint64_t *seg_out, int64_t *counters_out, cudaStream_t s);
+int mws_agglom_blocks(const void *affs, int aff_dtype, const uint8_t *mask, int C, int n_blocks, int Z, int Y, int X, const int32_t *offsets,
+                      const int32_t *strides, const double *bias, double noise_eps, const unsigned long long *block_seeds_host,
+                      int zero_is_repulsive, uint32_t *labels_out, int64_t *counters_out, cudaStream_t s);
+int graph_mws(const uint64_t *nodes, int64_t n, const uint64_t *u, const uint64_t *v, const float *scores, int64_t m, double weight,
+              double bias, uint64_t *out, int64_t *counters_out, cudaStream_t s);
 
 // ---- device helpers ----
 __device__ __forceinline__ unsigned lanemask_lt() {

@@ -55,6 +55,11 @@ struct MwsGeom {
     int has_noise;
     double noise_eps, noise_k;
     unsigned long long seed;
+    // blockwise use (volara ExtractFrags): the volume is nseg read ROIs of depth seg_z stacked along z; the lattices above
+    // describe ONE segment, edges never cross a segment boundary, noise is keyed by (seg_seeds[segment], channel, voxel
+    // within the segment).  Single volume: nseg = 1, seg_z = Z, seg_seeds = nullptr.
+    int nseg, seg_z;
+    const unsigned long long *seg_seeds;
 };
 
 __device__ __forceinline__ uint64_t mws_splitmix64(uint64_t x) {
@@ -74,8 +79,10 @@ __device__ __forceinline__ void mws_slot(const MwsGeom &G, unsigned long long e,
     const int ix = (int)(k % (unsigned)G.nx[c]);
     k /= (unsigned)G.nx[c];
     const int iy = (int)(k % (unsigned)G.ny[c]);
-    const int iz = (int)(k / (unsigned)G.ny[c]);
-    const int z = G.z0[c] + iz * G.st[c][0], y = G.y0[c] + iy * G.st[c][1], x = G.x0[c] + ix * G.st[c][2];
+    k /= (unsigned)G.ny[c];
+    const int iz = (int)(k % (unsigned)max(G.nz[c], 1));
+    const int seg = (int)(k / (unsigned)max(G.nz[c], 1));
+    const int z = seg * G.seg_z + G.z0[c] + iz * G.st[c][0], y = G.y0[c] + iy * G.st[c][1], x = G.x0[c] + ix * G.st[c][2];
     p = (uint32_t)(((long long)z * G.Y + y) * G.X + x);
     q = (uint32_t)(((long long)(z + G.off[c][0]) * G.Y + (y + G.off[c][1])) * G.X + (x + G.off[c][2]));
 }
@@ -94,7 +101,14 @@ __device__ __forceinline__ double mws_weight(const MwsGeom &G, const T *affs, co
     double sh = 0.0;
     if (G.has_noise) {
         // seeded stand-in for numpy's unseeded randn: sum of four 16-bit uniforms, centred and scaled to unit variance
-        const uint64_t h = mws_mixw(mws_mixw(mws_mixw(G.seed, c), (long long)p), 11);
+        uint64_t seed = G.seed;
+        long long pl = (long long)p;
+        if (G.seg_seeds) {
+            const long long segv = (long long)G.seg_z * G.Y * G.X;
+            seed = G.seg_seeds[pl / segv];
+            pl = pl % segv;
+        }
+        const uint64_t h = mws_mixw(mws_mixw(mws_mixw(seed, c), pl), 11);
         const long long sum = (long long)(h & 0xFFFF) + (long long)((h >> 16) & 0xFFFF) + (long long)((h >> 32) & 0xFFFF) + (long long)(h >> 48);
         const double n = __dmul_rn((double)(sum - 131070), G.noise_k);
         sh = __dadd_rn(sh, __dmul_rn(n, G.noise_eps));
@@ -386,9 +400,17 @@ __global__ void __launch_bounds__(256) k_mws_rekey(const uint2 *__restrict__ mli
     }
 }
 
-__global__ void k_mws_labels(const uint32_t *__restrict__ parent, size_t V, uint64_t *__restrict__ labels) {
+__global__ void k_mws_isroot(const uint32_t *__restrict__ parent, size_t V, uint8_t *__restrict__ flag) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (size_t)gridDim.x * blockDim.x) flag[i] = parent[i] == (uint32_t)i;
+}
+__global__ void k_mws_dense_labels(const uint32_t *__restrict__ parent, const uint32_t *__restrict__ rank, size_t V, uint32_t *__restrict__ labels) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (size_t)gridDim.x * blockDim.x)
-        labels[i] = (uint64_t)uf_find(parent, (uint32_t)i) + 1u;
+        labels[i] = rank[uf_find(parent, (uint32_t)i)] + 1u;
+}
+template <typename L>
+__global__ void k_mws_labels(const uint32_t *__restrict__ parent, size_t V, L *__restrict__ labels) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (size_t)gridDim.x * blockDim.x)
+        labels[i] = (L)uf_find(parent, (uint32_t)i) + 1u;
 }
 
 // remove_small_objects(labels, min_size) of simple_mutex (post/watershed_mutex.py:272-277): labels with fewer voxels -> 0
@@ -413,15 +435,113 @@ static unsigned long long g_mws_probe_budget = getenv("BS_MWS_PROBES") ? strtoul
 
 static unsigned grid_for(size_t n) { return (unsigned)std::min<size_t>(std::max<size_t>((n + 255) / 256, 1), 148 * 16); }
 
+// The rounds: eu (voxel / node | ATTR_BIT, NONE32 = dropped), ev, E edges in sequential order (rank = index), V nodes, nrep =
+// number of repulsive edges.  `parent` (4 V bytes, identity on entry) holds the forest on return (root = smallest index).
+// h_cnt: [2] merges [3] mutex edges [4] blocked; rounds / rebuilds counted.
+static int mws_rounds(const uint32_t *eu, const uint32_t *ev, unsigned long long E, size_t V, unsigned long long nrep, uint32_t *parent,
+                      unsigned long long *d_cnt, unsigned long long *h_cnt, int *rounds_out, int *rebuilds_out, cudaStream_t s) {
+    DevBuf root, nonfree, win, win2, wroots, keep, did, pos, bestA, tab, mlist, mlist2, ehead, etail, enext, pairmark;
+    int rounds = 0, rebuilds = 0;
+    {
+        // mutex set: at most one entry per executed repulsive edge
+        uint64_t tcap = 1024;
+        while (tcap < 2 * nrep + 16) tcap <<= 1;
+        BS_TRY(tab.alloc_fill(8 * tcap, 0xFF, s));
+        BS_TRY(mlist.alloc(8 * (size_t)(nrep + 1), s));
+        BS_TRY(mlist2.alloc(8 * (size_t)(nrep + 1), s));
+        BS_TRY(bestA.alloc_fill(4 * V, 0xFF, s));
+        BS_TRY(root.alloc(4 * V, s));
+        BS_TRY(ehead.alloc(4 * V, s));
+        BS_TRY(etail.alloc(4 * V, s));
+        BS_TRY(enext.alloc(4 * V, s));
+        BS_TRY(pairmark.alloc_zero(4 * V, s));
+        BS_TRY(nonfree.alloc_zero(V, s));
+        // epoch 0: every voxel is its own cluster
+        BS_LAUNCH(k_mws_flatten, grid_for(V), 256, 0, s, parent, root.as<uint32_t>(), ehead.as<uint32_t>(), etail.as<uint32_t>(),
+                  enext.as<uint32_t>(), V);
+        BS_LAUNCH(k_mws_mark_repulsive, grid_for(E), 256, 0, s, eu, ev, (size_t)E, nonfree.as<uint8_t>());
+        const uint32_t wcap = (uint32_t)std::min<unsigned long long>(E, g_mws_window);
+        BS_TRY(win.alloc(4 * (size_t)wcap, s));
+        BS_TRY(win2.alloc(4 * (size_t)wcap, s));
+        BS_TRY(wroots.alloc(8 * (size_t)wcap, s));
+        BS_TRY(keep.alloc((size_t)wcap, s));
+        BS_TRY(did.alloc((size_t)wcap, s));
+        BS_TRY(pos.alloc(4 * (size_t)wcap, s));
+        // first window: the wcap best edges
+        uint32_t cursor = 0;
+        size_t nwin = 0;
+        BS_CUDA(cudaMemsetAsync(d_cnt + 6, 0, 8, s));
+        BS_LAUNCH(k_mws_next_window, grid_for(wcap), 256, 0, s, win.as<uint32_t>(), keep.as<uint8_t>(), pos.as<uint32_t>(), (size_t)0,
+                  (const uint32_t *)(d_cnt + 6), cursor, wcap, (uint32_t)E, win.as<uint32_t>());
+        nwin = wcap;
+        cursor = wcap;
+        int since_rebuild = 0;
+        bool unions_since_rebuild = false;
+        while (nwin > 0) {
+            rounds++;
+            since_rebuild++;
+            BS_CUDA(cudaMemsetAsync(d_cnt + 5, 0, 8, s));
+            BS_CUDA(cudaMemsetAsync(d_cnt + 8, 0, 8, s));
+            BS_LAUNCH(k_mws_best, grid_for(nwin), 256, 0, s, win.as<uint32_t>(), nwin, eu, ev, parent,
+                      bestA.as<uint32_t>(), keep.as<uint8_t>(), did.as<uint8_t>(), wroots.as<uint2>());
+            BS_LAUNCH(k_mws_repulsive, grid_for(nwin), 256, 0, s, win.as<uint32_t>(), nwin, eu, ev,
+                      wroots.as<uint2>(), bestA.as<uint32_t>(), root.as<uint32_t>(), keep.as<uint8_t>(), tab.as<unsigned long long>(), tcap - 1,
+                      mlist.as<uint2>(), d_cnt);
+            BS_LAUNCH(k_mws_attractive, grid_for(nwin), 256, 0, s, win.as<uint32_t>(), nwin, eu, wroots.as<uint2>(),
+                      parent, bestA.as<uint32_t>(), nonfree.as<uint8_t>(), ehead.as<uint32_t>(), enext.as<uint32_t>(),
+                      pairmark.as<uint32_t>(), (uint32_t)rounds, keep.as<uint8_t>(), did.as<uint8_t>(), tab.as<unsigned long long>(), tcap - 1,
+                      d_cnt);
+            BS_LAUNCH(k_mws_post_lists, grid_for(nwin), 256, 0, s, wroots.as<uint2>(), did.as<uint8_t>(), nwin, parent,
+                      nonfree.as<uint8_t>(), pairmark.as<uint32_t>(), (uint32_t)rounds, ehead.as<uint32_t>(), etail.as<uint32_t>(),
+                      enext.as<uint32_t>());
+            BS_LAUNCH(k_mws_post_flags, grid_for(nwin), 256, 0, s, wroots.as<uint2>(), did.as<uint8_t>(), nwin, parent,
+                      nonfree.as<uint8_t>());
+            BS_LAUNCH(k_mws_reset_best, grid_for(nwin), 256, 0, s, wroots.as<uint2>(), nwin, bestA.as<uint32_t>());
+            // next window: survivors (order preserved) + refill
+            BS_TRY(scan_exclusive_u8(keep.as<uint8_t>(), pos.as<uint32_t>(), nwin, (uint32_t *)(d_cnt + 6), s));
+            BS_LAUNCH(k_mws_next_window, grid_for(wcap), 256, 0, s, win.as<uint32_t>(), keep.as<uint8_t>(), pos.as<uint32_t>(), nwin,
+                      (const uint32_t *)(d_cnt + 6), cursor, wcap, (uint32_t)E, win2.as<uint32_t>());
+            win.swap(win2);
+            BS_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 128, cudaMemcpyDeviceToHost, s));
+            BS_CUDA(cudaStreamSynchronize(s));
+            const uint32_t nkeep = (uint32_t)h_cnt[6];
+            const uint32_t nfill = std::min<uint32_t>(wcap - nkeep, (uint32_t)E - cursor);
+            BS_ARG(nkeep < nwin || nfill > 0, "bs_mws_agglom: a round executed no edge (internal error)");
+            cursor += nfill;
+            nwin = (size_t)nkeep + nfill;
+            if (h_cnt[5] > 0) unions_since_rebuild = true;
+            if (nwin > 0 && unions_since_rebuild && ((unsigned long long)since_rebuild >= g_mws_epoch || h_cnt[8] > g_mws_probe_budget)) {
+                // rebuild: roots of all voxels become the epoch roots, the lists collapse, the mutex set is re-keyed
+                rebuilds++;
+                since_rebuild = 0;
+                unions_since_rebuild = false;
+                BS_LAUNCH(k_mws_flatten, grid_for(V), 256, 0, s, parent, root.as<uint32_t>(), ehead.as<uint32_t>(),
+                          etail.as<uint32_t>(), enext.as<uint32_t>(), V);
+                BS_CUDA(cudaMemcpyAsync(parent, root.p, 4 * V, cudaMemcpyDeviceToDevice, s));
+                const size_t nm = (size_t)h_cnt[1];
+                if (nm) {
+                    BS_CUDA(cudaMemsetAsync(tab.p, 0xFF, 8 * tcap, s));
+                    BS_CUDA(cudaMemsetAsync(d_cnt + 1, 0, 8, s));
+                    BS_LAUNCH(k_mws_rekey, grid_for(nm), 256, 0, s, mlist.as<uint2>(), nm, root.as<uint32_t>(), tab.as<unsigned long long>(),
+                              tcap - 1, mlist2.as<uint2>(), d_cnt + 1);
+                    mlist.swap(mlist2);
+                }
+            }
+        }
+    }
+    *rounds_out = rounds;
+    *rebuilds_out = rebuilds;
+    return BS_OK;
+}
+
 template <typename T>
 static int mws_run(const T *affs, const uint8_t *mask, MwsGeom &G, int zero_is_repulsive, int remove_debris, uint64_t *labels_out,
-                   uint64_t *seg_out, int64_t *counters_out, cudaStream_t s) {
+                   uint32_t *labels32_out, uint64_t *seg_out, int64_t *counters_out, cudaStream_t s) {
     const size_t V = (size_t)G.Z * G.Y * G.X;
     const unsigned long long E = G.ebase[G.C];
     BS_ARG(V < (1ull << 31), "bs_mws_agglom: volume too large for 31-bit voxel indices");
     BS_ARG(E < (1ull << 32) - 1, "bs_mws_agglom: more than 2^32 edges");
-    DevBuf parent, root, nonfree, keys, keys2, vals, vals2, eu, ev, win, win2, wroots, keep, did, pos, bestA, counts, tab, mlist, mlist2, ehead,
-        etail, enext, pairmark;
+    DevBuf parent, keys, keys2, vals, vals2, eu, ev, counts;
     BS_TRY(parent.alloc(4 * V, s));
     BS_LAUNCH(k_mws_init, grid_for(V), 256, 0, s, parent.as<uint32_t>(), V);
     BS_TRY(counts.alloc_zero(128, s));
@@ -448,97 +568,27 @@ static int mws_run(const T *affs, const uint8_t *mask, MwsGeom &G, int zero_is_r
         vals.release();
         BS_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 128, cudaMemcpyDeviceToHost, s));
         BS_CUDA(cudaStreamSynchronize(s));
-        const unsigned long long nrep = h_cnt[0];
-        // mutex set: at most one entry per executed repulsive edge
-        uint64_t tcap = 1024;
-        while (tcap < 2 * nrep + 16) tcap <<= 1;
-        BS_TRY(tab.alloc_fill(8 * tcap, 0xFF, s));
-        BS_TRY(mlist.alloc(8 * (size_t)(nrep + 1), s));
-        BS_TRY(mlist2.alloc(8 * (size_t)(nrep + 1), s));
-        BS_TRY(bestA.alloc_fill(4 * V, 0xFF, s));
-        BS_TRY(root.alloc(4 * V, s));
-        BS_TRY(ehead.alloc(4 * V, s));
-        BS_TRY(etail.alloc(4 * V, s));
-        BS_TRY(enext.alloc(4 * V, s));
-        BS_TRY(pairmark.alloc_zero(4 * V, s));
-        BS_TRY(nonfree.alloc_zero(V, s));
-        // epoch 0: every voxel is its own cluster
-        BS_LAUNCH(k_mws_flatten, grid_for(V), 256, 0, s, parent.as<uint32_t>(), root.as<uint32_t>(), ehead.as<uint32_t>(), etail.as<uint32_t>(),
-                  enext.as<uint32_t>(), V);
-        BS_LAUNCH(k_mws_mark_repulsive, grid_for(E), 256, 0, s, eu.as<uint32_t>(), ev.as<uint32_t>(), (size_t)E, nonfree.as<uint8_t>());
-        const uint32_t wcap = (uint32_t)std::min<unsigned long long>(E, g_mws_window);
-        BS_TRY(win.alloc(4 * (size_t)wcap, s));
-        BS_TRY(win2.alloc(4 * (size_t)wcap, s));
-        BS_TRY(wroots.alloc(8 * (size_t)wcap, s));
-        BS_TRY(keep.alloc((size_t)wcap, s));
-        BS_TRY(did.alloc((size_t)wcap, s));
-        BS_TRY(pos.alloc(4 * (size_t)wcap, s));
-        // first window: the wcap best edges
-        uint32_t cursor = 0;
-        size_t nwin = 0;
-        BS_CUDA(cudaMemsetAsync(d_cnt + 6, 0, 8, s));
-        BS_LAUNCH(k_mws_next_window, grid_for(wcap), 256, 0, s, win.as<uint32_t>(), keep.as<uint8_t>(), pos.as<uint32_t>(), (size_t)0,
-                  (const uint32_t *)(d_cnt + 6), cursor, wcap, (uint32_t)E, win.as<uint32_t>());
-        nwin = wcap;
-        cursor = wcap;
-        int since_rebuild = 0;
-        bool unions_since_rebuild = false;
-        while (nwin > 0) {
-            rounds++;
-            since_rebuild++;
-            BS_CUDA(cudaMemsetAsync(d_cnt + 5, 0, 8, s));
-            BS_CUDA(cudaMemsetAsync(d_cnt + 8, 0, 8, s));
-            BS_LAUNCH(k_mws_best, grid_for(nwin), 256, 0, s, win.as<uint32_t>(), nwin, eu.as<uint32_t>(), ev.as<uint32_t>(), parent.as<uint32_t>(),
-                      bestA.as<uint32_t>(), keep.as<uint8_t>(), did.as<uint8_t>(), wroots.as<uint2>());
-            BS_LAUNCH(k_mws_repulsive, grid_for(nwin), 256, 0, s, win.as<uint32_t>(), nwin, eu.as<uint32_t>(), ev.as<uint32_t>(),
-                      wroots.as<uint2>(), bestA.as<uint32_t>(), root.as<uint32_t>(), keep.as<uint8_t>(), tab.as<unsigned long long>(), tcap - 1,
-                      mlist.as<uint2>(), d_cnt);
-            BS_LAUNCH(k_mws_attractive, grid_for(nwin), 256, 0, s, win.as<uint32_t>(), nwin, eu.as<uint32_t>(), wroots.as<uint2>(),
-                      parent.as<uint32_t>(), bestA.as<uint32_t>(), nonfree.as<uint8_t>(), ehead.as<uint32_t>(), enext.as<uint32_t>(),
-                      pairmark.as<uint32_t>(), (uint32_t)rounds, keep.as<uint8_t>(), did.as<uint8_t>(), tab.as<unsigned long long>(), tcap - 1,
-                      d_cnt);
-            BS_LAUNCH(k_mws_post_lists, grid_for(nwin), 256, 0, s, wroots.as<uint2>(), did.as<uint8_t>(), nwin, parent.as<uint32_t>(),
-                      nonfree.as<uint8_t>(), pairmark.as<uint32_t>(), (uint32_t)rounds, ehead.as<uint32_t>(), etail.as<uint32_t>(),
-                      enext.as<uint32_t>());
-            BS_LAUNCH(k_mws_post_flags, grid_for(nwin), 256, 0, s, wroots.as<uint2>(), did.as<uint8_t>(), nwin, parent.as<uint32_t>(),
-                      nonfree.as<uint8_t>());
-            BS_LAUNCH(k_mws_reset_best, grid_for(nwin), 256, 0, s, wroots.as<uint2>(), nwin, bestA.as<uint32_t>());
-            // next window: survivors (order preserved) + refill
-            BS_TRY(scan_exclusive_u8(keep.as<uint8_t>(), pos.as<uint32_t>(), nwin, (uint32_t *)(d_cnt + 6), s));
-            BS_LAUNCH(k_mws_next_window, grid_for(wcap), 256, 0, s, win.as<uint32_t>(), keep.as<uint8_t>(), pos.as<uint32_t>(), nwin,
-                      (const uint32_t *)(d_cnt + 6), cursor, wcap, (uint32_t)E, win2.as<uint32_t>());
-            win.swap(win2);
-            BS_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 128, cudaMemcpyDeviceToHost, s));
-            BS_CUDA(cudaStreamSynchronize(s));
-            const uint32_t nkeep = (uint32_t)h_cnt[6];
-            const uint32_t nfill = std::min<uint32_t>(wcap - nkeep, (uint32_t)E - cursor);
-            BS_ARG(nkeep < nwin || nfill > 0, "bs_mws_agglom: a round executed no edge (internal error)");
-            cursor += nfill;
-            nwin = (size_t)nkeep + nfill;
-            if (h_cnt[5] > 0) unions_since_rebuild = true;
-            if (nwin > 0 && unions_since_rebuild && ((unsigned long long)since_rebuild >= g_mws_epoch || h_cnt[8] > g_mws_probe_budget)) {
-                // rebuild: roots of all voxels become the epoch roots, the lists collapse, the mutex set is re-keyed
-                rebuilds++;
-                since_rebuild = 0;
-                unions_since_rebuild = false;
-                BS_LAUNCH(k_mws_flatten, grid_for(V), 256, 0, s, parent.as<uint32_t>(), root.as<uint32_t>(), ehead.as<uint32_t>(),
-                          etail.as<uint32_t>(), enext.as<uint32_t>(), V);
-                BS_CUDA(cudaMemcpyAsync(parent.p, root.p, 4 * V, cudaMemcpyDeviceToDevice, s));
-                const size_t nm = (size_t)h_cnt[1];
-                if (nm) {
-                    BS_CUDA(cudaMemsetAsync(tab.p, 0xFF, 8 * tcap, s));
-                    BS_CUDA(cudaMemsetAsync(d_cnt + 1, 0, 8, s));
-                    BS_LAUNCH(k_mws_rekey, grid_for(nm), 256, 0, s, mlist.as<uint2>(), nm, root.as<uint32_t>(), tab.as<unsigned long long>(),
-                              tcap - 1, mlist2.as<uint2>(), d_cnt + 1);
-                    mlist.swap(mlist2);
-                }
-            }
-        }
+        BS_TRY(mws_rounds(eu.as<uint32_t>(), ev.as<uint32_t>(), E, V, h_cnt[0], parent.as<uint32_t>(), d_cnt, h_cnt, &rounds, &rebuilds, s));
     }
     h_cnt[7] = (unsigned long long)rounds;
     if (getenv("BS_MWS_VERBOSE")) fprintf(stderr, "[bs mws] edges %llu rounds %d rebuilds %d\n", (unsigned long long)E, rounds, rebuilds);
-    BS_LAUNCH(k_mws_labels, grid_for(V), 256, 0, s, parent.as<uint32_t>(), V, labels_out);   // flat: parent == roots
-    if (seg_out) {
+    unsigned long long n_labels = 0;
+    if (labels32_out) {
+        // dense labels 1..n in the order of every cluster's first voxel
+        DevBuf flag, rank, tot;
+        BS_TRY(flag.alloc(V, s));
+        BS_TRY(rank.alloc(4 * V, s));
+        BS_TRY(tot.alloc_zero(16, s));
+        BS_LAUNCH(k_mws_isroot, grid_for(V), 256, 0, s, parent.as<uint32_t>(), V, flag.as<uint8_t>());
+        BS_TRY(scan_exclusive_u8(flag.as<uint8_t>(), rank.as<uint32_t>(), V, tot.as<uint32_t>(), s));
+        BS_LAUNCH(k_mws_dense_labels, grid_for(V), 256, 0, s, parent.as<uint32_t>(), rank.as<uint32_t>(), V, labels32_out);
+        uint32_t h_tot = 0;
+        BS_CUDA(cudaMemcpyAsync(&h_tot, tot.p, 4, cudaMemcpyDeviceToHost, s));
+        BS_CUDA(cudaStreamSynchronize(s));
+        n_labels = h_tot;
+    }
+    if (labels_out) BS_LAUNCH((k_mws_labels<uint64_t>), grid_for(V), 256, 0, s, parent.as<uint32_t>(), V, labels_out);
+    if (seg_out && labels_out) {
         if (remove_debris > 0) {
             DevBuf cnt;
             BS_TRY(cnt.alloc_zero(4 * V, s));
@@ -557,18 +607,22 @@ static int mws_run(const T *affs, const uint8_t *mask, MwsGeom &G, int zero_is_r
         counters_out[2] = (int64_t)h_cnt[3];
         counters_out[3] = (int64_t)h_cnt[4];
         counters_out[4] = (int64_t)h_cnt[7];
+        if (labels32_out) counters_out[5] = (int64_t)n_labels;
     }
     return BS_OK;
 }
 
-int mws_agglom(const void *affs, int aff_dtype, const uint8_t *mask, int C, int Z, int Y, int X, const int32_t *offsets,
-               const int32_t *strides, const double *bias, double noise_eps, unsigned long long noise_seed, int zero_is_repulsive,
-               int remove_debris, uint64_t *labels_out, uint64_t *seg_out, int64_t *counters_out, cudaStream_t s) {
+static int mws_agglom_impl(const void *affs, int aff_dtype, const uint8_t *mask, int C, int nseg, int Z, int Y, int X, const int32_t *offsets,
+                           const int32_t *strides, const double *bias, double noise_eps, unsigned long long noise_seed,
+                           const unsigned long long *seg_seeds_host, int zero_is_repulsive, int remove_debris, uint64_t *labels_out,
+                           uint32_t *labels32_out, uint64_t *seg_out, int64_t *counters_out, cudaStream_t s) {
     BS_ARG(C >= 1 && C <= 32, "bs_mws_agglom: 1..32 affinity channels");
-    BS_ARG(Z > 0 && Y > 0 && X > 0, "bs_mws_agglom: empty volume");
+    BS_ARG(Z > 0 && Y > 0 && X > 0 && nseg >= 1, "bs_mws_agglom: empty volume");
+    BS_ARG((long long)nseg * Z < (1LL << 31), "bs_mws_agglom: volume too large");
     MwsGeom G;
     memset(&G, 0, sizeof(G));
-    G.C = C, G.Z = Z, G.Y = Y, G.X = X;
+    G.C = C, G.Z = nseg * Z, G.Y = Y, G.X = X;
+    G.nseg = nseg, G.seg_z = Z;
     const int dims[3] = {Z, Y, X};
     unsigned long long e = 0;
     for (int c = 0; c < C; c++) {
@@ -586,7 +640,7 @@ int mws_agglom(const void *affs, int aff_dtype, const uint8_t *mask, int C, int 
         G.z0[c] = first[0], G.y0[c] = first[1], G.x0[c] = first[2];
         G.nz[c] = count[0], G.ny[c] = count[1], G.nx[c] = count[2];
         G.ebase[c] = e;
-        e += (unsigned long long)count[0] * count[1] * count[2];
+        e += (unsigned long long)nseg * count[0] * count[1] * count[2];
         if (count[0] == 0 || count[1] == 0 || count[2] == 0) G.nz[c] = 0, G.ny[c] = 1, G.nx[c] = 1;   // empty lattice, no division by zero
         G.bias[c] = bias ? bias[c] : 0.0;
     }
@@ -595,9 +649,129 @@ int mws_agglom(const void *affs, int aff_dtype, const uint8_t *mask, int C, int 
     G.noise_eps = noise_eps;
     G.noise_k = 1.7320508075688772 / 65536.0;    // sqrt(3) / 2^16: unit variance for the sum of four 16-bit uniforms
     G.seed = noise_seed;
+    DevBuf seeds;
+    if (seg_seeds_host && G.has_noise) {
+        BS_TRY(seeds.alloc(8 * (size_t)nseg, s));
+        BS_CUDA(cudaMemcpyAsync(seeds.p, seg_seeds_host, 8 * (size_t)nseg, cudaMemcpyHostToDevice, s));
+        BS_CUDA(cudaStreamSynchronize(s));
+        G.seg_seeds = seeds.as<unsigned long long>();
+    }
     if (aff_dtype == BS_DTYPE_U8)
-        return mws_run<uint8_t>((const uint8_t *)affs, mask, G, zero_is_repulsive, remove_debris, labels_out, seg_out, counters_out, s);
-    return mws_run<float>((const float *)affs, mask, G, zero_is_repulsive, remove_debris, labels_out, seg_out, counters_out, s);
+        return mws_run<uint8_t>((const uint8_t *)affs, mask, G, zero_is_repulsive, remove_debris, labels_out, labels32_out, seg_out,
+                                counters_out, s);
+    return mws_run<float>((const float *)affs, mask, G, zero_is_repulsive, remove_debris, labels_out, labels32_out, seg_out, counters_out, s);
+}
+
+int mws_agglom(const void *affs, int aff_dtype, const uint8_t *mask, int C, int Z, int Y, int X, const int32_t *offsets,
+               const int32_t *strides, const double *bias, double noise_eps, unsigned long long noise_seed, int zero_is_repulsive,
+               int remove_debris, uint64_t *labels_out, uint64_t *seg_out, int64_t *counters_out, cudaStream_t s) {
+    return mws_agglom_impl(affs, aff_dtype, mask, C, 1, Z, Y, X, offsets, strides, bias, noise_eps, noise_seed, nullptr, zero_is_repulsive,
+                           remove_debris, labels_out, nullptr, seg_out, counters_out, s);
+}
+
+// volara ExtractFrags' fragmenter for many blocks at once: n_blocks read ROIs (Z, Y, X) stacked along z, one independent mutex
+// watershed each (edges never leave a block, noise keyed per block).  labels: 1 + smallest raveled index of the cluster in the
+// stacked volume.
+int mws_agglom_blocks(const void *affs, int aff_dtype, const uint8_t *mask, int C, int n_blocks, int Z, int Y, int X, const int32_t *offsets,
+                      const int32_t *strides, const double *bias, double noise_eps, const unsigned long long *block_seeds_host,
+                      int zero_is_repulsive, uint32_t *labels_out, int64_t *counters_out, cudaStream_t s) {
+    return mws_agglom_impl(affs, aff_dtype, mask, C, n_blocks, Z, Y, X, offsets, strides, bias, noise_eps, 0, block_seeds_host,
+                           zero_is_repulsive, 0, nullptr, labels_out, nullptr, counters_out, s);
+}
+
+// ------------------------------------------------------------------ mutex watershed on a graph (volara GraphMWS)
+// nodes ascending ids; edge weight w = weight * score + bias in float64 (NaN scores dropped); visited by descending |w|, equal
+// |w| in input order (the caller passes edges sorted by (u, v): declared tie rule, the upstream order is the database's);
+// w > 0 attractive, w <= 0 repulsive.  out[i] = smallest node id of node i's cluster.
+__global__ void __launch_bounds__(256) k_gmws_keys(const float *__restrict__ scores, size_t m, double weight, double bias,
+                                                   uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < m; e += (size_t)gridDim.x * blockDim.x) {
+        const double w = __dadd_rn(__dmul_rn(weight, (double)scores[e]), bias);
+        keys[e] = w != w ? EMPTY64 : ~(uint64_t)__double_as_longlong(fabs(w));
+        vals[e] = (uint32_t)e;
+    }
+}
+__device__ __forceinline__ uint32_t gmws_rank(const uint64_t *__restrict__ nodes, uint32_t n, uint64_t id) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (nodes[mid] < id)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return (lo < n && nodes[lo] == id) ? lo : NONE32;
+}
+__global__ void __launch_bounds__(256) k_gmws_endpoints(const uint64_t *__restrict__ nodes, uint32_t n, const uint64_t *__restrict__ u,
+                                                        const uint64_t *__restrict__ v, const float *__restrict__ scores, size_t m,
+                                                        double weight, double bias, const uint32_t *__restrict__ vals,
+                                                        uint32_t *__restrict__ eu, uint32_t *__restrict__ ev,
+                                                        unsigned long long *__restrict__ counts) {
+    unsigned long long nrep = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t e = vals[i];
+        const double w = __dadd_rn(__dmul_rn(weight, (double)scores[e]), bias);
+        const uint32_t a = gmws_rank(nodes, n, u[e]), b = gmws_rank(nodes, n, v[e]);
+        if (w != w || a == NONE32 || b == NONE32 || a == b) {
+            eu[i] = NONE32, ev[i] = NONE32;
+        } else {
+            const bool attractive = w > 0.0;
+            eu[i] = a | (attractive ? ATTR_BIT : 0u);
+            ev[i] = b;
+            nrep += attractive ? 0 : 1;
+        }
+    }
+    nrep = __reduce_add_sync(0xFFFFFFFFu, (unsigned)nrep);
+    if ((threadIdx.x & 31) == 0 && nrep) atomicAdd(&counts[0], nrep);
+}
+__global__ void k_gmws_out(const uint32_t *__restrict__ parent, const uint64_t *__restrict__ nodes, size_t n, uint64_t *__restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = nodes[uf_find(parent, (uint32_t)i)];
+}
+
+int graph_mws(const uint64_t *nodes, int64_t n, const uint64_t *u, const uint64_t *v, const float *scores, int64_t m, double weight,
+              double bias, uint64_t *out, int64_t *counters_out, cudaStream_t s) {
+    BS_ARG(n >= 0 && n < (1LL << 31) && m >= 0 && m < (1LL << 32) - 1, "bs_graph_mws: graph too large");
+    if (n == 0) return BS_OK;
+    DevBuf parent, keys, keys2, vals, vals2, eu, ev, counts;
+    BS_TRY(parent.alloc(4 * (size_t)n, s));
+    BS_LAUNCH(k_mws_init, grid_for((size_t)n), 256, 0, s, parent.as<uint32_t>(), (size_t)n);
+    BS_TRY(counts.alloc_zero(128, s));
+    unsigned long long *d_cnt = counts.as<unsigned long long>();
+    unsigned long long h_cnt[16];
+    memset(h_cnt, 0, sizeof(h_cnt));
+    int rounds = 0, rebuilds = 0;
+    if (m) {
+        BS_TRY(keys.alloc(8 * (size_t)m, s));
+        BS_TRY(keys2.alloc(8 * (size_t)m, s));
+        BS_TRY(vals.alloc(4 * (size_t)m, s));
+        BS_TRY(vals2.alloc(4 * (size_t)m, s));
+        BS_LAUNCH(k_gmws_keys, grid_for((size_t)m), 256, 0, s, scores, (size_t)m, weight, bias, keys.as<uint64_t>(), vals.as<uint32_t>());
+        BS_TRY(radix_sort_pairs(keys.as<uint64_t>(), vals.as<uint32_t>(), keys2.as<uint64_t>(), vals2.as<uint32_t>(), (size_t)m, 0, 64, s));
+        keys.release();
+        keys2.release();
+        vals2.release();
+        BS_TRY(eu.alloc(4 * (size_t)m, s));
+        BS_TRY(ev.alloc(4 * (size_t)m, s));
+        BS_LAUNCH(k_gmws_endpoints, grid_for((size_t)m), 256, 0, s, nodes, (uint32_t)n, u, v, scores, (size_t)m, weight, bias, vals.as<uint32_t>(),
+                  eu.as<uint32_t>(), ev.as<uint32_t>(), d_cnt);
+        vals.release();
+        BS_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 128, cudaMemcpyDeviceToHost, s));
+        BS_CUDA(cudaStreamSynchronize(s));
+        BS_TRY(mws_rounds(eu.as<uint32_t>(), ev.as<uint32_t>(), (unsigned long long)m, (size_t)n, h_cnt[0], parent.as<uint32_t>(), d_cnt, h_cnt,
+                          &rounds, &rebuilds, s));
+    }
+    BS_LAUNCH(k_gmws_out, grid_for((size_t)n), 256, 0, s, parent.as<uint32_t>(), nodes, (size_t)n, out);
+    BS_CUDA(cudaStreamSynchronize(s));
+    BS_CUDA(cudaGetLastError());
+    if (counters_out) {
+        counters_out[0] = m;
+        counters_out[1] = (int64_t)h_cnt[2];
+        counters_out[2] = (int64_t)h_cnt[3];
+        counters_out[3] = (int64_t)h_cnt[4];
+        counters_out[4] = rounds;
+    }
+    return BS_OK;
 }
 
 }  // namespace bs

@@ -17,6 +17,7 @@ class SQLiteRag:
     def __init__(self, path, edge_attrs=None):
         self.path = path
         self.edge_attrs = edge_attrs or {"merge_score": "float"}
+        self.attr = list(self.edge_attrs)[0]      # one float attribute per edge: merge_score (ws), zyx_aff (mws)
 
     @property
     def id(self):
@@ -30,7 +31,7 @@ class SQLiteRag:
         with self._con() as con:
             con.execute("CREATE TABLE IF NOT EXISTS nodes (id INTEGER PRIMARY KEY, position_0 INTEGER, "
                         "position_1 INTEGER, position_2 INTEGER, size INTEGER)")
-            con.execute("CREATE TABLE IF NOT EXISTS edges (u INTEGER, v INTEGER, merge_score REAL, PRIMARY KEY (u, v))")
+            con.execute(f"CREATE TABLE IF NOT EXISTS edges (u INTEGER, v INTEGER, {self.attr} REAL, PRIMARY KEY (u, v))")
 
     def drop(self):
         if os.path.exists(self.path):
@@ -59,23 +60,23 @@ class SQLiteRag:
         with self._con() as con:
             if roi is None:
                 nodes = np.array([r[0] for r in con.execute("SELECT id FROM nodes ORDER BY id")], dtype=np.int64)
-                rows = list(con.execute("SELECT u, v, merge_score FROM edges"))
+                rows = list(con.execute(f"SELECT u, v, {self.attr} FROM edges"))
             else:
                 lo = [int(v) for v in roi[0]]
                 hi = [int(o) + int(n) for o, n in zip(roi[0], roi[1])]
                 cond = " AND ".join(f"position_{d} >= ? AND position_{d} < ?" for d in range(3))
                 args = [v for d in range(3) for v in (lo[d], hi[d])]
                 nodes = np.array([r[0] for r in con.execute(f"SELECT id FROM nodes WHERE {cond} ORDER BY id", args)], dtype=np.int64)
-                rows = list(con.execute(f"SELECT u, v, merge_score FROM edges WHERE u IN (SELECT id FROM nodes WHERE {cond})", args))
+                rows = list(con.execute(f"SELECT u, v, {self.attr} FROM edges WHERE u IN (SELECT id FROM nodes WHERE {cond})", args))
         edges = np.array([(r[0], r[1]) for r in rows], dtype=np.int64).reshape(-1, 2)
         scores = np.array([np.nan if r[2] is None else r[2] for r in rows], dtype=np.float32)
         return nodes.view(np.uint64), edges.view(np.uint64), scores
 
 
-def open_db(db_config):
-    """post/watershed.py:104-113"""
+def open_db(db_config, edge_attrs=None):
+    """post/watershed.py:104-113 (edge_attrs merge_score), post/watershed_mutex.py:108-117 (edge_attrs zyx_aff)"""
     if "db_file" in db_config:
-        return SQLiteRag(db_config["db_file"], edge_attrs={"merge_score": "float"})
+        return SQLiteRag(db_config["db_file"], edge_attrs=edge_attrs or {"merge_score": "float"})
     raise NotImplementedError("PostgreSQL RAG stores are not available in this environment; use db_file (SQLite)")
 
 

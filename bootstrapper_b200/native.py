@@ -54,7 +54,7 @@ EXPORTS = [
     "bs_last_error", "bs_launch_count", "bs_version", "bs_config_size", "bs_plan_create", "bs_plan_destroy", "bs_plan_num_blocks",
     "bs_plan_block_info", "bs_plan_set_owned", "bs_stage1_fragments", "bs_stage1_num_nodes", "bs_stage1_get_nodes",
     "bs_stage1_block_counts", "bs_stage1_set_block_counts", "bs_plan_node_ids", "bs_stage2_agglomerate", "bs_stage2_agglomerate_until", "bs_stage1_from_labels", "bs_stage2_num_edges",
-    "bs_stage2_get_edges", "bs_waterz_segment", "bs_waterz_segment_quantile", "bs_cc_affs", "bs_mws_agglom", "bs_aff_errors", "bs_label_stats", "bs_shift_affinities", "bs_connected_components", "bs_stage3_components", "bs_relabel", "bs_stage3_relabel", "bs_stage3_dense_fragments", "bs_expand_compact", "bs_watershed_from_affinities",
+    "bs_stage2_get_edges", "bs_waterz_segment", "bs_waterz_segment_quantile", "bs_cc_affs", "bs_mws_agglom", "bs_mws_agglom_blocks", "bs_aff_agglom", "bs_graph_mws", "bs_aff_errors", "bs_label_stats", "bs_shift_affinities", "bs_connected_components", "bs_stage3_components", "bs_relabel", "bs_stage3_relabel", "bs_stage3_dense_fragments", "bs_expand_compact", "bs_watershed_from_affinities",
     "bs_synth_affs", "bs_debug_fetch", "bs_set_debug", "bs_set_profiling", "bs_get_profile",
     "bs_release_scratch", "bs_set_flood_version", "bs_set_front_version", "bs_set_agglom_version", "bs_dbg_scan_u32", "bs_dbg_scan_u8", "bs_dbg_sort_pairs",
 ]
@@ -294,6 +294,15 @@ class Plan:
     def agglomerate(self, affs, frags):
         _check(lib().bs_stage2_agglomerate(self._h, _dev(affs), _dev(frags, torch.int64), _stream()))
 
+    def aff_agglom(self, affs, frags, offsets):
+        """volara AffAgglom(scores={"zyx_aff": neighborhood}) for the owned blocks (bs_aff_agglom): mean affinity over all
+        offsets between every pair of fragments that touch through one; results through edges()"""
+        off = np.ascontiguousarray(np.asarray(offsets, dtype=np.int32).reshape(-1, 3))
+        if off.shape[0] != affs.shape[0]:
+            raise BsError("Number of offsets must match number of affinities channels")
+        _check(lib().bs_aff_agglom(self._h, _dev(affs), _dev(frags, torch.int64), C.c_int(int(affs.shape[0])), off.ctypes.data_as(C.c_void_p),
+                                   _stream()))
+
     def agglomerate_until(self, affs, frags, threshold):
         """waterz mergeUntil(threshold) instead of the blockwise 1.0 (epsilon_agglomerate, watershed_frags.py:158-176): the
         edges of merged pairs carry their merge score, all others NaN"""
@@ -460,6 +469,58 @@ def mws_agglom(affs, offsets, bias, strides=None, mask=None, noise_eps=None, noi
                                b.ctypes.data_as(C.c_void_p), C.c_double(float(noise_eps or 0.0)), C.c_ulonglong(int(noise_seed)),
                                C.c_int(int(remove_debris or 0)), _dev(frags), _dev(seg), cnt, _stream()))
     return frags, seg, dict(edges=cnt[0], merges=cnt[1], mutexes=cnt[2], blocked=cnt[3], rounds=cnt[4])
+
+
+def _mws_arrays(Cn, offsets, bias, strides):
+    off = np.ascontiguousarray(np.asarray(offsets, dtype=np.int32).reshape(-1, 3))
+    if off.shape[0] != Cn:
+        raise BsError("Number of offsets must match number of affinities channels")
+    b = np.ascontiguousarray(np.asarray(bias, dtype=np.float64).reshape(-1))
+    if b.shape[0] != Cn:
+        raise BsError("Number of biases must match number of affinities channels")
+    st = None
+    if strides is not None:
+        st = np.ascontiguousarray(np.asarray(strides, dtype=np.int32).reshape(-1, 3))
+        if st.shape[0] != Cn:
+            raise BsError("Number of strides must match number of affinities channels")
+    return off, b, st
+
+
+def mws_agglom_blocks(affs, n_blocks, offsets, bias, strides=None, noise_eps=None, block_seeds=None):
+    """volara ExtractFrags' fragmenter for n_blocks read ROIs stacked along z in one device array (C, n_blocks * Z, Y, X)
+    (bs_mws_agglom_blocks): one independent mutex watershed per block.  Returns (int32 labels (n_blocks * Z, Y, X): clusters
+    numbered 1..n in the order of their first voxel in the stack, counters incl. n_labels)."""
+    Cn, ZZ, Y, X = affs.shape
+    if ZZ % n_blocks:
+        raise BsError("stacked depth is not a multiple of the block count")
+    off, b, st = _mws_arrays(Cn, offsets, bias, strides)
+    seeds = None
+    if noise_eps:
+        seeds = np.ascontiguousarray(np.asarray(block_seeds, dtype=np.uint64).reshape(-1))
+        if seeds.shape[0] != n_blocks:
+            raise BsError("one noise seed per block is needed")
+    labels = torch.empty((ZZ, Y, X), dtype=torch.int32, device=affs.device)
+    cnt = (C.c_int64 * 6)()
+    _check(lib().bs_mws_agglom_blocks(_dev(affs), C.c_int(_aff_dtype(affs)), None, C.c_int(Cn), C.c_int(int(n_blocks)), C.c_int(ZZ // n_blocks),
+                                      C.c_int(Y), C.c_int(X), off.ctypes.data_as(C.c_void_p),
+                                      st.ctypes.data_as(C.c_void_p) if st is not None else None, b.ctypes.data_as(C.c_void_p),
+                                      C.c_double(float(noise_eps or 0.0)), seeds.ctypes.data_as(C.c_void_p) if seeds is not None else None,
+                                      _dev(labels, torch.int32), cnt, _stream()))
+    return labels, dict(edges=cnt[0], merges=cnt[1], mutexes=cnt[2], blocked=cnt[3], rounds=cnt[4], n_labels=cnt[5])
+
+
+def graph_mws(nodes, edges_u, edges_v, scores, weight=1.0, bias=-0.5):
+    """volara GraphMWS on the device (bs_graph_mws): mutex watershed over the fragment graph with w = weight * score + bias;
+    edges must come sorted by (u, v) (the declared order of equal |w|).  Returns (clusters: smallest node id of every node's
+    cluster, counters)."""
+    out = torch.empty_like(nodes)
+    cnt = (C.c_int64 * 5)()
+    m = edges_u.numel()
+    _check(lib().bs_graph_mws(_dev(nodes, torch.int64) if nodes.numel() else None, C.c_int64(nodes.numel()),
+                              _dev(edges_u, torch.int64) if m else None, _dev(edges_v, torch.int64) if m else None,
+                              _dev(scores, torch.float32) if m else None, C.c_int64(m), C.c_double(float(weight)), C.c_double(float(bias)),
+                              _dev(out, torch.int64) if nodes.numel() else None, cnt, _stream()))
+    return out, dict(edges=cnt[0], merges=cnt[1], mutexes=cnt[2], blocked=cnt[3], rounds=cnt[4])
 
 
 def label_stats(seg, capacity=1 << 20):

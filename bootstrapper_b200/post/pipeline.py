@@ -180,6 +180,109 @@ def epsilon_fragments(plan, affs, p, frags_out, mask=None):
     return nid[order], torch.cat([n[1] for n in nodes_all])[order], torch.cat([n[2] for n in nodes_all])[order]
 
 
+def _stack_read_rois(plan, affs, mask, members, rs, wo, ctx):
+    """the read ROIs of the blocks `members` (all of read shape rs) stacked along z: zero fill outside the array, mask applied
+    (affs_data *= mask_data) -- the arrays the reference's per-block task body sees"""
+    dev = affs.device
+    vol = tuple(affs.shape[1:])
+    rz, ry, rx = rs
+    fake = torch.zeros((affs.shape[0], len(members) * rz, ry, rx), dtype=affs.dtype, device=dev)
+    for k, bi in enumerate(members):
+        ro = [int(wo[bi][d]) - ctx[d] for d in range(3)]
+        lo = [max(ro[d], 0) for d in range(3)]
+        hi = [min(ro[d] + rs[d], vol[d]) for d in range(3)]
+        if any(h <= l for l, h in zip(lo, hi)):
+            continue
+        src = (slice(None),) + tuple(slice(l, h) for l, h in zip(lo, hi))
+        dz, dy, dx = (lo[d] - ro[d] for d in range(3))
+        piece = affs[src]
+        if mask is not None:
+            piece = piece * (mask[src[1:]] > 0).to(piece.dtype)
+        fake[:, k * rz + dz:k * rz + dz + (hi[0] - lo[0]), dy:dy + (hi[1] - lo[1]), dx:dx + (hi[2] - lo[2])] = piece
+    return fake
+
+
+MWS_DEFAULTS = dict(aff_neighborhood=None, bias=None, global_bias=[1.0, -0.5], filter_fragments=None, sigma=None, noise_eps=None,
+                    strides=None, randomized_strides=False, remove_debris=0, min_seed_distance=None, noise_seed=0)
+
+
+def segment_mws_blockwise(affs, params, block_size=None, context=None, mask=None, roi=None, block_index_offset=None):
+    """In-memory core of the blockwise mws pipeline (post/watershed_mutex.py:8-174: ExtractFrags -> AffAgglom -> GraphMWS ->
+    Relabel, the four volara tasks) on a CUDA tensor (C, Z, Y, X) uint8 / float32.
+      ExtractFrags: per block, mutex-watershed fragments of the read ROI from all C channels (bs_mws_agglom_blocks: every
+                    block of one read shape in one call), then filter_fragments / remove_debris / crop / label / id bump /
+                    nodes exactly as WatershedFrags' back half (bs_stage1_from_labels);
+      AffAgglom:    mean affinity over all offsets between touching fragments (bs_aff_agglom);
+      GraphMWS:     global mutex watershed on the fragment graph, w = weight * zyx_aff + bias (bs_graph_mws);
+      Relabel:      bs_stage3_relabel.
+    Returns dict(fragments, nodes, edges (u, v, zyx_aff), lut (nodes, clusters), seg)."""
+    if not affs.is_cuda:
+        raise native.BsError("segment_mws_blockwise needs the affinities on a CUDA device (no CPU fallback)")
+    from ..synth import block_seed
+    p = dict(MWS_DEFAULTS)
+    p.update(params or {})
+    nbh, bias = p["aff_neighborhood"], p["bias"]
+    if nbh is None:
+        raise ValueError("Affinities neighborhood must be provided")
+    if bias is None:
+        raise ValueError("Affinities bias must be provided")
+    assert len(nbh) == len(bias), "Number of biases must match number of affinities channels"
+    assert len(nbh) == affs.shape[0], "Number of offsets must match number of affinities channels"
+    if p["sigma"] is not None:
+        raise NotImplementedError("mws parameter 'sigma' is not implemented in the CUDA path")
+    if p["randomized_strides"]:
+        raise NotImplementedError("randomized_strides=True draws an unseeded random subset of the stride lattice in mwatershed: "
+                                  "not reproducible, not implemented; set randomized_strides = false")
+    dev = affs.device
+    affs = affs.contiguous()
+    vol = tuple(affs.shape[1:])
+    if block_size is None:
+        block_size, context = vol, (0, 0, 0)
+    elif context is None:
+        context = default_context(block_size)
+    roi_offset, roi_shape = roi if roi is not None else ((0, 0, 0), vol)
+    plan = native.Plan(vol, block_size, context, native._aff_dtype(affs), roi_offset=roi_offset, roi_shape=roi_shape,
+                       block_index_offset=block_index_offset, n_channels=affs.shape[0], fragments_in_xy=False,
+                       filter_fragments=float(p["filter_fragments"] or 0.0), remove_debris=int(p["remove_debris"] or 0))
+    ids, wo, ws = plan.block_info()
+    ctx = [int(plan.cfg.context[d]) for d in range(3)]
+    groups = {}
+    for i in range(len(ids)):
+        groups.setdefault(tuple(int(ws[i][d]) + 2 * ctx[d] for d in range(3)), []).append(i)
+    frags = torch.zeros(plan.roi_shape, dtype=torch.int64, device=dev)
+    counts = np.zeros(len(ids), np.int64)
+    nodes_all, mws_counters = [], []
+    for rs, members in sorted(groups.items()):
+        fake = _stack_read_rois(plan, affs, mask, members, rs, wo, ctx)
+        seeds = [block_seed(p["noise_seed"], int(ids[bi])) for bi in members] if p["noise_eps"] else None
+        labels, cnt = native.mws_agglom_blocks(fake, len(members), nbh, bias, strides=p["strides"], noise_eps=p["noise_eps"], block_seeds=seeds)
+        del fake
+        mws_counters.append(cnt)
+        plan.set_owned(members)
+        plan.fragments_from_labels(affs, labels, cnt["n_labels"], frags, mask=mask)
+        del labels
+        c = plan.block_counts()
+        counts[members] = c[members]
+        if plan.num_nodes():
+            nodes_all.append(plan.nodes(dev))
+    plan.set_owned(np.arange(len(ids)))
+    plan.set_block_counts(counts)
+    if nodes_all:
+        nid = torch.cat([n[0] for n in nodes_all])
+        order = torch.argsort(nid)
+        nodes = (nid[order], torch.cat([n[1] for n in nodes_all])[order], torch.cat([n[2] for n in nodes_all])[order])
+    else:
+        nodes = (torch.zeros(0, dtype=torch.int64, device=dev), torch.zeros((0, 3), dtype=torch.int32, device=dev),
+                 torch.zeros(0, dtype=torch.int32, device=dev))
+    plan.aff_agglom(affs, frags, nbh)
+    eu, ev, es = plan.edges(dev)
+    weight, gbias = (float(v) for v in tuple(p["global_bias"]))
+    clusters, gcnt = native.graph_mws(nodes[0], eu, ev, es, weight, gbias)
+    seg = plan.relabel(frags, [clusters])[0] if nodes[0].numel() else torch.zeros_like(frags)
+    return dict(fragments=frags, nodes=nodes, edges=(eu, ev, es), lut=(nodes[0], clusters), seg=seg, plan=plan, params=p,
+                counters=dict(extract_frags=mws_counters, graph_mws=gcnt))
+
+
 def segment_blockwise(affs, params=None, block_size=None, context=None, roi=None, mask=None, plan=None,
                       out=None):
     """affs: CUDA tensor (C, Z, Y, X) uint8 or float32.  Returns a dict of CUDA tensors:

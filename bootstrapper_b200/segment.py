@@ -3,7 +3,7 @@
 Same key set, defaults, override order and error behaviour as the reference's
 bootstrapper/segment.py (DEFAULTS :10-62, get_seg_config :95-135, run_segmentation :138-163);
 pinned by tests/golden/seg_config.json, which was produced by executing the reference file.
-The ws, cc and (non-blockwise) mws methods run on the CUDA path; blockwise mws raises.
+The ws, cc and mws methods (single shot and blockwise) run on the CUDA path.
 """
 import ast
 import copy

@@ -38,6 +38,11 @@ def _hash(seed, *words):
     return x
 
 
+def block_seed(seed, block_id):
+    """noise seed of one block of a blockwise task: SplitMix64 chain over (seed, block id, 29)"""
+    return int(_hash(seed, np.int64(block_id), np.int64(29)))
+
+
 def _uniform(h):
     return (h >> np.uint64(11)).astype(np.float64) * (2.0 ** -53)
 

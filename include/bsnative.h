@@ -233,6 +233,32 @@ int bs_mws_agglom(const void *affs, int aff_dtype, const uint8_t *mask, int n_ch
                   const int32_t *strides, const double *bias, double noise_eps, unsigned long long noise_seed, int remove_debris,
                   uint64_t *frags_out, uint64_t *seg_out, int64_t *counters_out, void *stream);
 
+/* ---- `bs segment --mws -b`: the blockwise mutex-watershed pipeline --------------------------------
+ * replaces the arithmetic of the volara tasks post/watershed_mutex.py:8-174 runs (ExtractFrags :123-141, AffAgglom :144-154,
+ * GraphMWS :156-162; volara is third-party and not in the reference tree: restated, parity unpinned).
+ *
+ * bs_mws_agglom_blocks -- ExtractFrags' fragmenter for many blocks in one call: affs (C, n_blocks * Z, Y, X) holds the read
+ *   ROIs (Z, Y, X) of n_blocks blocks stacked along z (zero fill / mask already applied by the caller as the task does); one
+ *   independent mutex watershed per block exactly as bs_mws_agglom computes it (edges never leave a block; noise, if any,
+ *   from block_seeds[block] -- host uint64 [n_blocks]).  labels_out (n_blocks * Z, Y, X) uint32: clusters numbered 1..n in the
+ *   order of their first voxel in the stacked volume; counters_out host[6]: edges, merges, mutex edges, blocked, rounds, n.
+ *   The rest of the task (filter, crop, relabel, id bump, nodes) is bs_stage1_from_labels.
+ * bs_aff_agglom -- AffAgglom(scores={"zyx_aff": neighborhood}) for the plan's owned blocks: per block, fragments and
+ *   affinities of its read ROI (zero fill outside); for every offset c and voxel p with p + offset_c inside the read ROI a pair
+ *   of different non-zero fragments adds affs[c][p] to the edge (min id, max id); edge attribute = mean over all contributions
+ *   (exact integer sums, one rounding); an edge is written by the block that owns its smaller endpoint.  Results: the plan's
+ *   edge arrays (bs_stage2_num_edges / bs_stage2_get_edges), sorted by (u, v).
+ * bs_graph_mws -- GraphMWS(weights={"zyx_aff": (weight, bias)}): mutex watershed on the fragment graph; w = weight * score +
+ *   bias in float64 (NaN scores skipped), edges by descending |w| (equal |w|: input order -- pass edges sorted by (u, v)),
+ *   w > 0 attractive else repulsive.  nodes ascending; clusters_out[i] = smallest node id of node i's cluster (the LUT row).
+ *   counters_out host[5] or NULL: edges, merges, mutex edges, blocked, rounds. */
+int bs_mws_agglom_blocks(const void *affs, int aff_dtype, const uint8_t *mask, int n_channels, int n_blocks, int Z, int Y, int X,
+                         const int32_t *offsets, const int32_t *strides, const double *bias, double noise_eps, const uint64_t *block_seeds,
+                         uint32_t *labels_out, int64_t *counters_out, void *stream);
+int bs_aff_agglom(bs_plan *p, const void *affs, const uint64_t *frags, int n_channels, const int32_t *offsets, void *stream);
+int bs_graph_mws(const uint64_t *nodes, int64_t n, const uint64_t *edges_u, const uint64_t *edges_v, const float *scores, int64_t m,
+                 double weight, double bias, uint64_t *clusters_out, int64_t *counters_out, void *stream);
+
 /* ---- per-label statistics (`bs refine`) --------------------------------------
  * replaces: the tile scans of refine.py -- `_global_sizes` (:98-108, fastremap.unique + bincount) and the z-extent loop
  * of `z_filter` (:236-255): voxel count, first and last z plane of every non-zero id of a label volume, ids ascending

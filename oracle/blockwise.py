@@ -192,8 +192,9 @@ class Rag:
 
 
 def watershed_in_block(block, affs, frags_out, rag, p, roi_offset, block_size, mask=None,
-                       seed_tie="heap", stats_mode="faithful"):
-    """watershed_frags.py:196-246.  frags_out is the task-ROI-sized uint64 array."""
+                       seed_tie="heap", stats_mode="faithful", fragmenter=None):
+    """watershed_frags.py:196-246.  frags_out is the task-ROI-sized uint64 array.
+    fragmenter(affs_data, block) replaces get_fragments (volara ExtractFrags shares this skeleton, oracle/mws.py)."""
     affs_data = to_ndarray(affs, block.read_offset, block.read_shape, 0)
     if affs.dtype == np.uint8:
         max_affinity_value = 255.0
@@ -210,7 +211,10 @@ def watershed_in_block(block, affs, frags_out, rag, p, roi_offset, block_size, m
         if np.max(mask_data) == 255:
             mask_data = (mask_data > 0).astype(np.uint8)
         affs_data *= mask_data
-    fragments_data = get_fragments(affs_data, p, seed_tie, stats_mode, block.block_id)
+    if fragmenter is not None:
+        fragments_data = fragmenter(affs_data, block)
+    else:
+        fragments_data = get_fragments(affs_data, p, seed_tie, stats_mode, block.block_id)
     # crop to the write roi
     c0 = [w - r for w, r in zip(block.write_offset, block.read_offset)]
     sl = tuple(slice(c, c + s) for c, s in zip(c0, block.write_shape))
