@@ -1683,8 +1683,13 @@ __global__ void __launch_bounds__(256) k_fragstats(const Tile *__restrict__ tile
                 else
                     outside = 1;
                 if (need_stats) {
-                    size_t gi = ((size_t)(t.gz + z - A.z0) * A.Y + (t.gy + y)) * A.X + (t.gx + x);
-                    val = AffOps<T>::value(a, nvol, gi);
+                    // a watershed fragment lies inside the mask, hence inside the volume; given labels (bs_stage1_from_labels:
+                    // mutex-watershed fragments) also cover the zero-filled margin and masked-out voxels, whose affinity is 0
+                    const int gz = t.gz + z, gy = t.gy + y, gx = t.gx + x;
+                    if (gz >= A.z0 && gz < A.z0 + A.Zw && gy >= 0 && gy < A.Y && gx >= 0 && gx < A.X) {
+                        size_t gi = ((size_t)(gz - A.z0) * A.Y + gy) * A.X + gx;
+                        if (!A.mask || A.mask[gi] > 0) val = AffOps<T>::value(a, nvol, gi);
+                    }
                 }
             }
         }

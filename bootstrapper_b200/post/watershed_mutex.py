@@ -14,20 +14,11 @@ from .mws import mwatershed_from_affinities
 from .naming import build_name, dump_params
 
 
-def volara_pipeline(config):
-    """post/watershed_mutex.py:8-174"""
+def volara_plan(config, affs_shape, affs_chunk_shape, affs_roi):
+    """the orchestration of post/watershed_mutex.py:22-173 without the arrays: parameter defaults, block size / context rule,
+    the arguments of the four volara tasks and the dataset / LUT names (pinned against the reference function by
+    tests/golden/volara_pipeline_glue.json)"""
     from pathlib import Path
-
-    from ..graphdb import LUT, open_db
-    from .naming import dump_lut_params
-    from .pipeline import segment_mws_blockwise
-
-    affs_dataset = config["affs_dataset"]
-    fragments_dataset_prefix = config["fragments_dataset"]
-    db_config = config["db"]
-    mask_dataset = config.get("mask_dataset")
-    lut_dir = config["lut_dir"]
-    seg_dataset_prefix = config["seg_dataset_prefix"]
     neighborhood, bias = config.get("aff_neighborhood"), config.get("bias")
     global_bias = tuple(config.get("global_bias", [1.0, -0.5]))
     filter_fragments, sigma, noise_eps = config.get("filter_fragments"), config.get("sigma"), config.get("noise_eps")
@@ -35,28 +26,53 @@ def volara_pipeline(config):
     remove_debris, min_seed_distance = config.get("remove_debris", 0), config.get("min_seed_distance")
     roi_offset, roi_shape = config.get("roi_offset"), config.get("roi_shape")
     blockwise = config.get("blockwise", False)
+    num_workers = config.get("num_workers", 1) if blockwise else 1
     block_shape, context = config.get("block_shape"), config.get("context")
     if neighborhood is None:
         raise ValueError("Affinities neighborhood must be provided")
     if bias is None:
         raise ValueError("Affinities bias must be provided")
     assert len(neighborhood) == len(bias), "Number of biases must match number of affinities channels"
-
-    affs = open_ds(affs_dataset)
-    vs = affs.voxel_size
-    offset, shape = (tuple(roi_offset), tuple(roi_shape)) if roi_offset is not None else affs.roi
+    roi = (tuple(roi_offset), tuple(roi_shape)) if roi_offset is not None else (tuple(affs_roi[0]), tuple(affs_roi[1]))
     if blockwise:
-        block_size = tuple(block_shape) if block_shape else tuple(affs.chunk_shape[1:])
+        block_size = tuple(block_shape) if block_shape else tuple(affs_chunk_shape[1:])
         ctx = tuple(context) if context else tuple(max(1, s // 8) for s in block_size)
     else:
-        block_size, ctx = tuple(affs.shape[1:]), (0, 0, 0)
-
+        block_size, ctx = tuple(affs_shape[1:]), (0,) * len(affs_roi[0])
     frag_params = {"min_seed_distance": min_seed_distance, "sigma": sigma, "noise_eps": noise_eps, "bias": bias, "strides": strides,
                    "randomized_strides": randomized_strides, "filter_fragments": filter_fragments, "remove_debris": remove_debris}
     seg_params = {"global_bias": list(global_bias), **frag_params}
-    frags_ds_name = str(Path(fragments_dataset_prefix) / build_name(frag_params))
-    lut_name = str(Path(lut_dir) / build_name(seg_params))
-    seg_name = str(Path(seg_dataset_prefix) / build_name(seg_params))
+    return dict(
+        blockwise=blockwise, num_workers=num_workers, block_size=block_size, context=ctx, roi=roi, frag_params=frag_params, seg_params=seg_params,
+        frags_ds_name=str(Path(config["fragments_dataset"]) / build_name(frag_params)),
+        lut_name=str(Path(config["lut_dir"]) / build_name(seg_params)),
+        seg_name=str(Path(config["seg_dataset_prefix"]) / build_name(seg_params)),
+        extract_frags=dict(bias=bias, sigma=sigma, noise_eps=noise_eps, filter_fragments=filter_fragments, remove_debris=remove_debris,
+                           strides=strides, randomized_strides=randomized_strides, min_seed_distance=min_seed_distance),
+        scores={"zyx_aff": neighborhood}, weights={"zyx_aff": global_bias}, edge_attrs={"zyx_aff": "float"})
+
+
+def volara_pipeline(config):
+    """post/watershed_mutex.py:8-174"""
+    from ..graphdb import LUT, open_db
+    from .naming import dump_lut_params
+    from .pipeline import segment_mws_blockwise
+
+    affs_dataset = config["affs_dataset"]
+    db_config = config["db"]
+    mask_dataset = config.get("mask_dataset")
+    lut_dir = config["lut_dir"]
+    affs = open_ds(affs_dataset)
+    vs = affs.voxel_size
+    pl = volara_plan(config, affs.shape, affs.chunk_shape, affs.roi)
+    blockwise, block_size, ctx = pl["blockwise"], pl["block_size"], pl["context"]
+    offset, shape = pl["roi"]
+    frag_params, seg_params = pl["frag_params"], pl["seg_params"]
+    frags_ds_name, lut_name, seg_name = pl["frags_ds_name"], pl["lut_name"], pl["seg_name"]
+    neighborhood, bias, global_bias = config.get("aff_neighborhood"), config.get("bias"), pl["weights"]["zyx_aff"]
+    ef = pl["extract_frags"]
+    filter_fragments, sigma, noise_eps, strides = ef["filter_fragments"], ef["sigma"], ef["noise_eps"], ef["strides"]
+    randomized_strides, remove_debris = ef["randomized_strides"], ef["remove_debris"]
 
     affs_t = torch.from_numpy(np.ascontiguousarray(affs.read())).cuda()
     if affs_t.dtype not in (torch.uint8, torch.float32):
@@ -82,7 +98,7 @@ def volara_pipeline(config):
     out.write(r["fragments"].cpu().numpy().view(np.uint64))
     dump_params(frags_ds_name, {"method": "mws", "blockwise": blockwise, **frag_params})
 
-    db = open_db(db_config, edge_attrs={"zyx_aff": "float"})
+    db = open_db(db_config, edge_attrs=pl["edge_attrs"])
     db.drop()
     db.init()
     nid, npos, nsz = [t.cpu().numpy() for t in r["nodes"]]

@@ -752,6 +752,96 @@ def golden_waterz_pipeline_glue():
     print("waterz_pipeline_glue.npz", len(out), meta["frags_name"], meta["names"])
 
 
+def golden_volara_pipeline_glue():
+    """post/watershed_mutex.py `volara_pipeline` (:8-174), the function executed as it stands in the reference file (extracted
+    by ast) with the reference's own naming.py; the volara tasks / datasets / LUT / DB are stand-ins that record their
+    arguments.  Pins the orchestration of the blockwise mws pipeline: parameter defaults, block size and the `// 8` context
+    rule, the arguments every task receives (ExtractFrags, AffAgglom scores, GraphMWS weights, Relabel) and the dataset / LUT
+    names."""
+    import ast
+    sys.modules.setdefault("zarr", types.ModuleType("zarr"))
+    tasks = []
+
+    class Coordinate(tuple):
+        def __new__(cls, v):
+            return super().__new__(cls, (int(x) for x in v))
+
+    class Roi:
+        def __init__(self, offset, shape):
+            self.offset, self.shape, self.dims = Coordinate(offset), Coordinate(shape), len(shape)
+
+    class DS:
+        shape, chunk_shape = (6, 20, 96, 80), (6, 5, 48, 40)
+        roi = Roi((0, 0, 0), (20, 96, 80))
+
+    class Holder:
+        def __init__(self, **kw):
+            self.__dict__.update(kw)
+
+    def make(name):
+        return type(name, (Holder,), {})
+
+    ExtractFrags, AffAgglom, GraphMWS, Relabel = make("ExtractFrags"), make("AffAgglom"), make("GraphMWS"), make("Relabel")
+
+    def plain(v):
+        if isinstance(v, Holder):
+            return {k: plain(x) for k, x in v.__dict__.items()}
+        if isinstance(v, Roi):
+            return [list(v.offset), list(v.shape)]
+        if isinstance(v, dict):
+            return {k: plain(x) for k, x in v.items()}
+        if isinstance(v, (list, tuple)):
+            return [plain(x) for x in v]
+        return v
+
+    def run_volara_task(task, blockwise=None, multiprocessing=None):
+        tasks.append(dict(task=type(task).__name__, args=plain(task), blockwise=blockwise, multiprocessing=multiprocessing))
+
+    mods = {
+        "funlib": types.ModuleType("funlib"), "funlib.geometry": Holder(Coordinate=Coordinate, Roi=Roi),
+        "funlib.persistence": Holder(open_ds=lambda path: DS()),
+        "volara": types.ModuleType("volara"),
+        "volara.blockwise": Holder(ExtractFrags=ExtractFrags, AffAgglom=AffAgglom, GraphMWS=GraphMWS, Relabel=Relabel),
+        "volara.datasets": Holder(Affs=make("Affs"), Labels=make("Labels"), Raw=make("Raw")),
+        "volara.dbs": Holder(SQLite=make("SQLite"), PostgreSQL=make("PostgreSQL")),
+        "volara.lut": Holder(LUT=make("LUT")), "volara.logging": Holder(set_log_basedir=lambda p: None),
+        "refmws": types.ModuleType("refmws"), "refmws.post": types.ModuleType("refmws.post"),
+        "refmws.blockwise": Holder(run_volara_task=run_volara_task),
+    }
+    for n in ("refmws", "refmws.post"):
+        mods[n].__path__ = []
+    sys.modules.update(mods)
+    naming = load("refmws.post.naming", f"{REF}/post/naming.py")
+    naming.dump_params = naming.dump_lut_params = lambda *a, **k: None
+    sys.modules["refmws.post.naming"] = naming
+    src = open(f"{REF}/post/watershed_mutex.py").read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "volara_pipeline")
+    ns = {"__package__": "refmws.post", "__name__": "refmws.post.watershed_mutex"}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "watershed_mutex.volara_pipeline", "exec"), ns)
+    nbh = [[-1, 0, 0], [0, -1, 0], [0, 0, -1], [-2, 0, 0], [0, -5, 0], [0, 0, -5]]
+    tmp = tempfile.mkdtemp()
+    base = dict(affs_dataset="v.zarr/affs", fragments_dataset="v.zarr/post/fragments", seg_dataset_prefix="v.zarr/post/segmentations",
+                lut_dir=os.path.join(tmp, "luts"), db={"db_file": "rag.db"}, aff_neighborhood=nbh, bias=[-0.4] * 3 + [-0.7] * 3)
+    cases = [dict(blockwise=True, num_workers=4, noise_eps=0.001, remove_debris=8),
+             dict(blockwise=True, block_shape=[10, 48, 40], context=[2, 6, 6], strides=[[1, 1, 1]] * 3 + [[1, 2, 2]] * 3, filter_fragments=0.2,
+                  global_bias=[0.9, -0.4], roi_offset=[0, 0, 0], roi_shape=[10, 96, 80]),
+             dict(blockwise=False, noise_eps=0.002)]
+    out = []
+    for extra in cases:
+        tasks.clear()
+        cfg = dict(base, **extra)
+        ns["volara_pipeline"](cfg)
+        for t in tasks:
+            for k in ("lut",):
+                if isinstance(t["args"].get(k), dict) and "path" in t["args"][k]:
+                    t["args"][k]["path"] = os.path.relpath(t["args"][k]["path"], tmp)
+        out.append(dict(cfg={k: v for k, v in extra.items()}, tasks=json.loads(json.dumps(tasks))))
+    with open(os.path.join(OUT, "volara_pipeline_glue.json"), "w") as f:
+        json.dump(dict(base={k: v for k, v in base.items() if k != "lut_dir"}, affs=dict(shape=list(DS.shape), chunk_shape=list(DS.chunk_shape)),
+                       cases=out), f, indent=1)
+    print("volara_pipeline_glue.json", [[t["task"] for t in c["tasks"]] for c in out])
+
+
 def golden_cc_affs_func():
     """post/connected_components.py `cc_affs` (:12-119), the function executed as it stands in the reference file
     (extracted by ast) with the reference's own cc.py and naming.py; funlib's open_ds / prepare_ds / Roi are in-memory
@@ -1048,6 +1138,7 @@ if __name__ == "__main__":
     golden_watershed_in_block_glue()
     golden_simple_watershed_glue()
     golden_waterz_pipeline_glue()
+    golden_volara_pipeline_glue()
     golden_cc_affs_func()
     golden_refine_filters()
     golden_task_states()

@@ -128,7 +128,8 @@ BW_CASES = [
     ((13, 50, 45), (6, 24, 24), (2, 6, 6), dict(aff_neighborhood=NBH6, bias=[-0.4] * 3 + [-0.7] * 3, noise_eps=0.001,
                                                 strides=[[1, 1, 1]] * 3 + [[1, 2, 2]] * 3, filter_fragments=0.3, remove_debris=3,
                                                 global_bias=[1.0, -0.4]), np.uint8, False),       # ragged blocks
-    ((10, 40, 40), (5, 20, 20), (1, 5, 5), dict(aff_neighborhood=NBH3, bias=[-0.5] * 3, noise_eps=0.002, noise_seed=7), np.float32, True),
+    ((10, 40, 40), (5, 20, 20), (1, 5, 5), dict(aff_neighborhood=NBH3, bias=[-0.5] * 3, noise_eps=0.002, noise_seed=7, filter_fragments=0.3), np.float32, True),
+    ((10, 40, 40), (5, 20, 20), (1, 5, 5), dict(aff_neighborhood=NBH3, bias=[-0.5] * 3, noise_eps=0.002, filter_fragments=0.45, remove_debris=2), np.uint8, True),
     ((8, 36, 36), None, None, dict(aff_neighborhood=NBH6, bias=[-0.3] * 3 + [-0.8] * 3, noise_eps=0.001), np.uint8, False),   # one block
 ]
 
