@@ -1658,7 +1658,7 @@ __device__ __forceinline__ uint32_t lab_get(const uint16_t *lab, long long i) { 
 
 template <typename T, typename LT>
 __global__ void __launch_bounds__(256) k_fragstats(const Tile *__restrict__ tiles, AffView A, const LT *__restrict__ lab,
-                                                   const uint32_t *__restrict__ fbase, int need_stats,
+                                                   const uint32_t *__restrict__ fbase, int need_stats, int all_cross,
                                                    typename AffOps<T>::acc_t *__restrict__ fsum, uint32_t *__restrict__ fcnt,
                                                    uint32_t *__restrict__ fmin, uint8_t *__restrict__ fflag) {
     const Tile t = tiles[blockIdx.y];
@@ -1709,7 +1709,8 @@ __global__ void __launch_bounds__(256) k_fragstats(const Tile *__restrict__ tile
             if (leader) {
                 atomicAdd(&fcnt[fi], (uint32_t)__popc(peers));
                 if (wmin != NONE32) atomicMin(&fmin[fi], wmin);
-                if (anyout) fflag[fi] = FF_CROSS;   // every writer stores the same value
+                // given fragments (mutex watershed with long-range edges) need not be connected: all go through the relabel
+                if (anyout || all_cross) fflag[fi] = FF_CROSS;   // every writer stores the same value
             }
         }
     }
@@ -2718,10 +2719,10 @@ static int stage1_batch(Plan &P, const std::vector<int> &bidx, AffView A, uint64
     BS_TRY(fflag.alloc_zero(nF, s));
     const bool lab16 = F.lab16;
     if (lab16)
-        BS_LAUNCH((k_fragstats<T, uint16_t>), grid, 256, 0, s, dt, A, lab.as<uint16_t>(), d_fbase, need_stats ? 1 : 0, fsum.as<acc_t>(),
+        BS_LAUNCH((k_fragstats<T, uint16_t>), grid, 256, 0, s, dt, A, lab.as<uint16_t>(), d_fbase, need_stats ? 1 : 0, ext_labels ? 1 : 0, fsum.as<acc_t>(),
                   fcnt.as<uint32_t>(), fmin.as<uint32_t>(), fflag.as<uint8_t>());
     else
-        BS_LAUNCH((k_fragstats<T, uint32_t>), grid, 256, 0, s, dt, A, lab.as<uint32_t>(), d_fbase, need_stats ? 1 : 0, fsum.as<acc_t>(),
+        BS_LAUNCH((k_fragstats<T, uint32_t>), grid, 256, 0, s, dt, A, lab.as<uint32_t>(), d_fbase, need_stats ? 1 : 0, ext_labels ? 1 : 0, fsum.as<acc_t>(),
                   fcnt.as<uint32_t>(), fmin.as<uint32_t>(), fflag.as<uint8_t>());
     BS_LAUNCH((k_frag_decide<acc_t>), cdiv(nF, 256), 256, 0, s, fsum.as<acc_t>(), fcnt.as<uint32_t>(), fflag.as<uint8_t>(), nF,
               need_stats ? cfg.filter_fragments : 0.0, need_stats ? cfg.remove_debris : 0, sizeof(T) == 1 ? 1 : 0);
