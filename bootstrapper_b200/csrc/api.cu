@@ -65,16 +65,16 @@ int bs_set_debug(int on) {
 
 // keep freed scratch in the stream-ordered pool instead of returning it to the driver at every sync
 static void init_mempool() {
-    static bool done = false;
-    if (done) return;
+    static std::atomic<unsigned long long> done(0);   // one bit per device
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    if (done.load() & (1ull << dev)) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         uint64_t thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
-    done = true;
+    done.fetch_or(1ull << dev);
 }
 
 int bs_set_flood_version(int v) {

@@ -48,7 +48,7 @@ const char *get_error();
     } while (0)
 
 // launch counter (bench.py reports gpu_launches from it)
-extern unsigned long long g_launches;
+extern thread_local unsigned long long g_launches;   // per host thread, like the arena and the profiler
 #define BS_LAUNCH(kernel, grid, block, smem, stream, ...)          \
     do {                                                           \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); \
@@ -60,15 +60,20 @@ extern unsigned long long g_launches;
 // batch): a stage issues ~50 allocations whose sizes depend on the data, and carving them from a cached slab keeps
 // cudaMallocAsync / cudaFreeAsync (and the pool's occasional re-mapping) out of the step.  The first run of a
 // given size finds no arena, allocates stream-ordered and records the bytes it needed; the next run gets the slab.
+// Scratch slab of one host thread on one device: a stage call bump-allocates its temporaries from it and resets it when the
+// next stage call of the same thread begins (stage calls synchronise their stream before they return).  thread_local: two
+// host threads driving two plans never share scratch; a thread that switches devices gets a fresh slab.
 struct Arena {
     char *base = nullptr;
     size_t cap = 0, off = 0, need = 0, need_last = 0;
     bool active = false;
+    int device = -1;
+    ~Arena() { if (base) cudaFree(base); }
     int begin(bool enable);   // (re)size from the recorded need, reset the bump pointer
     void end();
     void destroy();
 };
-extern Arena g_arena;
+extern thread_local Arena g_arena;
 
 struct DevBuf {
     void *p = nullptr;
@@ -149,7 +154,7 @@ struct Profiler {
     void finish(cudaStream_t s);                   // closes the last phase, synchronises, accumulates
     void reset();
 };
-extern Profiler g_prof;
+extern thread_local Profiler g_prof;
 
 // ---- primitives (prims.cu) ----
 // out[i] = sum_{j<i} in[j]; total (device pointer, may be null) = sum of all.  in/out may alias.

@@ -6,15 +6,28 @@ namespace bs {
 static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
 const char *get_error() { return g_err.c_str(); }
-unsigned long long g_launches = 0;
-Profiler g_prof;
-Arena g_arena;
+thread_local unsigned long long g_launches = 0;
+thread_local Profiler g_prof;
+thread_local Arena g_arena;
 
 int Arena::begin(bool enable) {
     active = false;
     off = 0;
     need = 0;
     if (!enable) return BS_OK;
+    int cur = 0;
+    BS_CUDA(cudaGetDevice(&cur));
+    if (base && cur != device) {
+        // the thread moved to another device: the old slab stays where it is until it is released, a new one is sized here
+        int old = device;
+        cudaSetDevice(old);
+        cudaDeviceSynchronize();
+        cudaFree(base);
+        cudaSetDevice(cur);
+        base = nullptr;
+        cap = 0;
+    }
+    device = cur;
     if (need_last > cap) {
         // nothing of the previous stage call is live any more: stage results are plan-owned (alloc_persistent)
         BS_CUDA(cudaDeviceSynchronize());

@@ -22,6 +22,8 @@
 //   k_crop_*         keep/drop decision, 8/26-connected relabel of the cropped write ROI
 //   k_finalize       raster-order ids (+ block_id * prod(block_size)), uint64 output, node statistics
 #include <cuda.h>
+
+#include <atomic>
 #include <stdlib.h>
 #include <string.h>
 
@@ -40,6 +42,14 @@ static constexpr uint32_t DBIG = 0x3FFFFFFFu;
 static constexpr int MAXW = 4096;
 // pixels a 256-thread CTA of the per-pixel kernels walks through: enough work to amortise the tile set-up, enough CTAs
 // (tiles x pixels / PIX_PER_CTA) to fill 148 SMs on small batches
+// true if this device's bit was already set in `mask` (and sets it)
+static bool dev_once(std::atomic<unsigned long long> &mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    const unsigned long long bit = 1ull << dev;
+    return (mask.fetch_or(bit) & bit) != 0;
+}
+
 static const long long PIX_PER_CTA = getenv("BS_PIX_PER_CTA") ? atoll(getenv("BS_PIX_PER_CTA")) : 4096;
 static constexpr unsigned FULL = 0xFFFFFFFFu;
 
@@ -1989,10 +1999,9 @@ static int launch_edt(const Tile *dt, const TileDims &td, bool three_d, const ui
     const bool use_strip = strip_smem <= 96 * 1024;
     const dim3 grid_strip((unsigned)std::min<long long>((long long)td.maxD * ((td.maxW + CS_W - 1) / CS_W), 8192), td.ntiles);
     if (use_strip) {
-        static bool attr_strip = false;
-        if (!attr_strip) {
+        static std::atomic<unsigned long long> attr_strip(0);   // one bit per device: function attributes are per device
+        if (!dev_once(attr_strip)) {
             BS_CUDA(cudaFuncSetAttribute(k_coldist_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            attr_strip = true;
         }
     }
     uint32_t *plane_out = three_d ? tmp : out;
@@ -2014,10 +2023,9 @@ static int launch_seeds(const Tile *dt, const TileDims &td, bool three_d, int ms
                            (long long)td.maxD * ((td.maxW + MF_TW - 1) / MF_TW) * ((td.maxH + MF_TH - 1) / MF_TH), 8192),
                        td.ntiles);
     if (use_mf) {
-        static bool attr_mf = false;
-        if (!attr_mf) {
+        static std::atomic<unsigned long long> attr_mf(0);   // one bit per device: function attributes are per device
+        if (!dev_once(attr_mf)) {
             BS_CUDA(cudaFuncSetAttribute(k_maxfilt_xy, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            attr_mf = true;
         }
     }
     if (!three_d) {
@@ -2362,10 +2370,9 @@ static int stage1_front_unfused(Plan &P, const std::vector<int> &bidx, AffView A
         }
         const size_t smem = gavail ? (size_t)F2_WARPS * (F2_HASH + (slev ? levcap + (levcap + 31) / 32 : 0)) * 4
                                    : (size_t)F2_WARPS * (nwords_max + F2_HASH) * 4;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static std::atomic<unsigned long long> attr_set(0);   // one bit per device: function attributes are per device
+        if (!dev_once(attr_set)) {
             BS_CUDA(cudaFuncSetAttribute(k_flood2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
         }
 #define BS_FLOOD2(G_, S_)                                                                                                    \
     BS_LAUNCH((k_flood2<G_, S_>), cdiv(ntiles, F2_WARPS), 32 * F2_WARPS, smem, s, dt, ntiles, lab.as<uint32_t>(),             \

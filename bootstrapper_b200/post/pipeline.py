@@ -182,24 +182,31 @@ def epsilon_fragments(plan, affs, p, frags_out, mask=None):
 
 def _stack_read_rois(plan, affs, mask, members, rs, wo, ctx):
     """the read ROIs of the blocks `members` (all of read shape rs) stacked along z: zero fill outside the array, mask applied
-    (affs_data *= mask_data) -- the arrays the reference's per-block task body sees"""
+    (affs_data *= mask_data) -- the arrays the reference's per-block task body sees.  Also returns, per block, whether the
+    reference would skip it (`if affs_data.max() < 1e-3: return`, checked on the raw values before mask and scaling)."""
     dev = affs.device
     vol = tuple(affs.shape[1:])
     rz, ry, rx = rs
-    fake = torch.zeros((affs.shape[0], len(members) * rz, ry, rx), dtype=affs.dtype, device=dev)
+    nb = len(members)
+    fake = torch.zeros((affs.shape[0], nb * rz, ry, rx), dtype=affs.dtype, device=dev)
+    mstack = None if mask is None else torch.zeros((nb * rz, ry, rx), dtype=torch.bool, device=dev)
     for k, bi in enumerate(members):
         ro = [int(wo[bi][d]) - ctx[d] for d in range(3)]
         lo = [max(ro[d], 0) for d in range(3)]
         hi = [min(ro[d] + rs[d], vol[d]) for d in range(3)]
         if any(h <= l for l, h in zip(lo, hi)):
             continue
-        src = (slice(None),) + tuple(slice(l, h) for l, h in zip(lo, hi))
+        src = tuple(slice(l, h) for l, h in zip(lo, hi))
         dz, dy, dx = (lo[d] - ro[d] for d in range(3))
-        piece = affs[src]
+        dst = (slice(k * rz + dz, k * rz + dz + (hi[0] - lo[0])), slice(dy, dy + (hi[1] - lo[1])), slice(dx, dx + (hi[2] - lo[2])))
+        fake[(slice(None),) + dst] = affs[(slice(None),) + src]
         if mask is not None:
-            piece = piece * (mask[src[1:]] > 0).to(piece.dtype)
-        fake[:, k * rz + dz:k * rz + dz + (hi[0] - lo[0]), dy:dy + (hi[1] - lo[1]), dx:dx + (hi[2] - lo[2])] = piece
-    return fake
+            mstack[dst] = mask[src] > 0
+    peak = fake.view(affs.shape[0], nb, rz, ry, rx).amax(dim=(0, 2, 3, 4))
+    empty = (peak == 0) if affs.dtype == torch.uint8 else (peak < 1e-3)
+    if mstack is not None:
+        fake *= mstack.to(fake.dtype)
+    return fake, empty.cpu().numpy()
 
 
 MWS_DEFAULTS = dict(aff_neighborhood=None, bias=None, global_bias=[1.0, -0.5], filter_fragments=None, sigma=None, noise_eps=None,
@@ -253,10 +260,12 @@ def segment_mws_blockwise(affs, params, block_size=None, context=None, mask=None
     counts = np.zeros(len(ids), np.int64)
     nodes_all, mws_counters = [], []
     for rs, members in sorted(groups.items()):
-        fake = _stack_read_rois(plan, affs, mask, members, rs, wo, ctx)
+        fake, empty = _stack_read_rois(plan, affs, mask, members, rs, wo, ctx)
         seeds = [block_seed(p["noise_seed"], int(ids[bi])) for bi in members] if p["noise_eps"] else None
         labels, cnt = native.mws_agglom_blocks(fake, len(members), nbh, bias, strides=p["strides"], noise_eps=p["noise_eps"], block_seeds=seeds)
         del fake
+        for k in np.nonzero(empty)[0]:      # the reference returns before it writes anything for such a block
+            labels[int(k) * rs[0]:(int(k) + 1) * rs[0]] = 0
         mws_counters.append(cnt)
         plan.set_owned(members)
         plan.fragments_from_labels(affs, labels, cnt["n_labels"], frags, mask=mask)

@@ -5,8 +5,9 @@
  * (torch tensors on the Python side), a cudaStream_t passed as void*.  Every entry
  * point returns 0 on success or a negative BS_ERR_* code; bs_last_error() gives the
  * thread-local message.  There is NO CPU fallback anywhere behind this ABI.
- * One host thread per process drives the library (scratch arena, launch counter and profiler are process-wide);
- * calls are ordered on the stream they are given and synchronise it where a count has to reach the host.
+ * Scratch arena, launch counter and stage profiler are per host thread (thread_local; the arena also per device): several
+ * host threads may drive different plans concurrently, one plan is driven by one thread at a time.  Calls are ordered on
+ * the stream they are given and synchronise it where a count has to reach the host.
  *
  * Each entry point names the reference interface it replaces (paths relative to
  * /root/reference/bootstrapper, upstream ucsdmanorlab/bootstrapper v0.3.2).

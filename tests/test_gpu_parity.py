@@ -684,3 +684,40 @@ def test_refine_filters_match_oracle():
         refine.remap(r["fragments"], remove_ids=[5], merge_groups=[[5, 6]])
     empty = torch.zeros((3, 8, 8), dtype=torch.int64, device="cuda")
     assert refine.global_sizes(empty)[0].size == 0
+
+
+def test_two_host_threads_do_not_share_scratch():
+    """the library's scratch arena / profiler / launch counter are per host thread: two threads driving two plans on two
+    streams at the same time get the results of the serial runs (process-global scratch)"""
+    import threading
+    from bootstrapper_b200 import native
+    from bootstrapper_b200.post.pipeline import segment_blockwise
+    shape, block, ctx = (24, 260, 260), (12, 130, 130), (2, 16, 16)
+    affs = [native.synth_affs(shape, seed=s) for s in (1, 2)]
+    serial = [segment_blockwise(a, {}, block, ctx) for a in affs]
+    torch.cuda.synchronize()
+    got, errs = [None, None], []
+
+    def work(k):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(4):
+                    r = segment_blockwise(affs[k], {}, block, ctx)
+                st.synchronize()
+            got[k] = r
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for k in range(2):
+        assert torch.equal(got[k]["fragments"], serial[k]["fragments"])
+        for a, b in zip(got[k]["edges"], serial[k]["edges"]):
+            assert torch.equal(a.view(torch.int32) if a.dtype == torch.float32 else a, b.view(torch.int32) if b.dtype == torch.float32 else b)
+        for thr in serial[k]["segs"]:
+            assert torch.equal(got[k]["segs"][thr], serial[k]["segs"][thr])
