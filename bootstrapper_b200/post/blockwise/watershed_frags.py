@@ -134,7 +134,8 @@ class WatershedFrags(BlockwiseTask):
                 world = npos.cpu().numpy().astype(np.int64) * np.array(self.voxel_size) + np.array(a.offset)
                 self.db.write_nodes(nid.cpu().numpy().view(np.uint64), world, nsz.cpu().numpy().astype(np.int64))
             return
-        plan.fragments(self._load_affs(), frags_out=self._frags(), mask=self._mask_dev())
+        from ..pipeline import fragments_all_blocks
+        fragments_all_blocks(plan, self._load_affs(), self.params, frags_out=self._frags(), mask=self._mask_dev())
         self._store(plan)
 
     @contextmanager

@@ -107,6 +107,50 @@ def make_plan(affs, params, block_size, context=None, roi=None, **kw):
                        noise_eps=p["noise_eps"], noise_seed=p.get("noise_seed", 0) or 0, **kw), p
 
 
+def _empty_block_check_needed(p):
+    """The reference returns from a block whose raw affinities are all < 1e-3 before it does anything (watershed_frags.py:
+    201-202).  Without that test such a block has no boundary mask and hence no fragments either -- unless the shift can lift
+    mean(affs + shift) above 0.5: a bias, or noise (the seeded generator is bounded by 3.47 sigma)."""
+    bias = p.get("bias")
+    bmax = 0.0 if bias is None else max(bias) if isinstance(bias, (list, tuple)) else float(bias)
+    return bmax + 3.47 * float(p.get("noise_eps") or 0.0) + 3e-3 > 0.5
+
+
+def empty_blocks(plan, affs):
+    """per block of the plan: raw affinities of the read ROI (all channels, before mask and scaling) all < 1e-3"""
+    ids, wo, ws = plan.block_info()
+    ctx = [int(plan.cfg.context[d]) for d in range(3)]
+    vol = tuple(affs.shape[1:])
+    peaks = []
+    for i in range(len(ids)):
+        lo = [max(int(wo[i][d]) - ctx[d], 0) for d in range(3)]
+        hi = [min(int(wo[i][d]) + int(ws[i][d]) + ctx[d], vol[d]) for d in range(3)]
+        peaks.append(affs[:, lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]].amax().to(torch.float32))
+    peak = torch.stack(peaks).cpu().numpy()
+    return (peak == 0) if affs.dtype == torch.uint8 else (peak < 1e-3)
+
+
+def fragments_all_blocks(plan, affs, p, frags_out=None, mask=None):
+    """stage 1 for every block of `plan` (bs_stage1_fragments), leaving out the blocks the reference skips as empty when that
+    can change the result (see _empty_block_check_needed).  Returns the fragments tensor."""
+    n, _ = plan.num_blocks()
+    if not _empty_block_check_needed(p):
+        return plan.fragments(affs, frags_out=frags_out, mask=mask)
+    empty = empty_blocks(plan, affs)
+    if frags_out is None:
+        frags_out = torch.zeros(plan.roi_shape, dtype=torch.int64, device=affs.device)
+    elif empty.any():
+        frags_out.zero_()
+    plan.set_owned(np.nonzero(~empty)[0])
+    if not empty.all():
+        plan.fragments(affs, frags_out=frags_out, mask=mask)
+    counts = plan.block_counts()
+    counts[empty] = 0
+    plan.set_owned(np.arange(n))
+    plan.set_block_counts(counts)
+    return frags_out
+
+
 def epsilon_fragments(plan, affs, p, frags_out, mask=None):
     """WatershedFrags with epsilon_agglomerate > 0 (watershed_frags.py:158-176, 182-183) for all blocks of `plan`:
     per block, the watershed fragments of its read ROI are merged by waterz (mean affinity, BinQueue<256>, float32
@@ -310,7 +354,7 @@ def segment_blockwise(affs, params=None, block_size=None, context=None, roi=None
         frags = out.get("fragments") if out is not None else torch.zeros(plan.roi_shape, dtype=torch.int64, device=dev)
         node_ids, node_pos, node_size = epsilon_fragments(plan, affs, p, frags, mask=mask)
     else:
-        frags = plan.fragments(affs, frags_out=None if out is None else out.get("fragments"), mask=mask)
+        frags = fragments_all_blocks(plan, affs, p, frags_out=None if out is None else out.get("fragments"), mask=mask)
         node_ids, node_pos, node_size = plan.nodes(dev)
     plan.agglomerate(affs, frags)
     eu, ev, es = plan.edges(dev)

@@ -89,6 +89,21 @@ def test_pipeline_matches_oracle(shape, block, ctx, params, dtype):
     _check(_run_gpu(affs, params, block, ctx), _oracle(affs, params, block, ctx))
 
 
+@pytest.mark.parametrize("dtype,params", [(np.uint8, {"bias": [0.6, 0.6, 0.6]}), (np.float32, {"bias": 0.3, "noise_eps": 0.07, "fragments_in_xy": False})])
+def test_empty_blocks_are_skipped_like_the_reference(dtype, params):
+    """watershed_frags.py:201-202: a block whose raw affinities are all < 1e-3 is left untouched even when a bias / noise would
+    lift its (shifted) affinities over the boundary threshold"""
+    from bootstrapper_b200.synth import synth_affs
+    affs = synth_affs((12, 80, 80), seed=6, dtype=dtype)
+    affs[:, 0:7, 0:45, 0:45] = 0               # the read ROI of block (0, 0, 0)
+    if dtype == np.float32:
+        affs[:, 0:7, 0:45, 0:45] = 5e-4        # below the reference's 1e-3
+    block, ctx = (6, 40, 40), (1, 5, 5)
+    ref = _oracle(affs, params, block, ctx)
+    assert not ref["fragments"][:6, :40, :40].any() and ref["fragments"].any()
+    _check(_run_gpu(affs, params, block, ctx), ref)
+
+
 def test_single_block_roi_mode():
     """block_shape == "roi": one block, no context (post/watershed.py:84-86, :361-364)"""
     from bootstrapper_b200.synth import synth_affs
