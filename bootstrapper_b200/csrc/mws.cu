@@ -373,9 +373,11 @@ __global__ void k_mws_flatten(const uint32_t *__restrict__ parent, uint32_t *__r
             p = parent[x];
         }
         out[i] = x;
-        ehead[i] = (uint32_t)i;
-        etail[i] = (uint32_t)i;
-        enext[i] = NONE32;
+        if (x == (uint32_t)i) {     // lists hang off roots only
+            ehead[i] = (uint32_t)i;
+            etail[i] = (uint32_t)i;
+            enext[i] = NONE32;
+        }
     }
 }
 
@@ -427,7 +429,7 @@ __global__ void k_mws_debris(const uint64_t *__restrict__ labels, size_t V, cons
 }
 
 // edges per round (BS_MWS_WINDOW overrides; the result does not depend on it)
-static unsigned long long g_mws_window = getenv("BS_MWS_WINDOW") ? strtoull(getenv("BS_MWS_WINDOW"), nullptr, 10) : (1ull << 21);
+static unsigned long long g_mws_window = getenv("BS_MWS_WINDOW") ? strtoull(getenv("BS_MWS_WINDOW"), nullptr, 10) : (1ull << 17);
 
 // rounds between two rebuilds of the mutex set (BS_MWS_EPOCH), and the number of set probes in one round that forces one early
 static unsigned long long g_mws_epoch = getenv("BS_MWS_EPOCH") ? strtoull(getenv("BS_MWS_EPOCH"), nullptr, 10) : 64;
