@@ -34,16 +34,22 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
+
+#include <cooperative_groups.h>
 
 #include "common.cuh"
 #include "../../include/bsnative.h"
+
+namespace cg = cooperative_groups;
 
 namespace bs {
 
 static constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 static constexpr unsigned long long EMPTY64 = 0xFFFFFFFFFFFFFFFFull;
 static constexpr uint32_t ATTR_BIT = 0x80000000u;
+static constexpr unsigned FULL32 = 0xFFFFFFFFu;
 
 struct MwsGeom {
     int C, Z, Y, X;
@@ -428,12 +434,233 @@ __global__ void k_mws_debris(const uint64_t *__restrict__ labels, size_t V, cons
     }
 }
 
+// ------------------------------------------------------------------ the rounds of one epoch in ONE cooperative launch
+// With a window of 2^17 edges the nine launches + host sync of a round cost more than its work; this kernel keeps the grid
+// resident and runs round after round (phases separated by grid-wide barriers) until the window is empty, a rebuild of the
+// mutex set is due, or max_rounds is reached.  Phase bodies = the kernels above; the survivors are compacted in order by a
+// block-sum / ordered-scatter pass.  Arrays that change inside the kernel are accessed through plain (coherent) pointers.
+static constexpr int COOP_NT = 512;
+struct MwsCoop {
+    const uint32_t *eu, *ev;
+    uint32_t E, wcap;
+    uint32_t *parent;
+    const uint32_t *eroot;
+    uint32_t *bestA, *ehead, *etail, *enext, *pairmark;
+    uint8_t *nonfree;
+    uint32_t *win[2];
+    uint2 *wroots;
+    uint8_t *keep, *did;
+    unsigned long long *tab;
+    unsigned long long tmask;
+    uint2 *mlist;
+    unsigned long long *cnt;   // the counters of mws_rounds
+    uint32_t *ctl;             // [0] nwin [1] cursor [2] window buffer in use [3] rounds so far [4] rounds since the rebuild
+                               // [5] unions since the rebuild [6] stop: 1 = rebuild due, 2 = a round executed nothing
+    uint32_t *blocksum;        // gridDim.x
+    uint32_t epoch, max_rounds;
+    unsigned long long probe_budget;
+};
+
+__global__ void __launch_bounds__(COOP_NT) k_mws_coop(MwsCoop a) {
+    cg::grid_group grid = cg::this_grid();
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gn = (size_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ uint32_t s_w[COOP_NT / 32], s_w2[COOP_NT / 32];
+    __shared__ uint32_t s_base, s_total;
+    volatile uint32_t *ctl = a.ctl;
+    for (uint32_t it = 0; it < a.max_rounds; it++) {
+        const uint32_t nwin = ctl[0], cursor = ctl[1], par = ctl[2], round = ctl[3] + 1;
+        if (nwin == 0 || ctl[6]) break;
+        const uint32_t *win = a.win[par];
+        uint32_t *wout = a.win[par ^ 1];
+        // ---- A: roots, dead edges, bestA
+        for (size_t j = gtid; j < nwin; j += gn) {
+            const uint32_t i = win[j];
+            const uint32_t u = a.eu[i], v = a.ev[i];
+            uint32_t ru = NONE32, rv = NONE32;
+            if (v != NONE32) ru = mws_find(a.parent, u & ~ATTR_BIT), rv = mws_find(a.parent, v);
+            a.wroots[j] = make_uint2(ru, rv);
+            a.did[j] = 0;
+            if (ru == rv) {
+                a.keep[j] = 0;
+                continue;
+            }
+            a.keep[j] = 1;
+            if (u & ATTR_BIT) {
+                atomicMin(&a.bestA[ru], i);
+                atomicMin(&a.bestA[rv], i);
+            }
+        }
+        grid.sync();
+        // ---- B: repulsive edges
+        for (size_t j = gtid; j < nwin; j += gn) {
+            if (!a.keep[j]) continue;
+            const uint32_t i = win[j];
+            const uint32_t u = a.eu[i], v = a.ev[i];
+            if (u & ATTR_BIT) continue;
+            const uint2 r = a.wroots[j];
+            if (i < a.bestA[r.x] && i < a.bestA[r.y]) {
+                a.keep[j] = 0;
+                const uint32_t ea = a.eroot[u], eb = a.eroot[v];
+                const unsigned long long key = ((unsigned long long)min(ea, eb) << 32) | max(ea, eb);
+                if (mws_set_insert(a.tab, a.tmask, key)) {
+                    const unsigned long long slot = atomicAdd(&a.cnt[1], 1ull);
+                    a.mlist[slot] = make_uint2(u, v);
+                }
+                atomicAdd(&a.cnt[3], 1ull);
+            }
+        }
+        grid.sync();
+        // ---- C: attractive edges
+        for (size_t j = gtid; j < nwin; j += gn) {
+            if (!a.keep[j]) continue;
+            const uint32_t i = win[j];
+            if (!(a.eu[i] & ATTR_BIT)) continue;
+            const uint32_t ru = a.wroots[j].x, rv = a.wroots[j].y;
+            const bool top_u = a.bestA[ru] == i, top_v = a.bestA[rv] == i;
+            if (!top_u && !top_v) continue;
+            const bool nf_u = a.nonfree[ru], nf_v = a.nonfree[rv];
+            const bool free_u = top_u && !nf_u, free_v = top_v && !nf_v;
+            if (!(top_u && top_v) && !free_u && !free_v) continue;
+            a.keep[j] = 0;
+            bool blocked = false;
+            if (nf_u && nf_v) {
+                unsigned long long probes = 0;
+                for (uint32_t ea = a.ehead[ru]; ea != NONE32 && !blocked; ea = a.enext[ea])
+                    for (uint32_t eb = a.ehead[rv]; eb != NONE32; eb = a.enext[eb]) {
+                        probes++;
+                        if (mws_set_has(a.tab, a.tmask, ((unsigned long long)min(ea, eb) << 32) | max(ea, eb))) {
+                            blocked = true;
+                            break;
+                        }
+                    }
+                atomicAdd(&a.cnt[8], probes);
+            }
+            if (blocked) {
+                atomicAdd(&a.cnt[4], 1ull);
+            } else {
+                if (nf_u && nf_v) a.pairmark[ru] = round, a.pairmark[rv] = round;
+                a.did[j] = 1;
+                uf_union(a.parent, ru, rv);
+                atomicAdd(&a.cnt[2], 1ull);
+                atomicAdd(&a.cnt[5], 1ull);
+            }
+        }
+        grid.sync();
+        // ---- D: epoch-cluster lists of the new clusters
+        for (size_t j = gtid; j < nwin; j += gn) {
+            if (!a.did[j]) continue;
+            const uint32_t x = a.wroots[j].x, y = a.wroots[j].y;
+            const bool nfx = a.nonfree[x], nfy = a.nonfree[y];
+            if (!nfx && !nfy) continue;
+            const uint32_t R = mws_find(a.parent, x);
+            if (nfx && nfy) {
+                const uint32_t hx = a.ehead[x], tx = a.etail[x], hy = a.ehead[y], ty = a.etail[y];
+                a.enext[tx] = hy;
+                a.ehead[R] = hx;
+                a.etail[R] = ty;
+            } else {
+                const uint32_t n = nfx ? x : y;
+                if (a.pairmark[n] == round || R == n) continue;
+                const uint32_t h = a.ehead[n], t = a.etail[n];
+                a.ehead[R] = h;
+                a.etail[R] = t;
+            }
+        }
+        grid.sync();
+        // ---- E: non-free flags, bestA reset, survivors per CTA chunk
+        for (size_t j = gtid; j < nwin; j += gn) {
+            const uint2 r = a.wroots[j];
+            if (a.did[j] && (a.nonfree[r.x] || a.nonfree[r.y])) a.nonfree[mws_find(a.parent, r.x)] = 1;
+        }
+        for (size_t j = gtid; j < nwin; j += gn) {
+            const uint2 r = a.wroots[j];
+            if (r.x != NONE32) a.bestA[r.x] = NONE32, a.bestA[r.y] = NONE32;
+        }
+        const uint32_t chunk = (nwin + gridDim.x - 1) / gridDim.x;
+        const uint32_t lo = min(nwin, blockIdx.x * chunk), hi = min(nwin, lo + chunk);
+        {
+            uint32_t c = 0;
+            for (uint32_t j = lo + threadIdx.x; j < hi; j += COOP_NT) c += a.keep[j];
+            c = __reduce_add_sync(FULL32, c);
+            if (lane == 0) s_w[warp] = c;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t t = 0;
+                for (int w = 0; w < COOP_NT / 32; w++) t += s_w[w];
+                a.blocksum[blockIdx.x] = t;
+            }
+        }
+        grid.sync();
+        // ---- F: ordered compaction + refill
+        {
+            // gridDim.x <= COOP_NT: one block sum per thread, reduced by the block
+            const uint32_t v = threadIdx.x < gridDim.x ? __ldcg(&a.blocksum[threadIdx.x]) : 0u;
+            const uint32_t tb = __reduce_add_sync(FULL32, threadIdx.x < blockIdx.x ? v : 0u), tt = __reduce_add_sync(FULL32, v);
+            __syncthreads();                       // s_w of phase E is consumed
+            if (lane == 0) s_w[warp] = tb, s_w2[warp] = tt;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t b = 0, t = 0;
+                for (int w = 0; w < COOP_NT / 32; w++) b += s_w[w], t += s_w2[w];
+                s_base = b;
+                s_total = t;
+            }
+            __syncthreads();
+        }
+        const uint32_t nkeep = s_total;
+        uint32_t run = s_base;
+        for (uint32_t j0 = lo; j0 < hi; j0 += COOP_NT) {
+            const uint32_t j = j0 + threadIdx.x;
+            const bool f = j < hi && a.keep[j];
+            const unsigned bal = __ballot_sync(FULL32, f);
+            __syncthreads();                       // s_w of the previous tile is consumed
+            if (lane == 0) s_w[warp] = __popc(bal);
+            __syncthreads();
+            uint32_t wpre = 0, tot = 0;
+            for (int w = 0; w < COOP_NT / 32; w++) {
+                const uint32_t v = s_w[w];
+                if (w < warp) wpre += v;
+                tot += v;
+            }
+            if (f) wout[run + wpre + __popc(bal & ((1u << lane) - 1u))] = win[j];
+            run += tot;
+        }
+        const uint32_t nfill = min(a.wcap - nkeep, a.E - cursor);
+        for (size_t j = gtid; j < nfill; j += gn) wout[nkeep + j] = cursor + (uint32_t)j;
+        grid.sync();
+        // ---- G: bookkeeping by one thread
+        if (gtid == 0) {
+            const uint32_t nnew = nkeep + nfill;
+            ctl[0] = nnew;
+            ctl[1] = cursor + nfill;
+            ctl[2] = par ^ 1;
+            ctl[3] = round;
+            ctl[4] = ctl[4] + 1;
+            volatile unsigned long long *cnt = a.cnt;
+            if (cnt[5] > 0) ctl[5] = 1;
+            if (nkeep == nwin && nfill == 0)
+                ctl[6] = 2;
+            else if (nnew > 0 && ctl[5] && (ctl[4] >= a.epoch || cnt[8] > a.probe_budget))
+                ctl[6] = 1;
+            cnt[5] = 0;
+            cnt[8] = 0;
+            __threadfence();
+        }
+        grid.sync();
+    }
+}
+
 // edges per round (BS_MWS_WINDOW overrides; the result does not depend on it)
 static unsigned long long g_mws_window = getenv("BS_MWS_WINDOW") ? strtoull(getenv("BS_MWS_WINDOW"), nullptr, 10) : (1ull << 17);
 
 // rounds between two rebuilds of the mutex set (BS_MWS_EPOCH), and the number of set probes in one round that forces one early
 static unsigned long long g_mws_epoch = getenv("BS_MWS_EPOCH") ? strtoull(getenv("BS_MWS_EPOCH"), nullptr, 10) : 64;
 static unsigned long long g_mws_probe_budget = getenv("BS_MWS_PROBES") ? strtoull(getenv("BS_MWS_PROBES"), nullptr, 10) : (1ull << 23);
+
+// BS_MWS_COOP=0: one set of launches per round instead of the cooperative kernel (same results)
+static double g_mws_rebuild_s = 0.0;   // BS_MWS_VERBOSE: seconds spent in rebuilds (cooperative path)
+static int g_mws_coop = getenv("BS_MWS_COOP") ? atoi(getenv("BS_MWS_COOP")) : 1;
 
 static unsigned grid_for(size_t n) { return (unsigned)std::min<size_t>(std::max<size_t>((n + 255) / 256, 1), 148 * 16); }
 
@@ -479,6 +706,69 @@ static int mws_rounds(const uint32_t *eu, const uint32_t *ev, unsigned long long
         cursor = wcap;
         int since_rebuild = 0;
         bool unions_since_rebuild = false;
+        // ---- cooperative path: all rounds of an epoch in one launch
+        int coop_grid = 0;
+        if (g_mws_coop) {
+            int dev = 0, ok = 0, sms = 0, nb = 0;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&ok, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && ok &&
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_mws_coop, COOP_NT, 0) == cudaSuccess && nb >= 1)
+                coop_grid = std::min(getenv("BS_MWS_COOP_GRID") ? atoi(getenv("BS_MWS_COOP_GRID")) : sms, std::min(sms * nb, COOP_NT));
+            else
+                cudaGetLastError();
+        }
+        if (coop_grid > 0) {
+            DevBuf ctl, blocksum;
+            BS_TRY(ctl.alloc_zero(32, s));
+            BS_TRY(blocksum.alloc_zero(4 * (size_t)coop_grid, s));
+            uint32_t h_ctl[8] = {(uint32_t)nwin, cursor, 0, 0, 0, 0, 0, 0};
+            BS_CUDA(cudaMemcpyAsync(ctl.p, h_ctl, 32, cudaMemcpyHostToDevice, s));
+            BS_CUDA(cudaMemsetAsync(d_cnt + 5, 0, 8, s));
+            BS_CUDA(cudaMemsetAsync(d_cnt + 8, 0, 8, s));
+            MwsCoop A;
+            A.eu = eu, A.ev = ev, A.E = (uint32_t)E, A.wcap = wcap;
+            A.parent = parent, A.eroot = root.as<uint32_t>();
+            A.bestA = bestA.as<uint32_t>(), A.ehead = ehead.as<uint32_t>(), A.etail = etail.as<uint32_t>(), A.enext = enext.as<uint32_t>();
+            A.pairmark = pairmark.as<uint32_t>(), A.nonfree = nonfree.as<uint8_t>();
+            A.win[0] = win.as<uint32_t>(), A.win[1] = win2.as<uint32_t>();
+            A.wroots = wroots.as<uint2>(), A.keep = keep.as<uint8_t>(), A.did = did.as<uint8_t>();
+            A.tab = tab.as<unsigned long long>(), A.tmask = tcap - 1;
+            A.cnt = d_cnt, A.ctl = ctl.as<uint32_t>(), A.blocksum = blocksum.as<uint32_t>();
+            A.epoch = (uint32_t)g_mws_epoch, A.max_rounds = 1u << 14, A.probe_budget = g_mws_probe_budget;
+            for (;;) {
+                A.mlist = mlist.as<uint2>();          // swapped by a rebuild
+                void *args[] = {&A};
+                BS_CUDA(cudaLaunchCooperativeKernel((void *)k_mws_coop, dim3((unsigned)coop_grid), dim3(COOP_NT), args, 0, s));
+                g_launches++;
+                BS_CUDA(cudaMemcpyAsync(h_ctl, ctl.p, 32, cudaMemcpyDeviceToHost, s));
+                BS_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 128, cudaMemcpyDeviceToHost, s));
+                BS_CUDA(cudaStreamSynchronize(s));
+                rounds = (int)h_ctl[3];
+                BS_ARG(h_ctl[6] != 2, "bs_mws_agglom: a round executed no edge (internal error)");
+                if (h_ctl[0] == 0) break;
+                if (h_ctl[6] == 1) {
+                    rebuilds++;
+                    const auto r0 = std::chrono::steady_clock::now();
+                    BS_LAUNCH(k_mws_flatten, grid_for(V), 256, 0, s, parent, root.as<uint32_t>(), ehead.as<uint32_t>(), etail.as<uint32_t>(),
+                              enext.as<uint32_t>(), V);
+                    BS_CUDA(cudaMemcpyAsync(parent, root.p, 4 * V, cudaMemcpyDeviceToDevice, s));
+                    const size_t nm = (size_t)h_cnt[1];
+                    if (nm) {
+                        BS_CUDA(cudaMemsetAsync(tab.p, 0xFF, 8 * tcap, s));
+                        BS_CUDA(cudaMemsetAsync(d_cnt + 1, 0, 8, s));
+                        BS_LAUNCH(k_mws_rekey, grid_for(nm), 256, 0, s, mlist.as<uint2>(), nm, root.as<uint32_t>(), tab.as<unsigned long long>(),
+                                  tcap - 1, mlist2.as<uint2>(), d_cnt + 1);
+                        mlist.swap(mlist2);
+                    }
+                    BS_CUDA(cudaMemsetAsync(ctl.as<uint32_t>() + 4, 0, 12, s));
+                    if (getenv("BS_MWS_VERBOSE")) {
+                        cudaStreamSynchronize(s);
+                        g_mws_rebuild_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - r0).count();
+                    }
+                }
+            }
+            nwin = 0;
+        }
         while (nwin > 0) {
             rounds++;
             since_rebuild++;
@@ -553,6 +843,13 @@ static int mws_run(const T *affs, const uint8_t *mask, MwsGeom &G, int zero_is_r
     unsigned long long h_cnt[16];
     memset(h_cnt, 0, sizeof(h_cnt));
     int rounds = 0, rebuilds = 0;
+    const bool verbose = getenv("BS_MWS_VERBOSE") != nullptr;
+    auto now = [&]() {
+        if (verbose) cudaStreamSynchronize(s);
+        return std::chrono::steady_clock::now();
+    };
+    const auto t0 = now();
+    auto t1 = t0, t2 = t0;
     if (E) {
         BS_TRY(keys.alloc(8 * (size_t)E, s));
         BS_TRY(keys2.alloc(8 * (size_t)E, s));
@@ -570,10 +867,15 @@ static int mws_run(const T *affs, const uint8_t *mask, MwsGeom &G, int zero_is_r
         vals.release();
         BS_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 128, cudaMemcpyDeviceToHost, s));
         BS_CUDA(cudaStreamSynchronize(s));
+        t1 = now();
         BS_TRY(mws_rounds(eu.as<uint32_t>(), ev.as<uint32_t>(), E, V, h_cnt[0], parent.as<uint32_t>(), d_cnt, h_cnt, &rounds, &rebuilds, s));
+        t2 = now();
     }
     h_cnt[7] = (unsigned long long)rounds;
-    if (getenv("BS_MWS_VERBOSE")) fprintf(stderr, "[bs mws] edges %llu rounds %d rebuilds %d\n", (unsigned long long)E, rounds, rebuilds);
+    if (verbose)
+        fprintf(stderr, "[bs mws] edges %llu rounds %d rebuilds %d; rank edges %.3f s, rounds + rebuilds %.3f s (rebuilds %.3f s)\n",
+                (unsigned long long)E, rounds, rebuilds, std::chrono::duration<double>(t1 - t0).count(),
+                std::chrono::duration<double>(t2 - t1).count(), g_mws_rebuild_s), g_mws_rebuild_s = 0.0;
     unsigned long long n_labels = 0;
     if (labels32_out) {
         // dense labels 1..n in the order of every cluster's first voxel
