@@ -80,6 +80,7 @@ struct DevBuf {
     size_t bytes = 0;
     cudaStream_t s = 0;
     bool from_arena = false;
+    bool persistent = false;   // plan-owned results: freed with cudaFree (the stream they were made on may be gone by then)
     DevBuf() {}
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
@@ -109,6 +110,7 @@ struct DevBuf {
         bytes = n;
         if (n == 0) n = 16;
         BS_CUDA(cudaMallocAsync(&p, n, stream));
+        persistent = true;
         return BS_OK;
     }
     int alloc_zero(size_t n, cudaStream_t stream) {
@@ -122,16 +124,23 @@ struct DevBuf {
         return BS_OK;
     }
     void release() {
-        if (p && !from_arena) cudaFreeAsync(p, s);
+        if (p && !from_arena) {
+            if (persistent)
+                cudaFree(p);
+            else
+                cudaFreeAsync(p, s);
+        }
         p = nullptr;
         bytes = 0;
         from_arena = false;
+        persistent = false;
     }
     void swap(DevBuf &o) {
         std::swap(p, o.p);
         std::swap(bytes, o.bytes);
         std::swap(s, o.s);
         std::swap(from_arena, o.from_arena);
+        std::swap(persistent, o.persistent);
     }
     template <typename T>
     T *as() const {
