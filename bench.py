@@ -577,7 +577,28 @@ def run_ours(args):
                             "counters": {k: int(v) for k, v in cnt9.items()},
                             "parity": "bit-identical to the sequential restatement of mwatershed.agglom at oracle-sized cases "
                                       "(tests/test_gpu_mws.py; declared tie rule D4, parity unpinned)"}
-        del a9, frags9
+        del frags9
+        # the same volume through the blockwise pipeline with SURVEY 8(d)'s config-3 geometry: 128^3 blocks, context 16
+        from bootstrapper_b200.post.pipeline import segment_mws_blockwise
+        torch.cuda.empty_cache()
+        p9 = dict(aff_neighborhood=MWS_NBH, bias=MWS_BIAS, strides=MWS_STRIDES, noise_eps=0.001, noise_seed=0)
+        torch.cuda.synchronize()
+        ev[0].record()
+        rb = segment_mws_blockwise(a9, p9, (128, 128, 128), (16, 16, 16), profile=True)
+        ev[1].record()
+        torch.cuda.synchronize()
+        msb = ev[0].elapsed_time(ev[1])
+        extra["config3_blockwise"] = {
+            "workload": "blockwise mws pipeline (bs segment --mws -b: ExtractFrags -> AffAgglom -> GraphMWS -> Relabel), 9x(512,512,512) uint8 "
+                        "affinities, 64 blocks of (128,128,128), context (16,16,16), reference default offsets / biases / strides, seeded noise "
+                        "0.001, global_bias [1.0, -0.5], one GPU",
+            "ms_per_step": msb, "value": 512.0 ** 3 / (msb * 1e-3), "unit": "voxels/s", "steps": 1, "warmup": 0,
+            "stage_s": {k: round(v, 3) for k, v in rb["stage_s"].items()},
+            "fragments": int(rb["nodes"][0].numel()), "edges": int(rb["edges"][0].numel()),
+            "counters": {"extract_frags": [{k: int(v) for k, v in c.items()} for c in rb["counters"]["extract_frags"]],
+                         "graph_mws": {k: int(v) for k, v in rb["counters"]["graph_mws"].items()}},
+            "parity": "bit-identical to the oracle's restatement of the four volara tasks at oracle-sized cases (tests/test_gpu_mws.py; parity unpinned)"}
+        del a9, rb
         torch.cuda.empty_cache()
         native.release_scratch()
     if job.rank == 0:

@@ -207,10 +207,12 @@ static int aff_agglom_impl(Plan &P, const T *affs, const uint64_t *frags, int C,
         for (int k = 0; k < 3; k++) d.ro[k] = b.ro[k], d.rs[k] = b.rs[k];
         d.own_first = (uint32_t)P.block_nbase[P.owned[i]];
         d.own_count = (uint32_t)P.block_count[P.owned[i]];
-        double est = 0;
-        for (int k = 0; k < 27; k++)
-            if (b.nb[k] >= 0) est += (b.nb[k] == P.owned[i] ? 1.0 : 0.5) * (double)P.block_count[b.nb[k]];
-        d.tcap = aa_pow2((uint64_t)std::max(4096.0, 8.0 * (double)C * est * mult));
+        // distinct pairs: the block's own fragments plus the share of its neighbours' that reaches into the halo, each with a
+        // few partners per offset; too small a table is detected and the call repeated with 4x the slots
+        double halo = 0;
+        for (int k = 0; k < 3; k++) halo += 2.0 * (double)cfg.context[k] / (double)std::max(1, cfg.block_size[k]);
+        const double est = (double)P.block_count[P.owned[i]] * (1.0 + halo) + 64.0;
+        d.tcap = aa_pow2((uint64_t)std::max(4096.0, 2.0 * (double)C * est * mult));
         d.tbase = (uint32_t)tcur;
         tcur += d.tcap;
         BS_ARG(tcur < (1ull << 32), "bs_aff_agglom: hash tables exceed 32-bit indexing");

@@ -257,7 +257,8 @@ MWS_DEFAULTS = dict(aff_neighborhood=None, bias=None, global_bias=[1.0, -0.5], f
                     strides=None, randomized_strides=False, remove_debris=0, min_seed_distance=None, noise_seed=0)
 
 
-def segment_mws_blockwise(affs, params, block_size=None, context=None, mask=None, roi=None, block_index_offset=None):
+def segment_mws_blockwise(affs, params, block_size=None, context=None, mask=None, roi=None, block_index_offset=None,
+                          agglom_chunk_blocks=None, profile=False):
     """In-memory core of the blockwise mws pipeline (post/watershed_mutex.py:8-174: ExtractFrags -> AffAgglom -> GraphMWS ->
     Relabel, the four volara tasks) on a CUDA tensor (C, Z, Y, X) uint8 / float32.
       ExtractFrags: per block, mutex-watershed fragments of the read ROI from all C channels (bs_mws_agglom_blocks: every
@@ -287,6 +288,14 @@ def segment_mws_blockwise(affs, params, block_size=None, context=None, mask=None
     dev = affs.device
     affs = affs.contiguous()
     vol = tuple(affs.shape[1:])
+    import time as _time
+    stage_s = {}
+
+    def _tick(name, t0):
+        if profile:
+            torch.cuda.synchronize()
+            stage_s[name] = stage_s.get(name, 0.0) + _time.perf_counter() - t0
+        return _time.perf_counter()
     if block_size is None:
         block_size, context = vol, (0, 0, 0)
     elif context is None:
@@ -304,16 +313,20 @@ def segment_mws_blockwise(affs, params, block_size=None, context=None, mask=None
     counts = np.zeros(len(ids), np.int64)
     nodes_all, mws_counters = [], []
     for rs, members in sorted(groups.items()):
+        t0 = _tick("-", 0.0)
         fake, empty = _stack_read_rois(plan, affs, mask, members, rs, wo, ctx)
+        t0 = _tick("stack_read_rois", t0)
         seeds = [block_seed(p["noise_seed"], int(ids[bi])) for bi in members] if p["noise_eps"] else None
         labels, cnt = native.mws_agglom_blocks(fake, len(members), nbh, bias, strides=p["strides"], noise_eps=p["noise_eps"], block_seeds=seeds)
         del fake
+        t0 = _tick("extract_frags.mws", t0)
         for k in np.nonzero(empty)[0]:      # the reference returns before it writes anything for such a block
             labels[int(k) * rs[0]:(int(k) + 1) * rs[0]] = 0
         mws_counters.append(cnt)
         plan.set_owned(members)
         plan.fragments_from_labels(affs, labels, cnt["n_labels"], frags, mask=mask)
         del labels
+        t0 = _tick("extract_frags.back_half", t0)
         c = plan.block_counts()
         counts[members] = c[members]
         if plan.num_nodes():
@@ -327,13 +340,31 @@ def segment_mws_blockwise(affs, params, block_size=None, context=None, mask=None
     else:
         nodes = (torch.zeros(0, dtype=torch.int64, device=dev), torch.zeros((0, 3), dtype=torch.int32, device=dev),
                  torch.zeros(0, dtype=torch.int32, device=dev))
-    plan.aff_agglom(affs, frags, nbh)
-    eu, ev, es = plan.edges(dev)
+    t0 = _tick("-", 0.0)
+    # AffAgglom in chunks of blocks (bounded hash-table memory); every edge is written by exactly one block
+    read_vox = max(int(np.prod([int(ws[i][d]) + 2 * ctx[d] for d in range(3)])) for i in range(len(ids)))
+    per_chunk = int(agglom_chunk_blocks) if agglom_chunk_blocks else max(1, (1 << 27) // max(read_vox, 1))
+    parts = []
+    for c0 in range(0, len(ids), per_chunk):
+        plan.set_owned(np.arange(c0, min(c0 + per_chunk, len(ids))))
+        plan.aff_agglom(affs, frags, nbh)
+        parts.append(plan.edges(dev))
+    plan.set_owned(np.arange(len(ids)))
+    eu, ev, es = (torch.cat([p_[k] for p_ in parts]) for k in range(3))
+    if len(parts) > 1 and eu.numel():
+        nid0 = nodes[0]
+        key = torch.searchsorted(nid0, eu) * nid0.numel() + torch.searchsorted(nid0, ev)      # (u, v) order of the dense numbers
+        order = torch.argsort(key)
+        eu, ev, es = eu[order].contiguous(), ev[order].contiguous(), es[order].contiguous()
+    t0 = _tick("aff_agglom", t0)
     weight, gbias = (float(v) for v in tuple(p["global_bias"]))
     clusters, gcnt = native.graph_mws(nodes[0], eu, ev, es, weight, gbias)
+    t0 = _tick("graph_mws", t0)
     seg = plan.relabel(frags, [clusters])[0] if nodes[0].numel() else torch.zeros_like(frags)
+    t0 = _tick("relabel", t0)
+    stage_s.pop("-", None)
     return dict(fragments=frags, nodes=nodes, edges=(eu, ev, es), lut=(nodes[0], clusters), seg=seg, plan=plan, params=p,
-                counters=dict(extract_frags=mws_counters, graph_mws=gcnt))
+                counters=dict(extract_frags=mws_counters, graph_mws=gcnt), stage_s=stage_s)
 
 
 def segment_blockwise(affs, params=None, block_size=None, context=None, roi=None, mask=None, plan=None,
