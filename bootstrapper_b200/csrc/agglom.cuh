@@ -1,4 +1,4 @@
-// Shared declarations of the waterz agglomeration kernels (stage2.cu, agglom_smem.cu, agglom_pq.cu).
+// Shared declarations of the waterz agglomeration kernels (stage2.cu, agglom_par.cu, agglom_pq.cu).
 // Internal header.
 #pragma once
 #include "geom.h"
@@ -39,15 +39,6 @@ __device__ __forceinline__ int score_bin(float score, int nbins) {
     int i = (int)__fmul_rn(score, (float)nbins);
     return min(max(0, i), nbins - 1);
 }
-
-// agglom_smem.cu: BinQueue<256> agglomeration with the whole block state in shared memory.
-// `list` (device) = indices into blks of the blocks to process; u8 selects the affinity sum scaling.
-size_t agglom_smem_bytes(uint32_t Ecap, uint32_t Ncap, bool sum64);
-size_t agglom_work_bytes(uint32_t Ecap, uint32_t Ncap, bool sum64, int idx);
-int agglom_global_launch(const AggBlk *blks, const int *list, int nlist, const AggArrays &A, float threshold, int keep_cheaper,
-                         bool u8, unsigned char *work, const unsigned long long *woff, cudaStream_t s);
-int agglom_smem_launch(const AggBlk *blks, const int *list, int nlist, const AggArrays &A, float threshold, int keep_cheaper,
-                       bool u8, bool sum64, uint32_t Ecap, uint32_t Ncap, cudaStream_t s);
 
 // agglom_par.cu: the same agglomeration by a CTA of several warps that commits independent merges of a batch together
 size_t agglom_par_bytes(uint32_t Ecap, uint32_t Ncap, bool sum64, int idx);

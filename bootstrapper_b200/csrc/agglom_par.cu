@@ -1,6 +1,6 @@
 // waterz BinQueue<256> agglomeration of one daisy block by a CTA of PNW warps that commits several merges per round.
 //
-// Same result as the single-warp kernel (agglom_smem.cu), to the bit: the pop order of the FIFO bin queue is
+// Same result as a single warp popping one entry at a time (the kernel of round 1, since removed), to the bit: the pop order of the FIFO bin queue is
 // emulated exactly, but a whole batch of queue entries is resolved per round and the merges found in it run
 // concurrently, one warp each.  A prefix of the batch may commit together when processing it entry by entry would
 // give the same state:

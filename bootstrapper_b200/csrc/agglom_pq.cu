@@ -6,7 +6,7 @@
 // and pushed back, deleted ones skipped, everything else merged.  The pop order is a closed
 // total order, so the queue is emulated by a 32-ary min-heap of 64-bit keys (sortable score bits << 32 | edge):
 // one warp owns the graph, a pop sifts down with one coalesced load of 32 children per level, a push climbs
-// log32(E) levels.  The merge itself is the list-splicing / node-mark scheme of agglom_smem.cu on 32-bit indices.
+// log32(E) levels.  The merge itself splices incidence lists and marks common neighbours by a generation stamp, on 32-bit indices.
 // Thresholds are processed in ascending order; after each one the root of every node is written out, which is
 // the segmentation waterz yields at that threshold.
 //

@@ -11,7 +11,7 @@
 
 namespace bs {
 int g_debug = 0;
-int g_agglom_version = 0;  // 0 = auto (shared-memory kernel when the block fits), 1 = force the global-memory kernel
+int g_agglom_version = 0;  // 0 = auto (shared-memory kernel when the block fits), 3 / 4 = force the global-slab kernels
 int g_front_version = 0;   // stage-1 front end: 0 = auto (fused when eligible), 1 = unfused chain, 2 = fused without TMA, 3 = fused, TMA required
 int g_flood_version = 0;   // 0 = auto (v2 when eligible), 1 = force the global-memory flood
 int stage1_run(Plan &P, const void *affs, const uint8_t *mask, uint64_t *frags_out, cudaStream_t s, const uint32_t *ext_labels = nullptr,
@@ -88,6 +88,7 @@ int bs_set_front_version(int v) {
 }
 
 int bs_set_agglom_version(int v) {
+    BS_ARG(v == 0 || v == 3 || v == 4, "bs_set_agglom_version: 0 (automatic), 3 or 4 (the single-warp kernels 1 / 2 were removed)");
     g_agglom_version = v;
     return BS_OK;
 }

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libbsnative.so")
-SOURCES = ["prims.cu", "plan.cu", "stage1.cu", "stage2.cu", "agglom_smem.cu", "agglom_par.cu", "agglom_pq.cu", "stage3.cu", "cc.cu", "mws.cu", "affagglom.cu", "gauss.cu", "afferr.cu", "labelstats.cu", "synth.cu", "api.cu"]
+SOURCES = ["prims.cu", "plan.cu", "stage1.cu", "stage2.cu", "agglom_par.cu", "agglom_pq.cu", "stage3.cu", "cc.cu", "mws.cu", "affagglom.cu", "gauss.cu", "afferr.cu", "labelstats.cu", "synth.cu", "api.cu"]
 HEADERS = ["common.cuh", "geom.h", "agglom.cuh", "front2d.cuh", os.path.join("..", "..", "include", "bsnative.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

@@ -19,7 +19,7 @@ static constexpr uint64_t EMPTY64 = 0xFFFFFFFFFFFFFFFFull;
 static constexpr uint64_t TOMB64 = 0xFFFFFFFFFFFFFFFEull;
 static constexpr unsigned FULL = 0xFFFFFFFFu;
 extern int g_debug;
-extern int g_agglom_version;   // 0 = shared-memory kernel when the block fits, 1 = force the global-memory kernel
+extern int g_agglom_version;   // 0 = shared-memory kernel when the block fits, 3 / 4 = force the global-slab kernels
 
 struct S2Blk {
     long long block_id;
@@ -595,7 +595,7 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
         return BS_OK;
     }
 
-    // ---- which blocks fit the shared-memory kernel (agglom_smem.cu)
+    // ---- which blocks fit the shared-memory kernel
     std::vector<AggBlk> ab(nown);
     std::vector<int> l_smem, l_glob;
     uint32_t Emax = 8, Nmax = 8;
@@ -611,16 +611,14 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
         if (u8 && 765.0 * hb[i].rs[0] * hb[i].rs[1] * hb[i].rs[2] >= 4294967295.0) sum64 = true;
     }
     // g_agglom_version: 0 = parallel-merge kernels (shared memory when the block fits, else a global slab),
-    //                    1 = single-warp kernel on global slabs, 2 = single-warp kernel in shared memory when it fits,
-    //                    3 = parallel-merge kernel on global slabs
+    //                    3 = parallel-merge kernel on global slabs for every block,
     //                    4 = as 3 with every array in the slab (no shared-memory union-find / queue bins)
-    const bool par = g_agglom_version == 0 || g_agglom_version == 3 || g_agglom_version == 4;
     {
-        const size_t limit = 227 * 1024 - (par ? agglom_par_static_smem() : 0);
+        const size_t limit = 227 * 1024 - agglom_par_static_smem();
         for (int i = 0; i < nown; i++) {
             uint32_t Ec = (std::max<uint32_t>(ab[i].E, 8) + 7) & ~7u, Nc = (std::max<uint32_t>(ab[i].nv, 8) + 7) & ~7u;
-            auto bytes = [&](uint32_t e_, uint32_t n_) { return par ? agglom_par_bytes(e_, n_, sum64, 2) : agglom_smem_bytes(e_, n_, sum64); };
-            bool fits = (g_agglom_version == 0 || g_agglom_version == 2) && Ec <= 32760 && Nc <= 32760 && bytes(Ec, Nc) <= limit;
+            auto bytes = [&](uint32_t e_, uint32_t n_) { return agglom_par_bytes(e_, n_, sum64, 2); };
+            bool fits = g_agglom_version == 0 && Ec <= 32760 && Nc <= 32760 && bytes(Ec, Nc) <= limit;
             if (fits && bytes(std::max(Emax, Ec), std::max(Nmax, Nc)) <= limit) {
                 Emax = std::max(Emax, Ec);
                 Nmax = std::max(Nmax, Nc);
@@ -637,7 +635,7 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
         const AggBlk &a = ab[l_glob[k]];
         uint32_t Ec = (std::max<uint32_t>(a.E, 8) + 7) & ~7u, Nc = (std::max<uint32_t>(a.nv, 8) + 7) & ~7u;
         Nglob_max = std::max(Nglob_max, Nc);
-        h_woff[k + 1] = h_woff[k] + (par ? agglom_par_bytes(Ec, Nc, true, 4) : agglom_work_bytes(Ec, Nc, true, 4));
+        h_woff[k + 1] = h_woff[k] + agglom_par_bytes(Ec, Nc, true, 4);
     }
     const bool any_glob = !l_glob.empty();
 
@@ -673,20 +671,12 @@ static int stage2_impl(Plan &P, const void *affs, const uint64_t *frags, int tab
     A.counters = counters.as<uint32_t>();
     A.error = err.as<uint32_t>();
     BS_ARG(cfg.queue_bins == 256, "stage2: only the BinQueue<256> agglomeration of the blockwise path is implemented");
-    if (par) {
-        BS_TRY(agglom_par_launch(d_ab.as<AggBlk>(), d_list.as<int>(), (int)l_smem.size(), A, P.agg_threshold, cfg.keep_cheaper, u8, sum64, Emax,
-                                 Nmax, s));
-        if (any_glob)
-            BS_TRY(agglom_par_global_launch(d_ab.as<AggBlk>(), d_list.as<int>() + l_smem.size(), (int)l_glob.size(), A, P.agg_threshold,
-                                            cfg.keep_cheaper, u8, gwork.as<unsigned char>(), d_woff.as<unsigned long long>(),
-                                            Nglob_max, g_agglom_version != 4, s));
-    } else {
-        BS_TRY(agglom_smem_launch(d_ab.as<AggBlk>(), d_list.as<int>(), (int)l_smem.size(), A, P.agg_threshold, cfg.keep_cheaper, u8, sum64,
-                                  Emax, Nmax, s));
-        if (any_glob)
-            BS_TRY(agglom_global_launch(d_ab.as<AggBlk>(), d_list.as<int>() + l_smem.size(), (int)l_glob.size(), A, P.agg_threshold,
-                                        cfg.keep_cheaper, u8, gwork.as<unsigned char>(), d_woff.as<unsigned long long>(), s));
-    }
+    BS_TRY(agglom_par_launch(d_ab.as<AggBlk>(), d_list.as<int>(), (int)l_smem.size(), A, P.agg_threshold, cfg.keep_cheaper, u8, sum64, Emax,
+                             Nmax, s));
+    if (any_glob)
+        BS_TRY(agglom_par_global_launch(d_ab.as<AggBlk>(), d_list.as<int>() + l_smem.size(), (int)l_glob.size(), A, P.agg_threshold,
+                                        cfg.keep_cheaper, u8, gwork.as<unsigned char>(), d_woff.as<unsigned long long>(),
+                                        Nglob_max, g_agglom_version != 4, s));
 
     // ---- merge-tree scores, ownership, output (host sync: number of owned edges)
     g_prof.mark("s2.lca", s);

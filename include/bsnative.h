@@ -321,8 +321,8 @@ int bs_set_flood_version(int v);
  * 3 = fused, the TMA mask kernel required where the affinity rows are 16-byte aligned */
 int bs_set_front_version(int v);
 /* agglomeration kernel: 0 = automatic (parallel merges; shared memory when a block's graph fits, else a global slab),
- * 1 = single warp on global slabs, 2 = single warp in shared memory, 3 = parallel merges on global slabs (queue bins,
- * parents and stamps in shared memory), 4 = parallel merges with every array in the global slab */
+ * 3 = parallel merges on global slabs for every block (queue bins, parents and stamps in shared memory), 4 = parallel merges
+ * with every array in the global slab */
 int bs_set_agglom_version(int v);
 /* return the library's cached scratch memory (stream-ordered pool) to the driver */
 int bs_release_scratch(void);

@@ -7,7 +7,7 @@ from bootstrapper_b200.post.pipeline import make_plan
 shape = tuple(int(v) for v in sys.argv[1:4]) if len(sys.argv) > 3 else (50, 750, 750)
 affs = native.synth_affs(shape, seed=0)
 native.set_debug(True); native.set_profiling(True)
-if os.environ.get("BS_AGG_GLOBAL"): native.set_agglom_version(1)
+if os.environ.get("BS_AGG_GLOBAL"): native.set_agglom_version(3)
 blk = tuple(int(v) for v in sys.argv[4:7]) if len(sys.argv) > 6 else (25, 250, 250)
 plan, p = make_plan(affs, {}, blk, tuple(max(1, b // 8) for b in blk))
 frags = plan.fragments(affs)

@@ -384,7 +384,7 @@ def test_full_size_properties():
         assert bool((seg <= frags).all())
     # the kernel variants chosen by batch size (flood with the bitmap in shared / global memory, level tables in shared
     # memory; agglomeration sequential / parallel merges) are the same function at this size too
-    for fv, av in ((2, 2), (4, 0), (3, 3)):
+    for fv, av in ((2, 0), (4, 4), (3, 3)):
         try:
             native.set_flood_version(fv)
             native.set_agglom_version(av)
@@ -526,7 +526,7 @@ def test_agglomeration_kernels_agree():
     affs = synth_affs((20, 160, 160), seed=5)
     block, ctx = (10, 80, 80), (2, 10, 10)
     ref = _oracle(affs, {}, block, ctx)
-    for version in (1, 2, 3, 4):   # single warp / global slab, single warp / shared memory, parallel merges / global slab (hybrid, plain)
+    for version in (3, 4):   # parallel merges on global slabs: hybrid (shared-memory union-find / bins) and plain
         try:
             native.set_agglom_version(version)
             r = _run_gpu(affs, {}, block, ctx)
