@@ -71,6 +71,16 @@ def _worker(rank, world, port, shape, block, ctx, frags_ref, edges_ref, owner_ra
         U3, V3, S3 = sharded.allgather_edges(u, v, s, world, state=state)
         ok_grow = U3.tolist() == U.tolist() and V3.tolist() == V.tolist() and state["cap"] > int(caps.item())
         assert ok_again and ok_grow
+        # the form the GPU path ships: dense int32 node numbers, 12 bytes per edge, NaN scores intact
+        ids = sorted({e[0] for e in edges_ref} | {e[1] for e in edges_ref})
+        rank_of = {n: k + 1 for k, n in enumerate(ids)}
+        du = torch.tensor([rank_of[int(x)] for x in u.tolist()], dtype=torch.int32)
+        dv = torch.tensor([rank_of[int(x)] for x in v.tolist()], dtype=torch.int32)
+        D, E2, S4 = sharded.allgather_edges(du, dv, s, world, state={})
+        assert D.dtype == torch.int32 and S4.dtype == torch.float32
+        back = sorted(zip([ids[k - 1] for k in D.tolist()], [ids[k - 1] for k in E2.tolist()], [x if x == x else None for x in S4.tolist()]),
+                      key=lambda t: t[:2])
+        assert back == want
         counts = np.zeros(4, np.int64)
         counts[rank] = rank + 1
         tot = sharded.allgather_counts(counts, world, "cpu")
