@@ -458,6 +458,51 @@ def run_e2e_compact(job, res, steps):
     return dict(ms=ms, d2h=d2h, h2d=host_affs.numel(), expand_ms=expand_ms, threads=threads, n_nodes=n)
 
 
+def run_e2e_expanded(job, res, steps):
+    """host-buffer leg that delivers the SAME uint64 arrays in host memory as run_e2e, by the compact route: per step the
+    affinities go up, 4 bytes per voxel + tables come down, and a decoder thread (bs_expand_compact on this rank's share of the
+    host cores) rebuilds fragments + all segmentations in host memory while the device works on the next volume.  Host clock
+    from a synchronised start to the last decoded volume."""
+    import torch
+    from bootstrapper_b200.sharded import HostExpander
+    seg, affs = res["seg"], res["affs"]
+    host_affs = torch.empty(affs.shape, dtype=affs.dtype, pin_memory=True)
+    host_affs.copy_(affs)
+    T = len(THRESHOLDS)
+    cap = int(np.prod(seg.vol_shape)) // 256 + 4096
+    sets = [dict(dense=torch.empty(seg.own_shape, dtype=torch.int32, pin_memory=True), nodes=torch.empty(cap, dtype=torch.int64, pin_memory=True),
+                 luts=[torch.empty(cap, dtype=torch.int64, pin_memory=True) for _ in range(T)]) for _ in range(2)]
+    outs = [torch.zeros(seg.own_shape, dtype=torch.int64) for _ in range(1 + T)]
+    threads = max(1, (os.cpu_count() or 1) // job.world)
+    exp = HostExpander(threads)
+    e_steps = max(2, min(steps, 8))
+    info = None
+
+    def step(k):
+        exp.acquire()
+        i = seg.run_host_compact(host_affs, sets[k % 2], wait=False)
+        exp.submit(i["done"], sets[k % 2], i["n_nodes"], outs)
+        return i
+    for k in range(3):
+        info = step(k)
+    exp.flush()
+    seg.drain()
+    job.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(e_steps):
+        info = step(k + 1)
+    exp.flush()
+    seg.drain()
+    ms = job.max_over_ranks((time.perf_counter() - t0) * 1e3) / e_steps
+    job.barrier()
+    exp.close()
+    # the decoded arrays are the device results
+    ok = all(bool(torch.equal(o, d.cpu())) for o, d in zip(outs[1:], res["out"]))      # the timed run's device segmentations, same input
+    n = info["n_nodes"]
+    return dict(ms=ms, d2h=int(np.prod(seg.own_shape)) * 4 + n * 8 * (1 + T), h2d=host_affs.numel(), threads=threads, checked=ok)
+
+
 def multi_gpu_parity(job):
     """N > 1: a small volume through the sharded path on all ranks, then rank 0 runs the same volume alone (single-GPU
     path, bit-exact vs the oracle in the tests) and compares its own slab + the global graph.  Outside every timed region."""
@@ -503,9 +548,27 @@ def run_ours(args):
     e2e_c = None
     if args.config == 2 and not args.no_e2e:
         e2e_c = run_e2e_compact(job, res, args.steps)
+    e2e_x = None
+    if args.config == 2 and not args.no_e2e:
+        e2e_x = run_e2e_expanded(job, res, args.steps)
     line = None
     if job.rank == 0:
         line = report(args, job, res, e2e)
+        if e2e_x is not None:
+            V_total = float(np.prod(res["shape"]))
+            xline = {
+                "value": V_total / (e2e_x["ms"] * 1e-3), "unit": "voxels/s", "ms_per_step": e2e_x["ms"], "h2d_bytes_per_step": e2e_x["h2d"],
+                "d2h_bytes_per_step": e2e_x["d2h"], "host_decode_threads_per_rank": e2e_x["threads"], "decoded_equals_device_result": e2e_x["checked"],
+                "what": "the same uint64 fragments + segmentations in host memory as `e2e`, delivered by the compact route: 4 bytes per voxel "
+                        "+ tables cross the bus, a decoder thread (bs_expand_compact) rebuilds the arrays in host memory while the device works "
+                        "on the next volume; host clock from a synchronised start to the last decoded volume, decode INSIDE the timed region"}
+            # `e2e` = the faster of the two routes that end with the full uint64 arrays in host memory; the other one is kept beside it
+            if line["e2e"] is not None and xline["ms_per_step"] < line["e2e"]["ms_per_step"]:
+                line["e2e_streamed"] = line["e2e"]
+                line["e2e"] = dict(xline, mode="compact transfer + overlapped host decode (ShardedSegmenter.run_host_compact + HostExpander); "
+                                               "e2e_streamed is the plain download of the uint64 arrays")
+            else:
+                line["e2e_expanded"] = xline
         if pipelined is not None:
             line["pipelined"] = pipelined
         if e2e_c is not None:

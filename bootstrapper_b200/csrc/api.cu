@@ -308,6 +308,15 @@ int bs_stage3_dense_fragments(bs_plan *p, const uint64_t *frags, int64_t n_vox, 
     return dense_fragments(*p->p, frags, n_vox, dense_out, (cudaStream_t)stream);
 }
 
+#if defined(__x86_64__)
+#include <emmintrin.h>
+static inline void host_stream_store(uint64_t *p, uint64_t v) { _mm_stream_si64((long long *)p, (long long)v); }
+static inline void host_stream_fence() { _mm_sfence(); }
+#else
+static inline void host_stream_store(uint64_t *p, uint64_t v) { *p = v; }
+static inline void host_stream_fence() {}
+#endif
+
 // host side of the compact result form: dense ids + node-id table + LUT rows -> the uint64 arrays the reference writes
 int bs_expand_compact(const uint32_t *dense, int64_t n_vox, const uint64_t *node_ids, int64_t n_nodes, const uint64_t *const *luts,
                       int n_thresholds, uint64_t *frags_out, uint64_t *const *segs_out, int n_threads) {
@@ -322,15 +331,18 @@ int bs_expand_compact(const uint32_t *dense, int64_t n_vox, const uint64_t *node
         const int64_t a = (int64_t)k * chunk, b = std::min<int64_t>(n_vox, a + chunk);
         if (a >= b) break;
         pool.emplace_back([=, &bad]() {
+            // the outputs are written once and not read back here: streaming stores skip the read-for-ownership of every
+            // output line (the decoder is bound by host memory traffic)
             for (int64_t i = a; i < b; i++) {
                 const uint32_t d = dense[i];
                 if ((int64_t)d > n_nodes) {
                     bad.store(1);
                     continue;
                 }
-                if (frags_out) frags_out[i] = d ? node_ids[d - 1] : 0;
-                for (int t = 0; t < n_thresholds; t++) segs_out[t][i] = d ? luts[t][d - 1] : 0;
+                if (frags_out) host_stream_store(&frags_out[i], d ? node_ids[d - 1] : 0);
+                for (int t = 0; t < n_thresholds; t++) host_stream_store(&segs_out[t][i], d ? luts[t][d - 1] : 0);
             }
+            host_stream_fence();
         });
     }
     for (auto &th : pool) th.join();

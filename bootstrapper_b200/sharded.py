@@ -128,6 +128,56 @@ def allgather_edges(u, v, s, world, group=None, state=None):
         return U, V, S
 
 
+class HostExpander:
+    """Decoder thread of the expanded host path: the results cross the bus in the compact form (run_host_compact, 4 bytes per
+    voxel) and the uint64 fragments + segmentations the reference writes are rebuilt in HOST memory by bs_expand_compact while
+    the device works on the next volume.  Two compact buffer sets alternate: acquire() before a set is overwritten,
+    submit() after run_host_compact(wait=False) queued its copies, flush() before the arrays are read."""
+
+    def __init__(self, threads):
+        import queue
+        import threading
+        self.threads = int(threads)
+        self.q = queue.Queue()
+        self.free = threading.Semaphore(2)
+        self.error = None
+        self.thread = threading.Thread(target=self._work, daemon=True)
+        self.thread.start()
+
+    def _work(self):
+        while True:
+            item = self.q.get()
+            try:
+                if item is None:
+                    return
+                done, hs, n, outs = item
+                done.synchronize()
+                native.expand_compact(hs["dense"], hs["nodes"][:n], [l[:n] for l in hs["luts"]], outs[0], outs[1:], threads=self.threads)
+            except Exception as e:  # noqa: BLE001
+                self.error = e
+            finally:
+                if item is not None:
+                    self.free.release()
+                self.q.task_done()
+
+    def acquire(self):
+        self.free.acquire()
+        if self.error is not None:
+            raise native.BsError(f"host expander failed: {self.error!r}")
+
+    def submit(self, done, host_set, n_nodes, outs):
+        self.q.put((done, host_set, int(n_nodes), outs))
+
+    def flush(self):
+        self.q.join()
+        if self.error is not None:
+            raise native.BsError(f"host expander failed: {self.error!r}")
+
+    def close(self):
+        self.q.put(None)
+        self.thread.join()
+
+
 def global_node_ids(block_ids, counts, nvox_block, device):
     """fragment ids are 1..n per block + block_id * prod(block_size) (watershed_frags.py:224): the sorted
     global node list follows from the per-block counts alone (blocks ascending by id)."""
@@ -416,7 +466,7 @@ class ShardedSegmenter:
         self._inflight.append((done, (r, dense), affs, None))
         while len(self._inflight) > (0 if wait else 2):
             self._wait_done(self._inflight.pop(0)[0])
-        return dict(n_nodes=n)
+        return dict(n_nodes=n, done=done)
 
     def drain(self):
         """wait for the device->host copies of every volume queued by run_host(wait=False)"""

@@ -663,6 +663,39 @@ def test_run_host_compact_expands_to_the_blocking_result():
             assert torch.equal(a, b)
 
 
+def test_host_expander_pipeline_delivers_every_volume():
+    """the expanded host path: compact transfers of several volumes in flight (two buffer sets), a decoder thread rebuilding the
+    uint64 arrays in host memory while the device works on -- every decoded volume equals the blocking result"""
+    from bootstrapper_b200.sharded import HostExpander, ShardedSegmenter
+    from bootstrapper_b200.synth import synth_affs
+    shape, block, ctx = (12, 120, 120), (6, 60, 60), (1, 8, 8)
+    thrs = [0.2, 0.5]
+    seg = ShardedSegmenter(shape, block, ctx, {"thresholds": thrs}, device=torch.device("cuda"))
+    cap = 1 << 16
+    vols = [torch.from_numpy(synth_affs(shape, seed=s_)).pin_memory() for s_ in (1, 2, 3, 4, 5)]
+    want = []
+    for v in vols:
+        ho = [torch.empty(shape, dtype=torch.int64).pin_memory() for _ in range(3)]
+        seg.run_host(v, ho)
+        want.append([h.clone() for h in ho])
+    sets = [dict(dense=torch.empty(shape, dtype=torch.int32).pin_memory(), nodes=torch.empty(cap, dtype=torch.int64).pin_memory(),
+                 luts=[torch.empty(cap, dtype=torch.int64).pin_memory() for _ in thrs]) for _ in range(2)]
+    outs = [[torch.zeros(shape, dtype=torch.int64) for _ in range(3)] for _ in vols]
+    exp = HostExpander(threads=3)
+    try:
+        for k, v in enumerate(vols):
+            exp.acquire()
+            info = seg.run_host_compact(v, sets[k % 2], wait=False)
+            exp.submit(info["done"], sets[k % 2], info["n_nodes"], outs[k])
+        exp.flush()
+        seg.drain()
+    finally:
+        exp.close()
+    for got, ref in zip(outs, want):
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b)
+
+
 # ---------------------------------------------------------------- `bs refine` filters (SURVEY 8f N4)
 def test_refine_filters_match_oracle():
     """per-id table (sizes, z-extents) and the four filters of refine.py against the numpy restatement"""
