@@ -473,7 +473,8 @@ def run_e2e_expanded(job, res, steps):
     sets = [dict(dense=torch.empty(seg.own_shape, dtype=torch.int32, pin_memory=True), nodes=torch.empty(cap, dtype=torch.int64, pin_memory=True),
                  luts=[torch.empty(cap, dtype=torch.int64, pin_memory=True) for _ in range(T)]) for _ in range(2)]
     outs = [torch.zeros(seg.own_shape, dtype=torch.int64) for _ in range(1 + T)]
-    threads = max(1, (os.cpu_count() or 1) // job.world)
+    # one core of the rank's share stays with the thread that drives the device
+    threads = max(1, (os.cpu_count() or 1) // job.world - 1)
     exp = HostExpander(threads)
     e_steps = max(2, min(steps, 8))
     info = None
