@@ -3,6 +3,7 @@
 TAG=${1:-final}
 set -x
 timeout 1100 python -m pytest tests -q -m gpu --timeout 300 > gpurun_out/${TAG}_pytest_gpu.log 2>&1; tail -3 gpurun_out/${TAG}_pytest_gpu.log
+timeout 120 python -c 'import __graft_entry__ as g; g.smoke(); print("smoke ok")' > gpurun_out/${TAG}_smoke.log 2>&1; tail -1 gpurun_out/${TAG}_smoke.log
 timeout 300 python bench.py > gpurun_out/${TAG}_bench_config2_n1.json 2> gpurun_out/${TAG}_bench.err; tail -c 600 gpurun_out/${TAG}_bench_config2_n1.json
 timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference_arm.json 2>> gpurun_out/${TAG}_bench.err
 timeout 300 python bench.py --config 5 --steps 3 --warmup 2 --no-cpu > gpurun_out/${TAG}_bench_config5_one_rank.json 2>> gpurun_out/${TAG}_bench.err
