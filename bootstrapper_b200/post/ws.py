@@ -21,9 +21,22 @@ def watershed_from_affinities(affs, max_affinity_value=1.0, fragments_in_xy=Fals
     if t.dtype == torch.uint8:
         if max_affinity_value != 255:
             raise ValueError("uint8 affinities require max_affinity_value=255")
+    elif t.dtype == torch.float64:
+        # the kernels read uint8 / float32; the affinities enter post/ws.py only through the boundary mask (:64,77 / :100),
+        # so float64 input gets its mask from the reference's own float64 expression (elementwise IEEE arithmetic, evaluated
+        # on the device) and goes down as a uint8 stand-in with exactly that mask (255 where set: 510 > 255, 765 > 382)
+        if t.shape[0] < 2:
+            raise ValueError("need at least the y and x affinity channels")
+        t = t.cuda()
+        if fragments_in_xy:
+            mask = 0.5 * (t[-1] + t[-2]) > 0.5 * max_affinity_value
+        else:
+            acc = t[0]
+            for c in range(1, t.shape[0]):
+                acc = acc + t[c]                                  # np.mean(affs, axis=0): planes added in order, one division
+            mask = acc / float(t.shape[0]) > 0.5 * max_affinity_value
+        t = (mask.to(torch.uint8) * 255).unsqueeze(0).expand(3, -1, -1, -1)
     else:
-        if t.dtype == torch.float64:
-            raise NotImplementedError("float64 affinities: pass uint8 (raw) or float32")
         if max_affinity_value != 1.0:
             raise ValueError("float affinities require max_affinity_value=1.0")
     if t.shape[0] < 2:

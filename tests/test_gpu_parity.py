@@ -326,6 +326,15 @@ def test_watershed_from_affinities_plug():
         assert got.dtype == np.uint64 and n == len(np.unique(got)) - 1
         pairs = np.unique(np.stack([got.ravel().astype(np.int64), ref.ravel().astype(np.int64)], 1), axis=0)
         assert len(np.unique(pairs[:, 0])) == len(pairs) == len(np.unique(pairs[:, 1]))
+        # float64 affinities (what the reference's own callers hand to the plug): the mask comes from the reference's float64
+        # expression, values that sit exactly on / next to the 0.5 threshold included
+        a64 = affs.astype(np.float64) / 255
+        a64[1, :, ::7, ::5] = 0.5
+        a64[2, :, ::7, ::5] = np.nextafter(0.5, 1.0)
+        got64, n64 = watershed_from_affinities(a64, fragments_in_xy=xy, min_seed_distance=10)
+        ref64, _ = ref_ws(a64, fragments_in_xy=xy, min_seed_distance=10, seed_tie="index")
+        pairs = np.unique(np.stack([got64.ravel().astype(np.int64), ref64.ravel().astype(np.int64)], 1), axis=0)
+        assert len(np.unique(pairs[:, 0])) == len(pairs) == len(np.unique(pairs[:, 1])) and n64 == len(np.unique(got64)) - 1
 
 
 def test_connected_components_and_relabel_kernels():
