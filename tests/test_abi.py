@@ -87,3 +87,30 @@ def test_gaussian_weights_match_scipy():
         assert r == int(4.0 * float(sigma) + 0.5)
         assert np.array_equal(w, _filters._gaussian_kernel1d(float(sigma), 0, r)[::-1])
     assert gaussian_weights(0)[0] == -1
+
+
+def test_host_decoder_of_the_compact_form(built_lib):
+    """bs_expand_compact is host code (no GPU): dense numbers + node-id table + LUT rows -> the uint64 arrays, background
+    stays 0, any thread count gives the same arrays, a dense id beyond the table is refused"""
+    import numpy as np
+    import pytest
+    import torch
+    from bootstrapper_b200 import native
+    rng = np.random.default_rng(3)
+    n = 1000
+    nodes = np.sort(rng.choice(10 ** 12, n, replace=False)).astype(np.int64) + 1
+    luts = [nodes[rng.integers(0, n, n)] for _ in range(3)]
+    dense = rng.integers(0, n + 1, (7, 33, 41)).astype(np.int32)
+    want_f = np.where(dense > 0, nodes[np.maximum(dense, 1) - 1], 0)
+    td, tn, tl = torch.from_numpy(dense), torch.from_numpy(nodes), [torch.from_numpy(l) for l in luts]
+    for threads in (1, 5, 64):
+        f, segs = native.expand_compact(td, tn, tl, threads=threads)
+        assert np.array_equal(f.numpy(), want_f)
+        for s_, l in zip(segs, luts):
+            assert np.array_equal(s_.numpy(), np.where(dense > 0, l[np.maximum(dense, 1) - 1], 0))
+    f0, s0 = native.expand_compact(td, tn, [], threads=2)          # fragments only
+    assert np.array_equal(f0.numpy(), want_f) and s0 == []
+    bad = td.clone()
+    bad[0, 0, 0] = n + 1
+    with pytest.raises(native.BsError):
+        native.expand_compact(bad, tn, tl, threads=2)
