@@ -492,3 +492,89 @@ def test_histogram_quantile_scores_against_brute_force():
             pivot = q * len(bins) // 100 + 1
             want = np.float32(1.0 - (bins[pivot - 1] + 0.5) / 256)
             assert s_ == want, (a, b, s_, want)
+
+
+def test_mws_oracle_against_an_independent_brute_force():
+    """the C++ restatement of mwatershed.agglom against a second, deliberately naive implementation (explicit edge list, python
+    sort with the declared key, clusters as sets, mutexes as a set of frozenset pairs rebuilt on every union): random
+    volumes, offsets (incl. positive and diagonal ones), strides, ties from quantised weights, NaNs"""
+    from oracle import native as on
+    rng = np.random.default_rng(12)
+    for trial in range(12):
+        shape = tuple(int(v) for v in rng.integers(2, 6, 3))
+        C_ = int(rng.integers(1, 5))
+        offsets = []
+        while len(offsets) < C_:
+            o = [int(v) for v in rng.integers(-2, 3, 3)]
+            if any(o) and o not in offsets:
+                offsets.append(o)
+        strides = [[int(v) for v in rng.integers(1, 3, 3)] for _ in range(C_)] if trial % 2 else None
+        w = rng.normal(0, 1, (C_,) + shape)
+        if trial % 3 == 0:
+            w = np.round(w * 2) / 2                      # many equal |w|, exact zeros
+        if trial % 4 == 0:
+            w[rng.random(w.shape) < 0.05] = np.nan
+        # --- brute force
+        V = int(np.prod(shape))
+        idx = np.arange(V).reshape(shape)
+        edges = []
+        for c, off in enumerate(offsets):
+            for p in np.ndindex(*shape):
+                q = tuple(a + b for a, b in zip(p, off))
+                if any(v < 0 or v >= n for v, n in zip(q, shape)):
+                    continue
+                if strides is not None and any(a % s for a, s in zip(p, strides[c])):
+                    continue
+                x = w[(c,) + p]
+                if x != x:
+                    continue
+                edges.append((-abs(x), c, int(idx[p]), int(idx[q]), bool(x > 0)))
+        edges.sort(key=lambda e: e[:3])
+        cluster = {i: {i} for i in range(V)}
+        of = list(range(V))
+        mutex = set()
+        for _, _, a, b, attractive in edges:
+            ca, cb = of[a], of[b]
+            if ca == cb:
+                continue
+            if attractive:
+                if frozenset((ca, cb)) in mutex:
+                    continue
+                keep, gone = min(ca, cb), max(ca, cb)
+                for v in cluster[gone]:
+                    of[v] = keep
+                cluster[keep] |= cluster.pop(gone)
+                mutex = {frozenset(keep if x == gone else x for x in m) for m in mutex}
+            else:
+                mutex.add(frozenset((ca, cb)))
+        want = np.array([min(cluster[of[i]]) + 1 for i in range(V)], dtype=np.uint64).reshape(shape)
+        got = on.mws_agglom(w, offsets, strides)
+        assert np.array_equal(got, want), (trial, shape, offsets, strides)
+
+
+def test_graph_mws_cluster_against_naive_sets():
+    """oracle.mws.mws_cluster (union-find + per-root mutex sets, smaller set moved) against clusters-as-sets with a global set
+    of mutex pairs, on random signed graphs"""
+    from oracle import mws as om
+    rng = np.random.default_rng(21)
+    for n, m in ((6, 12), (40, 160), (120, 300)):
+        edges = [(bool(rng.random() < 0.55), int(a), int(b)) for a, b in rng.integers(0, n, (m, 2)) if a != b]
+        of = list(range(n))
+        members = {i: {i} for i in range(n)}
+        mutex = set()
+        for attractive, a, b in edges:
+            ca, cb = of[a], of[b]
+            if ca == cb:
+                continue
+            if attractive:
+                if frozenset((ca, cb)) in mutex:
+                    continue
+                keep, gone = min(ca, cb), max(ca, cb)
+                for v in members[gone]:
+                    of[v] = keep
+                members[keep] |= members.pop(gone)
+                mutex = {frozenset(keep if x == gone else x for x in p) for p in mutex}
+            else:
+                mutex.add(frozenset((ca, cb)))
+        want = [min(members[of[i]]) for i in range(n)]
+        assert om.mws_cluster(n, edges).tolist() == want
