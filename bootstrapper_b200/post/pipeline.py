@@ -258,7 +258,7 @@ MWS_DEFAULTS = dict(aff_neighborhood=None, bias=None, global_bias=[1.0, -0.5], f
 
 
 def segment_mws_blockwise(affs, params, block_size=None, context=None, mask=None, roi=None, block_index_offset=None,
-                          agglom_chunk_blocks=None, profile=False):
+                          agglom_chunk_blocks=None, profile=False, mws_chunk_blocks=None):
     """In-memory core of the blockwise mws pipeline (post/watershed_mutex.py:8-174: ExtractFrags -> AffAgglom -> GraphMWS ->
     Relabel, the four volara tasks) on a CUDA tensor (C, Z, Y, X) uint8 / float32.
       ExtractFrags: per block, mutex-watershed fragments of the read ROI from all C channels (bs_mws_agglom_blocks: every
@@ -312,7 +312,16 @@ def segment_mws_blockwise(affs, params, block_size=None, context=None, mask=None
     frags = torch.zeros(plan.roi_shape, dtype=torch.int64, device=dev)
     counts = np.zeros(len(ids), np.int64)
     nodes_all, mws_counters = [], []
+    # one mutex watershed per call over as many stacked read ROIs as its 31-bit voxel / 32-bit edge indices hold
+    Cn = int(affs.shape[0])
+    limit_vox = min((1 << 31) - 1, ((1 << 32) - 2) // Cn)
+    work = []
     for rs, members in sorted(groups.items()):
+        per_call = max(1, limit_vox // int(np.prod(rs)))
+        if mws_chunk_blocks:
+            per_call = min(per_call, int(mws_chunk_blocks))
+        work += [(rs, members[c0:c0 + per_call]) for c0 in range(0, len(members), per_call)]
+    for rs, members in work:
         t0 = _tick("-", 0.0)
         fake, empty = _stack_read_rois(plan, affs, mask, members, rs, wo, ctx)
         t0 = _tick("stack_read_rois", t0)

@@ -154,7 +154,8 @@ def test_mws_blockwise_pipeline_matches_oracle(shape, block, ctx, params, dtype,
     seed = params.get("noise_seed", 0)
     ref = om.volara_pipeline(affs, params, shape if block is None else block, (0, 0, 0) if block is None else ctx, mask=mask, noise_seed=seed)
     r = segment_mws_blockwise(torch.from_numpy(affs).cuda(), params, block, ctx, mask=None if mask is None else torch.from_numpy(mask).cuda(),
-                              agglom_chunk_blocks=3 if shape == (13, 50, 45) else None)          # one case through the chunked AffAgglom
+                              agglom_chunk_blocks=3 if shape == (13, 50, 45) else None,          # one case through the chunked AffAgglom
+                              mws_chunk_blocks=2 if shape == (13, 50, 45) else None)             # ... and through several mws calls per shape group
     torch.cuda.synchronize()
     f = r["fragments"].cpu().numpy().view(np.uint64)
     assert np.array_equal(f, ref["fragments"]), "fragments differ"
