@@ -1,4 +1,8 @@
-import os, time, torch, torch.distributed as dist
+"""NCCL sanity numbers of a box: all-gather and ring send/recv of 64 MiB per rank (torchrun --nproc-per-node N tools/nccl_probe.py)"""
+import os
+
+import torch
+import torch.distributed as dist
 rank=int(os.environ["RANK"]); world=int(os.environ["WORLD_SIZE"]); torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
 x=torch.empty(64*1024*1024//4, dtype=torch.int32, device="cuda"); out=torch.empty(world*x.numel(), dtype=torch.int32, device="cuda")
