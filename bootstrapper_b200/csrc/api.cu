@@ -56,7 +56,7 @@ extern "C" {
 
 const char *bs_last_error(void) { return get_error(); }
 unsigned long long bs_launch_count(void) { return g_launches; }
-int bs_version(void) { return 101; }
+int bs_version(void) { return 102; }
 unsigned long long bs_config_size(void) { return sizeof(bs_ws_config); }
 int bs_set_debug(int on) {
     g_debug = on;
