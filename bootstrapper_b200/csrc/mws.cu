@@ -467,12 +467,17 @@ __global__ void __launch_bounds__(COOP_NT) k_mws_coop(MwsCoop a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ uint32_t s_w[COOP_NT / 32], s_w2[COOP_NT / 32];
     __shared__ uint32_t s_base, s_total;
-    volatile uint32_t *ctl = a.ctl;
-    for (uint32_t it = 0; it < a.max_rounds; it++) {
-        const uint32_t nwin = ctl[0], cursor = ctl[1], par = ctl[2], round = ctl[3] + 1;
-        if (nwin == 0 || ctl[6]) break;
+    // every thread keeps the round's bookkeeping itself (same inputs, same result): no barrier for it
+    uint32_t nwin = a.ctl[0], cursor = a.ctl[1], par = a.ctl[2], round = a.ctl[3], since = a.ctl[4], unions = a.ctl[5], stop = a.ctl[6];
+    volatile unsigned long long *cntv = a.cnt;
+    for (uint32_t it = 0; it < a.max_rounds && nwin != 0 && stop == 0; it++) {
+        round++;
         const uint32_t *win = a.win[par];
         uint32_t *wout = a.win[par ^ 1];
+        // per-round counters (merges, probes) rotate through three slots: the slot of the NEXT round is cleared now -- its last
+        // readers (the bookkeeping of round - 2) are two barriers behind, its next writers one round ahead
+        unsigned long long *rc = a.cnt + 16 + 4 * (round % 3);
+        if (gtid == 0) a.cnt[16 + 4 * ((round + 1) % 3)] = 0, a.cnt[16 + 4 * ((round + 1) % 3) + 1] = 0;
         // ---- A: roots, dead edges, bestA
         for (size_t j = gtid; j < nwin; j += gn) {
             const uint32_t i = win[j];
@@ -511,7 +516,8 @@ __global__ void __launch_bounds__(COOP_NT) k_mws_coop(MwsCoop a) {
             }
         }
         grid.sync();
-        // ---- C: attractive edges
+        // ---- C: attractive edges; did = 1 | non-free(u) << 1 | non-free(v) << 2 for an executed union (the flags as of now:
+        // the next phase must not read them while it also sets them)
         for (size_t j = gtid; j < nwin; j += gn) {
             if (!a.keep[j]) continue;
             const uint32_t i = win[j];
@@ -534,26 +540,30 @@ __global__ void __launch_bounds__(COOP_NT) k_mws_coop(MwsCoop a) {
                             break;
                         }
                     }
-                atomicAdd(&a.cnt[8], probes);
+                atomicAdd(&rc[1], probes);
             }
             if (blocked) {
                 atomicAdd(&a.cnt[4], 1ull);
             } else {
                 if (nf_u && nf_v) a.pairmark[ru] = round, a.pairmark[rv] = round;
-                a.did[j] = 1;
+                a.did[j] = (uint8_t)(1u | (nf_u ? 2u : 0u) | (nf_v ? 4u : 0u));
                 uf_union(a.parent, ru, rv);
                 atomicAdd(&a.cnt[2], 1ull);
-                atomicAdd(&a.cnt[5], 1ull);
+                atomicAdd(&rc[0], 1ull);
             }
         }
         grid.sync();
-        // ---- D: epoch-cluster lists of the new clusters
+        // ---- D: epoch-cluster lists and non-free flags of the new clusters, bestA reset, survivors per CTA chunk
         for (size_t j = gtid; j < nwin; j += gn) {
-            if (!a.did[j]) continue;
-            const uint32_t x = a.wroots[j].x, y = a.wroots[j].y;
-            const bool nfx = a.nonfree[x], nfy = a.nonfree[y];
+            const uint2 r = a.wroots[j];
+            if (r.x != NONE32) a.bestA[r.x] = NONE32, a.bestA[r.y] = NONE32;
+            const uint32_t d = a.did[j];
+            if (!d) continue;
+            const uint32_t x = r.x, y = r.y;
+            const bool nfx = (d & 2u) != 0, nfy = (d & 4u) != 0;
             if (!nfx && !nfy) continue;
             const uint32_t R = mws_find(a.parent, x);
+            a.nonfree[R] = 1;
             if (nfx && nfy) {
                 const uint32_t hx = a.ehead[x], tx = a.etail[x], hy = a.ehead[y], ty = a.etail[y];
                 a.enext[tx] = hy;
@@ -566,16 +576,6 @@ __global__ void __launch_bounds__(COOP_NT) k_mws_coop(MwsCoop a) {
                 a.ehead[R] = h;
                 a.etail[R] = t;
             }
-        }
-        grid.sync();
-        // ---- E: non-free flags, bestA reset, survivors per CTA chunk
-        for (size_t j = gtid; j < nwin; j += gn) {
-            const uint2 r = a.wroots[j];
-            if (a.did[j] && (a.nonfree[r.x] || a.nonfree[r.y])) a.nonfree[mws_find(a.parent, r.x)] = 1;
-        }
-        for (size_t j = gtid; j < nwin; j += gn) {
-            const uint2 r = a.wroots[j];
-            if (r.x != NONE32) a.bestA[r.x] = NONE32, a.bestA[r.y] = NONE32;
         }
         const uint32_t chunk = (nwin + gridDim.x - 1) / gridDim.x;
         const uint32_t lo = min(nwin, blockIdx.x * chunk), hi = min(nwin, lo + chunk);
@@ -592,12 +592,12 @@ __global__ void __launch_bounds__(COOP_NT) k_mws_coop(MwsCoop a) {
             }
         }
         grid.sync();
-        // ---- F: ordered compaction + refill
+        // ---- E: ordered compaction + refill
         {
             // gridDim.x <= COOP_NT: one block sum per thread, reduced by the block
             const uint32_t v = threadIdx.x < gridDim.x ? __ldcg(&a.blocksum[threadIdx.x]) : 0u;
             const uint32_t tb = __reduce_add_sync(FULL32, threadIdx.x < blockIdx.x ? v : 0u), tt = __reduce_add_sync(FULL32, v);
-            __syncthreads();                       // s_w of phase E is consumed
+            __syncthreads();                       // s_w of phase D is consumed
             if (lane == 0) s_w[warp] = tb, s_w2[warp] = tt;
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -629,25 +629,21 @@ __global__ void __launch_bounds__(COOP_NT) k_mws_coop(MwsCoop a) {
         const uint32_t nfill = min(a.wcap - nkeep, a.E - cursor);
         for (size_t j = gtid; j < nfill; j += gn) wout[nkeep + j] = cursor + (uint32_t)j;
         grid.sync();
-        // ---- G: bookkeeping by one thread
-        if (gtid == 0) {
-            const uint32_t nnew = nkeep + nfill;
-            ctl[0] = nnew;
-            ctl[1] = cursor + nfill;
-            ctl[2] = par ^ 1;
-            ctl[3] = round;
-            ctl[4] = ctl[4] + 1;
-            volatile unsigned long long *cnt = a.cnt;
-            if (cnt[5] > 0) ctl[5] = 1;
-            if (nkeep == nwin && nfill == 0)
-                ctl[6] = 2;
-            else if (nnew > 0 && ctl[5] && (ctl[4] >= a.epoch || cnt[8] > a.probe_budget))
-                ctl[6] = 1;
-            cnt[5] = 0;
-            cnt[8] = 0;
-            __threadfence();
-        }
-        grid.sync();
+        // ---- bookkeeping, by every thread for itself (the counters of this round are complete and stay until round + 2)
+        const unsigned long long merges = cntv[16 + 4 * (round % 3)], probes = cntv[16 + 4 * (round % 3) + 1];
+        const uint32_t nnew = nkeep + nfill;
+        since++;
+        if (merges > 0) unions = 1;
+        if (nkeep == nwin && nfill == 0)
+            stop = 2;
+        else if (nnew > 0 && unions && (since >= a.epoch || probes > a.probe_budget))
+            stop = 1;
+        cursor += nfill;
+        nwin = nnew;
+        par ^= 1;
+    }
+    if (gtid == 0) {
+        a.ctl[0] = nwin, a.ctl[1] = cursor, a.ctl[2] = par, a.ctl[3] = round, a.ctl[4] = since, a.ctl[5] = unions, a.ctl[6] = stop;
     }
 }
 
@@ -713,7 +709,7 @@ static int mws_rounds(const uint32_t *eu, const uint32_t *ev, unsigned long long
             if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&ok, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && ok &&
                 cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_mws_coop, COOP_NT, 0) == cudaSuccess && nb >= 1)
-                coop_grid = std::min(getenv("BS_MWS_COOP_GRID") ? atoi(getenv("BS_MWS_COOP_GRID")) : sms, std::min(sms * nb, COOP_NT));
+                coop_grid = std::min(getenv("BS_MWS_COOP_GRID") ? atoi(getenv("BS_MWS_COOP_GRID")) : 2 * sms, std::min(sms * nb, COOP_NT));
             else
                 cudaGetLastError();
         }
@@ -836,7 +832,7 @@ static int mws_run(const T *affs, const uint8_t *mask, MwsGeom &G, int zero_is_r
     DevBuf parent, keys, keys2, vals, vals2, eu, ev, counts;
     BS_TRY(parent.alloc(4 * V, s));
     BS_LAUNCH(k_mws_init, grid_for(V), 256, 0, s, parent.as<uint32_t>(), V);
-    BS_TRY(counts.alloc_zero(128, s));
+    BS_TRY(counts.alloc_zero(256, s));
     unsigned long long *d_cnt = counts.as<unsigned long long>();   // [0] repulsive edges [1] mutex list length [2] merges
                                                                    // [3] repulsive executed [4] blocked [5] merges this round [6] survivors
                                                                    // [8] mutex-set probes of this round
@@ -1040,7 +1036,7 @@ int graph_mws(const uint64_t *nodes, int64_t n, const uint64_t *u, const uint64_
     DevBuf parent, keys, keys2, vals, vals2, eu, ev, counts;
     BS_TRY(parent.alloc(4 * (size_t)n, s));
     BS_LAUNCH(k_mws_init, grid_for((size_t)n), 256, 0, s, parent.as<uint32_t>(), (size_t)n);
-    BS_TRY(counts.alloc_zero(128, s));
+    BS_TRY(counts.alloc_zero(256, s));
     unsigned long long *d_cnt = counts.as<unsigned long long>();
     unsigned long long h_cnt[16];
     memset(h_cnt, 0, sizeof(h_cnt));
