@@ -218,7 +218,7 @@ __device__ __forceinline__ uint64_t mws_hash(uint64_t k) {
 // returns true if the key was new
 __device__ __forceinline__ bool mws_set_insert(unsigned long long *tab, uint64_t mask, unsigned long long key) {
     uint64_t s = mws_hash(key) & mask;
-    for (;;) {
+    for (uint64_t n = 0; n <= mask; n++) {      // the table is kept at most half full; the bound only rules out spinning
         unsigned long long k = tab[s];
         if (k == key) return false;
         if (k == EMPTY64) {
@@ -228,15 +228,17 @@ __device__ __forceinline__ bool mws_set_insert(unsigned long long *tab, uint64_t
         }
         s = (s + 1) & mask;
     }
+    return false;
 }
 __device__ __forceinline__ bool mws_set_has(const unsigned long long *tab, uint64_t mask, unsigned long long key) {
     uint64_t s = mws_hash(key) & mask;
-    for (;;) {
+    for (uint64_t n = 0; n <= mask; n++) {
         const unsigned long long k = tab[s];
         if (k == key) return true;
         if (k == EMPTY64) return false;
         s = (s + 1) & mask;
     }
+    return false;
 }
 
 // phase B: repulsive edges with no pending higher-priority attractive edge at either cluster become mutexes
@@ -368,9 +370,9 @@ __global__ void k_mws_next_window(const uint32_t *__restrict__ win, const uint8_
     }
 }
 
-// rebuild, part 1: roots of all voxels (= their epoch roots until the next rebuild), written to a second array so that the
-// walks never see a half-updated forest; every cluster's epoch list collapses to the cluster itself
-__global__ void k_mws_flatten(const uint32_t *__restrict__ parent, uint32_t *__restrict__ out, uint32_t *__restrict__ ehead,
+// rebuild, part 1: roots of all voxels (= their epoch roots until the next rebuild), into `out` and -- path compression -- into
+// the forest itself; every cluster's epoch list collapses to the cluster itself
+__global__ void k_mws_flatten(uint32_t *parent, uint32_t *__restrict__ out, uint32_t *__restrict__ ehead,
                               uint32_t *__restrict__ etail, uint32_t *__restrict__ enext, size_t V) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (size_t)gridDim.x * blockDim.x) {
         uint32_t x = (uint32_t)i, p = parent[x];
@@ -379,6 +381,7 @@ __global__ void k_mws_flatten(const uint32_t *__restrict__ parent, uint32_t *__r
             p = parent[x];
         }
         out[i] = x;
+        parent[i] = x;              // in place as well: a walker that meets the new value continues from an ancestor
         if (x == (uint32_t)i) {     // lists hang off roots only
             ehead[i] = (uint32_t)i;
             etail[i] = (uint32_t)i;
@@ -457,7 +460,7 @@ struct MwsCoop {
     uint32_t *ctl;             // [0] nwin [1] cursor [2] window buffer in use [3] rounds so far [4] rounds since the rebuild
                                // [5] unions since the rebuild [6] stop: 1 = rebuild due, 2 = a round executed nothing
     uint32_t *blocksum;        // gridDim.x
-    uint32_t epoch, max_rounds;
+    uint32_t epoch, max_rounds, cap_rounds;
     unsigned long long probe_budget;
 };
 
@@ -636,7 +639,7 @@ __global__ void __launch_bounds__(COOP_NT) k_mws_coop(MwsCoop a) {
         if (merges > 0) unions = 1;
         if (nkeep == nwin && nfill == 0)
             stop = 2;
-        else if (nnew > 0 && unions && (since >= a.epoch || probes > a.probe_budget))
+        else if (nnew > 0 && ((unions && (since >= a.epoch || probes > a.probe_budget)) || since >= a.cap_rounds))
             stop = 1;
         cursor += nfill;
         nwin = nnew;
@@ -672,6 +675,22 @@ static int mws_rounds(const uint32_t *eu, const uint32_t *ev, unsigned long long
         uint64_t tcap = 1024;
         while (tcap < 2 * nrep + 16) tcap <<= 1;
         BS_TRY(tab.alloc_fill(8 * tcap, 0xFF, s));
+        // ... of which an epoch uses a prefix sized for the mutexes it starts with plus what its rounds can add (a window of
+        // repulsive edges per round): clearing and probing a table of the live size instead of the worst-case one
+        const uint64_t win_edges = std::min<unsigned long long>(E, g_mws_window);
+        auto table_for = [&](uint64_t live) {
+            uint64_t t = 1024;
+            while (t < 2 * (live + win_edges * (g_mws_epoch + 1)) + 16 && t < tcap) t <<= 1;
+            return std::min(t, tcap);
+        };
+        uint64_t teff = table_for(0);
+        // rounds an epoch may last before its inserts could fill half the table (reached only by epochs without unions)
+        // (the whole table holds every mutex the run can make: no limit then)
+        auto rounds_for = [&](uint64_t live) {
+            if (teff == tcap) return (uint32_t)(1u << 30);
+            return (uint32_t)std::min<uint64_t>((teff / 2 > live ? (teff / 2 - live) / win_edges : 1), 1u << 30);
+        };
+        uint32_t cap_rounds = std::max<uint32_t>(rounds_for(0), 1);
         BS_TRY(mlist.alloc(8 * (size_t)(nrep + 1), s));
         BS_TRY(mlist2.alloc(8 * (size_t)(nrep + 1), s));
         BS_TRY(bestA.alloc_fill(4 * V, 0xFF, s));
@@ -728,11 +747,12 @@ static int mws_rounds(const uint32_t *eu, const uint32_t *ev, unsigned long long
             A.pairmark = pairmark.as<uint32_t>(), A.nonfree = nonfree.as<uint8_t>();
             A.win[0] = win.as<uint32_t>(), A.win[1] = win2.as<uint32_t>();
             A.wroots = wroots.as<uint2>(), A.keep = keep.as<uint8_t>(), A.did = did.as<uint8_t>();
-            A.tab = tab.as<unsigned long long>(), A.tmask = tcap - 1;
+            A.tab = tab.as<unsigned long long>();
             A.cnt = d_cnt, A.ctl = ctl.as<uint32_t>(), A.blocksum = blocksum.as<uint32_t>();
             A.epoch = (uint32_t)g_mws_epoch, A.max_rounds = 1u << 14, A.probe_budget = g_mws_probe_budget;
             for (;;) {
                 A.mlist = mlist.as<uint2>();          // swapped by a rebuild
+                A.tmask = teff - 1, A.cap_rounds = cap_rounds;
                 void *args[] = {&A};
                 BS_CUDA(cudaLaunchCooperativeKernel((void *)k_mws_coop, dim3((unsigned)coop_grid), dim3(COOP_NT), args, 0, s));
                 g_launches++;
@@ -747,13 +767,14 @@ static int mws_rounds(const uint32_t *eu, const uint32_t *ev, unsigned long long
                     const auto r0 = std::chrono::steady_clock::now();
                     BS_LAUNCH(k_mws_flatten, grid_for(V), 256, 0, s, parent, root.as<uint32_t>(), ehead.as<uint32_t>(), etail.as<uint32_t>(),
                               enext.as<uint32_t>(), V);
-                    BS_CUDA(cudaMemcpyAsync(parent, root.p, 4 * V, cudaMemcpyDeviceToDevice, s));
                     const size_t nm = (size_t)h_cnt[1];
+                    teff = table_for(nm);
+                    cap_rounds = std::max<uint32_t>(rounds_for(nm), 1);
+                    BS_CUDA(cudaMemsetAsync(tab.p, 0xFF, 8 * teff, s));
                     if (nm) {
-                        BS_CUDA(cudaMemsetAsync(tab.p, 0xFF, 8 * tcap, s));
                         BS_CUDA(cudaMemsetAsync(d_cnt + 1, 0, 8, s));
                         BS_LAUNCH(k_mws_rekey, grid_for(nm), 256, 0, s, mlist.as<uint2>(), nm, root.as<uint32_t>(), tab.as<unsigned long long>(),
-                                  tcap - 1, mlist2.as<uint2>(), d_cnt + 1);
+                                  teff - 1, mlist2.as<uint2>(), d_cnt + 1);
                         mlist.swap(mlist2);
                     }
                     BS_CUDA(cudaMemsetAsync(ctl.as<uint32_t>() + 4, 0, 12, s));
@@ -773,11 +794,11 @@ static int mws_rounds(const uint32_t *eu, const uint32_t *ev, unsigned long long
             BS_LAUNCH(k_mws_best, grid_for(nwin), 256, 0, s, win.as<uint32_t>(), nwin, eu, ev, parent,
                       bestA.as<uint32_t>(), keep.as<uint8_t>(), did.as<uint8_t>(), wroots.as<uint2>());
             BS_LAUNCH(k_mws_repulsive, grid_for(nwin), 256, 0, s, win.as<uint32_t>(), nwin, eu, ev,
-                      wroots.as<uint2>(), bestA.as<uint32_t>(), root.as<uint32_t>(), keep.as<uint8_t>(), tab.as<unsigned long long>(), tcap - 1,
+                      wroots.as<uint2>(), bestA.as<uint32_t>(), root.as<uint32_t>(), keep.as<uint8_t>(), tab.as<unsigned long long>(), teff - 1,
                       mlist.as<uint2>(), d_cnt);
             BS_LAUNCH(k_mws_attractive, grid_for(nwin), 256, 0, s, win.as<uint32_t>(), nwin, eu, wroots.as<uint2>(),
                       parent, bestA.as<uint32_t>(), nonfree.as<uint8_t>(), ehead.as<uint32_t>(), enext.as<uint32_t>(),
-                      pairmark.as<uint32_t>(), (uint32_t)rounds, keep.as<uint8_t>(), did.as<uint8_t>(), tab.as<unsigned long long>(), tcap - 1,
+                      pairmark.as<uint32_t>(), (uint32_t)rounds, keep.as<uint8_t>(), did.as<uint8_t>(), tab.as<unsigned long long>(), teff - 1,
                       d_cnt);
             BS_LAUNCH(k_mws_post_lists, grid_for(nwin), 256, 0, s, wroots.as<uint2>(), did.as<uint8_t>(), nwin, parent,
                       nonfree.as<uint8_t>(), pairmark.as<uint32_t>(), (uint32_t)rounds, ehead.as<uint32_t>(), etail.as<uint32_t>(),
@@ -798,20 +819,22 @@ static int mws_rounds(const uint32_t *eu, const uint32_t *ev, unsigned long long
             cursor += nfill;
             nwin = (size_t)nkeep + nfill;
             if (h_cnt[5] > 0) unions_since_rebuild = true;
-            if (nwin > 0 && unions_since_rebuild && ((unsigned long long)since_rebuild >= g_mws_epoch || h_cnt[8] > g_mws_probe_budget)) {
+            if (nwin > 0 && ((unions_since_rebuild && ((unsigned long long)since_rebuild >= g_mws_epoch || h_cnt[8] > g_mws_probe_budget)) ||
+                             (uint32_t)since_rebuild >= cap_rounds)) {
                 // rebuild: roots of all voxels become the epoch roots, the lists collapse, the mutex set is re-keyed
                 rebuilds++;
                 since_rebuild = 0;
                 unions_since_rebuild = false;
                 BS_LAUNCH(k_mws_flatten, grid_for(V), 256, 0, s, parent, root.as<uint32_t>(), ehead.as<uint32_t>(),
                           etail.as<uint32_t>(), enext.as<uint32_t>(), V);
-                BS_CUDA(cudaMemcpyAsync(parent, root.p, 4 * V, cudaMemcpyDeviceToDevice, s));
                 const size_t nm = (size_t)h_cnt[1];
+                teff = table_for(nm);
+                cap_rounds = std::max<uint32_t>(rounds_for(nm), 1);
+                BS_CUDA(cudaMemsetAsync(tab.p, 0xFF, 8 * teff, s));
                 if (nm) {
-                    BS_CUDA(cudaMemsetAsync(tab.p, 0xFF, 8 * tcap, s));
                     BS_CUDA(cudaMemsetAsync(d_cnt + 1, 0, 8, s));
                     BS_LAUNCH(k_mws_rekey, grid_for(nm), 256, 0, s, mlist.as<uint2>(), nm, root.as<uint32_t>(), tab.as<unsigned long long>(),
-                              tcap - 1, mlist2.as<uint2>(), d_cnt + 1);
+                              teff - 1, mlist2.as<uint2>(), d_cnt + 1);
                     mlist.swap(mlist2);
                 }
             }
