@@ -578,3 +578,43 @@ def test_graph_mws_cluster_against_naive_sets():
                 mutex.add(frozenset((ca, cb)))
         want = [min(members[of[i]]) for i in range(n)]
         assert om.mws_cluster(n, edges).tolist() == want
+
+
+def test_aff_agglom_restatement_against_voxel_loops():
+    """oracle.mws.aff_agglom_in_block (slices + np.unique) against plain loops over (offset, voxel): the same pairs, integer
+    sums, counts and means, and only edges whose smaller node sits in the block's write ROI are written"""
+    from oracle import mws as om
+    import oracle.blockwise as ob
+    rng = np.random.default_rng(8)
+    shape = (6, 9, 8)
+    frags = rng.integers(0, 7, shape).astype(np.uint64)
+    frags = np.where(rng.random(shape) < 0.15, 0, frags).astype(np.uint64)
+    nbh = [[-1, 0, 0], [0, -1, 0], [0, 0, -1], [-2, 0, 0], [0, 3, 0], [0, -2, 2]]
+    for dtype in (np.uint8, np.float32):
+        affs = rng.integers(0, 256, (len(nbh),) + shape).astype(np.uint8)
+        if dtype == np.float32:
+            affs = (affs.astype(np.float32) / np.float32(255))
+        blk = ob.Block(index=(0, 0, 0), block_id=0, write_offset=(1, 2, 1), write_shape=(4, 5, 6), read_offset=(0, 0, 0), read_shape=shape)
+        rag = ob.Rag()
+        for f in range(1, 7):           # nodes 1..3 positioned inside the write ROI, 4..6 outside
+            rag.node_pos[f] = (2, 3, 2) if f <= 3 else (0, 0, 0)
+        om.aff_agglom_in_block(blk, affs, frags, rag, (0, 0, 0), nbh, None)
+        want = {}
+        for c, off in enumerate(nbh):
+            for p in np.ndindex(*shape):
+                q = tuple(a + b for a, b in zip(p, off))
+                if any(v < 0 or v >= n for v, n in zip(q, shape)):
+                    continue
+                f1, f2 = int(frags[p]), int(frags[q])
+                if f1 == 0 or f2 == 0 or f1 == f2:
+                    continue
+                x = affs[(c,) + p]
+                v = int(x) if dtype == np.uint8 else int(np.rint(np.ldexp(np.float64(x), 38)))
+                e = want.setdefault((min(f1, f2), max(f1, f2)), [0, 0])
+                e[0] += v
+                e[1] += 1
+        want = {k: v for k, v in want.items() if k[0] <= 3}
+        assert set(rag.edges) == set(want) and len(want) > 5
+        for k, (sm, cn) in want.items():
+            mean = np.float32(np.float64(sm) / 255.0 / cn) if dtype == np.uint8 else np.float32(np.ldexp(np.float64(sm), -38) / cn)
+            assert np.float32(rag.edges[k]) == mean
